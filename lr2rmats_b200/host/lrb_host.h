@@ -1,0 +1,108 @@
+// lrb_host.h -- host side of lr2rmats_b200 above the C ABI (include/lr2rmats_b200.h).
+//
+// What lives here is what the reference does around its per-alignment hot path:
+// decode alignments into structure-of-arrays batches (the reference uses htslib's
+// sam_read1; we decode SAM text / BAM ourselves straight into SoA, never building
+// bam1_t), read the annotation GTF and STAR SJ.out.tab with the reference's exact
+// quirks (gtf.c:431-521), and print GTF / BED / detail / summary byte-compatibly
+// (gtf.c:597-632, update_gtf.c:297-419,535-576).
+#ifndef LRB_HOST_H
+#define LRB_HOST_H
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "../../include/lr2rmats_b200.h"
+
+namespace lrb {
+
+// ---------------------------------------------------------------- alignments
+struct Header {
+    std::vector<std::string> names;
+    std::vector<uint32_t> lens;
+    std::string text;                              // SAM header text (for BAM re-emission)
+    std::unordered_map<std::string, int> index;
+    int name2id(const std::string &s) const { auto it = index.find(s); return it == index.end() ? -1 : it->second; }
+    void add(const std::string &n, uint32_t len) { if (!index.count(n)) index[n] = (int)names.size(); names.push_back(n); lens.push_back(len); }
+};
+
+struct Records {
+    std::vector<int32_t> tid, pos, l_qseq, nm;
+    std::vector<uint16_t> flag;
+    std::vector<int8_t> xs;
+    std::vector<uint64_t> qhash;
+    std::vector<uint32_t> cigar_off{0}, cigar;
+    std::vector<uint32_t> name_off{0};
+    std::vector<char> names;                       // NUL-terminated qnames
+    bool keep_raw = false;                         // keep BAM-encoded records for `filter` re-emission
+    std::vector<uint64_t> raw_off{0};
+    std::vector<uint8_t> raw;                      // block_size-prefixed BAM records
+    size_t n() const { return tid.size(); }
+    const char *qname(size_t i) const { return names.data() + name_off[i]; }
+    lrb_batch view() const;
+};
+
+uint64_t hash_name(const char *s, size_t n);
+
+// Reads SAM text or BAM (BGZF) -- autodetected like sam_open(..., "rb").  Returns false and sets err on failure.
+bool read_alignments(const std::string &path, Header &h, Records &r, std::string &err);
+// Writes a BAM (BGZF) stream with the header and the selected raw records (filter's stdout, bam_filter.c:127-159).
+bool write_bam(FILE *out, const Header &h, const Records &r, const uint32_t *idx, int64_t n, std::string &err);
+
+// ---------------------------------------------------------------- annotation
+struct Anno {                                       // read_anno_trans / read_gtf_trans result
+    std::vector<int32_t> tid, start, end, gene;
+    std::vector<uint8_t> is_rev;
+    std::vector<uint32_t> exon_off{0};
+    std::vector<int32_t> es, ee;
+    std::vector<std::string> gene_id, gene_name, trans_id, trans_name;
+    int gene_n = 0;                                 // T->gene_n (gtf.c:495 / :553)
+    size_t n() const { return tid.size(); }
+    lrb_anno view() const;
+    lrb_chains chains() const;
+};
+// gtf_mode=false: read_anno_trans (gtf.c:468); true: read_gtf_trans (gtf.c:524).  Fatal format errors -> false + err.
+bool read_gtf(const std::string &fn, const Header &h, Anno &a, bool gtf_mode, std::string &err);
+
+struct ChrNames {                                   // chr_name_t, gtf.c:336-412
+    std::vector<std::string> names;
+    int get_id(const std::string &s) { for (size_t i = 0; i < names.size(); ++i) if (names[i] == s) return (int)i; names.push_back(s); return (int)names.size() - 1; }
+    void seed(const Header &h) { for (auto &s : h.names) get_id(s); }
+};
+struct SjTable {
+    std::vector<int32_t> tid, don, acc, uniq, multi;
+    lrb_sj view() const;
+};
+bool read_sj(const std::string &fn, ChrNames &cn, SjTable &sj, std::string &err);   // read_sj_group, gtf.c:431
+
+// ------------------------------------------------------------------ emitters
+struct RowNames {                                   // where trans_id / trans_name of a read row come from
+    const Records *rec = nullptr;                   // BAM mode: qname of read_idx[row]
+    const Anno *chains = nullptr;                   // -m g mode: names from the input GTF
+};
+
+void emit_bam2gtf(FILE *out, const lrb_exon_result &ex, const Records &rec, const ChrNames &cn, const char *src);
+void emit_update_outputs(const lrb_update_result &res, const RowNames &rn, const Anno &anno, const Header &h, const ChrNames &cn,
+                         const char *src, int anno_gene_n, int anno_trans_n,
+                         FILE *updated, FILE *bam_gtf, FILE *detail, FILE *known, FILE *novel, FILE *unrecog, FILE *summary, FILE *bed);
+void emit_unique(FILE *out, const lrb_unique_result &res, const RowNames &rn, const ChrNames &cn, const char *src, bool intersect);
+
+// -------------------------------------------------------------------- engine
+// The CLI core is engine-agnostic so that the oracle tool (oracle/port_main.cpp) can drive the CPU restatement through
+// the very same readers and emitters.  The product binary binds this to the CUDA C ABI only (no CPU path exists there).
+struct Engine {
+    void *self = nullptr;
+    int (*set_tables)(void *, const lrb_anno *anno, const lrb_anno *rm, const lrb_sj *sj) = nullptr;
+    int (*filter)(void *, const lrb_batch *, const lrb_filter_params *, lrb_filter_result *) = nullptr;
+    int (*bam2gtf)(void *, const lrb_batch *, const lrb_exon_params *, lrb_exon_result *) = nullptr;
+    int (*update)(void *, const lrb_batch *, const lrb_chains *, const lrb_exon_params *, const lrb_update_params *, lrb_update_result *) = nullptr;
+    int (*unique)(void *, const lrb_batch *, const lrb_chains *, const lrb_exon_params *, const lrb_update_params *, lrb_unique_result *) = nullptr;
+    const char *(*error)(void *) = nullptr;
+};
+
+int cli_main(int argc, char **argv, Engine &eng);   // main.c:37-49 dispatch + the four subcommands
+
+}  // namespace lrb
+#endif

@@ -1,0 +1,202 @@
+"""ctypes binding of liblr2rmats_b200.so (the C ABI of include/lr2rmats_b200.h) for tests and bench.py.
+
+This is plumbing only: numpy arrays in, numpy arrays out, every bit of compute happens in the CUDA library.  There is no
+CPU path: `Context()` raises when the library is not built or no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import cabi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "liblr2rmats_b200.so")
+CLI_PATH = os.path.join(_HERE, "host", "lr2rmats-b200")
+
+ENTRY_POINTS = [
+    "lrb_ctx_create", "lrb_ctx_destroy", "lrb_last_error", "lrb_version", "lrb_anno_upload", "lrb_rm_upload", "lrb_sj_upload",
+    "lrb_batch_upload", "lrb_chains_upload", "lrb_filter_run", "lrb_exon_run", "lrb_pipeline_run", "lrb_update_run", "lrb_unique_run",
+    "lrb_sync", "lrb_filter_fetch", "lrb_exon_fetch", "lrb_update_fetch", "lrb_unique_fetch", "lrb_filter", "lrb_bam2gtf",
+    "lrb_update_gtf", "lrb_unique_gtf", "lrb_timing_enable", "lrb_timing_get", "lrb_launch_count", "lrb_shard_cuts",
+]
+
+T_NAMES = ["filter", "exon", "classify", "merge", "summary"]
+
+
+class LrbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"lr2rmats_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the CUDA library and declare prototypes.  Raises if it is not built (run __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} is missing: build it with `make -C lr2rmats_b200/csrc` (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    vp = C.c_void_p
+    L.lrb_ctx_create.argtypes = [C.c_int, P(vp)]
+    L.lrb_ctx_destroy.argtypes = [vp]; L.lrb_ctx_destroy.restype = None
+    L.lrb_last_error.argtypes = [vp]; L.lrb_last_error.restype = C.c_char_p
+    L.lrb_version.restype = C.c_char_p
+    L.lrb_anno_upload.argtypes = [vp, P(cabi.Anno)]
+    L.lrb_rm_upload.argtypes = [vp, P(cabi.Anno)]
+    L.lrb_sj_upload.argtypes = [vp, P(cabi.Sj)]
+    L.lrb_batch_upload.argtypes = [vp, P(cabi.Batch)]
+    L.lrb_chains_upload.argtypes = [vp, P(cabi.Chains)]
+    L.lrb_filter_run.argtypes = [vp, P(cabi.FilterParams)]
+    L.lrb_exon_run.argtypes = [vp, P(cabi.ExonParams), C.c_int]
+    L.lrb_pipeline_run.argtypes = [vp, P(cabi.FilterParams), P(cabi.ExonParams)]
+    L.lrb_update_run.argtypes = [vp, P(cabi.UpdateParams)]
+    L.lrb_unique_run.argtypes = [vp, P(cabi.UpdateParams)]
+    L.lrb_sync.argtypes = [vp]
+    L.lrb_filter_fetch.argtypes = [vp, P(cabi.FilterResult)]
+    L.lrb_exon_fetch.argtypes = [vp, P(cabi.ExonResult)]
+    L.lrb_update_fetch.argtypes = [vp, P(cabi.UpdateResult)]
+    L.lrb_unique_fetch.argtypes = [vp, P(cabi.UniqueResult)]
+    L.lrb_filter.argtypes = [vp, P(cabi.Batch), P(cabi.FilterParams), P(cabi.FilterResult)]
+    L.lrb_bam2gtf.argtypes = [vp, P(cabi.Batch), P(cabi.ExonParams), P(cabi.ExonResult)]
+    L.lrb_update_gtf.argtypes = [vp, P(cabi.Batch), P(cabi.ExonParams), P(cabi.UpdateParams), P(cabi.UpdateResult)]
+    L.lrb_unique_gtf.argtypes = [vp, P(cabi.Batch), P(cabi.ExonParams), P(cabi.UpdateParams), P(cabi.UniqueResult)]
+    L.lrb_timing_enable.argtypes = [vp, C.c_int]
+    L.lrb_timing_get.argtypes = [vp, P(C.c_float * 5), P(C.c_int64)]
+    L.lrb_launch_count.argtypes = [vp]; L.lrb_launch_count.restype = C.c_int64
+    L.lrb_shard_cuts.argtypes = [cabi.i32p, cabi.i32p, cabi.i32p, C.c_int64, C.c_int, P(C.c_int64)]
+    _lib = L
+    return L
+
+
+class Context:
+    """One lrb_ctx (one device, one stream).  Mirrors the C ABI one to one."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        rc = self.L.lrb_ctx_create(device, C.byref(self.h))
+        if rc != 0:
+            raise LrbError(rc, "lrb_ctx_create failed (no CUDA device? there is no CPU fallback)")
+        self._keep = {}
+
+    def close(self):
+        if self.h:
+            self.L.lrb_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise LrbError(rc, self.L.lrb_last_error(self.h).decode())
+
+    # ---- tables
+    def set_anno(self, soa: dict | None):
+        if soa is None:
+            self._ck(self.L.lrb_anno_upload(self.h, None)); return
+        a, k = cabi.make_anno(soa); self._keep["anno"] = k
+        self._ck(self.L.lrb_anno_upload(self.h, C.byref(a)))
+
+    def set_rm(self, soa: dict | None):
+        if soa is None:
+            self._ck(self.L.lrb_rm_upload(self.h, None)); return
+        a, k = cabi.make_anno(soa); self._keep["rm"] = k
+        self._ck(self.L.lrb_rm_upload(self.h, C.byref(a)))
+
+    def set_sj(self, soa: dict | None):
+        if soa is None or len(soa["tid"]) == 0:
+            self._ck(self.L.lrb_sj_upload(self.h, None)); return
+        s, k = cabi.make_sj(soa); self._keep["sj"] = k
+        self._ck(self.L.lrb_sj_upload(self.h, C.byref(s)))
+
+    # ---- device-resident stages
+    def upload(self, batch_soa: dict):
+        b, k = cabi.make_batch(batch_soa); self._keep["batch"] = (b, k)
+        self._ck(self.L.lrb_batch_upload(self.h, C.byref(b)))
+
+    def upload_struct(self, b):
+        self._ck(self.L.lrb_batch_upload(self.h, C.byref(b)))
+
+    def upload_chains(self, soa: dict):
+        c, k = cabi.make_chains(soa); self._keep["chains"] = k
+        self._ck(self.L.lrb_chains_upload(self.h, C.byref(c)))
+
+    def filter_run(self, p): self._ck(self.L.lrb_filter_run(self.h, C.byref(p)))
+    def exon_run(self, p, use_keep_list=False): self._ck(self.L.lrb_exon_run(self.h, C.byref(p), 1 if use_keep_list else 0))
+    def pipeline_run(self, fp, ep): self._ck(self.L.lrb_pipeline_run(self.h, C.byref(fp), C.byref(ep)))
+    def update_run(self, p): self._ck(self.L.lrb_update_run(self.h, C.byref(p)))
+    def unique_run(self, p): self._ck(self.L.lrb_unique_run(self.h, C.byref(p)))
+    def sync(self): self._ck(self.L.lrb_sync(self.h))
+
+    def filter_fetch(self) -> dict:
+        r = cabi.FilterResult(); self._ck(self.L.lrb_filter_fetch(self.h, C.byref(r))); return cabi.filter_to_np(r)
+
+    def exon_fetch(self) -> dict:
+        r = cabi.ExonResult(); self._ck(self.L.lrb_exon_fetch(self.h, C.byref(r))); return cabi.exon_to_np(r)
+
+    def update_fetch(self, raw=False):
+        r = cabi.UpdateResult(); self._ck(self.L.lrb_update_fetch(self.h, C.byref(r)))
+        return r if raw else cabi.update_to_np(r)
+
+    def unique_fetch(self) -> dict:
+        r = cabi.UniqueResult(); self._ck(self.L.lrb_unique_fetch(self.h, C.byref(r))); return cabi.unique_to_np(r)
+
+    # ---- one-call forms (host buffers in, host buffers out)
+    def filter(self, batch_soa, p) -> dict:
+        b, k = cabi.make_batch(batch_soa); r = cabi.FilterResult()
+        self._ck(self.L.lrb_filter(self.h, C.byref(b), C.byref(p), C.byref(r))); return cabi.filter_to_np(r)
+
+    def bam2gtf(self, batch_soa, p) -> dict:
+        b, k = cabi.make_batch(batch_soa); r = cabi.ExonResult()
+        self._ck(self.L.lrb_bam2gtf(self.h, C.byref(b), C.byref(p), C.byref(r))); return cabi.exon_to_np(r)
+
+    def update_gtf(self, batch_soa, ep, up) -> dict:
+        r = cabi.UpdateResult()
+        if batch_soa is None:
+            self._ck(self.L.lrb_update_gtf(self.h, None, C.byref(ep), C.byref(up), C.byref(r)))
+        else:
+            b, k = cabi.make_batch(batch_soa)
+            self._ck(self.L.lrb_update_gtf(self.h, C.byref(b), C.byref(ep), C.byref(up), C.byref(r)))
+        return cabi.update_to_np(r)
+
+    def unique_gtf(self, batch_soa, ep, up) -> dict:
+        r = cabi.UniqueResult()
+        if batch_soa is None:
+            self._ck(self.L.lrb_unique_gtf(self.h, None, C.byref(ep), C.byref(up), C.byref(r)))
+        else:
+            b, k = cabi.make_batch(batch_soa)
+            self._ck(self.L.lrb_unique_gtf(self.h, C.byref(b), C.byref(ep), C.byref(up), C.byref(r)))
+        return cabi.unique_to_np(r)
+
+    # ---- measurement
+    def timing(self, on=True): self._ck(self.L.lrb_timing_enable(self.h, 1 if on else 0))
+
+    def timing_get(self):
+        ms = (C.c_float * 5)(); n = C.c_int64()
+        self._ck(self.L.lrb_timing_get(self.h, C.byref(ms), C.byref(n)))
+        return dict(zip(T_NAMES, list(ms))), int(n.value)
+
+    def launch_count(self) -> int:
+        return int(self.L.lrb_launch_count(self.h))
+
+
+def shard_cuts(tid, start, end, n_shards: int) -> np.ndarray:
+    L = load_library()
+    tid = np.ascontiguousarray(tid, np.int32); start = np.ascontiguousarray(start, np.int32); end = np.ascontiguousarray(end, np.int32)
+    cuts = (C.c_int64 * (n_shards + 1))()
+    rc = L.lrb_shard_cuts(tid.ctypes.data_as(cabi.i32p), start.ctypes.data_as(cabi.i32p), end.ctypes.data_as(cabi.i32p), len(tid), n_shards, cuts)
+    if rc != 0:
+        raise LrbError(rc, "lrb_shard_cuts")
+    return np.array(list(cuts), np.int64)

@@ -1,0 +1,900 @@
+// lrb_capi.cu -- the C ABI of liblr2rmats_b200.so (include/lr2rmats_b200.h): context, HBM residency, stage
+// orchestration on one CUDA stream, pinned result buffers.  No compute happens on the host here beyond building the
+// small lookup indices of the replicated tables (prefix-max keys, the remove-GTF index) at upload time.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+#include "lrb_common.cuh"
+#include "lrb_kernels.cuh"
+#include "lrb_summary.cuh"
+
+namespace lrbk { extern int64_t g_launches_update, g_launches_summary; }
+using namespace lrbk;
+
+namespace {
+
+struct Buf {                                        // device buffer, grow-only, contents not preserved on growth
+    void *p = nullptr; size_t cap = 0;
+    bool ensure(size_t bytes)
+    {
+        if (bytes <= cap) return true;
+        if (p) cudaFree(p);
+        size_t nc = bytes + bytes / 4 + 256;
+        if (cudaMalloc(&p, nc) != cudaSuccess) { p = nullptr; cap = 0; cudaGetLastError(); return false; }
+        cap = nc; return true;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+struct PBuf {                                       // pinned host buffer
+    void *p = nullptr; size_t cap = 0;
+    bool ensure(size_t bytes)
+    {
+        if (bytes <= cap) return true;
+        if (p) cudaFreeHost(p);
+        size_t nc = bytes + bytes / 4 + 256;
+        if (cudaMallocHost(&p, nc) != cudaSuccess) { p = nullptr; cap = 0; cudaGetLastError(); return false; }
+        cap = nc; return true;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return (T *)p; }
+};
+
+struct MergeBufs {                                  // scratch + output of one merge fold
+    Buf keys, head, locus_start, locus_cnt, dropped;
+    Buf w_cand, w_cov, w_tid, w_start, w_end, w_fs, w_le;
+    Buf o_cand, o_cov, o_tid, o_start, o_end, o_fs, o_le;
+    int64_t n_out = 0, n_loci = 0;
+};
+
+}  // namespace
+
+struct lrb_ctx {
+    int device = 0; cudaStream_t st = nullptr; std::string err;
+    // tables
+    DAnno anno; DSj sj; DRmIndex rm;
+    Buf a_tid, a_start, a_end, a_gene, a_rev, a_off, a_es, a_ee, a_pmax;
+    Buf s_tid, s_don, s_acc, s_u, s_m, s_pmax, s_dkey;
+    Buf r_gtid, r_goff, r_start, r_pmax;
+    // batch
+    DBatch b; Buf b_tid, b_pos, b_lq, b_nm, b_flag, b_xs, b_qh, b_coff, b_cig;
+    bool have_batch = false;
+    // filter
+    Buf f_pass, f_score, f_intron, f_keep_row_mask, f_keep_rec_mask, f_keep_idx, f_keep_rows;
+    int64_t n_pass = 0, n_keep = 0; bool have_filter = false;
+    // rows + exons
+    DRows rows, rows2; DRows *cur = nullptr; DExons ex;
+    Buf r_read, r_tid, r_rs, r_re, r_rev, r_beg, r_n;
+    Buf q_read, q_tid, q_rs, q_re, q_rev, q_beg, q_n;
+    Buf e_s, e_e, e_f;
+    bool have_exons = false, rows_compact = false;
+    // update
+    Buf u_cls, u_ref, u_nnovel, u_noff, u_mk, u_mu, u_ck, u_cr, u_cu, u_cn, u_known, u_unrecog, u_sub;
+    DTransList novel; Buf n_row, n_lo, n_cnt, n_piece;
+    DTransList tmp_list; Buf t_row, t_lo, t_cnt, t_piece;
+    MergeBufs mg, mg2;
+    int64_t n_known = 0, n_unrecog = 0; bool have_update = false, have_unique = false;
+    int32_t summary[LRB_S_COUNT];
+    // summary
+    Buf h_khi, h_klo, h_min, h_score, y_barcnt, y_barseg, y_genebar, y_bedcnt, y_bedoff, y_counts, y_nelem;
+    Buf bd_tid, bd_s, bd_e, bd_sc, bd_ty, bd_rv; int64_t n_bed = 0;
+    // unique
+    Buf q_shared; int64_t n_shared = 0;
+    // look-back state, small device scalars and their pinned mirror
+    Buf tile_state, scalars; PBuf h_scalars;
+    // pinned result buffers
+    PBuf p[40];
+    // timing
+    bool timing = false; cudaEvent_t ev[LRB_T_COUNT + 1]; float ms[LRB_T_COUNT]; int64_t launches0 = 0, launches_last = 0;
+    lrb_update_params last_up;
+};
+
+namespace {
+
+int64_t total_launches() { return lrbk::count_launches() + lrbk::g_launches_update + lrbk::g_launches_summary; }
+
+int fail(lrb_ctx *c, int code, const std::string &msg) { c->err = msg; return code; }
+#define CK(call)                                                                                               \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(c, LRB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+#define NEED(buf, bytes) do { if (!(buf).ensure(bytes)) return fail(c, LRB_E_NOMEM, "device allocation failed: " #buf); } while (0)
+#define NEEDP(buf, bytes) do { if (!(buf).ensure(bytes)) return fail(c, LRB_E_NOMEM, "pinned allocation failed: " #buf); } while (0)
+
+// device scalars: [0..7] uint64 totals, then uint32 ticket, err flags, counts[8]
+uint64_t *d_totals(lrb_ctx *c) { return c->scalars.as<uint64_t>(); }
+uint32_t *d_ticket(lrb_ctx *c) { return (uint32_t *)(c->scalars.as<uint64_t>() + 8); }
+uint32_t *d_err(lrb_ctx *c) { return d_ticket(c) + 1; }
+
+int read_totals(lrb_ctx *c, uint64_t *out, int n)
+{
+    CK(cudaMemcpyAsync(c->h_scalars.p, d_totals(c), 8 * (size_t)n, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    memcpy(out, c->h_scalars.p, 8 * (size_t)n);
+    return LRB_OK;
+}
+
+int ensure_tiles(lrb_ctx *c, int64_t n_items)
+{
+    int64_t tiles = n_items / 8 + 1024;             // generous for every tiling used (>= n/256/8, n/reads_per_tile>=8)
+    NEED(c->tile_state, (size_t)tiles * 8);
+    return LRB_OK;
+}
+
+void tick(lrb_ctx *c, int k) { if (c->timing) cudaEventRecord(c->ev[k], c->st); }
+
+template <class T> int h2d(lrb_ctx *c, Buf &dst, const T *src, size_t n)
+{
+    NEED(dst, std::max<size_t>(n, 1) * sizeof(T));
+    if (n) CK(cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, c->st));
+    return LRB_OK;
+}
+template <class T> int d2h(lrb_ctx *c, PBuf &dst, const T *src, size_t n)
+{
+    NEEDP(dst, std::max<size_t>(n, 1) * sizeof(T));
+    if (n) CK(cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyDeviceToHost, c->st));
+    return LRB_OK;
+}
+
+int setup_rows(lrb_ctx *c, DRows &r, Buf &read, Buf &tid, Buf &rs, Buf &re, Buf &rev, Buf &beg, Buf &cnt, int64_t cap)
+{
+    size_t n = (size_t)std::max<int64_t>(cap, 1);
+    NEED(read, n * 4); NEED(tid, n * 4); NEED(rs, n * 4); NEED(re, n * 4); NEED(rev, n); NEED(beg, n * 4); NEED(cnt, n * 4);
+    r.cap = cap; r.read_idx = read.as<uint32_t>(); r.tid = tid.as<int32_t>(); r.start = rs.as<int32_t>(); r.end = re.as<int32_t>();
+    r.is_rev = rev.as<uint8_t>(); r.ex_beg = beg.as<uint32_t>(); r.ex_n = cnt.as<uint32_t>();
+    return LRB_OK;
+}
+int setup_exons(lrb_ctx *c, int64_t cap)
+{
+    size_t n = (size_t)std::max<int64_t>(cap, 1);
+    NEED(c->e_s, n * 4); NEED(c->e_e, n * 4); NEED(c->e_f, n);
+    c->ex.cap = (int64_t)std::min(c->e_s.cap / 4, std::min(c->e_e.cap / 4, c->e_f.cap));
+    c->ex.es = c->e_s.as<int32_t>(); c->ex.ee = c->e_e.as<int32_t>(); c->ex.flag = c->e_f.as<uint8_t>();
+    return LRB_OK;
+}
+
+// the scan stage in one of its three modes; on return rows.n / ex.n are known on the host
+int run_scan(lrb_ctx *c, int mode, const lrb_filter_params *fp, const lrb_exon_params *ep, const uint8_t *sel_mask)
+{
+    const int64_t n = c->b.n;
+    int rc;
+    if ((rc = ensure_tiles(c, n)) != LRB_OK) return rc;
+    if ((rc = setup_rows(c, c->rows, c->r_read, c->r_tid, c->r_rs, c->r_re, c->r_rev, c->r_beg, c->r_n, n)) != LRB_OK) return rc;
+    if (mode != 1) { NEED(c->f_pass, (size_t)n + 1); NEED(c->f_score, (size_t)n * 4 + 4); NEED(c->f_intron, (size_t)n * 4 + 4); }
+    if (n == 0) { c->rows.n = 0; c->ex.n = 0; if (mode != 0 && (rc = setup_exons(c, 16)) != LRB_OK) return rc; return LRB_OK; }
+    const double avg = (double)c->b.n_cigar / (double)n;
+    const bool warp_mode = avg > 48.0;
+    int R = 256;
+    if (warp_mode) { R = (int)(4096.0 / avg); R = std::max(8, std::min(256, R)); }
+    int stage_words = (int)(R * avg * 1.6) + 512; stage_words = (stage_words + 255) & ~255; stage_words = std::max(2048, std::min(12288, stage_words));
+    const int n_tiles = (int)((n + R - 1) / R);
+    if (mode != 0) {
+        int64_t bound = c->b.n_cigar + n + 16, est = c->b.n_cigar / 2 + n + 4096;
+        if ((rc = setup_exons(c, std::min(bound, std::max(est, c->ex.cap)))) != LRB_OK) return rc;
+    }
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        ScanArgs a{};
+        a.b = c->b; if (fp) a.fp = *fp; if (ep) a.ep = *ep; a.rm = c->rm; a.mode = mode; a.sel_mask = sel_mask;
+        a.pass = c->f_pass.as<uint8_t>(); a.score = c->f_score.as<int32_t>(); a.intron_n = c->f_intron.as<int32_t>();
+        a.rows = c->rows; a.ex = c->ex; a.tile_state = c->tile_state.as<uint64_t>(); a.ticket = d_ticket(c); a.totals = d_totals(c);
+        a.reads_per_tile = R; a.stage_words = stage_words;
+        CK(cudaMemsetAsync(c->tile_state.p, 0, (size_t)n_tiles * 8, c->st));
+        CK(cudaMemsetAsync(c->scalars.p, 0, 8 * 8 + 4, c->st));
+        size_t smem = (size_t)stage_words * 4 + (size_t)3072 * 8;
+        launch_cigar_scan(a, n_tiles, warp_mode, smem, c->st);
+        CK(cudaGetLastError());
+        uint64_t t[2];
+        if ((rc = read_totals(c, t, 2)) != LRB_OK) return rc;
+        c->rows.n = (int64_t)t[0]; c->ex.n = (int64_t)t[1];
+        if (mode == 0 || c->ex.n <= c->ex.cap) break;
+        if (attempt == 1) return fail(c, LRB_E_NOMEM, "exon pool still too small after regrow");
+        if ((rc = setup_exons(c, c->ex.n + 16)) != LRB_OK) return rc;          // exact size known now: walk again
+    }
+    return LRB_OK;
+}
+
+int run_select(lrb_ctx *c, const lrb_filter_params *fp)
+{
+    const int64_t n = c->b.n, np = c->rows.n;
+    NEED(c->f_keep_row_mask, (size_t)std::max<int64_t>(np, 1)); NEED(c->f_keep_rec_mask, (size_t)std::max<int64_t>(n, 1));
+    NEED(c->f_keep_idx, (size_t)std::max<int64_t>(np, 1) * 4); NEED(c->f_keep_rows, (size_t)std::max<int64_t>(np, 1) * 4);
+    CK(cudaMemsetAsync(c->f_keep_row_mask.p, 0, (size_t)std::max<int64_t>(np, 1), c->st));
+    CK(cudaMemsetAsync(c->f_keep_rec_mask.p, 0, (size_t)std::max<int64_t>(n, 1), c->st));
+    launch_select_runs(c->b, c->rows.read_idx, np, c->f_score.as<int32_t>(), c->f_intron.as<int32_t>(), *fp,
+                       c->f_keep_row_mask.as<uint8_t>(), c->f_keep_rec_mask.as<uint8_t>(), c->st);
+    launch_compact_mask(c->f_keep_row_mask.as<uint8_t>(), np, c->rows.read_idx, c->f_keep_idx.as<uint32_t>(), c->f_keep_rows.as<uint32_t>(),
+                        c->tile_state.as<uint64_t>(), d_ticket(c), d_totals(c), c->st);
+    CK(cudaGetLastError());
+    uint64_t t; int rc = read_totals(c, &t, 1); if (rc) return rc;
+    c->n_pass = np; c->n_keep = (int64_t)t;
+    return LRB_OK;
+}
+
+int setup_merge(lrb_ctx *c, MergeBufs &m, int64_t n_cand)
+{
+    size_t n = (size_t)std::max<int64_t>(n_cand, 1);
+    NEED(m.keys, n * 8); NEED(m.head, n); NEED(m.locus_start, (n + 1) * 4); NEED(m.locus_cnt, n * 4); NEED(m.dropped, n);
+    Buf *w[] = {&m.w_cand, &m.w_cov, &m.w_tid, &m.w_start, &m.w_end, &m.w_fs, &m.w_le, &m.o_cand, &m.o_cov, &m.o_tid, &m.o_start, &m.o_end, &m.o_fs, &m.o_le};
+    for (Buf *b : w) NEED(*b, n * 4);
+    return LRB_OK;
+}
+DMerged merged_view(Buf &cand, Buf &cov, Buf &tid, Buf &st, Buf &en, Buf &fs, Buf &le, int64_t n)
+{
+    DMerged d; d.n = n; d.cap = n; d.cand = cand.as<uint32_t>(); d.cov = cov.as<int32_t>(); d.tid = tid.as<int32_t>(); d.start = st.as<int32_t>();
+    d.end = en.as<int32_t>(); d.fs = fs.as<int32_t>(); d.le = le.as<int32_t>();
+    return d;
+}
+
+// merge fold over `list` (n_cand entries); result in m (o_* arrays, n_out)
+int run_merge(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_cand, const lrb_update_params &up, bool gather)
+{
+    int rc;
+    if ((rc = setup_merge(c, m, n_cand)) != LRB_OK) return rc;
+    if ((rc = ensure_tiles(c, n_cand)) != LRB_OK) return rc;
+    m.n_out = 0; m.n_loci = 0;
+    if (n_cand == 0) return LRB_OK;
+    MergeArgs a{};
+    a.rows = *c->cur; a.ex = c->ex; a.up = up; a.list = list; a.n_cand = n_cand;
+    a.keys = m.keys.as<uint64_t>(); a.head = m.head.as<uint8_t>(); a.locus_start = m.locus_start.as<uint32_t>(); a.locus_cnt = m.locus_cnt.as<uint32_t>();
+    a.dropped = m.dropped.as<uint8_t>();
+    a.work = merged_view(m.w_cand, m.w_cov, m.w_tid, m.w_start, m.w_end, m.w_fs, m.w_le, n_cand);
+    a.out = merged_view(m.o_cand, m.o_cov, m.o_tid, m.o_start, m.o_end, m.o_fs, m.o_le, n_cand);
+    a.tile_state = c->tile_state.as<uint64_t>(); a.ticket = d_ticket(c); a.totals = d_totals(c);
+    launch_merge_prepare(a, c->st);
+    CK(cudaGetLastError());
+    uint64_t t[2];
+    if ((rc = read_totals(c, t, 1)) != LRB_OK) return rc;
+    m.n_loci = (int64_t)t[0];
+    launch_merge_fold(a, m.n_loci, c->st);
+    launch_merge_compact(a, m.n_loci, c->st);
+    CK(cudaGetLastError());
+    if ((rc = read_totals(c, t, 2)) != LRB_OK) return rc;
+    m.n_out = (int64_t)t[1];
+    if (gather) { launch_merge_gather(a, m.n_out, c->st); CK(cudaGetLastError()); }
+    return LRB_OK;
+}
+
+int setup_list(lrb_ctx *c, DTransList &l, Buf &row, Buf &lo, Buf &cnt, Buf &piece, int64_t n)
+{
+    size_t k = (size_t)std::max<int64_t>(n, 1);
+    NEED(row, k * 4); NEED(lo, k * 4); NEED(cnt, k * 4); NEED(piece, k * 4);
+    l.n = n; l.cap = n; l.row = row.as<uint32_t>(); l.lo = lo.as<uint32_t>(); l.cnt = cnt.as<uint32_t>(); l.piece = piece.as<int32_t>();
+    return LRB_OK;
+}
+
+uint64_t pow2_at_least(uint64_t x) { uint64_t p = 1024; while (p < x) p <<= 1; return p; }
+
+}  // namespace
+
+// ====================================================================================================== C ABI
+extern "C" {
+
+const char *lrb_version(void) { return "lr2rmats_b200 0.1 (sm_100a)"; }
+
+int lrb_ctx_create(int device, lrb_ctx **out)
+{
+    if (!out) return LRB_E_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return LRB_E_NODEVICE; }
+    if (device < 0 || device >= ndev) return LRB_E_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return LRB_E_CUDA; }
+    lrb_ctx *c = new lrb_ctx();
+    c->device = device;
+    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return LRB_E_CUDA; }
+    if (!c->scalars.ensure(256) || !c->h_scalars.ensure(256)) { delete c; return LRB_E_NOMEM; }
+    cudaMemsetAsync(c->scalars.p, 0, 256, c->st);
+    for (int i = 0; i <= LRB_T_COUNT; ++i) cudaEventCreate(&c->ev[i]);
+    memset(c->ms, 0, sizeof c->ms); memset(c->summary, 0, sizeof c->summary);
+    c->launches0 = total_launches();
+    *out = c;
+    return LRB_OK;
+}
+
+void lrb_ctx_destroy(lrb_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->st);
+    Buf *bufs[] = {&c->a_tid, &c->a_start, &c->a_end, &c->a_gene, &c->a_rev, &c->a_off, &c->a_es, &c->a_ee, &c->a_pmax, &c->s_tid, &c->s_don, &c->s_acc,
+                   &c->s_u, &c->s_m, &c->s_pmax, &c->s_dkey, &c->r_gtid, &c->r_goff, &c->r_start, &c->r_pmax, &c->b_tid, &c->b_pos, &c->b_lq, &c->b_nm,
+                   &c->b_flag, &c->b_xs, &c->b_qh, &c->b_coff, &c->b_cig, &c->f_pass, &c->f_score, &c->f_intron, &c->f_keep_row_mask, &c->f_keep_rec_mask,
+                   &c->f_keep_idx, &c->f_keep_rows, &c->r_read, &c->r_tid, &c->r_rs, &c->r_re, &c->r_rev, &c->r_beg, &c->r_n, &c->q_read, &c->q_tid,
+                   &c->q_rs, &c->q_re, &c->q_rev, &c->q_beg, &c->q_n, &c->e_s, &c->e_e, &c->e_f, &c->u_cls, &c->u_ref, &c->u_nnovel, &c->u_noff, &c->u_mk,
+                   &c->u_mu, &c->u_ck, &c->u_cr, &c->u_cu, &c->u_cn, &c->u_known, &c->u_unrecog, &c->u_sub, &c->n_row, &c->n_lo, &c->n_cnt, &c->n_piece,
+                   &c->t_row, &c->t_lo, &c->t_cnt, &c->t_piece, &c->h_khi, &c->h_klo, &c->h_min, &c->h_score, &c->y_barcnt, &c->y_barseg, &c->y_genebar,
+                   &c->y_bedcnt, &c->y_bedoff, &c->y_counts, &c->y_nelem, &c->bd_tid, &c->bd_s, &c->bd_e, &c->bd_sc, &c->bd_ty, &c->bd_rv, &c->q_shared,
+                   &c->tile_state, &c->scalars};
+    for (Buf *b : bufs) b->release();
+    for (MergeBufs *m : {&c->mg, &c->mg2}) {
+        Buf *w[] = {&m->keys, &m->head, &m->locus_start, &m->locus_cnt, &m->dropped, &m->w_cand, &m->w_cov, &m->w_tid, &m->w_start, &m->w_end, &m->w_fs,
+                    &m->w_le, &m->o_cand, &m->o_cov, &m->o_tid, &m->o_start, &m->o_end, &m->o_fs, &m->o_le};
+        for (Buf *b : w) b->release();
+    }
+    for (PBuf &p : c->p) p.release();
+    c->h_scalars.release();
+    for (int i = 0; i <= LRB_T_COUNT; ++i) cudaEventDestroy(c->ev[i]);
+    cudaStreamDestroy(c->st);
+    delete c;
+}
+
+const char *lrb_last_error(const lrb_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+// -------------------------------------------------------------------------------------------------- tables
+int lrb_anno_upload(lrb_ctx *c, const lrb_anno *a)
+{
+    if (!c) return LRB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    c->anno = DAnno{};
+    if (!a || a->n_trans == 0) return LRB_OK;
+    const int32_t n = a->n_trans;
+    std::vector<uint64_t> pm((size_t)n);
+    uint64_t run = 0;
+    for (int32_t i = 0; i < n; ++i) {               // P_j, SURVEY App. B.1
+        uint64_t k = ((uint64_t)(uint32_t)(a->tid[i] + 1) << 32) | (uint32_t)a->end[i];
+        run = std::max(run, k); pm[(size_t)i] = run;
+    }
+    int rc;
+    if ((rc = h2d(c, c->a_tid, a->tid, (size_t)n))) return rc;
+    if ((rc = h2d(c, c->a_start, a->start, (size_t)n))) return rc;
+    if ((rc = h2d(c, c->a_end, a->end, (size_t)n))) return rc;
+    if ((rc = h2d(c, c->a_gene, a->gene, (size_t)n))) return rc;
+    if ((rc = h2d(c, c->a_rev, a->is_rev, (size_t)n))) return rc;
+    if ((rc = h2d(c, c->a_off, a->exon_off, (size_t)n + 1))) return rc;
+    if ((rc = h2d(c, c->a_es, a->exon_start, (size_t)a->n_exon))) return rc;
+    if ((rc = h2d(c, c->a_ee, a->exon_end, (size_t)a->n_exon))) return rc;
+    if ((rc = h2d(c, c->a_pmax, pm.data(), (size_t)n))) return rc;
+    CK(cudaStreamSynchronize(c->st));               // pm is a local
+    c->anno.n = n; c->anno.n_exon = a->n_exon; c->anno.tid = c->a_tid.as<int32_t>(); c->anno.start = c->a_start.as<int32_t>();
+    c->anno.end = c->a_end.as<int32_t>(); c->anno.gene = c->a_gene.as<int32_t>(); c->anno.is_rev = c->a_rev.as<uint8_t>();
+    c->anno.exon_off = c->a_off.as<uint32_t>(); c->anno.es = c->a_es.as<int32_t>(); c->anno.ee = c->a_ee.as<int32_t>();
+    c->anno.pmax_key = c->a_pmax.as<uint64_t>();
+    return LRB_OK;
+}
+
+int lrb_rm_upload(lrb_ctx *c, const lrb_anno *rmt)
+{
+    if (!c) return LRB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    c->rm = DRmIndex{};
+    if (!rmt || rmt->n_trans == 0) return LRB_OK;
+    // entries visible to remove_overlap()'s early exit (bam_filter.c:54-57): for a read on tid t the scan stops after the
+    // first entry with tid > t, so only entries in front of it exist for t.  Group them per tid, sort by start, running max end.
+    const int32_t n = rmt->n_trans;
+    std::map<int32_t, std::vector<std::pair<int32_t, int32_t>>> groups;
+    std::vector<int32_t> pmax_tid((size_t)n);
+    int32_t run = INT32_MIN;
+    for (int32_t i = 0; i < n; ++i) { run = std::max(run, rmt->tid[i]); pmax_tid[(size_t)i] = run; }
+    for (int32_t i = 0; i < n; ++i) {
+        int32_t t = rmt->tid[i];
+        // visible iff no earlier-or-equal position has prefix max tid > t  <=>  pmax_tid[i] <= t (i itself has tid t)
+        if (pmax_tid[(size_t)i] > t) continue;
+        groups[t].push_back({rmt->start[i], rmt->end[i]});
+    }
+    std::vector<int32_t> gt, go{0}, st, pe;
+    for (auto &g : groups) {
+        std::sort(g.second.begin(), g.second.end());
+        int32_t m = INT32_MIN;
+        for (auto &iv : g.second) { m = std::max(m, iv.second); st.push_back(iv.first); pe.push_back(m); }
+        gt.push_back(g.first); go.push_back((int32_t)st.size());
+    }
+    int rc;
+    if ((rc = h2d(c, c->r_gtid, gt.data(), gt.size()))) return rc;
+    if ((rc = h2d(c, c->r_goff, go.data(), go.size()))) return rc;
+    if ((rc = h2d(c, c->r_start, st.data(), st.size()))) return rc;
+    if ((rc = h2d(c, c->r_pmax, pe.data(), pe.size()))) return rc;
+    CK(cudaStreamSynchronize(c->st));
+    c->rm.n_groups = (int32_t)gt.size(); c->rm.n = (int32_t)st.size(); c->rm.g_tid = c->r_gtid.as<int32_t>(); c->rm.g_off = c->r_goff.as<int32_t>();
+    c->rm.start = c->r_start.as<int32_t>(); c->rm.pmax_end = c->r_pmax.as<int32_t>();
+    return LRB_OK;
+}
+
+int lrb_sj_upload(lrb_ctx *c, const lrb_sj *s)
+{
+    if (!c) return LRB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    c->sj = DSj{};
+    if (!s || s->n == 0) return LRB_OK;
+    const int64_t n = s->n;
+    std::vector<uint64_t> pm((size_t)n), dk((size_t)n);
+    uint64_t run = 0;
+    for (int64_t i = 0; i < n; ++i) {               // Q_i, SURVEY App. B.2
+        uint64_t k = ((uint64_t)(uint32_t)(s->tid[i] + 1) << 32) | (uint32_t)s->acc[i];
+        run = std::max(run, k); pm[(size_t)i] = run;
+        dk[(size_t)i] = ((uint64_t)(uint32_t)(s->tid[i] + 1) << 32) | (uint32_t)s->don[i];
+        if (i && dk[(size_t)i] < dk[(size_t)i - 1]) return fail(c, LRB_E_ARG, "SJ table is not sorted by (tid,don,acc)");
+    }
+    int rc;
+    if ((rc = h2d(c, c->s_tid, s->tid, (size_t)n))) return rc;
+    if ((rc = h2d(c, c->s_don, s->don, (size_t)n))) return rc;
+    if ((rc = h2d(c, c->s_acc, s->acc, (size_t)n))) return rc;
+    if ((rc = h2d(c, c->s_u, s->uniq_c, (size_t)n))) return rc;
+    if ((rc = h2d(c, c->s_m, s->multi_c, (size_t)n))) return rc;
+    if ((rc = h2d(c, c->s_pmax, pm.data(), (size_t)n))) return rc;
+    if ((rc = h2d(c, c->s_dkey, dk.data(), (size_t)n))) return rc;
+    CK(cudaStreamSynchronize(c->st));
+    c->sj.n = n; c->sj.tid = c->s_tid.as<int32_t>(); c->sj.don = c->s_don.as<int32_t>(); c->sj.acc = c->s_acc.as<int32_t>();
+    c->sj.cnt_u = c->s_u.as<int32_t>(); c->sj.cnt_m = c->s_m.as<int32_t>(); c->sj.pmax_key = c->s_pmax.as<uint64_t>(); c->sj.don_key = c->s_dkey.as<uint64_t>();
+    return LRB_OK;
+}
+
+// --------------------------------------------------------------------------------------------------- batch
+int lrb_batch_upload(lrb_ctx *c, const lrb_batch *b)
+{
+    if (!c || !b || b->n < 0) return LRB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    const size_t n = (size_t)b->n;
+    const size_t nc = n ? b->cigar_off[n] : 0;
+    if (b->n >= (1ll << 31) - 1) return fail(c, LRB_E_ARG, "batch too large: at most 2^31-2 records per batch");
+    int rc;
+    if ((rc = h2d(c, c->b_tid, b->tid, n))) return rc;
+    if ((rc = h2d(c, c->b_pos, b->pos, n))) return rc;
+    if ((rc = h2d(c, c->b_flag, b->flag, n))) return rc;
+    if ((rc = h2d(c, c->b_lq, b->l_qseq, n))) return rc;
+    if ((rc = h2d(c, c->b_nm, b->nm, n))) return rc;
+    if ((rc = h2d(c, c->b_xs, b->xs, n))) return rc;
+    if ((rc = h2d(c, c->b_qh, b->qname_hash, n))) return rc;
+    if (n) { if ((rc = h2d(c, c->b_coff, b->cigar_off, n + 1))) return rc; }
+    else { uint32_t z = 0; NEED(c->b_coff, 8); CK(cudaMemcpyAsync(c->b_coff.p, &z, 4, cudaMemcpyHostToDevice, c->st)); CK(cudaStreamSynchronize(c->st)); }
+    if ((rc = h2d(c, c->b_cig, b->cigar, nc))) return rc;
+    c->b.n = b->n; c->b.n_cigar = (int64_t)nc;
+    c->b.tid = c->b_tid.as<int32_t>(); c->b.pos = c->b_pos.as<int32_t>(); c->b.flag = c->b_flag.as<uint16_t>(); c->b.l_qseq = c->b_lq.as<int32_t>();
+    c->b.nm = c->b_nm.as<int32_t>(); c->b.xs = c->b_xs.as<int8_t>(); c->b.qhash = c->b_qh.as<uint64_t>(); c->b.cigar_off = c->b_coff.as<uint32_t>();
+    c->b.cigar = c->b_cig.as<uint32_t>();
+    c->have_batch = true; c->have_filter = c->have_exons = c->have_update = c->have_unique = false;
+    return LRB_OK;
+}
+
+// rows straight from exon chains (-m g input): start/end/ex_beg/ex_n derived on device
+__global__ void chains_rows_kernel(DRows rows, const uint32_t *__restrict__ off, const int32_t *__restrict__ es, const int32_t *__restrict__ ee, int64_t n)
+{
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    uint32_t lo = off[r], hi = off[r + 1];
+    rows.read_idx[r] = (uint32_t)r; rows.ex_beg[r] = lo; rows.ex_n[r] = hi - lo;
+    rows.start[r] = hi > lo ? es[lo] : 0; rows.end[r] = hi > lo ? ee[hi - 1] : 0;
+}
+
+int lrb_chains_upload(lrb_ctx *c, const lrb_chains *ch)
+{
+    if (!c || !ch || ch->n < 0) return LRB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    const int64_t n = ch->n; const int64_t ne = n ? ch->exon_off[n] : 0;
+    int rc;
+    if ((rc = setup_rows(c, c->rows, c->r_read, c->r_tid, c->r_rs, c->r_re, c->r_rev, c->r_beg, c->r_n, n))) return rc;
+    if ((rc = setup_exons(c, ne + 16))) return rc;
+    if ((rc = h2d(c, c->r_tid, ch->tid, (size_t)n))) return rc;
+    if ((rc = h2d(c, c->r_rev, ch->is_rev, (size_t)n))) return rc;
+    if ((rc = h2d(c, c->e_s, ch->exon_start, (size_t)ne))) return rc;
+    if ((rc = h2d(c, c->e_e, ch->exon_end, (size_t)ne))) return rc;
+    if ((rc = h2d(c, c->u_noff, ch->exon_off, (size_t)n + 1))) return rc;          // scratch for the offsets
+    if (n) { chains_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->st>>>(c->rows, c->u_noff.as<uint32_t>(), c->ex.es, c->ex.ee, n); CK(cudaGetLastError()); }
+    c->rows.n = n; c->ex.n = ne; c->cur = &c->rows; c->rows_compact = true;
+    c->b.n = 0; c->have_batch = false; c->have_filter = false; c->have_exons = true; c->have_update = c->have_unique = false;
+    return LRB_OK;
+}
+
+// -------------------------------------------------------------------------------------------------- stages
+int lrb_filter_run(lrb_ctx *c, const lrb_filter_params *p)
+{
+    if (!c || !p) return LRB_E_ARG;
+    if (!c->have_batch) return fail(c, LRB_E_ARG, "lrb_filter_run: no batch uploaded");
+    CK(cudaSetDevice(c->device));
+    int64_t l0 = total_launches(); tick(c, 0);
+    int rc = run_scan(c, 0, p, nullptr, nullptr); if (rc) return rc;
+    if ((rc = run_select(c, p))) return rc;
+    tick(c, 1);
+    c->have_filter = true; c->have_exons = false; c->launches_last = total_launches() - l0;
+    if (c->timing) { CK(cudaStreamSynchronize(c->st)); cudaEventElapsedTime(&c->ms[LRB_T_FILTER], c->ev[0], c->ev[1]); }
+    return LRB_OK;
+}
+
+int lrb_exon_run(lrb_ctx *c, const lrb_exon_params *p, int use_keep_list)
+{
+    if (!c || !p) return LRB_E_ARG;
+    if (!c->have_batch) return fail(c, LRB_E_ARG, "lrb_exon_run: no batch uploaded");
+    if (use_keep_list && !c->have_filter) return fail(c, LRB_E_ARG, "lrb_exon_run: keep list requested but lrb_filter_run has not run");
+    CK(cudaSetDevice(c->device));
+    int64_t l0 = total_launches(); tick(c, 0);
+    int rc = run_scan(c, 1, nullptr, p, use_keep_list ? c->f_keep_rec_mask.as<uint8_t>() : nullptr); if (rc) return rc;
+    tick(c, 1);
+    c->cur = &c->rows; c->rows_compact = true; c->have_exons = true; c->have_update = c->have_unique = false;
+    c->launches_last = total_launches() - l0;
+    if (c->timing) { CK(cudaStreamSynchronize(c->st)); cudaEventElapsedTime(&c->ms[LRB_T_EXON], c->ev[0], c->ev[1]); }
+    return LRB_OK;
+}
+
+int lrb_pipeline_run(lrb_ctx *c, const lrb_filter_params *fp, const lrb_exon_params *ep)
+{
+    if (!c || !fp || !ep) return LRB_E_ARG;
+    if (!c->have_batch) return fail(c, LRB_E_ARG, "lrb_pipeline_run: no batch uploaded");
+    CK(cudaSetDevice(c->device));
+    int64_t l0 = total_launches(); tick(c, 0);
+    int rc = run_scan(c, 2, fp, ep, nullptr); if (rc) return rc;
+    if ((rc = run_select(c, fp))) return rc;
+    if ((rc = setup_rows(c, c->rows2, c->q_read, c->q_tid, c->q_rs, c->q_re, c->q_rev, c->q_beg, c->q_n, c->n_keep))) return rc;
+    launch_gather_rows(c->rows, c->f_keep_rows.as<uint32_t>(), c->n_keep, c->rows2, c->st);
+    CK(cudaGetLastError());
+    c->rows2.n = c->n_keep;
+    tick(c, 1);
+    c->cur = &c->rows2; c->rows_compact = false; c->have_filter = true; c->have_exons = true; c->have_update = c->have_unique = false;
+    c->launches_last = total_launches() - l0;
+    if (c->timing) { CK(cudaStreamSynchronize(c->st)); cudaEventElapsedTime(&c->ms[LRB_T_FILTER], c->ev[0], c->ev[1]); c->ms[LRB_T_EXON] = 0; }
+    return LRB_OK;
+}
+
+static int check_err_flags(lrb_ctx *c)
+{
+    uint32_t e = 0;
+    CK(cudaMemcpyAsync(c->h_scalars.p, d_err(c), 4, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    memcpy(&e, c->h_scalars.p, 4);
+    if (e & 2u) return fail(c, LRB_E_UNMAPPED, "unmapped record / empty exon chain in update/unique input (the reference aborts here, bam2gtf.c:95-100)");
+    if (e & 1u) return fail(c, LRB_E_UNSORTED, "reads are not sorted by (tid,start) (update_gtf.c:41)");
+    return LRB_OK;
+}
+
+__global__ void invert_mask_kernel(const uint8_t *a, uint8_t *o, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = !a[i];
+}
+
+// empty-chain / sortedness check for unique (classification does it for update)
+__global__ void rows_check_kernel(DRows rows, uint32_t *err, int check_sorted)
+{
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows.n) return;
+    if (rows.ex_n[r] == 0) atomicOr(err, 2u);
+    (void)check_sorted;
+}
+
+int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
+{
+    if (!c || !up) return LRB_E_ARG;
+    if (!c->have_exons) return fail(c, LRB_E_ARG, "lrb_update_run: exon chains missing (run lrb_exon_run / lrb_pipeline_run / lrb_chains_upload)");
+    CK(cudaSetDevice(c->device));
+    int64_t l0 = total_launches();
+    DRows &rows = *c->cur; const int64_t n = rows.n; const size_t nn = (size_t)std::max<int64_t>(n, 1);
+    int rc;
+    memset(c->summary, 0, sizeof c->summary); c->n_bed = 0; c->last_up = *up;
+    NEED(c->u_cls, nn * 4); NEED(c->u_ref, nn * 4); NEED(c->u_nnovel, nn * 4); NEED(c->u_noff, (nn + 1) * 4);
+    NEED(c->u_mk, nn); NEED(c->u_mu, nn); NEED(c->u_known, nn * 4); NEED(c->u_unrecog, nn * 4);
+    if (up->want_summary) { NEED(c->u_ck, nn); NEED(c->u_cr, nn); NEED(c->u_cu, nn); NEED(c->u_cn, nn); NEED(c->u_sub, nn * 4); }
+    if ((rc = ensure_tiles(c, std::max<int64_t>(n, c->ex.n)))) return rc;
+    CK(cudaMemsetAsync(d_err(c), 0, 4, c->st));
+    tick(c, 0);
+    // ---- classification (+ SJ support)
+    ClassArgs ca{};
+    ca.rows = rows; ca.ex = c->ex; ca.anno = c->anno; ca.sj = c->sj; ca.up = *up;
+    ca.cls = c->u_cls.as<uint32_t>(); ca.ref = c->u_ref.as<int32_t>(); ca.n_novel = c->u_nnovel.as<uint32_t>(); ca.err_flags = d_err(c);
+    launch_classify(ca, c->st);
+    CK(cudaGetLastError());
+    tick(c, 1);
+    // ---- class lists
+    launch_class_masks(ca.cls, n, c->u_mk.as<uint8_t>(), c->u_mu.as<uint8_t>(), up->want_summary ? c->u_ck.as<uint8_t>() : nullptr,
+                       c->u_cr.as<uint8_t>(), c->u_cu.as<uint8_t>(), c->u_cn.as<uint8_t>(), c->st);
+    launch_scan_sum_u32(ca.n_novel, c->u_noff.as<uint32_t>(), n, c->tile_state.as<uint64_t>(), d_ticket(c), d_totals(c) + 0, c->st);
+    launch_compact_mask(c->u_mk.as<uint8_t>(), n, nullptr, c->u_known.as<uint32_t>(), nullptr, c->tile_state.as<uint64_t>(), d_ticket(c), d_totals(c) + 1, c->st);
+    launch_compact_mask(c->u_mu.as<uint8_t>(), n, nullptr, c->u_unrecog.as<uint32_t>(), nullptr, c->tile_state.as<uint64_t>(), d_ticket(c), d_totals(c) + 2, c->st);
+    CK(cudaGetLastError());
+    if ((rc = check_err_flags(c))) return rc;
+    uint64_t t[4];
+    if ((rc = read_totals(c, t, 3))) return rc;
+    const int64_t n_novel = n ? (int64_t)t[0] : 0; c->n_known = n ? (int64_t)t[1] : 0; c->n_unrecog = n ? (int64_t)t[2] : 0;
+    if ((rc = setup_list(c, c->novel, c->n_row, c->n_lo, c->n_cnt, c->n_piece, n_novel))) return rc;
+    ListArgs la{};
+    la.rows = rows; la.ex = c->ex; la.up = *up; la.cls = ca.cls; la.n_novel = ca.n_novel; la.novel = c->novel;
+    launch_emit_novel(la, c->u_noff.as<uint32_t>(), c->st);
+    CK(cudaGetLastError());
+    // ---- updated_T = merge fold over novel_T
+    tick(c, 2);
+    if ((rc = run_merge(c, c->mg, c->novel, n_novel, *up, true))) return rc;
+    tick(c, 3);
+    // ---- summary
+    if (up->want_summary) {
+        int32_t *s = c->summary;
+        // class counts + uniq_* folds over bam_T (update_gtf.c:501-528)
+        struct { Buf *mask; int cnt_idx, uniq_idx; } cl[4] = {{&c->u_ck, LRB_S_KNOWN_TRANS, LRB_S_UNIQ_KNOWN}, {&c->u_cr, LRB_S_NOVEL_RELIABLE, LRB_S_UNIQ_RELIABLE},
+                                                             {&c->u_cu, LRB_S_NOVEL_UNRELIABLE, LRB_S_UNIQ_UNRELIABLE}, {&c->u_cn, LRB_S_UNRECOG, LRB_S_UNIQ_UNRECOG}};
+        for (auto &k : cl) {
+            launch_compact_mask(k.mask->as<uint8_t>(), n, nullptr, c->u_sub.as<uint32_t>(), nullptr, c->tile_state.as<uint64_t>(), d_ticket(c), d_totals(c), c->st);
+            CK(cudaGetLastError());
+            if ((rc = read_totals(c, t, 1))) return rc;
+            int64_t m = n ? (int64_t)t[0] : 0;
+            s[k.cnt_idx] = (int32_t)m;
+            if ((rc = setup_list(c, c->tmp_list, c->t_row, c->t_lo, c->t_cnt, c->t_piece, m))) return rc;
+            launch_rows_as_list(rows, c->u_sub.as<uint32_t>(), m, c->tmp_list, c->st);
+            if ((rc = run_merge(c, c->mg2, c->tmp_list, m, *up, false))) return rc;
+            s[k.uniq_idx] = (int32_t)c->mg2.n_out;
+        }
+        s[LRB_S_NOVEL_BAM] = s[LRB_S_NOVEL_RELIABLE] + s[LRB_S_NOVEL_UNRELIABLE];
+        // sets over updated_T
+        const int64_t nu = c->mg.n_out; const size_t nun = (size_t)std::max<int64_t>(nu, 1);
+        NEED(c->y_barcnt, nun * 16); NEED(c->y_barseg, nun * 16); NEED(c->y_genebar, nun * 8); NEED(c->y_bedcnt, nun * 4); NEED(c->y_bedoff, nun * 4);
+        NEED(c->y_counts, 64); NEED(c->y_nelem, 8);
+        CK(cudaMemsetAsync(c->y_counts.p, 0, 64, c->st)); CK(cudaMemsetAsync(c->y_nelem.p, 0, 8, c->st));
+        SummaryArgs sa{};
+        sa.rows = rows; sa.ex = c->ex; sa.list = c->novel; sa.n_upd = nu;
+        sa.upd = merged_view(c->mg.o_cand, c->mg.o_cov, c->mg.o_tid, c->mg.o_start, c->mg.o_end, c->mg.o_fs, c->mg.o_le, nu);
+        sa.ref = c->u_ref.as<int32_t>(); sa.anno_gene = c->anno.gene;
+        sa.bar_cnt = c->y_barcnt.as<uint32_t>(); sa.bar_seg = c->y_barseg.as<uint32_t>(); sa.gene_bar = c->y_genebar.as<uint64_t>();
+        sa.bed_cnt = c->y_bedcnt.as<uint32_t>(); sa.bed_off = c->y_bedoff.as<uint32_t>(); sa.counts = c->y_counts.as<uint32_t>();
+        launch_summary_count(sa, c->y_nelem.as<unsigned long long>(), c->st);
+        CK(cudaMemcpyAsync(c->h_scalars.p, c->y_nelem.p, 8, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        uint64_t n_elem; memcpy(&n_elem, c->h_scalars.p, 8);
+        const uint64_t capn = pow2_at_least(2 * (n_elem + (uint64_t)s[LRB_S_KNOWN_TRANS]) + 1024);
+        NEED(c->h_khi, capn * 8); NEED(c->h_klo, capn * 8); NEED(c->h_min, capn * 8); NEED(c->h_score, capn * 4);
+        CK(cudaMemsetAsync(c->h_khi.p, 0xFF, capn * 8, c->st)); CK(cudaMemsetAsync(c->h_klo.p, 0xFF, capn * 8, c->st));
+        CK(cudaMemsetAsync(c->h_min.p, 0xFF, capn * 8, c->st)); CK(cudaMemsetAsync(c->h_score.p, 0, capn * 4, c->st));
+        sa.tab.mask = capn - 1; sa.tab.khi = c->h_khi.as<uint64_t>(); sa.tab.klo = c->h_klo.as<uint64_t>(); sa.tab.minpos = c->h_min.as<uint64_t>();
+        sa.tab.score = c->h_score.as<int32_t>();
+        launch_summary_sets(sa, ca.cls, n, c->tile_state.as<uint64_t>(), d_ticket(c), d_totals(c) + 3, c->st);
+        CK(cudaGetLastError());
+        if ((rc = read_totals(c, t, 4))) return rc;
+        c->n_bed = nu ? (int64_t)t[3] : 0;
+        const size_t nb = (size_t)std::max<int64_t>(c->n_bed, 1);
+        NEED(c->bd_tid, nb * 4); NEED(c->bd_s, nb * 4); NEED(c->bd_e, nb * 4); NEED(c->bd_sc, nb * 4); NEED(c->bd_ty, nb); NEED(c->bd_rv, nb);
+        sa.bed_tid = c->bd_tid.as<int32_t>(); sa.bed_start = c->bd_s.as<int32_t>(); sa.bed_end = c->bd_e.as<int32_t>(); sa.bed_score = c->bd_sc.as<int32_t>();
+        sa.bed_type = c->bd_ty.as<uint8_t>(); sa.bed_rev = c->bd_rv.as<uint8_t>();
+        launch_summary_bed(sa, c->st);
+        CK(cudaGetLastError());
+        uint32_t cnt[8];
+        CK(cudaMemcpyAsync(c->h_scalars.p, c->y_counts.p, 32, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        memcpy(cnt, c->h_scalars.p, 32);
+        s[LRB_S_UPD_GENES] = (int32_t)cnt[4]; s[LRB_S_NOVEL_TRANS] = (int32_t)nu; s[LRB_S_NOVEL_PARTIAL] = (int32_t)cnt[6];
+        s[LRB_S_NOVEL_FULL] = (int32_t)nu - (int32_t)cnt[6]; s[LRB_S_NOVEL_EXONS] = (int32_t)cnt[0]; s[LRB_S_NOVEL_SITES] = (int32_t)(cnt[1] + cnt[2]);
+        s[LRB_S_NOVEL_JUNC] = (int32_t)cnt[3]; s[LRB_S_KNOWN_GENES] = (int32_t)cnt[5];
+    }
+    tick(c, 4);
+    c->have_update = true; c->launches_last = total_launches() - l0;
+    if (c->timing) {
+        CK(cudaStreamSynchronize(c->st));
+        cudaEventElapsedTime(&c->ms[LRB_T_CLASSIFY], c->ev[0], c->ev[1]);
+        float lists = 0; cudaEventElapsedTime(&lists, c->ev[1], c->ev[2]);
+        cudaEventElapsedTime(&c->ms[LRB_T_MERGE], c->ev[2], c->ev[3]); c->ms[LRB_T_MERGE] += lists;
+        cudaEventElapsedTime(&c->ms[LRB_T_SUMMARY], c->ev[3], c->ev[4]);
+    }
+    return LRB_OK;
+}
+
+int lrb_unique_run(lrb_ctx *c, const lrb_update_params *up)
+{
+    if (!c || !up) return LRB_E_ARG;
+    if (!c->have_exons) return fail(c, LRB_E_ARG, "lrb_unique_run: exon chains missing");
+    CK(cudaSetDevice(c->device));
+    int64_t l0 = total_launches();
+    DRows &rows = *c->cur; const int64_t n = rows.n;
+    int rc;
+    CK(cudaMemsetAsync(d_err(c), 0, 4, c->st));
+    tick(c, 0);
+    if (n) { rows_check_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->st>>>(rows, d_err(c), 0); CK(cudaGetLastError()); }
+    if ((rc = check_err_flags(c))) return rc;
+    if ((rc = setup_list(c, c->tmp_list, c->t_row, c->t_lo, c->t_cnt, c->t_piece, n))) return rc;
+    launch_rows_as_list(rows, nullptr, n, c->tmp_list, c->st);
+    if ((rc = run_merge(c, c->mg, c->tmp_list, n, *up, true))) return rc;
+    // shared_T = rows the fold absorbed: complement of the alive mask (kept in mg.dropped); mg.head is free again
+    NEED(c->q_shared, (size_t)std::max<int64_t>(n, 1) * 4);
+    c->n_shared = 0;
+    if (n) {
+        invert_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->st>>>(c->mg.dropped.as<uint8_t>(), c->mg.head.as<uint8_t>(), n);
+        launch_compact_mask(c->mg.head.as<uint8_t>(), n, nullptr, c->q_shared.as<uint32_t>(), nullptr, c->tile_state.as<uint64_t>(), d_ticket(c), d_totals(c), c->st);
+        CK(cudaGetLastError());
+        uint64_t t; if ((rc = read_totals(c, &t, 1))) return rc;
+        c->n_shared = (int64_t)t;
+    }
+    tick(c, 1);
+    c->have_unique = true; c->launches_last = total_launches() - l0;
+    if (c->timing) { CK(cudaStreamSynchronize(c->st)); cudaEventElapsedTime(&c->ms[LRB_T_MERGE], c->ev[0], c->ev[1]); }
+    return LRB_OK;
+}
+
+int lrb_sync(lrb_ctx *c)
+{
+    if (!c) return LRB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->st));
+    return LRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------- fetches
+int lrb_filter_fetch(lrb_ctx *c, lrb_filter_result *out)
+{
+    if (!c || !out) return LRB_E_ARG;
+    if (!c->have_filter) return fail(c, LRB_E_ARG, "lrb_filter_fetch: filter stage has not run");
+    CK(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->b.n; int rc;
+    if ((rc = d2h(c, c->p[0], c->f_pass.as<uint8_t>(), n))) return rc;
+    if ((rc = d2h(c, c->p[1], c->f_score.as<int32_t>(), n))) return rc;
+    if ((rc = d2h(c, c->p[2], c->f_intron.as<int32_t>(), n))) return rc;
+    if ((rc = d2h(c, c->p[3], c->f_keep_idx.as<uint32_t>(), (size_t)c->n_keep))) return rc;
+    CK(cudaStreamSynchronize(c->st));
+    out->n = c->b.n; out->pass = c->p[0].as<uint8_t>(); out->score = c->p[1].as<int32_t>(); out->intron_n = c->p[2].as<int32_t>();
+    out->n_keep = c->n_keep; out->keep_idx = c->p[3].as<uint32_t>();
+    return LRB_OK;
+}
+
+// compact copy of the exon data of the current rows (rows may reference a sparse subset of the pool after the fused pass)
+__global__ void exon_gather_kernel(DRows rows, DExons ex, const uint32_t *__restrict__ off, int32_t *es, int32_t *ee, uint8_t *fl, int with_flags)
+{
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows.n) return;
+    uint32_t b = rows.ex_beg[r], n = rows.ex_n[r], o = off[r];
+    for (uint32_t j = 0; j < n; ++j) { es[o + j] = ex.es[b + j]; ee[o + j] = ex.ee[b + j]; if (with_flags) fl[o + j] = ex.flag[b + j]; }
+}
+
+static int fetch_exons(lrb_ctx *c, lrb_exon_result *out, bool with_flags, const uint8_t **flags_out, int pbase)
+{
+    DRows &rows = *c->cur; const int64_t n = rows.n; int rc;
+    if ((rc = d2h(c, c->p[pbase + 0], rows.read_idx, (size_t)n))) return rc;
+    if ((rc = d2h(c, c->p[pbase + 1], rows.tid, (size_t)n))) return rc;
+    if ((rc = d2h(c, c->p[pbase + 2], rows.is_rev, (size_t)n))) return rc;
+    int64_t ne = 0;
+    NEEDP(c->p[pbase + 3], ((size_t)n + 1) * 4);
+    if (c->rows_compact) {
+        ne = c->ex.n;
+        if (n) CK(cudaMemcpyAsync(c->p[pbase + 3].p, rows.ex_beg, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
+        if ((rc = d2h(c, c->p[pbase + 4], c->ex.es, (size_t)ne))) return rc;
+        if ((rc = d2h(c, c->p[pbase + 5], c->ex.ee, (size_t)ne))) return rc;
+        if (with_flags && (rc = d2h(c, c->p[pbase + 6], c->ex.flag, (size_t)ne))) return rc;
+        CK(cudaStreamSynchronize(c->st));
+        c->p[pbase + 3].as<uint32_t>()[n] = (uint32_t)ne;
+    } else {
+        // exclusive scan of ex_n -> offsets, then gather into scratch (the summary hash buffers are free at fetch time)
+        if ((rc = ensure_tiles(c, n))) return rc;
+        NEED(c->u_sub, ((size_t)n + 1) * 4);
+        launch_scan_sum_u32(rows.ex_n, c->u_sub.as<uint32_t>(), n, c->tile_state.as<uint64_t>(), d_ticket(c), d_totals(c), c->st);
+        uint64_t t; if ((rc = read_totals(c, &t, 1))) return rc;
+        ne = n ? (int64_t)t : 0;
+        const size_t k = (size_t)std::max<int64_t>(ne, 1);
+        NEED(c->y_barcnt, k * 4); NEED(c->y_barseg, k * 4); NEED(c->y_bedcnt, k);
+        if (n) {
+            exon_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->st>>>(rows, c->ex, c->u_sub.as<uint32_t>(), c->y_barcnt.as<int32_t>(),
+                                                                                 c->y_barseg.as<int32_t>(), c->y_bedcnt.as<uint8_t>(), with_flags ? 1 : 0);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(c->p[pbase + 3].p, c->u_sub.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->st));
+        }
+        if ((rc = d2h(c, c->p[pbase + 4], c->y_barcnt.as<int32_t>(), (size_t)ne))) return rc;
+        if ((rc = d2h(c, c->p[pbase + 5], c->y_barseg.as<int32_t>(), (size_t)ne))) return rc;
+        if (with_flags && (rc = d2h(c, c->p[pbase + 6], c->y_bedcnt.as<uint8_t>(), (size_t)ne))) return rc;
+        CK(cudaStreamSynchronize(c->st));
+        c->p[pbase + 3].as<uint32_t>()[n] = (uint32_t)ne;
+    }
+    out->n_reads = n; out->read_idx = c->have_batch ? c->p[pbase + 0].as<uint32_t>() : nullptr; out->tid = c->p[pbase + 1].as<int32_t>();
+    out->is_rev = c->p[pbase + 2].as<uint8_t>(); out->exon_off = c->p[pbase + 3].as<uint32_t>();
+    out->exon_start = c->p[pbase + 4].as<int32_t>(); out->exon_end = c->p[pbase + 5].as<int32_t>();
+    if (flags_out) *flags_out = with_flags ? c->p[pbase + 6].as<uint8_t>() : nullptr;
+    return LRB_OK;
+}
+
+int lrb_exon_fetch(lrb_ctx *c, lrb_exon_result *out)
+{
+    if (!c || !out) return LRB_E_ARG;
+    if (!c->have_exons) return fail(c, LRB_E_ARG, "lrb_exon_fetch: exon stage has not run");
+    CK(cudaSetDevice(c->device));
+    return fetch_exons(c, out, false, nullptr, 4);
+}
+
+static int fetch_merged(lrb_ctx *c, MergeBufs &m, lrb_merged_list *o, int pbase)
+{
+    const size_t n = (size_t)m.n_out; int rc;
+    Buf *src[] = {&m.o_cand, &m.o_cov, &m.o_tid, &m.o_start, &m.o_end, &m.o_fs, &m.o_le};
+    for (int i = 0; i < 7; ++i) if ((rc = d2h(c, c->p[pbase + i], src[i]->as<uint32_t>(), n))) return rc;
+    o->n = m.n_out; o->cand = c->p[pbase].as<uint32_t>(); o->cov = c->p[pbase + 1].as<int32_t>(); o->t_tid = c->p[pbase + 2].as<int32_t>();
+    o->t_start = c->p[pbase + 3].as<int32_t>(); o->t_end = c->p[pbase + 4].as<int32_t>(); o->first_start = c->p[pbase + 5].as<int32_t>();
+    o->last_end = c->p[pbase + 6].as<int32_t>();
+    return LRB_OK;
+}
+
+int lrb_update_fetch(lrb_ctx *c, lrb_update_result *out)
+{
+    if (!c || !out) return LRB_E_ARG;
+    if (!c->have_update) return fail(c, LRB_E_ARG, "lrb_update_fetch: update stage has not run");
+    CK(cudaSetDevice(c->device));
+    memset(out, 0, sizeof *out);
+    int rc; const int64_t n = c->cur->n;
+    if ((rc = fetch_exons(c, &out->ex, true, &out->exon_flag, 4))) return rc;
+    if ((rc = d2h(c, c->p[11], c->u_cls.as<uint32_t>(), (size_t)n))) return rc;
+    if ((rc = d2h(c, c->p[12], c->u_ref.as<int32_t>(), (size_t)n))) return rc;
+    if ((rc = d2h(c, c->p[13], c->u_known.as<uint32_t>(), (size_t)c->n_known))) return rc;
+    if ((rc = d2h(c, c->p[14], c->u_unrecog.as<uint32_t>(), (size_t)c->n_unrecog))) return rc;
+    if ((rc = d2h(c, c->p[15], c->novel.row, (size_t)c->novel.n))) return rc;
+    if ((rc = d2h(c, c->p[16], c->novel.lo, (size_t)c->novel.n))) return rc;
+    if ((rc = d2h(c, c->p[17], c->novel.cnt, (size_t)c->novel.n))) return rc;
+    if ((rc = d2h(c, c->p[18], c->novel.piece, (size_t)c->novel.n))) return rc;
+    if ((rc = fetch_merged(c, c->mg, &out->updated, 19))) return rc;
+    if ((rc = d2h(c, c->p[26], c->bd_tid.as<int32_t>(), (size_t)c->n_bed))) return rc;
+    if ((rc = d2h(c, c->p[27], c->bd_s.as<int32_t>(), (size_t)c->n_bed))) return rc;
+    if ((rc = d2h(c, c->p[28], c->bd_e.as<int32_t>(), (size_t)c->n_bed))) return rc;
+    if ((rc = d2h(c, c->p[29], c->bd_sc.as<int32_t>(), (size_t)c->n_bed))) return rc;
+    if ((rc = d2h(c, c->p[30], c->bd_ty.as<uint8_t>(), (size_t)c->n_bed))) return rc;
+    if ((rc = d2h(c, c->p[31], c->bd_rv.as<uint8_t>(), (size_t)c->n_bed))) return rc;
+    CK(cudaStreamSynchronize(c->st));
+    out->cls = c->p[11].as<uint32_t>(); out->ref_anno = c->p[12].as<int32_t>();
+    out->n_known = c->n_known; out->known_idx = c->p[13].as<uint32_t>(); out->n_unrecog = c->n_unrecog; out->unrecog_idx = c->p[14].as<uint32_t>();
+    out->novel.n = c->novel.n; out->novel.read = c->p[15].as<uint32_t>(); out->novel.exon_lo = c->p[16].as<uint32_t>();
+    out->novel.exon_n = c->p[17].as<uint32_t>(); out->novel.piece = c->p[18].as<int32_t>();
+    memcpy(out->summary, c->summary, sizeof c->summary);
+    out->bed.n = c->n_bed; out->bed.tid = c->p[26].as<int32_t>(); out->bed.start = c->p[27].as<int32_t>(); out->bed.end = c->p[28].as<int32_t>();
+    out->bed.score = c->p[29].as<int32_t>(); out->bed.type = c->p[30].as<uint8_t>(); out->bed.is_rev = c->p[31].as<uint8_t>();
+    return LRB_OK;
+}
+
+int lrb_unique_fetch(lrb_ctx *c, lrb_unique_result *out)
+{
+    if (!c || !out) return LRB_E_ARG;
+    if (!c->have_unique) return fail(c, LRB_E_ARG, "lrb_unique_fetch: unique stage has not run");
+    CK(cudaSetDevice(c->device));
+    memset(out, 0, sizeof *out);
+    int rc;
+    if ((rc = fetch_exons(c, &out->ex, false, nullptr, 4))) return rc;
+    if ((rc = fetch_merged(c, c->mg, &out->uniq, 19))) return rc;
+    if ((rc = d2h(c, c->p[26], c->q_shared.as<uint32_t>(), (size_t)c->n_shared))) return rc;
+    CK(cudaStreamSynchronize(c->st));
+    out->n_shared = c->n_shared; out->shared_idx = c->p[26].as<uint32_t>();
+    return LRB_OK;
+}
+
+// -------------------------------------------------------------------------------------------- one-call forms
+int lrb_filter(lrb_ctx *c, const lrb_batch *b, const lrb_filter_params *p, lrb_filter_result *out)
+{
+    int rc;
+    if ((rc = lrb_batch_upload(c, b))) return rc;
+    if ((rc = lrb_filter_run(c, p))) return rc;
+    return lrb_filter_fetch(c, out);
+}
+int lrb_bam2gtf(lrb_ctx *c, const lrb_batch *b, const lrb_exon_params *p, lrb_exon_result *out)
+{
+    int rc;
+    if ((rc = lrb_batch_upload(c, b))) return rc;
+    if ((rc = lrb_exon_run(c, p, 0))) return rc;
+    return lrb_exon_fetch(c, out);
+}
+int lrb_update_gtf(lrb_ctx *c, const lrb_batch *b, const lrb_exon_params *ep, const lrb_update_params *up, lrb_update_result *out)
+{
+    int rc;
+    if (b) { if ((rc = lrb_batch_upload(c, b))) return rc; if ((rc = lrb_exon_run(c, ep, 0))) return rc; }
+    if ((rc = lrb_update_run(c, up))) return rc;
+    return lrb_update_fetch(c, out);
+}
+int lrb_unique_gtf(lrb_ctx *c, const lrb_batch *b, const lrb_exon_params *ep, const lrb_update_params *up, lrb_unique_result *out)
+{
+    int rc;
+    if (b) { if ((rc = lrb_batch_upload(c, b))) return rc; if ((rc = lrb_exon_run(c, ep, 0))) return rc; }
+    if ((rc = lrb_unique_run(c, up))) return rc;
+    return lrb_unique_fetch(c, out);
+}
+
+// ------------------------------------------------------------------------------------------------ measurement
+int lrb_timing_enable(lrb_ctx *c, int on) { if (!c) return LRB_E_ARG; c->timing = on != 0; return LRB_OK; }
+int lrb_timing_get(lrb_ctx *c, float ms[LRB_T_COUNT], int64_t *n_launches)
+{
+    if (!c) return LRB_E_ARG;
+    if (ms) memcpy(ms, c->ms, sizeof c->ms);
+    if (n_launches) *n_launches = c->launches_last;
+    return LRB_OK;
+}
+int64_t lrb_launch_count(const lrb_ctx *c) { return c ? total_launches() - c->launches0 : 0; }
+
+// ----------------------------------------------------------------------------------------------------- shards
+int lrb_shard_cuts(const int32_t *tid, const int32_t *start, const int32_t *end, int64_t n, int n_shards, int64_t *cuts)
+{
+    if (n_shards <= 0 || !cuts || n < 0) return LRB_E_ARG;
+    // a cut is exact where the read starts beyond every earlier end on its chromosome;
+    // take the first such position at or after each ideal boundary k*n/n_shards
+    cuts[0] = 0; cuts[n_shards] = n;
+    uint64_t run = 0; int k = 1; int64_t want = n_shards > 1 ? n / n_shards : n;
+    for (int64_t i = 0; i < n && k < n_shards; ++i) {
+        uint64_t ks = ((uint64_t)(uint32_t)(tid[i] + 1) << 32) | (uint32_t)start[i];
+        if (i >= want && i > cuts[k - 1] && ks > run) { cuts[k++] = i; want = (int64_t)((__int128)n * k / n_shards); }
+        uint64_t ke = ((uint64_t)(uint32_t)(tid[i] + 1) << 32) | (uint32_t)end[i];
+        if (ke > run) run = ke;
+    }
+    for (; k < n_shards; ++k) cuts[k] = n;
+    return LRB_OK;
+}
+
+}  // extern "C"

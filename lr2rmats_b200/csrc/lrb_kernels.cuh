@@ -1,0 +1,130 @@
+// lrb_kernels.cuh -- device-side data layout and kernel launchers shared by the .cu files of liblr2rmats_b200.so.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/lr2rmats_b200.h"
+
+namespace lrbk {
+
+// ---- record batch resident in HBM (structure of arrays; mirrors lrb_batch)
+struct DBatch {
+    int64_t n = 0, n_cigar = 0;
+    int32_t *tid = nullptr, *pos = nullptr, *l_qseq = nullptr, *nm = nullptr;
+    uint16_t *flag = nullptr;
+    int8_t *xs = nullptr;
+    uint64_t *qhash = nullptr;
+    uint32_t *cigar_off = nullptr, *cigar = nullptr;
+};
+
+// ---- remove table (-r GTF) as an index: per tid the entries visible to remove_overlap()'s early exit
+// (bam_filter.c:54-57), sorted by start with a running max of end.
+struct DRmIndex {
+    int32_t n_groups = 0, n = 0;
+    int32_t *g_tid = nullptr, *g_off = nullptr;     // n_groups, n_groups+1
+    int32_t *start = nullptr, *pmax_end = nullptr;  // n
+};
+
+// ---- annotation in HBM: transcripts in file order + exon pools + prefix-max keys for the cursor closed form
+struct DAnno {
+    int32_t n = 0; int64_t n_exon = 0;
+    int32_t *tid = nullptr, *start = nullptr, *end = nullptr, *gene = nullptr;
+    uint8_t *is_rev = nullptr;
+    uint32_t *exon_off = nullptr;
+    int32_t *es = nullptr, *ee = nullptr;
+    uint64_t *pmax_key = nullptr;                   // P_j = max_{i<=j} ((tid_i+1)<<32 | end_i)   
+};
+struct DSj {
+    int64_t n = 0;
+    int32_t *tid = nullptr, *don = nullptr, *acc = nullptr, *cnt_u = nullptr, *cnt_m = nullptr;
+    uint64_t *pmax_key = nullptr;                   // Q_i = max_{k<=i} ((tid_k+1)<<32 | acc_k)   
+    uint64_t *don_key = nullptr;                    // (tid+1)<<32 | don  (non-decreasing: table is sorted)
+};
+
+// ---- read rows (the reads that went through the CIGAR walk, in record order)
+struct DRows {
+    int64_t n = 0, cap = 0;
+    uint32_t *read_idx = nullptr;                   // record index in the batch
+    int32_t *tid = nullptr, *start = nullptr, *end = nullptr;   // trans_t.tid / start / end
+    uint8_t *is_rev = nullptr;
+    uint32_t *ex_beg = nullptr, *ex_n = nullptr;    // exon slots [ex_beg, ex_beg+ex_n) in the pools
+};
+struct DExons {
+    int64_t n = 0, cap = 0;
+    int32_t *es = nullptr, *ee = nullptr;
+    uint8_t *flag = nullptr;                        // LRB_F_* per slot (classification output)
+};
+
+struct ScanArgs {
+    DBatch b;
+    lrb_filter_params fp; lrb_exon_params ep;
+    DRmIndex rm;
+    int mode;                                       // 0 filter only, 1 exon only, 2 fused
+    const uint8_t *sel_mask;                        // mode 1: records to walk (NULL = all)
+    uint8_t *pass; int32_t *score, *intron_n;       // filter outputs (record level)
+    DRows rows; DExons ex;
+    uint64_t *tile_state; uint32_t *ticket;         // look-back state (zeroed per launch)
+    uint64_t *totals;                               // [0] rows, [1] exons
+    int reads_per_tile, stage_words;
+};
+
+void launch_cigar_scan(const ScanArgs &a, int n_tiles, bool warp_mode, size_t smem_bytes, cudaStream_t st);
+void launch_select_runs(const DBatch &b, const uint32_t *row_read, int64_t n_rows, const int32_t *score, const int32_t *intron_n,
+                        lrb_filter_params fp, uint8_t *keep_row_mask, uint8_t *keep_rec_mask, cudaStream_t st);
+// ordered compaction of the set positions of a byte mask: out[k] = index of k-th nonzero (optionally mapped through `map`)
+void launch_compact_mask(const uint8_t *mask, int64_t n, const uint32_t *map, uint32_t *out, uint32_t *out2_unmapped,
+                         uint64_t *tile_state, uint32_t *ticket, uint64_t *total, cudaStream_t st);
+void launch_gather_rows(const DRows &src, const uint32_t *sel, int64_t n_sel, DRows &dst, cudaStream_t st);
+
+// ---- classification
+struct ClassArgs {
+    DRows rows; DExons ex; DAnno anno; DSj sj;
+    lrb_update_params up;
+    uint32_t *cls; int32_t *ref;
+    uint32_t *n_novel;                              // per row: 0, 1 (whole read) or number of split pieces
+    uint32_t *err_flags;                            // bit0 unsorted, bit1 unmapped/empty chain
+};
+void launch_classify(const ClassArgs &a, cudaStream_t st);
+
+// ---- novel_T / known / unrecog lists + merge fold
+struct DTransList {                                 // transcript rows of a list (whole reads or split pieces)
+    int64_t n = 0, cap = 0;
+    uint32_t *row = nullptr, *lo = nullptr, *cnt = nullptr; int32_t *piece = nullptr;
+};
+struct ListArgs {
+    DRows rows; DExons ex; lrb_update_params up;
+    const uint32_t *cls; const uint32_t *n_novel;
+    DTransList novel; uint32_t *known, *unrecog;
+    uint64_t *tile_state; uint32_t *ticket; uint64_t *totals;   // [0] novel, [1] known, [2] unrecog
+};
+void launch_build_lists(const ListArgs &a, cudaStream_t st);
+
+struct DMerged {
+    int64_t n = 0, cap = 0;
+    uint32_t *cand = nullptr; int32_t *cov = nullptr, *tid = nullptr, *start = nullptr, *end = nullptr, *fs = nullptr, *le = nullptr;
+};
+struct MergeArgs {
+    DRows rows; DExons ex; lrb_update_params up;
+    DTransList list;                                // candidates in fold order
+    const uint32_t *subset;                         // optional: rows subset as whole-read candidates (list.n==0): indices into rows
+    int64_t n_cand;
+    // scratch
+    uint64_t *keys;                                 // per candidate (tid+1)<<32|real_end, then prefix max
+    uint8_t *head;                                  // locus head flags
+    uint32_t *locus_start;                          // compacted heads (+ sentinel)
+    DMerged work;                                   // per-candidate slots (T entries live at their locus' range)
+    uint32_t *locus_cnt;                            // surviving entries per locus
+    uint8_t *dropped;                               // per candidate: absorbed/dropped by the fold
+    DMerged out;                                    // compacted result
+    uint64_t *tile_state; uint32_t *ticket; uint64_t *totals;  // [0] n_loci, [1] n_out
+};
+void launch_merge_prepare(const MergeArgs &a, cudaStream_t st);     // keys + prefix max + heads
+void launch_merge_fold(const MergeArgs &a, int64_t n_loci, cudaStream_t st);
+void launch_merge_compact(const MergeArgs &a, int64_t n_loci, cudaStream_t st);
+
+// generic device scans used by the stages above
+void launch_scan_max_u64(uint64_t *data, int64_t n, uint64_t *tile_state, uint32_t *ticket, cudaStream_t st);   // inclusive prefix max, in place
+void launch_scan_sum_u32(const uint32_t *in, uint32_t *out_excl, int64_t n, uint64_t *tile_state, uint32_t *ticket, uint64_t *total, cudaStream_t st);
+
+int64_t count_launches();   // kernels launched by this library since load (every launch_* bumps it)
+
+}  // namespace lrbk

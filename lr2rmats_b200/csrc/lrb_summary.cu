@@ -1,0 +1,263 @@
+// lrb_summary.cu -- K6: the "sets" of print_trans_summary() (update_gtf.c:421-587) as data-parallel passes.
+//
+// The reference builds five sets over updated_T by back-scans that test for an equal key first and stop at the first
+// inserted entry with a smaller tid (add_simp_gene/_exon/_site/_sj, update_gtf.c:181-295).  For a tid-monotone stream
+// that is "distinct by key, payload of the first occurrence, insertion order".  Split pieces carry trans_t.tid == 0
+// (SURVEY Q14), which turns their gene / site / junction entries into barriers inside a chromosome block.  The exact
+// rule used here (derivation in DESIGN.md):
+//   * an element whose entry tid is 0 is inserted iff its key never occurred before among tid-0 elements
+//     (genes: among all elements, gene equality ignores tid);
+//   * an element with tid t > 0 is inserted iff no equal key occurred earlier within its segment, where a segment ends
+//     at every *inserted* tid-0 element of the same set (genes: and it does not equal the gene of that barrier element
+//     when the barrier lies inside the same chromosome block).
+// Both are first-occurrence queries, answered with one lock-free open-addressing table keyed by (set, segment, tid,
+// k1, k2) that keeps the minimum stream position per key; exon scores are atomically accumulated per key.
+#include "lrb_common.cuh"
+#include "lrb_kernels.cuh"
+#include "lrb_summary.cuh"
+
+namespace lrbk {
+
+extern int64_t g_launches_summary;
+int64_t g_launches_summary = 0;
+#define LRB_COUNT_LAUNCH() (++g_launches_summary)
+
+static constexpr uint64_t EMPTY = ~0ull;
+static constexpr uint32_t SEG_TID0 = 0x1FFFFFFEu;   // pseudo segment of the tid-0 phase
+
+LRB_DEVINL uint64_t mix64(uint64_t x) { x ^= x >> 33; x *= 0xFF51AFD7ED558CCDull; x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ull; x ^= x >> 33; return x; }
+LRB_DEVINL uint64_t key_hi(int set, uint32_t seg, int tid) { return ((uint64_t)(((uint32_t)set << 29) | (seg & 0x1FFFFFFFu)) << 32) | (uint32_t)tid; }
+LRB_DEVINL uint64_t key_lo(int k1, int k2) { return ((uint64_t)(uint32_t)k1 << 32) | (uint32_t)k2; }
+
+// insert-or-find; returns the slot
+LRB_DEVINL uint64_t tab_upsert(const HashTab &t, uint64_t hi, uint64_t lo)
+{
+    uint64_t s = mix64(hi * 0x9E3779B97F4A7C15ull ^ mix64(lo)) & t.mask;
+    for (;;) {
+        unsigned long long p = atomicCAS((unsigned long long *)&t.khi[s], (unsigned long long)EMPTY, (unsigned long long)hi);
+        if (p == EMPTY || p == hi) {
+            unsigned long long q = atomicCAS((unsigned long long *)&t.klo[s], (unsigned long long)EMPTY, (unsigned long long)lo);
+            if (q == EMPTY || q == lo) return s;
+        }
+        s = (s + 1) & t.mask;
+    }
+}
+LRB_DEVINL uint64_t tab_find(const HashTab &t, uint64_t hi, uint64_t lo)
+{
+    uint64_t s = mix64(hi * 0x9E3779B97F4A7C15ull ^ mix64(lo)) & t.mask;
+    for (;;) {
+        uint64_t a = t.khi[s];
+        if (a == hi && t.klo[s] == lo) return s;
+        if (a == EMPTY) return EMPTY;
+        s = (s + 1) & t.mask;
+    }
+}
+LRB_DEVINL void tab_min(const HashTab &t, uint64_t s, uint64_t pos) { atomicMin((unsigned long long *)&t.minpos[s], (unsigned long long)pos); }
+
+struct EntryView {
+    int n; uint32_t gbeg; int fs, le; int t_tid, real_tid, rev, cov, gene, piece; uint32_t row;
+};
+LRB_DEVINL EntryView load_entry(const SummaryArgs &a, int64_t i)
+{
+    EntryView e; uint32_t c = a.upd.cand[i];
+    e.row = a.list.row[c]; e.n = (int)a.list.cnt[c]; e.gbeg = a.rows.ex_beg[e.row] + a.list.lo[c];
+    e.fs = a.upd.fs[i]; e.le = a.upd.le[i]; e.t_tid = a.upd.tid[i]; e.real_tid = a.rows.tid[e.row];
+    e.rev = a.rows.is_rev[e.row]; e.cov = a.upd.cov[i]; e.piece = a.list.piece[c];
+    int ref = a.ref[e.row];
+    e.gene = ref >= 0 ? a.anno_gene[ref] : -1;
+    return e;
+}
+LRB_DEVINL int ent_s(const SummaryArgs &a, const EntryView &e, int j) { return j == 0 ? e.fs : a.ex.es[e.gbeg + j]; }
+LRB_DEVINL int ent_e(const SummaryArgs &a, const EntryView &e, int j) { return j == e.n - 1 ? e.le : a.ex.ee[e.gbeg + j]; }
+LRB_DEVINL uint64_t pos_of(int64_t i, int j) { return ((uint64_t)i << 20) | (uint32_t)j; }
+
+enum { SET_E = 0, SET_D = 1, SET_A = 2, SET_J = 3, SET_G = 4, SET_KG = 5 };
+
+// element counts per set (sizes the table) -- one thread per updated entry
+__global__ void sum_count_kernel(SummaryArgs a, unsigned long long *n_elems)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long c = 0;
+    if (i < a.n_upd) {
+        EntryView e = load_entry(a, i);
+        const uint8_t *f = a.ex.flag + e.gbeg;
+        c = 1;
+        for (int j = 0; j < e.n; ++j) {
+            uint8_t x = f[j];
+            c += (x & LRB_F_NOVEL_EXON) != 0;
+            if (j < e.n - 1) c += ((x & LRB_F_NOVEL_DON) != 0) + ((x & LRB_F_NOVEL_ACC) != 0) + ((x & LRB_F_NOVEL_JUNC) != 0);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+    if (lane_id() == 0 && c) atomicAdd(n_elems, c);
+}
+
+// phase 1: exons (all entries), tid-0 elements of D/A/J, every gene element (gene equality ignores tid)
+__global__ void sum_phase1_kernel(SummaryArgs a)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_upd) return;
+    EntryView e = load_entry(a, i);
+    const uint8_t *f = a.ex.flag + e.gbeg;
+    tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_G, SEG_TID0, 0), key_lo(e.gene, 0)), pos_of(i, 0));
+    for (int j = 0; j < e.n; ++j) {
+        uint8_t x = f[j];
+        if (x & LRB_F_NOVEL_EXON) {
+            uint64_t s = tab_upsert(a.tab, key_hi(SET_E, 0, e.real_tid), key_lo(ent_s(a, e, j), ent_e(a, e, j)));
+            tab_min(a.tab, s, pos_of(i, j));
+            atomicAdd(&a.tab.score[s], e.cov);
+        }
+        if (e.t_tid == 0 && j < e.n - 1) {
+            if (x & LRB_F_NOVEL_DON) tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_D, SEG_TID0, 0), key_lo(ent_e(a, e, j), 0)), pos_of(i, j));
+            if (x & LRB_F_NOVEL_ACC) tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_A, SEG_TID0, 0), key_lo(ent_s(a, e, j + 1), 0)), pos_of(i, j));
+            if (x & LRB_F_NOVEL_JUNC) tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_J, SEG_TID0, 0), key_lo(ent_e(a, e, j), ent_s(a, e, j + 1))), pos_of(i, j));
+        }
+    }
+}
+
+// phase 2: per entry, how many of its tid-0 elements were inserted (= barriers), per set; exon first occurrences
+__global__ void sum_phase2_kernel(SummaryArgs a)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_upd) return;
+    EntryView e = load_entry(a, i);
+    const uint8_t *f = a.ex.flag + e.gbeg;
+    uint32_t cd = 0, ca = 0, cj = 0, cg = 0, ce = 0;
+    if (e.t_tid == 0) {
+        uint64_t s = tab_find(a.tab, key_hi(SET_G, SEG_TID0, 0), key_lo(e.gene, 0));
+        cg = a.tab.minpos[s] == pos_of(i, 0);
+    }
+    for (int j = 0; j < e.n; ++j) {
+        uint8_t x = f[j];
+        if (x & LRB_F_NOVEL_EXON) {
+            uint64_t s = tab_find(a.tab, key_hi(SET_E, 0, e.real_tid), key_lo(ent_s(a, e, j), ent_e(a, e, j)));
+            ce += a.tab.minpos[s] == pos_of(i, j);
+        }
+        if (e.t_tid == 0 && j < e.n - 1) {
+            if (x & LRB_F_NOVEL_DON) cd += a.tab.minpos[tab_find(a.tab, key_hi(SET_D, SEG_TID0, 0), key_lo(ent_e(a, e, j), 0))] == pos_of(i, j);
+            if (x & LRB_F_NOVEL_ACC) ca += a.tab.minpos[tab_find(a.tab, key_hi(SET_A, SEG_TID0, 0), key_lo(ent_s(a, e, j + 1), 0))] == pos_of(i, j);
+            if (x & LRB_F_NOVEL_JUNC) cj += a.tab.minpos[tab_find(a.tab, key_hi(SET_J, SEG_TID0, 0), key_lo(ent_e(a, e, j), ent_s(a, e, j + 1)))] == pos_of(i, j);
+        }
+    }
+    a.bar_cnt[0 * a.n_upd + i] = cd; a.bar_cnt[1 * a.n_upd + i] = ca; a.bar_cnt[2 * a.n_upd + i] = cj; a.bar_cnt[3 * a.n_upd + i] = cg;
+    a.bed_cnt[i] = ce;
+    a.gene_bar[i] = cg ? (uint64_t)(i + 1) : 0;       // for the "last inserted tid-0 gene entry before x" max-scan
+    if (cd | ca | cj | cg) {
+        if (cd) atomicAdd(&a.counts[SET_D], cd);
+        if (ca) atomicAdd(&a.counts[SET_A], ca);
+        if (cj) atomicAdd(&a.counts[SET_J], cj);
+        if (cg) atomicAdd(&a.counts[SET_G], cg);
+    }
+    if (ce) atomicAdd(&a.counts[SET_E], ce);
+    if (e.piece >= 0) atomicAdd(&a.counts[6], 1u);   // partial-read transcripts
+}
+
+// phase 3: tid>0 elements go into their segment
+__global__ void sum_phase3_kernel(SummaryArgs a)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_upd) return;
+    EntryView e = load_entry(a, i);
+    if (e.t_tid == 0) return;
+    const uint8_t *f = a.ex.flag + e.gbeg;
+    const uint32_t sd = a.bar_seg[0 * a.n_upd + i], sa = a.bar_seg[1 * a.n_upd + i], sj = a.bar_seg[2 * a.n_upd + i], sg = a.bar_seg[3 * a.n_upd + i];
+    tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_G, sg, e.t_tid), key_lo(e.gene, 0)), pos_of(i, 0));
+    for (int j = 0; j < e.n - 1; ++j) {
+        uint8_t x = f[j];
+        if (x & LRB_F_NOVEL_DON) tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_D, sd, e.t_tid), key_lo(ent_e(a, e, j), 0)), pos_of(i, j));
+        if (x & LRB_F_NOVEL_ACC) tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_A, sa, e.t_tid), key_lo(ent_s(a, e, j + 1), 0)), pos_of(i, j));
+        if (x & LRB_F_NOVEL_JUNC) tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_J, sj, e.t_tid), key_lo(ent_e(a, e, j), ent_s(a, e, j + 1))), pos_of(i, j));
+    }
+}
+__global__ void sum_phase4_kernel(SummaryArgs a)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_upd) return;
+    EntryView e = load_entry(a, i);
+    if (e.t_tid == 0) return;
+    const uint8_t *f = a.ex.flag + e.gbeg;
+    const uint32_t sd = a.bar_seg[0 * a.n_upd + i], sa = a.bar_seg[1 * a.n_upd + i], sj = a.bar_seg[2 * a.n_upd + i], sg = a.bar_seg[3 * a.n_upd + i];
+    uint32_t cd = 0, ca = 0, cj = 0, cg = 0;
+    {
+        uint64_t s = tab_find(a.tab, key_hi(SET_G, sg, e.t_tid), key_lo(e.gene, 0));
+        bool first = a.tab.minpos[s] == pos_of(i, 0);
+        uint64_t bar = a.gene_bar[i];                // index+1 of the last inserted tid-0 gene entry before i (inclusive scan, own value 0)
+        if (first && bar) {
+            EntryView b = load_entry(a, (int64_t)bar - 1);
+            if (b.real_tid == e.t_tid && b.gene == e.gene) first = false;     // equal to the barrier itself (match precedes stop)
+        }
+        cg = first;
+    }
+    for (int j = 0; j < e.n - 1; ++j) {
+        uint8_t x = f[j];
+        if (x & LRB_F_NOVEL_DON) cd += a.tab.minpos[tab_find(a.tab, key_hi(SET_D, sd, e.t_tid), key_lo(ent_e(a, e, j), 0))] == pos_of(i, j);
+        if (x & LRB_F_NOVEL_ACC) ca += a.tab.minpos[tab_find(a.tab, key_hi(SET_A, sa, e.t_tid), key_lo(ent_s(a, e, j + 1), 0))] == pos_of(i, j);
+        if (x & LRB_F_NOVEL_JUNC) cj += a.tab.minpos[tab_find(a.tab, key_hi(SET_J, sj, e.t_tid), key_lo(ent_e(a, e, j), ent_s(a, e, j + 1)))] == pos_of(i, j);
+    }
+    if (cd) atomicAdd(&a.counts[SET_D], cd);
+    if (ca) atomicAdd(&a.counts[SET_A], ca);
+    if (cj) atomicAdd(&a.counts[SET_J], cj);
+    if (cg) atomicAdd(&a.counts[SET_G], cg);
+}
+
+// BED rows: first occurrences of the exon set in stream order (bed_off = exclusive scan of bed_cnt)
+__global__ void sum_bed_kernel(SummaryArgs a)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_upd || a.bed_cnt[i] == 0) return;
+    EntryView e = load_entry(a, i);
+    const uint8_t *f = a.ex.flag + e.gbeg;
+    uint32_t o = a.bed_off[i];
+    for (int j = 0; j < e.n; ++j) {
+        if (!(f[j] & LRB_F_NOVEL_EXON)) continue;
+        int s0 = ent_s(a, e, j), e0 = ent_e(a, e, j);
+        uint64_t s = tab_find(a.tab, key_hi(SET_E, 0, e.real_tid), key_lo(s0, e0));
+        if (a.tab.minpos[s] != pos_of(i, j)) continue;
+        a.bed_tid[o] = e.real_tid; a.bed_start[o] = s0; a.bed_end[o] = e0; a.bed_score[o] = a.tab.score[s];
+        a.bed_type[o] = e.n > 1 ? ((j == 0 || j == e.n - 1) ? 0 : 1) : 2; a.bed_rev[o] = (uint8_t)e.rev;
+        ++o;
+    }
+}
+
+// genes of the known reads (update_gtf.c:503-506): distinct (tid, gene) over bam_T rows flagged known
+__global__ void sum_known_genes_kernel(SummaryArgs a, const uint32_t *__restrict__ cls, int64_t n_rows, int pass)
+{
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows || !(cls[r] & LRB_C_KNOWN)) return;
+    int ref = a.ref[r]; int gene = ref >= 0 ? a.anno_gene[ref] : -1;
+    uint64_t hi = key_hi(SET_KG, 0, a.rows.tid[r]), lo = key_lo(gene, 0);
+    if (pass == 0) tab_min(a.tab, tab_upsert(a.tab, hi, lo), (uint64_t)r);
+    else if (a.tab.minpos[tab_find(a.tab, hi, lo)] == (uint64_t)r) atomicAdd(&a.counts[SET_KG], 1u);
+}
+
+static inline unsigned nblk(int64_t n) { return (unsigned)((n + 255) / 256); }
+
+void launch_summary_count(const SummaryArgs &a, unsigned long long *n_elems, cudaStream_t st)
+{
+    if (a.n_upd <= 0) return;
+    sum_count_kernel<<<nblk(a.n_upd), 256, 0, st>>>(a, n_elems); LRB_COUNT_LAUNCH();
+}
+void launch_summary_sets(const SummaryArgs &a, const uint32_t *cls, int64_t n_rows, uint64_t *tile_state, uint32_t *ticket, uint64_t *bed_total, cudaStream_t st)
+{
+    if (a.n_upd > 0) {
+        sum_phase1_kernel<<<nblk(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
+        sum_phase2_kernel<<<nblk(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
+        for (int s = 0; s < 4; ++s)
+            launch_scan_sum_u32(a.bar_cnt + (int64_t)s * a.n_upd, a.bar_seg + (int64_t)s * a.n_upd, a.n_upd, tile_state, ticket, nullptr, st);
+        launch_scan_max_u64(a.gene_bar, a.n_upd, tile_state, ticket, st);
+        launch_scan_sum_u32(a.bed_cnt, a.bed_off, a.n_upd, tile_state, ticket, bed_total, st);
+        sum_phase3_kernel<<<nblk(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
+        sum_phase4_kernel<<<nblk(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
+    } else cudaMemsetAsync(bed_total, 0, 8, st);
+    if (n_rows > 0) {
+        sum_known_genes_kernel<<<nblk(n_rows), 256, 0, st>>>(a, cls, n_rows, 0); LRB_COUNT_LAUNCH();
+        sum_known_genes_kernel<<<nblk(n_rows), 256, 0, st>>>(a, cls, n_rows, 1); LRB_COUNT_LAUNCH();
+    }
+}
+void launch_summary_bed(const SummaryArgs &a, cudaStream_t st)
+{
+    if (a.n_upd <= 0) return;
+    sum_bed_kernel<<<nblk(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
+}
+
+}  // namespace lrbk

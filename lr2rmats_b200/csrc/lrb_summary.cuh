@@ -1,0 +1,35 @@
+// lrb_summary.cuh -- argument blocks of the summary-set kernels (lrb_summary.cu)
+#pragma once
+#include "lrb_kernels.cuh"
+
+namespace lrbk {
+
+struct HashTab {                                    // open addressing, 128-bit keys, all words memset to 0xFF when empty
+    uint64_t mask = 0;
+    uint64_t *khi = nullptr, *klo = nullptr, *minpos = nullptr;
+    int32_t *score = nullptr;                       // zeroed
+};
+
+struct SummaryArgs {
+    DRows rows; DExons ex; DTransList list; DMerged upd; int64_t n_upd;
+    const int32_t *ref; const int32_t *anno_gene;
+    HashTab tab;
+    uint32_t *bar_cnt, *bar_seg;                    // [4][n_upd]: inserted tid-0 elements per entry / their exclusive scan
+    uint64_t *gene_bar;                             // [n_upd]
+    uint32_t *bed_cnt, *bed_off;                    // [n_upd]
+    uint32_t *counts;                               // [8]: E D A J G KG partial -
+    int32_t *bed_tid, *bed_start, *bed_end, *bed_score; uint8_t *bed_type, *bed_rev;
+};
+
+void launch_summary_count(const SummaryArgs &a, unsigned long long *n_elems, cudaStream_t st);
+void launch_summary_sets(const SummaryArgs &a, const uint32_t *cls, int64_t n_rows, uint64_t *tile_state, uint32_t *ticket, uint64_t *bed_total, cudaStream_t st);
+void launch_summary_bed(const SummaryArgs &a, cudaStream_t st);
+
+// from lrb_update.cu
+void launch_class_masks(const uint32_t *cls, int64_t n, uint8_t *m_known, uint8_t *m_unrecog, uint8_t *c_known, uint8_t *c_rel,
+                        uint8_t *c_unrel, uint8_t *c_unrec, cudaStream_t st);
+void launch_emit_novel(const ListArgs &a, const uint32_t *novel_off, cudaStream_t st);
+void launch_rows_as_list(const DRows &rows, const uint32_t *subset, int64_t n, DTransList &out, cudaStream_t st);
+void launch_merge_gather(const MergeArgs &a, int64_t n_out, cudaStream_t st);
+
+}  // namespace lrbk

@@ -1,0 +1,461 @@
+// lrb_update.cu -- K3/K4/K5: classification against the annotation, short-read SJ support, split pieces, and the
+// locus-parallel greedy merge fold.
+//
+// Replaces, for all reads at once:
+//   check_with_anno_trans / comp_trans / check_full / set_full / check_splice_site   update_gtf.c:629-696,717-835
+//   check_with_short_sj / check_short_sj / check_short_sj1                           update_gtf.c:589-627,698-709
+//   split_trans                                                                       update_gtf.c:837-913
+//   merge_trans / merge_trans1 / merge_trans2 + check_iden                            update_gtf.c:98-163, gtf.c:54-92
+//
+// The reference's two monotone cursors are replaced by closed forms over prefix-max keys, which
+// makes every read independent; the order-dependent merge fold is exact per locus (App. A.6/B.3) and loci run in
+// parallel, one warp each, the warp evaluating a whole window of the back-scan per step.
+#include "lrb_common.cuh"
+#include "lrb_kernels.cuh"
+
+namespace lrbk {
+
+extern int64_t g_launches_update;
+int64_t g_launches_update = 0;
+#define LRB_COUNT_LAUNCH() (++g_launches_update)
+
+static constexpr int CL_THREADS = 256;
+static constexpr int CL_G = 8;                      // lanes per read
+static constexpr int CL_SLOTS = 64;                 // exon slots per read staged in shared memory
+
+LRB_DEVINL bool ex_ovlp(int s1, int e1, int s2, int e2) { return !(s1 > e2 || s2 > e1); }
+// exon_overlap_frac (update_gtf.c:80-89): double quotient rounded to float
+LRB_DEVINL float ovlp_frac(int s1, int e1, int s2, int e2)
+{
+    if (s1 > e2 || s2 > e1) return 0.0f;
+    int ov = min(e1, e2) - max(s1, s2) + 1;
+    int ml = min(e1 - s1 + 1, e2 - s2 + 1);
+    return (float)__ddiv_rn((double)ov, (double)ml + 0.0);
+}
+
+template <int G>
+__global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a)
+{
+    constexpr int GPB = CL_THREADS / G;
+    __shared__ int s_es[GPB][CL_SLOTS], s_ee[GPB][CL_SLOTS];
+    __shared__ uint8_t s_fl[GPB][CL_SLOTS];
+    const int g = threadIdx.x / G, gl = threadIdx.x % G;
+    const unsigned gm = group_mask<G>();
+    const int dis = a.up.ss_dis, level = a.up.full_level;
+
+    for (int64_t row = (int64_t)blockIdx.x * GPB + g; row < a.rows.n; row += (int64_t)gridDim.x * GPB) {
+        const int n = (int)a.rows.ex_n[row];
+        const uint32_t beg = a.rows.ex_beg[row];
+        const int tid_b = a.rows.tid[row], start_b = a.rows.start[row], end_b = a.rows.end[row];
+        if (n == 0) { if (gl == 0) { atomicOr(a.err_flags, 2u); a.cls[row] = 0; a.ref[row] = -1; a.n_novel[row] = 0; } continue; }
+        if (row > 0 && gl == 0) {
+            int pt = a.rows.tid[row - 1], ps = a.rows.start[row - 1];
+            if (pt > tid_b || (pt == tid_b && ps > start_b)) atomicOr(a.err_flags, 1u);
+        }
+        // exon chain + flags: shared memory when it fits, else straight on the HBM arrays
+        const bool in_smem = n <= CL_SLOTS;
+        int *es = in_smem ? s_es[g] : a.ex.es + beg, *ee = in_smem ? s_ee[g] : a.ex.ee + beg;
+        uint8_t *fl = in_smem ? s_fl[g] : a.ex.flag + beg;
+        __syncwarp(gm);
+        for (int j = gl; j < n; j += G) {
+            if (in_smem) { es[j] = a.ex.es[beg + j]; ee[j] = a.ex.ee[beg + j]; }
+            fl[j] = (j < n - 1) ? (LRB_F_NOVEL_EXON | LRB_F_NOVEL_DON | LRB_F_NOVEL_ACC | LRB_F_NOVEL_JUNC) : LRB_F_NOVEL_EXON;
+        }
+        __syncwarp(gm);
+        const int b0s = es[0], b0e = ee[0], bls = es[n - 1], ble = ee[n - 1];
+
+        // ---- annotation window: F(b) by binary search on the prefix-max keys, sweep to the first "after"
+        const uint64_t key_b = ((uint64_t)(uint32_t)(tid_b + 1) << 32) | (uint32_t)start_b;
+        int i = (int)upper_bound_dev<uint64_t>(a.anno.pmax_key, 0, a.anno.n, key_b);
+        int lfull = 0, rfull = 0, lnoth = 1, rnoth = 1, known = 0, known_site = 0, ref = -1;
+        for (; i < a.anno.n; ++i) {
+            const int at = a.anno.tid[i], as_ = a.anno.start[i], ae_ = a.anno.end[i];
+            if (tid_b < at || (tid_b == at && end_b <= as_)) break;                       // comp_trans < 0
+            if (at < tid_b || (at == tid_b && ae_ <= start_b)) continue;                  // comp_trans > 0
+            const uint32_t ao = a.anno.exon_off[i]; const int na = (int)(a.anno.exon_off[i + 1] - ao);
+            const int *xs = a.anno.es + ao, *xe = a.anno.ee + ao;
+            // check_full, update_gtf.c:629-681
+            if (!(lfull && rfull) && level <= 4) {
+                const int a0s = xs[0], a0e = xe[0], als = xs[na - 1], ale = xe[na - 1];
+                if (level == 1) {
+                    if (!lfull && b0e == a0e) lfull = 1;
+                    if (!rfull && bls == als) rfull = 1;
+                } else if (level == 2) {
+                    if (!lfull && ex_ovlp(b0s, b0e, a0s, a0e)) lfull = 1;
+                    if (!rfull && ex_ovlp(bls, ble, als, ale)) rfull = 1;
+                } else if (level == 3 || level == 4) {
+                    if (!lfull) {
+                        if (ex_ovlp(b0s, b0e, a0s, a0e)) lfull = 1;
+                        else if (lnoth) {
+                            int any = 0;
+                            for (int ii = gl; ii < na; ii += G) any |= ex_ovlp(b0s, b0e, xs[ii], xe[ii]);
+                            if (group_or<G>(gm, any)) lnoth = 0;
+                        }
+                    }
+                    if (level == 3 && !rfull) {
+                        if (ex_ovlp(bls, ble, als, ale)) rfull = 1;
+                        else if (rnoth) {
+                            int any = 0;
+                            for (int ii = gl; ii < na; ii += G) any |= ex_ovlp(bls, ble, xs[ii], xe[ii]);
+                            if (group_or<G>(gm, any)) rnoth = 0;
+                        }
+                    }
+                }
+            }
+            if (n == 1 && na == 1) {                                                       // update_gtf.c:806-811
+                if (ovlp_frac(b0s, b0e, xs[0], xe[0]) >= a.up.single_exon_ovlp_frac) { ref = i; known = 1; break; }
+            } else if (n > 1 && na > 1) {                                                  // check_splice_site :717-779
+                const int os = max(start_b, as_), oe = min(end_b, ae_);
+                int ovl = 0, iden = 0;
+                for (int j = gl; j < n - 1; j += G) {
+                    int e = ee[j], s = es[j + 1];
+                    ovl += (e >= os && e <= oe) + (s >= os && s <= oe);
+                }
+                for (int k = 0; k < na; ++k) {
+                    const int a_s = xs[k], a_e = xe[k];
+                    const bool has_next = k < na - 1;
+                    const int a_sn = has_next ? xs[k + 1] : 0;
+                    const bool don_ok = has_next && a_e >= os && a_e <= oe;
+                    const bool acc_ok = k >= 1 && a_s >= os && a_s <= oe;
+                    for (int j = gl; j < n; j += G) {
+                        const int bs = es[j], be = ee[j];
+                        uint8_t f = fl[j], f0 = f;
+                        const bool de = iabs_dev(a_e - be) <= dis, ds = iabs_dev(a_s - bs) <= dis;
+                        if (j < n - 1) {
+                            if (don_ok && de) { ++iden; f &= ~LRB_F_NOVEL_DON; }
+                            if (acc_ok && ds) { ++iden; f &= ~LRB_F_NOVEL_ACC; }
+                            if (has_next && de && iabs_dev(a_sn - es[j + 1]) <= dis) f &= ~LRB_F_NOVEL_JUNC;
+                        }
+                        if (ds && de) f &= ~LRB_F_NOVEL_EXON;
+                        if (f != f0) fl[j] = f;
+                    }
+                }
+                ovl = group_sum<G>(gm, ovl); iden = group_sum<G>(gm, iden);
+                if (2 * (n - 1) == ovl && ovl == iden) { known = 1; ref = i; break; }
+                else if (iden > 0) { known_site = 1; ref = i; }
+            }
+        }
+        int is_rev = a.rows.is_rev[row];
+        if (ref != -1) is_rev = a.anno.is_rev[ref];                                       // update_gtf.c:823-833
+        int full;                                                                          // set_full :683-696
+        if (level == 5) full = 1;
+        else if (level == 4) full = (lfull || lnoth);
+        else if (level == 3) full = ((lfull || lnoth) && (rfull || rnoth));
+        else full = (lfull && rfull);
+        __syncwarp(gm);
+
+        // ---- short-read SJ support, update_gtf.c:589-627,698-709 (cursor closed form, App. B.2)
+        int sj_checked = 0, unreliable = 0;
+        if (full && !known && known_site && a.sj.n > 0) {
+            sj_checked = 1;
+            int64_t S = upper_bound_dev<uint64_t>(a.sj.pmax_key, 0, a.sj.n, key_b);
+            int ok = 1;
+            if (S >= a.sj.n) ok = 0;
+            else {
+                int st = a.sj.tid[S];
+                if (st > tid_b || (st == tid_b && a.sj.don[S] >= end_b)) ok = 0;
+                else {
+                    int bad = 0;
+                    const uint64_t tk = (uint64_t)(uint32_t)(tid_b + 1) << 32;
+                    for (int j = gl; j < n - 1; j += G) {
+                        if (!(fl[j] & LRB_F_NOVEL_JUNC)) continue;
+                        const int is = ee[j] + 1, ie = es[j + 1] - 1;                      // intron [is, ie]
+                        // rows with tid==tid_b, don in [is-dis, is+dis], don < ie, index >= S
+                        int dlo = is - dis; if (dlo < 0) dlo = 0;
+                        int64_t dhi = (int64_t)is + dis + 1; if (dhi > ie) dhi = ie; if (dhi < 0) dhi = 0;
+                        int64_t lo = lower_bound_dev<uint64_t>(a.sj.don_key, S, a.sj.n, tk | (uint32_t)dlo);
+                        int64_t hi = lower_bound_dev<uint64_t>(a.sj.don_key, lo, a.sj.n, tk | (uint64_t)dhi);
+                        int found = 0;
+                        for (int64_t q = lo; q < hi && !found; ++q) {
+                            if (iabs_dev(a.sj.acc[q] - ie) <= dis) {
+                                int c = a.up.use_multi ? a.sj.cnt_u[q] + a.sj.cnt_m[q] : a.sj.cnt_u[q];
+                                if (c >= a.up.min_sj_cnt) found = 1;
+                            }
+                        }
+                        if (!found) { fl[j] |= LRB_F_UNRELIABLE; bad = 1; }
+                    }
+                    if (group_or<G>(gm, bad)) ok = 0;
+                }
+            }
+            unreliable = !ok;
+        }
+        __syncwarp(gm);
+
+        // ---- novel_T contribution: the read itself, or its split pieces (split_trans :837-913)
+        uint32_t nn = 0;
+        if (full && !known && known_site) {
+            if (!sj_checked || !unreliable) nn = 1;
+            else if (a.up.split_trans && gl == 0) {
+                int last = 0, has_novel = 0, has_known = 0;
+                for (int k = 0; k <= n - 1; ++k) {
+                    bool at_end = k == n - 1;
+                    uint8_t f = fl[k];
+                    if (!at_end) { if (f & LRB_F_NOVEL_JUNC) has_novel = 1; else has_known = 1; }
+                    if (at_end || (f & LRB_F_UNRELIABLE)) {
+                        if (has_novel && has_known && k - last >= 1) ++nn;
+                        last = k + 1; has_novel = 0; has_known = 0;
+                    }
+                }
+            }
+        }
+        if (in_smem) for (int j = gl; j < n; j += G) a.ex.flag[beg + j] = fl[j];
+        if (gl == 0) {
+            a.cls[row] = (known ? LRB_C_KNOWN : 0) | (known_site ? LRB_C_KNOWN_SITE : 0) | (unreliable ? LRB_C_UNRELIABLE : 0) |
+                         (full ? LRB_C_FULL : 0) | (lfull ? LRB_C_LFULL : 0) | (rfull ? LRB_C_RFULL : 0) | (lnoth ? LRB_C_LNOTH : 0) |
+                         (rnoth ? LRB_C_RNOTH : 0) | (sj_checked ? LRB_C_SJ_CHECKED : 0);
+            a.ref[row] = ref;
+            a.rows.is_rev[row] = (uint8_t)is_rev;
+            a.n_novel[row] = nn;
+        }
+    }
+}
+
+void launch_classify(const ClassArgs &a, cudaStream_t st)
+{
+    if (a.rows.n <= 0) return;
+    constexpr int GPB = CL_THREADS / CL_G;
+    int64_t bl = (a.rows.n + GPB - 1) / GPB;
+    if (bl > 148 * 64) bl = 148 * 64;
+    classify_kernel<CL_G><<<(unsigned)bl, CL_THREADS, 0, st>>>(a);
+    LRB_COUNT_LAUNCH();
+}
+
+// ------------------------------------------------------------------------------------ novel_T rows (reads / pieces)
+__global__ void emit_novel_kernel(ListArgs a, const uint32_t *__restrict__ novel_off)
+{
+    int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= a.rows.n) return;
+    uint32_t nn = a.n_novel[row];
+    if (!nn) return;
+    uint32_t o = novel_off[row];
+    const int n = (int)a.rows.ex_n[row];
+    uint32_t c = a.cls[row];
+    if (!((c & LRB_C_SJ_CHECKED) && (c & LRB_C_UNRELIABLE))) {
+        a.novel.row[o] = (uint32_t)row; a.novel.lo[o] = 0; a.novel.cnt[o] = (uint32_t)n; a.novel.piece[o] = -1;
+        return;
+    }
+    const uint8_t *fl = a.ex.flag + a.rows.ex_beg[row];
+    int last = 0, has_novel = 0, has_known = 0, k2 = 0;
+    for (int k = 0; k <= n - 1; ++k) {
+        bool at_end = k == n - 1;
+        uint8_t f = fl[k];
+        if (!at_end) { if (f & LRB_F_NOVEL_JUNC) has_novel = 1; else has_known = 1; }
+        if (at_end || (f & LRB_F_UNRELIABLE)) {
+            if (has_novel && has_known && k - last >= 1) {
+                a.novel.row[o] = (uint32_t)row; a.novel.lo[o] = (uint32_t)last; a.novel.cnt[o] = (uint32_t)(k - last + 1); a.novel.piece[o] = k2;
+                ++o; ++k2;
+            }
+            last = k + 1; has_novel = 0; has_known = 0;
+        }
+    }
+}
+
+__global__ void class_masks_kernel(const uint32_t *__restrict__ cls, int64_t n, uint8_t *m_known, uint8_t *m_unrecog,
+                                   uint8_t *c_known, uint8_t *c_rel, uint8_t *c_unrel, uint8_t *c_unrec)
+{
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    uint32_t c = cls[r];
+    bool full = c & LRB_C_FULL, known = c & LRB_C_KNOWN, ks = c & LRB_C_KNOWN_SITE, ur = c & LRB_C_UNRELIABLE;
+    m_known[r] = full && known; m_unrecog[r] = full && !known && !ks;
+    if (c_known) { c_known[r] = known; c_rel[r] = !known && ks && !ur; c_unrel[r] = !known && ks && ur; c_unrec[r] = !known && !ks; }
+}
+void launch_class_masks(const uint32_t *cls, int64_t n, uint8_t *m_known, uint8_t *m_unrecog, uint8_t *c_known, uint8_t *c_rel,
+                        uint8_t *c_unrel, uint8_t *c_unrec, cudaStream_t st)
+{
+    if (n <= 0) return;
+    class_masks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cls, n, m_known, m_unrecog, c_known, c_rel, c_unrel, c_unrec);
+    LRB_COUNT_LAUNCH();
+}
+void launch_emit_novel(const ListArgs &a, const uint32_t *novel_off, cudaStream_t st)
+{
+    if (a.rows.n <= 0) return;
+    emit_novel_kernel<<<(unsigned)((a.rows.n + 255) / 256), 256, 0, st>>>(a, novel_off);
+    LRB_COUNT_LAUNCH();
+}
+
+__global__ void rows_as_list_kernel(DRows rows, const uint32_t *__restrict__ subset, int64_t n, DTransList out)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t row = subset ? subset[k] : (uint32_t)k;
+    out.row[k] = row; out.lo[k] = 0; out.cnt[k] = rows.ex_n[row]; out.piece[k] = -1;
+}
+void launch_rows_as_list(const DRows &rows, const uint32_t *subset, int64_t n, DTransList &out, cudaStream_t st)
+{
+    if (n <= 0) return;
+    rows_as_list_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows, subset, n, out);
+    LRB_COUNT_LAUNCH();
+}
+
+// --------------------------------------------------------------------------------------------------- merge fold
+struct Cand {                                       // one transcript entering the fold
+    int tid, start, end, rev;                       // trans_t fields (0/0/0/0 for split pieces)
+    int n; uint32_t gbeg;                           // exon slots [gbeg, gbeg+n) in the pools
+    int fs, le;                                     // exon[0].start, exon[n-1].end
+};
+LRB_DEVINL Cand load_cand(const DRows &rows, const DExons &ex, const DTransList &L, int64_t c)
+{
+    Cand t; uint32_t row = L.row[c];
+    t.n = (int)L.cnt[c]; t.gbeg = rows.ex_beg[row] + L.lo[c];
+    t.fs = ex.es[t.gbeg]; t.le = ex.ee[t.gbeg + t.n - 1];
+    if (L.piece[c] >= 0) { t.tid = 0; t.start = 0; t.end = 0; t.rev = 0; }
+    else { t.tid = rows.tid[row]; t.start = t.fs; t.end = t.le; t.rev = rows.is_rev[row]; }
+    return t;
+}
+
+__global__ void merge_keys_kernel(MergeArgs a)
+{
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_cand) return;
+    uint32_t row = a.list.row[c];
+    uint32_t gb = a.rows.ex_beg[row] + a.list.lo[c];
+    int real_end = a.ex.ee[gb + a.list.cnt[c] - 1];
+    a.keys[c] = ((uint64_t)(uint32_t)(a.rows.tid[row] + 1) << 32) | (uint32_t)real_end;
+}
+__global__ void merge_heads_kernel(MergeArgs a)
+{
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_cand) return;
+    uint32_t row = a.list.row[c];
+    uint32_t gb = a.rows.ex_beg[row] + a.list.lo[c];
+    uint64_t k = ((uint64_t)(uint32_t)(a.rows.tid[row] + 1) << 32) | (uint32_t)a.ex.es[gb];
+    a.head[c] = (c == 0 || k > a.keys[c - 1]) ? 1 : 0;   // new locus: start beyond every earlier end on this chromosome
+}
+void launch_merge_prepare(const MergeArgs &a, cudaStream_t st)
+{
+    if (a.n_cand <= 0) { cudaMemsetAsync(a.totals, 0, 16, st); return; }
+    unsigned bl = (unsigned)((a.n_cand + 255) / 256);
+    merge_keys_kernel<<<bl, 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
+    launch_scan_max_u64(a.keys, a.n_cand, a.tile_state, a.ticket, st);
+    merge_heads_kernel<<<bl, 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
+    launch_compact_mask(a.head, a.n_cand, nullptr, a.locus_start, nullptr, a.tile_state, a.ticket, a.totals, st);
+}
+
+// check_iden (gtf.c:54-92) between candidate t and fold entry E (first start / last end may have been extended)
+struct Entry { int n; uint32_t gbeg; int fs, le; };
+LRB_DEVINL int x_s(const DExons &ex, const Entry &e, int i) { return i == 0 ? e.fs : ex.es[e.gbeg + i]; }
+LRB_DEVINL int x_e(const DExons &ex, const Entry &e, int i) { return i == e.n - 1 ? e.le : ex.ee[e.gbeg + i]; }
+LRB_DEVINL int chain_iden(const DExons &ex, const Entry &t1, const Entry &t2, int ss_dis, int end_dis)
+{
+    const Entry &l = t1.n >= t2.n ? t1 : t2, &s = t1.n >= t2.n ? t2 : t1;
+    if (t1.n == t2.n) {
+        if (iabs_dev(l.fs - s.fs) > end_dis) return -1;
+        for (int i = 0; i < l.n - 1; ++i) {
+            if (iabs_dev(x_e(ex, l, i) - x_e(ex, s, i)) > ss_dis) return -1;
+            if (iabs_dev(x_s(ex, l, i + 1) - x_s(ex, s, i + 1)) > ss_dis) return -1;
+        }
+        if (iabs_dev(l.le - s.le) > end_dis) return -1;
+        return 0;
+    }
+    int pm = -1;
+    if (iabs_dev(l.fs - s.fs) > end_dis) return -1;
+    const int s_e0 = x_e(ex, s, 0), s_s1 = x_s(ex, s, 1);
+    for (int i = 0; i < l.n - 1; ++i) {
+        if (iabs_dev(x_e(ex, l, i) - s_e0) <= ss_dis && iabs_dev(x_s(ex, l, i + 1) - s_s1) <= ss_dis) {
+            pm = 2;
+            int j = 1;
+            for (i = i + 1; i < l.n - 1 && j < s.n - 1; ++i, ++j) {
+                if (iabs_dev(x_e(ex, l, i) - x_e(ex, s, j)) > ss_dis) return -1;
+                if (iabs_dev(x_s(ex, l, i + 1) - x_s(ex, s, j + 1)) > ss_dis) return -1;
+            }
+            break;
+        }
+    }
+    if (iabs_dev(l.le - s.le) > end_dis) return -1;
+    return pm;
+}
+
+static constexpr int MF_WARPS = 4;
+// one warp per locus; tlist[ls + k] = candidate index of the k-th entry of the locus' T; entry data lives at work[cand]
+__global__ void __launch_bounds__(MF_WARPS * 32) merge_fold_kernel(MergeArgs a, int64_t n_loci, uint32_t *tlist, uint8_t *alive)
+{
+    const int lane = lane_id();
+    for (int64_t loc = (int64_t)blockIdx.x * MF_WARPS + warp_id(); loc < n_loci; loc += (int64_t)gridDim.x * MF_WARPS) {
+        const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : a.n_cand;
+        int cnt = 0;
+        for (int64_t c = ls; c < le; ++c) {
+            const Cand t = load_cand(a.rows, a.ex, a.list, c);
+            const Entry te = {t.n, t.gbeg, t.fs, t.le};
+            int result = 0;                                      // 0 append, 1 absorbed / dropped
+            for (int base = cnt - 1; base >= 0; base -= 32) {
+                const int k = base - lane;
+                int ev = 0;                                      // 1 stop, 2 merge (identical), 3 drop (partial)
+                uint32_t ec = 0;
+                if (k >= 0) {
+                    ec = tlist[ls + k];
+                    const int e_tid = a.work.tid[ec], e_end = a.work.end[ec];
+                    if (t.tid > e_tid || t.start > e_end) ev = 1;                                     // update_gtf.c:148
+                    else {
+                        const uint32_t erow = a.list.row[ec];
+                        const int e_rev = a.list.piece[ec] >= 0 ? 0 : a.rows.is_rev[erow];
+                        if (!(a.up.force_strand && t.rev != e_rev)) {                                 // :149
+                            Entry E = {(int)a.list.cnt[ec], a.rows.ex_beg[erow] + a.list.lo[ec], a.work.fs[ec], a.work.le[ec]};
+                            if (t.n == 1 && E.n == 1) {                                               // merge_trans2 :122-140
+                                if (iabs_dev(t.fs - E.fs) <= a.up.end_dis && iabs_dev(t.le - E.le) <= a.up.end_dis &&
+                                    ovlp_frac(t.fs, t.le, E.fs, E.le) >= a.up.single_exon_ovlp_frac) ev = 2;
+                            } else if (t.n > 1 && E.n > 1) {                                          // merge_trans1 :98-119
+                                int r = chain_iden(a.ex, te, E, a.up.ss_dis, a.up.end_dis);
+                                if (r == 0) ev = 2; else if (r == 2) ev = 3;
+                            }
+                        }
+                    }
+                }
+                const unsigned m = __ballot_sync(FULL, ev != 0);
+                if (m) {
+                    const int win = __ffs(m) - 1;                // lowest lane = entry nearest to the end of T
+                    const int wev = __shfl_sync(FULL, ev, win);
+                    if (wev == 2 && lane == win) {
+                        a.work.cov[ec] += 1;
+                        if (t.fs < a.work.fs[ec]) { a.work.fs[ec] = t.fs; a.work.start[ec] = t.fs; }
+                        if (t.le > a.work.le[ec]) { a.work.le[ec] = t.le; a.work.end[ec] = t.le; }
+                    }
+                    result = wev == 1 ? 0 : 1;
+                    break;
+                }
+            }
+            __syncwarp();
+            if (result == 0) {
+                if (lane == 0) {
+                    tlist[ls + cnt] = (uint32_t)c; alive[c] = 1;
+                    a.work.cand[c] = (uint32_t)c; a.work.cov[c] = 1; a.work.tid[c] = t.tid; a.work.start[c] = t.start; a.work.end[c] = t.end;
+                    a.work.fs[c] = t.fs; a.work.le[c] = t.le;
+                }
+                ++cnt;
+            } else if (lane == 0) alive[c] = 0;
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void merge_gather_kernel(DMerged work, const uint32_t *__restrict__ sel, int64_t n, DMerged out)
+{
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t c = sel[k];
+    out.cand[k] = c; out.cov[k] = work.cov[c]; out.tid[k] = work.tid[c]; out.start[k] = work.start[c]; out.end[k] = work.end[c];
+    out.fs[k] = work.fs[c]; out.le[k] = work.le[c];
+}
+
+void launch_merge_fold(const MergeArgs &a, int64_t n_loci, cudaStream_t st)
+{
+    if (n_loci <= 0) return;
+    int64_t bl = (n_loci + MF_WARPS - 1) / MF_WARPS; if (bl > 148 * 16) bl = 148 * 16;
+    // tlist reuses the (no longer needed) 64-bit key scratch; alive reuses the head mask's sibling buffer `dropped`
+    merge_fold_kernel<<<(unsigned)bl, MF_WARPS * 32, 0, st>>>(a, n_loci, (uint32_t *)a.keys, a.dropped);
+    LRB_COUNT_LAUNCH();
+}
+void launch_merge_compact(const MergeArgs &a, int64_t n_loci, cudaStream_t st)
+{
+    (void)n_loci;
+    // a.dropped holds the alive mask; a.locus_cnt is scratch for the compacted candidate ids
+    launch_compact_mask(a.dropped, a.n_cand, nullptr, a.locus_cnt, nullptr, a.tile_state, a.ticket, a.totals + 1, st);
+}
+void launch_merge_gather(const MergeArgs &a, int64_t n_out, cudaStream_t st)
+{
+    if (n_out <= 0) return;
+    merge_gather_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(a.work, a.locus_cnt, n_out, a.out);
+    LRB_COUNT_LAUNCH();
+}
+
+}  // namespace lrbk

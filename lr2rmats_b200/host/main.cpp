@@ -1,0 +1,50 @@
+// main.cpp -- the product binary `lr2rmats-b200`: the drop-in CLI (cli.cpp) bound to the CUDA library through the C ABI.
+// There is no CPU engine in this binary: without a CUDA device every subcommand fails loudly.
+#include <cstdio>
+#include <cstdlib>
+#include "lrb_host.h"
+
+namespace {
+struct CudaEngine { lrb_ctx *ctx = nullptr; };
+
+int set_tables(void *s, const lrb_anno *a, const lrb_anno *rm, const lrb_sj *sj)
+{
+    lrb_ctx *c = ((CudaEngine *)s)->ctx; int rc;
+    if ((rc = lrb_anno_upload(c, a))) return rc;
+    if ((rc = lrb_rm_upload(c, rm))) return rc;
+    return lrb_sj_upload(c, sj);
+}
+int do_filter(void *s, const lrb_batch *b, const lrb_filter_params *p, lrb_filter_result *o) { return lrb_filter(((CudaEngine *)s)->ctx, b, p, o); }
+int do_bam2gtf(void *s, const lrb_batch *b, const lrb_exon_params *p, lrb_exon_result *o) { return lrb_bam2gtf(((CudaEngine *)s)->ctx, b, p, o); }
+int do_update(void *s, const lrb_batch *b, const lrb_chains *ch, const lrb_exon_params *ep, const lrb_update_params *up, lrb_update_result *o)
+{
+    lrb_ctx *c = ((CudaEngine *)s)->ctx;
+    if (!b) { int rc = lrb_chains_upload(c, ch); if (rc) return rc; }
+    return lrb_update_gtf(c, b, ep, up, o);
+}
+int do_unique(void *s, const lrb_batch *b, const lrb_chains *ch, const lrb_exon_params *ep, const lrb_update_params *up, lrb_unique_result *o)
+{
+    lrb_ctx *c = ((CudaEngine *)s)->ctx;
+    if (!b) { int rc = lrb_chains_upload(c, ch); if (rc) return rc; }
+    return lrb_unique_gtf(c, b, ep, up, o);
+}
+const char *err(void *s) { return lrb_last_error(((CudaEngine *)s)->ctx); }
+}  // namespace
+
+int main(int argc, char **argv)
+{
+    CudaEngine ce; lrb::Engine eng;
+    if (argc >= 3) {                                  // usage-only invocations need no device
+        const char *dev = getenv("LRB_DEVICE");
+        int rc = lrb_ctx_create(dev ? atoi(dev) : 0, &ce.ctx);
+        if (rc != LRB_OK) {
+            fprintf(stderr, "[lr2rmats-b200] cannot create a CUDA context (code %d): this build has no CPU fallback\n", rc);
+            return 2;
+        }
+    }
+    eng.self = &ce; eng.set_tables = set_tables; eng.filter = do_filter; eng.bam2gtf = do_bam2gtf; eng.update = do_update;
+    eng.unique = do_unique; eng.error = err;
+    int rc = lrb::cli_main(argc, argv, eng);
+    if (ce.ctx) lrb_ctx_destroy(ce.ctx);
+    return rc;
+}

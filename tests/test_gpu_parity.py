@@ -1,0 +1,237 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs --
+bit-exact on every output array -- plus size-independent properties (shard invariance, fused == unfused, idempotence)."""
+import numpy as np
+import pytest
+
+from lr2rmats_b200 import cabi, synth
+from tests import oracle_port as op
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from lr2rmats_b200 import api
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def data():
+    anno = synth.make_annotation(1500, n_chrom=4, seed=21)
+    rr = synth.make_rrna(anno, 40, seed=22)
+    iso = synth.make_reads(anno, 30000, seed=23, ont=False, reject_frac=0.2, rrna=rr)
+    ont = synth.make_reads(anno, 4000, seed=24, ont=True, reject_frac=0.2, rrna=rr)
+    return dict(anno=anno, rr=rr, iso=iso, ont=ont)
+
+
+def assert_dict_equal(a, b, path=""):
+    assert set(a) == set(b), (path, set(a) ^ set(b))
+    for k in a:
+        if isinstance(a[k], dict):
+            assert_dict_equal(a[k], b[k], path + "/" + k)
+        elif a[k] is None or b[k] is None:
+            assert a[k] is None and b[k] is None, path + "/" + k
+        elif isinstance(a[k], np.ndarray):
+            assert a[k].shape == b[k].shape, (path + "/" + k, a[k].shape, b[k].shape)
+            if not np.array_equal(a[k], b[k]):
+                i = int(np.nonzero(a[k] != b[k])[0][0])
+                raise AssertionError(f"{path}/{k} differs first at {i}: {a[k][i]} vs {b[k][i]} ({int((a[k] != b[k]).sum())} diffs)")
+        else:
+            assert a[k] == b[k], path + "/" + k
+
+
+def filter_valid(f):
+    """score / intron_n are only defined where pass (the reference leaves them unset otherwise)."""
+    m = f["pass_"].astype(bool)
+    return dict(pass_=f["pass_"], score=np.where(m, f["score"], 0), intron_n=np.where(m, f["intron_n"], 0), keep_idx=f["keep_idx"])
+
+
+@pytest.mark.parametrize("which", ["iso", "ont"])
+@pytest.mark.parametrize("with_rm", [True, False])
+def test_filter(ctx, data, which, with_rm):
+    r = data[which]
+    fp = cabi.FilterParams.default()
+    ctx.set_rm(data["rr"] if with_rm else None)
+    g = ctx.filter(r.soa(), fp)
+    o = op.filter(r.soa(), data["rr"] if with_rm else None, fp)
+    assert_dict_equal(filter_valid(g), filter_valid(o))
+    assert 0 < len(o["keep_idx"]) < r.n
+
+
+def test_filter_params(ctx, data):
+    r = data["iso"]
+    ctx.set_rm(data["rr"])
+    for fp in (cabi.FilterParams.default(cov_rate=0.9, map_qual=0.9, sec_rat=0.5), cabi.FilterParams.default(min_intron_n=2),
+               cabi.FilterParams.default(sec_rat=1.5), cabi.FilterParams.default(cov_rate=0.0, map_qual=0.0)):
+        assert_dict_equal(filter_valid(ctx.filter(r.soa(), fp)), filter_valid(op.filter(r.soa(), data["rr"], fp)))
+
+
+@pytest.mark.parametrize("which", ["iso", "ont"])
+def test_bam2gtf(ctx, data, which):
+    r = data[which]
+    for ep in (cabi.ExonParams.default(), cabi.ExonParams.default(min_exon=1, min_intron=30, max_delet=2), cabi.ExonParams.default(min_exon=40)):
+        g = ctx.bam2gtf(r.soa(), ep); o = op.bam2gtf(r.soa(), ep)
+        g["read_idx"] = None
+        assert_dict_equal(g, o)
+
+
+def test_exon_with_keep_list_and_fused(ctx, data):
+    r = data["iso"]
+    fp, ep = cabi.FilterParams.default(), cabi.ExonParams.default()
+    ctx.set_rm(data["rr"])
+    of = op.filter(r.soa(), data["rr"], fp)
+    oe = op.bam2gtf(r.soa(), ep, sel=of["keep_idx"])
+    # unfused: filter stage, then the walk restricted to the keep list
+    ctx.upload(r.soa()); ctx.filter_run(fp); ctx.exon_run(ep, use_keep_list=True)
+    assert_dict_equal(ctx.exon_fetch(), oe)
+    # fused single pass
+    ctx.upload(r.soa()); ctx.pipeline_run(fp, ep)
+    assert_dict_equal(ctx.exon_fetch(), oe)
+    assert_dict_equal(filter_valid(ctx.filter_fetch()), filter_valid(of))
+
+
+def _kept_chains(data, which):
+    r = data[which]
+    of = op.filter(r.soa(), data["rr"], cabi.FilterParams.default())
+    kept = r.take(of["keep_idx"])
+    return kept, op.bam2gtf(kept.soa(), cabi.ExonParams.default())
+
+
+@pytest.mark.parametrize("which", ["iso", "ont"])
+@pytest.mark.parametrize("level", [1, 2, 3, 4, 5])
+def test_update_pass1(ctx, data, which, level):
+    kept, chains = _kept_chains(data, which)
+    up = cabi.UpdateParams.default(full_level=level)
+    ctx.set_anno(data["anno"].soa()); ctx.set_sj(None)
+    g = ctx.update_gtf(kept.soa(), cabi.ExonParams.default(), up)
+    rc, o = op.update(chains, data["anno"].soa(), None, up)
+    assert rc == 0
+    o["ex"]["read_idx"] = g["ex"]["read_idx"]
+    assert_dict_equal(g, o)
+    assert len(o["updated"]["cand"]) > 0
+
+
+@pytest.mark.parametrize("which", ["iso", "ont"])
+@pytest.mark.parametrize("kw", [dict(split_trans=1), dict(split_trans=0), dict(split_trans=1, ss_dis=4, min_sj_cnt=2),
+                                dict(split_trans=1, use_multi=1, force_strand=1, full_level=5), dict(split_trans=1, end_dis=30)])
+def test_update_pass2_sj(ctx, data, which, kw):
+    kept, chains = _kept_chains(data, which)
+    sj = synth.make_sj((chains["tid"], chains["exon_off"], chains["exon_start"], chains["exon_end"]), 0.7, seed=5)
+    args = dict(full_level=3); args.update(kw)
+    up = cabi.UpdateParams.default(**args)
+    ctx.set_anno(data["anno"].soa()); ctx.set_sj(sj)
+    g = ctx.update_gtf(kept.soa(), cabi.ExonParams.default(), up)
+    rc, o = op.update(chains, data["anno"].soa(), sj, up)
+    assert rc == 0
+    o["ex"]["read_idx"] = g["ex"]["read_idx"]
+    assert_dict_equal(g, o)
+    if kw.get("split_trans"):
+        assert (o["novel"]["piece"] >= 0).sum() > 0, "the fixture must exercise split pieces"
+
+
+@pytest.mark.parametrize("which", ["iso", "ont"])
+def test_unique(ctx, data, which):
+    kept, chains = _kept_chains(data, which)
+    for kw in (dict(), dict(force_strand=1), dict(ss_dis=6), dict(end_dis=25, single_exon_ovlp_frac=0.5)):
+        up = cabi.UpdateParams.default(**kw)
+        g = ctx.unique_gtf(kept.soa(), cabi.ExonParams.default(), up)
+        rc, o = op.unique(chains, up)
+        assert rc == 0
+        o["ex"]["read_idx"] = g["ex"]["read_idx"]
+        assert_dict_equal(g, o)
+
+
+def test_chains_input_mode(ctx, data):
+    """-m g: read-derived transcripts given as exon chains (read_gtf_trans) instead of CIGARs."""
+    kept, chains = _kept_chains(data, "iso")
+    up = cabi.UpdateParams.default(full_level=3)
+    ctx.set_anno(data["anno"].soa()); ctx.set_sj(None)
+    ctx.upload_chains(dict(tid=chains["tid"], is_rev=chains["is_rev"], exon_off=chains["exon_off"], exon_start=chains["exon_start"], exon_end=chains["exon_end"]))
+    g = ctx.update_gtf(None, cabi.ExonParams.default(), up)
+    rc, o = op.update(chains, data["anno"].soa(), None, up)
+    assert_dict_equal(g, o)
+
+
+def test_edge_cases(ctx, data):
+    anno = data["anno"]
+    ctx.set_anno(anno.soa()); ctx.set_sj(None); ctx.set_rm(None)
+    ep, fp, up = cabi.ExonParams.default(), cabi.FilterParams.default(), cabi.UpdateParams.default()
+    # empty batch
+    empty = data["iso"].take(np.zeros(0, np.int64))
+    assert ctx.filter(empty.soa(), fp)["keep_idx"].size == 0
+    assert ctx.bam2gtf(empty.soa(), ep)["n_reads"] == 0
+    g = ctx.update_gtf(empty.soa(), ep, up)
+    assert g["ex"]["n_reads"] == 0 and g["updated"]["cand"].size == 0
+    # a single read
+    one = data["iso"].take(np.array([5]))
+    assert_dict_equal(filter_valid(ctx.filter(one.soa(), fp)), filter_valid(op.filter(one.soa(), None, fp)))
+    # hand-made CIGARs: very long (> staging capacity, > 64 exons), leading N, zero-length CIGAR / unmapped
+    M, I, D, N, S = synth.M, synth.I, synth.D, synth.N, synth.S
+    def w(l, o): return (l << 4) | o
+    long_c = []
+    for k in range(3000):
+        long_c += [w(30 + k % 7, M), w(100 + k % 13, N)] if k % 3 else [w(20, M), w(2, I), w(15, M), w(60, D)]
+    long_c.append(w(50, M))
+    cigs = [long_c, [w(100, N), w(50, M)], [w(5, S), w(40, M), w(2, N), w(40, M), w(51, D), w(10, M), w(5, S)], [], [w(70, M)] * 1]
+    rds = synth.Reads()
+    rds.tid = np.array([0, 0, 0, -1, 1], np.int32); rds.pos = np.array([1000, 2000, 3000, -1, 500], np.int32)
+    rds.flag = np.array([0, 16, 0, 4, 0], np.uint16); rds.nm = np.array([3, 0, 1, 0, 0], np.int32); rds.xs = np.array([0, ord('+'), ord('-'), 0, 7], np.int8)
+    qn = lambda c: sum((x >> 4) for x in c if (x & 15) in (M, I, S, 7, 8))
+    rds.l_qseq = np.array([qn(c) for c in cigs], np.int32); rds.qid = np.arange(5); rds.qname_hash = synth.splitmix64(np.arange(5))
+    rds.cigar = np.array(sum(cigs, []), np.uint32); rds.cigar_off = np.cumsum([0] + [len(c) for c in cigs]).astype(np.uint32)
+    for e in (ep, cabi.ExonParams.default(min_exon=0, min_intron=0, max_delet=0)):
+        g = ctx.bam2gtf(rds.soa(), e); o = op.bam2gtf(rds.soa(), e); g["read_idx"] = None
+        assert_dict_equal(g, o)
+    assert_dict_equal(filter_valid(ctx.filter(rds.soa(), fp)), filter_valid(op.filter(rds.soa(), None, fp)))
+    # update on a batch with an unmapped record fails loudly like the reference (it aborts)
+    from lr2rmats_b200 import api
+    with pytest.raises(api.LrbError) as ei:
+        ctx.update_gtf(rds.soa(), ep, up)
+    assert ei.value.code == -5
+    # unsorted reads are rejected
+    rev = data["iso"].take(np.arange(200)[::-1])
+    with pytest.raises(api.LrbError) as ei:
+        ctx.update_gtf(rev.soa(), ep, up)
+    assert ei.value.code == -4
+    # the mapped subset (long chain of > 64 exons included) goes through update and unique
+    sub = rds.take(np.array([4]))    # tid 1 read alone
+    mapped = rds.take(np.array([0, 1, 2]))
+    g = ctx.update_gtf(mapped.soa(), ep, up); ch = op.bam2gtf(mapped.soa(), ep)
+    rc, o = op.update(ch, anno.soa(), None, up); o["ex"]["read_idx"] = g["ex"]["read_idx"]
+    assert_dict_equal(g, o)
+    g = ctx.unique_gtf(mapped.soa(), ep, up); rc, o = op.unique(ch, up); o["ex"]["read_idx"] = g["ex"]["read_idx"]
+    assert_dict_equal(g, o)
+
+
+def test_shard_invariance(ctx, data):
+    """cutting the read stream at locus gaps and processing shards independently reproduces the unsharded
+    result (the multi-GPU decomposition).  Checked here on one GPU, shard after shard."""
+    from lr2rmats_b200 import api
+    kept, chains = _kept_chains(data, "iso")
+    off = chains["exon_off"].astype(np.int64)
+    cuts = api.shard_cuts(chains["tid"], chains["exon_start"][off[:-1]], chains["exon_end"][off[1:] - 1], 4)
+    up = cabi.UpdateParams.default(full_level=3, want_summary=0)
+    ctx.set_anno(data["anno"].soa()); ctx.set_sj(None)
+    whole = ctx.update_gtf(kept.soa(), cabi.ExonParams.default(), up)
+    cov, fs, le, n_upd = [], [], [], 0
+    for k in range(4):
+        part = kept.take(np.arange(cuts[k], cuts[k + 1]))
+        g = ctx.update_gtf(part.soa(), cabi.ExonParams.default(), up)
+        cov.append(g["updated"]["cov"]); fs.append(g["updated"]["first_start"]); le.append(g["updated"]["last_end"])
+    assert np.array_equal(np.concatenate(cov), whole["updated"]["cov"])
+    assert np.array_equal(np.concatenate(fs), whole["updated"]["first_start"])
+    assert np.array_equal(np.concatenate(le), whole["updated"]["last_end"])
+
+
+def test_idempotent_and_launches(ctx, data):
+    kept, chains = _kept_chains(data, "iso")
+    up = cabi.UpdateParams.default(full_level=3)
+    ctx.set_anno(data["anno"].soa()); ctx.set_sj(None)
+    n0 = ctx.launch_count()
+    a = ctx.update_gtf(kept.soa(), cabi.ExonParams.default(), up)
+    n1 = ctx.launch_count()
+    b = ctx.update_gtf(kept.soa(), cabi.ExonParams.default(), up)
+    assert_dict_equal(a, b)
+    assert n1 - n0 >= 10, "the CUDA kernels must actually have been launched"

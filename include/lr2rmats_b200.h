@@ -258,10 +258,18 @@ int lrb_unique_gtf(lrb_ctx *ctx, const lrb_batch *b, const lrb_exon_params *ep,
 #define LRB_T_CLASSIFY 2
 #define LRB_T_MERGE    3
 #define LRB_T_SUMMARY  4
-#define LRB_T_COUNT    5
+#define LRB_T_K_SCAN   5   /* the cigar_scan kernel alone */
+#define LRB_T_K_FOLD   6   /* the merge_fold kernel alone (updated_T fold) */
+#define LRB_T_COUNT    7
 int lrb_timing_enable(lrb_ctx *ctx, int on);
 int lrb_timing_get(lrb_ctx *ctx, float ms[LRB_T_COUNT], int64_t *n_launches);
 int64_t lrb_launch_count(const lrb_ctx *ctx);   /* kernels launched since ctx creation */
+/* CUDA events on the ctx stream (the stream every kernel of this library is launched on): slot in [0,8) */
+int lrb_mark(lrb_ctx *ctx, int slot);
+int lrb_elapsed_ms(lrb_ctx *ctx, int slot_from, int slot_to, float *ms);   /* synchronises on slot_to */
+/* pinned host memory for record batches (what the host decoder fills) */
+void *lrb_host_alloc(size_t bytes);
+void lrb_host_free(void *p);
 
 /* Multi-GPU plumbing: the caller (one process per GPU) owns the communicator;
  * tables are broadcast by the caller (torch.distributed / NCCL) into host or

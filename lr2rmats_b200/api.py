@@ -21,9 +21,10 @@ ENTRY_POINTS = [
     "lrb_batch_upload", "lrb_chains_upload", "lrb_filter_run", "lrb_exon_run", "lrb_pipeline_run", "lrb_update_run", "lrb_unique_run",
     "lrb_sync", "lrb_filter_fetch", "lrb_exon_fetch", "lrb_update_fetch", "lrb_unique_fetch", "lrb_filter", "lrb_bam2gtf",
     "lrb_update_gtf", "lrb_unique_gtf", "lrb_timing_enable", "lrb_timing_get", "lrb_launch_count", "lrb_shard_cuts",
+    "lrb_mark", "lrb_elapsed_ms", "lrb_host_alloc", "lrb_host_free",
 ]
 
-T_NAMES = ["filter", "exon", "classify", "merge", "summary"]
+T_NAMES = ["filter", "exon", "classify", "merge", "summary", "k_scan", "k_fold"]
 
 
 class LrbError(RuntimeError):
@@ -69,7 +70,11 @@ def load_library():
     L.lrb_update_gtf.argtypes = [vp, P(cabi.Batch), P(cabi.ExonParams), P(cabi.UpdateParams), P(cabi.UpdateResult)]
     L.lrb_unique_gtf.argtypes = [vp, P(cabi.Batch), P(cabi.ExonParams), P(cabi.UpdateParams), P(cabi.UniqueResult)]
     L.lrb_timing_enable.argtypes = [vp, C.c_int]
-    L.lrb_timing_get.argtypes = [vp, P(C.c_float * 5), P(C.c_int64)]
+    L.lrb_timing_get.argtypes = [vp, P(C.c_float * 7), P(C.c_int64)]
+    L.lrb_mark.argtypes = [vp, C.c_int]
+    L.lrb_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, P(C.c_float)]
+    L.lrb_host_alloc.argtypes = [C.c_size_t]; L.lrb_host_alloc.restype = C.c_void_p
+    L.lrb_host_free.argtypes = [C.c_void_p]; L.lrb_host_free.restype = None
     L.lrb_launch_count.argtypes = [vp]; L.lrb_launch_count.restype = C.c_int64
     L.lrb_shard_cuts.argtypes = [cabi.i32p, cabi.i32p, cabi.i32p, C.c_int64, C.c_int, P(C.c_int64)]
     _lib = L
@@ -184,12 +189,17 @@ class Context:
     def timing(self, on=True): self._ck(self.L.lrb_timing_enable(self.h, 1 if on else 0))
 
     def timing_get(self):
-        ms = (C.c_float * 5)(); n = C.c_int64()
+        ms = (C.c_float * 7)(); n = C.c_int64()
         self._ck(self.L.lrb_timing_get(self.h, C.byref(ms), C.byref(n)))
         return dict(zip(T_NAMES, list(ms))), int(n.value)
 
     def launch_count(self) -> int:
         return int(self.L.lrb_launch_count(self.h))
+
+    def mark(self, slot: int): self._ck(self.L.lrb_mark(self.h, slot))
+
+    def elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float(); self._ck(self.L.lrb_elapsed_ms(self.h, a, b, C.byref(ms))); return float(ms.value)
 
 
 def shard_cuts(tid, start, end, n_shards: int) -> np.ndarray:

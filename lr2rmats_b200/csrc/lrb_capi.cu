@@ -88,7 +88,7 @@ struct lrb_ctx {
     // pinned result buffers
     PBuf p[40];
     // timing
-    bool timing = false; cudaEvent_t ev[LRB_T_COUNT + 1]; float ms[LRB_T_COUNT]; int64_t launches0 = 0, launches_last = 0;
+    bool timing = false; cudaEvent_t ev[12]; cudaEvent_t marks[8]; float ms[LRB_T_COUNT]; int64_t launches0 = 0, launches_last = 0;
     lrb_update_params last_up;
 };
 
@@ -182,11 +182,14 @@ int run_scan(lrb_ctx *c, int mode, const lrb_filter_params *fp, const lrb_exon_p
         CK(cudaMemsetAsync(c->tile_state.p, 0, (size_t)n_tiles * 8, c->st));
         CK(cudaMemsetAsync(c->scalars.p, 0, 8 * 8 + 4, c->st));
         size_t smem = (size_t)stage_words * 4 + (size_t)3072 * 8;
+        tick(c, 8);
         launch_cigar_scan(a, n_tiles, warp_mode, smem, c->st);
+        tick(c, 9);
         CK(cudaGetLastError());
         uint64_t t[2];
         if ((rc = read_totals(c, t, 2)) != LRB_OK) return rc;
         c->rows.n = (int64_t)t[0]; c->ex.n = (int64_t)t[1];
+        if (c->timing) cudaEventElapsedTime(&c->ms[LRB_T_K_SCAN], c->ev[8], c->ev[9]);
         if (mode == 0 || c->ex.n <= c->ex.cap) break;
         if (attempt == 1) return fail(c, LRB_E_NOMEM, "exon pool still too small after regrow");
         if ((rc = setup_exons(c, c->ex.n + 16)) != LRB_OK) return rc;          // exact size known now: walk again
@@ -246,11 +249,14 @@ int run_merge(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_cand, 
     uint64_t t[2];
     if ((rc = read_totals(c, t, 1)) != LRB_OK) return rc;
     m.n_loci = (int64_t)t[0];
+    tick(c, 10);
     launch_merge_fold(a, m.n_loci, c->st);
+    tick(c, 11);
     launch_merge_compact(a, m.n_loci, c->st);
     CK(cudaGetLastError());
     if ((rc = read_totals(c, t, 2)) != LRB_OK) return rc;
     m.n_out = (int64_t)t[1];
+    if (c->timing && gather) cudaEventElapsedTime(&c->ms[LRB_T_K_FOLD], c->ev[10], c->ev[11]);
     if (gather) { launch_merge_gather(a, m.n_out, c->st); CK(cudaGetLastError()); }
     return LRB_OK;
 }
@@ -285,7 +291,8 @@ int lrb_ctx_create(int device, lrb_ctx **out)
     if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return LRB_E_CUDA; }
     if (!c->scalars.ensure(256) || !c->h_scalars.ensure(256)) { delete c; return LRB_E_NOMEM; }
     cudaMemsetAsync(c->scalars.p, 0, 256, c->st);
-    for (int i = 0; i <= LRB_T_COUNT; ++i) cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 12; ++i) cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 8; ++i) cudaEventCreate(&c->marks[i]);
     memset(c->ms, 0, sizeof c->ms); memset(c->summary, 0, sizeof c->summary);
     c->launches0 = total_launches();
     *out = c;
@@ -314,7 +321,8 @@ void lrb_ctx_destroy(lrb_ctx *c)
     }
     for (PBuf &p : c->p) p.release();
     c->h_scalars.release();
-    for (int i = 0; i <= LRB_T_COUNT; ++i) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 12; ++i) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(c->marks[i]);
     cudaStreamDestroy(c->st);
     delete c;
 }
@@ -878,6 +886,23 @@ int lrb_timing_get(lrb_ctx *c, float ms[LRB_T_COUNT], int64_t *n_launches)
     return LRB_OK;
 }
 int64_t lrb_launch_count(const lrb_ctx *c) { return c ? total_launches() - c->launches0 : 0; }
+int lrb_mark(lrb_ctx *c, int slot)
+{
+    if (!c || slot < 0 || slot >= 8) return LRB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->marks[slot], c->st));
+    return LRB_OK;
+}
+int lrb_elapsed_ms(lrb_ctx *c, int a, int b, float *ms)
+{
+    if (!c || !ms || a < 0 || a >= 8 || b < 0 || b >= 8) return LRB_E_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventSynchronize(c->marks[b]));
+    CK(cudaEventElapsedTime(ms, c->marks[a], c->marks[b]));
+    return LRB_OK;
+}
+void *lrb_host_alloc(size_t bytes) { void *p = nullptr; if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
+void lrb_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 // ----------------------------------------------------------------------------------------------------- shards
 int lrb_shard_cuts(const int32_t *tid, const int32_t *start, const int32_t *end, int64_t n, int n_shards, int64_t *cuts)

@@ -47,6 +47,7 @@ struct MergeBufs {                                  // scratch + output of one m
     Buf keys, head, locus_start, locus_cnt, dropped;
     Buf w_cand, w_cov, w_tid, w_start, w_end, w_fs, w_le;
     Buf o_cand, o_cov, o_tid, o_start, o_end, o_fs, o_le;
+    Buf c_tid, c_start, c_end, c_rev, c_n, c_fs, c_le, c_gbeg, c_hash;
     int64_t n_out = 0, n_loci = 0;
 };
 
@@ -56,7 +57,7 @@ struct lrb_ctx {
     int device = 0; cudaStream_t st = nullptr; std::string err;
     // tables
     DAnno anno; DSj sj; DRmIndex rm;
-    Buf a_tid, a_start, a_end, a_gene, a_rev, a_off, a_es, a_ee, a_pmax;
+    Buf a_tid, a_start, a_end, a_gene, a_rev, a_off, a_es, a_ee, a_pmax, a_mono;
     Buf s_tid, s_don, s_acc, s_u, s_m, s_pmax, s_dkey;
     Buf r_gtid, r_goff, r_start, r_pmax;
     // batch
@@ -220,6 +221,9 @@ int setup_merge(lrb_ctx *c, MergeBufs &m, int64_t n_cand)
     NEED(m.keys, n * 8); NEED(m.head, n); NEED(m.locus_start, (n + 1) * 4); NEED(m.locus_cnt, n * 4); NEED(m.dropped, n);
     Buf *w[] = {&m.w_cand, &m.w_cov, &m.w_tid, &m.w_start, &m.w_end, &m.w_fs, &m.w_le, &m.o_cand, &m.o_cov, &m.o_tid, &m.o_start, &m.o_end, &m.o_fs, &m.o_le};
     for (Buf *b : w) NEED(*b, n * 4);
+    Buf *cb[] = {&m.c_tid, &m.c_start, &m.c_end, &m.c_rev, &m.c_n, &m.c_fs, &m.c_le, &m.c_gbeg};
+    for (Buf *b : cb) NEED(*b, n * 4);
+    NEED(m.c_hash, n * 8);
     return LRB_OK;
 }
 DMerged merged_view(Buf &cand, Buf &cov, Buf &tid, Buf &st, Buf &en, Buf &fs, Buf &le, int64_t n)
@@ -243,6 +247,9 @@ int run_merge(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_cand, 
     a.dropped = m.dropped.as<uint8_t>();
     a.work = merged_view(m.w_cand, m.w_cov, m.w_tid, m.w_start, m.w_end, m.w_fs, m.w_le, n_cand);
     a.out = merged_view(m.o_cand, m.o_cov, m.o_tid, m.o_start, m.o_end, m.o_fs, m.o_le, n_cand);
+    a.cd.tid = m.c_tid.as<int32_t>(); a.cd.start = m.c_start.as<int32_t>(); a.cd.end = m.c_end.as<int32_t>(); a.cd.rev = m.c_rev.as<int32_t>();
+    a.cd.n = m.c_n.as<int32_t>(); a.cd.fs = m.c_fs.as<int32_t>(); a.cd.le = m.c_le.as<int32_t>(); a.cd.gbeg = m.c_gbeg.as<uint32_t>();
+    a.cd.hash = m.c_hash.as<uint64_t>();
     a.tile_state = c->tile_state.as<uint64_t>(); a.ticket = d_ticket(c); a.totals = d_totals(c);
     launch_merge_prepare(a, c->st);
     CK(cudaGetLastError());
@@ -304,7 +311,7 @@ void lrb_ctx_destroy(lrb_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->st);
-    Buf *bufs[] = {&c->a_tid, &c->a_start, &c->a_end, &c->a_gene, &c->a_rev, &c->a_off, &c->a_es, &c->a_ee, &c->a_pmax, &c->s_tid, &c->s_don, &c->s_acc,
+    Buf *bufs[] = {&c->a_tid, &c->a_start, &c->a_end, &c->a_gene, &c->a_rev, &c->a_off, &c->a_es, &c->a_ee, &c->a_pmax, &c->a_mono, &c->s_tid, &c->s_don, &c->s_acc,
                    &c->s_u, &c->s_m, &c->s_pmax, &c->s_dkey, &c->r_gtid, &c->r_goff, &c->r_start, &c->r_pmax, &c->b_tid, &c->b_pos, &c->b_lq, &c->b_nm,
                    &c->b_flag, &c->b_xs, &c->b_qh, &c->b_coff, &c->b_cig, &c->f_pass, &c->f_score, &c->f_intron, &c->f_keep_row_mask, &c->f_keep_rec_mask,
                    &c->f_keep_idx, &c->f_keep_rows, &c->r_read, &c->r_tid, &c->r_rs, &c->r_re, &c->r_rev, &c->r_beg, &c->r_n, &c->q_read, &c->q_tid,
@@ -316,7 +323,8 @@ void lrb_ctx_destroy(lrb_ctx *c)
     for (Buf *b : bufs) b->release();
     for (MergeBufs *m : {&c->mg, &c->mg2}) {
         Buf *w[] = {&m->keys, &m->head, &m->locus_start, &m->locus_cnt, &m->dropped, &m->w_cand, &m->w_cov, &m->w_tid, &m->w_start, &m->w_end, &m->w_fs,
-                    &m->w_le, &m->o_cand, &m->o_cov, &m->o_tid, &m->o_start, &m->o_end, &m->o_fs, &m->o_le};
+                    &m->w_le, &m->o_cand, &m->o_cov, &m->o_tid, &m->o_start, &m->o_end, &m->o_fs, &m->o_le,
+                    &m->c_tid, &m->c_start, &m->c_end, &m->c_rev, &m->c_n, &m->c_fs, &m->c_le, &m->c_gbeg, &m->c_hash};
         for (Buf *b : w) b->release();
     }
     for (PBuf &p : c->p) p.release();
@@ -343,7 +351,15 @@ int lrb_anno_upload(lrb_ctx *c, const lrb_anno *a)
         uint64_t k = ((uint64_t)(uint32_t)(a->tid[i] + 1) << 32) | (uint32_t)a->end[i];
         run = std::max(run, k); pm[(size_t)i] = run;
     }
+    std::vector<uint8_t> mono((size_t)n);
+    for (int32_t i = 0; i < n; ++i) {
+        uint8_t m = 1;
+        for (uint32_t k = a->exon_off[i] + 1; k < a->exon_off[i + 1]; ++k)
+            if (a->exon_start[k] <= a->exon_start[k - 1] || a->exon_end[k] <= a->exon_end[k - 1]) { m = 0; break; }
+        mono[(size_t)i] = m;
+    }
     int rc;
+    if ((rc = h2d(c, c->a_mono, mono.data(), (size_t)n))) return rc;
     if ((rc = h2d(c, c->a_tid, a->tid, (size_t)n))) return rc;
     if ((rc = h2d(c, c->a_start, a->start, (size_t)n))) return rc;
     if ((rc = h2d(c, c->a_end, a->end, (size_t)n))) return rc;
@@ -357,7 +373,7 @@ int lrb_anno_upload(lrb_ctx *c, const lrb_anno *a)
     c->anno.n = n; c->anno.n_exon = a->n_exon; c->anno.tid = c->a_tid.as<int32_t>(); c->anno.start = c->a_start.as<int32_t>();
     c->anno.end = c->a_end.as<int32_t>(); c->anno.gene = c->a_gene.as<int32_t>(); c->anno.is_rev = c->a_rev.as<uint8_t>();
     c->anno.exon_off = c->a_off.as<uint32_t>(); c->anno.es = c->a_es.as<int32_t>(); c->anno.ee = c->a_ee.as<int32_t>();
-    c->anno.pmax_key = c->a_pmax.as<uint64_t>();
+    c->anno.pmax_key = c->a_pmax.as<uint64_t>(); c->anno.mono = c->a_mono.as<uint8_t>();
     return LRB_OK;
 }
 

@@ -104,6 +104,46 @@ template <int G> LRB_DEVINL int group_or(unsigned m, int v)
     return v;
 }
 
+// cooperative (G+1)-ary searches: the G lanes of a group probe G pivots per step (one load each, in parallel), so a
+// search over n keys costs ~log_{G+1}(n) dependent loads instead of log_2(n).  `a` non-decreasing; all lanes of the
+// group must call with the same arguments and receive the same result.
+template <int G, class T> LRB_DEVINL int64_t group_upper_bound(unsigned m, int gl, const T *a, int64_t lo, int64_t hi, T key)
+{
+    const int sh = (lane_id() / G) * G;
+    while (hi - lo > G) {
+        const int64_t span = hi - lo;
+        const int64_t p = lo + (span * (gl + 1)) / (G + 1);            // lo <= p < hi, strictly increasing in gl
+        const unsigned b = (__ballot_sync(m, a[p] > key) >> sh) & ((1u << G) - 1u);
+        if (b) {
+            const int f = __ffs(b) - 1;                                  // first pivot above the key
+            const int64_t pf = lo + (span * (f + 1)) / (G + 1);
+            const int64_t pl = f ? lo + (span * f) / (G + 1) + 1 : lo;
+            lo = pl; hi = pf;
+        } else lo = lo + (span * G) / (G + 1) + 1;
+    }
+    const int64_t q = lo + gl;
+    const unsigned b = (__ballot_sync(m, q < hi && a[q] > key) >> sh) & ((1u << G) - 1u);
+    return b ? lo + (__ffs(b) - 1) : hi;
+}
+template <int G, class T> LRB_DEVINL int64_t group_lower_bound(unsigned m, int gl, const T *a, int64_t lo, int64_t hi, T key)
+{
+    const int sh = (lane_id() / G) * G;
+    while (hi - lo > G) {
+        const int64_t span = hi - lo;
+        const int64_t p = lo + (span * (gl + 1)) / (G + 1);
+        const unsigned b = (__ballot_sync(m, a[p] >= key) >> sh) & ((1u << G) - 1u);
+        if (b) {
+            const int f = __ffs(b) - 1;
+            const int64_t pf = lo + (span * (f + 1)) / (G + 1);
+            const int64_t pl = f ? lo + (span * f) / (G + 1) + 1 : lo;
+            lo = pl; hi = pf;
+        } else lo = lo + (span * G) / (G + 1) + 1;
+    }
+    const int64_t q = lo + gl;
+    const unsigned b = (__ballot_sync(m, q < hi && a[q] >= key) >> sh) & ((1u << G) - 1u);
+    return b ? lo + (__ffs(b) - 1) : hi;
+}
+
 // --------------------------------------------------------------------------------------------- memory helpers
 LRB_DEVINL uint4 ldg_stream_u4(const uint4 *p) { uint4 r; asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p)); return r; }
 LRB_DEVINL uint32_t ldg_stream_u32(const uint32_t *p) { uint32_t r; asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p)); return r; }

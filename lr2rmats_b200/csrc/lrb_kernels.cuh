@@ -32,6 +32,7 @@ struct DAnno {
     uint32_t *exon_off = nullptr;
     int32_t *es = nullptr, *ee = nullptr;
     uint64_t *pmax_key = nullptr;                   // P_j = max_{i<=j} ((tid_i+1)<<32 | end_i)   
+    uint8_t *mono = nullptr;                        // 1: exon starts and exon ends of the transcript strictly increase
 };
 struct DSj {
     int64_t n = 0;
@@ -102,8 +103,12 @@ struct DMerged {
     int64_t n = 0, cap = 0;
     uint32_t *cand = nullptr; int32_t *cov = nullptr, *tid = nullptr, *start = nullptr, *end = nullptr, *fs = nullptr, *le = nullptr;
 };
+struct CandSoA {                                    // flattened fold candidates (see merge_cand_kernel)
+    int32_t *tid = nullptr, *start = nullptr, *end = nullptr, *rev = nullptr, *n = nullptr, *fs = nullptr, *le = nullptr;
+    uint32_t *gbeg = nullptr; uint64_t *hash = nullptr;
+};
 struct MergeArgs {
-    DRows rows; DExons ex; lrb_update_params up;
+    DRows rows; DExons ex; lrb_update_params up; CandSoA cd;
     DTransList list;                                // candidates in fold order
     const uint32_t *subset;                         // optional: rows subset as whole-read candidates (list.n==0): indices into rows
     int64_t n_cand;

@@ -33,12 +33,21 @@ LRB_DEVINL float ovlp_frac(int s1, int e1, int s2, int e2)
     return (float)__ddiv_rn((double)ov, (double)ml + 0.0);
 }
 
+// first index in [0,n) with a[idx] >= key (small sorted exon arrays of one transcript)
+LRB_DEVINL int small_lower_bound(const int *a, int n, int key)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
 template <int G>
 __global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a)
 {
     constexpr int GPB = CL_THREADS / G;
-    __shared__ int s_es[GPB][CL_SLOTS], s_ee[GPB][CL_SLOTS];
-    __shared__ uint8_t s_fl[GPB][CL_SLOTS];
+    constexpr int STRIDE = CL_SLOTS + 8;             // +8 words: the 4 groups of a warp land on disjoint banks
+    __shared__ int s_es[GPB][STRIDE], s_ee[GPB][STRIDE];
+    __shared__ uint8_t s_fl[GPB][STRIDE];
     const int g = threadIdx.x / G, gl = threadIdx.x % G;
     const unsigned gm = group_mask<G>();
     const int dis = a.up.ss_dis, level = a.up.full_level;
@@ -64,9 +73,9 @@ __global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a)
         __syncwarp(gm);
         const int b0s = es[0], b0e = ee[0], bls = es[n - 1], ble = ee[n - 1];
 
-        // ---- annotation window: F(b) by binary search on the prefix-max keys, sweep to the first "after"
+        // ---- annotation window: F(b) by a cooperative search on the prefix-max keys, sweep to the first "after"
         const uint64_t key_b = ((uint64_t)(uint32_t)(tid_b + 1) << 32) | (uint32_t)start_b;
-        int i = (int)upper_bound_dev<uint64_t>(a.anno.pmax_key, 0, a.anno.n, key_b);
+        int i = (int)group_upper_bound<G, uint64_t>(gm, gl, a.anno.pmax_key, 0, a.anno.n, key_b);
         int lfull = 0, rfull = 0, lnoth = 1, rnoth = 1, known = 0, known_site = 0, ref = -1;
         for (; i < a.anno.n; ++i) {
             const int at = a.anno.tid[i], as_ = a.anno.start[i], ae_ = a.anno.end[i];
@@ -107,27 +116,50 @@ __global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a)
             } else if (n > 1 && na > 1) {                                                  // check_splice_site :717-779
                 const int os = max(start_b, as_), oe = min(end_b, ae_);
                 int ovl = 0, iden = 0;
-                for (int j = gl; j < n - 1; j += G) {
-                    int e = ee[j], s = es[j + 1];
-                    ovl += (e >= os && e <= oe) + (s >= os && s <= oe);
-                }
-                for (int k = 0; k < na; ++k) {
-                    const int a_s = xs[k], a_e = xe[k];
-                    const bool has_next = k < na - 1;
-                    const int a_sn = has_next ? xs[k + 1] : 0;
-                    const bool don_ok = has_next && a_e >= os && a_e <= oe;
-                    const bool acc_ok = k >= 1 && a_s >= os && a_s <= oe;
+                if (dis == 0 && a.anno.mono[i]) {
+                    // exact-match fast path: exon starts and ends of this transcript are strictly increasing, so every read
+                    // coordinate matches at most one annotation exon -- two binary searches per read exon replace the
+                    // na x n sweep, and the pair counts of the reference become match counts.
                     for (int j = gl; j < n; j += G) {
                         const int bs = es[j], be = ee[j];
+                        const int ie = small_lower_bound(xe, na, be), is = small_lower_bound(xs, na, bs);
+                        const bool hit_e = ie < na && xe[ie] == be, hit_s = is < na && xs[is] == bs;
                         uint8_t f = fl[j], f0 = f;
-                        const bool de = iabs_dev(a_e - be) <= dis, ds = iabs_dev(a_s - bs) <= dis;
                         if (j < n - 1) {
-                            if (don_ok && de) { ++iden; f &= ~LRB_F_NOVEL_DON; }
-                            if (acc_ok && ds) { ++iden; f &= ~LRB_F_NOVEL_ACC; }
-                            if (has_next && de && iabs_dev(a_sn - es[j + 1]) <= dis) f &= ~LRB_F_NOVEL_JUNC;
+                            const int sn = es[j + 1];
+                            ovl += (be >= os && be <= oe) + (sn >= os && sn <= oe);
+                            if (hit_e && ie < na - 1) {
+                                if (be >= os && be <= oe) { ++iden; f &= ~LRB_F_NOVEL_DON; }
+                                if (xs[ie + 1] == sn) f &= ~LRB_F_NOVEL_JUNC;
+                            }
+                            if (hit_s && is >= 1 && bs >= os && bs <= oe) { ++iden; f &= ~LRB_F_NOVEL_ACC; }
                         }
-                        if (ds && de) f &= ~LRB_F_NOVEL_EXON;
+                        if (hit_s && hit_e && is == ie) f &= ~LRB_F_NOVEL_EXON;
                         if (f != f0) fl[j] = f;
+                    }
+                } else {
+                    for (int j = gl; j < n - 1; j += G) {
+                        int e = ee[j], s = es[j + 1];
+                        ovl += (e >= os && e <= oe) + (s >= os && s <= oe);
+                    }
+                    for (int k = 0; k < na; ++k) {
+                        const int a_s = xs[k], a_e = xe[k];
+                        const bool has_next = k < na - 1;
+                        const int a_sn = has_next ? xs[k + 1] : 0;
+                        const bool don_ok = has_next && a_e >= os && a_e <= oe;
+                        const bool acc_ok = k >= 1 && a_s >= os && a_s <= oe;
+                        for (int j = gl; j < n; j += G) {
+                            const int bs = es[j], be = ee[j];
+                            uint8_t f = fl[j], f0 = f;
+                            const bool de = iabs_dev(a_e - be) <= dis, ds = iabs_dev(a_s - bs) <= dis;
+                            if (j < n - 1) {
+                                if (don_ok && de) { ++iden; f &= ~LRB_F_NOVEL_DON; }
+                                if (acc_ok && ds) { ++iden; f &= ~LRB_F_NOVEL_ACC; }
+                                if (has_next && de && iabs_dev(a_sn - es[j + 1]) <= dis) f &= ~LRB_F_NOVEL_JUNC;
+                            }
+                            if (ds && de) f &= ~LRB_F_NOVEL_EXON;
+                            if (f != f0) fl[j] = f;
+                        }
                     }
                 }
                 ovl = group_sum<G>(gm, ovl); iden = group_sum<G>(gm, iden);
@@ -148,7 +180,7 @@ __global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a)
         int sj_checked = 0, unreliable = 0;
         if (full && !known && known_site && a.sj.n > 0) {
             sj_checked = 1;
-            int64_t S = upper_bound_dev<uint64_t>(a.sj.pmax_key, 0, a.sj.n, key_b);
+            const int64_t S = group_upper_bound<G, uint64_t>(gm, gl, a.sj.pmax_key, 0, a.sj.n, key_b);
             int ok = 1;
             if (S >= a.sj.n) ok = 0;
             else {
@@ -157,16 +189,20 @@ __global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a)
                 else {
                     int bad = 0;
                     const uint64_t tk = (uint64_t)(uint32_t)(tid_b + 1) << 32;
+                    // rows that can matter have tid == tid_b and don in [start_b - dis, end_b): narrow once per read
+                    int wlo = start_b - dis; if (wlo < 0) wlo = 0;
+                    const int64_t R0 = group_lower_bound<G, uint64_t>(gm, gl, a.sj.don_key, S, a.sj.n, tk | (uint32_t)wlo);
+                    const int64_t R1 = group_lower_bound<G, uint64_t>(gm, gl, a.sj.don_key, R0, a.sj.n, tk | (uint32_t)(end_b < 0 ? 0 : end_b));
                     for (int j = gl; j < n - 1; j += G) {
                         if (!(fl[j] & LRB_F_NOVEL_JUNC)) continue;
                         const int is = ee[j] + 1, ie = es[j + 1] - 1;                      // intron [is, ie]
                         // rows with tid==tid_b, don in [is-dis, is+dis], don < ie, index >= S
                         int dlo = is - dis; if (dlo < 0) dlo = 0;
                         int64_t dhi = (int64_t)is + dis + 1; if (dhi > ie) dhi = ie; if (dhi < 0) dhi = 0;
-                        int64_t lo = lower_bound_dev<uint64_t>(a.sj.don_key, S, a.sj.n, tk | (uint32_t)dlo);
-                        int64_t hi = lower_bound_dev<uint64_t>(a.sj.don_key, lo, a.sj.n, tk | (uint64_t)dhi);
+                        int64_t lo = lower_bound_dev<uint64_t>(a.sj.don_key, R0, R1, tk | (uint32_t)dlo);
                         int found = 0;
-                        for (int64_t q = lo; q < hi && !found; ++q) {
+                        for (int64_t q = lo; q < R1 && !found; ++q) {
+                            if (a.sj.don_key[q] >= (tk | (uint64_t)dhi)) break;
                             if (iabs_dev(a.sj.acc[q] - ie) <= dis) {
                                 int c = a.up.use_multi ? a.sj.cnt_u[q] + a.sj.cnt_m[q] : a.sj.cnt_u[q];
                                 if (c >= a.up.min_sj_cnt) found = 1;
@@ -289,57 +325,58 @@ void launch_rows_as_list(const DRows &rows, const uint32_t *subset, int64_t n, D
 }
 
 // --------------------------------------------------------------------------------------------------- merge fold
-struct Cand {                                       // one transcript entering the fold
-    int tid, start, end, rev;                       // trans_t fields (0/0/0/0 for split pieces)
-    int n; uint32_t gbeg;                           // exon slots [gbeg, gbeg+n) in the pools
-    int fs, le;                                     // exon[0].start, exon[n-1].end
-};
-LRB_DEVINL Cand load_cand(const DRows &rows, const DExons &ex, const DTransList &L, int64_t c)
-{
-    Cand t; uint32_t row = L.row[c];
-    t.n = (int)L.cnt[c]; t.gbeg = rows.ex_beg[row] + L.lo[c];
-    t.fs = ex.es[t.gbeg]; t.le = ex.ee[t.gbeg + t.n - 1];
-    if (L.piece[c] >= 0) { t.tid = 0; t.start = 0; t.end = 0; t.rev = 0; }
-    else { t.tid = rows.tid[row]; t.start = t.fs; t.end = t.le; t.rev = rows.is_rev[row]; }
-    return t;
-}
+// Candidate SoA (one row per transcript entering the fold), built once by merge_cand_kernel:
+//   tid/start/end/rev : trans_t fields (0/0/0/0 for split pieces)      n, gbeg : exon slots in the pools
+//   fs/le             : exon[0].start, exon[n-1].end                               hash    : of the internal boundaries
+LRB_DEVINL uint64_t mixh(uint64_t h, uint32_t v) { h ^= v; h *= 0x9E3779B97F4A7C15ull; h ^= h >> 29; return h; }
 
-__global__ void merge_keys_kernel(MergeArgs a)
+__global__ void merge_cand_kernel(MergeArgs a)
 {
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_cand) return;
-    uint32_t row = a.list.row[c];
-    uint32_t gb = a.rows.ex_beg[row] + a.list.lo[c];
-    int real_end = a.ex.ee[gb + a.list.cnt[c] - 1];
-    a.keys[c] = ((uint64_t)(uint32_t)(a.rows.tid[row] + 1) << 32) | (uint32_t)real_end;
+    const uint32_t row = a.list.row[c];
+    const int n = (int)a.list.cnt[c];
+    const uint32_t gb = a.rows.ex_beg[row] + a.list.lo[c];
+    const int fs = a.ex.es[gb], le = a.ex.ee[gb + n - 1];
+    const bool piece = a.list.piece[c] >= 0;
+    const int rtid = a.rows.tid[row];
+    a.cd.tid[c] = piece ? 0 : rtid; a.cd.start[c] = piece ? 0 : fs; a.cd.end[c] = piece ? 0 : le;
+    int mono = 2;                                   // bit 1: exon ends never decrease (always true for CIGAR chains)
+    for (int i = 0; i + 1 < n - 1; ++i) if (a.ex.ee[gb + i] > a.ex.ee[gb + i + 1]) { mono = 0; break; }
+    a.cd.rev[c] = (piece ? 0 : a.rows.is_rev[row]) | mono;
+    a.cd.n[c] = n; a.cd.gbeg[c] = gb; a.cd.fs[c] = fs; a.cd.le[c] = le;
+    uint64_t h = 0x243F6A8885A308D3ull ^ (uint64_t)n;
+    for (int i = 0; i < n - 1; ++i) { h = mixh(h, (uint32_t)a.ex.ee[gb + i]); h = mixh(h, (uint32_t)a.ex.es[gb + i + 1]); }
+    a.cd.hash[c] = h;
+    a.keys[c] = ((uint64_t)(uint32_t)(rtid + 1) << 32) | (uint32_t)le;          // real coordinates: locus segmentation
 }
 __global__ void merge_heads_kernel(MergeArgs a)
 {
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_cand) return;
-    uint32_t row = a.list.row[c];
-    uint32_t gb = a.rows.ex_beg[row] + a.list.lo[c];
-    uint64_t k = ((uint64_t)(uint32_t)(a.rows.tid[row] + 1) << 32) | (uint32_t)a.ex.es[gb];
+    const uint32_t row = a.list.row[c];
+    uint64_t k = ((uint64_t)(uint32_t)(a.rows.tid[row] + 1) << 32) | (uint32_t)a.cd.fs[c];
     a.head[c] = (c == 0 || k > a.keys[c - 1]) ? 1 : 0;   // new locus: start beyond every earlier end on this chromosome
 }
 void launch_merge_prepare(const MergeArgs &a, cudaStream_t st)
 {
     if (a.n_cand <= 0) { cudaMemsetAsync(a.totals, 0, 16, st); return; }
     unsigned bl = (unsigned)((a.n_cand + 255) / 256);
-    merge_keys_kernel<<<bl, 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
+    merge_cand_kernel<<<bl, 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
     launch_scan_max_u64(a.keys, a.n_cand, a.tile_state, a.ticket, st);
     merge_heads_kernel<<<bl, 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
     launch_compact_mask(a.head, a.n_cand, nullptr, a.locus_start, nullptr, a.tile_state, a.ticket, a.totals, st);
 }
 
 // check_iden (gtf.c:54-92) between candidate t and fold entry E (first start / last end may have been extended)
-struct Entry { int n; uint32_t gbeg; int fs, le; };
+struct Entry { int n; uint32_t gbeg; int fs, le; uint64_t hash; int mono; };
 LRB_DEVINL int x_s(const DExons &ex, const Entry &e, int i) { return i == 0 ? e.fs : ex.es[e.gbeg + i]; }
 LRB_DEVINL int x_e(const DExons &ex, const Entry &e, int i) { return i == e.n - 1 ? e.le : ex.ee[e.gbeg + i]; }
 LRB_DEVINL int chain_iden(const DExons &ex, const Entry &t1, const Entry &t2, int ss_dis, int end_dis)
 {
     const Entry &l = t1.n >= t2.n ? t1 : t2, &s = t1.n >= t2.n ? t2 : t1;
     if (t1.n == t2.n) {
+        if (ss_dis == 0 && t1.hash != t2.hash) return -1;        // some internal boundary differs
         if (iabs_dev(l.fs - s.fs) > end_dis) return -1;
         for (int i = 0; i < l.n - 1; ++i) {
             if (iabs_dev(x_e(ex, l, i) - x_e(ex, s, i)) > ss_dis) return -1;
@@ -350,14 +387,23 @@ LRB_DEVINL int chain_iden(const DExons &ex, const Entry &t1, const Entry &t2, in
     }
     int pm = -1;
     if (iabs_dev(l.fs - s.fs) > end_dis) return -1;
-    const int s_e0 = x_e(ex, s, 0), s_s1 = x_s(ex, s, 1);
-    for (int i = 0; i < l.n - 1; ++i) {
-        if (iabs_dev(x_e(ex, l, i) - s_e0) <= ss_dis && iabs_dev(x_s(ex, l, i + 1) - s_s1) <= ss_dis) {
+    const int s_e0 = ex.ee[s.gbeg], s_s1 = ex.es[s.gbeg + 1];    // s has >= 2 exons: both are pool values
+    int i = 0;
+    const bool jump = ss_dis == 0 && l.mono;
+    if (jump) {                                                  // exon ends of this chain never decrease: jump to the first candidate
+        int lo = 0, hi = l.n - 1;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (ex.ee[l.gbeg + mid] < s_e0) lo = mid + 1; else hi = mid; }
+        i = lo;
+    }
+    for (; i < l.n - 1; ++i) {
+        const int le_i = ex.ee[l.gbeg + i];
+        if (jump && le_i > s_e0) break;
+        if (iabs_dev(le_i - s_e0) <= ss_dis && iabs_dev(ex.es[l.gbeg + i + 1] - s_s1) <= ss_dis) {
             pm = 2;
             int j = 1;
             for (i = i + 1; i < l.n - 1 && j < s.n - 1; ++i, ++j) {
-                if (iabs_dev(x_e(ex, l, i) - x_e(ex, s, j)) > ss_dis) return -1;
-                if (iabs_dev(x_s(ex, l, i + 1) - x_s(ex, s, j + 1)) > ss_dis) return -1;
+                if (iabs_dev(ex.ee[l.gbeg + i] - ex.ee[s.gbeg + j]) > ss_dis) return -1;
+                if (iabs_dev(ex.es[l.gbeg + i + 1] - ex.es[s.gbeg + j + 1]) > ss_dis) return -1;
             }
             break;
         }
@@ -366,84 +412,94 @@ LRB_DEVINL int chain_iden(const DExons &ex, const Entry &t1, const Entry &t2, in
     return pm;
 }
 
-static constexpr int MF_WARPS = 4;
-// one warp per locus; tlist[ls + k] = candidate index of the k-th entry of the locus' T; entry data lives at work[cand]
-__global__ void __launch_bounds__(MF_WARPS * 32) merge_fold_kernel(MergeArgs a, int64_t n_loci, uint32_t *tlist, uint8_t *alive)
+static constexpr int MF_THREADS = 128;
+static constexpr int MF_SMALL = 48;                 // loci up to this many candidates go to 8-lane groups
+// G lanes per locus; tlist[ls + k] = candidate index of the k-th entry of the locus' T; mutable entry data lives at work[cand]
+template <int G, bool SMALL>
+__global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, int64_t n_loci, uint32_t *tlist, uint8_t *alive)
 {
-    const int lane = lane_id();
-    for (int64_t loc = (int64_t)blockIdx.x * MF_WARPS + warp_id(); loc < n_loci; loc += (int64_t)gridDim.x * MF_WARPS) {
+    constexpr int GPB = MF_THREADS / G;
+    const int gl = threadIdx.x % G;
+    const unsigned gm = group_mask<G>();
+    const int sh = (lane_id() / G) * G;
+    const CandSoA &cd = a.cd;
+    for (int64_t loc = (int64_t)blockIdx.x * GPB + threadIdx.x / G; loc < n_loci; loc += (int64_t)gridDim.x * GPB) {
         const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : a.n_cand;
+        if (SMALL != (le - ls <= MF_SMALL)) continue;
         int cnt = 0;
         for (int64_t c = ls; c < le; ++c) {
-            const Cand t = load_cand(a.rows, a.ex, a.list, c);
-            const Entry te = {t.n, t.gbeg, t.fs, t.le};
+            const int t_tid = cd.tid[c], t_start = cd.start[c], t_rv = cd.rev[c], t_rev = t_rv & 1;
+            const Entry te = {cd.n[c], cd.gbeg[c], cd.fs[c], cd.le[c], cd.hash[c], t_rv & 2};
             int result = 0;                                      // 0 append, 1 absorbed / dropped
-            for (int base = cnt - 1; base >= 0; base -= 32) {
-                const int k = base - lane;
+            for (int base = cnt - 1; base >= 0; base -= G) {
+                const int k = base - gl;
                 int ev = 0;                                      // 1 stop, 2 merge (identical), 3 drop (partial)
                 uint32_t ec = 0;
                 if (k >= 0) {
                     ec = tlist[ls + k];
-                    const int e_tid = a.work.tid[ec], e_end = a.work.end[ec];
-                    if (t.tid > e_tid || t.start > e_end) ev = 1;                                     // update_gtf.c:148
-                    else {
-                        const uint32_t erow = a.list.row[ec];
-                        const int e_rev = a.list.piece[ec] >= 0 ? 0 : a.rows.is_rev[erow];
-                        if (!(a.up.force_strand && t.rev != e_rev)) {                                 // :149
-                            Entry E = {(int)a.list.cnt[ec], a.rows.ex_beg[erow] + a.list.lo[ec], a.work.fs[ec], a.work.le[ec]};
-                            if (t.n == 1 && E.n == 1) {                                               // merge_trans2 :122-140
-                                if (iabs_dev(t.fs - E.fs) <= a.up.end_dis && iabs_dev(t.le - E.le) <= a.up.end_dis &&
-                                    ovlp_frac(t.fs, t.le, E.fs, E.le) >= a.up.single_exon_ovlp_frac) ev = 2;
-                            } else if (t.n > 1 && E.n > 1) {                                          // merge_trans1 :98-119
-                                int r = chain_iden(a.ex, te, E, a.up.ss_dis, a.up.end_dis);
-                                if (r == 0) ev = 2; else if (r == 2) ev = 3;
-                            }
+                    if (t_tid > cd.tid[ec] || t_start > a.work.end[ec]) ev = 1;                       // update_gtf.c:148
+                    else if (!(a.up.force_strand && t_rev != (cd.rev[ec] & 1))) {                     // :149
+                        const Entry E = {cd.n[ec], cd.gbeg[ec], a.work.fs[ec], a.work.le[ec], cd.hash[ec], cd.rev[ec] & 2};
+                        if (te.n == 1 && E.n == 1) {                                                  // merge_trans2 :122-140
+                            if (iabs_dev(te.fs - E.fs) <= a.up.end_dis && iabs_dev(te.le - E.le) <= a.up.end_dis &&
+                                ovlp_frac(te.fs, te.le, E.fs, E.le) >= a.up.single_exon_ovlp_frac) ev = 2;
+                        } else if (te.n > 1 && E.n > 1) {                                             // merge_trans1 :98-119
+                            int r = chain_iden(a.ex, te, E, a.up.ss_dis, a.up.end_dis);
+                            if (r == 0) ev = 2; else if (r == 2) ev = 3;
                         }
                     }
                 }
-                const unsigned m = __ballot_sync(FULL, ev != 0);
+                const unsigned m = (__ballot_sync(gm, ev != 0) >> sh) & (G == 32 ? 0xffffffffu : ((1u << G) - 1u));
                 if (m) {
                     const int win = __ffs(m) - 1;                // lowest lane = entry nearest to the end of T
-                    const int wev = __shfl_sync(FULL, ev, win);
-                    if (wev == 2 && lane == win) {
+                    const int wev = __shfl_sync(gm, ev, sh + win);
+                    if (wev == 2 && gl == win) {
                         a.work.cov[ec] += 1;
-                        if (t.fs < a.work.fs[ec]) { a.work.fs[ec] = t.fs; a.work.start[ec] = t.fs; }
-                        if (t.le > a.work.le[ec]) { a.work.le[ec] = t.le; a.work.end[ec] = t.le; }
+                        if (te.fs < a.work.fs[ec]) { a.work.fs[ec] = te.fs; a.work.start[ec] = te.fs; }
+                        if (te.le > a.work.le[ec]) { a.work.le[ec] = te.le; a.work.end[ec] = te.le; }
                     }
                     result = wev == 1 ? 0 : 1;
                     break;
                 }
             }
-            __syncwarp();
+            __syncwarp(gm);
             if (result == 0) {
-                if (lane == 0) {
+                if (gl == 0) {
                     tlist[ls + cnt] = (uint32_t)c; alive[c] = 1;
-                    a.work.cand[c] = (uint32_t)c; a.work.cov[c] = 1; a.work.tid[c] = t.tid; a.work.start[c] = t.start; a.work.end[c] = t.end;
-                    a.work.fs[c] = t.fs; a.work.le[c] = t.le;
+                    a.work.cov[c] = 1; a.work.start[c] = t_start; a.work.end[c] = cd.end[c]; a.work.fs[c] = te.fs; a.work.le[c] = te.le;
                 }
                 ++cnt;
-            } else if (lane == 0) alive[c] = 0;
-            __syncwarp();
+            } else if (gl == 0) alive[c] = 0;
+            __syncwarp(gm);
         }
     }
 }
 
-__global__ void merge_gather_kernel(DMerged work, const uint32_t *__restrict__ sel, int64_t n, DMerged out)
+__global__ void merge_gather_kernel(DMerged work, CandSoA cd, const uint32_t *__restrict__ sel, int64_t n, DMerged out)
 {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     uint32_t c = sel[k];
-    out.cand[k] = c; out.cov[k] = work.cov[c]; out.tid[k] = work.tid[c]; out.start[k] = work.start[c]; out.end[k] = work.end[c];
+    out.cand[k] = c; out.cov[k] = work.cov[c]; out.tid[k] = cd.tid[c]; out.start[k] = work.start[c]; out.end[k] = work.end[c];
     out.fs[k] = work.fs[c]; out.le[k] = work.le[c];
 }
 
 void launch_merge_fold(const MergeArgs &a, int64_t n_loci, cudaStream_t st)
 {
     if (n_loci <= 0) return;
-    int64_t bl = (n_loci + MF_WARPS - 1) / MF_WARPS; if (bl > 148 * 16) bl = 148 * 16;
     // tlist reuses the (no longer needed) 64-bit key scratch; alive reuses the head mask's sibling buffer `dropped`
-    merge_fold_kernel<<<(unsigned)bl, MF_WARPS * 32, 0, st>>>(a, n_loci, (uint32_t *)a.keys, a.dropped);
-    LRB_COUNT_LAUNCH();
+    {
+        constexpr int GPB = MF_THREADS / 8;
+        int64_t bl = (n_loci + GPB - 1) / GPB; if (bl > 148 * 16) bl = 148 * 16;
+        merge_fold_kernel<8, true><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, n_loci, (uint32_t *)a.keys, a.dropped);
+        LRB_COUNT_LAUNCH();
+    }
+    {
+        constexpr int GPB = MF_THREADS / 32;
+        int64_t bl = (n_loci + GPB - 1) / GPB; if (bl > 148 * 8) bl = 148 * 8;
+        merge_fold_kernel<32, false><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, n_loci, (uint32_t *)a.keys, a.dropped);
+        LRB_COUNT_LAUNCH();
+    }
 }
 void launch_merge_compact(const MergeArgs &a, int64_t n_loci, cudaStream_t st)
 {
@@ -454,7 +510,7 @@ void launch_merge_compact(const MergeArgs &a, int64_t n_loci, cudaStream_t st)
 void launch_merge_gather(const MergeArgs &a, int64_t n_out, cudaStream_t st)
 {
     if (n_out <= 0) return;
-    merge_gather_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(a.work, a.locus_cnt, n_out, a.out);
+    merge_gather_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(a.work, a.cd, a.locus_cnt, n_out, a.out);
     LRB_COUNT_LAUNCH();
 }
 

@@ -10,6 +10,7 @@
 // The reference's two monotone cursors are replaced by closed forms over prefix-max keys, which
 // makes every read independent; the order-dependent merge fold is exact per locus (App. A.6/B.3) and loci run in
 // parallel, one warp each, the warp evaluating a whole window of the back-scan per step.
+#include <cstdlib>
 #include "lrb_common.cuh"
 #include "lrb_kernels.cuh"
 
@@ -20,8 +21,6 @@ int64_t g_launches_update = 0;
 #define LRB_COUNT_LAUNCH() (++g_launches_update)
 
 static constexpr int CL_THREADS = 256;
-static constexpr int CL_G = 8;                      // lanes per read
-static constexpr int CL_SLOTS = 64;                 // exon slots per read staged in shared memory
 
 LRB_DEVINL bool ex_ovlp(int s1, int e1, int s2, int e2) { return !(s1 > e2 || s2 > e1); }
 // exon_overlap_frac (update_gtf.c:80-89): double quotient rounded to float
@@ -41,11 +40,13 @@ LRB_DEVINL int small_lower_bound(const int *a, int n, int key)
     return lo;
 }
 
-template <int G>
+// G lanes per read (power of two), CL_SLOTS exon slots per read staged in shared memory
+template <int G, int CL_SLOTS>
 __global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a)
 {
     constexpr int GPB = CL_THREADS / G;
-    constexpr int STRIDE = CL_SLOTS + 8;             // +8 words: the 4 groups of a warp land on disjoint banks
+    constexpr int STRIDE = CL_SLOTS + G;             // STRIDE = G * odd: the 32/G groups of a warp land on disjoint banks
+    static_assert(((STRIDE / G) & 1) == 1 && STRIDE % G == 0, "bank-conflict-free stride");
     __shared__ int s_es[GPB][STRIDE], s_ee[GPB][STRIDE];
     __shared__ uint8_t s_fl[GPB][STRIDE];
     const int g = threadIdx.x / G, gl = threadIdx.x % G;
@@ -246,13 +247,24 @@ __global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a)
     }
 }
 
+template <int G, int SLOTS> static void launch_classify_t(const ClassArgs &a, cudaStream_t st)
+{
+    constexpr int GPB = CL_THREADS / G;
+    int64_t bl = (a.rows.n + GPB - 1) / GPB;
+    if (bl > 148 * 64) bl = 148 * 64;
+    classify_kernel<G, SLOTS><<<(unsigned)bl, CL_THREADS, 0, st>>>(a);
+}
 void launch_classify(const ClassArgs &a, cudaStream_t st)
 {
     if (a.rows.n <= 0) return;
-    constexpr int GPB = CL_THREADS / CL_G;
-    int64_t bl = (a.rows.n + GPB - 1) / GPB;
-    if (bl > 148 * 64) bl = 148 * 64;
-    classify_kernel<CL_G><<<(unsigned)bl, CL_THREADS, 0, st>>>(a);
+    static int g = -1;
+    if (g < 0) { const char *e = getenv("LRB_CLASSIFY_G"); g = e ? atoi(e) : 8; }
+    switch (g) {
+    case 1: launch_classify_t<1, 16>(a, st); break;
+    case 2: launch_classify_t<2, 16>(a, st); break;
+    case 4: launch_classify_t<4, 16>(a, st); break;
+    default: launch_classify_t<8, 64>(a, st); break;
+    }
     LRB_COUNT_LAUNCH();
 }
 
@@ -488,10 +500,14 @@ void launch_merge_fold(const MergeArgs &a, int64_t n_loci, cudaStream_t st)
 {
     if (n_loci <= 0) return;
     // tlist reuses the (no longer needed) 64-bit key scratch; alive reuses the head mask's sibling buffer `dropped`
+    static int g = -1;
+    if (g < 0) { const char *e = getenv("LRB_FOLD_G"); g = e ? atoi(e) : 8; }
     {
-        constexpr int GPB = MF_THREADS / 8;
-        int64_t bl = (n_loci + GPB - 1) / GPB; if (bl > 148 * 16) bl = 148 * 16;
-        merge_fold_kernel<8, true><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, n_loci, (uint32_t *)a.keys, a.dropped);
+        int64_t bl = (n_loci * g + MF_THREADS - 1) / MF_THREADS; if (bl > 148 * 16) bl = 148 * 16;
+        if (g == 2) merge_fold_kernel<2, true><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, n_loci, (uint32_t *)a.keys, a.dropped);
+        else if (g == 4) merge_fold_kernel<4, true><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, n_loci, (uint32_t *)a.keys, a.dropped);
+        else if (g == 16) merge_fold_kernel<16, true><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, n_loci, (uint32_t *)a.keys, a.dropped);
+        else merge_fold_kernel<8, true><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, n_loci, (uint32_t *)a.keys, a.dropped);
         LRB_COUNT_LAUNCH();
     }
     {

@@ -21,6 +21,7 @@ int64_t g_launches_update = 0;
 #define LRB_COUNT_LAUNCH() (++g_launches_update)
 
 static constexpr int CL_THREADS = 256;
+static constexpr int CL_ITERS = 4;                    // rows per block = (CL_THREADS / G) * CL_ITERS
 
 LRB_DEVINL bool ex_ovlp(int s1, int e1, int s2, int e2) { return !(s1 > e2 || s2 > e1); }
 // exon_overlap_frac (update_gtf.c:80-89): double quotient rounded to float
@@ -49,11 +50,32 @@ __global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a)
     static_assert(((STRIDE / G) & 1) == 1 && STRIDE % G == 0, "bank-conflict-free stride");
     __shared__ int s_es[GPB][STRIDE], s_ee[GPB][STRIDE];
     __shared__ uint8_t s_fl[GPB][STRIDE];
+    __shared__ int s_win[6];                         // search windows of this block's rows: F, S, don_key lower bounds
     const int g = threadIdx.x / G, gl = threadIdx.x % G;
     const unsigned gm = group_mask<G>();
     const int dis = a.up.ss_dis, level = a.up.full_level;
 
-    for (int64_t row = (int64_t)blockIdx.x * GPB + g; row < a.rows.n; row += (int64_t)gridDim.x * GPB) {
+    // Rows are sorted by (tid,start), so the annotation cursor F(b), the SJ cursor S(b) and the first SJ row at or after
+    // the read start are monotone in the row index: six full binary searches per block bracket them for all its rows.
+    const int64_t r0 = (int64_t)blockIdx.x * GPB * CL_ITERS;
+    const int64_t r1 = min(a.rows.n, r0 + (int64_t)GPB * CL_ITERS);
+    if (threadIdx.x < 6) {
+        const int64_t rr = (threadIdx.x & 1) ? r1 - 1 : r0;
+        const int t = a.rows.tid[rr], st = a.rows.start[rr];
+        const uint64_t key = ((uint64_t)(uint32_t)(t + 1) << 32) | (uint32_t)st;
+        int v;
+        if (threadIdx.x < 2) v = (int)upper_bound_dev<uint64_t>(a.anno.pmax_key, 0, a.anno.n, key);
+        else if (threadIdx.x < 4) v = a.sj.n ? (int)upper_bound_dev<uint64_t>(a.sj.pmax_key, 0, a.sj.n, key) : 0;
+        else {
+            int wlo = st - dis; if (wlo < 0) wlo = 0;
+            v = a.sj.n ? (int)lower_bound_dev<uint64_t>(a.sj.don_key, 0, a.sj.n, (((uint64_t)(uint32_t)(t + 1)) << 32) | (uint32_t)wlo) : 0;
+        }
+        s_win[threadIdx.x] = v;
+    }
+    __syncthreads();
+    const int Flo = s_win[0], Fhi = max(s_win[0], s_win[1]), Slo = s_win[2], Shi = max(s_win[2], s_win[3]), Dlo = s_win[4], Dhi = max(s_win[4], s_win[5]);
+
+    for (int64_t row = r0 + g; row < r1; row += GPB) {
         const int n = (int)a.rows.ex_n[row];
         const uint32_t beg = a.rows.ex_beg[row];
         const int tid_b = a.rows.tid[row], start_b = a.rows.start[row], end_b = a.rows.end[row];
@@ -76,7 +98,7 @@ __global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a)
 
         // ---- annotation window: F(b) by a cooperative search on the prefix-max keys, sweep to the first "after"
         const uint64_t key_b = ((uint64_t)(uint32_t)(tid_b + 1) << 32) | (uint32_t)start_b;
-        int i = (int)group_upper_bound<G, uint64_t>(gm, gl, a.anno.pmax_key, 0, a.anno.n, key_b);
+        int i = (int)group_upper_bound<G, uint64_t>(gm, gl, a.anno.pmax_key, Flo, Fhi, key_b);
         int lfull = 0, rfull = 0, lnoth = 1, rnoth = 1, known = 0, known_site = 0, ref = -1;
         for (; i < a.anno.n; ++i) {
             const int at = a.anno.tid[i], as_ = a.anno.start[i], ae_ = a.anno.end[i];
@@ -181,7 +203,7 @@ __global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a)
         int sj_checked = 0, unreliable = 0;
         if (full && !known && known_site && a.sj.n > 0) {
             sj_checked = 1;
-            const int64_t S = group_upper_bound<G, uint64_t>(gm, gl, a.sj.pmax_key, 0, a.sj.n, key_b);
+            const int64_t S = group_upper_bound<G, uint64_t>(gm, gl, a.sj.pmax_key, Slo, Shi, key_b);
             int ok = 1;
             if (S >= a.sj.n) ok = 0;
             else {
@@ -190,20 +212,24 @@ __global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a)
                 else {
                     int bad = 0;
                     const uint64_t tk = (uint64_t)(uint32_t)(tid_b + 1) << 32;
-                    // rows that can matter have tid == tid_b and don in [start_b - dis, end_b): narrow once per read
+                    // first row with tid == tid_b and don >= start_b - dis (never below the cursor S)
                     int wlo = start_b - dis; if (wlo < 0) wlo = 0;
-                    const int64_t R0 = group_lower_bound<G, uint64_t>(gm, gl, a.sj.don_key, S, a.sj.n, tk | (uint32_t)wlo);
-                    const int64_t R1 = group_lower_bound<G, uint64_t>(gm, gl, a.sj.don_key, R0, a.sj.n, tk | (uint32_t)(end_b < 0 ? 0 : end_b));
+                    int64_t R0 = group_lower_bound<G, uint64_t>(gm, gl, a.sj.don_key, Dlo, Dhi, tk | (uint32_t)wlo);
+                    if (R0 < S) R0 = S;
                     for (int j = gl; j < n - 1; j += G) {
                         if (!(fl[j] & LRB_F_NOVEL_JUNC)) continue;
                         const int is = ee[j] + 1, ie = es[j + 1] - 1;                      // intron [is, ie]
-                        // rows with tid==tid_b, don in [is-dis, is+dis], don < ie, index >= S
+                        // rows with tid==tid_b, don in [is-dis, is+dis], don < ie, index >= S: gallop from R0, then bisect
                         int dlo = is - dis; if (dlo < 0) dlo = 0;
                         int64_t dhi = (int64_t)is + dis + 1; if (dhi > ie) dhi = ie; if (dhi < 0) dhi = 0;
-                        int64_t lo = lower_bound_dev<uint64_t>(a.sj.don_key, R0, R1, tk | (uint32_t)dlo);
+                        const uint64_t klo = tk | (uint32_t)dlo, khi = tk | (uint64_t)dhi;
+                        int64_t lo = R0, step = 1, hi = R0;
+                        while (hi < a.sj.n && a.sj.don_key[hi] < klo) { lo = hi + 1; hi += step; step <<= 1; }
+                        if (hi > a.sj.n) hi = a.sj.n;
+                        lo = lower_bound_dev<uint64_t>(a.sj.don_key, lo, hi, klo);
                         int found = 0;
-                        for (int64_t q = lo; q < R1 && !found; ++q) {
-                            if (a.sj.don_key[q] >= (tk | (uint64_t)dhi)) break;
+                        for (int64_t q = lo; q < a.sj.n && !found; ++q) {
+                            if (a.sj.don_key[q] >= khi) break;
                             if (iabs_dev(a.sj.acc[q] - ie) <= dis) {
                                 int c = a.up.use_multi ? a.sj.cnt_u[q] + a.sj.cnt_m[q] : a.sj.cnt_u[q];
                                 if (c >= a.up.min_sj_cnt) found = 1;
@@ -249,9 +275,8 @@ __global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a)
 
 template <int G, int SLOTS> static void launch_classify_t(const ClassArgs &a, cudaStream_t st)
 {
-    constexpr int GPB = CL_THREADS / G;
-    int64_t bl = (a.rows.n + GPB - 1) / GPB;
-    if (bl > 148 * 64) bl = 148 * 64;
+    constexpr int per_block = (CL_THREADS / G) * CL_ITERS;
+    int64_t bl = (a.rows.n + per_block - 1) / per_block;
     classify_kernel<G, SLOTS><<<(unsigned)bl, CL_THREADS, 0, st>>>(a);
 }
 void launch_classify(const ClassArgs &a, cudaStream_t st)

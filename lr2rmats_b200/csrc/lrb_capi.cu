@@ -233,13 +233,16 @@ DMerged merged_view(Buf &cand, Buf &cov, Buf &tid, Buf &st, Buf &en, Buf &fs, Bu
     return d;
 }
 
-// merge fold over `list` (n_cand entries); result in m (o_* arrays, n_out)
-int run_merge(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_cand, const lrb_update_params &up, bool gather)
+// merge fold over `list` (n_cand entries).  class_off != nullptr: the list is four independent sub-streams folded in one
+// launch and only the survivors per sub-stream are counted (into class_counts); else the result goes to m (o_* arrays, n_out).
+int run_merge(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_cand, const lrb_update_params &up,
+              const int64_t *class_off = nullptr, uint32_t *class_counts = nullptr)
 {
     int rc;
     if ((rc = setup_merge(c, m, n_cand)) != LRB_OK) return rc;
     if ((rc = ensure_tiles(c, n_cand)) != LRB_OK) return rc;
     m.n_out = 0; m.n_loci = 0;
+    if (class_counts) memset(class_counts, 0, 16);
     if (n_cand == 0) return LRB_OK;
     MergeArgs a{};
     a.rows = *c->cur; a.ex = c->ex; a.up = up; a.list = list; a.n_cand = n_cand;
@@ -251,20 +254,31 @@ int run_merge(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_cand, 
     a.cd.n = m.c_n.as<int32_t>(); a.cd.fs = m.c_fs.as<int32_t>(); a.cd.le = m.c_le.as<int32_t>(); a.cd.gbeg = m.c_gbeg.as<uint32_t>();
     a.cd.hash = m.c_hash.as<uint64_t>();
     a.tile_state = c->tile_state.as<uint64_t>(); a.ticket = d_ticket(c); a.totals = d_totals(c);
+    if (class_off) {
+        for (int k = 0; k < 5; ++k) a.class_off[k] = class_off[k];
+        NEED(c->y_counts, 64);
+        a.class_alive = c->y_counts.as<uint32_t>() + 8;
+        CK(cudaMemsetAsync(a.class_alive, 0, 16, c->st));
+    }
     launch_merge_prepare(a, c->st);
+    tick(c, 10);
+    launch_merge_fold(a, c->st);                     // locus count is consumed on the device: no host round trip
+    tick(c, 11);
+    if (class_off) {
+        launch_merge_class_counts(a, c->st);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(c->h_scalars.p, a.class_alive, 16, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        memcpy(class_counts, c->h_scalars.p, 16);
+        return LRB_OK;
+    }
+    launch_merge_compact(a, 0, c->st);
+    launch_merge_gather(a, n_cand, c->st);
     CK(cudaGetLastError());
     uint64_t t[2];
-    if ((rc = read_totals(c, t, 1)) != LRB_OK) return rc;
-    m.n_loci = (int64_t)t[0];
-    tick(c, 10);
-    launch_merge_fold(a, m.n_loci, c->st);
-    tick(c, 11);
-    launch_merge_compact(a, m.n_loci, c->st);
-    CK(cudaGetLastError());
     if ((rc = read_totals(c, t, 2)) != LRB_OK) return rc;
-    m.n_out = (int64_t)t[1];
-    if (c->timing && gather) cudaEventElapsedTime(&c->ms[LRB_T_K_FOLD], c->ev[10], c->ev[11]);
-    if (gather) { launch_merge_gather(a, m.n_out, c->st); CK(cudaGetLastError()); }
+    m.n_loci = (int64_t)t[0]; m.n_out = (int64_t)t[1];
+    if (c->timing) cudaEventElapsedTime(&c->ms[LRB_T_K_FOLD], c->ev[10], c->ev[11]);
     return LRB_OK;
 }
 
@@ -585,7 +599,7 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
     memset(c->summary, 0, sizeof c->summary); c->n_bed = 0; c->last_up = *up;
     NEED(c->u_cls, nn * 4); NEED(c->u_ref, nn * 4); NEED(c->u_nnovel, nn * 4); NEED(c->u_noff, (nn + 1) * 4);
     NEED(c->u_mk, nn); NEED(c->u_mu, nn); NEED(c->u_known, nn * 4); NEED(c->u_unrecog, nn * 4);
-    if (up->want_summary) { NEED(c->u_ck, nn); NEED(c->u_cr, nn); NEED(c->u_cu, nn); NEED(c->u_cn, nn); NEED(c->u_sub, nn * 4); }
+    if (up->want_summary) { NEED(c->u_ck, nn); NEED(c->u_cr, nn); NEED(c->u_cu, nn); NEED(c->u_cn, nn); NEED(c->u_sub, nn * 16); }
     if ((rc = ensure_tiles(c, std::max<int64_t>(n, c->ex.n)))) return rc;
     CK(cudaMemsetAsync(d_err(c), 0, 4, c->st));
     tick(c, 0);
@@ -614,25 +628,33 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
     CK(cudaGetLastError());
     // ---- updated_T = merge fold over novel_T
     tick(c, 2);
-    if ((rc = run_merge(c, c->mg, c->novel, n_novel, *up, true))) return rc;
+    if ((rc = run_merge(c, c->mg, c->novel, n_novel, *up))) return rc;
     tick(c, 3);
     // ---- summary
     if (up->want_summary) {
         int32_t *s = c->summary;
-        // class counts + uniq_* folds over bam_T (update_gtf.c:501-528)
-        struct { Buf *mask; int cnt_idx, uniq_idx; } cl[4] = {{&c->u_ck, LRB_S_KNOWN_TRANS, LRB_S_UNIQ_KNOWN}, {&c->u_cr, LRB_S_NOVEL_RELIABLE, LRB_S_UNIQ_RELIABLE},
-                                                             {&c->u_cu, LRB_S_NOVEL_UNRELIABLE, LRB_S_UNIQ_UNRELIABLE}, {&c->u_cn, LRB_S_UNRECOG, LRB_S_UNIQ_UNRECOG}};
-        for (auto &k : cl) {
-            launch_compact_mask(k.mask->as<uint8_t>(), n, nullptr, c->u_sub.as<uint32_t>(), nullptr, c->tile_state.as<uint64_t>(), d_ticket(c), d_totals(c), c->st);
-            CK(cudaGetLastError());
-            if ((rc = read_totals(c, t, 1))) return rc;
-            int64_t m = n ? (int64_t)t[0] : 0;
-            s[k.cnt_idx] = (int32_t)m;
-            if ((rc = setup_list(c, c->tmp_list, c->t_row, c->t_lo, c->t_cnt, c->t_piece, m))) return rc;
-            launch_rows_as_list(rows, c->u_sub.as<uint32_t>(), m, c->tmp_list, c->st);
-            if ((rc = run_merge(c, c->mg2, c->tmp_list, m, *up, false))) return rc;
-            s[k.uniq_idx] = (int32_t)c->mg2.n_out;
+        // class counts + uniq_* folds over bam_T (update_gtf.c:501-528): the four classes partition the rows, so they are
+        // laid out back to back in one candidate list and folded together (class-tagged segmentation keys keep them apart)
+        Buf *masks[4] = {&c->u_ck, &c->u_cr, &c->u_cu, &c->u_cn};
+        const int cnt_idx[4] = {LRB_S_KNOWN_TRANS, LRB_S_NOVEL_RELIABLE, LRB_S_NOVEL_UNRELIABLE, LRB_S_UNRECOG};
+        const int uniq_idx[4] = {LRB_S_UNIQ_KNOWN, LRB_S_UNIQ_RELIABLE, LRB_S_UNIQ_UNRELIABLE, LRB_S_UNIQ_UNRECOG};
+        NEED(c->u_sub, nn * 4 * 4);
+        for (int k = 0; k < 4; ++k)
+            launch_compact_mask(masks[k]->as<uint8_t>(), n, nullptr, c->u_sub.as<uint32_t>() + (size_t)k * nn, nullptr, c->tile_state.as<uint64_t>(),
+                                d_ticket(c), d_totals(c) + k, c->st);
+        CK(cudaGetLastError());
+        if ((rc = read_totals(c, t, 4))) return rc;
+        int64_t coff[5] = {0, 0, 0, 0, 0};
+        for (int k = 0; k < 4; ++k) { int64_t m = n ? (int64_t)t[k] : 0; s[cnt_idx[k]] = (int32_t)m; coff[k + 1] = coff[k] + m; }
+        if ((rc = setup_list(c, c->tmp_list, c->t_row, c->t_lo, c->t_cnt, c->t_piece, coff[4]))) return rc;
+        for (int k = 0; k < 4; ++k) {
+            DTransList part = c->tmp_list;
+            part.row += coff[k]; part.lo += coff[k]; part.cnt += coff[k]; part.piece += coff[k];
+            launch_rows_as_list(rows, c->u_sub.as<uint32_t>() + (size_t)k * nn, coff[k + 1] - coff[k], part, c->st);
         }
+        uint32_t alive[4];
+        if ((rc = run_merge(c, c->mg2, c->tmp_list, coff[4], *up, coff, alive))) return rc;
+        for (int k = 0; k < 4; ++k) s[uniq_idx[k]] = (int32_t)alive[k];
         s[LRB_S_NOVEL_BAM] = s[LRB_S_NOVEL_RELIABLE] + s[LRB_S_NOVEL_UNRELIABLE];
         // sets over updated_T
         const int64_t nu = c->mg.n_out; const size_t nun = (size_t)std::max<int64_t>(nu, 1);
@@ -699,7 +721,7 @@ int lrb_unique_run(lrb_ctx *c, const lrb_update_params *up)
     if ((rc = check_err_flags(c))) return rc;
     if ((rc = setup_list(c, c->tmp_list, c->t_row, c->t_lo, c->t_cnt, c->t_piece, n))) return rc;
     launch_rows_as_list(rows, nullptr, n, c->tmp_list, c->st);
-    if ((rc = run_merge(c, c->mg, c->tmp_list, n, *up, true))) return rc;
+    if ((rc = run_merge(c, c->mg, c->tmp_list, n, *up))) return rc;
     // shared_T = rows the fold absorbed: complement of the alive mask (kept in mg.dropped); mg.head is free again
     NEED(c->q_shared, (size_t)std::max<int64_t>(n, 1) * 4);
     c->n_shared = 0;

@@ -112,6 +112,8 @@ struct MergeArgs {
     DTransList list;                                // candidates in fold order
     const uint32_t *subset;                         // optional: rows subset as whole-read candidates (list.n==0): indices into rows
     int64_t n_cand;
+    int64_t class_off[5];                           // optional: candidate ranges of independent sub-streams (class folds); class_off[4]==0: unused
+    uint32_t *class_alive;                          // [4] surviving entries per sub-stream
     // scratch
     uint64_t *keys;                                 // per candidate (tid+1)<<32|real_end, then prefix max
     uint8_t *head;                                  // locus head flags
@@ -123,7 +125,8 @@ struct MergeArgs {
     uint64_t *tile_state; uint32_t *ticket; uint64_t *totals;  // [0] n_loci, [1] n_out
 };
 void launch_merge_prepare(const MergeArgs &a, cudaStream_t st);     // keys + prefix max + heads
-void launch_merge_fold(const MergeArgs &a, int64_t n_loci, cudaStream_t st);
+void launch_merge_fold(const MergeArgs &a, cudaStream_t st);            // number of loci is read from a.totals[0] on the device
+void launch_merge_class_counts(const MergeArgs &a, cudaStream_t st);
 void launch_merge_compact(const MergeArgs &a, int64_t n_loci, cudaStream_t st);
 
 // generic device scans used by the stages above

@@ -283,7 +283,7 @@ void launch_classify(const ClassArgs &a, cudaStream_t st)
 {
     if (a.rows.n <= 0) return;
     static int g = -1;
-    if (g < 0) { const char *e = getenv("LRB_CLASSIFY_G"); g = e ? atoi(e) : 8; }
+    if (g < 0) { const char *e = getenv("LRB_CLASSIFY_G"); g = e ? atoi(e) : 4; }
     switch (g) {
     case 1: launch_classify_t<1, 16>(a, st); break;
     case 2: launch_classify_t<2, 16>(a, st); break;
@@ -367,6 +367,15 @@ void launch_rows_as_list(const DRows &rows, const uint32_t *subset, int64_t n, D
 //   fs/le             : exon[0].start, exon[n-1].end                               hash    : of the internal boundaries
 LRB_DEVINL uint64_t mixh(uint64_t h, uint32_t v) { h ^= v; h *= 0x9E3779B97F4A7C15ull; h ^= h >> 29; return h; }
 
+// independent sub-streams folded in one launch: the tag sits above the tid bits of the segmentation keys, so a new
+// sub-stream always starts a new locus
+LRB_DEVINL uint64_t class_tag(const MergeArgs &a, int64_t c)
+{
+    if (a.class_off[4] == 0) return 0;
+    int k = (c >= a.class_off[1]) + (c >= a.class_off[2]) + (c >= a.class_off[3]);
+    return (uint64_t)k << 56;
+}
+
 __global__ void merge_cand_kernel(MergeArgs a)
 {
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -385,14 +394,14 @@ __global__ void merge_cand_kernel(MergeArgs a)
     uint64_t h = 0x243F6A8885A308D3ull ^ (uint64_t)n;
     for (int i = 0; i < n - 1; ++i) { h = mixh(h, (uint32_t)a.ex.ee[gb + i]); h = mixh(h, (uint32_t)a.ex.es[gb + i + 1]); }
     a.cd.hash[c] = h;
-    a.keys[c] = ((uint64_t)(uint32_t)(rtid + 1) << 32) | (uint32_t)le;          // real coordinates: locus segmentation
+    a.keys[c] = class_tag(a, c) | ((uint64_t)(uint32_t)(rtid + 1) << 32) | (uint32_t)le;   // real coordinates: locus segmentation
 }
 __global__ void merge_heads_kernel(MergeArgs a)
 {
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_cand) return;
     const uint32_t row = a.list.row[c];
-    uint64_t k = ((uint64_t)(uint32_t)(a.rows.tid[row] + 1) << 32) | (uint32_t)a.cd.fs[c];
+    uint64_t k = class_tag(a, c) | ((uint64_t)(uint32_t)(a.rows.tid[row] + 1) << 32) | (uint32_t)a.cd.fs[c];
     a.head[c] = (c == 0 || k > a.keys[c - 1]) ? 1 : 0;   // new locus: start beyond every earlier end on this chromosome
 }
 void launch_merge_prepare(const MergeArgs &a, cudaStream_t st)
@@ -453,8 +462,9 @@ static constexpr int MF_THREADS = 128;
 static constexpr int MF_SMALL = 48;                 // loci up to this many candidates go to 8-lane groups
 // G lanes per locus; tlist[ls + k] = candidate index of the k-th entry of the locus' T; mutable entry data lives at work[cand]
 template <int G, bool SMALL>
-__global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, int64_t n_loci, uint32_t *tlist, uint8_t *alive)
+__global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uint32_t *tlist, uint8_t *alive)
 {
+    const int64_t n_loci = (int64_t)a.totals[0];
     constexpr int GPB = MF_THREADS / G;
     const int gl = threadIdx.x % G;
     const unsigned gm = group_mask<G>();
@@ -512,46 +522,63 @@ __global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, int
     }
 }
 
-__global__ void merge_gather_kernel(DMerged work, CandSoA cd, const uint32_t *__restrict__ sel, int64_t n, DMerged out)
+__global__ void merge_gather_kernel(DMerged work, CandSoA cd, const uint32_t *__restrict__ sel, const uint64_t *__restrict__ n_dev, DMerged out)
 {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
+    if (k >= (int64_t)*n_dev) return;
     uint32_t c = sel[k];
     out.cand[k] = c; out.cov[k] = work.cov[c]; out.tid[k] = cd.tid[c]; out.start[k] = work.start[c]; out.end[k] = work.end[c];
     out.fs[k] = work.fs[c]; out.le[k] = work.le[c];
 }
 
-void launch_merge_fold(const MergeArgs &a, int64_t n_loci, cudaStream_t st)
+void launch_merge_fold(const MergeArgs &a, cudaStream_t st)
 {
-    if (n_loci <= 0) return;
-    // tlist reuses the (no longer needed) 64-bit key scratch; alive reuses the head mask's sibling buffer `dropped`
+    if (a.n_cand <= 0) return;
+    // tlist reuses the (no longer needed) 64-bit key scratch; alive reuses the head mask's sibling buffer `dropped`.
+    // Grids are sized for the worst case (every candidate its own locus); the locus count is read on the device.
     static int g = -1;
     if (g < 0) { const char *e = getenv("LRB_FOLD_G"); g = e ? atoi(e) : 8; }
     {
-        int64_t bl = (n_loci * g + MF_THREADS - 1) / MF_THREADS; if (bl > 148 * 16) bl = 148 * 16;
-        if (g == 2) merge_fold_kernel<2, true><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, n_loci, (uint32_t *)a.keys, a.dropped);
-        else if (g == 4) merge_fold_kernel<4, true><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, n_loci, (uint32_t *)a.keys, a.dropped);
-        else if (g == 16) merge_fold_kernel<16, true><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, n_loci, (uint32_t *)a.keys, a.dropped);
-        else merge_fold_kernel<8, true><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, n_loci, (uint32_t *)a.keys, a.dropped);
+        int64_t bl = (a.n_cand * g + MF_THREADS - 1) / MF_THREADS; if (bl > 148 * 16) bl = 148 * 16;
+        if (g == 4) merge_fold_kernel<4, true><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped);
+        else if (g == 16) merge_fold_kernel<16, true><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped);
+        else merge_fold_kernel<8, true><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped);
         LRB_COUNT_LAUNCH();
     }
     {
-        constexpr int GPB = MF_THREADS / 32;
-        int64_t bl = (n_loci + GPB - 1) / GPB; if (bl > 148 * 8) bl = 148 * 8;
-        merge_fold_kernel<32, false><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, n_loci, (uint32_t *)a.keys, a.dropped);
+        int64_t bl = (a.n_cand / MF_SMALL + 1 + 3) / 4; if (bl > 148 * 8) bl = 148 * 8;     // a large locus has > MF_SMALL candidates
+        merge_fold_kernel<32, false><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped);
         LRB_COUNT_LAUNCH();
     }
 }
+
+__global__ void merge_class_counts_kernel(MergeArgs a, const uint8_t *__restrict__ alive)
+{
+    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int k = -1;
+    if (c < a.n_cand && alive[c]) k = (c >= a.class_off[1]) + (c >= a.class_off[2]) + (c >= a.class_off[3]);
+    for (int q = 0; q < 4; ++q) {
+        unsigned m = __ballot_sync(FULL, k == q);
+        if (m && lane_id() == 0) atomicAdd(&a.class_alive[q], (uint32_t)__popc(m));
+    }
+}
+void launch_merge_class_counts(const MergeArgs &a, cudaStream_t st)
+{
+    if (a.n_cand <= 0) return;
+    merge_class_counts_kernel<<<(unsigned)((a.n_cand + 255) / 256), 256, 0, st>>>(a, a.dropped);
+    LRB_COUNT_LAUNCH();
+}
+
 void launch_merge_compact(const MergeArgs &a, int64_t n_loci, cudaStream_t st)
 {
     (void)n_loci;
     // a.dropped holds the alive mask; a.locus_cnt is scratch for the compacted candidate ids
     launch_compact_mask(a.dropped, a.n_cand, nullptr, a.locus_cnt, nullptr, a.tile_state, a.ticket, a.totals + 1, st);
 }
-void launch_merge_gather(const MergeArgs &a, int64_t n_out, cudaStream_t st)
+void launch_merge_gather(const MergeArgs &a, int64_t n_upper, cudaStream_t st)
 {
-    if (n_out <= 0) return;
-    merge_gather_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(a.work, a.cd, a.locus_cnt, n_out, a.out);
+    if (n_upper <= 0) return;
+    merge_gather_kernel<<<(unsigned)((n_upper + 255) / 256), 256, 0, st>>>(a.work, a.cd, a.locus_cnt, a.totals + 1, a.out);
     LRB_COUNT_LAUNCH();
 }
 

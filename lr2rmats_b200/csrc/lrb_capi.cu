@@ -47,7 +47,7 @@ struct MergeBufs {                                  // scratch + output of one m
     Buf keys, head, locus_start, locus_cnt, dropped;
     Buf w_cand, w_cov, w_tid, w_start, w_end, w_fs, w_le;
     Buf o_cand, o_cov, o_tid, o_start, o_end, o_fs, o_le;
-    Buf c_tid, c_start, c_end, c_rev, c_n, c_fs, c_le, c_gbeg, c_hash;
+    Buf c_tid, c_start, c_end, c_rev, c_n, c_fs, c_le, c_gbeg, c_hash, c_j0, c_sig;
     int64_t n_out = 0, n_loci = 0;
 };
 
@@ -223,7 +223,7 @@ int setup_merge(lrb_ctx *c, MergeBufs &m, int64_t n_cand)
     for (Buf *b : w) NEED(*b, n * 4);
     Buf *cb[] = {&m.c_tid, &m.c_start, &m.c_end, &m.c_rev, &m.c_n, &m.c_fs, &m.c_le, &m.c_gbeg};
     for (Buf *b : cb) NEED(*b, n * 4);
-    NEED(m.c_hash, n * 8);
+    NEED(m.c_hash, n * 8); NEED(m.c_j0, n * 8); NEED(m.c_sig, n * 8);
     return LRB_OK;
 }
 DMerged merged_view(Buf &cand, Buf &cov, Buf &tid, Buf &st, Buf &en, Buf &fs, Buf &le, int64_t n)
@@ -252,7 +252,7 @@ int run_merge(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_cand, 
     a.out = merged_view(m.o_cand, m.o_cov, m.o_tid, m.o_start, m.o_end, m.o_fs, m.o_le, n_cand);
     a.cd.tid = m.c_tid.as<int32_t>(); a.cd.start = m.c_start.as<int32_t>(); a.cd.end = m.c_end.as<int32_t>(); a.cd.rev = m.c_rev.as<int32_t>();
     a.cd.n = m.c_n.as<int32_t>(); a.cd.fs = m.c_fs.as<int32_t>(); a.cd.le = m.c_le.as<int32_t>(); a.cd.gbeg = m.c_gbeg.as<uint32_t>();
-    a.cd.hash = m.c_hash.as<uint64_t>();
+    a.cd.hash = m.c_hash.as<uint64_t>(); a.cd.j0 = m.c_j0.as<uint64_t>(); a.cd.sig = m.c_sig.as<uint64_t>();
     a.tile_state = c->tile_state.as<uint64_t>(); a.ticket = d_ticket(c); a.totals = d_totals(c);
     if (class_off) {
         for (int k = 0; k < 5; ++k) a.class_off[k] = class_off[k];
@@ -338,7 +338,7 @@ void lrb_ctx_destroy(lrb_ctx *c)
     for (MergeBufs *m : {&c->mg, &c->mg2}) {
         Buf *w[] = {&m->keys, &m->head, &m->locus_start, &m->locus_cnt, &m->dropped, &m->w_cand, &m->w_cov, &m->w_tid, &m->w_start, &m->w_end, &m->w_fs,
                     &m->w_le, &m->o_cand, &m->o_cov, &m->o_tid, &m->o_start, &m->o_end, &m->o_fs, &m->o_le,
-                    &m->c_tid, &m->c_start, &m->c_end, &m->c_rev, &m->c_n, &m->c_fs, &m->c_le, &m->c_gbeg, &m->c_hash};
+                    &m->c_tid, &m->c_start, &m->c_end, &m->c_rev, &m->c_n, &m->c_fs, &m->c_le, &m->c_gbeg, &m->c_hash, &m->c_j0, &m->c_sig};
         for (Buf *b : w) b->release();
     }
     for (PBuf &p : c->p) p.release();

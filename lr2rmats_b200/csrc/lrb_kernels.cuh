@@ -106,6 +106,8 @@ struct DMerged {
 struct CandSoA {                                    // flattened fold candidates (see merge_cand_kernel)
     int32_t *tid = nullptr, *start = nullptr, *end = nullptr, *rev = nullptr, *n = nullptr, *fs = nullptr, *le = nullptr;
     uint32_t *gbeg = nullptr; uint64_t *hash = nullptr;
+    uint64_t *j0 = nullptr;                         // first junction (exon[0].end << 32 | exon[1].start), 0 for single-exon chains
+    uint64_t *sig = nullptr;                        // 64-bit membership signature of all junctions of the chain
 };
 struct MergeArgs {
     DRows rows; DExons ex; lrb_update_params up; CandSoA cd;

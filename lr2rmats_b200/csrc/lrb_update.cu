@@ -366,6 +366,7 @@ void launch_rows_as_list(const DRows &rows, const uint32_t *subset, int64_t n, D
 //   tid/start/end/rev : trans_t fields (0/0/0/0 for split pieces)      n, gbeg : exon slots in the pools
 //   fs/le             : exon[0].start, exon[n-1].end                               hash    : of the internal boundaries
 LRB_DEVINL uint64_t mixh(uint64_t h, uint32_t v) { h ^= v; h *= 0x9E3779B97F4A7C15ull; h ^= h >> 29; return h; }
+LRB_DEVINL int junc_bit(uint64_t jk) { jk *= 0xD6E8FEB86659FD93ull; return (int)(jk >> 58); }
 
 // independent sub-streams folded in one launch: the tag sits above the tid bits of the segmentation keys, so a new
 // sub-stream always starts a new locus
@@ -391,9 +392,15 @@ __global__ void merge_cand_kernel(MergeArgs a)
     for (int i = 0; i + 1 < n - 1; ++i) if (a.ex.ee[gb + i] > a.ex.ee[gb + i + 1]) { mono = 0; break; }
     a.cd.rev[c] = (piece ? 0 : a.rows.is_rev[row]) | mono;
     a.cd.n[c] = n; a.cd.gbeg[c] = gb; a.cd.fs[c] = fs; a.cd.le[c] = le;
-    uint64_t h = 0x243F6A8885A308D3ull ^ (uint64_t)n;
-    for (int i = 0; i < n - 1; ++i) { h = mixh(h, (uint32_t)a.ex.ee[gb + i]); h = mixh(h, (uint32_t)a.ex.es[gb + i + 1]); }
-    a.cd.hash[c] = h;
+    uint64_t h = 0x243F6A8885A308D3ull ^ (uint64_t)n, sig = 0, j0 = 0;
+    for (int i = 0; i < n - 1; ++i) {
+        const uint32_t e = (uint32_t)a.ex.ee[gb + i], s2 = (uint32_t)a.ex.es[gb + i + 1];
+        h = mixh(h, e); h = mixh(h, s2);
+        const uint64_t jk = ((uint64_t)e << 32) | s2;
+        if (i == 0) j0 = jk;
+        sig |= 1ull << (junc_bit(jk));
+    }
+    a.cd.hash[c] = h; a.cd.j0[c] = j0; a.cd.sig[c] = sig;
     a.keys[c] = class_tag(a, c) | ((uint64_t)(uint32_t)(rtid + 1) << 32) | (uint32_t)le;   // real coordinates: locus segmentation
 }
 __global__ void merge_heads_kernel(MergeArgs a)
@@ -415,7 +422,7 @@ void launch_merge_prepare(const MergeArgs &a, cudaStream_t st)
 }
 
 // check_iden (gtf.c:54-92) between candidate t and fold entry E (first start / last end may have been extended)
-struct Entry { int n; uint32_t gbeg; int fs, le; uint64_t hash; int mono; };
+struct Entry { int n; uint32_t gbeg; int fs, le; uint64_t hash; int mono; uint64_t j0, sig; };
 LRB_DEVINL int x_s(const DExons &ex, const Entry &e, int i) { return i == 0 ? e.fs : ex.es[e.gbeg + i]; }
 LRB_DEVINL int x_e(const DExons &ex, const Entry &e, int i) { return i == e.n - 1 ? e.le : ex.ee[e.gbeg + i]; }
 LRB_DEVINL int chain_iden(const DExons &ex, const Entry &t1, const Entry &t2, int ss_dis, int end_dis)
@@ -433,7 +440,8 @@ LRB_DEVINL int chain_iden(const DExons &ex, const Entry &t1, const Entry &t2, in
     }
     int pm = -1;
     if (iabs_dev(l.fs - s.fs) > end_dis) return -1;
-    const int s_e0 = ex.ee[s.gbeg], s_s1 = ex.es[s.gbeg + 1];    // s has >= 2 exons: both are pool values
+    if (ss_dis == 0 && !((l.sig >> junc_bit(s.j0)) & 1ull)) return -1;   // the first junction of s is not a junction of l
+    const int s_e0 = (int)(uint32_t)(s.j0 >> 32), s_s1 = (int)(uint32_t)s.j0;   // s has >= 2 exons
     int i = 0;
     const bool jump = ss_dis == 0 && l.mono;
     if (jump) {                                                  // exon ends of this chain never decrease: jump to the first candidate
@@ -459,7 +467,7 @@ LRB_DEVINL int chain_iden(const DExons &ex, const Entry &t1, const Entry &t2, in
 }
 
 static constexpr int MF_THREADS = 128;
-static constexpr int MF_SMALL = 48;                 // loci up to this many candidates go to 8-lane groups
+static constexpr int MF_SMALL = 32;                 // loci up to this many candidates are folded in shared memory (== MF_SLAB)
 // G lanes per locus; tlist[ls + k] = candidate index of the k-th entry of the locus' T; mutable entry data lives at work[cand]
 template <int G, bool SMALL>
 __global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uint32_t *tlist, uint8_t *alive)
@@ -476,7 +484,7 @@ __global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uin
         int cnt = 0;
         for (int64_t c = ls; c < le; ++c) {
             const int t_tid = cd.tid[c], t_start = cd.start[c], t_rv = cd.rev[c], t_rev = t_rv & 1;
-            const Entry te = {cd.n[c], cd.gbeg[c], cd.fs[c], cd.le[c], cd.hash[c], t_rv & 2};
+            const Entry te = {cd.n[c], cd.gbeg[c], cd.fs[c], cd.le[c], cd.hash[c], t_rv & 2, cd.j0[c], cd.sig[c]};
             int result = 0;                                      // 0 append, 1 absorbed / dropped
             for (int base = cnt - 1; base >= 0; base -= G) {
                 const int k = base - gl;
@@ -486,7 +494,7 @@ __global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uin
                     ec = tlist[ls + k];
                     if (t_tid > cd.tid[ec] || t_start > a.work.end[ec]) ev = 1;                       // update_gtf.c:148
                     else if (!(a.up.force_strand && t_rev != (cd.rev[ec] & 1))) {                     // :149
-                        const Entry E = {cd.n[ec], cd.gbeg[ec], a.work.fs[ec], a.work.le[ec], cd.hash[ec], cd.rev[ec] & 2};
+                        const Entry E = {cd.n[ec], cd.gbeg[ec], a.work.fs[ec], a.work.le[ec], cd.hash[ec], cd.rev[ec] & 2, cd.j0[ec], cd.sig[ec]};
                         if (te.n == 1 && E.n == 1) {                                                  // merge_trans2 :122-140
                             if (iabs_dev(te.fs - E.fs) <= a.up.end_dis && iabs_dev(te.le - E.le) <= a.up.end_dis &&
                                 ovlp_frac(te.fs, te.le, E.fs, E.le) >= a.up.single_exon_ovlp_frac) ev = 2;
@@ -522,6 +530,86 @@ __global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uin
     }
 }
 
+// Small loci (<= MF_SLAB candidates): the whole fold state of a locus lives in a shared-memory slab of its 8-lane group --
+// static candidate fields are loaded once, cooperatively and coalesced; the back-scan, the event arbitration and the
+// cov / end extensions run on shared memory; only a verified identical chain or a signature hit of a partial match touches
+// the exon pools.  Results (alive mask, mutable fields of survivors) are written back once.
+static constexpr int MF_SLAB = 32;
+struct __align__(16) Slab {
+    int tid[MF_SLAB], start[MF_SLAB], end[MF_SLAB], rv[MF_SLAB], n[MF_SLAB], fs[MF_SLAB], le[MF_SLAB], cov[MF_SLAB];
+    uint32_t gbeg[MF_SLAB];
+    uint64_t hash[MF_SLAB], j0[MF_SLAB], sig[MF_SLAB];
+    uint8_t tl[MF_SLAB], alive[MF_SLAB];
+};
+__global__ void __launch_bounds__(MF_THREADS) merge_fold_small_kernel(MergeArgs a, uint8_t *alive)
+{
+    constexpr int G = 8, GPB = MF_THREADS / G;
+    __shared__ Slab slabs[GPB];
+    const int gl = threadIdx.x % G, sh = (lane_id() / G) * G;
+    const unsigned gm = group_mask<G>();
+    Slab &S = slabs[threadIdx.x / G];
+    const CandSoA &cd = a.cd;
+    const int64_t n_loci = (int64_t)a.totals[0];
+    for (int64_t loc = (int64_t)blockIdx.x * GPB + threadIdx.x / G; loc < n_loci; loc += (int64_t)gridDim.x * GPB) {
+        const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : a.n_cand;
+        const int m = (int)(le - ls);
+        if (m > MF_SLAB) continue;                               // large loci: merge_fold_kernel<32,false>
+        __syncwarp(gm);
+        for (int k = gl; k < m; k += G) {
+            const int64_t c = ls + k;
+            S.tid[k] = cd.tid[c]; S.start[k] = cd.start[c]; S.end[k] = cd.end[c]; S.rv[k] = cd.rev[c]; S.n[k] = cd.n[c];
+            S.fs[k] = cd.fs[c]; S.le[k] = cd.le[c]; S.gbeg[k] = cd.gbeg[c]; S.hash[k] = cd.hash[c]; S.j0[k] = cd.j0[c]; S.sig[k] = cd.sig[c];
+            S.cov[k] = 1; S.alive[k] = 0;
+        }
+        __syncwarp(gm);
+        int cnt = 0;
+        for (int c = 0; c < m; ++c) {
+            const int t_tid = S.tid[c], t_start = S.start[c], t_rev = S.rv[c] & 1;
+            const Entry te = {S.n[c], S.gbeg[c], S.fs[c], S.le[c], S.hash[c], S.rv[c] & 2, S.j0[c], S.sig[c]};
+            int result = 0;
+            for (int base = cnt - 1; base >= 0; base -= G) {
+                const int k = base - gl;
+                int ev = 0, ec = 0;
+                if (k >= 0) {
+                    ec = S.tl[k];
+                    if (t_tid > S.tid[ec] || t_start > S.end[ec]) ev = 1;
+                    else if (!(a.up.force_strand && t_rev != (S.rv[ec] & 1))) {
+                        const Entry E = {S.n[ec], S.gbeg[ec], S.fs[ec], S.le[ec], S.hash[ec], S.rv[ec] & 2, S.j0[ec], S.sig[ec]};
+                        if (te.n == 1 && E.n == 1) {
+                            if (iabs_dev(te.fs - E.fs) <= a.up.end_dis && iabs_dev(te.le - E.le) <= a.up.end_dis &&
+                                ovlp_frac(te.fs, te.le, E.fs, E.le) >= a.up.single_exon_ovlp_frac) ev = 2;
+                        } else if (te.n > 1 && E.n > 1) {
+                            int r = chain_iden(a.ex, te, E, a.up.ss_dis, a.up.end_dis);
+                            if (r == 0) ev = 2; else if (r == 2) ev = 3;
+                        }
+                    }
+                }
+                const unsigned mk = (__ballot_sync(gm, ev != 0) >> sh) & 0xffu;
+                if (mk) {
+                    const int win = __ffs(mk) - 1;
+                    const int wev = __shfl_sync(gm, ev, sh + win);
+                    if (wev == 2 && gl == win) {
+                        S.cov[ec] += 1;
+                        if (te.fs < S.fs[ec]) { S.fs[ec] = te.fs; S.start[ec] = te.fs; }
+                        if (te.le > S.le[ec]) { S.le[ec] = te.le; S.end[ec] = te.le; }
+                    }
+                    result = wev == 1 ? 0 : 1;
+                    break;
+                }
+            }
+            __syncwarp(gm);
+            if (result == 0) { if (gl == 0) { S.tl[cnt] = (uint8_t)c; S.alive[c] = 1; } ++cnt; }
+            __syncwarp(gm);
+        }
+        for (int k = gl; k < m; k += G) {
+            const int64_t c = ls + k;
+            const uint8_t al = S.alive[k];
+            alive[c] = al;
+            if (al) { a.work.cov[c] = S.cov[k]; a.work.start[c] = S.start[k]; a.work.end[c] = S.end[k]; a.work.fs[c] = S.fs[k]; a.work.le[c] = S.le[k]; }
+        }
+    }
+}
+
 __global__ void merge_gather_kernel(DMerged work, CandSoA cd, const uint32_t *__restrict__ sel, const uint64_t *__restrict__ n_dev, DMerged out)
 {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -536,13 +624,10 @@ void launch_merge_fold(const MergeArgs &a, cudaStream_t st)
     if (a.n_cand <= 0) return;
     // tlist reuses the (no longer needed) 64-bit key scratch; alive reuses the head mask's sibling buffer `dropped`.
     // Grids are sized for the worst case (every candidate its own locus); the locus count is read on the device.
-    static int g = -1;
-    if (g < 0) { const char *e = getenv("LRB_FOLD_G"); g = e ? atoi(e) : 8; }
     {
-        int64_t bl = (a.n_cand * g + MF_THREADS - 1) / MF_THREADS; if (bl > 148 * 16) bl = 148 * 16;
-        if (g == 4) merge_fold_kernel<4, true><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped);
-        else if (g == 16) merge_fold_kernel<16, true><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped);
-        else merge_fold_kernel<8, true><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped);
+        constexpr int GPB = MF_THREADS / 8;
+        int64_t bl = (a.n_cand + GPB - 1) / GPB; if (bl > 148 * 12) bl = 148 * 12;
+        merge_fold_small_kernel<<<(unsigned)bl, MF_THREADS, 0, st>>>(a, a.dropped);
         LRB_COUNT_LAUNCH();
     }
     {

@@ -469,8 +469,8 @@ LRB_DEVINL int chain_iden(const DExons &ex, const Entry &t1, const Entry &t2, in
 static constexpr int MF_THREADS = 128;
 static constexpr int MF_SMALL = 32;                 // loci up to this many candidates are folded in shared memory (== MF_SLAB)
 // G lanes per locus; tlist[ls + k] = candidate index of the k-th entry of the locus' T; mutable entry data lives at work[cand]
-template <int G, bool SMALL>
-__global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uint32_t *tlist, uint8_t *alive)
+template <int G>
+__global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uint32_t *tlist, uint8_t *alive, const uint8_t *locus_hard, int min_m)
 {
     const int64_t n_loci = (int64_t)a.totals[0];
     constexpr int GPB = MF_THREADS / G;
@@ -480,7 +480,7 @@ __global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uin
     const CandSoA &cd = a.cd;
     for (int64_t loc = (int64_t)blockIdx.x * GPB + threadIdx.x / G; loc < n_loci; loc += (int64_t)gridDim.x * GPB) {
         const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : a.n_cand;
-        if (SMALL != (le - ls <= MF_SMALL)) continue;
+        if (le - ls < min_m && !(locus_hard && locus_hard[ls])) continue;    // smaller loci were folded by the flat kernels
         int cnt = 0;
         for (int64_t c = ls; c < le; ++c) {
             const int t_tid = cd.tid[c], t_start = cd.start[c], t_rv = cd.rev[c], t_rev = t_rv & 1;
@@ -610,6 +610,152 @@ __global__ void __launch_bounds__(MF_THREADS) merge_fold_small_kernel(MergeArgs 
     }
 }
 
+// ------------------------------------------------------------------------------------------ flat fold (ss_dis == 0)
+// With exact splice-site matching the relation between two multi-exon chains is STATIC (internal boundaries only; the
+// mutable first start / last end enter through the end_dis tests alone), identity is transitive, and the partial-match
+// relation is a relation between identity classes.  That moves every exon-pool access out of the ordered part:
+//   fold_rep_kernel   thread per candidate: its identity class = first earlier candidate of the locus with the same
+//                     (exon count, chain hash[, strand]), verified once on the pools (a hash collision marks the locus
+//                     "hard": it is left to merge_fold_kernel);
+//   fold_rel_kernel   thread per candidate: bit mask (over the <= 64 earlier candidates of its locus) of the entries that
+//                     could absorb it -- same class, a class in partial-match relation (junction-signature pre-filter,
+//                     verified on the pools, decided once per class representative), other single-exon reads;
+//   fold_seq_kernel   thread per locus: the ordered fold itself on that mask and an alive mask held in registers: walk
+//                     the alive entries from the newest, stop on the reference's stop rule (dynamic end), take the first
+//                     confirmed event.  A warp folds 32 loci in lock step.
+static constexpr int FF_MAX = 64;                   // loci up to this many candidates; larger ones -> merge_fold_kernel
+static constexpr uint32_t FF_BIG = 0xffffffffu;
+
+// does the chain s (fewer exons) continue the chain l from the first occurrence of its first junction on?  (gtf.c:79-88, dis 0)
+LRB_DEVINL bool partial_static(const DExons &ex, uint32_t l_gbeg, int l_n, bool l_mono, uint64_t s_j0, uint32_t s_gbeg, int s_n)
+{
+    const int s_e0 = (int)(uint32_t)(s_j0 >> 32), s_s1 = (int)(uint32_t)s_j0;
+    int i = 0;
+    if (l_mono) {
+        int lo = 0, hi = l_n - 1;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (ex.ee[l_gbeg + mid] < s_e0) lo = mid + 1; else hi = mid; }
+        i = lo;
+    }
+    for (; i < l_n - 1; ++i) {
+        const int le_i = ex.ee[l_gbeg + i];
+        if (l_mono && le_i > s_e0) return false;
+        if (le_i == s_e0 && ex.es[l_gbeg + i + 1] == s_s1) {
+            int j = 1;
+            for (i = i + 1; i < l_n - 1 && j < s_n - 1; ++i, ++j) {
+                if (ex.ee[l_gbeg + i] != ex.ee[s_gbeg + j]) return false;
+                if (ex.es[l_gbeg + i + 1] != ex.es[s_gbeg + j + 1]) return false;
+            }
+            return true;
+        }
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(256) fold_rep_kernel(MergeArgs a, uint32_t *__restrict__ rep, uint32_t *__restrict__ lstart, uint8_t *locus_hard)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_cand) return;
+    const CandSoA &cd = a.cd;
+    const bool force = a.up.force_strand != 0;
+    const int nc = cd.n[c], rvc = cd.rev[c] & 1;
+    const uint64_t hc = cd.hash[c];
+    int64_t e = c, r = c;
+    int steps = 0;
+    while (!a.head[e]) {
+        if (++steps >= FF_MAX) { lstart[c] = FF_BIG; rep[c] = (uint32_t)c; return; }      // deeper than the masks reach
+        --e;
+        if (nc > 1 && cd.n[e] == nc && cd.hash[e] == hc && (!force || (cd.rev[e] & 1) == rvc)) r = e;
+    }
+    if (r != c) {
+        const uint32_t gc = cd.gbeg[c], gr = cd.gbeg[r];
+        bool same = true;
+        for (int i = 0; i < nc - 1; ++i)
+            same = same && a.ex.ee[gc + i] == a.ex.ee[gr + i] && a.ex.es[gc + i + 1] == a.ex.es[gr + i + 1];
+        if (!same) locus_hard[e] = 1;
+    }
+    rep[c] = (uint32_t)r; lstart[c] = (uint32_t)e;
+}
+
+__global__ void __launch_bounds__(256) fold_rel_kernel(MergeArgs a, const uint32_t *__restrict__ rep, const uint32_t *__restrict__ lstart, uint64_t *__restrict__ evmask)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_cand) return;
+    const CandSoA &cd = a.cd;
+    const uint32_t ls = lstart[c];
+    if (ls == FF_BIG) return;
+    const bool force = a.up.force_strand != 0;
+    const int nc = cd.n[c], rvc = cd.rev[c];
+    const uint32_t rc = rep[c];
+    uint64_t mask = 0;
+    if (nc == 1) {
+        for (uint32_t e = ls; e < (uint32_t)c; ++e)
+            if (cd.n[e] == 1 && (!force || ((cd.rev[e] ^ rvc) & 1) == 0)) mask |= 1ull << (e - ls);
+    } else {
+        const uint64_t sig_c = cd.sig[c], j0_c = cd.j0[c];
+        const uint32_t gb_c = cd.gbeg[c];
+        for (uint32_t e = ls; e < (uint32_t)c; ++e) {
+            const int ne = cd.n[e];
+            if (ne <= 1) continue;
+            const uint32_t re = rep[e];
+            const uint64_t bit = 1ull << (e - ls);
+            if (re != e) { if ((mask >> (re - ls)) & 1ull) mask |= bit; continue; }       // as its representative (decided before)
+            if (ne == nc) { if (re == rc) mask |= bit; continue; }
+            const int rve = cd.rev[e];
+            if (force && ((rve ^ rvc) & 1)) continue;
+            bool hit;
+            if (nc > ne) {
+                const uint64_t j0_e = cd.j0[e];
+                hit = ((sig_c >> junc_bit(j0_e)) & 1ull) && partial_static(a.ex, gb_c, nc, (rvc & 2) != 0, j0_e, cd.gbeg[e], ne);
+            } else
+                hit = ((cd.sig[e] >> junc_bit(j0_c)) & 1ull) && partial_static(a.ex, cd.gbeg[e], ne, (rve & 2) != 0, j0_c, gb_c, nc);
+            if (hit) mask |= bit;
+        }
+    }
+    evmask[c] = mask;
+}
+
+__global__ void __launch_bounds__(128) fold_seq_kernel(MergeArgs a, const uint32_t *__restrict__ rep, const uint64_t *__restrict__ evmask,
+                                                       const uint8_t *__restrict__ locus_hard, uint8_t *alive_out)
+{
+    const int64_t loc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t n_loci = (int64_t)a.totals[0];
+    if (loc >= n_loci) return;
+    const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : a.n_cand;
+    if (le - ls > FF_MAX || locus_hard[ls]) return;
+    const int m = (int)(le - ls);
+    const CandSoA &cd = a.cd;
+    const int end_dis = a.up.end_dis;
+    uint64_t alive = 0;
+    for (int k = 0; k < m; ++k) {
+        const int64_t c = ls + k;
+        const int t_tid = cd.tid[c], t_start = cd.start[c], nc = cd.n[c], fs = cd.fs[c], lend = cd.le[c];
+        const uint64_t ev = evmask[c];
+        uint64_t scan = alive;
+        int kind = 0; int64_t hit = 0;                                // kind: 0 append, 1 merge (identical), 2 drop (partial)
+        while (scan & ev) {                                           // no candidate event left below: append whatever the stops say
+            const int b = 63 - __clzll((long long)scan);
+            const int64_t e = ls + b;
+            if (t_tid > cd.tid[e] || t_start > a.work.end[e]) break;                         // update_gtf.c:148
+            if ((ev >> b) & 1ull) {
+                const int efs = a.work.fs[e], ele = a.work.le[e];
+                bool ok = iabs_dev(fs - efs) <= end_dis && iabs_dev(lend - ele) <= end_dis;  // merge_trans2 :124-125 / check_iden's end tests
+                if (nc == 1) ok = ok && ovlp_frac(fs, lend, efs, ele) >= a.up.single_exon_ovlp_frac;
+                if (ok) { hit = e; kind = (nc == 1 || rep[e] == rep[c]) ? 1 : 2; break; }
+            }
+            scan &= ~(1ull << b);
+        }
+        if (kind == 1) {
+            a.work.cov[hit] += 1;
+            if (fs < a.work.fs[hit]) { a.work.fs[hit] = fs; a.work.start[hit] = fs; }
+            if (lend > a.work.le[hit]) { a.work.le[hit] = lend; a.work.end[hit] = lend; }
+        } else if (kind == 0) {
+            alive |= 1ull << k;
+            a.work.cov[c] = 1; a.work.start[c] = t_start; a.work.end[c] = cd.end[c]; a.work.fs[c] = fs; a.work.le[c] = lend;
+        }
+        alive_out[c] = kind == 0 ? 1 : 0;
+    }
+}
+
 __global__ void merge_gather_kernel(DMerged work, CandSoA cd, const uint32_t *__restrict__ sel, const uint64_t *__restrict__ n_dev, DMerged out)
 {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -622,8 +768,24 @@ __global__ void merge_gather_kernel(DMerged work, CandSoA cd, const uint32_t *__
 void launch_merge_fold(const MergeArgs &a, cudaStream_t st)
 {
     if (a.n_cand <= 0) return;
-    // tlist reuses the (no longer needed) 64-bit key scratch; alive reuses the head mask's sibling buffer `dropped`.
-    // Grids are sized for the worst case (every candidate its own locus); the locus count is read on the device.
+    // tlist reuses the (no longer needed) 64-bit key scratch; alive reuses the head mask's sibling buffer `dropped`; the
+    // head mask itself becomes the per-locus "hard" flag.  Grids are sized for the worst case (every candidate its own
+    // locus); the locus count is read on the device.
+    static int v4 = -1;
+    if (v4 < 0) { const char *e = getenv("LRB_FOLD_V4"); v4 = e ? atoi(e) : 1; }
+    if (v4 && a.up.ss_dis == 0) {
+        cudaMemsetAsync(a.hard, 0, (size_t)a.n_cand, st);
+        const unsigned bl = (unsigned)((a.n_cand + 255) / 256);
+        fold_rep_kernel<<<bl, 256, 0, st>>>(a, a.rep, a.lstart, a.hard); LRB_COUNT_LAUNCH();
+        fold_rel_kernel<<<bl, 256, 0, st>>>(a, a.rep, a.lstart, a.evmask); LRB_COUNT_LAUNCH();
+        fold_seq_kernel<<<(unsigned)((a.n_cand + 127) / 128), 128, 0, st>>>(a, a.rep, a.evmask, a.hard, a.dropped); LRB_COUNT_LAUNCH();
+        {   // loci beyond the masks, and the (hash-collision) hard ones
+            int64_t bl2 = (a.n_cand / (FF_MAX + 1) + 1 + 3) / 4 + 8; if (bl2 > 148 * 8) bl2 = 148 * 8;
+            merge_fold_kernel<32><<<(unsigned)bl2, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, a.hard, FF_MAX + 1);
+            LRB_COUNT_LAUNCH();
+        }
+        return;
+    }
     {
         constexpr int GPB = MF_THREADS / 8;
         int64_t bl = (a.n_cand + GPB - 1) / GPB; if (bl > 148 * 12) bl = 148 * 12;
@@ -632,7 +794,7 @@ void launch_merge_fold(const MergeArgs &a, cudaStream_t st)
     }
     {
         int64_t bl = (a.n_cand / MF_SMALL + 1 + 3) / 4; if (bl > 148 * 8) bl = 148 * 8;     // a large locus has > MF_SMALL candidates
-        merge_fold_kernel<32, false><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped);
+        merge_fold_kernel<32><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, nullptr, MF_SMALL + 1);
         LRB_COUNT_LAUNCH();
     }
 }

@@ -68,7 +68,7 @@ struct lrb_ctx {
     int64_t n_pass = 0, n_keep = 0; bool have_filter = false;
     // rows + exons
     DRows rows, rows2; DRows *cur = nullptr; DExons ex;
-    Buf r_read, r_tid, r_rs, r_re, r_rev, r_beg, r_n;
+    Buf r_read, r_tid, r_rs, r_re, r_rev, r_beg, r_n, r_nonmono;
     Buf q_read, q_tid, q_rs, q_re, q_rev, q_beg, q_n;
     Buf e_s, e_e, e_f;
     bool have_exons = false, rows_compact = false;
@@ -330,7 +330,7 @@ void lrb_ctx_destroy(lrb_ctx *c)
     Buf *bufs[] = {&c->a_tid, &c->a_start, &c->a_end, &c->a_gene, &c->a_rev, &c->a_off, &c->a_es, &c->a_ee, &c->a_pmax, &c->a_mono, &c->s_tid, &c->s_don, &c->s_acc,
                    &c->s_u, &c->s_m, &c->s_pmax, &c->s_dkey, &c->r_gtid, &c->r_goff, &c->r_start, &c->r_pmax, &c->b_tid, &c->b_pos, &c->b_lq, &c->b_nm,
                    &c->b_flag, &c->b_xs, &c->b_qh, &c->b_coff, &c->b_cig, &c->f_pass, &c->f_score, &c->f_intron, &c->f_keep_row_mask, &c->f_keep_rec_mask,
-                   &c->f_keep_idx, &c->f_keep_rows, &c->r_read, &c->r_tid, &c->r_rs, &c->r_re, &c->r_rev, &c->r_beg, &c->r_n, &c->q_read, &c->q_tid,
+                   &c->f_keep_idx, &c->f_keep_rows, &c->r_read, &c->r_tid, &c->r_rs, &c->r_re, &c->r_rev, &c->r_beg, &c->r_n, &c->r_nonmono, &c->q_read, &c->q_tid,
                    &c->q_rs, &c->q_re, &c->q_rev, &c->q_beg, &c->q_n, &c->e_s, &c->e_e, &c->e_f, &c->u_cls, &c->u_ref, &c->u_nnovel, &c->u_noff, &c->u_mk,
                    &c->u_mu, &c->u_ck, &c->u_cr, &c->u_cu, &c->u_cn, &c->u_known, &c->u_unrecog, &c->u_sub, &c->n_row, &c->n_lo, &c->n_cnt, &c->n_piece,
                    &c->t_row, &c->t_lo, &c->t_cnt, &c->t_piece, &c->h_khi, &c->h_klo, &c->h_min, &c->h_score, &c->y_barcnt, &c->y_barseg, &c->y_genebar,
@@ -487,11 +487,15 @@ int lrb_batch_upload(lrb_ctx *c, const lrb_batch *b)
 }
 
 // rows straight from exon chains (-m g input): start/end/ex_beg/ex_n derived on device
-__global__ void chains_rows_kernel(DRows rows, const uint32_t *__restrict__ off, const int32_t *__restrict__ es, const int32_t *__restrict__ ee, int64_t n)
+__global__ void chains_rows_kernel(DRows rows, const uint32_t *__restrict__ off, const int32_t *__restrict__ es, const int32_t *__restrict__ ee, int64_t n,
+                                   uint8_t *nonmono)
 {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     uint32_t lo = off[r], hi = off[r + 1];
+    uint8_t nm = 0;                                  // GTF chains may be anything; CIGAR chains always ascend
+    for (uint32_t k = lo + 1; k < hi; ++k) if (es[k] < es[k - 1] || ee[k] < ee[k - 1]) nm = 1;
+    nonmono[r] = nm;
     rows.read_idx[r] = (uint32_t)r; rows.ex_beg[r] = lo; rows.ex_n[r] = hi - lo;
     rows.start[r] = hi > lo ? es[lo] : 0; rows.end[r] = hi > lo ? ee[hi - 1] : 0;
 }
@@ -509,7 +513,8 @@ int lrb_chains_upload(lrb_ctx *c, const lrb_chains *ch)
     if ((rc = h2d(c, c->e_s, ch->exon_start, (size_t)ne))) return rc;
     if ((rc = h2d(c, c->e_e, ch->exon_end, (size_t)ne))) return rc;
     if ((rc = h2d(c, c->u_noff, ch->exon_off, (size_t)n + 1))) return rc;          // scratch for the offsets
-    if (n) { chains_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->st>>>(c->rows, c->u_noff.as<uint32_t>(), c->ex.es, c->ex.ee, n); CK(cudaGetLastError()); }
+    NEED(c->r_nonmono, (size_t)std::max<int64_t>(n, 1));
+    if (n) { chains_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->st>>>(c->rows, c->u_noff.as<uint32_t>(), c->ex.es, c->ex.ee, n, c->r_nonmono.as<uint8_t>()); CK(cudaGetLastError()); }
     c->rows.n = n; c->ex.n = ne; c->cur = &c->rows; c->rows_compact = true;
     c->b.n = 0; c->have_batch = false; c->have_filter = false; c->have_exons = true; c->have_update = c->have_unique = false;
     return LRB_OK;
@@ -608,8 +613,9 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
     // ---- classification (+ SJ support)
     ClassArgs ca{};
     ca.rows = rows; ca.ex = c->ex; ca.anno = c->anno; ca.sj = c->sj; ca.up = *up;
+    ca.row_nonmono = c->have_batch ? nullptr : c->r_nonmono.as<uint8_t>();
     ca.cls = c->u_cls.as<uint32_t>(); ca.ref = c->u_ref.as<int32_t>(); ca.n_novel = c->u_nnovel.as<uint32_t>(); ca.err_flags = d_err(c);
-    launch_classify(ca, c->st);
+    launch_classify(ca, c->u_mk.as<uint8_t>(), c->st);     // u_mk doubles as the slow-row mask until the class masks are built
     CK(cudaGetLastError());
     tick(c, 1);
     // ---- class lists

@@ -89,7 +89,8 @@ LRB_DEVINL uint32_t block_excl_sum(uint32_t v, uint32_t *sm, uint32_t *total)
 }
 
 // ---------------------------------------------------------------------------------------------- lane groups
-template <int G> LRB_DEVINL unsigned group_mask() { return G == 32 ? FULL : (((1u << G) - 1u) << ((lane_id() / G) * G)); }
+template <int G> LRB_DEVINL constexpr unsigned lane_bits() { return G >= 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u); }
+template <int G> LRB_DEVINL unsigned group_mask() { return G == 32 ? FULL : (lane_bits<G>() << ((lane_id() / G) * G)); }
 // the shuffles name only the group's own lanes, so groups sharing a warp may diverge from each other
 template <int G> LRB_DEVINL int group_sum(unsigned m, int v)
 {
@@ -113,7 +114,7 @@ template <int G, class T> LRB_DEVINL int64_t group_upper_bound(unsigned m, int g
     while (hi - lo > G) {
         const int64_t span = hi - lo;
         const int64_t p = lo + (span * (gl + 1)) / (G + 1);            // lo <= p < hi, strictly increasing in gl
-        const unsigned b = (__ballot_sync(m, a[p] > key) >> sh) & ((1u << G) - 1u);
+        const unsigned b = (__ballot_sync(m, a[p] > key) >> sh) & lane_bits<G>();
         if (b) {
             const int f = __ffs(b) - 1;                                  // first pivot above the key
             const int64_t pf = lo + (span * (f + 1)) / (G + 1);
@@ -122,7 +123,7 @@ template <int G, class T> LRB_DEVINL int64_t group_upper_bound(unsigned m, int g
         } else lo = lo + (span * G) / (G + 1) + 1;
     }
     const int64_t q = lo + gl;
-    const unsigned b = (__ballot_sync(m, q < hi && a[q] > key) >> sh) & ((1u << G) - 1u);
+    const unsigned b = (__ballot_sync(m, q < hi && a[q] > key) >> sh) & lane_bits<G>();
     return b ? lo + (__ffs(b) - 1) : hi;
 }
 template <int G, class T> LRB_DEVINL int64_t group_lower_bound(unsigned m, int gl, const T *a, int64_t lo, int64_t hi, T key)
@@ -131,7 +132,7 @@ template <int G, class T> LRB_DEVINL int64_t group_lower_bound(unsigned m, int g
     while (hi - lo > G) {
         const int64_t span = hi - lo;
         const int64_t p = lo + (span * (gl + 1)) / (G + 1);
-        const unsigned b = (__ballot_sync(m, a[p] >= key) >> sh) & ((1u << G) - 1u);
+        const unsigned b = (__ballot_sync(m, a[p] >= key) >> sh) & lane_bits<G>();
         if (b) {
             const int f = __ffs(b) - 1;
             const int64_t pf = lo + (span * (f + 1)) / (G + 1);
@@ -140,7 +141,7 @@ template <int G, class T> LRB_DEVINL int64_t group_lower_bound(unsigned m, int g
         } else lo = lo + (span * G) / (G + 1) + 1;
     }
     const int64_t q = lo + gl;
-    const unsigned b = (__ballot_sync(m, q < hi && a[q] >= key) >> sh) & ((1u << G) - 1u);
+    const unsigned b = (__ballot_sync(m, q < hi && a[q] >= key) >> sh) & lane_bits<G>();
     return b ? lo + (__ffs(b) - 1) : hi;
 }
 

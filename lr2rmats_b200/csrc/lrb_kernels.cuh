@@ -83,8 +83,9 @@ struct ClassArgs {
     uint32_t *cls; int32_t *ref;
     uint32_t *n_novel;                              // per row: 0, 1 (whole read) or number of split pieces
     uint32_t *err_flags;                            // bit0 unsorted, bit1 unmapped/empty chain
+    const uint8_t *row_nonmono;                     // NULL: every row's exon starts/ends are non-decreasing (always true for CIGAR chains)
 };
-void launch_classify(const ClassArgs &a, cudaStream_t st);
+void launch_classify(const ClassArgs &a, uint8_t *slow_rows_scratch, cudaStream_t st);   // scratch: one byte per row
 
 // ---- novel_T / known / unrecog lists + merge fold
 struct DTransList {                                 // transcript rows of a list (whole reads or split pieces)

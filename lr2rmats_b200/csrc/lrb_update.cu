@@ -43,7 +43,7 @@ LRB_DEVINL int small_lower_bound(const int *a, int n, int key)
 
 // G lanes per read (power of two), CL_SLOTS exon slots per read staged in shared memory
 template <int G, int CL_SLOTS>
-__global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a)
+__global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a, const uint8_t *__restrict__ only)
 {
     constexpr int GPB = CL_THREADS / G;
     constexpr int STRIDE = CL_SLOTS + G;             // STRIDE = G * odd: the 32/G groups of a warp land on disjoint banks
@@ -59,6 +59,11 @@ __global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a)
     // the read start are monotone in the row index: six full binary searches per block bracket them for all its rows.
     const int64_t r0 = (int64_t)blockIdx.x * GPB * CL_ITERS;
     const int64_t r1 = min(a.rows.n, r0 + (int64_t)GPB * CL_ITERS);
+    if (only) {                                      // nothing left for this block after classify_row_kernel?
+        int any = 0;
+        for (int64_t r = r0 + threadIdx.x; r < r1; r += CL_THREADS) any |= only[r];
+        if (!__syncthreads_or(any)) return;
+    }
     if (threadIdx.x < 6) {
         const int64_t rr = (threadIdx.x & 1) ? r1 - 1 : r0;
         const int t = a.rows.tid[rr], st = a.rows.start[rr];
@@ -76,6 +81,7 @@ __global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a)
     const int Flo = s_win[0], Fhi = max(s_win[0], s_win[1]), Slo = s_win[2], Shi = max(s_win[2], s_win[3]), Dlo = s_win[4], Dhi = max(s_win[4], s_win[5]);
 
     for (int64_t row = r0 + g; row < r1; row += GPB) {
+        if (only && !only[row]) continue;               // classified by classify_fast_kernel
         const int n = (int)a.rows.ex_n[row];
         const uint32_t beg = a.rows.ex_beg[row];
         const int tid_b = a.rows.tid[row], start_b = a.rows.start[row], end_b = a.rows.end[row];
@@ -273,22 +279,218 @@ __global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a)
     }
 }
 
-template <int G, int SLOTS> static void launch_classify_t(const ClassArgs &a, cudaStream_t st)
+// ---------------------------------------------------------------------------------- classification, thread per read
+// The common case (exact splice-site matching, reads and window transcripts with increasing exon coordinates, at most
+// 32 exons per read) runs here; every other read is flagged in `slow` and goes through classify_kernel above, which
+// implements the same rules without those restrictions.  One thread replays the reference's sweep for one read: the 32
+// reads of a warp are neighbours in (tid,start) order, so they sweep the same transcripts -- annotation loads are warp
+// broadcasts and the lanes stay converged.  Per (read, transcript) pair one merge walk over the two sorted exon lists
+// replaces the reference's three nested loops; the four per-exon flag arrays live in four 32-bit registers.
+static constexpr int CR_THREADS = 128;
+
+__global__ void __launch_bounds__(CR_THREADS) classify_row_kernel(ClassArgs a, uint8_t *__restrict__ slow, const uint8_t *__restrict__ row_nonmono)
+{
+    __shared__ int s_win[6];
+    const int t = threadIdx.x;
+    const int dis = a.up.ss_dis, level = a.up.full_level;
+    const int64_t r0 = (int64_t)blockIdx.x * CR_THREADS, r1 = min(a.rows.n, r0 + (int64_t)CR_THREADS);
+    {   // bracket the three cursors for the rows of this tile (rows are sorted): six cooperative 33-ary searches, warps 0..3
+        const int w = warp_id(), lane = lane_id();
+        for (int q = w; q < 6; q += CR_THREADS / 32) {
+            const int64_t rr = (q & 1) ? r1 - 1 : r0;
+            const int tt = a.rows.tid[rr], st = a.rows.start[rr];
+            const uint64_t key = ((uint64_t)(uint32_t)(tt + 1) << 32) | (uint32_t)st;
+            int v;
+            if (q < 2) v = (int)group_upper_bound<32, uint64_t>(FULL, lane, a.anno.pmax_key, 0, a.anno.n, key);
+            else if (q < 4) v = a.sj.n ? (int)group_upper_bound<32, uint64_t>(FULL, lane, a.sj.pmax_key, 0, a.sj.n, key) : 0;
+            else {
+                int wlo = st - dis; if (wlo < 0) wlo = 0;
+                v = a.sj.n ? (int)group_lower_bound<32, uint64_t>(FULL, lane, a.sj.don_key, 0, a.sj.n, (((uint64_t)(uint32_t)(tt + 1)) << 32) | (uint32_t)wlo) : 0;
+            }
+            if (lane == 0) s_win[q] = v;
+        }
+    }
+    __syncthreads();
+    const int64_t row = r0 + t;
+    if (row >= r1) return;
+    const int Flo = s_win[0], Fhi = max(s_win[0], s_win[1]), Slo = s_win[2], Shi = max(s_win[2], s_win[3]), Dlo = s_win[4], Dhi = max(s_win[4], s_win[5]);
+    const int n = (int)a.rows.ex_n[row];
+    const uint32_t beg = a.rows.ex_beg[row];
+    const int tid_b = a.rows.tid[row], start_b = a.rows.start[row], end_b = a.rows.end[row];
+    if (row > 0) {
+        const int pt = a.rows.tid[row - 1], ps = a.rows.start[row - 1];
+        if (pt > tid_b || (pt == tid_b && ps > start_b)) atomicOr(a.err_flags, 1u);             // the closed forms need (tid,start) order
+    }
+    if (dis != 0 || n < 1 || n > 32 || (row_nonmono && row_nonmono[row])) { slow[row] = 1; return; }
+    const int *__restrict__ es = a.ex.es + beg, *__restrict__ ee = a.ex.ee + beg;
+    const int b0s = es[0], b0e = ee[0], bls = es[n - 1], ble = ee[n - 1];
+    const uint64_t key_b = ((uint64_t)(uint32_t)(tid_b + 1) << 32) | (uint32_t)start_b;
+
+    // ---- annotation window: F(b) on the prefix-max keys, sweep to the first "after" (update_gtf.c:792-835)
+    int lfull = 0, rfull = 0, lnoth = 1, rnoth = 1, known = 0, known_site = 0, ref = -1;
+    uint32_t c_don = 0, c_acc = 0, c_junc = 0, c_exon = 0;                                     // cleared novel_* flags, bit j
+    for (int i = (int)upper_bound_dev<uint64_t>(a.anno.pmax_key, Flo, Fhi, key_b); i < a.anno.n; ++i) {
+        const int at = a.anno.tid[i], as_ = a.anno.start[i];
+        if (tid_b < at || (tid_b == at && end_b <= as_)) break;                                 // comp_trans < 0
+        const int ae_ = a.anno.end[i];
+        if (at < tid_b || (at == tid_b && ae_ <= start_b)) continue;                            // comp_trans > 0
+        if (!a.anno.mono[i]) { slow[row] = 1; return; }                                         // nothing was written yet
+        const uint32_t ao = a.anno.exon_off[i]; const int na = (int)(a.anno.exon_off[i + 1] - ao);
+        const int *__restrict__ xs = a.anno.es + ao, *__restrict__ xe = a.anno.ee + ao;
+        if (!(lfull && rfull) && level <= 4) {                                                  // check_full, update_gtf.c:629-681
+            const int a0s = xs[0], a0e = xe[0], als = xs[na - 1], ale = xe[na - 1];
+            if (level == 1) {
+                if (!lfull && b0e == a0e) lfull = 1;
+                if (!rfull && bls == als) rfull = 1;
+            } else if (level == 2) {
+                if (!lfull && ex_ovlp(b0s, b0e, a0s, a0e)) lfull = 1;
+                if (!rfull && ex_ovlp(bls, ble, als, ale)) rfull = 1;
+            } else if (level == 3 || level == 4) {
+                bool need_l = false, need_r = false;
+                if (!lfull) { if (ex_ovlp(b0s, b0e, a0s, a0e)) lfull = 1; else need_l = lnoth; }
+                if (level == 3 && !rfull) { if (ex_ovlp(bls, ble, als, ale)) rfull = 1; else need_r = rnoth; }
+                if (need_l | need_r) {
+                    bool lany = false, rany = false;
+                    for (int k = 0; k < na; ++k) { const int s2 = xs[k], e2 = xe[k]; lany |= ex_ovlp(b0s, b0e, s2, e2); rany |= ex_ovlp(bls, ble, s2, e2); }
+                    if (need_l && lany) lnoth = 0;
+                    if (need_r && rany) rnoth = 0;
+                }
+            }
+        }
+        if (n == 1 && na == 1) {                                                                // update_gtf.c:806-811
+            if (ovlp_frac(b0s, b0e, xs[0], xe[0]) >= a.up.single_exon_ovlp_frac) { ref = i; known = 1; break; }
+        } else if (n > 1 && na > 1) {                                                           // check_splice_site :717-779, exact matching
+            const int os = max(start_b, as_), oe = min(end_b, ae_);
+            int ovl = 0, iden = 0, ps = 0, pe = 0, bs = b0s, be = b0e;
+            for (int j = 0; j < n; ++j) {
+                while (ps < na && xs[ps] < bs) ++ps;
+                while (pe < na && xe[pe] < be) ++pe;
+                const bool hit_s = ps < na && xs[ps] == bs, hit_e = pe < na && xe[pe] == be;
+                const uint32_t bit = 1u << j;
+                if (hit_s && hit_e && ps == pe) c_exon |= bit;
+                if (j < n - 1) {
+                    const int sn = es[j + 1];
+                    ovl += (be >= os && be <= oe) + (sn >= os && sn <= oe);
+                    if (hit_e && pe < na - 1) {
+                        if (be >= os && be <= oe) { ++iden; c_don |= bit; }
+                        if (xs[pe + 1] == sn) c_junc |= bit;
+                    }
+                    if (hit_s && ps >= 1 && bs >= os && bs <= oe) { ++iden; c_acc |= bit; }
+                    bs = sn; be = ee[j + 1];
+                }
+            }
+            if (2 * (n - 1) == ovl && ovl == iden) { known = 1; ref = i; break; }
+            else if (iden > 0) { known_site = 1; ref = i; }
+        }
+    }
+    int full;                                                                                    // set_full :683-696
+    if (level == 5) full = 1;
+    else if (level == 4) full = (lfull || lnoth);
+    else if (level == 3) full = ((lfull || lnoth) && (rfull || rnoth));
+    else full = (lfull && rfull);
+
+    // ---- short-read SJ support, update_gtf.c:589-627,698-709 (cursor closed form, App. B.2)
+    int sj_checked = 0, unreliable = 0;
+    uint32_t unrel = 0;
+    if (full && !known && known_site && a.sj.n > 0) {
+        sj_checked = 1;
+        const int64_t S = upper_bound_dev<uint64_t>(a.sj.pmax_key, Slo, Shi, key_b);
+        int ok = 1;
+        if (S >= a.sj.n) ok = 0;
+        else {
+            const int st = a.sj.tid[S];
+            if (st > tid_b || (st == tid_b && a.sj.don[S] >= end_b)) ok = 0;
+            else {
+                const uint64_t tk = (uint64_t)(uint32_t)(tid_b + 1) << 32;
+                int wlo = start_b - dis; if (wlo < 0) wlo = 0;
+                int64_t R0 = lower_bound_dev<uint64_t>(a.sj.don_key, Dlo, Dhi, tk | (uint32_t)wlo);
+                if (R0 < S) R0 = S;
+                uint32_t nj = ~c_junc & (n >= 2 ? (0xffffffffu >> (33 - n)) : 0u);              // novel junctions j < n-1, ascending
+                while (nj) {
+                    const int j = __ffs(nj) - 1; nj &= nj - 1;
+                    const int is = ee[j] + 1, ie = es[j + 1] - 1;                               // intron [is, ie]
+                    int dlo = is - dis; if (dlo < 0) dlo = 0;
+                    int64_t dhi = (int64_t)is + dis + 1; if (dhi > ie) dhi = ie; if (dhi < 0) dhi = 0;
+                    const uint64_t klo = tk | (uint32_t)dlo, khi = tk | (uint64_t)dhi;
+                    int64_t l2 = R0, step = 1, h2 = R0;
+                    while (h2 < a.sj.n && a.sj.don_key[h2] < klo) { l2 = h2 + 1; h2 += step; step <<= 1; }
+                    if (h2 > a.sj.n) h2 = a.sj.n;
+                    l2 = lower_bound_dev<uint64_t>(a.sj.don_key, l2, h2, klo);
+                    R0 = l2;                                                                    // junctions ascend: the next search starts here
+                    int found = 0;
+                    for (int64_t q = l2; q < a.sj.n && !found; ++q) {
+                        if (a.sj.don_key[q] >= khi) break;
+                        if (iabs_dev(a.sj.acc[q] - ie) <= dis) {
+                            const int c = a.up.use_multi ? a.sj.cnt_u[q] + a.sj.cnt_m[q] : a.sj.cnt_u[q];
+                            if (c >= a.up.min_sj_cnt) found = 1;
+                        }
+                    }
+                    if (!found) unrel |= 1u << j;
+                }
+                if (unrel) ok = 0;
+            }
+        }
+        unreliable = !ok;
+    }
+
+    // ---- novel_T contribution: the read itself, or its split pieces (split_trans :837-913)
+    uint32_t nn = 0;
+    if (full && !known && known_site) {
+        if (!sj_checked || !unreliable) nn = 1;
+        else if (a.up.split_trans) {
+            int last = 0, has_novel = 0, has_known = 0;
+            for (int k = 0; k <= n - 1; ++k) {
+                const bool at_end = k == n - 1;
+                if (!at_end) { if (!((c_junc >> k) & 1u)) has_novel = 1; else has_known = 1; }
+                if (at_end || ((unrel >> k) & 1u)) {
+                    if (has_novel && has_known && k - last >= 1) ++nn;
+                    last = k + 1; has_novel = 0; has_known = 0;
+                }
+            }
+        }
+    }
+    uint8_t *fl = a.ex.flag + beg;
+    for (int j = 0; j < n; ++j) {
+        uint32_t f = ((c_exon >> j) & 1u) ? 0u : LRB_F_NOVEL_EXON;
+        if (j < n - 1) {
+            if (!((c_don >> j) & 1u)) f |= LRB_F_NOVEL_DON;
+            if (!((c_acc >> j) & 1u)) f |= LRB_F_NOVEL_ACC;
+            if (!((c_junc >> j) & 1u)) f |= LRB_F_NOVEL_JUNC;
+            if ((unrel >> j) & 1u) f |= LRB_F_UNRELIABLE;
+        }
+        fl[j] = (uint8_t)f;
+    }
+    slow[row] = 0;
+    a.cls[row] = (known ? LRB_C_KNOWN : 0) | (known_site ? LRB_C_KNOWN_SITE : 0) | (unreliable ? LRB_C_UNRELIABLE : 0) |
+                 (full ? LRB_C_FULL : 0) | (lfull ? LRB_C_LFULL : 0) | (rfull ? LRB_C_RFULL : 0) | (lnoth ? LRB_C_LNOTH : 0) |
+                 (rnoth ? LRB_C_RNOTH : 0) | (sj_checked ? LRB_C_SJ_CHECKED : 0);
+    a.ref[row] = ref;
+    if (ref != -1) a.rows.is_rev[row] = a.anno.is_rev[ref];                                     // update_gtf.c:823-833
+    a.n_novel[row] = nn;
+}
+
+template <int G, int SLOTS> static void launch_classify_t(const ClassArgs &a, const uint8_t *only, cudaStream_t st)
 {
     constexpr int per_block = (CL_THREADS / G) * CL_ITERS;
     int64_t bl = (a.rows.n + per_block - 1) / per_block;
-    classify_kernel<G, SLOTS><<<(unsigned)bl, CL_THREADS, 0, st>>>(a);
+    classify_kernel<G, SLOTS><<<(unsigned)bl, CL_THREADS, 0, st>>>(a, only);
 }
-void launch_classify(const ClassArgs &a, cudaStream_t st)
+void launch_classify(const ClassArgs &a, uint8_t *slow, cudaStream_t st)
 {
     if (a.rows.n <= 0) return;
-    static int g = -1;
-    if (g < 0) { const char *e = getenv("LRB_CLASSIFY_G"); g = e ? atoi(e) : 4; }
+    static int g = -1, fast = -1;
+    if (g < 0) { const char *e = getenv("LRB_CLASSIFY_G"); g = e ? atoi(e) : 4; e = getenv("LRB_CLASSIFY_FAST"); fast = e ? atoi(e) : 1; }
+    const uint8_t *only = nullptr;
+    if (fast && a.up.ss_dis == 0 && slow) {
+        classify_row_kernel<<<(unsigned)((a.rows.n + CR_THREADS - 1) / CR_THREADS), CR_THREADS, 0, st>>>(a, slow, a.row_nonmono);
+        LRB_COUNT_LAUNCH();
+        only = slow;
+    }
     switch (g) {
-    case 1: launch_classify_t<1, 16>(a, st); break;
-    case 2: launch_classify_t<2, 16>(a, st); break;
-    case 4: launch_classify_t<4, 16>(a, st); break;
-    default: launch_classify_t<8, 64>(a, st); break;
+    case 1: launch_classify_t<1, 16>(a, only, st); break;
+    case 2: launch_classify_t<2, 16>(a, only, st); break;
+    case 4: launch_classify_t<4, 16>(a, only, st); break;
+    default: launch_classify_t<8, 64>(a, only, st); break;
     }
     LRB_COUNT_LAUNCH();
 }

@@ -202,6 +202,25 @@ typedef struct {               /* check_trans + print_trans_summary, update_gtf.
     lrb_bed_list     bed;
 } lrb_update_result;
 
+/* Self-contained rows of a transcript list as print_read_trans() needs them
+ * (gtf.c:607-632): everything the default outputs of update-gtf (-o updated GTF,
+ * -y summary, -E BED) require, without the per-read tables.  Names stay on the
+ * host: name_idx is the record index of the batch (or the chain index for -m g
+ * input); pieces print "<name>.split.<piece>". */
+typedef struct {
+    int64_t         n;
+    const uint32_t *name_idx;
+    const int32_t  *piece;     /* -1 whole read */
+    const int32_t  *t_tid, *t_start, *t_end;  /* transcript line: trans_t.tid/start/end (0/0/0 for pieces) */
+    const uint8_t  *t_rev;     /* transcript line strand (0 for pieces) */
+    const int32_t  *e_tid;     /* exon lines: the read's chromosome */
+    const uint8_t  *e_rev;     /* exon lines strand; also selects descending exon order */
+    const int32_t  *cov;
+    const int32_t  *ref_anno;  /* gene_id / gene_name source (-1: "NA") */
+    const uint32_t *exon_off;  /* n+1 */
+    const int32_t  *exon_start, *exon_end;    /* first start / last end already extended by the fold */
+} lrb_trans_table;
+
 typedef struct {               /* uniq_trans, unique_gtf.c:73-84 */
     lrb_exon_result  ex;
     lrb_merged_list  uniq;     /* unique_T (cand = read row) */
@@ -237,9 +256,13 @@ int lrb_sync(lrb_ctx *ctx);
 
 /* Results -> pinned host buffers owned by the ctx. */
 int lrb_filter_fetch(lrb_ctx *ctx, lrb_filter_result *out);
+int lrb_filter_fetch_keep(lrb_ctx *ctx, int64_t *n_keep, const uint32_t **keep_idx); /* only the records sam_write1 would emit */
 int lrb_exon_fetch(lrb_ctx *ctx, lrb_exon_result *out);
 int lrb_update_fetch(lrb_ctx *ctx, lrb_update_result *out);
 int lrb_unique_fetch(lrb_ctx *ctx, lrb_unique_result *out);
+/* updated_T as a self-contained table + BED rows + summary counters: the part of lrb_update_fetch that
+ * `update-gtf -o/-y/-E` prints (print_read_trans gtf.c:607-632, update_gtf.c:535-576); any argument may be NULL. */
+int lrb_update_fetch_table(lrb_ctx *ctx, lrb_trans_table *updated, lrb_bed_list *bed, int32_t summary[LRB_S_COUNT]);
 
 /* One-call forms with HOST buffers (upload + run + fetch), the calls the
  * reference's subcommands would make where they call gtf_filter /

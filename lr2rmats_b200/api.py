@@ -21,7 +21,7 @@ ENTRY_POINTS = [
     "lrb_batch_upload", "lrb_chains_upload", "lrb_filter_run", "lrb_exon_run", "lrb_pipeline_run", "lrb_update_run", "lrb_unique_run",
     "lrb_sync", "lrb_filter_fetch", "lrb_exon_fetch", "lrb_update_fetch", "lrb_unique_fetch", "lrb_filter", "lrb_bam2gtf",
     "lrb_update_gtf", "lrb_unique_gtf", "lrb_timing_enable", "lrb_timing_get", "lrb_launch_count", "lrb_shard_cuts",
-    "lrb_mark", "lrb_elapsed_ms", "lrb_host_alloc", "lrb_host_free",
+    "lrb_mark", "lrb_elapsed_ms", "lrb_host_alloc", "lrb_host_free", "lrb_update_fetch_table", "lrb_filter_fetch_keep",
 ]
 
 T_NAMES = ["filter", "exon", "classify", "merge", "summary", "k_scan", "k_fold"]
@@ -63,8 +63,10 @@ def load_library():
     L.lrb_sync.argtypes = [vp]
     L.lrb_filter_fetch.argtypes = [vp, P(cabi.FilterResult)]
     L.lrb_exon_fetch.argtypes = [vp, P(cabi.ExonResult)]
+    L.lrb_filter_fetch_keep.argtypes = [vp, P(C.c_int64), P(cabi.u32p)]
     L.lrb_update_fetch.argtypes = [vp, P(cabi.UpdateResult)]
     L.lrb_unique_fetch.argtypes = [vp, P(cabi.UniqueResult)]
+    L.lrb_update_fetch_table.argtypes = [vp, P(cabi.TransTable), P(cabi.BedList), P(C.c_int32 * cabi.S_COUNT)]
     L.lrb_filter.argtypes = [vp, P(cabi.Batch), P(cabi.FilterParams), P(cabi.FilterResult)]
     L.lrb_bam2gtf.argtypes = [vp, P(cabi.Batch), P(cabi.ExonParams), P(cabi.ExonResult)]
     L.lrb_update_gtf.argtypes = [vp, P(cabi.Batch), P(cabi.ExonParams), P(cabi.UpdateParams), P(cabi.UpdateResult)]
@@ -148,12 +150,25 @@ class Context:
     def filter_fetch(self) -> dict:
         r = cabi.FilterResult(); self._ck(self.L.lrb_filter_fetch(self.h, C.byref(r))); return cabi.filter_to_np(r)
 
+    def filter_fetch_keep(self, raw=False):
+        n = C.c_int64(); p = cabi.u32p()
+        self._ck(self.L.lrb_filter_fetch_keep(self.h, C.byref(n), C.byref(p)))
+        return (int(n.value), p) if raw else cabi._arr(p, n.value, np.uint32)
+
     def exon_fetch(self) -> dict:
         r = cabi.ExonResult(); self._ck(self.L.lrb_exon_fetch(self.h, C.byref(r))); return cabi.exon_to_np(r)
 
     def update_fetch(self, raw=False):
         r = cabi.UpdateResult(); self._ck(self.L.lrb_update_fetch(self.h, C.byref(r)))
         return r if raw else cabi.update_to_np(r)
+
+    def update_fetch_table(self, raw=False, want_bed=True):
+        """updated_T as a self-contained table + BED rows + summary counters (what update-gtf -o/-y/-E print)."""
+        t = cabi.TransTable(); b = cabi.BedList(); s = (C.c_int32 * cabi.S_COUNT)()
+        self._ck(self.L.lrb_update_fetch_table(self.h, C.byref(t), C.byref(b) if want_bed else None, C.byref(s)))
+        if raw:
+            return t, b, s
+        return dict(table=cabi.table_to_np(t), bed=cabi.bed_to_np(b) if want_bed else None, summary=np.array(list(s), np.int32))
 
     def unique_fetch(self) -> dict:
         r = cabi.UniqueResult(); self._ck(self.L.lrb_unique_fetch(self.h, C.byref(r))); return cabi.unique_to_np(r)

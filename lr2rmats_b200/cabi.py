@@ -99,6 +99,11 @@ class UpdateResult(C.Structure):
                 ("novel", TransList), ("updated", MergedList), ("summary", C.c_int32 * S_COUNT), ("bed", BedList)]
 
 
+class TransTable(C.Structure):
+    _fields_ = [("n", C.c_int64), ("name_idx", u32p), ("piece", i32p), ("t_tid", i32p), ("t_start", i32p), ("t_end", i32p), ("t_rev", u8p),
+                ("e_tid", i32p), ("e_rev", u8p), ("cov", i32p), ("ref_anno", i32p), ("exon_off", u32p), ("exon_start", i32p), ("exon_end", i32p)]
+
+
 class UniqueResult(C.Structure):
     _fields_ = [("ex", ExonResult), ("uniq", MergedList), ("n_shared", C.c_int64), ("shared_idx", u32p)]
 
@@ -204,6 +209,20 @@ def update_to_np(r: UpdateResult) -> dict:
                 updated=merged_to_np(r.updated), summary=np.array(list(r.summary), np.int32),
                 bed={k: _arr(getattr(r.bed, k), r.bed.n, np.uint8 if k in ("type", "is_rev") else np.int32)
                      for k in ("tid", "start", "end", "score", "type", "is_rev")})
+
+
+def table_to_np(t: TransTable) -> dict:
+    n = int(t.n)
+    off = _arr(t.exon_off, n + 1, np.uint32)
+    ne = int(off[-1]) if n else 0
+    d = {k: _arr(getattr(t, k), n, np.uint8 if k in ("t_rev", "e_rev") else (np.uint32 if k == "name_idx" else np.int32))
+         for k in ("name_idx", "piece", "t_tid", "t_start", "t_end", "t_rev", "e_tid", "e_rev", "cov", "ref_anno")}
+    d.update(exon_off=off, exon_start=_arr(t.exon_start, ne, np.int32), exon_end=_arr(t.exon_end, ne, np.int32))
+    return d
+
+
+def bed_to_np(b: BedList) -> dict:
+    return {k: _arr(getattr(b, k), b.n, np.uint8 if k in ("type", "is_rev") else np.int32) for k in ("tid", "start", "end", "score", "type", "is_rev")}
 
 
 def unique_to_np(r: UniqueResult) -> dict:

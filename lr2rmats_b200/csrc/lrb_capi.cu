@@ -87,7 +87,8 @@ struct lrb_ctx {
     // look-back state, small device scalars and their pinned mirror
     Buf tile_state, scalars; PBuf h_scalars;
     // pinned result buffers
-    PBuf p[40];
+    PBuf p[48];
+    Buf tb_name, tb_piece, tb_ttid, tb_tstart, tb_tend, tb_trev, tb_etid, tb_erev, tb_cov, tb_ref, tb_cnt, tb_off, tb_es, tb_ee;
     // timing
     bool timing = false; cudaEvent_t ev[12]; cudaEvent_t marks[8]; float ms[LRB_T_COUNT]; int64_t launches0 = 0, launches_last = 0;
     lrb_update_params last_up;
@@ -334,7 +335,7 @@ void lrb_ctx_destroy(lrb_ctx *c)
                    &c->q_rs, &c->q_re, &c->q_rev, &c->q_beg, &c->q_n, &c->e_s, &c->e_e, &c->e_f, &c->u_cls, &c->u_ref, &c->u_nnovel, &c->u_noff, &c->u_mk,
                    &c->u_mu, &c->u_ck, &c->u_cr, &c->u_cu, &c->u_cn, &c->u_known, &c->u_unrecog, &c->u_sub, &c->n_row, &c->n_lo, &c->n_cnt, &c->n_piece,
                    &c->t_row, &c->t_lo, &c->t_cnt, &c->t_piece, &c->h_khi, &c->h_klo, &c->h_min, &c->h_score, &c->y_barcnt, &c->y_barseg, &c->y_genebar,
-                   &c->y_bedcnt, &c->y_bedoff, &c->y_counts, &c->y_nelem, &c->bd_tid, &c->bd_s, &c->bd_e, &c->bd_sc, &c->bd_ty, &c->bd_rv, &c->q_shared,
+                   &c->y_bedcnt, &c->y_bedoff, &c->y_counts, &c->y_nelem, &c->bd_tid, &c->bd_s, &c->bd_e, &c->bd_sc, &c->bd_ty, &c->bd_rv, &c->q_shared, &c->tb_name, &c->tb_piece, &c->tb_ttid, &c->tb_tstart, &c->tb_tend, &c->tb_trev, &c->tb_etid, &c->tb_erev, &c->tb_cov, &c->tb_ref, &c->tb_cnt, &c->tb_off, &c->tb_es, &c->tb_ee,
                    &c->tile_state, &c->scalars};
     for (Buf *b : bufs) b->release();
     for (MergeBufs *m : {&c->mg, &c->mg2}) {
@@ -771,6 +772,18 @@ int lrb_filter_fetch(lrb_ctx *c, lrb_filter_result *out)
     return LRB_OK;
 }
 
+int lrb_filter_fetch_keep(lrb_ctx *c, int64_t *n_keep, const uint32_t **keep_idx)
+{
+    if (!c || !n_keep || !keep_idx) return LRB_E_ARG;
+    if (!c->have_filter) return fail(c, LRB_E_ARG, "lrb_filter_fetch_keep: filter stage has not run");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = d2h(c, c->p[3], c->f_keep_idx.as<uint32_t>(), (size_t)c->n_keep))) return rc;
+    CK(cudaStreamSynchronize(c->st));
+    *n_keep = c->n_keep; *keep_idx = c->p[3].as<uint32_t>();
+    return LRB_OK;
+}
+
 // compact copy of the exon data of the current rows (rows may reference a sparse subset of the pool after the fused pass)
 __global__ void exon_gather_kernel(DRows rows, DExons ex, const uint32_t *__restrict__ off, int32_t *es, int32_t *ee, uint8_t *fl, int with_flags)
 {
@@ -874,6 +887,104 @@ int lrb_update_fetch(lrb_ctx *c, lrb_update_result *out)
     memcpy(out->summary, c->summary, sizeof c->summary);
     out->bed.n = c->n_bed; out->bed.tid = c->p[26].as<int32_t>(); out->bed.start = c->p[27].as<int32_t>(); out->bed.end = c->p[28].as<int32_t>();
     out->bed.score = c->p[29].as<int32_t>(); out->bed.type = c->p[30].as<uint8_t>(); out->bed.is_rev = c->p[31].as<uint8_t>();
+    return LRB_OK;
+}
+
+// ---- updated_T as a self-contained table (what print_read_trans needs), gathered on the device
+struct TabArgs {
+    DRows rows; DExons ex; DTransList list; DMerged upd; const int32_t *ref; int rows_have_read_idx;
+    uint32_t *name_idx; int32_t *piece, *t_tid, *t_start, *t_end, *e_tid, *cov, *ref_out; uint8_t *t_rev, *e_rev; uint32_t *cnt;
+    const uint32_t *off; int32_t *es, *ee;
+};
+__global__ void tab_rows_kernel(TabArgs a)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.upd.n) return;
+    const uint32_t cd = a.upd.cand[i], row = a.list.row[cd];
+    const int piece = a.list.piece[cd];
+    const uint8_t rev = a.rows.is_rev[row];
+    a.name_idx[i] = a.rows_have_read_idx ? a.rows.read_idx[row] : row;
+    a.piece[i] = piece; a.t_tid[i] = a.upd.tid[i]; a.t_start[i] = a.upd.start[i]; a.t_end[i] = a.upd.end[i];
+    a.t_rev[i] = piece >= 0 ? 0 : rev; a.e_tid[i] = a.rows.tid[row]; a.e_rev[i] = rev; a.cov[i] = a.upd.cov[i]; a.ref_out[i] = a.ref[row];
+    a.cnt[i] = a.list.cnt[cd];
+}
+__global__ void tab_exons_kernel(TabArgs a)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.upd.n) return;
+    const uint32_t cd = a.upd.cand[i], row = a.list.row[cd];
+    const uint32_t gb = a.rows.ex_beg[row] + a.list.lo[cd], o = a.off[i];
+    const int n = (int)a.list.cnt[cd];
+    for (int j = 0; j < n; ++j) {
+        a.es[o + j] = j == 0 ? a.upd.fs[i] : a.ex.es[gb + j];
+        a.ee[o + j] = j == n - 1 ? a.upd.le[i] : a.ex.ee[gb + j];
+    }
+}
+
+int lrb_update_fetch_table(lrb_ctx *c, lrb_trans_table *tab, lrb_bed_list *bed, int32_t *summary)
+{
+    if (!c) return LRB_E_ARG;
+    if (!c->have_update) return fail(c, LRB_E_ARG, "lrb_update_fetch_table: update stage has not run");
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if (summary) memcpy(summary, c->summary, sizeof c->summary);
+    if (bed) {
+        if (!c->last_up.want_summary) return fail(c, LRB_E_ARG, "lrb_update_fetch_table: BED rows need want_summary");
+        if ((rc = d2h(c, c->p[26], c->bd_tid.as<int32_t>(), (size_t)c->n_bed))) return rc;
+        if ((rc = d2h(c, c->p[27], c->bd_s.as<int32_t>(), (size_t)c->n_bed))) return rc;
+        if ((rc = d2h(c, c->p[28], c->bd_e.as<int32_t>(), (size_t)c->n_bed))) return rc;
+        if ((rc = d2h(c, c->p[29], c->bd_sc.as<int32_t>(), (size_t)c->n_bed))) return rc;
+        if ((rc = d2h(c, c->p[30], c->bd_ty.as<uint8_t>(), (size_t)c->n_bed))) return rc;
+        if ((rc = d2h(c, c->p[31], c->bd_rv.as<uint8_t>(), (size_t)c->n_bed))) return rc;
+        bed->n = c->n_bed; bed->tid = c->p[26].as<int32_t>(); bed->start = c->p[27].as<int32_t>(); bed->end = c->p[28].as<int32_t>();
+        bed->score = c->p[29].as<int32_t>(); bed->type = c->p[30].as<uint8_t>(); bed->is_rev = c->p[31].as<uint8_t>();
+    }
+    if (tab) {
+        const int64_t nu = c->mg.n_out; const size_t k = (size_t)std::max<int64_t>(nu, 1);
+        Buf *b4[] = {&c->tb_name, &c->tb_piece, &c->tb_ttid, &c->tb_tstart, &c->tb_tend, &c->tb_etid, &c->tb_cov, &c->tb_ref, &c->tb_cnt};
+        for (Buf *b : b4) NEED(*b, k * 4);
+        NEED(c->tb_trev, k); NEED(c->tb_erev, k); NEED(c->tb_off, (k + 1) * 4);
+        TabArgs a{};
+        a.rows = *c->cur; a.ex = c->ex; a.list = c->novel; a.ref = c->u_ref.as<int32_t>(); a.rows_have_read_idx = c->have_batch ? 1 : 0;
+        a.upd = merged_view(c->mg.o_cand, c->mg.o_cov, c->mg.o_tid, c->mg.o_start, c->mg.o_end, c->mg.o_fs, c->mg.o_le, nu);
+        a.name_idx = c->tb_name.as<uint32_t>(); a.piece = c->tb_piece.as<int32_t>(); a.t_tid = c->tb_ttid.as<int32_t>(); a.t_start = c->tb_tstart.as<int32_t>();
+        a.t_end = c->tb_tend.as<int32_t>(); a.e_tid = c->tb_etid.as<int32_t>(); a.cov = c->tb_cov.as<int32_t>(); a.ref_out = c->tb_ref.as<int32_t>();
+        a.t_rev = c->tb_trev.as<uint8_t>(); a.e_rev = c->tb_erev.as<uint8_t>(); a.cnt = c->tb_cnt.as<uint32_t>(); a.off = c->tb_off.as<uint32_t>();
+        int64_t ne = 0;
+        if (nu) {
+            if ((rc = ensure_tiles(c, nu))) return rc;
+            tab_rows_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, c->st>>>(a);
+            launch_scan_sum_u32(a.cnt, c->tb_off.as<uint32_t>(), nu, c->tile_state.as<uint64_t>(), d_ticket(c), d_totals(c), c->st);
+            CK(cudaGetLastError());
+            uint64_t t; if ((rc = read_totals(c, &t, 1))) return rc;
+            ne = (int64_t)t;
+            NEED(c->tb_es, (size_t)std::max<int64_t>(ne, 1) * 4); NEED(c->tb_ee, (size_t)std::max<int64_t>(ne, 1) * 4);
+            a.es = c->tb_es.as<int32_t>(); a.ee = c->tb_ee.as<int32_t>();
+            tab_exons_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, c->st>>>(a);
+            CK(cudaGetLastError());
+        }
+        const size_t n = (size_t)nu;
+        if ((rc = d2h(c, c->p[32], a.name_idx, n))) return rc;
+        if ((rc = d2h(c, c->p[33], a.piece, n))) return rc;
+        if ((rc = d2h(c, c->p[34], a.t_tid, n))) return rc;
+        if ((rc = d2h(c, c->p[35], a.t_start, n))) return rc;
+        if ((rc = d2h(c, c->p[36], a.t_end, n))) return rc;
+        if ((rc = d2h(c, c->p[37], a.t_rev, n))) return rc;
+        if ((rc = d2h(c, c->p[38], a.e_tid, n))) return rc;
+        if ((rc = d2h(c, c->p[39], a.e_rev, n))) return rc;
+        if ((rc = d2h(c, c->p[40], a.cov, n))) return rc;
+        if ((rc = d2h(c, c->p[41], a.ref_out, n))) return rc;
+        NEEDP(c->p[42], (n + 1) * 4);
+        if (n) CK(cudaMemcpyAsync(c->p[42].p, c->tb_off.p, n * 4, cudaMemcpyDeviceToHost, c->st));
+        if ((rc = d2h(c, c->p[43], c->tb_es.as<int32_t>(), (size_t)ne))) return rc;
+        if ((rc = d2h(c, c->p[44], c->tb_ee.as<int32_t>(), (size_t)ne))) return rc;
+        CK(cudaStreamSynchronize(c->st));
+        c->p[42].as<uint32_t>()[n] = (uint32_t)ne;
+        tab->n = nu; tab->name_idx = c->p[32].as<uint32_t>(); tab->piece = c->p[33].as<int32_t>(); tab->t_tid = c->p[34].as<int32_t>();
+        tab->t_start = c->p[35].as<int32_t>(); tab->t_end = c->p[36].as<int32_t>(); tab->t_rev = c->p[37].as<uint8_t>(); tab->e_tid = c->p[38].as<int32_t>();
+        tab->e_rev = c->p[39].as<uint8_t>(); tab->cov = c->p[40].as<int32_t>(); tab->ref_anno = c->p[41].as<int32_t>(); tab->exon_off = c->p[42].as<uint32_t>();
+        tab->exon_start = c->p[43].as<int32_t>(); tab->exon_end = c->p[44].as<int32_t>();
+    } else CK(cudaStreamSynchronize(c->st));
     return LRB_OK;
 }
 

@@ -245,14 +245,21 @@ static int cmd_update(int argc, char **argv, Engine &eng)
     lrb_anno av = anno.view(); lrb_sj sv = sj.view();
     int rc = eng.set_tables(eng.self, &av, nullptr, sj.tid.empty() ? nullptr : &sv);
     if (rc) engine_fail(eng, "update_gtf", rc);
-    lrb_update_result res;
     lrb_batch b = rec.view(); lrb_chains ch = chains.chains();
-    rc = eng.update(eng.self, input_mode == 0 ? &b : nullptr, input_mode == 0 ? nullptr : &ch, &ep, &up, &res);
-    if (rc) engine_fail(eng, "update_gtf", rc);
-
     RowNames rn; if (input_mode == 0) rn.rec = &rec; else rn.chains = &chains;
-    emit_update_outputs(res, rn, anno, h, cn, src.c_str(), anno.gene_n, (int)anno.n(),
-                        out_fp, bam_gtf_fp, detail_fp, known_fp, novel_fp, unrecog_fp, summary_fp, bed_fp);
+    const bool per_read_outputs = bam_gtf_fp || detail_fp || known_fp || novel_fp || unrecog_fp;
+    if (!per_read_outputs && eng.update_table) {      // -o / -y / -E only: fetch just the rows that get printed
+        lrb_trans_table tab{}; lrb_bed_list bed{}; int32_t counts[LRB_S_COUNT] = {0};
+        rc = eng.update_table(eng.self, input_mode == 0 ? &b : nullptr, input_mode == 0 ? nullptr : &ch, &ep, &up, &tab, up.want_summary ? &bed : nullptr, counts);
+        if (rc) engine_fail(eng, "update_gtf", rc);
+        emit_update_table(tab, up.want_summary ? &bed : nullptr, counts, rn, anno, h, cn, src.c_str(), anno.gene_n, (int)anno.n(), out_fp, summary_fp, bed_fp);
+    } else {
+        lrb_update_result res;
+        rc = eng.update(eng.self, input_mode == 0 ? &b : nullptr, input_mode == 0 ? nullptr : &ch, &ep, &up, &res);
+        if (rc) engine_fail(eng, "update_gtf", rc);
+        emit_update_outputs(res, rn, anno, h, cn, src.c_str(), anno.gene_n, (int)anno.n(),
+                            out_fp, bam_gtf_fp, detail_fp, known_fp, novel_fp, unrecog_fp, summary_fp, bed_fp);
+    }
     FILE *fps[] = {out_fp, bed_fp, bam_gtf_fp, detail_fp, known_fp, novel_fp, unrecog_fp, summary_fp};
     for (FILE *f : fps) if (f && f != stdout) fclose(f);
     return 0;

@@ -53,6 +53,49 @@ struct Namer {
 
 }  // namespace
 
+namespace {
+void put_summary(FILE *summary, const int32_t *s, int anno_gene_n, int anno_trans_n)   // update_gtf.c:535-570
+{
+    fprintf(summary, "==== Annotaion ====\n");
+    fprintf(summary, "%s\t%d\n", "Genes_of_annotation_GTF", anno_gene_n);
+    fprintf(summary, "%s\t%d\n", "Transcripts_of_annotation_GTF", anno_trans_n);
+    fprintf(summary, "\n===================\n");
+    fprintf(summary, "\n==== Updated information ====\n");
+    fprintf(summary, "%s\t%d\n", "Updated_Genes", s[LRB_S_UPD_GENES]);
+    fprintf(summary, "%s\t%d\n", "Added_Novel_Transcripts", s[LRB_S_NOVEL_FULL] + s[LRB_S_NOVEL_PARTIAL]);
+    fprintf(summary, "%s\t%d\n", "Added_Novel_Full-read_Transcripts", s[LRB_S_NOVEL_FULL]);
+    fprintf(summary, "%s\t%d\n", "Added_Novel_Partial-read_Transcripts", s[LRB_S_NOVEL_PARTIAL]);
+    fprintf(summary, "%s\t%d\n", "Added_Novel_Exons", s[LRB_S_NOVEL_EXONS]);
+    fprintf(summary, "%s\t%d\n", "Added_Novel_Sites", s[LRB_S_NOVEL_SITES]);
+    fprintf(summary, "%s\t%d\n", "Added_Novel_Splice_Junctions", s[LRB_S_NOVEL_JUNC]);
+    fprintf(summary, "\n=============================\n");
+    fprintf(summary, "\n==== Known information ====\n");
+    fprintf(summary, "%s\t%d\n", "Known_Transcripts_from_BAM", s[LRB_S_KNOWN_TRANS]);
+    fprintf(summary, "%s\t%d\n", "Genes_of_Known_Transcripts_from_BAM", s[LRB_S_KNOWN_GENES]);
+    fprintf(summary, "%s\t%d\n", "Uniq_Known_Transcripts_from_BAM", s[LRB_S_UNIQ_KNOWN]);
+    fprintf(summary, "\n===========================\n");
+    fprintf(summary, "\n==== Novel information ====\n");
+    fprintf(summary, "%s\t%d\n", "Novel_Transcript_from_BAM", s[LRB_S_NOVEL_RELIABLE] + s[LRB_S_NOVEL_UNRELIABLE]);
+    fprintf(summary, "%s\t%d\n", "Novel_Transcript_from_BAM_with_All_Reliable_Junction", s[LRB_S_NOVEL_RELIABLE]);
+    fprintf(summary, "%s\t%d\n", "Uniq_Novel_Transcript_from_BAM_with_All_Reliable_Junction", s[LRB_S_UNIQ_RELIABLE]);
+    fprintf(summary, "%s\t%d\n", "Novel_Transcript_from_BAM_with_Unreliable_Junction", s[LRB_S_NOVEL_UNRELIABLE]);
+    fprintf(summary, "%s\t%d\n", "Uniq_Novel_Transcript_from_BAM_with_Unreliable_Junction", s[LRB_S_UNIQ_UNRELIABLE]);
+    fprintf(summary, "\n===========================\n");
+    fprintf(summary, "\n==== Unrecognized information ====\n");
+    fprintf(summary, "%s\t%d\n", "Unrecognized_Transcript_from_BAM", s[LRB_S_UNRECOG]);
+    fprintf(summary, "%s\t%d\n", "Uniq_Unrecognized_Transcript_from_BAM", s[LRB_S_UNIQ_UNRECOG]);
+    fprintf(summary, "\n==================================\n");
+}
+void put_bed(FILE *bed, const lrb_bed_list &b, const Header &h)                          // update_gtf.c:571-576 (uses the BAM header names)
+{
+    Buf o(bed);
+    for (int64_t i = 0; i < b.n; ++i) {
+        o.put(h.names[b.tid[i]]); o.ch('\t'); o.num(b.start[i] - 1); o.ch('\t'); o.num(b.end[i]); o.ch('\t');
+        o.ch("TIS"[b.type[i]]); o.put("_exon\t"); o.num(b.score[i]); o.ch('\t'); o.ch("+-"[b.is_rev[i]]); o.ch('\n');
+    }
+}
+}  // namespace
+
 // bam2gtf's loop: print_trans for every mapped record (bam2gtf.c:150-156, gtf.c:597-605)
 void emit_bam2gtf(FILE *out, const lrb_exon_result &ex, const Records &rec, const ChrNames &cn, const char *src)
 {
@@ -148,45 +191,31 @@ void emit_update_outputs(const lrb_update_result &res, const RowNames &rn, const
     if (known) { Buf o(known); for (int64_t i = 0; i < res.n_known; ++i) put_row(o, res.known_idx[i]); }
     if (novel) { Buf o(novel); for (int64_t c = 0; c < res.novel.n; ++c) put_list_row(o, c, 1, 0, 0, 0, 0, 0, false); }
     if (unrecog) { Buf o(unrecog); for (int64_t i = 0; i < res.n_unrecog; ++i) put_row(o, res.unrecog_idx[i]); }
-    if (summary) {                                                   // update_gtf.c:535-570
-        const int32_t *s = res.summary;
-        fprintf(summary, "==== Annotaion ====\n");
-        fprintf(summary, "%s\t%d\n", "Genes_of_annotation_GTF", anno_gene_n);
-        fprintf(summary, "%s\t%d\n", "Transcripts_of_annotation_GTF", anno_trans_n);
-        fprintf(summary, "\n===================\n");
-        fprintf(summary, "\n==== Updated information ====\n");
-        fprintf(summary, "%s\t%d\n", "Updated_Genes", s[LRB_S_UPD_GENES]);
-        fprintf(summary, "%s\t%d\n", "Added_Novel_Transcripts", s[LRB_S_NOVEL_FULL] + s[LRB_S_NOVEL_PARTIAL]);
-        fprintf(summary, "%s\t%d\n", "Added_Novel_Full-read_Transcripts", s[LRB_S_NOVEL_FULL]);
-        fprintf(summary, "%s\t%d\n", "Added_Novel_Partial-read_Transcripts", s[LRB_S_NOVEL_PARTIAL]);
-        fprintf(summary, "%s\t%d\n", "Added_Novel_Exons", s[LRB_S_NOVEL_EXONS]);
-        fprintf(summary, "%s\t%d\n", "Added_Novel_Sites", s[LRB_S_NOVEL_SITES]);
-        fprintf(summary, "%s\t%d\n", "Added_Novel_Splice_Junctions", s[LRB_S_NOVEL_JUNC]);
-        fprintf(summary, "\n=============================\n");
-        fprintf(summary, "\n==== Known information ====\n");
-        fprintf(summary, "%s\t%d\n", "Known_Transcripts_from_BAM", s[LRB_S_KNOWN_TRANS]);
-        fprintf(summary, "%s\t%d\n", "Genes_of_Known_Transcripts_from_BAM", s[LRB_S_KNOWN_GENES]);
-        fprintf(summary, "%s\t%d\n", "Uniq_Known_Transcripts_from_BAM", s[LRB_S_UNIQ_KNOWN]);
-        fprintf(summary, "\n===========================\n");
-        fprintf(summary, "\n==== Novel information ====\n");
-        fprintf(summary, "%s\t%d\n", "Novel_Transcript_from_BAM", s[LRB_S_NOVEL_RELIABLE] + s[LRB_S_NOVEL_UNRELIABLE]);
-        fprintf(summary, "%s\t%d\n", "Novel_Transcript_from_BAM_with_All_Reliable_Junction", s[LRB_S_NOVEL_RELIABLE]);
-        fprintf(summary, "%s\t%d\n", "Uniq_Novel_Transcript_from_BAM_with_All_Reliable_Junction", s[LRB_S_UNIQ_RELIABLE]);
-        fprintf(summary, "%s\t%d\n", "Novel_Transcript_from_BAM_with_Unreliable_Junction", s[LRB_S_NOVEL_UNRELIABLE]);
-        fprintf(summary, "%s\t%d\n", "Uniq_Novel_Transcript_from_BAM_with_Unreliable_Junction", s[LRB_S_UNIQ_UNRELIABLE]);
-        fprintf(summary, "\n===========================\n");
-        fprintf(summary, "\n==== Unrecognized information ====\n");
-        fprintf(summary, "%s\t%d\n", "Unrecognized_Transcript_from_BAM", s[LRB_S_UNRECOG]);
-        fprintf(summary, "%s\t%d\n", "Uniq_Unrecognized_Transcript_from_BAM", s[LRB_S_UNIQ_UNRECOG]);
-        fprintf(summary, "\n==================================\n");
-    }
-    if (bed) {                                                       // update_gtf.c:571-576 (uses the BAM header names)
-        Buf o(bed);
-        for (int64_t i = 0; i < res.bed.n; ++i) {
-            o.put(h.names[res.bed.tid[i]]); o.ch('\t'); o.num(res.bed.start[i] - 1); o.ch('\t'); o.num(res.bed.end[i]); o.ch('\t');
-            o.ch("TIS"[res.bed.type[i]]); o.put("_exon\t"); o.num(res.bed.score[i]); o.ch('\t'); o.ch("+-"[res.bed.is_rev[i]]); o.ch('\n');
+    if (summary) put_summary(summary, res.summary, anno_gene_n, anno_trans_n);
+    if (bed) put_bed(bed, res.bed, h);
+}
+
+void emit_update_table(const lrb_trans_table &tab, const lrb_bed_list *bed, const int32_t *summary_counts, const RowNames &rn, const Anno &anno,
+                       const Header &h, const ChrNames &cn, const char *src, int anno_gene_n, int anno_trans_n, FILE *updated, FILE *summary, FILE *bed_fp)
+{
+    if (updated) {
+        Buf o(updated);
+        for (int64_t i = 0; i < tab.n; ++i) {
+            const uint32_t lo = tab.exon_off[i]; const int n = (int)(tab.exon_off[i + 1] - lo);
+            const int64_t k = tab.name_idx[i];
+            TransText t;
+            const int ref = tab.ref_anno[i];
+            if (ref >= 0) { t.gene_id = anno.gene_id[ref].c_str(); t.gene_name = anno.gene_name[ref].c_str(); } else { t.gene_id = "NA"; t.gene_name = "NA"; }
+            std::string id = rn.chains ? rn.chains->trans_id[k] : std::string(rn.rec->qname(k));
+            std::string name = rn.chains ? rn.chains->trans_name[k] : id;
+            if (tab.piece[i] >= 0) { id += ".split." + std::to_string(tab.piece[i]); name += ".split." + std::to_string(tab.piece[i]); }
+            t.trans_id = id.c_str(); t.trans_name = name.c_str();
+            put_read_trans(o, cn.names[tab.t_tid[i]].c_str(), src, tab.t_start[i], tab.t_end[i], tab.t_rev[i], t, tab.cov[i], n, tab.exon_start + lo,
+                           tab.exon_end + lo, tab.exon_start[lo], tab.exon_end[lo + n - 1], cn.names[tab.e_tid[i]].c_str(), tab.e_rev[i]);
         }
     }
+    if (summary && summary_counts) put_summary(summary, summary_counts, anno_gene_n, anno_trans_n);
+    if (bed_fp && bed) put_bed(bed_fp, *bed, h);
 }
 
 // unique-gtf: print_read_trans over unique_T or shared_T (unique_gtf.c:147-148)

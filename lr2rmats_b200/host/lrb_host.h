@@ -87,6 +87,10 @@ void emit_bam2gtf(FILE *out, const lrb_exon_result &ex, const Records &rec, cons
 void emit_update_outputs(const lrb_update_result &res, const RowNames &rn, const Anno &anno, const Header &h, const ChrNames &cn,
                          const char *src, int anno_gene_n, int anno_trans_n,
                          FILE *updated, FILE *bam_gtf, FILE *detail, FILE *known, FILE *novel, FILE *unrecog, FILE *summary, FILE *bed);
+// updated GTF / summary / BED straight from the self-contained table (lrb_update_fetch_table): same bytes as
+// emit_update_outputs(updated, summary, bed) without the per-read tables
+void emit_update_table(const lrb_trans_table &tab, const lrb_bed_list *bed, const int32_t *summary_counts, const RowNames &rn, const Anno &anno,
+                       const Header &h, const ChrNames &cn, const char *src, int anno_gene_n, int anno_trans_n, FILE *updated, FILE *summary, FILE *bed_fp);
 void emit_unique(FILE *out, const lrb_unique_result &res, const RowNames &rn, const ChrNames &cn, const char *src, bool intersect);
 
 // -------------------------------------------------------------------- engine
@@ -99,6 +103,9 @@ struct Engine {
     int (*bam2gtf)(void *, const lrb_batch *, const lrb_exon_params *, lrb_exon_result *) = nullptr;
     int (*update)(void *, const lrb_batch *, const lrb_chains *, const lrb_exon_params *, const lrb_update_params *, lrb_update_result *) = nullptr;
     int (*unique)(void *, const lrb_batch *, const lrb_chains *, const lrb_exon_params *, const lrb_update_params *, lrb_unique_result *) = nullptr;
+    // optional: run update and return only what -o / -y / -E print (NULL: the CLI uses `update` and the full tables)
+    int (*update_table)(void *, const lrb_batch *, const lrb_chains *, const lrb_exon_params *, const lrb_update_params *,
+                        lrb_trans_table *, lrb_bed_list *, int32_t *summary) = nullptr;
     const char *(*error)(void *) = nullptr;
 };
 

@@ -22,6 +22,15 @@ int do_update(void *s, const lrb_batch *b, const lrb_chains *ch, const lrb_exon_
     if (!b) { int rc = lrb_chains_upload(c, ch); if (rc) return rc; }
     return lrb_update_gtf(c, b, ep, up, o);
 }
+int do_update_table(void *s, const lrb_batch *b, const lrb_chains *ch, const lrb_exon_params *ep, const lrb_update_params *up,
+                    lrb_trans_table *tab, lrb_bed_list *bed, int32_t *summary)
+{
+    lrb_ctx *c = ((CudaEngine *)s)->ctx; int rc;
+    if (b) { if ((rc = lrb_batch_upload(c, b))) return rc; if ((rc = lrb_exon_run(c, ep, 0))) return rc; }
+    else if ((rc = lrb_chains_upload(c, ch))) return rc;
+    if ((rc = lrb_update_run(c, up))) return rc;
+    return lrb_update_fetch_table(c, tab, bed, summary);
+}
 int do_unique(void *s, const lrb_batch *b, const lrb_chains *ch, const lrb_exon_params *ep, const lrb_update_params *up, lrb_unique_result *o)
 {
     lrb_ctx *c = ((CudaEngine *)s)->ctx;
@@ -42,7 +51,7 @@ int main(int argc, char **argv)
             return 2;
         }
     }
-    eng.self = &ce; eng.set_tables = set_tables; eng.filter = do_filter; eng.bam2gtf = do_bam2gtf; eng.update = do_update;
+    eng.self = &ce; eng.set_tables = set_tables; eng.filter = do_filter; eng.bam2gtf = do_bam2gtf; eng.update = do_update; eng.update_table = getenv("LRB_FULL_FETCH") ? nullptr : do_update_table;
     eng.unique = do_unique; eng.error = err;
     int rc = lrb::cli_main(argc, argv, eng);
     if (ce.ctx) lrb_ctx_destroy(ce.ctx);

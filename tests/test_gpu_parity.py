@@ -235,3 +235,35 @@ def test_idempotent_and_launches(ctx, data):
     b = ctx.update_gtf(kept.soa(), cabi.ExonParams.default(), up)
     assert_dict_equal(a, b)
     assert n1 - n0 >= 10, "the CUDA kernels must actually have been launched"
+
+
+def _table_from_full(g, name_idx_from_read_idx=True):
+    """What lrb_update_fetch_table must return, derived from the full result tables (emit.cpp put_list_row, use_merged)."""
+    ex, nov, upd = g["ex"], g["novel"], g["updated"]
+    c = upd["cand"].astype(np.int64)
+    row = nov["read"][c].astype(np.int64); lo = ex["exon_off"][row].astype(np.int64) + nov["exon_lo"][c]; n = nov["exon_n"][c].astype(np.int64)
+    piece = nov["piece"][c]
+    off = np.zeros(len(c) + 1, np.uint32); off[1:] = np.cumsum(n)
+    es = np.concatenate([ex["exon_start"][a:a + k] for a, k in zip(lo, n)]) if len(c) else np.zeros(0, np.int32)
+    ee = np.concatenate([ex["exon_end"][a:a + k] for a, k in zip(lo, n)]) if len(c) else np.zeros(0, np.int32)
+    es = es.copy(); ee = ee.copy()
+    es[off[:-1]] = upd["first_start"]; ee[off[1:] - 1] = upd["last_end"]
+    rev = ex["is_rev"][row]
+    return dict(name_idx=(ex["read_idx"][row] if ex["read_idx"] is not None else row.astype(np.uint32)), piece=piece, t_tid=upd["t_tid"], t_start=upd["t_start"],
+                t_end=upd["t_end"], t_rev=np.where(piece >= 0, 0, rev).astype(np.uint8), e_tid=ex["tid"][row], e_rev=rev, cov=upd["cov"],
+                ref_anno=g["ref_anno"][row], exon_off=off, exon_start=es, exon_end=ee)
+
+
+@pytest.mark.parametrize("which", ["iso", "ont"])
+def test_update_fetch_table(ctx, data, which):
+    """The self-contained updated_T table (+ BED + summary) equals what the full per-read tables give."""
+    kept, chains = _kept_chains(data, which)
+    sj = synth.make_sj((chains["tid"], chains["exon_off"], chains["exon_start"], chains["exon_end"]), 0.7, seed=5)
+    up = cabi.UpdateParams.default(full_level=3, split_trans=1)
+    ctx.set_anno(data["anno"].soa()); ctx.set_sj(sj)
+    g = ctx.update_gtf(kept.soa(), cabi.ExonParams.default(), up)
+    t = ctx.update_fetch_table()
+    assert_dict_equal(t["table"], _table_from_full(g))
+    assert_dict_equal(t["bed"], g["bed"])
+    assert np.array_equal(t["summary"], g["summary"])
+    assert (t["table"]["piece"] >= 0).sum() > 0

@@ -44,7 +44,7 @@ struct PBuf {                                       // pinned host buffer
 };
 
 struct MergeBufs {                                  // scratch + output of one merge fold
-    Buf keys, head, locus_start, locus_cnt, dropped, rep, lstart, evmask, hard;
+    Buf keys, head, locus_start, locus_cnt, dropped, rep, lstart, evmask, samemask, hard;
     Buf w_cand, w_cov, w_tid, w_start, w_end, w_fs, w_le;
     Buf o_cand, o_cov, o_tid, o_start, o_end, o_fs, o_le;
     Buf c_tid, c_start, c_end, c_rev, c_n, c_fs, c_le, c_gbeg, c_hash, c_j0, c_sig;
@@ -220,7 +220,7 @@ int setup_merge(lrb_ctx *c, MergeBufs &m, int64_t n_cand)
 {
     size_t n = (size_t)std::max<int64_t>(n_cand, 1);
     NEED(m.keys, n * 8); NEED(m.head, n); NEED(m.locus_start, (n + 1) * 4); NEED(m.locus_cnt, n * 4); NEED(m.dropped, n);
-    NEED(m.rep, n * 4); NEED(m.lstart, n * 4); NEED(m.evmask, n * 8); NEED(m.hard, n);
+    NEED(m.rep, n * 4); NEED(m.lstart, n * 4); NEED(m.evmask, n * 8); NEED(m.samemask, n * 8); NEED(m.hard, n);
     Buf *w[] = {&m.w_cand, &m.w_cov, &m.w_tid, &m.w_start, &m.w_end, &m.w_fs, &m.w_le, &m.o_cand, &m.o_cov, &m.o_tid, &m.o_start, &m.o_end, &m.o_fs, &m.o_le};
     for (Buf *b : w) NEED(*b, n * 4);
     Buf *cb[] = {&m.c_tid, &m.c_start, &m.c_end, &m.c_rev, &m.c_n, &m.c_fs, &m.c_le, &m.c_gbeg};
@@ -235,10 +235,11 @@ DMerged merged_view(Buf &cand, Buf &cov, Buf &tid, Buf &st, Buf &en, Buf &fs, Bu
     return d;
 }
 
-// merge fold over `list` (n_cand entries).  class_off != nullptr: the list is four independent sub-streams folded in one
-// launch and only the survivors per sub-stream are counted (into class_counts); else the result goes to m (o_* arrays, n_out).
+// merge fold over `list` (n_cand entries).  kls != nullptr: the list carries four independent sub-streams (class id per
+// candidate) folded in one pass and only the survivors per sub-stream are counted (into class_counts); else the result goes
+// to m (o_* arrays, n_out).
 int run_merge(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_cand, const lrb_update_params &up,
-              const int64_t *class_off = nullptr, uint32_t *class_counts = nullptr)
+              const uint8_t *kls = nullptr, uint32_t *class_counts = nullptr)
 {
     int rc;
     if ((rc = setup_merge(c, m, n_cand)) != LRB_OK) return rc;
@@ -250,15 +251,15 @@ int run_merge(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_cand, 
     a.rows = *c->cur; a.ex = c->ex; a.up = up; a.list = list; a.n_cand = n_cand;
     a.keys = m.keys.as<uint64_t>(); a.head = m.head.as<uint8_t>(); a.locus_start = m.locus_start.as<uint32_t>(); a.locus_cnt = m.locus_cnt.as<uint32_t>();
     a.dropped = m.dropped.as<uint8_t>();
-    a.rep = m.rep.as<uint32_t>(); a.lstart = m.lstart.as<uint32_t>(); a.evmask = m.evmask.as<uint64_t>(); a.hard = m.hard.as<uint8_t>();
+    a.rep = m.rep.as<uint32_t>(); a.lstart = m.lstart.as<uint32_t>(); a.evmask = m.evmask.as<uint64_t>(); a.samemask = m.samemask.as<uint64_t>(); a.hard = m.hard.as<uint8_t>();
     a.work = merged_view(m.w_cand, m.w_cov, m.w_tid, m.w_start, m.w_end, m.w_fs, m.w_le, n_cand);
     a.out = merged_view(m.o_cand, m.o_cov, m.o_tid, m.o_start, m.o_end, m.o_fs, m.o_le, n_cand);
     a.cd.tid = m.c_tid.as<int32_t>(); a.cd.start = m.c_start.as<int32_t>(); a.cd.end = m.c_end.as<int32_t>(); a.cd.rev = m.c_rev.as<int32_t>();
     a.cd.n = m.c_n.as<int32_t>(); a.cd.fs = m.c_fs.as<int32_t>(); a.cd.le = m.c_le.as<int32_t>(); a.cd.gbeg = m.c_gbeg.as<uint32_t>();
     a.cd.hash = m.c_hash.as<uint64_t>(); a.cd.j0 = m.c_j0.as<uint64_t>(); a.cd.sig = m.c_sig.as<uint64_t>();
     a.tile_state = c->tile_state.as<uint64_t>(); a.ticket = d_ticket(c); a.totals = d_totals(c);
-    if (class_off) {
-        for (int k = 0; k < 5; ++k) a.class_off[k] = class_off[k];
+    if (kls) {
+        a.kls = kls;
         NEED(c->y_counts, 64);
         a.class_alive = c->y_counts.as<uint32_t>() + 8;
         CK(cudaMemsetAsync(a.class_alive, 0, 16, c->st));
@@ -267,7 +268,7 @@ int run_merge(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_cand, 
     tick(c, 10);
     launch_merge_fold(a, c->st);                     // locus count is consumed on the device: no host round trip
     tick(c, 11);
-    if (class_off) {
+    if (kls) {
         launch_merge_class_counts(a, c->st);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(c->h_scalars.p, a.class_alive, 16, cudaMemcpyDeviceToHost, c->st));
@@ -339,7 +340,7 @@ void lrb_ctx_destroy(lrb_ctx *c)
                    &c->tile_state, &c->scalars};
     for (Buf *b : bufs) b->release();
     for (MergeBufs *m : {&c->mg, &c->mg2}) {
-        Buf *w[] = {&m->keys, &m->head, &m->locus_start, &m->locus_cnt, &m->dropped, &m->rep, &m->lstart, &m->evmask, &m->hard, &m->w_cand, &m->w_cov, &m->w_tid, &m->w_start, &m->w_end, &m->w_fs,
+        Buf *w[] = {&m->keys, &m->head, &m->locus_start, &m->locus_cnt, &m->dropped, &m->rep, &m->lstart, &m->evmask, &m->samemask, &m->hard, &m->w_cand, &m->w_cov, &m->w_tid, &m->w_start, &m->w_end, &m->w_fs,
                     &m->w_le, &m->o_cand, &m->o_cov, &m->o_tid, &m->o_start, &m->o_end, &m->o_fs, &m->o_le,
                     &m->c_tid, &m->c_start, &m->c_end, &m->c_rev, &m->c_n, &m->c_fs, &m->c_le, &m->c_gbeg, &m->c_hash, &m->c_j0, &m->c_sig};
         for (Buf *b : w) b->release();
@@ -607,7 +608,7 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
     memset(c->summary, 0, sizeof c->summary); c->n_bed = 0; c->last_up = *up;
     NEED(c->u_cls, nn * 4); NEED(c->u_ref, nn * 4); NEED(c->u_nnovel, nn * 4); NEED(c->u_noff, (nn + 1) * 4);
     NEED(c->u_mk, nn); NEED(c->u_mu, nn); NEED(c->u_known, nn * 4); NEED(c->u_unrecog, nn * 4);
-    if (up->want_summary) { NEED(c->u_ck, nn); NEED(c->u_cr, nn); NEED(c->u_cu, nn); NEED(c->u_cn, nn); NEED(c->u_sub, nn * 16); }
+    if (up->want_summary) { NEED(c->u_ck, nn); NEED(c->y_counts, 64); CK(cudaMemsetAsync(c->y_counts.p, 0, 64, c->st)); }
     if ((rc = ensure_tiles(c, std::max<int64_t>(n, c->ex.n)))) return rc;
     CK(cudaMemsetAsync(d_err(c), 0, 4, c->st));
     tick(c, 0);
@@ -620,8 +621,9 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
     CK(cudaGetLastError());
     tick(c, 1);
     // ---- class lists
+    // u_ck: summary class per row; its sizes go to y_counts[12..15]
     launch_class_masks(ca.cls, n, c->u_mk.as<uint8_t>(), c->u_mu.as<uint8_t>(), up->want_summary ? c->u_ck.as<uint8_t>() : nullptr,
-                       c->u_cr.as<uint8_t>(), c->u_cu.as<uint8_t>(), c->u_cn.as<uint8_t>(), c->st);
+                       c->y_counts.as<uint32_t>() + 12, c->st);
     launch_scan_sum_u32(ca.n_novel, c->u_noff.as<uint32_t>(), n, c->tile_state.as<uint64_t>(), d_ticket(c), d_totals(c) + 0, c->st);
     launch_compact_mask(c->u_mk.as<uint8_t>(), n, nullptr, c->u_known.as<uint32_t>(), nullptr, c->tile_state.as<uint64_t>(), d_ticket(c), d_totals(c) + 1, c->st);
     launch_compact_mask(c->u_mu.as<uint8_t>(), n, nullptr, c->u_unrecog.as<uint32_t>(), nullptr, c->tile_state.as<uint64_t>(), d_ticket(c), d_totals(c) + 2, c->st);
@@ -642,28 +644,21 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
     // ---- summary
     if (up->want_summary) {
         int32_t *s = c->summary;
-        // class counts + uniq_* folds over bam_T (update_gtf.c:501-528): the four classes partition the rows, so they are
-        // laid out back to back in one candidate list and folded together (class-tagged segmentation keys keep them apart)
-        Buf *masks[4] = {&c->u_ck, &c->u_cr, &c->u_cu, &c->u_cn};
+        // class counts + uniq_* folds over bam_T (update_gtf.c:501-528): the four classes partition the rows; they are folded
+        // in ONE pass over all rows, each candidate seeing only the entries of its own class
         const int cnt_idx[4] = {LRB_S_KNOWN_TRANS, LRB_S_NOVEL_RELIABLE, LRB_S_NOVEL_UNRELIABLE, LRB_S_UNRECOG};
         const int uniq_idx[4] = {LRB_S_UNIQ_KNOWN, LRB_S_UNIQ_RELIABLE, LRB_S_UNIQ_UNRELIABLE, LRB_S_UNIQ_UNRECOG};
-        NEED(c->u_sub, nn * 4 * 4);
-        for (int k = 0; k < 4; ++k)
-            launch_compact_mask(masks[k]->as<uint8_t>(), n, nullptr, c->u_sub.as<uint32_t>() + (size_t)k * nn, nullptr, c->tile_state.as<uint64_t>(),
-                                d_ticket(c), d_totals(c) + k, c->st);
-        CK(cudaGetLastError());
-        if ((rc = read_totals(c, t, 4))) return rc;
-        int64_t coff[5] = {0, 0, 0, 0, 0};
-        for (int k = 0; k < 4; ++k) { int64_t m = n ? (int64_t)t[k] : 0; s[cnt_idx[k]] = (int32_t)m; coff[k + 1] = coff[k] + m; }
-        if ((rc = setup_list(c, c->tmp_list, c->t_row, c->t_lo, c->t_cnt, c->t_piece, coff[4]))) return rc;
-        for (int k = 0; k < 4; ++k) {
-            DTransList part = c->tmp_list;
-            part.row += coff[k]; part.lo += coff[k]; part.cnt += coff[k]; part.piece += coff[k];
-            launch_rows_as_list(rows, c->u_sub.as<uint32_t>() + (size_t)k * nn, coff[k + 1] - coff[k], part, c->st);
-        }
+        if ((rc = setup_list(c, c->tmp_list, c->t_row, c->t_lo, c->t_cnt, c->t_piece, n))) return rc;
+        launch_rows_as_list(rows, nullptr, n, c->tmp_list, c->st);
         uint32_t alive[4];
-        if ((rc = run_merge(c, c->mg2, c->tmp_list, coff[4], *up, coff, alive))) return rc;
-        for (int k = 0; k < 4; ++k) s[uniq_idx[k]] = (int32_t)alive[k];
+        if ((rc = run_merge(c, c->mg2, c->tmp_list, n, *up, c->u_ck.as<uint8_t>(), alive))) return rc;
+        uint32_t class_n[4] = {0, 0, 0, 0};
+        if (n) {
+            CK(cudaMemcpyAsync(c->h_scalars.p, c->y_counts.as<uint32_t>() + 12, 16, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            memcpy(class_n, c->h_scalars.p, 16);
+        }
+        for (int k = 0; k < 4; ++k) { s[cnt_idx[k]] = (int32_t)class_n[k]; s[uniq_idx[k]] = (int32_t)alive[k]; }
         s[LRB_S_NOVEL_BAM] = s[LRB_S_NOVEL_RELIABLE] + s[LRB_S_NOVEL_UNRELIABLE];
         // sets over updated_T
         const int64_t nu = c->mg.n_out; const size_t nun = (size_t)std::max<int64_t>(nu, 1);

@@ -115,7 +115,8 @@ struct MergeArgs {
     DTransList list;                                // candidates in fold order
     const uint32_t *subset;                         // optional: rows subset as whole-read candidates (list.n==0): indices into rows
     int64_t n_cand;
-    int64_t class_off[5];                           // optional: candidate ranges of independent sub-streams (class folds); class_off[4]==0: unused
+    const uint8_t *kls;                             // optional: sub-stream id per candidate (class folds: four independent folds in one pass); NULL: one stream
+    uint64_t *samemask;                             // flat fold with kls: earlier candidates of the locus in the same sub-stream
     uint32_t *class_alive;                          // [4] surviving entries per sub-stream
     // scratch
     uint64_t *keys;                                 // per candidate (tid+1)<<32|real_end, then prefix max

@@ -26,8 +26,7 @@ void launch_summary_sets(const SummaryArgs &a, const uint32_t *cls, int64_t n_ro
 void launch_summary_bed(const SummaryArgs &a, cudaStream_t st);
 
 // from lrb_update.cu
-void launch_class_masks(const uint32_t *cls, int64_t n, uint8_t *m_known, uint8_t *m_unrecog, uint8_t *c_known, uint8_t *c_rel,
-                        uint8_t *c_unrel, uint8_t *c_unrec, cudaStream_t st);
+void launch_class_masks(const uint32_t *cls, int64_t n, uint8_t *m_known, uint8_t *m_unrecog, uint8_t *kls, uint32_t *class_n, cudaStream_t st);
 void launch_emit_novel(const ListArgs &a, const uint32_t *novel_off, cudaStream_t st);
 void launch_rows_as_list(const DRows &rows, const uint32_t *subset, int64_t n, DTransList &out, cudaStream_t st);
 void launch_merge_gather(const MergeArgs &a, int64_t n_upper, cudaStream_t st);

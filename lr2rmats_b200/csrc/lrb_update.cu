@@ -525,21 +525,28 @@ __global__ void emit_novel_kernel(ListArgs a, const uint32_t *__restrict__ novel
     }
 }
 
-__global__ void class_masks_kernel(const uint32_t *__restrict__ cls, int64_t n, uint8_t *m_known, uint8_t *m_unrecog,
-                                   uint8_t *c_known, uint8_t *c_rel, uint8_t *c_unrel, uint8_t *c_unrec)
+// per row: known_T / unrecog_T membership masks and the summary class (update_gtf.c:501-528): 0 known, 1 novel with all
+// junctions reliable, 2 novel with an unreliable junction, 3 unrecognized; class sizes are counted on the fly
+__global__ void class_masks_kernel(const uint32_t *cls, int64_t n, uint8_t *m_known, uint8_t *m_unrecog, uint8_t *kls, uint32_t *class_n)
 {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    uint32_t c = cls[r];
-    bool full = c & LRB_C_FULL, known = c & LRB_C_KNOWN, ks = c & LRB_C_KNOWN_SITE, ur = c & LRB_C_UNRELIABLE;
-    m_known[r] = full && known; m_unrecog[r] = full && !known && !ks;
-    if (c_known) { c_known[r] = known; c_rel[r] = !known && ks && !ur; c_unrel[r] = !known && ks && ur; c_unrec[r] = !known && !ks; }
+    int k = -1;
+    if (r < n) {
+        uint32_t c = cls[r];
+        bool full = c & LRB_C_FULL, known = c & LRB_C_KNOWN, ks = c & LRB_C_KNOWN_SITE, ur = c & LRB_C_UNRELIABLE;
+        m_known[r] = full && known; m_unrecog[r] = full && !known && !ks;
+        if (kls) { k = known ? 0 : (ks ? (ur ? 2 : 1) : 3); kls[r] = (uint8_t)k; }
+    }
+    if (kls)
+        for (int q = 0; q < 4; ++q) {
+            unsigned m = __ballot_sync(FULL, k == q);
+            if (m && lane_id() == 0) atomicAdd(&class_n[q], (uint32_t)__popc(m));
+        }
 }
-void launch_class_masks(const uint32_t *cls, int64_t n, uint8_t *m_known, uint8_t *m_unrecog, uint8_t *c_known, uint8_t *c_rel,
-                        uint8_t *c_unrel, uint8_t *c_unrec, cudaStream_t st)
+void launch_class_masks(const uint32_t *cls, int64_t n, uint8_t *m_known, uint8_t *m_unrecog, uint8_t *kls, uint32_t *class_n, cudaStream_t st)
 {
     if (n <= 0) return;
-    class_masks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cls, n, m_known, m_unrecog, c_known, c_rel, c_unrel, c_unrec);
+    class_masks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cls, n, m_known, m_unrecog, kls, class_n);
     LRB_COUNT_LAUNCH();
 }
 void launch_emit_novel(const ListArgs &a, const uint32_t *novel_off, cudaStream_t st)
@@ -570,15 +577,6 @@ void launch_rows_as_list(const DRows &rows, const uint32_t *subset, int64_t n, D
 LRB_DEVINL uint64_t mixh(uint64_t h, uint32_t v) { h ^= v; h *= 0x9E3779B97F4A7C15ull; h ^= h >> 29; return h; }
 LRB_DEVINL int junc_bit(uint64_t jk) { jk *= 0xD6E8FEB86659FD93ull; return (int)(jk >> 58); }
 
-// independent sub-streams folded in one launch: the tag sits above the tid bits of the segmentation keys, so a new
-// sub-stream always starts a new locus
-LRB_DEVINL uint64_t class_tag(const MergeArgs &a, int64_t c)
-{
-    if (a.class_off[4] == 0) return 0;
-    int k = (c >= a.class_off[1]) + (c >= a.class_off[2]) + (c >= a.class_off[3]);
-    return (uint64_t)k << 56;
-}
-
 __global__ void merge_cand_kernel(MergeArgs a)
 {
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -603,14 +601,14 @@ __global__ void merge_cand_kernel(MergeArgs a)
         sig |= 1ull << (junc_bit(jk));
     }
     a.cd.hash[c] = h; a.cd.j0[c] = j0; a.cd.sig[c] = sig;
-    a.keys[c] = class_tag(a, c) | ((uint64_t)(uint32_t)(rtid + 1) << 32) | (uint32_t)le;   // real coordinates: locus segmentation
+    a.keys[c] = ((uint64_t)(uint32_t)(rtid + 1) << 32) | (uint32_t)le;   // real coordinates: locus segmentation
 }
 __global__ void merge_heads_kernel(MergeArgs a)
 {
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_cand) return;
     const uint32_t row = a.list.row[c];
-    uint64_t k = class_tag(a, c) | ((uint64_t)(uint32_t)(a.rows.tid[row] + 1) << 32) | (uint32_t)a.cd.fs[c];
+    uint64_t k = ((uint64_t)(uint32_t)(a.rows.tid[row] + 1) << 32) | (uint32_t)a.cd.fs[c];
     a.head[c] = (c == 0 || k > a.keys[c - 1]) ? 1 : 0;   // new locus: start beyond every earlier end on this chromosome
 }
 void launch_merge_prepare(const MergeArgs &a, cudaStream_t st)
@@ -669,10 +667,9 @@ LRB_DEVINL int chain_iden(const DExons &ex, const Entry &t1, const Entry &t2, in
 }
 
 static constexpr int MF_THREADS = 128;
-static constexpr int MF_SMALL = 32;                 // loci up to this many candidates are folded in shared memory (== MF_SLAB)
 // G lanes per locus; tlist[ls + k] = candidate index of the k-th entry of the locus' T; mutable entry data lives at work[cand]
 template <int G>
-__global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uint32_t *tlist, uint8_t *alive, const uint8_t *locus_hard, int min_m)
+__global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uint32_t *tlist, uint8_t *alive, const uint8_t *locus_hard, int min_m, int max_m)
 {
     const int64_t n_loci = (int64_t)a.totals[0];
     constexpr int GPB = MF_THREADS / G;
@@ -682,7 +679,7 @@ __global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uin
     const CandSoA &cd = a.cd;
     for (int64_t loc = (int64_t)blockIdx.x * GPB + threadIdx.x / G; loc < n_loci; loc += (int64_t)gridDim.x * GPB) {
         const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : a.n_cand;
-        if (le - ls < min_m && !(locus_hard && locus_hard[ls])) continue;    // smaller loci were folded by the flat kernels
+        if ((le - ls < min_m || le - ls > max_m) && !(locus_hard && locus_hard[ls])) continue;   // other loci: flat kernels / another group width
         int cnt = 0;
         for (int64_t c = ls; c < le; ++c) {
             const int t_tid = cd.tid[c], t_start = cd.start[c], t_rv = cd.rev[c], t_rev = t_rv & 1;
@@ -694,7 +691,8 @@ __global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uin
                 uint32_t ec = 0;
                 if (k >= 0) {
                     ec = tlist[ls + k];
-                    if (t_tid > cd.tid[ec] || t_start > a.work.end[ec]) ev = 1;                       // update_gtf.c:148
+                    if (a.kls && a.kls[ec] != a.kls[c]) ev = 0;                                       // another sub-stream: invisible
+                    else if (t_tid > cd.tid[ec] || t_start > a.work.end[ec]) ev = 1;                  // update_gtf.c:148
                     else if (!(a.up.force_strand && t_rev != (cd.rev[ec] & 1))) {                     // :149
                         const Entry E = {cd.n[ec], cd.gbeg[ec], a.work.fs[ec], a.work.le[ec], cd.hash[ec], cd.rev[ec] & 2, cd.j0[ec], cd.sig[ec]};
                         if (te.n == 1 && E.n == 1) {                                                  // merge_trans2 :122-140
@@ -728,86 +726,6 @@ __global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uin
                 ++cnt;
             } else if (gl == 0) alive[c] = 0;
             __syncwarp(gm);
-        }
-    }
-}
-
-// Small loci (<= MF_SLAB candidates): the whole fold state of a locus lives in a shared-memory slab of its 8-lane group --
-// static candidate fields are loaded once, cooperatively and coalesced; the back-scan, the event arbitration and the
-// cov / end extensions run on shared memory; only a verified identical chain or a signature hit of a partial match touches
-// the exon pools.  Results (alive mask, mutable fields of survivors) are written back once.
-static constexpr int MF_SLAB = 32;
-struct __align__(16) Slab {
-    int tid[MF_SLAB], start[MF_SLAB], end[MF_SLAB], rv[MF_SLAB], n[MF_SLAB], fs[MF_SLAB], le[MF_SLAB], cov[MF_SLAB];
-    uint32_t gbeg[MF_SLAB];
-    uint64_t hash[MF_SLAB], j0[MF_SLAB], sig[MF_SLAB];
-    uint8_t tl[MF_SLAB], alive[MF_SLAB];
-};
-__global__ void __launch_bounds__(MF_THREADS) merge_fold_small_kernel(MergeArgs a, uint8_t *alive)
-{
-    constexpr int G = 8, GPB = MF_THREADS / G;
-    __shared__ Slab slabs[GPB];
-    const int gl = threadIdx.x % G, sh = (lane_id() / G) * G;
-    const unsigned gm = group_mask<G>();
-    Slab &S = slabs[threadIdx.x / G];
-    const CandSoA &cd = a.cd;
-    const int64_t n_loci = (int64_t)a.totals[0];
-    for (int64_t loc = (int64_t)blockIdx.x * GPB + threadIdx.x / G; loc < n_loci; loc += (int64_t)gridDim.x * GPB) {
-        const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : a.n_cand;
-        const int m = (int)(le - ls);
-        if (m > MF_SLAB) continue;                               // large loci: merge_fold_kernel<32,false>
-        __syncwarp(gm);
-        for (int k = gl; k < m; k += G) {
-            const int64_t c = ls + k;
-            S.tid[k] = cd.tid[c]; S.start[k] = cd.start[c]; S.end[k] = cd.end[c]; S.rv[k] = cd.rev[c]; S.n[k] = cd.n[c];
-            S.fs[k] = cd.fs[c]; S.le[k] = cd.le[c]; S.gbeg[k] = cd.gbeg[c]; S.hash[k] = cd.hash[c]; S.j0[k] = cd.j0[c]; S.sig[k] = cd.sig[c];
-            S.cov[k] = 1; S.alive[k] = 0;
-        }
-        __syncwarp(gm);
-        int cnt = 0;
-        for (int c = 0; c < m; ++c) {
-            const int t_tid = S.tid[c], t_start = S.start[c], t_rev = S.rv[c] & 1;
-            const Entry te = {S.n[c], S.gbeg[c], S.fs[c], S.le[c], S.hash[c], S.rv[c] & 2, S.j0[c], S.sig[c]};
-            int result = 0;
-            for (int base = cnt - 1; base >= 0; base -= G) {
-                const int k = base - gl;
-                int ev = 0, ec = 0;
-                if (k >= 0) {
-                    ec = S.tl[k];
-                    if (t_tid > S.tid[ec] || t_start > S.end[ec]) ev = 1;
-                    else if (!(a.up.force_strand && t_rev != (S.rv[ec] & 1))) {
-                        const Entry E = {S.n[ec], S.gbeg[ec], S.fs[ec], S.le[ec], S.hash[ec], S.rv[ec] & 2, S.j0[ec], S.sig[ec]};
-                        if (te.n == 1 && E.n == 1) {
-                            if (iabs_dev(te.fs - E.fs) <= a.up.end_dis && iabs_dev(te.le - E.le) <= a.up.end_dis &&
-                                ovlp_frac(te.fs, te.le, E.fs, E.le) >= a.up.single_exon_ovlp_frac) ev = 2;
-                        } else if (te.n > 1 && E.n > 1) {
-                            int r = chain_iden(a.ex, te, E, a.up.ss_dis, a.up.end_dis);
-                            if (r == 0) ev = 2; else if (r == 2) ev = 3;
-                        }
-                    }
-                }
-                const unsigned mk = (__ballot_sync(gm, ev != 0) >> sh) & 0xffu;
-                if (mk) {
-                    const int win = __ffs(mk) - 1;
-                    const int wev = __shfl_sync(gm, ev, sh + win);
-                    if (wev == 2 && gl == win) {
-                        S.cov[ec] += 1;
-                        if (te.fs < S.fs[ec]) { S.fs[ec] = te.fs; S.start[ec] = te.fs; }
-                        if (te.le > S.le[ec]) { S.le[ec] = te.le; S.end[ec] = te.le; }
-                    }
-                    result = wev == 1 ? 0 : 1;
-                    break;
-                }
-            }
-            __syncwarp(gm);
-            if (result == 0) { if (gl == 0) { S.tl[cnt] = (uint8_t)c; S.alive[c] = 1; } ++cnt; }
-            __syncwarp(gm);
-        }
-        for (int k = gl; k < m; k += G) {
-            const int64_t c = ls + k;
-            const uint8_t al = S.alive[k];
-            alive[c] = al;
-            if (al) { a.work.cov[c] = S.cov[k]; a.work.start[c] = S.start[k]; a.work.end[c] = S.end[k]; a.work.fs[c] = S.fs[k]; a.work.le[c] = S.le[k]; }
         }
     }
 }
@@ -861,12 +779,13 @@ __global__ void __launch_bounds__(256) fold_rep_kernel(MergeArgs a, uint32_t *__
     const bool force = a.up.force_strand != 0;
     const int nc = cd.n[c], rvc = cd.rev[c] & 1;
     const uint64_t hc = cd.hash[c];
+    const uint8_t kc = a.kls ? a.kls[c] : 0;
     int64_t e = c, r = c;
     int steps = 0;
     while (!a.head[e]) {
         if (++steps >= FF_MAX) { lstart[c] = FF_BIG; rep[c] = (uint32_t)c; return; }      // deeper than the masks reach
         --e;
-        if (nc > 1 && cd.n[e] == nc && cd.hash[e] == hc && (!force || (cd.rev[e] & 1) == rvc)) r = e;
+        if (nc > 1 && cd.n[e] == nc && cd.hash[e] == hc && (!force || (cd.rev[e] & 1) == rvc) && (!a.kls || a.kls[e] == kc)) r = e;
     }
     if (r != c) {
         const uint32_t gc = cd.gbeg[c], gr = cd.gbeg[r];
@@ -888,7 +807,13 @@ __global__ void __launch_bounds__(256) fold_rel_kernel(MergeArgs a, const uint32
     const bool force = a.up.force_strand != 0;
     const int nc = cd.n[c], rvc = cd.rev[c];
     const uint32_t rc = rep[c];
-    uint64_t mask = 0;
+    uint64_t mask = 0, same = ~0ull;
+    if (a.kls) {                                     // sub-streams (class folds): only the own class is visible
+        const uint8_t kc = a.kls[c];
+        same = 0;
+        for (uint32_t e = ls; e < (uint32_t)c; ++e) if (a.kls[e] == kc) same |= 1ull << (e - ls);
+        a.samemask[c] = same;
+    }
     if (nc == 1) {
         for (uint32_t e = ls; e < (uint32_t)c; ++e)
             if (cd.n[e] == 1 && (!force || ((cd.rev[e] ^ rvc) & 1) == 0)) mask |= 1ull << (e - ls);
@@ -897,7 +822,7 @@ __global__ void __launch_bounds__(256) fold_rel_kernel(MergeArgs a, const uint32
         const uint32_t gb_c = cd.gbeg[c];
         for (uint32_t e = ls; e < (uint32_t)c; ++e) {
             const int ne = cd.n[e];
-            if (ne <= 1) continue;
+            if (ne <= 1 || !((same >> (e - ls)) & 1ull)) continue;
             const uint32_t re = rep[e];
             const uint64_t bit = 1ull << (e - ls);
             if (re != e) { if ((mask >> (re - ls)) & 1ull) mask |= bit; continue; }       // as its representative (decided before)
@@ -913,7 +838,7 @@ __global__ void __launch_bounds__(256) fold_rel_kernel(MergeArgs a, const uint32
             if (hit) mask |= bit;
         }
     }
-    evmask[c] = mask;
+    evmask[c] = mask & same;
 }
 
 __global__ void __launch_bounds__(128) fold_seq_kernel(MergeArgs a, const uint32_t *__restrict__ rep, const uint64_t *__restrict__ evmask,
@@ -932,7 +857,7 @@ __global__ void __launch_bounds__(128) fold_seq_kernel(MergeArgs a, const uint32
         const int64_t c = ls + k;
         const int t_tid = cd.tid[c], t_start = cd.start[c], nc = cd.n[c], fs = cd.fs[c], lend = cd.le[c];
         const uint64_t ev = evmask[c];
-        uint64_t scan = alive;
+        uint64_t scan = a.kls ? (alive & a.samemask[c]) : alive;
         int kind = 0; int64_t hit = 0;                                // kind: 0 append, 1 merge (identical), 2 drop (partial)
         while (scan & ev) {                                           // no candidate event left below: append whatever the stops say
             const int b = 63 - __clzll((long long)scan);
@@ -970,33 +895,32 @@ __global__ void merge_gather_kernel(DMerged work, CandSoA cd, const uint32_t *__
 void launch_merge_fold(const MergeArgs &a, cudaStream_t st)
 {
     if (a.n_cand <= 0) return;
-    // tlist reuses the (no longer needed) 64-bit key scratch; alive reuses the head mask's sibling buffer `dropped`; the
-    // head mask itself becomes the per-locus "hard" flag.  Grids are sized for the worst case (every candidate its own
-    // locus); the locus count is read on the device.
-    static int v4 = -1;
-    if (v4 < 0) { const char *e = getenv("LRB_FOLD_V4"); v4 = e ? atoi(e) : 1; }
-    if (v4 && a.up.ss_dis == 0) {
+    // tlist reuses the (no longer needed) 64-bit key scratch; alive goes to `dropped`.  Grids are sized for the worst
+    // case (every candidate its own locus); the locus count is read on the device.
+    static int flat = -1;
+    if (flat < 0) { const char *e = getenv("LRB_FOLD_FLAT"); flat = e ? atoi(e) : 1; }
+    if (flat && a.up.ss_dis == 0) {
         cudaMemsetAsync(a.hard, 0, (size_t)a.n_cand, st);
         const unsigned bl = (unsigned)((a.n_cand + 255) / 256);
         fold_rep_kernel<<<bl, 256, 0, st>>>(a, a.rep, a.lstart, a.hard); LRB_COUNT_LAUNCH();
         fold_rel_kernel<<<bl, 256, 0, st>>>(a, a.rep, a.lstart, a.evmask); LRB_COUNT_LAUNCH();
         fold_seq_kernel<<<(unsigned)((a.n_cand + 127) / 128), 128, 0, st>>>(a, a.rep, a.evmask, a.hard, a.dropped); LRB_COUNT_LAUNCH();
-        {   // loci beyond the masks, and the (hash-collision) hard ones
-            int64_t bl2 = (a.n_cand / (FF_MAX + 1) + 1 + 3) / 4 + 8; if (bl2 > 148 * 8) bl2 = 148 * 8;
-            merge_fold_kernel<32><<<(unsigned)bl2, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, a.hard, FF_MAX + 1);
-            LRB_COUNT_LAUNCH();
-        }
+        // loci beyond the masks, and the (hash-collision) hard ones
+        int64_t bl2 = (a.n_cand / (FF_MAX + 1) + 1 + 3) / 4 + 8; if (bl2 > 148 * 8) bl2 = 148 * 8;
+        merge_fold_kernel<32><<<(unsigned)bl2, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, a.hard, FF_MAX + 1, 0x7fffffff);
+        LRB_COUNT_LAUNCH();
         return;
     }
+    // inexact splice-site matching (-d > 0): the relation is neither static nor transitive -- lane groups replay the fold
     {
         constexpr int GPB = MF_THREADS / 8;
         int64_t bl = (a.n_cand + GPB - 1) / GPB; if (bl > 148 * 12) bl = 148 * 12;
-        merge_fold_small_kernel<<<(unsigned)bl, MF_THREADS, 0, st>>>(a, a.dropped);
+        merge_fold_kernel<8><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, nullptr, 1, 32);
         LRB_COUNT_LAUNCH();
     }
     {
-        int64_t bl = (a.n_cand / MF_SMALL + 1 + 3) / 4; if (bl > 148 * 8) bl = 148 * 8;     // a large locus has > MF_SMALL candidates
-        merge_fold_kernel<32><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, nullptr, MF_SMALL + 1);
+        int64_t bl = (a.n_cand / 33 + 1 + 3) / 4; if (bl > 148 * 8) bl = 148 * 8;
+        merge_fold_kernel<32><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, nullptr, 33, 0x7fffffff);
         LRB_COUNT_LAUNCH();
     }
 }
@@ -1005,7 +929,7 @@ __global__ void merge_class_counts_kernel(MergeArgs a, const uint8_t *__restrict
 {
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int k = -1;
-    if (c < a.n_cand && alive[c]) k = (c >= a.class_off[1]) + (c >= a.class_off[2]) + (c >= a.class_off[3]);
+    if (c < a.n_cand && alive[c]) k = a.kls[c];
     for (int q = 0; q < 4; ++q) {
         unsigned m = __ballot_sync(FULL, k == q);
         if (m && lane_id() == 0) atomicAdd(&a.class_alive[q], (uint32_t)__popc(m));

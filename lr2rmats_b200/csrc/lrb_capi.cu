@@ -77,7 +77,7 @@ struct lrb_ctx {
     DTransList novel; Buf n_row, n_lo, n_cnt, n_piece;
     DTransList tmp_list; Buf t_row, t_lo, t_cnt, t_piece;
     MergeBufs mg, mg2;
-    int64_t n_known = 0, n_unrecog = 0; bool have_update = false, have_unique = false;
+    int64_t n_known = 0, n_unrecog = 0, novel_cap_hint = 0; bool have_update = false, have_unique = false;
     int32_t summary[LRB_S_COUNT];
     // summary
     Buf h_khi, h_klo, h_min, h_score, y_barcnt, y_barseg, y_genebar, y_bedcnt, y_bedoff, y_counts, y_nelem;
@@ -104,9 +104,11 @@ int fail(lrb_ctx *c, int code, const std::string &msg) { c->err = msg; return co
 #define NEED(buf, bytes) do { if (!(buf).ensure(bytes)) return fail(c, LRB_E_NOMEM, "device allocation failed: " #buf); } while (0)
 #define NEEDP(buf, bytes) do { if (!(buf).ensure(bytes)) return fail(c, LRB_E_NOMEM, "pinned allocation failed: " #buf); } while (0)
 
-// device scalars: [0..7] uint64 totals, then uint32 ticket, err flags, counts[8]
+// device scalars: [0..31] uint64 totals, then uint32 ticket, err flags.  Slots 0..7 are scratch of the stage that is
+// running; the update stage parks its results in fixed slots so that ONE copy brings them all to the host:
+enum { T_NOVEL = 8, T_KNOWN = 9, T_UNREC = 10, T_LOCI = 11, T_UPD = 12, T_LOCI2 = 13, T_UPD2 = 14, T_NELEM = 15, T_BED = 16, T_SLOTS = 32 };
 uint64_t *d_totals(lrb_ctx *c) { return c->scalars.as<uint64_t>(); }
-uint32_t *d_ticket(lrb_ctx *c) { return (uint32_t *)(c->scalars.as<uint64_t>() + 8); }
+uint32_t *d_ticket(lrb_ctx *c) { return (uint32_t *)(c->scalars.as<uint64_t>() + T_SLOTS); }
 uint32_t *d_err(lrb_ctx *c) { return d_ticket(c) + 1; }
 
 int read_totals(lrb_ctx *c, uint64_t *out, int n)
@@ -182,7 +184,7 @@ int run_scan(lrb_ctx *c, int mode, const lrb_filter_params *fp, const lrb_exon_p
         a.rows = c->rows; a.ex = c->ex; a.tile_state = c->tile_state.as<uint64_t>(); a.ticket = d_ticket(c); a.totals = d_totals(c);
         a.reads_per_tile = R; a.stage_words = stage_words;
         CK(cudaMemsetAsync(c->tile_state.p, 0, (size_t)n_tiles * 8, c->st));
-        CK(cudaMemsetAsync(c->scalars.p, 0, 8 * 8 + 4, c->st));
+        CK(cudaMemsetAsync(c->scalars.p, 0, 8 * 8, c->st)); CK(cudaMemsetAsync(d_ticket(c), 0, 4, c->st));
         size_t smem = (size_t)stage_words * 4 + (size_t)3072 * 8;
         tick(c, 8);
         launch_cigar_scan(a, n_tiles, warp_mode, smem, c->st);
@@ -235,20 +237,21 @@ DMerged merged_view(Buf &cand, Buf &cov, Buf &tid, Buf &st, Buf &en, Buf &fs, Bu
     return d;
 }
 
-// merge fold over `list` (n_cand entries).  kls != nullptr: the list carries four independent sub-streams (class id per
-// candidate) folded in one pass and only the survivors per sub-stream are counted (into class_counts); else the result goes
-// to m (o_* arrays, n_out).
-int run_merge(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_cand, const lrb_update_params &up,
-              const uint8_t *kls = nullptr, uint32_t *class_counts = nullptr)
+// merge fold over `list`, asynchronous.  n_cand is the number of candidates, or (n_cand_dev != nullptr) the host's upper
+// bound of a count that lives on the device.  kls != nullptr: the list carries four independent sub-streams (class id per
+// candidate) folded in one pass and only the survivors per sub-stream are counted (class_alive); else the survivors are
+// compacted into m.o_*.  totals[0] <- number of loci, totals[1] <- number of survivors (device).
+int run_merge_async(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_cand, const uint64_t *n_cand_dev, const lrb_update_params &up,
+                    uint64_t *totals, const uint8_t *kls = nullptr, uint32_t *class_alive = nullptr, bool time_fold = false)
 {
     int rc;
     if ((rc = setup_merge(c, m, n_cand)) != LRB_OK) return rc;
     if ((rc = ensure_tiles(c, n_cand)) != LRB_OK) return rc;
     m.n_out = 0; m.n_loci = 0;
-    if (class_counts) memset(class_counts, 0, 16);
+    CK(cudaMemsetAsync(totals, 0, 16, c->st));
     if (n_cand == 0) return LRB_OK;
     MergeArgs a{};
-    a.rows = *c->cur; a.ex = c->ex; a.up = up; a.list = list; a.n_cand = n_cand;
+    a.rows = *c->cur; a.ex = c->ex; a.up = up; a.list = list; a.n_cand = n_cand; a.n_cand_dev = n_cand_dev;
     a.keys = m.keys.as<uint64_t>(); a.head = m.head.as<uint8_t>(); a.locus_start = m.locus_start.as<uint32_t>(); a.locus_cnt = m.locus_cnt.as<uint32_t>();
     a.dropped = m.dropped.as<uint8_t>();
     a.rep = m.rep.as<uint32_t>(); a.lstart = m.lstart.as<uint32_t>(); a.evmask = m.evmask.as<uint64_t>(); a.samemask = m.samemask.as<uint64_t>(); a.hard = m.hard.as<uint8_t>();
@@ -257,32 +260,26 @@ int run_merge(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_cand, 
     a.cd.tid = m.c_tid.as<int32_t>(); a.cd.start = m.c_start.as<int32_t>(); a.cd.end = m.c_end.as<int32_t>(); a.cd.rev = m.c_rev.as<int32_t>();
     a.cd.n = m.c_n.as<int32_t>(); a.cd.fs = m.c_fs.as<int32_t>(); a.cd.le = m.c_le.as<int32_t>(); a.cd.gbeg = m.c_gbeg.as<uint32_t>();
     a.cd.hash = m.c_hash.as<uint64_t>(); a.cd.j0 = m.c_j0.as<uint64_t>(); a.cd.sig = m.c_sig.as<uint64_t>();
-    a.tile_state = c->tile_state.as<uint64_t>(); a.ticket = d_ticket(c); a.totals = d_totals(c);
-    if (kls) {
-        a.kls = kls;
-        NEED(c->y_counts, 64);
-        a.class_alive = c->y_counts.as<uint32_t>() + 8;
-        CK(cudaMemsetAsync(a.class_alive, 0, 16, c->st));
-    }
+    a.tile_state = c->tile_state.as<uint64_t>(); a.ticket = d_ticket(c); a.totals = totals;
+    a.kls = kls; a.class_alive = class_alive;
     launch_merge_prepare(a, c->st);
-    tick(c, 10);
+    if (time_fold) tick(c, 10);
     launch_merge_fold(a, c->st);                     // locus count is consumed on the device: no host round trip
-    tick(c, 11);
-    if (kls) {
-        launch_merge_class_counts(a, c->st);
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(c->h_scalars.p, a.class_alive, 16, cudaMemcpyDeviceToHost, c->st));
-        CK(cudaStreamSynchronize(c->st));
-        memcpy(class_counts, c->h_scalars.p, 16);
-        return LRB_OK;
-    }
-    launch_merge_compact(a, 0, c->st);
-    launch_merge_gather(a, n_cand, c->st);
+    if (time_fold) tick(c, 11);
+    if (kls) launch_merge_class_counts(a, c->st);
+    else launch_merge_finish(a, c->st);
     CK(cudaGetLastError());
+    return LRB_OK;
+}
+
+int run_merge(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_cand, const lrb_update_params &up)
+{
+    int rc;
+    if ((rc = run_merge_async(c, m, list, n_cand, nullptr, up, d_totals(c), nullptr, nullptr, true)) != LRB_OK) return rc;
     uint64_t t[2];
     if ((rc = read_totals(c, t, 2)) != LRB_OK) return rc;
     m.n_loci = (int64_t)t[0]; m.n_out = (int64_t)t[1];
-    if (c->timing) cudaEventElapsedTime(&c->ms[LRB_T_K_FOLD], c->ev[10], c->ev[11]);
+    if (c->timing && n_cand) cudaEventElapsedTime(&c->ms[LRB_T_K_FOLD], c->ev[10], c->ev[11]);
     return LRB_OK;
 }
 
@@ -314,8 +311,8 @@ int lrb_ctx_create(int device, lrb_ctx **out)
     lrb_ctx *c = new lrb_ctx();
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return LRB_E_CUDA; }
-    if (!c->scalars.ensure(256) || !c->h_scalars.ensure(256)) { delete c; return LRB_E_NOMEM; }
-    cudaMemsetAsync(c->scalars.p, 0, 256, c->st);
+    if (!c->scalars.ensure(512) || !c->h_scalars.ensure(512)) { delete c; return LRB_E_NOMEM; }
+    cudaMemsetAsync(c->scalars.p, 0, 512, c->st);
     for (int i = 0; i < 12; ++i) cudaEventCreate(&c->ev[i]);
     for (int i = 0; i < 8; ++i) cudaEventCreate(&c->marks[i]);
     memset(c->ms, 0, sizeof c->ms); memset(c->summary, 0, sizeof c->summary);
@@ -605,10 +602,10 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
     int64_t l0 = total_launches();
     DRows &rows = *c->cur; const int64_t n = rows.n; const size_t nn = (size_t)std::max<int64_t>(n, 1);
     int rc;
-    memset(c->summary, 0, sizeof c->summary); c->n_bed = 0; c->last_up = *up;
-    NEED(c->u_cls, nn * 4); NEED(c->u_ref, nn * 4); NEED(c->u_nnovel, nn * 4); NEED(c->u_noff, (nn + 1) * 4);
-    NEED(c->u_mk, nn); NEED(c->u_mu, nn); NEED(c->u_known, nn * 4); NEED(c->u_unrecog, nn * 4);
-    if (up->want_summary) { NEED(c->u_ck, nn); NEED(c->y_counts, 64); CK(cudaMemsetAsync(c->y_counts.p, 0, 64, c->st)); }
+    memset(c->summary, 0, sizeof c->summary); c->n_bed = 0; c->last_up = *up; c->n_known = c->n_unrecog = 0;
+    NEED(c->u_cls, nn * 4); NEED(c->u_ref, nn * 4); NEED(c->u_nnovel, nn * 4);
+    NEED(c->u_mk, nn); NEED(c->u_known, nn * 4); NEED(c->u_unrecog, nn * 4); NEED(c->u_ck, nn);
+    NEED(c->y_counts, 64); NEED(c->y_nelem, 8);
     if ((rc = ensure_tiles(c, std::max<int64_t>(n, c->ex.n)))) return rc;
     CK(cudaMemsetAsync(d_err(c), 0, 4, c->st));
     tick(c, 0);
@@ -617,84 +614,104 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
     ca.rows = rows; ca.ex = c->ex; ca.anno = c->anno; ca.sj = c->sj; ca.up = *up;
     ca.row_nonmono = c->have_batch ? nullptr : c->r_nonmono.as<uint8_t>();
     ca.cls = c->u_cls.as<uint32_t>(); ca.ref = c->u_ref.as<int32_t>(); ca.n_novel = c->u_nnovel.as<uint32_t>(); ca.err_flags = d_err(c);
-    launch_classify(ca, c->u_mk.as<uint8_t>(), c->st);     // u_mk doubles as the slow-row mask until the class masks are built
+    launch_classify(ca, c->u_mk.as<uint8_t>(), c->st);     // u_mk: scratch for the slow-row mask
     CK(cudaGetLastError());
     tick(c, 1);
-    // ---- class lists
-    // u_ck: summary class per row; its sizes go to y_counts[12..15]
-    launch_class_masks(ca.cls, n, c->u_mk.as<uint8_t>(), c->u_mu.as<uint8_t>(), up->want_summary ? c->u_ck.as<uint8_t>() : nullptr,
-                       c->y_counts.as<uint32_t>() + 12, c->st);
-    launch_scan_sum_u32(ca.n_novel, c->u_noff.as<uint32_t>(), n, c->tile_state.as<uint64_t>(), d_ticket(c), d_totals(c) + 0, c->st);
-    launch_compact_mask(c->u_mk.as<uint8_t>(), n, nullptr, c->u_known.as<uint32_t>(), nullptr, c->tile_state.as<uint64_t>(), d_ticket(c), d_totals(c) + 1, c->st);
-    launch_compact_mask(c->u_mu.as<uint8_t>(), n, nullptr, c->u_unrecog.as<uint32_t>(), nullptr, c->tile_state.as<uint64_t>(), d_ticket(c), d_totals(c) + 2, c->st);
-    CK(cudaGetLastError());
-    if ((rc = check_err_flags(c))) return rc;
-    uint64_t t[4];
-    if ((rc = read_totals(c, t, 3))) return rc;
-    const int64_t n_novel = n ? (int64_t)t[0] : 0; c->n_known = n ? (int64_t)t[1] : 0; c->n_unrecog = n ? (int64_t)t[2] : 0;
-    if ((rc = setup_list(c, c->novel, c->n_row, c->n_lo, c->n_cnt, c->n_piece, n_novel))) return rc;
-    ListArgs la{};
-    la.rows = rows; la.ex = c->ex; la.up = *up; la.cls = ca.cls; la.n_novel = ca.n_novel; la.novel = c->novel;
-    launch_emit_novel(la, c->u_noff.as<uint32_t>(), c->st);
-    CK(cudaGetLastError());
-    // ---- updated_T = merge fold over novel_T
-    tick(c, 2);
-    if ((rc = run_merge(c, c->mg, c->novel, n_novel, *up))) return rc;
-    tick(c, 3);
-    // ---- summary
-    if (up->want_summary) {
+
+    // ---- lists, the updated_T fold, the class folds and the element count of the summary sets: one stream of launches,
+    // every count stays on the device; ONE copy brings them all back.  novel_T is sized optimistically (pieces are rare);
+    // if it turns out too small the pass is repeated once with the exact size.
+    uint64_t *T = d_totals(c);
+    int64_t cap = up->split_trans ? n + n / 8 + 1024 : n;
+    cap = std::max<int64_t>(cap, std::min<int64_t>(c->novel_cap_hint, n + c->ex.n / 2 + 1));
+    SummaryArgs sa{};
+    int64_t n_novel = 0, nu = 0; uint64_t n_elem = 0;
+    uint32_t cnt16[16];
+    for (int attempt = 0; n > 0; ++attempt) {
+        if ((rc = setup_list(c, c->novel, c->n_row, c->n_lo, c->n_cnt, c->n_piece, cap))) return rc;
+        c->novel.cap = cap;
+        CK(cudaMemsetAsync(c->y_counts.p, 0, 64, c->st)); CK(cudaMemsetAsync(c->y_nelem.p, 0, 8, c->st));
+        ListArgs la{};
+        la.rows = rows; la.ex = c->ex; la.up = *up; la.cls = ca.cls; la.n_novel = ca.n_novel; la.novel = c->novel;
+        la.known = c->u_known.as<uint32_t>(); la.unrecog = c->u_unrecog.as<uint32_t>();
+        la.kls = up->want_summary ? c->u_ck.as<uint8_t>() : nullptr; la.class_n = c->y_counts.as<uint32_t>() + 12;
+        la.tile_state = c->tile_state.as<uint64_t>(); la.ticket = d_ticket(c); la.totals = T + T_NOVEL;
+        launch_build_lists(la, c->st);
+        CK(cudaGetLastError());
+        if (attempt == 0) tick(c, 2);
+        // updated_T = merge fold over novel_T (update_gtf.c:949,956)
+        if ((rc = run_merge_async(c, c->mg, c->novel, cap, T + T_NOVEL, *up, T + T_LOCI, nullptr, nullptr, true))) return rc;
+        if (attempt == 0) tick(c, 3);
+        if (up->want_summary) {
+            // class counts + uniq_* folds over bam_T (update_gtf.c:501-528): the four classes partition the rows; they are
+            // folded in ONE pass over all rows, each candidate seeing only the entries of its own class
+            if ((rc = setup_list(c, c->tmp_list, c->t_row, c->t_lo, c->t_cnt, c->t_piece, n))) return rc;
+            launch_rows_as_list(rows, nullptr, n, c->tmp_list, c->st);
+            if ((rc = run_merge_async(c, c->mg2, c->tmp_list, n, nullptr, *up, T + T_LOCI2, c->u_ck.as<uint8_t>(), c->y_counts.as<uint32_t>() + 8))) return rc;
+            // sets over updated_T: element count (sizes the hash table)
+            const size_t capn = (size_t)std::max<int64_t>(cap, 1);
+            NEED(c->y_barcnt, capn * 16); NEED(c->y_barseg, capn * 16); NEED(c->y_genebar, capn * 8); NEED(c->y_bedcnt, capn * 4); NEED(c->y_bedoff, capn * 4);
+            sa = SummaryArgs{};
+            sa.rows = rows; sa.ex = c->ex; sa.list = c->novel; sa.n_upd = cap; sa.n_upd_dev = T + T_UPD;
+            sa.upd = merged_view(c->mg.o_cand, c->mg.o_cov, c->mg.o_tid, c->mg.o_start, c->mg.o_end, c->mg.o_fs, c->mg.o_le, cap);
+            sa.ref = c->u_ref.as<int32_t>(); sa.anno_gene = c->anno.gene;
+            sa.bar_cnt = c->y_barcnt.as<uint32_t>(); sa.bar_seg = c->y_barseg.as<uint32_t>(); sa.gene_bar = c->y_genebar.as<uint64_t>();
+            sa.bed_cnt = c->y_bedcnt.as<uint32_t>(); sa.bed_off = c->y_bedoff.as<uint32_t>(); sa.counts = c->y_counts.as<uint32_t>();
+            launch_summary_count(sa, c->y_nelem.as<unsigned long long>(), c->st);
+            CK(cudaGetLastError());
+        }
+        // ---- the one round trip: totals, error flags, class counters, element count
+        uint8_t *hp = (uint8_t *)c->h_scalars.p;
+        CK(cudaMemcpyAsync(hp, c->scalars.p, T_SLOTS * 8 + 8, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(hp + 320, c->y_counts.p, 64, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(hp + 384, c->y_nelem.p, 8, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaStreamSynchronize(c->st));
+        uint64_t t[T_SLOTS]; uint32_t e[2];
+        memcpy(t, hp, sizeof t); memcpy(e, hp + T_SLOTS * 8, 8); memcpy(cnt16, hp + 320, 64); memcpy(&n_elem, hp + 384, 8);
+        if (e[1] & 2u) return fail(c, LRB_E_UNMAPPED, "unmapped record / empty exon chain in update/unique input (the reference aborts here, bam2gtf.c:95-100)");
+        if (e[1] & 1u) return fail(c, LRB_E_UNSORTED, "reads are not sorted by (tid,start) (update_gtf.c:41)");
+        n_novel = (int64_t)t[T_NOVEL]; c->n_known = (int64_t)t[T_KNOWN]; c->n_unrecog = (int64_t)t[T_UNREC];
+        if (n_novel > cap) {                          // novel_T did not fit: once more with the exact size
+            if (attempt >= 1) return fail(c, LRB_E_CUDA, "novel_T size changed between passes");
+            cap = n_novel; c->novel_cap_hint = n_novel + n_novel / 16;
+            continue;
+        }
+        c->mg.n_loci = (int64_t)t[T_LOCI]; c->mg.n_out = nu = (int64_t)t[T_UPD];
+        break;
+    }
+    if (n == 0) { if ((rc = setup_list(c, c->novel, c->n_row, c->n_lo, c->n_cnt, c->n_piece, 0))) return rc; c->mg.n_out = c->mg.n_loci = 0; tick(c, 2); tick(c, 3); }
+    c->novel.n = n_novel; c->novel.cap = std::max<int64_t>(cap, 0);
+    if (c->timing && n) { CK(cudaStreamSynchronize(c->st)); cudaEventElapsedTime(&c->ms[LRB_T_K_FOLD], c->ev[10], c->ev[11]); }
+
+    // ---- summary sets (print_trans_summary, update_gtf.c:421-587)
+    if (up->want_summary && n > 0) {
         int32_t *s = c->summary;
-        // class counts + uniq_* folds over bam_T (update_gtf.c:501-528): the four classes partition the rows; they are folded
-        // in ONE pass over all rows, each candidate seeing only the entries of its own class
         const int cnt_idx[4] = {LRB_S_KNOWN_TRANS, LRB_S_NOVEL_RELIABLE, LRB_S_NOVEL_UNRELIABLE, LRB_S_UNRECOG};
         const int uniq_idx[4] = {LRB_S_UNIQ_KNOWN, LRB_S_UNIQ_RELIABLE, LRB_S_UNIQ_UNRELIABLE, LRB_S_UNIQ_UNRECOG};
-        if ((rc = setup_list(c, c->tmp_list, c->t_row, c->t_lo, c->t_cnt, c->t_piece, n))) return rc;
-        launch_rows_as_list(rows, nullptr, n, c->tmp_list, c->st);
-        uint32_t alive[4];
-        if ((rc = run_merge(c, c->mg2, c->tmp_list, n, *up, c->u_ck.as<uint8_t>(), alive))) return rc;
-        uint32_t class_n[4] = {0, 0, 0, 0};
-        if (n) {
-            CK(cudaMemcpyAsync(c->h_scalars.p, c->y_counts.as<uint32_t>() + 12, 16, cudaMemcpyDeviceToHost, c->st));
-            CK(cudaStreamSynchronize(c->st));
-            memcpy(class_n, c->h_scalars.p, 16);
-        }
-        for (int k = 0; k < 4; ++k) { s[cnt_idx[k]] = (int32_t)class_n[k]; s[uniq_idx[k]] = (int32_t)alive[k]; }
+        for (int k = 0; k < 4; ++k) { s[cnt_idx[k]] = (int32_t)cnt16[12 + k]; s[uniq_idx[k]] = (int32_t)cnt16[8 + k]; }
         s[LRB_S_NOVEL_BAM] = s[LRB_S_NOVEL_RELIABLE] + s[LRB_S_NOVEL_UNRELIABLE];
-        // sets over updated_T
-        const int64_t nu = c->mg.n_out; const size_t nun = (size_t)std::max<int64_t>(nu, 1);
-        NEED(c->y_barcnt, nun * 16); NEED(c->y_barseg, nun * 16); NEED(c->y_genebar, nun * 8); NEED(c->y_bedcnt, nun * 4); NEED(c->y_bedoff, nun * 4);
-        NEED(c->y_counts, 64); NEED(c->y_nelem, 8);
-        CK(cudaMemsetAsync(c->y_counts.p, 0, 64, c->st)); CK(cudaMemsetAsync(c->y_nelem.p, 0, 8, c->st));
-        SummaryArgs sa{};
-        sa.rows = rows; sa.ex = c->ex; sa.list = c->novel; sa.n_upd = nu;
-        sa.upd = merged_view(c->mg.o_cand, c->mg.o_cov, c->mg.o_tid, c->mg.o_start, c->mg.o_end, c->mg.o_fs, c->mg.o_le, nu);
-        sa.ref = c->u_ref.as<int32_t>(); sa.anno_gene = c->anno.gene;
-        sa.bar_cnt = c->y_barcnt.as<uint32_t>(); sa.bar_seg = c->y_barseg.as<uint32_t>(); sa.gene_bar = c->y_genebar.as<uint64_t>();
-        sa.bed_cnt = c->y_bedcnt.as<uint32_t>(); sa.bed_off = c->y_bedoff.as<uint32_t>(); sa.counts = c->y_counts.as<uint32_t>();
-        launch_summary_count(sa, c->y_nelem.as<unsigned long long>(), c->st);
-        CK(cudaMemcpyAsync(c->h_scalars.p, c->y_nelem.p, 8, cudaMemcpyDeviceToHost, c->st));
-        CK(cudaStreamSynchronize(c->st));
-        uint64_t n_elem; memcpy(&n_elem, c->h_scalars.p, 8);
+        sa.n_upd = nu; sa.n_upd_dev = nullptr; sa.upd.n = nu;
         const uint64_t capn = pow2_at_least(2 * (n_elem + (uint64_t)s[LRB_S_KNOWN_TRANS]) + 1024);
-        NEED(c->h_khi, capn * 8); NEED(c->h_klo, capn * 8); NEED(c->h_min, capn * 8); NEED(c->h_score, capn * 4);
-        CK(cudaMemsetAsync(c->h_khi.p, 0xFF, capn * 8, c->st)); CK(cudaMemsetAsync(c->h_klo.p, 0xFF, capn * 8, c->st));
-        CK(cudaMemsetAsync(c->h_min.p, 0xFF, capn * 8, c->st)); CK(cudaMemsetAsync(c->h_score.p, 0, capn * 4, c->st));
-        sa.tab.mask = capn - 1; sa.tab.khi = c->h_khi.as<uint64_t>(); sa.tab.klo = c->h_klo.as<uint64_t>(); sa.tab.minpos = c->h_min.as<uint64_t>();
+        NEED(c->h_khi, capn * 24); NEED(c->h_score, capn * 4);          // khi | klo | minpos in one buffer: one fill
+        CK(cudaMemsetAsync(c->h_khi.p, 0xFF, capn * 24, c->st)); CK(cudaMemsetAsync(c->h_score.p, 0, capn * 4, c->st));
+        sa.tab.mask = capn - 1; sa.tab.khi = c->h_khi.as<uint64_t>(); sa.tab.klo = sa.tab.khi + capn; sa.tab.minpos = sa.tab.khi + 2 * capn;
         sa.tab.score = c->h_score.as<int32_t>();
-        launch_summary_sets(sa, ca.cls, n, c->tile_state.as<uint64_t>(), d_ticket(c), d_totals(c) + 3, c->st);
-        CK(cudaGetLastError());
-        if ((rc = read_totals(c, t, 4))) return rc;
-        c->n_bed = nu ? (int64_t)t[3] : 0;
-        const size_t nb = (size_t)std::max<int64_t>(c->n_bed, 1);
+        // BED rows are the first occurrences of the exon set: at most one per counted element
+        const size_t nb = (size_t)std::max<uint64_t>(n_elem, 1);
         NEED(c->bd_tid, nb * 4); NEED(c->bd_s, nb * 4); NEED(c->bd_e, nb * 4); NEED(c->bd_sc, nb * 4); NEED(c->bd_ty, nb); NEED(c->bd_rv, nb);
         sa.bed_tid = c->bd_tid.as<int32_t>(); sa.bed_start = c->bd_s.as<int32_t>(); sa.bed_end = c->bd_e.as<int32_t>(); sa.bed_score = c->bd_sc.as<int32_t>();
         sa.bed_type = c->bd_ty.as<uint8_t>(); sa.bed_rev = c->bd_rv.as<uint8_t>();
+        CK(cudaMemsetAsync(c->y_counts.p, 0, 32, c->st));
+        launch_summary_sets(sa, ca.cls, n, c->tile_state.as<uint64_t>(), d_ticket(c), T + T_BED, c->st);
         launch_summary_bed(sa, c->st);
         CK(cudaGetLastError());
-        uint32_t cnt[8];
-        CK(cudaMemcpyAsync(c->h_scalars.p, c->y_counts.p, 32, cudaMemcpyDeviceToHost, c->st));
+        uint8_t *hp = (uint8_t *)c->h_scalars.p;
+        CK(cudaMemcpyAsync(hp, T + T_BED, 8, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(hp + 64, c->y_counts.p, 32, cudaMemcpyDeviceToHost, c->st));
         CK(cudaStreamSynchronize(c->st));
-        memcpy(cnt, c->h_scalars.p, 32);
+        uint64_t nbed; uint32_t cnt[8];
+        memcpy(&nbed, hp, 8); memcpy(cnt, hp + 64, 32);
+        c->n_bed = nu ? (int64_t)nbed : 0;
         s[LRB_S_UPD_GENES] = (int32_t)cnt[4]; s[LRB_S_NOVEL_TRANS] = (int32_t)nu; s[LRB_S_NOVEL_PARTIAL] = (int32_t)cnt[6];
         s[LRB_S_NOVEL_FULL] = (int32_t)nu - (int32_t)cnt[6]; s[LRB_S_NOVEL_EXONS] = (int32_t)cnt[0]; s[LRB_S_NOVEL_SITES] = (int32_t)(cnt[1] + cnt[2]);
         s[LRB_S_NOVEL_JUNC] = (int32_t)cnt[3]; s[LRB_S_KNOWN_GENES] = (int32_t)cnt[5];

@@ -95,10 +95,12 @@ struct DTransList {                                 // transcript rows of a list
 struct ListArgs {
     DRows rows; DExons ex; lrb_update_params up;
     const uint32_t *cls; const uint32_t *n_novel;
-    DTransList novel; uint32_t *known, *unrecog;
+    DTransList novel; uint32_t *known, *unrecog;    // novel.cap bounds the writes; the true size is totals[0]
+    uint8_t *kls; uint32_t *class_n;                // optional (summary): class per row, class sizes [4]
     uint64_t *tile_state; uint32_t *ticket; uint64_t *totals;   // [0] novel, [1] known, [2] unrecog
+    int n_tiles;
 };
-void launch_build_lists(const ListArgs &a, cudaStream_t st);
+void launch_build_lists(ListArgs a, cudaStream_t st);
 
 struct DMerged {
     int64_t n = 0, cap = 0;
@@ -114,7 +116,9 @@ struct MergeArgs {
     DRows rows; DExons ex; lrb_update_params up; CandSoA cd;
     DTransList list;                                // candidates in fold order
     const uint32_t *subset;                         // optional: rows subset as whole-read candidates (list.n==0): indices into rows
-    int64_t n_cand;
+    int64_t n_cand;                                 // candidates (host value, or the host's upper bound when n_cand_dev is set)
+    const uint64_t *n_cand_dev;                     // optional: the true count, produced on the device
+    int n_tiles;
     const uint8_t *kls;                             // optional: sub-stream id per candidate (class folds: four independent folds in one pass); NULL: one stream
     uint64_t *samemask;                             // flat fold with kls: earlier candidates of the locus in the same sub-stream
     uint32_t *class_alive;                          // [4] surviving entries per sub-stream
@@ -130,10 +134,10 @@ struct MergeArgs {
     DMerged out;                                    // compacted result
     uint64_t *tile_state; uint32_t *ticket; uint64_t *totals;  // [0] n_loci, [1] n_out
 };
-void launch_merge_prepare(const MergeArgs &a, cudaStream_t st);     // keys + prefix max + heads
-void launch_merge_fold(const MergeArgs &a, cudaStream_t st);            // number of loci is read from a.totals[0] on the device
+void launch_merge_prepare(MergeArgs a, cudaStream_t st);            // candidates, locus heads, locus_start; totals[0] = number of loci
+void launch_merge_fold(const MergeArgs &a, cudaStream_t st);        // number of loci is read from a.totals[0] on the device
 void launch_merge_class_counts(const MergeArgs &a, cudaStream_t st);
-void launch_merge_compact(const MergeArgs &a, int64_t n_loci, cudaStream_t st);
+void launch_merge_finish(MergeArgs a, cudaStream_t st);             // survivors compacted into a.out; totals[1] = their number
 
 // generic device scans used by the stages above
 void launch_scan_max_u64(uint64_t *data, int64_t n, uint64_t *tile_state, uint32_t *ticket, cudaStream_t st);   // inclusive prefix max, in place

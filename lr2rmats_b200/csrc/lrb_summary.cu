@@ -78,7 +78,7 @@ __global__ void sum_count_kernel(SummaryArgs a, unsigned long long *n_elems)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long c = 0;
-    if (i < a.n_upd) {
+    if (i < (a.n_upd_dev ? (int64_t)*a.n_upd_dev : a.n_upd)) {
         EntryView e = load_entry(a, i);
         const uint8_t *f = a.ex.flag + e.gbeg;
         c = 1;

@@ -12,6 +12,7 @@ struct HashTab {                                    // open addressing, 128-bit 
 
 struct SummaryArgs {
     DRows rows; DExons ex; DTransList list; DMerged upd; int64_t n_upd;
+    const uint64_t *n_upd_dev;                      // sum_count_kernel only: the count still lives on the device (n_upd is then an upper bound)
     const int32_t *ref; const int32_t *anno_gene;
     HashTab tab;
     uint32_t *bar_cnt, *bar_seg;                    // [4][n_upd]: inserted tid-0 elements per entry / their exclusive scan
@@ -26,9 +27,6 @@ void launch_summary_sets(const SummaryArgs &a, const uint32_t *cls, int64_t n_ro
 void launch_summary_bed(const SummaryArgs &a, cudaStream_t st);
 
 // from lrb_update.cu
-void launch_class_masks(const uint32_t *cls, int64_t n, uint8_t *m_known, uint8_t *m_unrecog, uint8_t *kls, uint32_t *class_n, cudaStream_t st);
-void launch_emit_novel(const ListArgs &a, const uint32_t *novel_off, cudaStream_t st);
 void launch_rows_as_list(const DRows &rows, const uint32_t *subset, int64_t n, DTransList &out, cudaStream_t st);
-void launch_merge_gather(const MergeArgs &a, int64_t n_upper, cudaStream_t st);
 
 }  // namespace lrbk

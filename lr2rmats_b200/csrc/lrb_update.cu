@@ -495,64 +495,77 @@ void launch_classify(const ClassArgs &a, uint8_t *slow, cudaStream_t st)
     LRB_COUNT_LAUNCH();
 }
 
-// ------------------------------------------------------------------------------------ novel_T rows (reads / pieces)
-__global__ void emit_novel_kernel(ListArgs a, const uint32_t *__restrict__ novel_off)
+// ------------------------------------------------------------------ class lists: novel_T / known_T / unrecog_T in one pass
+// One pass over the classified rows builds, in row order: novel_T (whole reads and the split pieces of split_trans,
+// update_gtf.c:837-913), the known_T and unrecog_T row lists (:941-962), and -- for the summary -- the class of every row
+// (0 known, 1 novel with all junctions reliable, 2 novel with an unreliable junction, 3 unrecognized; :501-528) with the class
+// sizes.  Three running counts ride on two look-back chains; the list sizes stay on the device (totals[0..2]).
+static constexpr int LS_THREADS = 256;
+__global__ void __launch_bounds__(LS_THREADS) build_lists_kernel(ListArgs a)
 {
-    int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint32_t s_scan[33];
+    __shared__ uint32_t s_tile; __shared__ uint64_t s_excl[2];
+    if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const int tile = (int)s_tile;
+    const int64_t row = (int64_t)tile * LS_THREADS + threadIdx.x;
+    uint32_t nn = 0, kn = 0, un = 0, c = 0;
+    int k = -1;
+    if (row < a.rows.n) {
+        c = a.cls[row]; nn = a.n_novel[row];
+        const bool full = c & LRB_C_FULL, known = c & LRB_C_KNOWN, ks = c & LRB_C_KNOWN_SITE, ur = c & LRB_C_UNRELIABLE;
+        kn = full && known; un = full && !known && !ks;
+        if (a.kls) { k = known ? 0 : (ks ? (ur ? 2 : 1) : 3); a.kls[row] = (uint8_t)k; }
+    }
+    if (a.kls)
+        for (int q = 0; q < 4; ++q) {
+            const unsigned m = __ballot_sync(FULL, k == q);
+            if (m && lane_id() == 0) atomicAdd(&a.class_n[q], (uint32_t)__popc(m));
+        }
+    uint32_t nn_tot, kn_tot, un_tot;
+    const uint32_t nn_ex = block_excl_sum(nn, s_scan, &nn_tot), kn_ex = block_excl_sum(kn, s_scan, &kn_tot), un_ex = block_excl_sum(un, s_scan, &un_tot);
+    if (warp_id() == 0) {
+        const uint64_t e0 = lookback_exclusive(a.tile_state, tile, pack_pair(nn_tot, kn_tot), OpAdd());
+        const uint64_t e1 = lookback_exclusive(a.tile_state + a.n_tiles, tile, (uint64_t)un_tot, OpAdd());
+        if (lane_id() == 0) { s_excl[0] = e0; s_excl[1] = e1; }
+    }
+    __syncthreads();
+    const uint32_t nn_base = pair_hi(s_excl[0]), kn_base = pair_lo(s_excl[0]), un_base = (uint32_t)s_excl[1];
+    if ((int64_t)(tile + 1) * LS_THREADS >= a.rows.n && threadIdx.x == 0) {
+        a.totals[0] = (uint64_t)nn_base + nn_tot; a.totals[1] = (uint64_t)kn_base + kn_tot; a.totals[2] = (uint64_t)un_base + un_tot;
+    }
     if (row >= a.rows.n) return;
-    uint32_t nn = a.n_novel[row];
+    if (kn) a.known[kn_base + kn_ex] = (uint32_t)row;
+    if (un) a.unrecog[un_base + un_ex] = (uint32_t)row;
     if (!nn) return;
-    uint32_t o = novel_off[row];
+    uint32_t o = nn_base + nn_ex;
+    if ((int64_t)o + nn > a.novel.cap) return;       // list sized too small: the host sees the total and repeats the pass
     const int n = (int)a.rows.ex_n[row];
-    uint32_t c = a.cls[row];
     if (!((c & LRB_C_SJ_CHECKED) && (c & LRB_C_UNRELIABLE))) {
         a.novel.row[o] = (uint32_t)row; a.novel.lo[o] = 0; a.novel.cnt[o] = (uint32_t)n; a.novel.piece[o] = -1;
         return;
     }
     const uint8_t *fl = a.ex.flag + a.rows.ex_beg[row];
     int last = 0, has_novel = 0, has_known = 0, k2 = 0;
-    for (int k = 0; k <= n - 1; ++k) {
-        bool at_end = k == n - 1;
-        uint8_t f = fl[k];
+    for (int j = 0; j <= n - 1; ++j) {
+        const bool at_end = j == n - 1;
+        const uint8_t f = fl[j];
         if (!at_end) { if (f & LRB_F_NOVEL_JUNC) has_novel = 1; else has_known = 1; }
         if (at_end || (f & LRB_F_UNRELIABLE)) {
-            if (has_novel && has_known && k - last >= 1) {
-                a.novel.row[o] = (uint32_t)row; a.novel.lo[o] = (uint32_t)last; a.novel.cnt[o] = (uint32_t)(k - last + 1); a.novel.piece[o] = k2;
+            if (has_novel && has_known && j - last >= 1) {
+                a.novel.row[o] = (uint32_t)row; a.novel.lo[o] = (uint32_t)last; a.novel.cnt[o] = (uint32_t)(j - last + 1); a.novel.piece[o] = k2;
                 ++o; ++k2;
             }
-            last = k + 1; has_novel = 0; has_known = 0;
+            last = j + 1; has_novel = 0; has_known = 0;
         }
     }
 }
-
-// per row: known_T / unrecog_T membership masks and the summary class (update_gtf.c:501-528): 0 known, 1 novel with all
-// junctions reliable, 2 novel with an unreliable junction, 3 unrecognized; class sizes are counted on the fly
-__global__ void class_masks_kernel(const uint32_t *cls, int64_t n, uint8_t *m_known, uint8_t *m_unrecog, uint8_t *kls, uint32_t *class_n)
+void launch_build_lists(ListArgs a, cudaStream_t st)
 {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int k = -1;
-    if (r < n) {
-        uint32_t c = cls[r];
-        bool full = c & LRB_C_FULL, known = c & LRB_C_KNOWN, ks = c & LRB_C_KNOWN_SITE, ur = c & LRB_C_UNRELIABLE;
-        m_known[r] = full && known; m_unrecog[r] = full && !known && !ks;
-        if (kls) { k = known ? 0 : (ks ? (ur ? 2 : 1) : 3); kls[r] = (uint8_t)k; }
-    }
-    if (kls)
-        for (int q = 0; q < 4; ++q) {
-            unsigned m = __ballot_sync(FULL, k == q);
-            if (m && lane_id() == 0) atomicAdd(&class_n[q], (uint32_t)__popc(m));
-        }
-}
-void launch_class_masks(const uint32_t *cls, int64_t n, uint8_t *m_known, uint8_t *m_unrecog, uint8_t *kls, uint32_t *class_n, cudaStream_t st)
-{
-    if (n <= 0) return;
-    class_masks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cls, n, m_known, m_unrecog, kls, class_n);
-    LRB_COUNT_LAUNCH();
-}
-void launch_emit_novel(const ListArgs &a, const uint32_t *novel_off, cudaStream_t st)
-{
-    if (a.rows.n <= 0) return;
-    emit_novel_kernel<<<(unsigned)((a.rows.n + 255) / 256), 256, 0, st>>>(a, novel_off);
+    if (a.rows.n <= 0) { cudaMemsetAsync(a.totals, 0, 24, st); return; }
+    a.n_tiles = (int)((a.rows.n + LS_THREADS - 1) / LS_THREADS);
+    cudaMemsetAsync(a.tile_state, 0, (size_t)a.n_tiles * 16, st); cudaMemsetAsync(a.ticket, 0, 4, st);
+    build_lists_kernel<<<(unsigned)a.n_tiles, LS_THREADS, 0, st>>>(a);
     LRB_COUNT_LAUNCH();
 }
 
@@ -577,48 +590,79 @@ void launch_rows_as_list(const DRows &rows, const uint32_t *subset, int64_t n, D
 LRB_DEVINL uint64_t mixh(uint64_t h, uint32_t v) { h ^= v; h *= 0x9E3779B97F4A7C15ull; h ^= h >> 29; return h; }
 LRB_DEVINL int junc_bit(uint64_t jk) { jk *= 0xD6E8FEB86659FD93ull; return (int)(jk >> 58); }
 
-__global__ void merge_cand_kernel(MergeArgs a)
+// (clamped to the host bound: an undersized list is detected and redone by the host, the kernels must only stay in bounds)
+LRB_DEVINL int64_t cand_count(const MergeArgs &a) { return a.n_cand_dev ? min((int64_t)*a.n_cand_dev, a.n_cand) : a.n_cand; }
+
+// One pass over the candidates: flatten (CandSoA), running max of (tid,end) across tiles (look-back, max), locus heads
+// (a candidate that starts beyond every earlier end on its chromosome, App. B.3) and their compaction into locus_start
+// (second look-back chain, sum).  The number of candidates may live on the device (n_cand_dev): the grid is sized by the
+// host's upper bound and surplus tiles only pass the chain on.
+static constexpr int FP_THREADS = 256;
+__global__ void __launch_bounds__(FP_THREADS) fold_prepare_kernel(MergeArgs a)
 {
-    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.n_cand) return;
-    const uint32_t row = a.list.row[c];
-    const int n = (int)a.list.cnt[c];
-    const uint32_t gb = a.rows.ex_beg[row] + a.list.lo[c];
-    const int fs = a.ex.es[gb], le = a.ex.ee[gb + n - 1];
-    const bool piece = a.list.piece[c] >= 0;
-    const int rtid = a.rows.tid[row];
-    a.cd.tid[c] = piece ? 0 : rtid; a.cd.start[c] = piece ? 0 : fs; a.cd.end[c] = piece ? 0 : le;
-    int mono = 2;                                   // bit 1: exon ends never decrease (always true for CIGAR chains)
-    for (int i = 0; i + 1 < n - 1; ++i) if (a.ex.ee[gb + i] > a.ex.ee[gb + i + 1]) { mono = 0; break; }
-    a.cd.rev[c] = (piece ? 0 : a.rows.is_rev[row]) | mono;
-    a.cd.n[c] = n; a.cd.gbeg[c] = gb; a.cd.fs[c] = fs; a.cd.le[c] = le;
-    uint64_t h = 0x243F6A8885A308D3ull ^ (uint64_t)n, sig = 0, j0 = 0;
-    for (int i = 0; i < n - 1; ++i) {
-        const uint32_t e = (uint32_t)a.ex.ee[gb + i], s2 = (uint32_t)a.ex.es[gb + i + 1];
-        h = mixh(h, e); h = mixh(h, s2);
-        const uint64_t jk = ((uint64_t)e << 32) | s2;
-        if (i == 0) j0 = jk;
-        sig |= 1ull << (junc_bit(jk));
+    __shared__ uint64_t s_w[FP_THREADS / 32];
+    __shared__ uint32_t s_scan[33];
+    __shared__ uint32_t s_tile; __shared__ uint64_t s_excl[2];
+    if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const int tile = (int)s_tile, lane = lane_id(), w = warp_id();
+    const int64_t n_cand = cand_count(a);
+    const int64_t c = (int64_t)tile * FP_THREADS + threadIdx.x;
+    uint64_t key_end = 0, key_start = 0;
+    if (c < n_cand) {
+        const uint32_t row = a.list.row[c];
+        const int n = (int)a.list.cnt[c];
+        const uint32_t gb = a.rows.ex_beg[row] + a.list.lo[c];
+        const int fs = a.ex.es[gb], le = a.ex.ee[gb + n - 1];
+        const bool piece = a.list.piece[c] >= 0;
+        const int rtid = a.rows.tid[row];
+        a.cd.tid[c] = piece ? 0 : rtid; a.cd.start[c] = piece ? 0 : fs; a.cd.end[c] = piece ? 0 : le;
+        int mono = 2;                               // bit 1: exon ends never decrease (always true for CIGAR chains)
+        uint64_t h = 0x243F6A8885A308D3ull ^ (uint64_t)n, sig = 0, j0 = 0;
+        int prev_e = 0;
+        for (int i = 0; i < n - 1; ++i) {
+            const int e_i = a.ex.ee[gb + i];
+            const uint32_t e = (uint32_t)e_i, s2 = (uint32_t)a.ex.es[gb + i + 1];
+            if (i > 0 && prev_e > e_i) mono = 0;
+            prev_e = e_i;
+            h = mixh(h, e); h = mixh(h, s2);
+            const uint64_t jk = ((uint64_t)e << 32) | s2;
+            if (i == 0) j0 = jk;
+            sig |= 1ull << (junc_bit(jk));
+        }
+        a.cd.rev[c] = (piece ? 0 : a.rows.is_rev[row]) | mono;
+        a.cd.n[c] = n; a.cd.gbeg[c] = gb; a.cd.fs[c] = fs; a.cd.le[c] = le;
+        a.cd.hash[c] = h; a.cd.j0[c] = j0; a.cd.sig[c] = sig;
+        key_end = ((uint64_t)(uint32_t)(rtid + 1) << 32) | (uint32_t)le;      // real coordinates: locus segmentation
+        key_start = ((uint64_t)(uint32_t)(rtid + 1) << 32) | (uint32_t)fs;
     }
-    a.cd.hash[c] = h; a.cd.j0[c] = j0; a.cd.sig[c] = sig;
-    a.keys[c] = ((uint64_t)(uint32_t)(rtid + 1) << 32) | (uint32_t)le;   // real coordinates: locus segmentation
+    // inclusive max over the block
+    uint64_t inc = key_end;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint64_t t = __shfl_up_sync(FULL, inc, o); if (lane >= o && t > inc) inc = t; }
+    if (lane == 31) s_w[w] = inc;
+    __syncthreads();
+    uint64_t pre = 0, tot = 0;
+    for (int k = 0; k < FP_THREADS / 32; ++k) { const uint64_t v = s_w[k]; if (k < w && v > pre) pre = v; if (v > tot) tot = v; }
+    uint64_t left = __shfl_up_sync(FULL, inc, 1); if (lane == 0) left = 0;
+    const uint64_t tpre = left > pre ? left : pre;                             // exclusive prefix max inside the tile
+    if (w == 0) { const uint64_t e = lookback_exclusive(a.tile_state, tile, tot, OpMax()); if (lane == 0) s_excl[0] = e; }
+    __syncthreads();
+    const uint64_t before = s_excl[0] > tpre ? s_excl[0] : tpre;
+    const uint32_t head = (c < n_cand && (c == 0 || key_start > before)) ? 1u : 0u;
+    if (c < n_cand) a.head[c] = (uint8_t)head;
+    uint32_t htot; const uint32_t hex = block_excl_sum(head, s_scan, &htot);
+    if (w == 0) { const uint64_t e = lookback_exclusive(a.tile_state + a.n_tiles, tile, (uint64_t)htot, OpAdd()); if (lane == 0) s_excl[1] = e; }
+    __syncthreads();
+    if (head) a.locus_start[(uint32_t)s_excl[1] + hex] = (uint32_t)c;
+    if (tile == a.n_tiles - 1 && threadIdx.x == 0) a.totals[0] = s_excl[1] + htot;
 }
-__global__ void merge_heads_kernel(MergeArgs a)
-{
-    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.n_cand) return;
-    const uint32_t row = a.list.row[c];
-    uint64_t k = ((uint64_t)(uint32_t)(a.rows.tid[row] + 1) << 32) | (uint32_t)a.cd.fs[c];
-    a.head[c] = (c == 0 || k > a.keys[c - 1]) ? 1 : 0;   // new locus: start beyond every earlier end on this chromosome
-}
-void launch_merge_prepare(const MergeArgs &a, cudaStream_t st)
+void launch_merge_prepare(MergeArgs a, cudaStream_t st)
 {
     if (a.n_cand <= 0) { cudaMemsetAsync(a.totals, 0, 16, st); return; }
-    unsigned bl = (unsigned)((a.n_cand + 255) / 256);
-    merge_cand_kernel<<<bl, 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
-    launch_scan_max_u64(a.keys, a.n_cand, a.tile_state, a.ticket, st);
-    merge_heads_kernel<<<bl, 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
-    launch_compact_mask(a.head, a.n_cand, nullptr, a.locus_start, nullptr, a.tile_state, a.ticket, a.totals, st);
+    a.n_tiles = (int)((a.n_cand + FP_THREADS - 1) / FP_THREADS);
+    cudaMemsetAsync(a.tile_state, 0, (size_t)a.n_tiles * 16, st); cudaMemsetAsync(a.ticket, 0, 4, st);
+    fold_prepare_kernel<<<(unsigned)a.n_tiles, FP_THREADS, 0, st>>>(a); LRB_COUNT_LAUNCH();
 }
 
 // check_iden (gtf.c:54-92) between candidate t and fold entry E (first start / last end may have been extended)
@@ -678,7 +722,7 @@ __global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uin
     const int sh = (lane_id() / G) * G;
     const CandSoA &cd = a.cd;
     for (int64_t loc = (int64_t)blockIdx.x * GPB + threadIdx.x / G; loc < n_loci; loc += (int64_t)gridDim.x * GPB) {
-        const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : a.n_cand;
+        const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : cand_count(a);
         if ((le - ls < min_m || le - ls > max_m) && !(locus_hard && locus_hard[ls])) continue;   // other loci: flat kernels / another group width
         int cnt = 0;
         for (int64_t c = ls; c < le; ++c) {
@@ -774,7 +818,7 @@ LRB_DEVINL bool partial_static(const DExons &ex, uint32_t l_gbeg, int l_n, bool 
 __global__ void __launch_bounds__(256) fold_rep_kernel(MergeArgs a, uint32_t *__restrict__ rep, uint32_t *__restrict__ lstart, uint8_t *locus_hard)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.n_cand) return;
+    if (c >= cand_count(a)) return;
     const CandSoA &cd = a.cd;
     const bool force = a.up.force_strand != 0;
     const int nc = cd.n[c], rvc = cd.rev[c] & 1;
@@ -800,7 +844,7 @@ __global__ void __launch_bounds__(256) fold_rep_kernel(MergeArgs a, uint32_t *__
 __global__ void __launch_bounds__(256) fold_rel_kernel(MergeArgs a, const uint32_t *__restrict__ rep, const uint32_t *__restrict__ lstart, uint64_t *__restrict__ evmask)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.n_cand) return;
+    if (c >= cand_count(a)) return;
     const CandSoA &cd = a.cd;
     const uint32_t ls = lstart[c];
     if (ls == FF_BIG) return;
@@ -847,7 +891,7 @@ __global__ void __launch_bounds__(128) fold_seq_kernel(MergeArgs a, const uint32
     const int64_t loc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n_loci = (int64_t)a.totals[0];
     if (loc >= n_loci) return;
-    const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : a.n_cand;
+    const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : cand_count(a);
     if (le - ls > FF_MAX || locus_hard[ls]) return;
     const int m = (int)(le - ls);
     const CandSoA &cd = a.cd;
@@ -883,13 +927,32 @@ __global__ void __launch_bounds__(128) fold_seq_kernel(MergeArgs a, const uint32
     }
 }
 
-__global__ void merge_gather_kernel(DMerged work, CandSoA cd, const uint32_t *__restrict__ sel, const uint64_t *__restrict__ n_dev, DMerged out)
+// survivors of the fold, compacted in candidate order with their mutated fields (one pass, look-back sum)
+__global__ void __launch_bounds__(FP_THREADS) fold_finish_kernel(MergeArgs a, const uint8_t *__restrict__ alive)
 {
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= (int64_t)*n_dev) return;
-    uint32_t c = sel[k];
-    out.cand[k] = c; out.cov[k] = work.cov[c]; out.tid[k] = cd.tid[c]; out.start[k] = work.start[c]; out.end[k] = work.end[c];
-    out.fs[k] = work.fs[c]; out.le[k] = work.le[c];
+    __shared__ uint32_t s_scan[33];
+    __shared__ uint32_t s_tile; __shared__ uint64_t s_excl;
+    if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const int tile = (int)s_tile;
+    const int64_t c = (int64_t)tile * FP_THREADS + threadIdx.x;
+    const uint32_t al = (c < cand_count(a) && alive[c]) ? 1u : 0u;
+    uint32_t tot; const uint32_t ex = block_excl_sum(al, s_scan, &tot);
+    if (warp_id() == 0) { const uint64_t e = lookback_exclusive(a.tile_state, tile, (uint64_t)tot, OpAdd()); if (lane_id() == 0) s_excl = e; }
+    __syncthreads();
+    if (al) {
+        const uint32_t k = (uint32_t)s_excl + ex;
+        a.out.cand[k] = (uint32_t)c; a.out.cov[k] = a.work.cov[c]; a.out.tid[k] = a.cd.tid[c]; a.out.start[k] = a.work.start[c]; a.out.end[k] = a.work.end[c];
+        a.out.fs[k] = a.work.fs[c]; a.out.le[k] = a.work.le[c];
+    }
+    if (tile == a.n_tiles - 1 && threadIdx.x == 0) a.totals[1] = s_excl + tot;
+}
+void launch_merge_finish(MergeArgs a, cudaStream_t st)
+{
+    if (a.n_cand <= 0) return;
+    a.n_tiles = (int)((a.n_cand + FP_THREADS - 1) / FP_THREADS);
+    cudaMemsetAsync(a.tile_state, 0, (size_t)a.n_tiles * 8, st); cudaMemsetAsync(a.ticket, 0, 4, st);
+    fold_finish_kernel<<<(unsigned)a.n_tiles, FP_THREADS, 0, st>>>(a, a.dropped); LRB_COUNT_LAUNCH();
 }
 
 void launch_merge_fold(const MergeArgs &a, cudaStream_t st)
@@ -929,7 +992,7 @@ __global__ void merge_class_counts_kernel(MergeArgs a, const uint8_t *__restrict
 {
     int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int k = -1;
-    if (c < a.n_cand && alive[c]) k = a.kls[c];
+    if (c < cand_count(a) && alive[c]) k = a.kls[c];
     for (int q = 0; q < 4; ++q) {
         unsigned m = __ballot_sync(FULL, k == q);
         if (m && lane_id() == 0) atomicAdd(&a.class_alive[q], (uint32_t)__popc(m));
@@ -939,19 +1002,6 @@ void launch_merge_class_counts(const MergeArgs &a, cudaStream_t st)
 {
     if (a.n_cand <= 0) return;
     merge_class_counts_kernel<<<(unsigned)((a.n_cand + 255) / 256), 256, 0, st>>>(a, a.dropped);
-    LRB_COUNT_LAUNCH();
-}
-
-void launch_merge_compact(const MergeArgs &a, int64_t n_loci, cudaStream_t st)
-{
-    (void)n_loci;
-    // a.dropped holds the alive mask; a.locus_cnt is scratch for the compacted candidate ids
-    launch_compact_mask(a.dropped, a.n_cand, nullptr, a.locus_cnt, nullptr, a.tile_state, a.ticket, a.totals + 1, st);
-}
-void launch_merge_gather(const MergeArgs &a, int64_t n_upper, cudaStream_t st)
-{
-    if (n_upper <= 0) return;
-    merge_gather_kernel<<<(unsigned)((n_upper + 255) / 256), 256, 0, st>>>(a.work, a.cd, a.locus_cnt, a.totals + 1, a.out);
     LRB_COUNT_LAUNCH();
 }
 

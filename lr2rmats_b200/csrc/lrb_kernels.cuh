@@ -130,6 +130,7 @@ struct MergeArgs {
     uint32_t *locus_cnt;                            // surviving entries per locus
     uint8_t *dropped;                               // per candidate: absorbed/dropped by the fold
     uint32_t *rep, *lstart; uint64_t *evmask;       // flat fold: class representative, locus head, absorber mask per candidate
+    uint16_t *desc; uint64_t *relsym;               // flat fold: class descriptor per candidate; per representative the related representatives
     uint8_t *hard;                                  // flat fold: per locus head, 1 = leave to merge_fold_kernel
     DMerged out;                                    // compacted result
     uint64_t *tile_state; uint32_t *ticket; uint64_t *totals;  // [0] n_loci, [1] n_out

@@ -500,70 +500,84 @@ void launch_classify(const ClassArgs &a, uint8_t *slow, cudaStream_t st)
 // update_gtf.c:837-913), the known_T and unrecog_T row lists (:941-962), and -- for the summary -- the class of every row
 // (0 known, 1 novel with all junctions reliable, 2 novel with an unreliable junction, 3 unrecognized; :501-528) with the class
 // sizes.  Three running counts ride on two look-back chains; the list sizes stay on the device (totals[0..2]).
-static constexpr int LS_THREADS = 256;
+static constexpr int LS_THREADS = 256, LS_ITEMS = 4;
 __global__ void __launch_bounds__(LS_THREADS) build_lists_kernel(ListArgs a)
 {
     __shared__ uint32_t s_scan[33];
-    __shared__ uint32_t s_tile; __shared__ uint64_t s_excl[2];
+    __shared__ uint32_t s_tile, s_class[4]; __shared__ uint64_t s_excl[2];
     if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
+    if (threadIdx.x < 4) s_class[threadIdx.x] = 0;
     __syncthreads();
     const int tile = (int)s_tile;
-    const int64_t row = (int64_t)tile * LS_THREADS + threadIdx.x;
-    uint32_t nn = 0, kn = 0, un = 0, c = 0;
-    int k = -1;
-    if (row < a.rows.n) {
-        c = a.cls[row]; nn = a.n_novel[row];
-        const bool full = c & LRB_C_FULL, known = c & LRB_C_KNOWN, ks = c & LRB_C_KNOWN_SITE, ur = c & LRB_C_UNRELIABLE;
-        kn = full && known; un = full && !known && !ks;
-        if (a.kls) { k = known ? 0 : (ks ? (ur ? 2 : 1) : 3); a.kls[row] = (uint8_t)k; }
-    }
-    if (a.kls)
-        for (int q = 0; q < 4; ++q) {
-            const unsigned m = __ballot_sync(FULL, k == q);
-            if (m && lane_id() == 0) atomicAdd(&a.class_n[q], (uint32_t)__popc(m));
+    const int64_t base = ((int64_t)tile * LS_THREADS + threadIdx.x) * LS_ITEMS;
+    uint32_t cw[LS_ITEMS], nn[LS_ITEMS], nn_sum = 0, kn_sum = 0, un_sum = 0, flags = 0, ccnt = 0;   // ccnt: four 8-bit class counters
+#pragma unroll
+    for (int i = 0; i < LS_ITEMS; ++i) {
+        cw[i] = 0; nn[i] = 0;
+        if (base + i < a.rows.n) {
+            const uint32_t c = a.cls[base + i];
+            cw[i] = c; nn[i] = a.n_novel[base + i];
+            const bool full = c & LRB_C_FULL, known = c & LRB_C_KNOWN, ks = c & LRB_C_KNOWN_SITE, ur = c & LRB_C_UNRELIABLE;
+            const uint32_t kn = full && known, un = full && !known && !ks;
+            flags |= (kn | (un << 1)) << (2 * i);
+            nn_sum += nn[i]; kn_sum += kn; un_sum += un;
+            if (a.kls) { const int k = known ? 0 : (ks ? (ur ? 2 : 1) : 3); a.kls[base + i] = (uint8_t)k; ccnt += 1u << (8 * k); }
         }
+    }
+    if (a.kls) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ccnt += __shfl_xor_sync(FULL, ccnt, o);     // <= 128 per class and warp: no carry between the bytes
+        if (lane_id() == 0) for (int q = 0; q < 4; ++q) { const uint32_t v = (ccnt >> (8 * q)) & 0xffu; if (v) atomicAdd(&s_class[q], v); }
+    }
     uint32_t nn_tot, kn_tot, un_tot;
-    const uint32_t nn_ex = block_excl_sum(nn, s_scan, &nn_tot), kn_ex = block_excl_sum(kn, s_scan, &kn_tot), un_ex = block_excl_sum(un, s_scan, &un_tot);
+    uint32_t nn_ex = block_excl_sum(nn_sum, s_scan, &nn_tot), kn_ex = block_excl_sum(kn_sum, s_scan, &kn_tot), un_ex = block_excl_sum(un_sum, s_scan, &un_tot);
     if (warp_id() == 0) {
         const uint64_t e0 = lookback_exclusive(a.tile_state, tile, pack_pair(nn_tot, kn_tot), OpAdd());
         const uint64_t e1 = lookback_exclusive(a.tile_state + a.n_tiles, tile, (uint64_t)un_tot, OpAdd());
         if (lane_id() == 0) { s_excl[0] = e0; s_excl[1] = e1; }
     }
     __syncthreads();
+    if (a.kls && threadIdx.x < 4 && s_class[threadIdx.x]) atomicAdd(&a.class_n[threadIdx.x], s_class[threadIdx.x]);
     const uint32_t nn_base = pair_hi(s_excl[0]), kn_base = pair_lo(s_excl[0]), un_base = (uint32_t)s_excl[1];
-    if ((int64_t)(tile + 1) * LS_THREADS >= a.rows.n && threadIdx.x == 0) {
+    if (tile == a.n_tiles - 1 && threadIdx.x == 0) {
         a.totals[0] = (uint64_t)nn_base + nn_tot; a.totals[1] = (uint64_t)kn_base + kn_tot; a.totals[2] = (uint64_t)un_base + un_tot;
     }
-    if (row >= a.rows.n) return;
-    if (kn) a.known[kn_base + kn_ex] = (uint32_t)row;
-    if (un) a.unrecog[un_base + un_ex] = (uint32_t)row;
-    if (!nn) return;
-    uint32_t o = nn_base + nn_ex;
-    if ((int64_t)o + nn > a.novel.cap) return;       // list sized too small: the host sees the total and repeats the pass
-    const int n = (int)a.rows.ex_n[row];
-    if (!((c & LRB_C_SJ_CHECKED) && (c & LRB_C_UNRELIABLE))) {
-        a.novel.row[o] = (uint32_t)row; a.novel.lo[o] = 0; a.novel.cnt[o] = (uint32_t)n; a.novel.piece[o] = -1;
-        return;
-    }
-    const uint8_t *fl = a.ex.flag + a.rows.ex_beg[row];
-    int last = 0, has_novel = 0, has_known = 0, k2 = 0;
-    for (int j = 0; j <= n - 1; ++j) {
-        const bool at_end = j == n - 1;
-        const uint8_t f = fl[j];
-        if (!at_end) { if (f & LRB_F_NOVEL_JUNC) has_novel = 1; else has_known = 1; }
-        if (at_end || (f & LRB_F_UNRELIABLE)) {
-            if (has_novel && has_known && j - last >= 1) {
-                a.novel.row[o] = (uint32_t)row; a.novel.lo[o] = (uint32_t)last; a.novel.cnt[o] = (uint32_t)(j - last + 1); a.novel.piece[o] = k2;
-                ++o; ++k2;
+    uint32_t o = nn_base + nn_ex, ko = kn_base + kn_ex, uo = un_base + un_ex;
+#pragma unroll
+    for (int i = 0; i < LS_ITEMS; ++i) {
+        const int64_t row = base + i;
+        if (row >= a.rows.n) break;
+        if ((flags >> (2 * i)) & 1u) a.known[ko++] = (uint32_t)row;
+        if ((flags >> (2 * i)) & 2u) a.unrecog[uo++] = (uint32_t)row;
+        if (!nn[i]) continue;
+        const uint32_t o0 = o; o += nn[i];
+        if ((int64_t)o0 + nn[i] > a.novel.cap) continue;             // list sized too small: the host sees the total and repeats the pass
+        const uint32_t c = cw[i];
+        const int n = (int)a.rows.ex_n[row];
+        if (!((c & LRB_C_SJ_CHECKED) && (c & LRB_C_UNRELIABLE))) {
+            a.novel.row[o0] = (uint32_t)row; a.novel.lo[o0] = 0; a.novel.cnt[o0] = (uint32_t)n; a.novel.piece[o0] = -1;
+            continue;
+        }
+        const uint8_t *fl = a.ex.flag + a.rows.ex_beg[row];
+        int last = 0, has_novel = 0, has_known = 0, k2 = 0; uint32_t w = o0;
+        for (int j = 0; j <= n - 1; ++j) {
+            const bool at_end = j == n - 1;
+            const uint8_t f = fl[j];
+            if (!at_end) { if (f & LRB_F_NOVEL_JUNC) has_novel = 1; else has_known = 1; }
+            if (at_end || (f & LRB_F_UNRELIABLE)) {
+                if (has_novel && has_known && j - last >= 1) {
+                    a.novel.row[w] = (uint32_t)row; a.novel.lo[w] = (uint32_t)last; a.novel.cnt[w] = (uint32_t)(j - last + 1); a.novel.piece[w] = k2;
+                    ++w; ++k2;
+                }
+                last = j + 1; has_novel = 0; has_known = 0;
             }
-            last = j + 1; has_novel = 0; has_known = 0;
         }
     }
 }
 void launch_build_lists(ListArgs a, cudaStream_t st)
 {
     if (a.rows.n <= 0) { cudaMemsetAsync(a.totals, 0, 24, st); return; }
-    a.n_tiles = (int)((a.rows.n + LS_THREADS - 1) / LS_THREADS);
+    a.n_tiles = (int)((a.rows.n + LS_THREADS * LS_ITEMS - 1) / (LS_THREADS * LS_ITEMS));
     cudaMemsetAsync(a.tile_state, 0, (size_t)a.n_tiles * 16, st); cudaMemsetAsync(a.ticket, 0, 4, st);
     build_lists_kernel<<<(unsigned)a.n_tiles, LS_THREADS, 0, st>>>(a);
     LRB_COUNT_LAUNCH();
@@ -597,7 +611,7 @@ LRB_DEVINL int64_t cand_count(const MergeArgs &a) { return a.n_cand_dev ? min((i
 // (a candidate that starts beyond every earlier end on its chromosome, App. B.3) and their compaction into locus_start
 // (second look-back chain, sum).  The number of candidates may live on the device (n_cand_dev): the grid is sized by the
 // host's upper bound and surplus tiles only pass the chain on.
-static constexpr int FP_THREADS = 256;
+static constexpr int FP_THREADS = 256, FP_ITEMS = 4;
 __global__ void __launch_bounds__(FP_THREADS) fold_prepare_kernel(MergeArgs a)
 {
     __shared__ uint64_t s_w[FP_THREADS / 32];
@@ -607,37 +621,27 @@ __global__ void __launch_bounds__(FP_THREADS) fold_prepare_kernel(MergeArgs a)
     __syncthreads();
     const int tile = (int)s_tile, lane = lane_id(), w = warp_id();
     const int64_t n_cand = cand_count(a);
-    const int64_t c = (int64_t)tile * FP_THREADS + threadIdx.x;
-    uint64_t key_end = 0, key_start = 0;
-    if (c < n_cand) {
-        const uint32_t row = a.list.row[c];
-        const int n = (int)a.list.cnt[c];
-        const uint32_t gb = a.rows.ex_beg[row] + a.list.lo[c];
-        const int fs = a.ex.es[gb], le = a.ex.ee[gb + n - 1];
-        const bool piece = a.list.piece[c] >= 0;
-        const int rtid = a.rows.tid[row];
-        a.cd.tid[c] = piece ? 0 : rtid; a.cd.start[c] = piece ? 0 : fs; a.cd.end[c] = piece ? 0 : le;
-        int mono = 2;                               // bit 1: exon ends never decrease (always true for CIGAR chains)
-        uint64_t h = 0x243F6A8885A308D3ull ^ (uint64_t)n, sig = 0, j0 = 0;
-        int prev_e = 0;
-        for (int i = 0; i < n - 1; ++i) {
-            const int e_i = a.ex.ee[gb + i];
-            const uint32_t e = (uint32_t)e_i, s2 = (uint32_t)a.ex.es[gb + i + 1];
-            if (i > 0 && prev_e > e_i) mono = 0;
-            prev_e = e_i;
-            h = mixh(h, e); h = mixh(h, s2);
-            const uint64_t jk = ((uint64_t)e << 32) | s2;
-            if (i == 0) j0 = jk;
-            sig |= 1ull << (junc_bit(jk));
+    const int64_t c0 = ((int64_t)tile * FP_THREADS + threadIdx.x) * FP_ITEMS;
+    // locus segmentation first (cheap loads, two look-back chains): the per-exon work below then overlaps the chains of later tiles
+    uint64_t key_end[FP_ITEMS], key_start[FP_ITEMS], run = 0;
+    uint32_t row[FP_ITEMS], gb[FP_ITEMS]; int n[FP_ITEMS], fs[FP_ITEMS], le[FP_ITEMS], rtid[FP_ITEMS]; bool piece[FP_ITEMS];
+#pragma unroll
+    for (int i = 0; i < FP_ITEMS; ++i) {
+        key_end[i] = 0; key_start[i] = 0; row[i] = 0; gb[i] = 0; n[i] = 0; fs[i] = 0; le[i] = 0; rtid[i] = 0; piece[i] = false;
+        if (c0 + i < n_cand) {
+            const int64_t c = c0 + i;
+            row[i] = a.list.row[c]; n[i] = (int)a.list.cnt[c];
+            gb[i] = a.rows.ex_beg[row[i]] + a.list.lo[c];
+            fs[i] = a.ex.es[gb[i]]; le[i] = a.ex.ee[gb[i] + n[i] - 1];
+            piece[i] = a.list.piece[c] >= 0;
+            rtid[i] = a.rows.tid[row[i]];
+            key_end[i] = ((uint64_t)(uint32_t)(rtid[i] + 1) << 32) | (uint32_t)le[i];     // real coordinates: locus segmentation
+            key_start[i] = ((uint64_t)(uint32_t)(rtid[i] + 1) << 32) | (uint32_t)fs[i];
         }
-        a.cd.rev[c] = (piece ? 0 : a.rows.is_rev[row]) | mono;
-        a.cd.n[c] = n; a.cd.gbeg[c] = gb; a.cd.fs[c] = fs; a.cd.le[c] = le;
-        a.cd.hash[c] = h; a.cd.j0[c] = j0; a.cd.sig[c] = sig;
-        key_end = ((uint64_t)(uint32_t)(rtid + 1) << 32) | (uint32_t)le;      // real coordinates: locus segmentation
-        key_start = ((uint64_t)(uint32_t)(rtid + 1) << 32) | (uint32_t)fs;
+        run = key_end[i] > run ? key_end[i] : run;
     }
-    // inclusive max over the block
-    uint64_t inc = key_end;
+    // inclusive max over the block (one value per thread: the max of its items)
+    uint64_t inc = run;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint64_t t = __shfl_up_sync(FULL, inc, o); if (lane >= o && t > inc) inc = t; }
     if (lane == 31) s_w[w] = inc;
@@ -645,22 +649,56 @@ __global__ void __launch_bounds__(FP_THREADS) fold_prepare_kernel(MergeArgs a)
     uint64_t pre = 0, tot = 0;
     for (int k = 0; k < FP_THREADS / 32; ++k) { const uint64_t v = s_w[k]; if (k < w && v > pre) pre = v; if (v > tot) tot = v; }
     uint64_t left = __shfl_up_sync(FULL, inc, 1); if (lane == 0) left = 0;
-    const uint64_t tpre = left > pre ? left : pre;                             // exclusive prefix max inside the tile
+    const uint64_t tpre = left > pre ? left : pre;                             // exclusive prefix max of this thread inside the tile
     if (w == 0) { const uint64_t e = lookback_exclusive(a.tile_state, tile, tot, OpMax()); if (lane == 0) s_excl[0] = e; }
     __syncthreads();
-    const uint64_t before = s_excl[0] > tpre ? s_excl[0] : tpre;
-    const uint32_t head = (c < n_cand && (c == 0 || key_start > before)) ? 1u : 0u;
-    if (c < n_cand) a.head[c] = (uint8_t)head;
-    uint32_t htot; const uint32_t hex = block_excl_sum(head, s_scan, &htot);
+    uint64_t before = s_excl[0] > tpre ? s_excl[0] : tpre;
+    uint32_t head = 0, nhead = 0;                                              // bit i: item i starts a locus
+#pragma unroll
+    for (int i = 0; i < FP_ITEMS; ++i) {
+        if (c0 + i < n_cand) {
+            const bool h = (c0 + i == 0) || key_start[i] > before;
+            if (h) { head |= 1u << i; ++nhead; }
+            a.head[c0 + i] = h ? 1 : 0;
+            before = key_end[i] > before ? key_end[i] : before;
+        }
+    }
+    uint32_t htot; const uint32_t hex = block_excl_sum(nhead, s_scan, &htot);
     if (w == 0) { const uint64_t e = lookback_exclusive(a.tile_state + a.n_tiles, tile, (uint64_t)htot, OpAdd()); if (lane == 0) s_excl[1] = e; }
     __syncthreads();
-    if (head) a.locus_start[(uint32_t)s_excl[1] + hex] = (uint32_t)c;
+    uint32_t ho = (uint32_t)s_excl[1] + hex;
+#pragma unroll
+    for (int i = 0; i < FP_ITEMS; ++i) if ((head >> i) & 1u) a.locus_start[ho++] = (uint32_t)(c0 + i);
     if (tile == a.n_tiles - 1 && threadIdx.x == 0) a.totals[0] = s_excl[1] + htot;
+    // flatten the candidates: trans-level fields, chain hash, junction signature
+#pragma unroll
+    for (int i = 0; i < FP_ITEMS; ++i) {
+        if (c0 + i >= n_cand) break;
+        const int64_t c = c0 + i;
+        const int ni = n[i]; const uint32_t g = gb[i];
+        a.cd.tid[c] = piece[i] ? 0 : rtid[i]; a.cd.start[c] = piece[i] ? 0 : fs[i]; a.cd.end[c] = piece[i] ? 0 : le[i];
+        int mono = 2;                               // bit 1: exon ends never decrease (always true for CIGAR chains)
+        uint64_t h = 0x243F6A8885A308D3ull ^ (uint64_t)ni, sig = 0, j0 = 0;
+        int prev_e = 0;
+        for (int j = 0; j < ni - 1; ++j) {
+            const int e_i = a.ex.ee[g + j];
+            const uint32_t e = (uint32_t)e_i, s2 = (uint32_t)a.ex.es[g + j + 1];
+            if (j > 0 && prev_e > e_i) mono = 0;
+            prev_e = e_i;
+            h = mixh(h, e); h = mixh(h, s2);
+            const uint64_t jk = ((uint64_t)e << 32) | s2;
+            if (j == 0) j0 = jk;
+            sig |= 1ull << (junc_bit(jk));
+        }
+        a.cd.rev[c] = (piece[i] ? 0 : a.rows.is_rev[row[i]]) | mono;
+        a.cd.n[c] = ni; a.cd.gbeg[c] = g; a.cd.fs[c] = fs[i]; a.cd.le[c] = le[i];
+        a.cd.hash[c] = h; a.cd.j0[c] = j0; a.cd.sig[c] = sig;
+    }
 }
 void launch_merge_prepare(MergeArgs a, cudaStream_t st)
 {
     if (a.n_cand <= 0) { cudaMemsetAsync(a.totals, 0, 16, st); return; }
-    a.n_tiles = (int)((a.n_cand + FP_THREADS - 1) / FP_THREADS);
+    a.n_tiles = (int)((a.n_cand + FP_THREADS * FP_ITEMS - 1) / (FP_THREADS * FP_ITEMS));
     cudaMemsetAsync(a.tile_state, 0, (size_t)a.n_tiles * 16, st); cudaMemsetAsync(a.ticket, 0, 4, st);
     fold_prepare_kernel<<<(unsigned)a.n_tiles, FP_THREADS, 0, st>>>(a); LRB_COUNT_LAUNCH();
 }
@@ -827,7 +865,7 @@ __global__ void __launch_bounds__(256) fold_rep_kernel(MergeArgs a, uint32_t *__
     int64_t e = c, r = c;
     int steps = 0;
     while (!a.head[e]) {
-        if (++steps >= FF_MAX) { lstart[c] = FF_BIG; rep[c] = (uint32_t)c; return; }      // deeper than the masks reach
+        if (++steps >= FF_MAX) { lstart[c] = FF_BIG; rep[c] = (uint32_t)c; a.desc[c] = 0; return; }   // deeper than the masks reach
         --e;
         if (nc > 1 && cd.n[e] == nc && cd.hash[e] == hc && (!force || (cd.rev[e] & 1) == rvc) && (!a.kls || a.kls[e] == kc)) r = e;
     }
@@ -839,56 +877,90 @@ __global__ void __launch_bounds__(256) fold_rep_kernel(MergeArgs a, uint32_t *__
         if (!same) locus_hard[e] = 1;
     }
     rep[c] = (uint32_t)r; lstart[c] = (uint32_t)e;
+    // class descriptor for the relation passes: [0:5] representative (locus-local), [6] single exon, [7] strand, [8:9] sub-stream
+    a.desc[c] = (uint16_t)((uint32_t)(r - e) | (nc == 1 ? 64u : 0u) | ((uint32_t)rvc << 7) | ((uint32_t)kc << 8));
+    a.relsym[c] = 0;
 }
 
-__global__ void __launch_bounds__(256) fold_rel_kernel(MergeArgs a, const uint32_t *__restrict__ rep, const uint32_t *__restrict__ lstart, uint64_t *__restrict__ evmask)
+// partial-match relation between the class representatives of a locus (threads of non-representatives leave at once):
+// relsym[r] gets a bit for every representative r' (earlier or later) whose class can absorb / be absorbed by r's
+__global__ void __launch_bounds__(256) fold_relrep_kernel(MergeArgs a, const uint32_t *__restrict__ lstart)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= cand_count(a)) return;
-    const CandSoA &cd = a.cd;
     const uint32_t ls = lstart[c];
     if (ls == FF_BIG) return;
+    const uint32_t d = a.desc[c];
+    if ((d & 64u) || (d & 63u) != (uint32_t)c - ls) return;          // single exon, or not the representative of its class
+    const CandSoA &cd = a.cd;
     const bool force = a.up.force_strand != 0;
-    const int nc = cd.n[c], rvc = cd.rev[c];
-    const uint32_t rc = rep[c];
-    uint64_t mask = 0, same = ~0ull;
-    if (a.kls) {                                     // sub-streams (class folds): only the own class is visible
-        const uint8_t kc = a.kls[c];
-        same = 0;
-        for (uint32_t e = ls; e < (uint32_t)c; ++e) if (a.kls[e] == kc) same |= 1ull << (e - ls);
-        a.samemask[c] = same;
-    }
-    if (nc == 1) {
-        for (uint32_t e = ls; e < (uint32_t)c; ++e)
-            if (cd.n[e] == 1 && (!force || ((cd.rev[e] ^ rvc) & 1) == 0)) mask |= 1ull << (e - ls);
-    } else {
-        const uint64_t sig_c = cd.sig[c], j0_c = cd.j0[c];
-        const uint32_t gb_c = cd.gbeg[c];
-        for (uint32_t e = ls; e < (uint32_t)c; ++e) {
-            const int ne = cd.n[e];
-            if (ne <= 1 || !((same >> (e - ls)) & 1ull)) continue;
-            const uint32_t re = rep[e];
-            const uint64_t bit = 1ull << (e - ls);
-            if (re != e) { if ((mask >> (re - ls)) & 1ull) mask |= bit; continue; }       // as its representative (decided before)
-            if (ne == nc) { if (re == rc) mask |= bit; continue; }
-            const int rve = cd.rev[e];
-            if (force && ((rve ^ rvc) & 1)) continue;
-            bool hit;
-            if (nc > ne) {
-                const uint64_t j0_e = cd.j0[e];
-                hit = ((sig_c >> junc_bit(j0_e)) & 1ull) && partial_static(a.ex, gb_c, nc, (rvc & 2) != 0, j0_e, cd.gbeg[e], ne);
-            } else
-                hit = ((cd.sig[e] >> junc_bit(j0_c)) & 1ull) && partial_static(a.ex, cd.gbeg[e], ne, (rve & 2) != 0, j0_c, gb_c, nc);
-            if (hit) mask |= bit;
+    const int nc = cd.n[c];
+    const uint64_t sig_c = cd.sig[c], j0_c = cd.j0[c];
+    const uint32_t gb_c = cd.gbeg[c];
+    const bool mono_c = (cd.rev[c] & 2) != 0;
+    for (uint32_t e = ls; e < (uint32_t)c; ++e) {
+        const uint32_t de = a.desc[e];
+        if ((de & 64u) || (de & 63u) != e - ls || ((de ^ d) & 0x300u)) continue;             // single / not a representative / other sub-stream
+        if (force && ((de ^ d) & 128u)) continue;
+        const int ne = cd.n[e];
+        if (ne == nc) continue;
+        bool hit;
+        if (nc > ne) {
+            const uint64_t j0_e = cd.j0[e];
+            hit = ((sig_c >> junc_bit(j0_e)) & 1ull) && partial_static(a.ex, gb_c, nc, mono_c, j0_e, cd.gbeg[e], ne);
+        } else
+            hit = ((cd.sig[e] >> junc_bit(j0_c)) & 1ull) && partial_static(a.ex, cd.gbeg[e], ne, (cd.rev[e] & 2) != 0, j0_c, gb_c, nc);
+        if (hit) {
+            atomicOr((unsigned long long *)&a.relsym[c], 1ull << (e - ls));
+            atomicOr((unsigned long long *)&a.relsym[e], 1ull << ((uint32_t)c - ls));
         }
     }
-    evmask[c] = mask & same;
 }
 
-__global__ void __launch_bounds__(128) fold_seq_kernel(MergeArgs a, const uint32_t *__restrict__ rep, const uint64_t *__restrict__ evmask,
-                                                       const uint8_t *__restrict__ locus_hard, uint8_t *alive_out)
+// per candidate: the mask (over the <= 63 earlier candidates of its locus) of the entries that could absorb it -- members of its
+// own class (identical chains), members of classes in partial-match relation, other single-exon reads -- and, for class
+// folds, the mask of the earlier candidates of its own sub-stream
+__global__ void __launch_bounds__(256) fold_relasm_kernel(MergeArgs a, const uint32_t *__restrict__ lstart, uint64_t *__restrict__ evmask)
 {
-    const int64_t loc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cand_count(a)) return;
+    const uint32_t ls = lstart[c];
+    if (ls == FF_BIG) return;
+    const uint32_t d = a.desc[c];
+    const bool force = a.up.force_strand != 0;
+    uint64_t mask = 0, same = 0;
+    if (d & 64u) {
+        for (uint32_t e = ls; e < (uint32_t)c; ++e) {
+            const uint32_t de = a.desc[e];
+            const uint64_t bit = 1ull << (e - ls);
+            if (!((de ^ d) & 0x300u)) { same |= bit; if ((de & 64u) && !(force && ((de ^ d) & 128u))) mask |= bit; }
+        }
+    } else {
+        const uint32_t r = d & 63u;
+        const uint64_t rel = a.relsym[ls + r] | (1ull << r);          // classes in partial-match relation, and its own
+        for (uint32_t e = ls; e < (uint32_t)c; ++e) {
+            const uint32_t de = a.desc[e];
+            const uint64_t bit = 1ull << (e - ls);
+            if (!((de ^ d) & 0x300u)) same |= bit;
+            if (!(de & 64u) && ((rel >> (de & 63u)) & 1ull)) mask |= bit;
+        }
+    }
+    evmask[c] = mask;
+    if (a.kls) a.samemask[c] = same;
+}
+
+// thread per locus.  The entries of T (the survivors so far) live in shared-memory slots in insertion order -- the back-scan
+// of merge_trans is a walk down the slots; a locus with more than FS_SLOTS survivors is handed to merge_fold_kernel.
+// A slot keeps exon[0].start / exon[last].end; T.start / T.end equal them except for a split piece that was not extended
+// yet (0 / 0) -- two flag bits.
+static constexpr int FS_THREADS = 64, FS_SLOTS = 32;
+__global__ void __launch_bounds__(FS_THREADS) fold_seq_kernel(MergeArgs a, const uint32_t *__restrict__ rep, const uint64_t *__restrict__ evmask,
+                                                              uint8_t *locus_hard, uint8_t *alive_out)
+{
+    __shared__ int s_tid[FS_SLOTS][FS_THREADS], s_fs[FS_SLOTS][FS_THREADS], s_le[FS_SLOTS][FS_THREADS];
+    __shared__ uint8_t s_cov[FS_SLOTS][FS_THREADS], s_rep[FS_SLOTS][FS_THREADS], s_cand[FS_SLOTS][FS_THREADS], s_flag[FS_SLOTS][FS_THREADS];
+    const int t = threadIdx.x;
+    const int64_t loc = (int64_t)blockIdx.x * FS_THREADS + t;
     const int64_t n_loci = (int64_t)a.totals[0];
     if (loc >= n_loci) return;
     const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : cand_count(a);
@@ -896,38 +968,60 @@ __global__ void __launch_bounds__(128) fold_seq_kernel(MergeArgs a, const uint32
     const int m = (int)(le - ls);
     const CandSoA &cd = a.cd;
     const int end_dis = a.up.end_dis;
+    const bool end_free = end_dis == 0x7fffffff;                      // the default: check_iden's end tests always pass
     uint64_t alive = 0;
+    int cnt = 0;
+    // candidate k+1 is loaded while candidate k is folded
+    int t_tid = cd.tid[ls], t_start = cd.start[ls], t_end = cd.end[ls], nc = cd.n[ls], fs = cd.fs[ls], lend = cd.le[ls];
+    uint32_t rc = rep[ls]; uint64_t ev = evmask[ls], same = a.kls ? a.samemask[ls] : ~0ull;
     for (int k = 0; k < m; ++k) {
         const int64_t c = ls + k;
-        const int t_tid = cd.tid[c], t_start = cd.start[c], nc = cd.n[c], fs = cd.fs[c], lend = cd.le[c];
-        const uint64_t ev = evmask[c];
-        uint64_t scan = a.kls ? (alive & a.samemask[c]) : alive;
-        int kind = 0; int64_t hit = 0;                                // kind: 0 append, 1 merge (identical), 2 drop (partial)
-        while (scan & ev) {                                           // no candidate event left below: append whatever the stops say
-            const int b = 63 - __clzll((long long)scan);
-            const int64_t e = ls + b;
-            if (t_tid > cd.tid[e] || t_start > a.work.end[e]) break;                         // update_gtf.c:148
-            if ((ev >> b) & 1ull) {
-                const int efs = a.work.fs[e], ele = a.work.le[e];
-                bool ok = iabs_dev(fs - efs) <= end_dis && iabs_dev(lend - ele) <= end_dis;  // merge_trans2 :124-125 / check_iden's end tests
-                if (nc == 1) ok = ok && ovlp_frac(fs, lend, efs, ele) >= a.up.single_exon_ovlp_frac;
-                if (ok) { hit = e; kind = (nc == 1 || rep[e] == rep[c]) ? 1 : 2; break; }
+        const int c_tid = t_tid, c_start = t_start, c_end = t_end, c_n = nc, c_fs = fs, c_le = lend;
+        const uint32_t c_rep = rc - (uint32_t)ls; const uint64_t c_ev = ev, c_same = same;
+        if (k + 1 < m) {
+            t_tid = cd.tid[c + 1]; t_start = cd.start[c + 1]; t_end = cd.end[c + 1]; nc = cd.n[c + 1]; fs = cd.fs[c + 1]; lend = cd.le[c + 1];
+            rc = rep[c + 1]; ev = evmask[c + 1]; if (a.kls) same = a.samemask[c + 1];
+        }
+        int kind = 0, hit = 0;                                        // kind: 0 append, 1 merge (identical), 2 drop (partial)
+        for (int sl = cnt - 1; sl >= 0; --sl) {
+            const int b = s_cand[sl][t];
+            if (!(c_ev & alive & ((2ull << b) - 1ull))) break;        // no candidate event at or below this entry: append whatever the stops say
+            if (!((c_same >> b) & 1ull)) continue;                    // another sub-stream: invisible
+            const int efs = s_fs[sl][t], ele = s_le[sl][t];
+            const int e_end = (s_flag[sl][t] & 2) ? 0 : ele;          // T.end
+            if (c_tid > s_tid[sl][t] || c_start > e_end) break;       // update_gtf.c:148
+            if ((c_ev >> b) & 1ull) {
+                bool ok = true;
+                if (!end_free || c_n == 1) {
+                    ok = iabs_dev(c_fs - efs) <= end_dis && iabs_dev(c_le - ele) <= end_dis; // merge_trans2 :124-125 / check_iden's end tests
+                    if (c_n == 1) ok = ok && ovlp_frac(c_fs, c_le, efs, ele) >= a.up.single_exon_ovlp_frac;
+                }
+                if (ok) { hit = sl; kind = (c_n == 1 || s_rep[sl][t] == (uint8_t)c_rep) ? 1 : 2; break; }
             }
-            scan &= ~(1ull << b);
         }
         if (kind == 1) {
-            a.work.cov[hit] += 1;
-            if (fs < a.work.fs[hit]) { a.work.fs[hit] = fs; a.work.start[hit] = fs; }
-            if (lend > a.work.le[hit]) { a.work.le[hit] = lend; a.work.end[hit] = lend; }
+            s_cov[hit][t] += 1;                                       // <= 64 candidates per locus: fits a byte
+            if (c_fs < s_fs[hit][t]) { s_fs[hit][t] = c_fs; s_flag[hit][t] &= ~1; }
+            if (c_le > s_le[hit][t]) { s_le[hit][t] = c_le; s_flag[hit][t] &= ~2; }
         } else if (kind == 0) {
+            if (cnt == FS_SLOTS) { locus_hard[ls] = 1; return; }      // too many survivors for the slots: merge_fold_kernel redoes the locus
             alive |= 1ull << k;
-            a.work.cov[c] = 1; a.work.start[c] = t_start; a.work.end[c] = cd.end[c]; a.work.fs[c] = fs; a.work.le[c] = lend;
+            s_tid[cnt][t] = c_tid; s_fs[cnt][t] = c_fs; s_le[cnt][t] = c_le; s_cov[cnt][t] = 1;
+            s_rep[cnt][t] = (uint8_t)c_rep; s_cand[cnt][t] = (uint8_t)k;
+            s_flag[cnt][t] = (uint8_t)((c_start != c_fs ? 1 : 0) | (c_end != c_le ? 2 : 0));   // only an unextended piece (start = end = 0)
+            ++cnt;
         }
         alive_out[c] = kind == 0 ? 1 : 0;
+    }
+    for (int sl = 0; sl < cnt; ++sl) {
+        const int64_t c = ls + s_cand[sl][t];
+        const int f = s_flag[sl][t], efs = s_fs[sl][t], ele = s_le[sl][t];
+        a.work.cov[c] = s_cov[sl][t]; a.work.start[c] = (f & 1) ? cd.start[c] : efs; a.work.end[c] = (f & 2) ? cd.end[c] : ele; a.work.fs[c] = efs; a.work.le[c] = ele;
     }
 }
 
 // survivors of the fold, compacted in candidate order with their mutated fields (one pass, look-back sum)
+static constexpr int FF_ITEMS = 8;
 __global__ void __launch_bounds__(FP_THREADS) fold_finish_kernel(MergeArgs a, const uint8_t *__restrict__ alive)
 {
     __shared__ uint32_t s_scan[33];
@@ -935,22 +1029,28 @@ __global__ void __launch_bounds__(FP_THREADS) fold_finish_kernel(MergeArgs a, co
     if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
     __syncthreads();
     const int tile = (int)s_tile;
-    const int64_t c = (int64_t)tile * FP_THREADS + threadIdx.x;
-    const uint32_t al = (c < cand_count(a) && alive[c]) ? 1u : 0u;
-    uint32_t tot; const uint32_t ex = block_excl_sum(al, s_scan, &tot);
+    const int64_t c0 = ((int64_t)tile * FP_THREADS + threadIdx.x) * FF_ITEMS, n = cand_count(a);
+    uint32_t al = 0, cnt = 0;
+#pragma unroll
+    for (int i = 0; i < FF_ITEMS; ++i) if (c0 + i < n && alive[c0 + i]) { al |= 1u << i; ++cnt; }
+    uint32_t tot; const uint32_t ex = block_excl_sum(cnt, s_scan, &tot);
     if (warp_id() == 0) { const uint64_t e = lookback_exclusive(a.tile_state, tile, (uint64_t)tot, OpAdd()); if (lane_id() == 0) s_excl = e; }
     __syncthreads();
-    if (al) {
-        const uint32_t k = (uint32_t)s_excl + ex;
-        a.out.cand[k] = (uint32_t)c; a.out.cov[k] = a.work.cov[c]; a.out.tid[k] = a.cd.tid[c]; a.out.start[k] = a.work.start[c]; a.out.end[k] = a.work.end[c];
-        a.out.fs[k] = a.work.fs[c]; a.out.le[k] = a.work.le[c];
-    }
+    uint32_t k = (uint32_t)s_excl + ex;
+#pragma unroll
+    for (int i = 0; i < FF_ITEMS; ++i)
+        if ((al >> i) & 1u) {
+            const int64_t c = c0 + i;
+            a.out.cand[k] = (uint32_t)c; a.out.cov[k] = a.work.cov[c]; a.out.tid[k] = a.cd.tid[c]; a.out.start[k] = a.work.start[c]; a.out.end[k] = a.work.end[c];
+            a.out.fs[k] = a.work.fs[c]; a.out.le[k] = a.work.le[c];
+            ++k;
+        }
     if (tile == a.n_tiles - 1 && threadIdx.x == 0) a.totals[1] = s_excl + tot;
 }
 void launch_merge_finish(MergeArgs a, cudaStream_t st)
 {
     if (a.n_cand <= 0) return;
-    a.n_tiles = (int)((a.n_cand + FP_THREADS - 1) / FP_THREADS);
+    a.n_tiles = (int)((a.n_cand + FP_THREADS * FF_ITEMS - 1) / (FP_THREADS * FF_ITEMS));
     cudaMemsetAsync(a.tile_state, 0, (size_t)a.n_tiles * 8, st); cudaMemsetAsync(a.ticket, 0, 4, st);
     fold_finish_kernel<<<(unsigned)a.n_tiles, FP_THREADS, 0, st>>>(a, a.dropped); LRB_COUNT_LAUNCH();
 }
@@ -966,8 +1066,9 @@ void launch_merge_fold(const MergeArgs &a, cudaStream_t st)
         cudaMemsetAsync(a.hard, 0, (size_t)a.n_cand, st);
         const unsigned bl = (unsigned)((a.n_cand + 255) / 256);
         fold_rep_kernel<<<bl, 256, 0, st>>>(a, a.rep, a.lstart, a.hard); LRB_COUNT_LAUNCH();
-        fold_rel_kernel<<<bl, 256, 0, st>>>(a, a.rep, a.lstart, a.evmask); LRB_COUNT_LAUNCH();
-        fold_seq_kernel<<<(unsigned)((a.n_cand + 127) / 128), 128, 0, st>>>(a, a.rep, a.evmask, a.hard, a.dropped); LRB_COUNT_LAUNCH();
+        fold_relrep_kernel<<<bl, 256, 0, st>>>(a, a.lstart); LRB_COUNT_LAUNCH();
+        fold_relasm_kernel<<<bl, 256, 0, st>>>(a, a.lstart, a.evmask); LRB_COUNT_LAUNCH();
+        fold_seq_kernel<<<(unsigned)((a.n_cand + FS_THREADS - 1) / FS_THREADS), FS_THREADS, 0, st>>>(a, a.rep, a.evmask, a.hard, a.dropped); LRB_COUNT_LAUNCH();
         // loci beyond the masks, and the (hash-collision) hard ones
         int64_t bl2 = (a.n_cand / (FF_MAX + 1) + 1 + 3) / 4 + 8; if (bl2 > 148 * 8) bl2 = 148 * 8;
         merge_fold_kernel<32><<<(unsigned)bl2, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, a.hard, FF_MAX + 1, 0x7fffffff);
@@ -988,20 +1089,25 @@ void launch_merge_fold(const MergeArgs &a, cudaStream_t st)
     }
 }
 
-__global__ void merge_class_counts_kernel(MergeArgs a, const uint8_t *__restrict__ alive)
+__global__ void __launch_bounds__(256) merge_class_counts_kernel(MergeArgs a, const uint8_t *__restrict__ alive)
 {
-    int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int k = -1;
-    if (c < cand_count(a) && alive[c]) k = a.kls[c];
-    for (int q = 0; q < 4; ++q) {
-        unsigned m = __ballot_sync(FULL, k == q);
-        if (m && lane_id() == 0) atomicAdd(&a.class_alive[q], (uint32_t)__popc(m));
-    }
+    __shared__ uint32_t s_class[4];
+    if (threadIdx.x < 4) s_class[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t n = cand_count(a);
+    uint32_t ccnt = 0;                                               // four 8-bit counters
+    for (int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4, i = 0; i < 4 && c + i < n; ++i)
+        if (alive[c + i]) ccnt += 1u << (8 * a.kls[c + i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ccnt += __shfl_xor_sync(FULL, ccnt, o);         // <= 128 per class and warp
+    if (lane_id() == 0) for (int q = 0; q < 4; ++q) { const uint32_t v = (ccnt >> (8 * q)) & 0xffu; if (v) atomicAdd(&s_class[q], v); }
+    __syncthreads();
+    if (threadIdx.x < 4 && s_class[threadIdx.x]) atomicAdd(&a.class_alive[threadIdx.x], s_class[threadIdx.x]);
 }
 void launch_merge_class_counts(const MergeArgs &a, cudaStream_t st)
 {
     if (a.n_cand <= 0) return;
-    merge_class_counts_kernel<<<(unsigned)((a.n_cand + 255) / 256), 256, 0, st>>>(a, a.dropped);
+    merge_class_counts_kernel<<<(unsigned)((a.n_cand + 1023) / 1024), 256, 0, st>>>(a, a.dropped);
     LRB_COUNT_LAUNCH();
 }
 

@@ -3,6 +3,7 @@
 // small lookup indices of the replicated tables (prefix-max keys, the remove-GTF index) at upload time.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -55,6 +56,9 @@ struct MergeBufs {                                  // scratch + output of one m
 
 struct lrb_ctx {
     int device = 0; cudaStream_t st = nullptr; std::string err;
+    // side stream: work of a stage that is independent of its main chain (the class folds of the summary) runs here,
+    // forked / joined with events, on its own look-back state
+    cudaStream_t st2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool side_stream = true;
     // tables
     DAnno anno; DSj sj; DRmIndex rm;
     Buf a_tid, a_start, a_end, a_gene, a_rev, a_off, a_es, a_ee, a_pmax, a_mono;
@@ -85,7 +89,7 @@ struct lrb_ctx {
     // unique
     Buf q_shared; int64_t n_shared = 0;
     // look-back state, small device scalars and their pinned mirror
-    Buf tile_state, scalars; PBuf h_scalars;
+    Buf tile_state, tile_state2, scalars; PBuf h_scalars;
     // pinned result buffers
     PBuf p[48];
     Buf tb_name, tb_piece, tb_ttid, tb_tstart, tb_tend, tb_trev, tb_etid, tb_erev, tb_cov, tb_ref, tb_cnt, tb_off, tb_es, tb_ee;
@@ -110,6 +114,7 @@ enum { T_NOVEL = 8, T_KNOWN = 9, T_UNREC = 10, T_LOCI = 11, T_UPD = 12, T_LOCI2 
 uint64_t *d_totals(lrb_ctx *c) { return c->scalars.as<uint64_t>(); }
 uint32_t *d_ticket(lrb_ctx *c) { return (uint32_t *)(c->scalars.as<uint64_t>() + T_SLOTS); }
 uint32_t *d_err(lrb_ctx *c) { return d_ticket(c) + 1; }
+uint32_t *d_ticket2(lrb_ctx *c) { return d_ticket(c) + 2; }          // ticket of the side stream
 
 int read_totals(lrb_ctx *c, uint64_t *out, int n)
 {
@@ -159,7 +164,9 @@ int setup_exons(lrb_ctx *c, int64_t cap)
 }
 
 // the scan stage in one of its three modes; on return rows.n / ex.n are known on the host
-int run_scan(lrb_ctx *c, int mode, const lrb_filter_params *fp, const lrb_exon_params *ep, const uint8_t *sel_mask)
+// by_record (fused pipeline): rows are written at their record index and the totals stay on the device (slots 0/1) -- the
+// caller reads them together with its own counts and repeats the pass if the exon pool was too small
+int run_scan(lrb_ctx *c, int mode, const lrb_filter_params *fp, const lrb_exon_params *ep, const uint8_t *sel_mask, bool by_record = false)
 {
     const int64_t n = c->b.n;
     int rc;
@@ -182,7 +189,7 @@ int run_scan(lrb_ctx *c, int mode, const lrb_filter_params *fp, const lrb_exon_p
         a.b = c->b; if (fp) a.fp = *fp; if (ep) a.ep = *ep; a.rm = c->rm; a.mode = mode; a.sel_mask = sel_mask;
         a.pass = c->f_pass.as<uint8_t>(); a.score = c->f_score.as<int32_t>(); a.intron_n = c->f_intron.as<int32_t>();
         a.rows = c->rows; a.ex = c->ex; a.tile_state = c->tile_state.as<uint64_t>(); a.ticket = d_ticket(c); a.totals = d_totals(c);
-        a.reads_per_tile = R; a.stage_words = stage_words;
+        a.reads_per_tile = R; a.stage_words = stage_words; a.rows_by_record = by_record ? 1 : 0;
         CK(cudaMemsetAsync(c->tile_state.p, 0, (size_t)n_tiles * 8, c->st));
         CK(cudaMemsetAsync(c->scalars.p, 0, 8 * 8, c->st)); CK(cudaMemsetAsync(d_ticket(c), 0, 4, c->st));
         size_t smem = (size_t)stage_words * 4 + (size_t)3072 * 8;
@@ -190,6 +197,7 @@ int run_scan(lrb_ctx *c, int mode, const lrb_filter_params *fp, const lrb_exon_p
         launch_cigar_scan(a, n_tiles, warp_mode, smem, c->st);
         tick(c, 9);
         CK(cudaGetLastError());
+        if (by_record) return LRB_OK;
         uint64_t t[2];
         if ((rc = read_totals(c, t, 2)) != LRB_OK) return rc;
         c->rows.n = (int64_t)t[0]; c->ex.n = (int64_t)t[1];
@@ -242,13 +250,15 @@ DMerged merged_view(Buf &cand, Buf &cov, Buf &tid, Buf &st, Buf &en, Buf &fs, Bu
 // candidate) folded in one pass and only the survivors per sub-stream are counted (class_alive); else the survivors are
 // compacted into m.o_*.  totals[0] <- number of loci, totals[1] <- number of survivors (device).
 int run_merge_async(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_cand, const uint64_t *n_cand_dev, const lrb_update_params &up,
-                    uint64_t *totals, const uint8_t *kls = nullptr, uint32_t *class_alive = nullptr, bool time_fold = false)
+                    uint64_t *totals, const uint8_t *kls = nullptr, uint32_t *class_alive = nullptr, bool time_fold = false, bool side = false)
 {
     int rc;
+    cudaStream_t st = side ? c->st2 : c->st;
     if ((rc = setup_merge(c, m, n_cand)) != LRB_OK) return rc;
-    if ((rc = ensure_tiles(c, n_cand)) != LRB_OK) return rc;
+    if (side) { NEED(c->tile_state2, (size_t)(n_cand / 8 + 1024) * 8); }
+    else if ((rc = ensure_tiles(c, n_cand)) != LRB_OK) return rc;
     m.n_out = 0; m.n_loci = 0;
-    CK(cudaMemsetAsync(totals, 0, 16, c->st));
+    CK(cudaMemsetAsync(totals, 0, 16, st));
     if (n_cand == 0) return LRB_OK;
     MergeArgs a{};
     a.rows = *c->cur; a.ex = c->ex; a.up = up; a.list = list; a.n_cand = n_cand; a.n_cand_dev = n_cand_dev;
@@ -260,14 +270,14 @@ int run_merge_async(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_
     a.cd.tid = m.c_tid.as<int32_t>(); a.cd.start = m.c_start.as<int32_t>(); a.cd.end = m.c_end.as<int32_t>(); a.cd.rev = m.c_rev.as<int32_t>();
     a.cd.n = m.c_n.as<int32_t>(); a.cd.fs = m.c_fs.as<int32_t>(); a.cd.le = m.c_le.as<int32_t>(); a.cd.gbeg = m.c_gbeg.as<uint32_t>();
     a.cd.hash = m.c_hash.as<uint64_t>(); a.cd.j0 = m.c_j0.as<uint64_t>(); a.cd.sig = m.c_sig.as<uint64_t>();
-    a.tile_state = c->tile_state.as<uint64_t>(); a.ticket = d_ticket(c); a.totals = totals;
+    a.tile_state = side ? c->tile_state2.as<uint64_t>() : c->tile_state.as<uint64_t>(); a.ticket = side ? d_ticket2(c) : d_ticket(c); a.totals = totals;
     a.kls = kls; a.class_alive = class_alive;
-    launch_merge_prepare(a, c->st);
+    launch_merge_prepare(a, st);
     if (time_fold) tick(c, 10);
-    launch_merge_fold(a, c->st);                     // locus count is consumed on the device: no host round trip
+    launch_merge_fold(a, st);                        // locus count is consumed on the device: no host round trip
     if (time_fold) tick(c, 11);
-    if (kls) launch_merge_class_counts(a, c->st);
-    else launch_merge_finish(a, c->st);
+    if (kls) launch_merge_class_counts(a, st);
+    else launch_merge_finish(a, st);
     CK(cudaGetLastError());
     return LRB_OK;
 }
@@ -311,6 +321,9 @@ int lrb_ctx_create(int device, lrb_ctx **out)
     lrb_ctx *c = new lrb_ctx();
     c->device = device;
     if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return LRB_E_CUDA; }
+    if (cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(c->st); delete c; return LRB_E_CUDA; }
+    cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    { const char *e = getenv("LRB_SIDE_STREAM"); if (e) c->side_stream = atoi(e) != 0; }
     if (!c->scalars.ensure(512) || !c->h_scalars.ensure(512)) { delete c; return LRB_E_NOMEM; }
     cudaMemsetAsync(c->scalars.p, 0, 512, c->st);
     for (int i = 0; i < 12; ++i) cudaEventCreate(&c->ev[i]);
@@ -325,7 +338,7 @@ void lrb_ctx_destroy(lrb_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->st);
+    cudaStreamSynchronize(c->st); cudaStreamSynchronize(c->st2);
     Buf *bufs[] = {&c->a_tid, &c->a_start, &c->a_end, &c->a_gene, &c->a_rev, &c->a_off, &c->a_es, &c->a_ee, &c->a_pmax, &c->a_mono, &c->s_tid, &c->s_don, &c->s_acc,
                    &c->s_u, &c->s_m, &c->s_pmax, &c->s_dkey, &c->r_gtid, &c->r_goff, &c->r_start, &c->r_pmax, &c->b_tid, &c->b_pos, &c->b_lq, &c->b_nm,
                    &c->b_flag, &c->b_xs, &c->b_qh, &c->b_coff, &c->b_cig, &c->f_pass, &c->f_score, &c->f_intron, &c->f_keep_row_mask, &c->f_keep_rec_mask,
@@ -334,7 +347,7 @@ void lrb_ctx_destroy(lrb_ctx *c)
                    &c->u_mu, &c->u_ck, &c->u_cr, &c->u_cu, &c->u_cn, &c->u_known, &c->u_unrecog, &c->u_sub, &c->n_row, &c->n_lo, &c->n_cnt, &c->n_piece,
                    &c->t_row, &c->t_lo, &c->t_cnt, &c->t_piece, &c->h_khi, &c->h_klo, &c->h_min, &c->h_score, &c->y_barcnt, &c->y_barseg, &c->y_genebar,
                    &c->y_bedcnt, &c->y_bedoff, &c->y_counts, &c->y_nelem, &c->bd_tid, &c->bd_s, &c->bd_e, &c->bd_sc, &c->bd_ty, &c->bd_rv, &c->q_shared, &c->tb_name, &c->tb_piece, &c->tb_ttid, &c->tb_tstart, &c->tb_tend, &c->tb_trev, &c->tb_etid, &c->tb_erev, &c->tb_cov, &c->tb_ref, &c->tb_cnt, &c->tb_off, &c->tb_es, &c->tb_ee,
-                   &c->tile_state, &c->scalars};
+                   &c->tile_state, &c->tile_state2, &c->scalars};
     for (Buf *b : bufs) b->release();
     for (MergeBufs *m : {&c->mg, &c->mg2}) {
         Buf *w[] = {&m->keys, &m->head, &m->locus_start, &m->locus_cnt, &m->dropped, &m->rep, &m->lstart, &m->evmask, &m->samemask, &m->hard, &m->desc, &m->relsym, &m->w_cand, &m->w_cov, &m->w_tid, &m->w_start, &m->w_end, &m->w_fs,
@@ -346,7 +359,8 @@ void lrb_ctx_destroy(lrb_ctx *c)
     c->h_scalars.release();
     for (int i = 0; i < 12; ++i) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(c->marks[i]);
-    cudaStreamDestroy(c->st);
+    cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
+    cudaStreamDestroy(c->st2); cudaStreamDestroy(c->st);
     delete c;
 }
 
@@ -555,11 +569,30 @@ int lrb_pipeline_run(lrb_ctx *c, const lrb_filter_params *fp, const lrb_exon_par
     if (!c->have_batch) return fail(c, LRB_E_ARG, "lrb_pipeline_run: no batch uploaded");
     CK(cudaSetDevice(c->device));
     int64_t l0 = total_launches(); tick(c, 0);
-    int rc = run_scan(c, 2, fp, ep, nullptr); if (rc) return rc;
-    if ((rc = run_select(c, fp))) return rc;
-    if ((rc = setup_rows(c, c->rows2, c->q_read, c->q_tid, c->q_rs, c->q_re, c->q_rev, c->q_beg, c->q_n, c->n_keep))) return rc;
-    launch_gather_rows(c->rows, c->f_keep_rows.as<uint32_t>(), c->n_keep, c->rows2, c->st);
-    CK(cudaGetLastError());
+    const int64_t n = c->b.n;
+    int rc;
+    NEED(c->f_keep_rec_mask, (size_t)std::max<int64_t>(n, 1)); NEED(c->f_keep_idx, (size_t)std::max<int64_t>(n, 1) * 4);
+    if ((rc = setup_rows(c, c->rows2, c->q_read, c->q_tid, c->q_rs, c->q_re, c->q_rev, c->q_beg, c->q_n, n))) return rc;
+    c->rows.n = 0; c->ex.n = 0; c->n_pass = c->n_keep = 0;
+    for (int attempt = 0; n > 0; ++attempt) {
+        // scan (rows at their record index) -> run selection on the record stream -> compaction + row gather: one
+        // round trip for (passing, exons, kept)
+        if ((rc = run_scan(c, 2, fp, ep, nullptr, true))) return rc;
+        CK(cudaMemsetAsync(c->f_keep_rec_mask.p, 0, (size_t)n, c->st));
+        launch_select_records(c->b, c->f_pass.as<uint8_t>(), c->f_score.as<int32_t>(), c->f_intron.as<int32_t>(), *fp, c->f_keep_rec_mask.as<uint8_t>(), c->st);
+        launch_compact_gather(c->f_keep_rec_mask.as<uint8_t>(), n, c->rows, c->rows2, c->f_keep_idx.as<uint32_t>(), c->tile_state.as<uint64_t>(),
+                              d_ticket(c), d_totals(c) + 2, c->st);
+        CK(cudaGetLastError());
+        uint64_t t[3];
+        if ((rc = read_totals(c, t, 3))) return rc;
+        c->n_pass = (int64_t)t[0]; c->ex.n = (int64_t)t[1]; c->n_keep = (int64_t)t[2];
+        if (c->timing) cudaEventElapsedTime(&c->ms[LRB_T_K_SCAN], c->ev[8], c->ev[9]);
+        if (c->ex.n <= c->ex.cap) break;
+        if (attempt == 1) return fail(c, LRB_E_NOMEM, "exon pool still too small after regrow");
+        if ((rc = setup_exons(c, c->ex.n + 16))) return rc;     // exact size known now: walk again
+    }
+    if (n == 0 && (rc = setup_exons(c, 16))) return rc;
+    c->rows.n = n;                                               // record-indexed: only the passing records' rows are valid
     c->rows2.n = c->n_keep;
     tick(c, 1);
     c->cur = &c->rows2; c->rows_compact = false; c->have_filter = true; c->have_exons = true; c->have_update = c->have_unique = false;
@@ -605,7 +638,7 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
     memset(c->summary, 0, sizeof c->summary); c->n_bed = 0; c->last_up = *up; c->n_known = c->n_unrecog = 0;
     NEED(c->u_cls, nn * 4); NEED(c->u_ref, nn * 4); NEED(c->u_nnovel, nn * 4);
     NEED(c->u_mk, nn); NEED(c->u_known, nn * 4); NEED(c->u_unrecog, nn * 4); NEED(c->u_ck, nn);
-    NEED(c->y_counts, 64); NEED(c->y_nelem, 8);
+    NEED(c->y_counts, 64); NEED(c->y_nelem, 64);       // y_nelem: element count, then (at +16) the six tickets of sum_scans_kernel
     if ((rc = ensure_tiles(c, std::max<int64_t>(n, c->ex.n)))) return rc;
     CK(cudaMemsetAsync(d_err(c), 0, 4, c->st));
     tick(c, 0);
@@ -639,15 +672,22 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
         launch_build_lists(la, c->st);
         CK(cudaGetLastError());
         if (attempt == 0) tick(c, 2);
+        if (up->want_summary) {
+            // class counts + uniq_* folds over bam_T (update_gtf.c:501-528): the four classes partition the rows; they are
+            // folded in ONE pass over all rows, each candidate seeing only the entries of its own class.  Independent of the
+            // updated_T fold and of the sets: forked onto the side stream, joined in front of the round trip below.
+            const bool side = c->side_stream;
+            cudaStream_t s2 = side ? c->st2 : c->st;
+            if ((rc = setup_list(c, c->tmp_list, c->t_row, c->t_lo, c->t_cnt, c->t_piece, n))) return rc;
+            if (side) { CK(cudaEventRecord(c->ev_fork, c->st)); CK(cudaStreamWaitEvent(c->st2, c->ev_fork, 0)); }
+            launch_rows_as_list(rows, nullptr, n, c->tmp_list, s2);
+            if ((rc = run_merge_async(c, c->mg2, c->tmp_list, n, nullptr, *up, T + T_LOCI2, c->u_ck.as<uint8_t>(), c->y_counts.as<uint32_t>() + 8, false, side))) return rc;
+            if (side) CK(cudaEventRecord(c->ev_join, c->st2));
+        }
         // updated_T = merge fold over novel_T (update_gtf.c:949,956)
         if ((rc = run_merge_async(c, c->mg, c->novel, cap, T + T_NOVEL, *up, T + T_LOCI, nullptr, nullptr, true))) return rc;
         if (attempt == 0) tick(c, 3);
         if (up->want_summary) {
-            // class counts + uniq_* folds over bam_T (update_gtf.c:501-528): the four classes partition the rows; they are
-            // folded in ONE pass over all rows, each candidate seeing only the entries of its own class
-            if ((rc = setup_list(c, c->tmp_list, c->t_row, c->t_lo, c->t_cnt, c->t_piece, n))) return rc;
-            launch_rows_as_list(rows, nullptr, n, c->tmp_list, c->st);
-            if ((rc = run_merge_async(c, c->mg2, c->tmp_list, n, nullptr, *up, T + T_LOCI2, c->u_ck.as<uint8_t>(), c->y_counts.as<uint32_t>() + 8))) return rc;
             // sets over updated_T: element count (sizes the hash table)
             const size_t capn = (size_t)std::max<int64_t>(cap, 1);
             NEED(c->y_barcnt, capn * 16); NEED(c->y_barseg, capn * 16); NEED(c->y_genebar, capn * 8); NEED(c->y_bedcnt, capn * 4); NEED(c->y_bedoff, capn * 4);
@@ -661,6 +701,7 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
             CK(cudaGetLastError());
         }
         // ---- the one round trip: totals, error flags, class counters, element count
+        if (up->want_summary && c->side_stream) CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
         uint8_t *hp = (uint8_t *)c->h_scalars.p;
         CK(cudaMemcpyAsync(hp, c->scalars.p, T_SLOTS * 8 + 8, cudaMemcpyDeviceToHost, c->st));
         CK(cudaMemcpyAsync(hp + 320, c->y_counts.p, 64, cudaMemcpyDeviceToHost, c->st));
@@ -692,17 +733,16 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
         s[LRB_S_NOVEL_BAM] = s[LRB_S_NOVEL_RELIABLE] + s[LRB_S_NOVEL_UNRELIABLE];
         sa.n_upd = nu; sa.n_upd_dev = nullptr; sa.upd.n = nu;
         const uint64_t capn = pow2_at_least(2 * (n_elem + (uint64_t)s[LRB_S_KNOWN_TRANS]) + 1024);
-        NEED(c->h_khi, capn * 24); NEED(c->h_score, capn * 4);          // khi | klo | minpos in one buffer: one fill
-        CK(cudaMemsetAsync(c->h_khi.p, 0xFF, capn * 24, c->st)); CK(cudaMemsetAsync(c->h_score.p, 0, capn * 4, c->st));
-        sa.tab.mask = capn - 1; sa.tab.khi = c->h_khi.as<uint64_t>(); sa.tab.klo = sa.tab.khi + capn; sa.tab.minpos = sa.tab.khi + 2 * capn;
-        sa.tab.score = c->h_score.as<int32_t>();
+        NEED(c->h_khi, capn * sizeof(HashSlot));
+        CK(cudaMemsetAsync(c->h_khi.p, 0xFF, capn * sizeof(HashSlot), c->st));
+        sa.tab.mask = capn - 1; sa.tab.slots = c->h_khi.as<HashSlot>();
         // BED rows are the first occurrences of the exon set: at most one per counted element
         const size_t nb = (size_t)std::max<uint64_t>(n_elem, 1);
         NEED(c->bd_tid, nb * 4); NEED(c->bd_s, nb * 4); NEED(c->bd_e, nb * 4); NEED(c->bd_sc, nb * 4); NEED(c->bd_ty, nb); NEED(c->bd_rv, nb);
         sa.bed_tid = c->bd_tid.as<int32_t>(); sa.bed_start = c->bd_s.as<int32_t>(); sa.bed_end = c->bd_e.as<int32_t>(); sa.bed_score = c->bd_sc.as<int32_t>();
         sa.bed_type = c->bd_ty.as<uint8_t>(); sa.bed_rev = c->bd_rv.as<uint8_t>();
         CK(cudaMemsetAsync(c->y_counts.p, 0, 32, c->st));
-        launch_summary_sets(sa, ca.cls, n, c->tile_state.as<uint64_t>(), d_ticket(c), T + T_BED, c->st);
+        launch_summary_sets(sa, ca.cls, n, c->tile_state.as<uint64_t>(), (uint32_t *)(c->y_nelem.as<uint8_t>() + 16), T + T_BED, c->st);
         launch_summary_bed(sa, c->st);
         CK(cudaGetLastError());
         uint8_t *hp = (uint8_t *)c->h_scalars.p;

@@ -66,6 +66,7 @@ struct ScanArgs {
     uint64_t *tile_state; uint32_t *ticket;         // look-back state (zeroed per launch)
     uint64_t *totals;                               // [0] rows, [1] exons
     int reads_per_tile, stage_words;
+    int rows_by_record;                             // 1: a passing record's row is written at its record index (no row compaction)
 };
 
 void launch_cigar_scan(const ScanArgs &a, int n_tiles, bool warp_mode, size_t smem_bytes, cudaStream_t st);
@@ -74,6 +75,10 @@ void launch_select_runs(const DBatch &b, const uint32_t *row_read, int64_t n_row
 // ordered compaction of the set positions of a byte mask: out[k] = index of k-th nonzero (optionally mapped through `map`)
 void launch_compact_mask(const uint8_t *mask, int64_t n, const uint32_t *map, uint32_t *out, uint32_t *out2_unmapped,
                          uint64_t *tile_state, uint32_t *ticket, uint64_t *total, cudaStream_t st);
+void launch_select_records(const DBatch &b, const uint8_t *pass, const int32_t *score, const int32_t *intron_n, lrb_filter_params fp,
+                           uint8_t *keep_rec_mask, cudaStream_t st);
+void launch_compact_gather(const uint8_t *mask, int64_t n, const DRows &src_by_record, DRows &dst, uint32_t *keep_idx,
+                           uint64_t *tile_state, uint32_t *ticket, uint64_t *total, cudaStream_t st);
 void launch_gather_rows(const DRows &src, const uint32_t *sel, int64_t n_sel, DRows &dst, cudaStream_t st);
 
 // ---- classification

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) cigar_scan_kernel(ScanArgs a)
 
     // ---- row records
     if (tid < nr && my_row) {
-        int64_t r = r0 + tid; uint32_t row = row_base + row_excl;
+        int64_t r = r0 + tid; uint32_t row = a.rows_by_record ? (uint32_t)r : row_base + row_excl;
         if ((int64_t)row < a.rows.cap) {
             a.rows.read_idx[row] = (uint32_t)r;
             if (do_exon) {
@@ -305,6 +305,79 @@ void launch_select_runs(const DBatch &b, const uint32_t *row_read, int64_t n_row
     if (n_rows <= 0) return;
     int th = 256; int64_t bl = (n_rows + th - 1) / th;
     select_runs_kernel<<<(unsigned)bl, th, 0, st>>>(b.qhash, row_read, n_rows, score, intron_n, fp, keep_row_mask, keep_rec_mask);
+    LRB_COUNT_LAUNCH();
+}
+
+// The same state machine on the record stream itself (fused filter + exon pass): the passing subsequence is walked through
+// the pass mask, so no compacted row list -- and no host round trip for its size -- is needed in front of the selection.
+__global__ void select_records_kernel(const uint64_t *__restrict__ qhash, const uint8_t *__restrict__ pass, int64_t n,
+                                      const int32_t *__restrict__ score, const int32_t *__restrict__ intron_n, lrb_filter_params fp, uint8_t *keep_rec_mask)
+{
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n || !pass[r]) return;
+    const uint64_t h = qhash[r];
+    int64_t p = r - 1;
+    while (p >= 0 && !pass[p]) --p;
+    if (p >= 0 && qhash[p] == h) return;                        // not a run head
+    int b_score = score[r], s_score = 0, b_intron = intron_n[r]; int64_t best = r;
+    for (int64_t j = r + 1; j < n; ++j) {
+        if (!pass[j]) continue;
+        if (qhash[j] != h) break;
+        int sc = score[j];
+        if (sc > b_score) { best = j; s_score = b_score; b_score = sc; b_intron = intron_n[j]; }
+        else if (sc > s_score) s_score = sc;
+    }
+    if ((float)s_score < __fmul_rn(fp.sec_rat, (float)b_score) && b_intron >= fp.min_intron_n) keep_rec_mask[best] = 1;
+}
+void launch_select_records(const DBatch &b, const uint8_t *pass, const int32_t *score, const int32_t *intron_n, lrb_filter_params fp,
+                           uint8_t *keep_rec_mask, cudaStream_t st)
+{
+    if (b.n <= 0) return;
+    select_records_kernel<<<(unsigned)((b.n + 255) / 256), 256, 0, st>>>(b.qhash, pass, b.n, score, intron_n, fp, keep_rec_mask);
+    LRB_COUNT_LAUNCH();
+}
+
+// ordered compaction of the kept records + gather of their (record-indexed) rows into the compact row table
+__global__ void __launch_bounds__(256) compact_gather_kernel(const uint8_t *__restrict__ mask, int64_t n, DRows src, DRows dst, uint32_t *keep_idx,
+                                                             uint64_t *tile_state, uint32_t *ticket, uint64_t *total)
+{
+    constexpr int ITEMS = 8;
+    __shared__ uint32_t s_scan[33];
+    __shared__ uint32_t s_tile; __shared__ uint64_t s_excl;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const int tile = (int)s_tile;
+    const int64_t base = ((int64_t)tile * 256 + threadIdx.x) * ITEMS;
+    uint32_t cnt = 0, m = 0;
+    if (base + ITEMS <= n) {                                     // 8 mask bytes in one load (base is a multiple of 8)
+        const uint2 q = *(const uint2 *)(mask + base);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { if ((q.x >> (8 * i)) & 0xffu) m |= 1u << i; if ((q.y >> (8 * i)) & 0xffu) m |= 1u << (4 + i); }
+    } else {
+        for (int i = 0; i < ITEMS; ++i) if (base + i < n && mask[base + i]) m |= 1u << i;
+    }
+    cnt = __popc(m);
+    uint32_t tot, excl = block_excl_sum(cnt, s_scan, &tot);
+    if (warp_id() == 0) { uint64_t e = lookback_exclusive(tile_state, tile, tot, OpAdd()); if (lane_id() == 0) s_excl = e; }
+    __syncthreads();
+    uint32_t o = (uint32_t)s_excl + excl;
+    while (m) {
+        const int i = __ffs(m) - 1; m &= m - 1;
+        const uint32_t s = (uint32_t)(base + i);
+        keep_idx[o] = s;
+        dst.read_idx[o] = s; dst.tid[o] = src.tid[s]; dst.start[o] = src.start[s]; dst.end[o] = src.end[s];
+        dst.is_rev[o] = src.is_rev[s]; dst.ex_beg[o] = src.ex_beg[s]; dst.ex_n[o] = src.ex_n[s];
+        ++o;
+    }
+    if ((int64_t)(tile + 1) * 256 * ITEMS >= n && threadIdx.x == 0) *total = s_excl + tot;
+}
+void launch_compact_gather(const uint8_t *mask, int64_t n, const DRows &src, DRows &dst, uint32_t *keep_idx,
+                           uint64_t *tile_state, uint32_t *ticket, uint64_t *total, cudaStream_t st)
+{
+    if (n <= 0) { cudaMemsetAsync(total, 0, 8, st); return; }
+    int64_t per = 256 * 8, bl = (n + per - 1) / per;
+    cudaMemsetAsync(tile_state, 0, (size_t)bl * 8, st); cudaMemsetAsync(ticket, 0, 4, st);
+    compact_gather_kernel<<<(unsigned)bl, 256, 0, st>>>(mask, n, src, dst, keep_idx, tile_state, ticket, total);
     LRB_COUNT_LAUNCH();
 }
 

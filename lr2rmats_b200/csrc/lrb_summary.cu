@@ -34,9 +34,9 @@ LRB_DEVINL uint64_t tab_upsert(const HashTab &t, uint64_t hi, uint64_t lo)
 {
     uint64_t s = mix64(hi * 0x9E3779B97F4A7C15ull ^ mix64(lo)) & t.mask;
     for (;;) {
-        unsigned long long p = atomicCAS((unsigned long long *)&t.khi[s], (unsigned long long)EMPTY, (unsigned long long)hi);
+        unsigned long long p = atomicCAS((unsigned long long *)&t.slots[s].khi, (unsigned long long)EMPTY, (unsigned long long)hi);
         if (p == EMPTY || p == hi) {
-            unsigned long long q = atomicCAS((unsigned long long *)&t.klo[s], (unsigned long long)EMPTY, (unsigned long long)lo);
+            unsigned long long q = atomicCAS((unsigned long long *)&t.slots[s].klo, (unsigned long long)EMPTY, (unsigned long long)lo);
             if (q == EMPTY || q == lo) return s;
         }
         s = (s + 1) & t.mask;
@@ -46,13 +46,14 @@ LRB_DEVINL uint64_t tab_find(const HashTab &t, uint64_t hi, uint64_t lo)
 {
     uint64_t s = mix64(hi * 0x9E3779B97F4A7C15ull ^ mix64(lo)) & t.mask;
     for (;;) {
-        uint64_t a = t.khi[s];
-        if (a == hi && t.klo[s] == lo) return s;
+        const ulonglong2 k = *(const ulonglong2 *)&t.slots[s].khi;      // both key words in one 16-byte load
+        const uint64_t a = k.x;
+        if (a == hi && k.y == lo) return s;
         if (a == EMPTY) return EMPTY;
         s = (s + 1) & t.mask;
     }
 }
-LRB_DEVINL void tab_min(const HashTab &t, uint64_t s, uint64_t pos) { atomicMin((unsigned long long *)&t.minpos[s], (unsigned long long)pos); }
+LRB_DEVINL void tab_min(const HashTab &t, uint64_t s, uint64_t pos) { atomicMin((unsigned long long *)&t.slots[s].minpos, (unsigned long long)pos); }
 
 struct EntryView {
     int n; uint32_t gbeg; int fs, le; int t_tid, real_tid, rev, cov, gene, piece; uint32_t row;
@@ -105,7 +106,7 @@ __global__ void sum_phase1_kernel(SummaryArgs a)
         if (x & LRB_F_NOVEL_EXON) {
             uint64_t s = tab_upsert(a.tab, key_hi(SET_E, 0, e.real_tid), key_lo(ent_s(a, e, j), ent_e(a, e, j)));
             tab_min(a.tab, s, pos_of(i, j));
-            atomicAdd(&a.tab.score[s], e.cov);
+            atomicAdd(&a.tab.slots[s].score, e.cov);
         }
         if (e.t_tid == 0 && j < e.n - 1) {
             if (x & LRB_F_NOVEL_DON) tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_D, SEG_TID0, 0), key_lo(ent_e(a, e, j), 0)), pos_of(i, j));
@@ -125,18 +126,18 @@ __global__ void sum_phase2_kernel(SummaryArgs a)
     uint32_t cd = 0, ca = 0, cj = 0, cg = 0, ce = 0;
     if (e.t_tid == 0) {
         uint64_t s = tab_find(a.tab, key_hi(SET_G, SEG_TID0, 0), key_lo(e.gene, 0));
-        cg = a.tab.minpos[s] == pos_of(i, 0);
+        cg = a.tab.slots[s].minpos == pos_of(i, 0);
     }
     for (int j = 0; j < e.n; ++j) {
         uint8_t x = f[j];
         if (x & LRB_F_NOVEL_EXON) {
             uint64_t s = tab_find(a.tab, key_hi(SET_E, 0, e.real_tid), key_lo(ent_s(a, e, j), ent_e(a, e, j)));
-            ce += a.tab.minpos[s] == pos_of(i, j);
+            ce += a.tab.slots[s].minpos == pos_of(i, j);
         }
         if (e.t_tid == 0 && j < e.n - 1) {
-            if (x & LRB_F_NOVEL_DON) cd += a.tab.minpos[tab_find(a.tab, key_hi(SET_D, SEG_TID0, 0), key_lo(ent_e(a, e, j), 0))] == pos_of(i, j);
-            if (x & LRB_F_NOVEL_ACC) ca += a.tab.minpos[tab_find(a.tab, key_hi(SET_A, SEG_TID0, 0), key_lo(ent_s(a, e, j + 1), 0))] == pos_of(i, j);
-            if (x & LRB_F_NOVEL_JUNC) cj += a.tab.minpos[tab_find(a.tab, key_hi(SET_J, SEG_TID0, 0), key_lo(ent_e(a, e, j), ent_s(a, e, j + 1)))] == pos_of(i, j);
+            if (x & LRB_F_NOVEL_DON) cd += a.tab.slots[tab_find(a.tab, key_hi(SET_D, SEG_TID0, 0), key_lo(ent_e(a, e, j), 0))].minpos == pos_of(i, j);
+            if (x & LRB_F_NOVEL_ACC) ca += a.tab.slots[tab_find(a.tab, key_hi(SET_A, SEG_TID0, 0), key_lo(ent_s(a, e, j + 1), 0))].minpos == pos_of(i, j);
+            if (x & LRB_F_NOVEL_JUNC) cj += a.tab.slots[tab_find(a.tab, key_hi(SET_J, SEG_TID0, 0), key_lo(ent_e(a, e, j), ent_s(a, e, j + 1)))].minpos == pos_of(i, j);
         }
     }
     a.bar_cnt[0 * a.n_upd + i] = cd; a.bar_cnt[1 * a.n_upd + i] = ca; a.bar_cnt[2 * a.n_upd + i] = cj; a.bar_cnt[3 * a.n_upd + i] = cg;
@@ -180,7 +181,7 @@ __global__ void sum_phase4_kernel(SummaryArgs a)
     uint32_t cd = 0, ca = 0, cj = 0, cg = 0;
     {
         uint64_t s = tab_find(a.tab, key_hi(SET_G, sg, e.t_tid), key_lo(e.gene, 0));
-        bool first = a.tab.minpos[s] == pos_of(i, 0);
+        bool first = a.tab.slots[s].minpos == pos_of(i, 0);
         uint64_t bar = a.gene_bar[i];                // index+1 of the last inserted tid-0 gene entry before i (inclusive scan, own value 0)
         if (first && bar) {
             EntryView b = load_entry(a, (int64_t)bar - 1);
@@ -190,9 +191,9 @@ __global__ void sum_phase4_kernel(SummaryArgs a)
     }
     for (int j = 0; j < e.n - 1; ++j) {
         uint8_t x = f[j];
-        if (x & LRB_F_NOVEL_DON) cd += a.tab.minpos[tab_find(a.tab, key_hi(SET_D, sd, e.t_tid), key_lo(ent_e(a, e, j), 0))] == pos_of(i, j);
-        if (x & LRB_F_NOVEL_ACC) ca += a.tab.minpos[tab_find(a.tab, key_hi(SET_A, sa, e.t_tid), key_lo(ent_s(a, e, j + 1), 0))] == pos_of(i, j);
-        if (x & LRB_F_NOVEL_JUNC) cj += a.tab.minpos[tab_find(a.tab, key_hi(SET_J, sj, e.t_tid), key_lo(ent_e(a, e, j), ent_s(a, e, j + 1)))] == pos_of(i, j);
+        if (x & LRB_F_NOVEL_DON) cd += a.tab.slots[tab_find(a.tab, key_hi(SET_D, sd, e.t_tid), key_lo(ent_e(a, e, j), 0))].minpos == pos_of(i, j);
+        if (x & LRB_F_NOVEL_ACC) ca += a.tab.slots[tab_find(a.tab, key_hi(SET_A, sa, e.t_tid), key_lo(ent_s(a, e, j + 1), 0))].minpos == pos_of(i, j);
+        if (x & LRB_F_NOVEL_JUNC) cj += a.tab.slots[tab_find(a.tab, key_hi(SET_J, sj, e.t_tid), key_lo(ent_e(a, e, j), ent_s(a, e, j + 1)))].minpos == pos_of(i, j);
     }
     if (cd) atomicAdd(&a.counts[SET_D], cd);
     if (ca) atomicAdd(&a.counts[SET_A], ca);
@@ -212,11 +213,59 @@ __global__ void sum_bed_kernel(SummaryArgs a)
         if (!(f[j] & LRB_F_NOVEL_EXON)) continue;
         int s0 = ent_s(a, e, j), e0 = ent_e(a, e, j);
         uint64_t s = tab_find(a.tab, key_hi(SET_E, 0, e.real_tid), key_lo(s0, e0));
-        if (a.tab.minpos[s] != pos_of(i, j)) continue;
-        a.bed_tid[o] = e.real_tid; a.bed_start[o] = s0; a.bed_end[o] = e0; a.bed_score[o] = a.tab.score[s];
+        if (a.tab.slots[s].minpos != pos_of(i, j)) continue;
+        a.bed_tid[o] = e.real_tid; a.bed_start[o] = s0; a.bed_end[o] = e0; a.bed_score[o] = a.tab.slots[s].score + 1;            // the table is filled with 0xFF: scores start at -1
         a.bed_type[o] = e.n > 1 ? ((j == 0 || j == e.n - 1) ? 0 : 1) : 2; a.bed_rev[o] = (uint8_t)e.rev;
         ++o;
     }
+}
+
+// the six scans between phase 2 and phase 3 in one launch: blockIdx.y selects the sequence (0-3 exclusive sums of the
+// barrier counts, 4 inclusive running max of gene_bar in place, 5 exclusive sum of bed_cnt with its total); every
+// sequence has its own ticket and look-back words
+static constexpr int MS_THREADS = 256, MS_ITEMS = 8;
+__global__ void __launch_bounds__(MS_THREADS) sum_scans_kernel(SummaryArgs a, uint64_t *tile_state, uint32_t *tickets, int n_tiles, uint64_t *bed_total)
+{
+    __shared__ uint32_t s_scan[33]; __shared__ uint64_t s_w[MS_THREADS / 32]; __shared__ uint32_t s_tile; __shared__ uint64_t s_excl;
+    const int which = blockIdx.y;
+    if (threadIdx.x == 0) s_tile = atomicAdd(tickets + which, 1u);
+    __syncthreads();
+    const int tile = (int)s_tile, lane = lane_id(), w = warp_id();
+    uint64_t *state = tile_state + (size_t)which * n_tiles;
+    const int64_t n = a.n_upd, base = ((int64_t)tile * MS_THREADS + threadIdx.x) * MS_ITEMS;
+    if (which == 4) {
+        uint64_t *data = a.gene_bar;
+        uint64_t v[MS_ITEMS], run = 0;
+#pragma unroll
+        for (int i = 0; i < MS_ITEMS; ++i) { v[i] = (base + i < n) ? data[base + i] : 0; run = v[i] > run ? v[i] : run; v[i] = run; }
+        uint64_t inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint64_t t = __shfl_up_sync(FULL, inc, o); if (lane >= o && t > inc) inc = t; }
+        if (lane == 31) s_w[w] = inc;
+        __syncthreads();
+        uint64_t pre = 0, tot = 0;
+        for (int k = 0; k < MS_THREADS / 32; ++k) { const uint64_t x = s_w[k]; if (k < w && x > pre) pre = x; if (x > tot) tot = x; }
+        uint64_t left = __shfl_up_sync(FULL, inc, 1); if (lane == 0) left = 0;
+        const uint64_t tpre = left > pre ? left : pre;
+        if (w == 0) { uint64_t e = lookback_exclusive(state, tile, tot, OpMax()); if (lane == 0) s_excl = e; }
+        __syncthreads();
+        const uint64_t ex = s_excl > tpre ? s_excl : tpre;
+#pragma unroll
+        for (int i = 0; i < MS_ITEMS; ++i) if (base + i < n) data[base + i] = v[i] > ex ? v[i] : ex;
+        return;
+    }
+    const uint32_t *in = which == 5 ? a.bed_cnt : a.bar_cnt + (int64_t)which * n;
+    uint32_t *out = which == 5 ? a.bed_off : a.bar_seg + (int64_t)which * n;
+    uint32_t v[MS_ITEMS], sum = 0;
+#pragma unroll
+    for (int i = 0; i < MS_ITEMS; ++i) { v[i] = (base + i < n) ? in[base + i] : 0; sum += v[i]; }
+    uint32_t tot, excl = block_excl_sum(sum, s_scan, &tot);
+    if (w == 0) { uint64_t e = lookback_exclusive(state, tile, tot, OpAdd()); if (lane == 0) s_excl = e; }
+    __syncthreads();
+    uint32_t o = (uint32_t)s_excl + excl;
+#pragma unroll
+    for (int i = 0; i < MS_ITEMS; ++i) if (base + i < n) { out[base + i] = o; o += v[i]; }
+    if (which == 5 && tile == n_tiles - 1 && threadIdx.x == 0) *bed_total = s_excl + tot;
 }
 
 // genes of the known reads (update_gtf.c:503-506): distinct (tid, gene) over bam_T rows flagged known
@@ -227,7 +276,7 @@ __global__ void sum_known_genes_kernel(SummaryArgs a, const uint32_t *__restrict
     int ref = a.ref[r]; int gene = ref >= 0 ? a.anno_gene[ref] : -1;
     uint64_t hi = key_hi(SET_KG, 0, a.rows.tid[r]), lo = key_lo(gene, 0);
     if (pass == 0) tab_min(a.tab, tab_upsert(a.tab, hi, lo), (uint64_t)r);
-    else if (a.tab.minpos[tab_find(a.tab, hi, lo)] == (uint64_t)r) atomicAdd(&a.counts[SET_KG], 1u);
+    else if (a.tab.slots[tab_find(a.tab, hi, lo)].minpos == (uint64_t)r) atomicAdd(&a.counts[SET_KG], 1u);
 }
 
 static inline unsigned nblk(int64_t n) { return (unsigned)((n + 255) / 256); }
@@ -237,22 +286,20 @@ void launch_summary_count(const SummaryArgs &a, unsigned long long *n_elems, cud
     if (a.n_upd <= 0) return;
     sum_count_kernel<<<nblk(a.n_upd), 256, 0, st>>>(a, n_elems); LRB_COUNT_LAUNCH();
 }
-void launch_summary_sets(const SummaryArgs &a, const uint32_t *cls, int64_t n_rows, uint64_t *tile_state, uint32_t *ticket, uint64_t *bed_total, cudaStream_t st)
+// tile_state: 6 * (n_upd / 2048 + 1) words; tickets: 6 words (zeroed here)
+void launch_summary_sets(const SummaryArgs &a, const uint32_t *cls, int64_t n_rows, uint64_t *tile_state, uint32_t *tickets, uint64_t *bed_total, cudaStream_t st)
 {
+    if (n_rows > 0) { sum_known_genes_kernel<<<nblk(n_rows), 256, 0, st>>>(a, cls, n_rows, 0); LRB_COUNT_LAUNCH(); }
     if (a.n_upd > 0) {
         sum_phase1_kernel<<<nblk(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
         sum_phase2_kernel<<<nblk(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
-        for (int s = 0; s < 4; ++s)
-            launch_scan_sum_u32(a.bar_cnt + (int64_t)s * a.n_upd, a.bar_seg + (int64_t)s * a.n_upd, a.n_upd, tile_state, ticket, nullptr, st);
-        launch_scan_max_u64(a.gene_bar, a.n_upd, tile_state, ticket, st);
-        launch_scan_sum_u32(a.bed_cnt, a.bed_off, a.n_upd, tile_state, ticket, bed_total, st);
+        const int n_tiles = (int)((a.n_upd + MS_THREADS * MS_ITEMS - 1) / (MS_THREADS * MS_ITEMS));
+        cudaMemsetAsync(tile_state, 0, (size_t)n_tiles * 6 * 8, st); cudaMemsetAsync(tickets, 0, 6 * 4, st);
+        sum_scans_kernel<<<dim3((unsigned)n_tiles, 6), MS_THREADS, 0, st>>>(a, tile_state, tickets, n_tiles, bed_total); LRB_COUNT_LAUNCH();
         sum_phase3_kernel<<<nblk(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
         sum_phase4_kernel<<<nblk(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
     } else cudaMemsetAsync(bed_total, 0, 8, st);
-    if (n_rows > 0) {
-        sum_known_genes_kernel<<<nblk(n_rows), 256, 0, st>>>(a, cls, n_rows, 0); LRB_COUNT_LAUNCH();
-        sum_known_genes_kernel<<<nblk(n_rows), 256, 0, st>>>(a, cls, n_rows, 1); LRB_COUNT_LAUNCH();
-    }
+    if (n_rows > 0) { sum_known_genes_kernel<<<nblk(n_rows), 256, 0, st>>>(a, cls, n_rows, 1); LRB_COUNT_LAUNCH(); }
 }
 void launch_summary_bed(const SummaryArgs &a, cudaStream_t st)
 {

@@ -4,10 +4,13 @@
 
 namespace lrbk {
 
-struct HashTab {                                    // open addressing, 128-bit keys, all words memset to 0xFF when empty
+// open addressing, 128-bit keys; one 32-byte slot (= one memory sector) carries the key, the minimum stream position and
+// the accumulated score of an element, so all atomics on an element stay in one sector.  Empty = all bytes 0xFF
+// (the score therefore starts at -1).
+struct __align__(32) HashSlot { uint64_t khi, klo, minpos; int32_t score, pad; };
+struct HashTab {
     uint64_t mask = 0;
-    uint64_t *khi = nullptr, *klo = nullptr, *minpos = nullptr;
-    int32_t *score = nullptr;                       // zeroed
+    HashSlot *slots = nullptr;
 };
 
 struct SummaryArgs {

@@ -700,8 +700,8 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
             launch_summary_count(sa, c->y_nelem.as<unsigned long long>(), c->st);
             CK(cudaGetLastError());
         }
-        // ---- the one round trip: totals, error flags, class counters, element count
-        if (up->want_summary && c->side_stream) CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
+        // ---- the one round trip: totals, error flags, class sizes, element count.  The class folds keep running on the
+        // side stream underneath the summary sets; they are joined in front of the last copy of this stage.
         uint8_t *hp = (uint8_t *)c->h_scalars.p;
         CK(cudaMemcpyAsync(hp, c->scalars.p, T_SLOTS * 8 + 8, cudaMemcpyDeviceToHost, c->st));
         CK(cudaMemcpyAsync(hp + 320, c->y_counts.p, 64, cudaMemcpyDeviceToHost, c->st));
@@ -715,6 +715,7 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
         if (n_novel > cap) {                          // novel_T did not fit: once more with the exact size
             if (attempt >= 1) return fail(c, LRB_E_CUDA, "novel_T size changed between passes");
             cap = n_novel; c->novel_cap_hint = n_novel + n_novel / 16;
+            if (up->want_summary && c->side_stream) CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));   // the counters are reset below
             continue;
         }
         c->mg.n_loci = (int64_t)t[T_LOCI]; c->mg.n_out = nu = (int64_t)t[T_UPD];
@@ -729,7 +730,7 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
         int32_t *s = c->summary;
         const int cnt_idx[4] = {LRB_S_KNOWN_TRANS, LRB_S_NOVEL_RELIABLE, LRB_S_NOVEL_UNRELIABLE, LRB_S_UNRECOG};
         const int uniq_idx[4] = {LRB_S_UNIQ_KNOWN, LRB_S_UNIQ_RELIABLE, LRB_S_UNIQ_UNRELIABLE, LRB_S_UNIQ_UNRECOG};
-        for (int k = 0; k < 4; ++k) { s[cnt_idx[k]] = (int32_t)cnt16[12 + k]; s[uniq_idx[k]] = (int32_t)cnt16[8 + k]; }
+        for (int k = 0; k < 4; ++k) s[cnt_idx[k]] = (int32_t)cnt16[12 + k];
         s[LRB_S_NOVEL_BAM] = s[LRB_S_NOVEL_RELIABLE] + s[LRB_S_NOVEL_UNRELIABLE];
         sa.n_upd = nu; sa.n_upd_dev = nullptr; sa.upd.n = nu;
         const uint64_t capn = pow2_at_least(2 * (n_elem + (uint64_t)s[LRB_S_KNOWN_TRANS]) + 1024);
@@ -745,12 +746,14 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
         launch_summary_sets(sa, ca.cls, n, c->tile_state.as<uint64_t>(), (uint32_t *)(c->y_nelem.as<uint8_t>() + 16), T + T_BED, c->st);
         launch_summary_bed(sa, c->st);
         CK(cudaGetLastError());
+        if (c->side_stream) CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
         uint8_t *hp = (uint8_t *)c->h_scalars.p;
         CK(cudaMemcpyAsync(hp, T + T_BED, 8, cudaMemcpyDeviceToHost, c->st));
-        CK(cudaMemcpyAsync(hp + 64, c->y_counts.p, 32, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(hp + 64, c->y_counts.p, 48, cudaMemcpyDeviceToHost, c->st));
         CK(cudaStreamSynchronize(c->st));
-        uint64_t nbed; uint32_t cnt[8];
-        memcpy(&nbed, hp, 8); memcpy(cnt, hp + 64, 32);
+        uint64_t nbed; uint32_t cnt[12];
+        memcpy(&nbed, hp, 8); memcpy(cnt, hp + 64, 48);
+        for (int k = 0; k < 4; ++k) s[uniq_idx[k]] = (int32_t)cnt[8 + k];
         c->n_bed = nu ? (int64_t)nbed : 0;
         s[LRB_S_UPD_GENES] = (int32_t)cnt[4]; s[LRB_S_NOVEL_TRANS] = (int32_t)nu; s[LRB_S_NOVEL_PARTIAL] = (int32_t)cnt[6];
         s[LRB_S_NOVEL_FULL] = (int32_t)nu - (int32_t)cnt[6]; s[LRB_S_NOVEL_EXONS] = (int32_t)cnt[0]; s[LRB_S_NOVEL_SITES] = (int32_t)(cnt[1] + cnt[2]);

@@ -288,7 +288,8 @@ __global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a, const
 // replaces the reference's three nested loops; the four per-exon flag arrays live in four 32-bit registers.
 static constexpr int CR_THREADS = 128;
 
-__global__ void __launch_bounds__(CR_THREADS) classify_row_kernel(ClassArgs a, uint8_t *__restrict__ slow, const uint8_t *__restrict__ row_nonmono)
+template <int MINB>
+__global__ void __launch_bounds__(CR_THREADS, MINB) classify_row_kernel(ClassArgs a, uint8_t *__restrict__ slow, const uint8_t *__restrict__ row_nonmono)
 {
     __shared__ int s_win[6];
     const int t = threadIdx.x;
@@ -478,11 +479,14 @@ template <int G, int SLOTS> static void launch_classify_t(const ClassArgs &a, co
 void launch_classify(const ClassArgs &a, uint8_t *slow, cudaStream_t st)
 {
     if (a.rows.n <= 0) return;
-    static int g = -1, fast = -1;
-    if (g < 0) { const char *e = getenv("LRB_CLASSIFY_G"); g = e ? atoi(e) : 4; e = getenv("LRB_CLASSIFY_FAST"); fast = e ? atoi(e) : 1; }
+    static int g = -1, fast = -1, occ = 9;
+    if (g < 0) { const char *e = getenv("LRB_CLASSIFY_G"); g = e ? atoi(e) : 4; e = getenv("LRB_CLASSIFY_FAST"); fast = e ? atoi(e) : 1; e = getenv("LRB_CR_OCC"); if (e) occ = atoi(e); }
     const uint8_t *only = nullptr;
     if (fast && a.up.ss_dis == 0 && slow) {
-        classify_row_kernel<<<(unsigned)((a.rows.n + CR_THREADS - 1) / CR_THREADS), CR_THREADS, 0, st>>>(a, slow, a.row_nonmono);
+        const unsigned bl = (unsigned)((a.rows.n + CR_THREADS - 1) / CR_THREADS);
+        if (occ >= 16) classify_row_kernel<16><<<bl, CR_THREADS, 0, st>>>(a, slow, a.row_nonmono);
+        else if (occ >= 12) classify_row_kernel<12><<<bl, CR_THREADS, 0, st>>>(a, slow, a.row_nonmono);
+        else classify_row_kernel<8><<<bl, CR_THREADS, 0, st>>>(a, slow, a.row_nonmono);
         LRB_COUNT_LAUNCH();
         only = slow;
     }

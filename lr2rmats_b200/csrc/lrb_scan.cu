@@ -50,6 +50,30 @@ LRB_DEVINL void walk_seq(const uint32_t *c, int n_c, int pos, const lrb_exon_par
     w.n_exon = n; w.intron_n = intron; w.del_len = del; w.ref_len = end - pos; w.first_start = first_start; w.last_end = end;
 }
 
+// ---- sequential walk that also keeps the exons: exon k (all but the last) is parked in the words 2k, 2k+1 of the read's own
+// staged CIGAR, which the walk has consumed by then whenever cuts are not adjacent and the CIGAR does not start with one
+// (word 2k+1 <= index of the cut that closes exon k).  A CIGAR that breaks this sets *ovf and is walked again later.
+LRB_DEVINL void walk_seq_inplace(uint32_t *c, int n_c, int pos, const lrb_exon_params &ep, WalkStats &w, bool *ovf, int *last_start)
+{
+    int n = 0, start = pos + 1, end = pos, intron = 0, del = 0; bool over = false;
+    for (int i = 0; i < n_c; ++i) {
+        uint32_t x = c[i]; int l = (int)(x >> 4); unsigned op = x & 15u;
+        bool cut = (op == OP_N && l >= ep.min_intron) || (op == OP_D && l > ep.max_delet);
+        if (op == OP_N) ++intron; else if (op == OP_D) del += l;
+        if (cut) {
+            if (n == 0 || (end - start + 1) >= ep.min_exon) {
+                if (2 * n + 1 <= i && !over) { c[2 * n] = (uint32_t)start; c[2 * n + 1] = (uint32_t)end; } else over = true;
+                ++n;
+            }
+            start = end + l + 1;
+        }
+        if (op_ref(op)) end += l;
+    }
+    ++n;
+    *ovf = over; *last_start = start;
+    w.n_exon = n; w.intron_n = intron; w.del_len = del; w.ref_len = end - pos; w.first_start = pos + 1; w.last_end = end;
+}
+
 // ---- cooperative walk (one warp, lanes over ops, 32 ops per step)
 template <bool EMIT>
 LRB_DEVINL void walk_warp(const uint32_t *c, int n_c, int pos, const lrb_exon_params &ep, int *es, int *ee, WalkStats &w)
@@ -106,12 +130,11 @@ LRB_DEVINL bool rm_hit(const DRmIndex &rm, int tid, int pos, int rlen)
 }
 
 // gtf_filter() predicate after the walk (bam_filter.c:73-84); mixed float/double compares kept as in C
-LRB_DEVINL bool filter_pass(const ScanArgs &a, int64_t r, const uint32_t *c, int n_c, const WalkStats &w, int *score)
+LRB_DEVINL bool filter_pass(const ScanArgs &a, int64_t r, uint32_t c0, uint32_t c1, int n_c, const WalkStats &w, int *score)
 {
     if (a.b.flag[r] & 4) return false;
     int l_qseq = a.b.l_qseq[r], qlen = l_qseq;
     if (n_c > 0) {
-        uint32_t c0 = c[0], c1 = c[n_c - 1];
         unsigned op0 = c0 & 15u, op1 = c1 & 15u;
         if (op0 == OP_S || op0 == OP_H) qlen -= (int)(c0 >> 4);
         if (n_c > 1 && (op1 == OP_S || op1 == OP_H)) qlen -= (int)(c1 >> 4);
@@ -169,10 +192,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) cigar_scan_kernel(ScanArgs a)
         uint32_t off = a.b.cigar_off[r];
         return staged ? (s_words + (off - w_lo)) : (a.b.cigar + off);
     };
-    auto finish_read = [&](int li, int64_t r, const uint32_t *c, int n_c, const WalkStats &w) {
+    auto finish_read = [&](int li, int64_t r, uint32_t c0, uint32_t c1, int n_c, const WalkStats &w) {
         bool mask;
         if (do_filter) {
-            int sc = 0; bool p = filter_pass(a, r, c, n_c, w, &sc);
+            int sc = 0; bool p = filter_pass(a, r, c0, c1, n_c, w, &sc);
             a.pass[r] = p ? 1 : 0;
             if (p) { a.score[r] = sc; a.intron_n[r] = w.intron_n; }
             mask = p;
@@ -182,19 +205,23 @@ __global__ void __launch_bounds__(SCAN_THREADS) cigar_scan_kernel(ScanArgs a)
         s_cnt[li] = (mask && do_exon && !unmapped) ? w.n_exon : 0;
         s_start[li] = w.first_start; s_end[li] = w.last_end;
     };
+    bool parked = false, park_ovf = false; int park_last_start = 0;      // thread mode: exons parked in the staged words by walk 1
     if (!WARP_MODE) {
         if (tid < nr) {
             int64_t r = r0 + tid;
             const uint32_t *c = read_ptr(r); int n_c = (int)(a.b.cigar_off[r + 1] - a.b.cigar_off[r]);
-            WalkStats w; walk_seq<false>(c, n_c, a.b.pos[r], a.ep, nullptr, nullptr, w);
-            finish_read(tid, r, c, n_c, w);
+            const uint32_t c0 = n_c > 0 ? c[0] : 0u, c1 = n_c > 0 ? c[n_c - 1] : 0u;
+            WalkStats w;
+            if (staged && do_exon) { parked = true; walk_seq_inplace(const_cast<uint32_t *>(c), n_c, a.b.pos[r], a.ep, w, &park_ovf, &park_last_start); }
+            else walk_seq<false>(c, n_c, a.b.pos[r], a.ep, nullptr, nullptr, w);
+            finish_read(tid, r, c0, c1, n_c, w);
         }
     } else {
         for (int li = warp_id(); li < nr; li += SCAN_THREADS / 32) {
             int64_t r = r0 + li;
             const uint32_t *c = read_ptr(r); int n_c = (int)(a.b.cigar_off[r + 1] - a.b.cigar_off[r]);
             WalkStats w; walk_warp<false>(c, n_c, a.b.pos[r], a.ep, nullptr, nullptr, w);
-            if (lane_id() == 0) finish_read(li, r, c, n_c, w);
+            if (lane_id() == 0) finish_read(li, r, n_c > 0 ? c[0] : 0u, n_c > 0 ? c[n_c - 1] : 0u, n_c, w);
         }
     }
     __syncthreads();
@@ -239,7 +266,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) cigar_scan_kernel(ScanArgs a)
             const uint32_t *c = read_ptr(r); int n_c = (int)(a.b.cigar_off[r + 1] - a.b.cigar_off[r]);
             int *es = ex_staged ? s_es + ex_excl : a.ex.es + ex_base + ex_excl;
             int *ee = ex_staged ? s_ee + ex_excl : a.ex.ee + ex_base + ex_excl;
-            WalkStats w; walk_seq<true>(c, n_c, a.b.pos[r], a.ep, es, ee, w);
+            if (parked && !park_ovf) {                            // move the parked exons; the open one is still in registers
+                const int last = (int)my_ex - 1;
+                for (int k = 0; k < last; ++k) { es[k] = (int)c[2 * k]; ee[k] = (int)c[2 * k + 1]; }
+                es[last] = park_last_start; ee[last] = s_end[tid];
+            } else {
+                if (parked) c = a.b.cigar + a.b.cigar_off[r];     // the staged copy is partly overwritten: walk the pool
+                WalkStats w; walk_seq<true>(c, n_c, a.b.pos[r], a.ep, es, ee, w);
+            }
         }
     } else {
         for (int li = warp_id(); li < nr; li += SCAN_THREADS / 32) {

@@ -74,34 +74,45 @@ LRB_DEVINL uint64_t pos_of(int64_t i, int j) { return ((uint64_t)i << 20) | (uin
 
 enum { SET_E = 0, SET_D = 1, SET_A = 2, SET_J = 3, SET_G = 4, SET_KG = 5 };
 
-// element counts per set (sizes the table) -- one thread per updated entry
+// Every pass below runs SG lanes per updated entry: lane l takes the exons l, l + SG, ... of the entry, so the dependent
+// chain of table operations per thread is one or two elements long instead of the whole exon list (the passes are bound
+// by the latency of those chains, not by bandwidth), and the lanes' counts are folded with group shuffles.
+static constexpr int SG = 8;
+#define SUM_ENTRY_PROLOGUE(n_limit)                                                                  \
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / SG;                         \
+    const int gl = threadIdx.x % SG;                                                                 \
+    if (i >= (n_limit)) return;                                                                      \
+    const unsigned gm = group_mask<SG>();                                                            \
+    (void)gm; (void)gl;
+
+// element counts per set (sizes the table)
 __global__ void sum_count_kernel(SummaryArgs a, unsigned long long *n_elems)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long c = 0;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / SG;
+    const int gl = threadIdx.x % SG;
+    int c = 0;
     if (i < (a.n_upd_dev ? (int64_t)*a.n_upd_dev : a.n_upd)) {
         EntryView e = load_entry(a, i);
         const uint8_t *f = a.ex.flag + e.gbeg;
-        c = 1;
-        for (int j = 0; j < e.n; ++j) {
+        c = gl == 0 ? 1 : 0;
+        for (int j = gl; j < e.n; j += SG) {
             uint8_t x = f[j];
             c += (x & LRB_F_NOVEL_EXON) != 0;
             if (j < e.n - 1) c += ((x & LRB_F_NOVEL_DON) != 0) + ((x & LRB_F_NOVEL_ACC) != 0) + ((x & LRB_F_NOVEL_JUNC) != 0);
         }
     }
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
-    if (lane_id() == 0 && c) atomicAdd(n_elems, c);
+    if (lane_id() == 0 && c) atomicAdd(n_elems, (unsigned long long)c);
 }
 
 // phase 1: exons (all entries), tid-0 elements of D/A/J, every gene element (gene equality ignores tid)
 __global__ void sum_phase1_kernel(SummaryArgs a)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n_upd) return;
+    SUM_ENTRY_PROLOGUE(a.n_upd)
     EntryView e = load_entry(a, i);
     const uint8_t *f = a.ex.flag + e.gbeg;
-    tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_G, SEG_TID0, 0), key_lo(e.gene, 0)), pos_of(i, 0));
-    for (int j = 0; j < e.n; ++j) {
+    if (gl == 0) tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_G, SEG_TID0, 0), key_lo(e.gene, 0)), pos_of(i, 0));
+    for (int j = gl; j < e.n; j += SG) {
         uint8_t x = f[j];
         if (x & LRB_F_NOVEL_EXON) {
             uint64_t s = tab_upsert(a.tab, key_hi(SET_E, 0, e.real_tid), key_lo(ent_s(a, e, j), ent_e(a, e, j)));
@@ -119,16 +130,15 @@ __global__ void sum_phase1_kernel(SummaryArgs a)
 // phase 2: per entry, how many of its tid-0 elements were inserted (= barriers), per set; exon first occurrences
 __global__ void sum_phase2_kernel(SummaryArgs a)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n_upd) return;
+    SUM_ENTRY_PROLOGUE(a.n_upd)
     EntryView e = load_entry(a, i);
     const uint8_t *f = a.ex.flag + e.gbeg;
-    uint32_t cd = 0, ca = 0, cj = 0, cg = 0, ce = 0;
-    if (e.t_tid == 0) {
+    int cd = 0, ca = 0, cj = 0, cg = 0, ce = 0;
+    if (e.t_tid == 0 && gl == 0) {
         uint64_t s = tab_find(a.tab, key_hi(SET_G, SEG_TID0, 0), key_lo(e.gene, 0));
         cg = a.tab.slots[s].minpos == pos_of(i, 0);
     }
-    for (int j = 0; j < e.n; ++j) {
+    for (int j = gl; j < e.n; j += SG) {
         uint8_t x = f[j];
         if (x & LRB_F_NOVEL_EXON) {
             uint64_t s = tab_find(a.tab, key_hi(SET_E, 0, e.real_tid), key_lo(ent_s(a, e, j), ent_e(a, e, j)));
@@ -140,30 +150,32 @@ __global__ void sum_phase2_kernel(SummaryArgs a)
             if (x & LRB_F_NOVEL_JUNC) cj += a.tab.slots[tab_find(a.tab, key_hi(SET_J, SEG_TID0, 0), key_lo(ent_e(a, e, j), ent_s(a, e, j + 1)))].minpos == pos_of(i, j);
         }
     }
+    ce = group_sum<SG>(gm, ce);
+    if (e.t_tid == 0) { cd = group_sum<SG>(gm, cd); ca = group_sum<SG>(gm, ca); cj = group_sum<SG>(gm, cj); cg = group_sum<SG>(gm, cg); }
+    if (gl != 0) return;
     a.bar_cnt[0 * a.n_upd + i] = cd; a.bar_cnt[1 * a.n_upd + i] = ca; a.bar_cnt[2 * a.n_upd + i] = cj; a.bar_cnt[3 * a.n_upd + i] = cg;
     a.bed_cnt[i] = ce;
     a.gene_bar[i] = cg ? (uint64_t)(i + 1) : 0;       // for the "last inserted tid-0 gene entry before x" max-scan
     if (cd | ca | cj | cg) {
-        if (cd) atomicAdd(&a.counts[SET_D], cd);
-        if (ca) atomicAdd(&a.counts[SET_A], ca);
-        if (cj) atomicAdd(&a.counts[SET_J], cj);
-        if (cg) atomicAdd(&a.counts[SET_G], cg);
+        if (cd) atomicAdd(&a.counts[SET_D], (uint32_t)cd);
+        if (ca) atomicAdd(&a.counts[SET_A], (uint32_t)ca);
+        if (cj) atomicAdd(&a.counts[SET_J], (uint32_t)cj);
+        if (cg) atomicAdd(&a.counts[SET_G], (uint32_t)cg);
     }
-    if (ce) atomicAdd(&a.counts[SET_E], ce);
+    if (ce) atomicAdd(&a.counts[SET_E], (uint32_t)ce);
     if (e.piece >= 0) atomicAdd(&a.counts[6], 1u);   // partial-read transcripts
 }
 
 // phase 3: tid>0 elements go into their segment
 __global__ void sum_phase3_kernel(SummaryArgs a)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n_upd) return;
+    SUM_ENTRY_PROLOGUE(a.n_upd)
     EntryView e = load_entry(a, i);
     if (e.t_tid == 0) return;
     const uint8_t *f = a.ex.flag + e.gbeg;
     const uint32_t sd = a.bar_seg[0 * a.n_upd + i], sa = a.bar_seg[1 * a.n_upd + i], sj = a.bar_seg[2 * a.n_upd + i], sg = a.bar_seg[3 * a.n_upd + i];
-    tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_G, sg, e.t_tid), key_lo(e.gene, 0)), pos_of(i, 0));
-    for (int j = 0; j < e.n - 1; ++j) {
+    if (gl == 0) tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_G, sg, e.t_tid), key_lo(e.gene, 0)), pos_of(i, 0));
+    for (int j = gl; j < e.n - 1; j += SG) {
         uint8_t x = f[j];
         if (x & LRB_F_NOVEL_DON) tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_D, sd, e.t_tid), key_lo(ent_e(a, e, j), 0)), pos_of(i, j));
         if (x & LRB_F_NOVEL_ACC) tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_A, sa, e.t_tid), key_lo(ent_s(a, e, j + 1), 0)), pos_of(i, j));
@@ -172,14 +184,13 @@ __global__ void sum_phase3_kernel(SummaryArgs a)
 }
 __global__ void sum_phase4_kernel(SummaryArgs a)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n_upd) return;
+    SUM_ENTRY_PROLOGUE(a.n_upd)
     EntryView e = load_entry(a, i);
     if (e.t_tid == 0) return;
     const uint8_t *f = a.ex.flag + e.gbeg;
     const uint32_t sd = a.bar_seg[0 * a.n_upd + i], sa = a.bar_seg[1 * a.n_upd + i], sj = a.bar_seg[2 * a.n_upd + i], sg = a.bar_seg[3 * a.n_upd + i];
-    uint32_t cd = 0, ca = 0, cj = 0, cg = 0;
-    {
+    int cd = 0, ca = 0, cj = 0, cg = 0;
+    if (gl == 0) {
         uint64_t s = tab_find(a.tab, key_hi(SET_G, sg, e.t_tid), key_lo(e.gene, 0));
         bool first = a.tab.slots[s].minpos == pos_of(i, 0);
         uint64_t bar = a.gene_bar[i];                // index+1 of the last inserted tid-0 gene entry before i (inclusive scan, own value 0)
@@ -189,34 +200,45 @@ __global__ void sum_phase4_kernel(SummaryArgs a)
         }
         cg = first;
     }
-    for (int j = 0; j < e.n - 1; ++j) {
+    for (int j = gl; j < e.n - 1; j += SG) {
         uint8_t x = f[j];
         if (x & LRB_F_NOVEL_DON) cd += a.tab.slots[tab_find(a.tab, key_hi(SET_D, sd, e.t_tid), key_lo(ent_e(a, e, j), 0))].minpos == pos_of(i, j);
         if (x & LRB_F_NOVEL_ACC) ca += a.tab.slots[tab_find(a.tab, key_hi(SET_A, sa, e.t_tid), key_lo(ent_s(a, e, j + 1), 0))].minpos == pos_of(i, j);
         if (x & LRB_F_NOVEL_JUNC) cj += a.tab.slots[tab_find(a.tab, key_hi(SET_J, sj, e.t_tid), key_lo(ent_e(a, e, j), ent_s(a, e, j + 1)))].minpos == pos_of(i, j);
     }
-    if (cd) atomicAdd(&a.counts[SET_D], cd);
-    if (ca) atomicAdd(&a.counts[SET_A], ca);
-    if (cj) atomicAdd(&a.counts[SET_J], cj);
-    if (cg) atomicAdd(&a.counts[SET_G], cg);
+    cd = group_sum<SG>(gm, cd); ca = group_sum<SG>(gm, ca); cj = group_sum<SG>(gm, cj);
+    if (gl != 0) return;
+    if (cd) atomicAdd(&a.counts[SET_D], (uint32_t)cd);
+    if (ca) atomicAdd(&a.counts[SET_A], (uint32_t)ca);
+    if (cj) atomicAdd(&a.counts[SET_J], (uint32_t)cj);
+    if (cg) atomicAdd(&a.counts[SET_G], (uint32_t)cg);
 }
 
-// BED rows: first occurrences of the exon set in stream order (bed_off = exclusive scan of bed_cnt)
+// BED rows: first occurrences of the exon set in stream order (bed_off = exclusive scan of bed_cnt); the lanes of an
+// entry rank their rows by exon index with a ballot per round of SG exons
 __global__ void sum_bed_kernel(SummaryArgs a)
 {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n_upd || a.bed_cnt[i] == 0) return;
+    SUM_ENTRY_PROLOGUE(a.n_upd)
+    if (a.bed_cnt[i] == 0) return;
     EntryView e = load_entry(a, i);
     const uint8_t *f = a.ex.flag + e.gbeg;
     uint32_t o = a.bed_off[i];
-    for (int j = 0; j < e.n; ++j) {
-        if (!(f[j] & LRB_F_NOVEL_EXON)) continue;
-        int s0 = ent_s(a, e, j), e0 = ent_e(a, e, j);
-        uint64_t s = tab_find(a.tab, key_hi(SET_E, 0, e.real_tid), key_lo(s0, e0));
-        if (a.tab.slots[s].minpos != pos_of(i, j)) continue;
-        a.bed_tid[o] = e.real_tid; a.bed_start[o] = s0; a.bed_end[o] = e0; a.bed_score[o] = a.tab.slots[s].score + 1;            // the table is filled with 0xFF: scores start at -1
-        a.bed_type[o] = e.n > 1 ? ((j == 0 || j == e.n - 1) ? 0 : 1) : 2; a.bed_rev[o] = (uint8_t)e.rev;
-        ++o;
+    const int sh = (lane_id() / SG) * SG;
+    for (int j0 = 0; j0 < e.n; j0 += SG) {
+        const int j = j0 + gl;
+        bool first = false; int s0 = 0, e0 = 0; uint64_t s = 0;
+        if (j < e.n && (f[j] & LRB_F_NOVEL_EXON)) {
+            s0 = ent_s(a, e, j); e0 = ent_e(a, e, j);
+            s = tab_find(a.tab, key_hi(SET_E, 0, e.real_tid), key_lo(s0, e0));
+            first = a.tab.slots[s].minpos == pos_of(i, j);
+        }
+        const unsigned b = (__ballot_sync(gm, first) >> sh) & lane_bits<SG>();
+        if (first) {
+            const uint32_t k = o + __popc(b & ((1u << gl) - 1u));
+            a.bed_tid[k] = e.real_tid; a.bed_start[k] = s0; a.bed_end[k] = e0; a.bed_score[k] = a.tab.slots[s].score + 1;        // the table is filled with 0xFF: scores start at -1
+            a.bed_type[k] = e.n > 1 ? ((j == 0 || j == e.n - 1) ? 0 : 1) : 2; a.bed_rev[k] = (uint8_t)e.rev;
+        }
+        o += __popc(b);
     }
 }
 
@@ -280,31 +302,32 @@ __global__ void sum_known_genes_kernel(SummaryArgs a, const uint32_t *__restrict
 }
 
 static inline unsigned nblk(int64_t n) { return (unsigned)((n + 255) / 256); }
+static inline unsigned nblk_g(int64_t n) { return (unsigned)((n * SG + 255) / 256); }       // SG lanes per entry
 
 void launch_summary_count(const SummaryArgs &a, unsigned long long *n_elems, cudaStream_t st)
 {
     if (a.n_upd <= 0) return;
-    sum_count_kernel<<<nblk(a.n_upd), 256, 0, st>>>(a, n_elems); LRB_COUNT_LAUNCH();
+    sum_count_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a, n_elems); LRB_COUNT_LAUNCH();
 }
 // tile_state: 6 * (n_upd / 2048 + 1) words; tickets: 6 words (zeroed here)
 void launch_summary_sets(const SummaryArgs &a, const uint32_t *cls, int64_t n_rows, uint64_t *tile_state, uint32_t *tickets, uint64_t *bed_total, cudaStream_t st)
 {
     if (n_rows > 0) { sum_known_genes_kernel<<<nblk(n_rows), 256, 0, st>>>(a, cls, n_rows, 0); LRB_COUNT_LAUNCH(); }
     if (a.n_upd > 0) {
-        sum_phase1_kernel<<<nblk(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
-        sum_phase2_kernel<<<nblk(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
+        sum_phase1_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
+        sum_phase2_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
         const int n_tiles = (int)((a.n_upd + MS_THREADS * MS_ITEMS - 1) / (MS_THREADS * MS_ITEMS));
         cudaMemsetAsync(tile_state, 0, (size_t)n_tiles * 6 * 8, st); cudaMemsetAsync(tickets, 0, 6 * 4, st);
         sum_scans_kernel<<<dim3((unsigned)n_tiles, 6), MS_THREADS, 0, st>>>(a, tile_state, tickets, n_tiles, bed_total); LRB_COUNT_LAUNCH();
-        sum_phase3_kernel<<<nblk(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
-        sum_phase4_kernel<<<nblk(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
+        sum_phase3_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
+        sum_phase4_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
     } else cudaMemsetAsync(bed_total, 0, 8, st);
     if (n_rows > 0) { sum_known_genes_kernel<<<nblk(n_rows), 256, 0, st>>>(a, cls, n_rows, 1); LRB_COUNT_LAUNCH(); }
 }
 void launch_summary_bed(const SummaryArgs &a, cudaStream_t st)
 {
     if (a.n_upd <= 0) return;
-    sum_bed_kernel<<<nblk(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
+    sum_bed_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
 }
 
 }  // namespace lrbk

@@ -5,8 +5,7 @@ mkdir -p gpurun_out
 nvidia-smi -L
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/pytest_gpu.log; cat gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
-( TAG=default python profiles/tune.py 1000000; TAG=side0 LRB_SIDE_STREAM=0 python profiles/tune.py 1000000;
-  TAG=occ12 LRB_CR_OCC=12 python profiles/tune.py 1000000; TAG=occ16 LRB_CR_OCC=16 python profiles/tune.py 1000000 ) > gpurun_out/tune.txt 2>&1; cat gpurun_out/tune.txt
+( TAG=default python profiles/tune.py 1000000; for v in $TUNE_VARIANTS; do env TAG=$v $v python profiles/tune.py 1000000; done ) > gpurun_out/tune.txt 2>&1; cat gpurun_out/tune.txt
 [ "$1" = quick ] && exit 0
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/launches.csv python profiles/run_step.py 1000000 3 > gpurun_out/launch.log 2>&1; tail -2 gpurun_out/launch.log
 python profiles/launch_table.py gpurun_out/launches.csv > gpurun_out/launch_table.txt; cat gpurun_out/launch_table.txt

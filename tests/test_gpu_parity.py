@@ -205,6 +205,38 @@ def test_edge_cases(ctx, data):
     assert_dict_equal(g, o)
 
 
+def test_random_cigars(ctx, data):
+    """Arbitrary op sequences (adjacent cuts, leading / trailing N and D, empty exons, clips in odd places): the CIGAR
+    walk and the filter statistics against the oracle, thread mode (short) and warp mode (long)."""
+    ctx.set_rm(None)
+    rng = np.random.default_rng(11)
+    fp = cabi.FilterParams.default()
+    for lo, hi, n in ((1, 24, 3000), (60, 400, 300)):
+        cigs = []
+        for _ in range(n):
+            k = int(rng.integers(lo, hi))
+            ops = rng.choice([0, 0, 0, 1, 2, 2, 3, 3, 3, 4, 7, 8], size=k)
+            lens = np.where(rng.random(k) < 0.3, rng.integers(0, 6, k), rng.integers(1, 400, k))
+            cigs.append(((lens.astype(np.uint32) << 4) | ops.astype(np.uint32)).tolist())
+        rds = synth.Reads()
+        rds.tid = np.zeros(n, np.int32); rds.pos = np.sort(rng.integers(0, 1_000_000, n)).astype(np.int32)
+        rds.flag = rng.choice([0, 16], size=n).astype(np.uint16); rds.nm = rng.integers(0, 10, n).astype(np.int32)
+        rds.xs = rng.choice([0, ord('+'), ord('-')], size=n).astype(np.int8)
+        rds.l_qseq = np.array([max(1, sum((x >> 4) for x in c if (x & 15) in (0, 1, 4, 7, 8))) for c in cigs], np.int32)
+        rds.qid = np.arange(n); rds.qname_hash = synth.splitmix64(np.arange(n))
+        rds.cigar = np.array(sum(cigs, []), np.uint32); rds.cigar_off = np.cumsum([0] + [len(c) for c in cigs]).astype(np.uint32)
+        for e in (cabi.ExonParams.default(), cabi.ExonParams.default(min_exon=0, min_intron=0, max_delet=0), cabi.ExonParams.default(min_exon=30, min_intron=3, max_delet=2)):
+            g = ctx.bam2gtf(rds.soa(), e); o = op.bam2gtf(rds.soa(), e); g["read_idx"] = None
+            assert_dict_equal(g, o)
+        assert_dict_equal(filter_valid(ctx.filter(rds.soa(), fp)), filter_valid(op.filter(rds.soa(), None, fp)))
+        # fused filter + walk: the chains of the kept records
+        ctx.upload(rds.soa()); ctx.pipeline_run(fp, cabi.ExonParams.default())
+        keep = ctx.filter_fetch()["keep_idx"]
+        g = ctx.exon_fetch(); o = op.bam2gtf(rds.take(keep).soa(), cabi.ExonParams.default())
+        for k in ("exon_off", "exon_start", "exon_end", "is_rev"):
+            assert np.array_equal(g[k], o[k]), k
+
+
 def test_shard_invariance(ctx, data):
     """cutting the read stream at locus gaps and processing shards independently reproduces the unsharded
     result (the multi-GPU decomposition).  Checked here on one GPU, shard after shard."""

@@ -178,7 +178,7 @@ int run_scan(lrb_ctx *c, int mode, const lrb_filter_params *fp, const lrb_exon_p
     const bool warp_mode = avg > 48.0;
     int R = 256;
     if (warp_mode) { R = (int)(4096.0 / avg); R = std::max(8, std::min(256, R)); }
-    int stage_words = (int)(R * avg * 1.6) + 512; stage_words = (stage_words + 255) & ~255; stage_words = std::max(2048, std::min(12288, stage_words));
+    int stage_words = (int)(R * avg * (warp_mode ? 1.6 : 1.3)) + (warp_mode ? 512 : 256); stage_words = (stage_words + 255) & ~255; stage_words = std::max(2048, std::min(12288, stage_words));
     const int n_tiles = (int)((n + R - 1) / R);
     if (mode != 0) {
         int64_t bound = c->b.n_cigar + n + 16, est = c->b.n_cigar / 2 + n + 4096;
@@ -192,7 +192,7 @@ int run_scan(lrb_ctx *c, int mode, const lrb_filter_params *fp, const lrb_exon_p
         a.reads_per_tile = R; a.stage_words = stage_words; a.rows_by_record = by_record ? 1 : 0;
         CK(cudaMemsetAsync(c->tile_state.p, 0, (size_t)n_tiles * 8, c->st));
         CK(cudaMemsetAsync(c->scalars.p, 0, 8 * 8, c->st)); CK(cudaMemsetAsync(d_ticket(c), 0, 4, c->st));
-        size_t smem = (size_t)stage_words * 4 + (size_t)3072 * 8;
+        size_t smem = (size_t)stage_words * 4 + (warp_mode ? (size_t)3072 * 8 : 0);   // exon staging only in warp mode
         tick(c, 8);
         launch_cigar_scan(a, n_tiles, warp_mode, smem, c->st);
         tick(c, 9);

@@ -255,7 +255,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) cigar_scan_kernel(ScanArgs a)
     if (!do_exon || ex_total == 0) return;
 
     // ---- walk 2: emit exons (into the shared staging buffer when the tile fits, else straight to HBM)
-    const bool ex_staged = ex_total <= (uint32_t)EX_STAGE;
+    // warp mode stages the exons of the tile and writes them out coalesced; thread mode moves each read's parked exons
+    // straight to the pools (one staging buffer less: 6 instead of 4 resident CTAs per SM cover the look-back waits)
+    const bool ex_staged = WARP_MODE && ex_total <= (uint32_t)EX_STAGE;
     s_cnt[tid] = (int)ex_excl;                                   // reuse as local exon offset (own slot only)
     __syncthreads();
     const bool room = (int64_t)ex_base + ex_total <= a.ex.cap;   // host re-runs with a larger pool otherwise

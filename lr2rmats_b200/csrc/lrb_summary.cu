@@ -77,7 +77,7 @@ enum { SET_E = 0, SET_D = 1, SET_A = 2, SET_J = 3, SET_G = 4, SET_KG = 5 };
 // Every pass below runs SG lanes per updated entry: lane l takes the exons l, l + SG, ... of the entry, so the dependent
 // chain of table operations per thread is one or two elements long instead of the whole exon list (the passes are bound
 // by the latency of those chains, not by bandwidth), and the lanes' counts are folded with group shuffles.
-static constexpr int SG = 8;
+static constexpr int SG = 1;    // measured on B200: 8 lanes per entry is SLOWER (the passes are bound by the entry gathers and the random table sectors, not by the chain length)
 #define SUM_ENTRY_PROLOGUE(n_limit)                                                                  \
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / SG;                         \
     const int gl = threadIdx.x % SG;                                                                 \

@@ -11,6 +11,7 @@
 // makes every read independent; the order-dependent merge fold is exact per locus (App. A.6/B.3) and loci run in
 // parallel, one warp each, the warp evaluating a whole window of the back-scan per step.
 #include <cstdlib>
+#include <climits>
 #include "lrb_common.cuh"
 #include "lrb_kernels.cuh"
 
@@ -288,8 +289,7 @@ __global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a, const
 // replaces the reference's three nested loops; the four per-exon flag arrays live in four 32-bit registers.
 static constexpr int CR_THREADS = 128;
 
-template <int MINB>
-__global__ void __launch_bounds__(CR_THREADS, MINB) classify_row_kernel(ClassArgs a, uint8_t *__restrict__ slow, const uint8_t *__restrict__ row_nonmono)
+__global__ void __launch_bounds__(CR_THREADS) classify_row_kernel(ClassArgs a, uint8_t *__restrict__ slow, const uint8_t *__restrict__ row_nonmono)
 {
     __shared__ int s_win[6];
     const int t = threadIdx.x;
@@ -364,9 +364,20 @@ __global__ void __launch_bounds__(CR_THREADS, MINB) classify_row_kernel(ClassArg
             const int os = max(start_b, as_), oe = min(end_b, ae_);
             int ovl = 0, iden = 0, ps = 0, pe = 0, bs = b0s, be = b0e;
             for (int j = 0; j < n; ++j) {
-                while (ps < na && xs[ps] < bs) ++ps;
-                while (pe < na && xe[pe] < be) ++pe;
-                const bool hit_s = ps < na && xs[ps] == bs, hit_e = pe < na && xe[pe] == be;
+                // advance both cursors to the first annotation start >= bs / end >= be.  The usual step is 0..2 exons: the two
+                // next values of each list are fetched together (four independent loads, one latency) and the cursors move by
+                // selects; only a longer jump (the skipped prefix of a truncated read) walks
+                int s0 = ps < na ? xs[ps] : INT_MAX, s1 = ps + 1 < na ? xs[ps + 1] : INT_MAX;
+                int e0 = pe < na ? xe[pe] : INT_MAX, e1 = pe + 1 < na ? xe[pe + 1] : INT_MAX;
+                if (s0 < bs) {
+                    ++ps; s0 = s1;
+                    if (s0 < bs) { ++ps; s0 = INT_MAX; while (ps < na && (s0 = xs[ps]) < bs) { ++ps; s0 = INT_MAX; } }
+                }
+                if (e0 < be) {
+                    ++pe; e0 = e1;
+                    if (e0 < be) { ++pe; e0 = INT_MAX; while (pe < na && (e0 = xe[pe]) < be) { ++pe; e0 = INT_MAX; } }
+                }
+                const bool hit_s = s0 == bs, hit_e = e0 == be;
                 const uint32_t bit = 1u << j;
                 if (hit_s && hit_e && ps == pe) c_exon |= bit;
                 if (j < n - 1) {
@@ -479,14 +490,11 @@ template <int G, int SLOTS> static void launch_classify_t(const ClassArgs &a, co
 void launch_classify(const ClassArgs &a, uint8_t *slow, cudaStream_t st)
 {
     if (a.rows.n <= 0) return;
-    static int g = -1, fast = -1, occ = 9;
-    if (g < 0) { const char *e = getenv("LRB_CLASSIFY_G"); g = e ? atoi(e) : 4; e = getenv("LRB_CLASSIFY_FAST"); fast = e ? atoi(e) : 1; e = getenv("LRB_CR_OCC"); if (e) occ = atoi(e); }
+    static int g = -1, fast = -1;
+    if (g < 0) { const char *e = getenv("LRB_CLASSIFY_G"); g = e ? atoi(e) : 4; e = getenv("LRB_CLASSIFY_FAST"); fast = e ? atoi(e) : 1; }
     const uint8_t *only = nullptr;
     if (fast && a.up.ss_dis == 0 && slow) {
-        const unsigned bl = (unsigned)((a.rows.n + CR_THREADS - 1) / CR_THREADS);
-        if (occ >= 16) classify_row_kernel<16><<<bl, CR_THREADS, 0, st>>>(a, slow, a.row_nonmono);
-        else if (occ >= 12) classify_row_kernel<12><<<bl, CR_THREADS, 0, st>>>(a, slow, a.row_nonmono);
-        else classify_row_kernel<8><<<bl, CR_THREADS, 0, st>>>(a, slow, a.row_nonmono);
+        classify_row_kernel<<<(unsigned)((a.rows.n + CR_THREADS - 1) / CR_THREADS), CR_THREADS, 0, st>>>(a, slow, a.row_nonmono);
         LRB_COUNT_LAUNCH();
         only = slow;
     }
@@ -628,19 +636,16 @@ __global__ void __launch_bounds__(FP_THREADS) fold_prepare_kernel(MergeArgs a)
     const int64_t c0 = ((int64_t)tile * FP_THREADS + threadIdx.x) * FP_ITEMS;
     // locus segmentation first (cheap loads, two look-back chains): the per-exon work below then overlaps the chains of later tiles
     uint64_t key_end[FP_ITEMS], key_start[FP_ITEMS], run = 0;
-    uint32_t row[FP_ITEMS], gb[FP_ITEMS]; int n[FP_ITEMS], fs[FP_ITEMS], le[FP_ITEMS], rtid[FP_ITEMS]; bool piece[FP_ITEMS];
 #pragma unroll
     for (int i = 0; i < FP_ITEMS; ++i) {
-        key_end[i] = 0; key_start[i] = 0; row[i] = 0; gb[i] = 0; n[i] = 0; fs[i] = 0; le[i] = 0; rtid[i] = 0; piece[i] = false;
+        key_end[i] = 0; key_start[i] = 0;
         if (c0 + i < n_cand) {
             const int64_t c = c0 + i;
-            row[i] = a.list.row[c]; n[i] = (int)a.list.cnt[c];
-            gb[i] = a.rows.ex_beg[row[i]] + a.list.lo[c];
-            fs[i] = a.ex.es[gb[i]]; le[i] = a.ex.ee[gb[i] + n[i] - 1];
-            piece[i] = a.list.piece[c] >= 0;
-            rtid[i] = a.rows.tid[row[i]];
-            key_end[i] = ((uint64_t)(uint32_t)(rtid[i] + 1) << 32) | (uint32_t)le[i];     // real coordinates: locus segmentation
-            key_start[i] = ((uint64_t)(uint32_t)(rtid[i] + 1) << 32) | (uint32_t)fs[i];
+            const uint32_t rw = a.list.row[c]; const int ni = (int)a.list.cnt[c];
+            const uint32_t g = a.rows.ex_beg[rw] + a.list.lo[c];
+            const uint64_t tk = (uint64_t)(uint32_t)(a.rows.tid[rw] + 1) << 32;
+            key_end[i] = tk | (uint32_t)a.ex.ee[g + ni - 1];                               // real coordinates: locus segmentation
+            key_start[i] = tk | (uint32_t)a.ex.es[g];
         }
         run = key_end[i] > run ? key_end[i] : run;
     }
@@ -674,13 +679,19 @@ __global__ void __launch_bounds__(FP_THREADS) fold_prepare_kernel(MergeArgs a)
 #pragma unroll
     for (int i = 0; i < FP_ITEMS; ++i) if ((head >> i) & 1u) a.locus_start[ho++] = (uint32_t)(c0 + i);
     if (tile == a.n_tiles - 1 && threadIdx.x == 0) a.totals[0] = s_excl[1] + htot;
-    // flatten the candidates: trans-level fields, chain hash, junction signature
-#pragma unroll
+    // flatten the candidates: trans-level fields, chain hash, junction signature.  Striped over the tile (thread t takes the
+    // candidates t, t + 256, ...): the exon ranges of neighbouring threads are adjacent in the pools, so the per-exon loads of a
+    // warp fall into a few lines instead of one line per lane
+    const int64_t t0 = (int64_t)tile * FP_THREADS * FP_ITEMS;
+#pragma unroll 1
     for (int i = 0; i < FP_ITEMS; ++i) {
-        if (c0 + i >= n_cand) break;
-        const int64_t c = c0 + i;
-        const int ni = n[i]; const uint32_t g = gb[i];
-        a.cd.tid[c] = piece[i] ? 0 : rtid[i]; a.cd.start[c] = piece[i] ? 0 : fs[i]; a.cd.end[c] = piece[i] ? 0 : le[i];
+        const int64_t c = t0 + (int64_t)i * FP_THREADS + threadIdx.x;
+        if (c >= n_cand) break;
+        const uint32_t rw = a.list.row[c]; const int ni = (int)a.list.cnt[c];
+        const uint32_t g = a.rows.ex_beg[rw] + a.list.lo[c];
+        const int fsi = a.ex.es[g], lei = a.ex.ee[g + ni - 1], rt = a.rows.tid[rw];
+        const bool pc = a.list.piece[c] >= 0;
+        a.cd.tid[c] = pc ? 0 : rt; a.cd.start[c] = pc ? 0 : fsi; a.cd.end[c] = pc ? 0 : lei;
         int mono = 2;                               // bit 1: exon ends never decrease (always true for CIGAR chains)
         uint64_t h = 0x243F6A8885A308D3ull ^ (uint64_t)ni, sig = 0, j0 = 0;
         int prev_e = 0;
@@ -694,8 +705,8 @@ __global__ void __launch_bounds__(FP_THREADS) fold_prepare_kernel(MergeArgs a)
             if (j == 0) j0 = jk;
             sig |= 1ull << (junc_bit(jk));
         }
-        a.cd.rev[c] = (piece[i] ? 0 : a.rows.is_rev[row[i]]) | mono;
-        a.cd.n[c] = ni; a.cd.gbeg[c] = g; a.cd.fs[c] = fs[i]; a.cd.le[c] = le[i];
+        a.cd.rev[c] = (pc ? 0 : a.rows.is_rev[rw]) | mono;
+        a.cd.n[c] = ni; a.cd.gbeg[c] = g; a.cd.fs[c] = fsi; a.cd.le[c] = lei;
         a.cd.hash[c] = h; a.cd.j0[c] = j0; a.cd.sig[c] = sig;
     }
 }
@@ -953,6 +964,110 @@ __global__ void __launch_bounds__(256) fold_relasm_kernel(MergeArgs a, const uin
     if (a.kls) a.samemask[c] = same;
 }
 
+// The three relation passes above in ONE launch, on shared memory: a block owns FR_THREADS consecutive candidates and stages
+// their flattened fields together with a halo of the FF_MAX-1 candidates in front (a candidate deeper than that in its locus
+// is beyond the masks anyway), so the class search, the representative-pair relation and the mask assembly of a locus never
+// leave the SM; the exon pools are touched only to verify a class (once per member) and a signature hit.  Relations between
+// halo representatives are recomputed by the block that needs them instead of being exchanged through global atomics.
+static constexpr int FR_THREADS = 256, FR_HALO = FF_MAX - 1, FR_N = FR_THREADS + FR_HALO;
+__global__ void __launch_bounds__(FR_THREADS) fold_rel_kernel(MergeArgs a, uint32_t *__restrict__ rep, uint32_t *__restrict__ lstart,
+                                                              uint64_t *__restrict__ evmask, uint8_t *locus_hard)
+{
+    __shared__ uint64_t s_hash[FR_N], s_j0[FR_N], s_sig[FR_N];
+    __shared__ unsigned long long s_rel[FR_N];
+    __shared__ uint32_t s_gbeg[FR_N];
+    __shared__ int s_n[FR_N];
+    __shared__ int16_t s_ls[FR_N];                  // tile slot of the locus head; -1: out of reach (deeper than the masks, or not needed)
+    __shared__ uint16_t s_desc[FR_N];               // [0:5] class representative (locus-local), [6] single exon, [7] strand, [8:9] sub-stream
+    __shared__ uint8_t s_fl[FR_N];                  // bit 0 locus head, bit 1 strand, bit 2 monotone exon ends
+    const int64_t n_cand = cand_count(a);
+    const int64_t c0 = (int64_t)blockIdx.x * FR_THREADS;
+    if (c0 >= n_cand) return;
+    const int64_t base = c0 - FR_HALO;              // candidate of tile slot 0 (negative in the first block)
+    const CandSoA &cd = a.cd;
+    const bool force = a.up.force_strand != 0;
+    for (int i = threadIdx.x; i < FR_N; i += FR_THREADS) {
+        const int64_t c = base + i;
+        if (c >= 0 && c < n_cand) {
+            const int rv = cd.rev[c];
+            s_n[i] = cd.n[c]; s_hash[i] = cd.hash[c]; s_j0[i] = cd.j0[c]; s_sig[i] = cd.sig[c]; s_gbeg[i] = cd.gbeg[c];
+            s_fl[i] = (uint8_t)((a.head[c] ? 1 : 0) | ((rv & 1) << 1) | ((rv & 2) << 1));
+            s_desc[i] = (uint16_t)(a.kls ? ((uint32_t)a.kls[c] << 8) : 0u);
+        } else { s_n[i] = 0; s_fl[i] = 1; s_desc[i] = 0; s_hash[i] = 0; s_j0[i] = 0; s_sig[i] = 0; s_gbeg[i] = 0; }
+        s_rel[i] = 0ull; s_ls[i] = -1;
+    }
+    __syncthreads();
+    // ---- classes: first earlier candidate of the locus with the same (exon count, chain hash[, strand], sub-stream)
+    for (int i = threadIdx.x; i < FR_N; i += FR_THREADS) {
+        const int64_t c = base + i;
+        if (c < 0 || c >= n_cand) continue;
+        const int nc = s_n[i]; const uint64_t hc = s_hash[i]; const uint32_t kc = s_desc[i] & 0x300u; const int rvc = (s_fl[i] >> 1) & 1;
+        int e = i, r = i, steps = 0; bool reach = true;
+        while (!(s_fl[e] & 1)) {
+            if (++steps >= FF_MAX || e == 0) { reach = false; break; }
+            --e;
+            if (nc > 1 && s_n[e] == nc && s_hash[e] == hc && (!force || ((s_fl[e] >> 1) & 1) == rvc) && (s_desc[e] & 0x300u) == kc) r = e;
+        }
+        if (!reach) continue;
+        if (r != i && i >= FR_HALO) {                // own member of a class: verify it on the pools (the halo's were verified by their block)
+            const uint32_t gc = s_gbeg[i], gr = s_gbeg[r];
+            bool same = true;
+            for (int k = 0; k < nc - 1; ++k) same = same && a.ex.ee[gc + k] == a.ex.ee[gr + k] && a.ex.es[gc + k + 1] == a.ex.es[gr + k + 1];
+            if (!same) locus_hard[base + e] = 1;
+        }
+        s_ls[i] = (int16_t)e;
+        s_desc[i] = (uint16_t)(kc | (uint32_t)(r - e) | (nc == 1 ? 64u : 0u) | ((uint32_t)rvc << 7));
+    }
+    __syncthreads();
+    // ---- partial-match relation between the class representatives of the loci that reach into the block's own range
+    const int first_ls = s_ls[FR_HALO] >= 0 ? s_ls[FR_HALO] : FR_HALO;
+    for (int i = threadIdx.x; i < FR_N; i += FR_THREADS) {
+        const int ls = s_ls[i];
+        if (ls < 0 || i < first_ls) continue;
+        const uint32_t d = s_desc[i];
+        if ((d & 64u) || (int)(d & 63u) != i - ls) continue;            // single exon, or not the representative of its class
+        const int nc = s_n[i]; const uint64_t sig_c = s_sig[i], j0_c = s_j0[i]; const uint32_t gb_c = s_gbeg[i]; const bool mono_c = (s_fl[i] & 4) != 0;
+        for (int e = ls; e < i; ++e) {
+            const uint32_t de = s_desc[e];
+            if ((de & 64u) || (int)(de & 63u) != e - ls || ((de ^ d) & 0x300u)) continue;
+            if (force && ((de ^ d) & 128u)) continue;
+            const int ne = s_n[e];
+            if (ne == nc) continue;
+            bool hit;
+            if (nc > ne) { const uint64_t j0_e = s_j0[e]; hit = ((sig_c >> junc_bit(j0_e)) & 1ull) && partial_static(a.ex, gb_c, nc, mono_c, j0_e, s_gbeg[e], ne); }
+            else hit = ((s_sig[e] >> junc_bit(j0_c)) & 1ull) && partial_static(a.ex, s_gbeg[e], ne, (s_fl[e] & 4) != 0, j0_c, gb_c, nc);
+            if (hit) { atomicOr(&s_rel[i], 1ull << (e - ls)); atomicOr(&s_rel[e], 1ull << (i - ls)); }
+        }
+    }
+    __syncthreads();
+    // ---- own candidates: the earlier entries of the locus that could absorb them (and, for class folds, those of their sub-stream)
+    {
+        const int i = FR_HALO + threadIdx.x; const int64_t c = base + i;
+        if (c >= n_cand) return;
+        const int ls = s_ls[i];
+        if (ls < 0) { lstart[c] = FF_BIG; rep[c] = (uint32_t)c; return; }
+        const uint32_t d = s_desc[i];
+        uint64_t mask = 0, same = 0;
+        if (d & 64u) {
+            for (int e = ls; e < i; ++e) {
+                const uint32_t de = s_desc[e]; const uint64_t bit = 1ull << (e - ls);
+                if (!((de ^ d) & 0x300u)) { same |= bit; if ((de & 64u) && !(force && ((de ^ d) & 128u))) mask |= bit; }
+            }
+        } else {
+            const uint32_t r = d & 63u;
+            const uint64_t rel = s_rel[ls + r] | (1ull << r);
+            for (int e = ls; e < i; ++e) {
+                const uint32_t de = s_desc[e]; const uint64_t bit = 1ull << (e - ls);
+                if (!((de ^ d) & 0x300u)) same |= bit;
+                if (!(de & 64u) && ((rel >> (de & 63u)) & 1ull)) mask |= bit;
+            }
+        }
+        rep[c] = (uint32_t)(base + ls + (d & 63u)); lstart[c] = (uint32_t)(base + ls);
+        evmask[c] = mask;
+        if (a.kls) a.samemask[c] = same;
+    }
+}
+
 // thread per locus.  The entries of T (the survivors so far) live in shared-memory slots in insertion order -- the back-scan
 // of merge_trans is a walk down the slots; a locus with more than FS_SLOTS survivors is handed to merge_fold_kernel.
 // A slot keeps exon[0].start / exon[last].end; T.start / T.end equal them except for a split piece that was not extended
@@ -1069,9 +1184,14 @@ void launch_merge_fold(const MergeArgs &a, cudaStream_t st)
     if (flat && a.up.ss_dis == 0) {
         cudaMemsetAsync(a.hard, 0, (size_t)a.n_cand, st);
         const unsigned bl = (unsigned)((a.n_cand + 255) / 256);
-        fold_rep_kernel<<<bl, 256, 0, st>>>(a, a.rep, a.lstart, a.hard); LRB_COUNT_LAUNCH();
-        fold_relrep_kernel<<<bl, 256, 0, st>>>(a, a.lstart); LRB_COUNT_LAUNCH();
-        fold_relasm_kernel<<<bl, 256, 0, st>>>(a, a.lstart, a.evmask); LRB_COUNT_LAUNCH();
+        static int fused = -1;
+        if (fused < 0) { const char *e = getenv("LRB_FOLD_FUSED"); fused = e ? atoi(e) : 1; }
+        if (fused) { fold_rel_kernel<<<bl, FR_THREADS, 0, st>>>(a, a.rep, a.lstart, a.evmask, a.hard); LRB_COUNT_LAUNCH(); }
+        else {
+            fold_rep_kernel<<<bl, 256, 0, st>>>(a, a.rep, a.lstart, a.hard); LRB_COUNT_LAUNCH();
+            fold_relrep_kernel<<<bl, 256, 0, st>>>(a, a.lstart); LRB_COUNT_LAUNCH();
+            fold_relasm_kernel<<<bl, 256, 0, st>>>(a, a.lstart, a.evmask); LRB_COUNT_LAUNCH();
+        }
         fold_seq_kernel<<<(unsigned)((a.n_cand + FS_THREADS - 1) / FS_THREADS), FS_THREADS, 0, st>>>(a, a.rep, a.evmask, a.hard, a.dropped); LRB_COUNT_LAUNCH();
         // loci beyond the masks, and the (hash-collision) hard ones
         int64_t bl2 = (a.n_cand / (FF_MAX + 1) + 1 + 3) / 4 + 8; if (bl2 > 148 * 8) bl2 = 148 * 8;

@@ -363,6 +363,16 @@ __global__ void __launch_bounds__(CR_THREADS) classify_row_kernel(ClassArgs a, u
         } else if (n > 1 && na > 1) {                                                           // check_splice_site :717-779, exact matching
             const int os = max(start_b, as_), oe = min(end_b, ae_);
             int ovl = 0, iden = 0, ps = 0, pe = 0, bs = b0s, be = b0e;
+            {   // both cursors jump over the transcript's exons in front of the read (the skipped prefix of a 5'-truncated read)
+                // by one paired binary search; its trip count depends on na only, so the lanes sweeping this transcript stay converged
+                int ls = na, le = na;
+                while (ls | le) {
+                    const int hs = ls >> 1, he = le >> 1;
+                    const int vs = ls ? xs[ps + hs] : INT_MAX, ve = le ? xe[pe + he] : INT_MAX;
+                    if (vs < bs) { ps += hs + 1; ls -= hs + 1; } else ls = hs;
+                    if (ve < be) { pe += he + 1; le -= he + 1; } else le = he;
+                }
+            }
             for (int j = 0; j < n; ++j) {
                 // advance both cursors to the first annotation start >= bs / end >= be.  The usual step is 0..2 exons: the two
                 // next values of each list are fetched together (four independent loads, one latency) and the cursors move by
@@ -1185,7 +1195,7 @@ void launch_merge_fold(const MergeArgs &a, cudaStream_t st)
         cudaMemsetAsync(a.hard, 0, (size_t)a.n_cand, st);
         const unsigned bl = (unsigned)((a.n_cand + 255) / 256);
         static int fused = -1;
-        if (fused < 0) { const char *e = getenv("LRB_FOLD_FUSED"); fused = e ? atoi(e) : 1; }
+        if (fused < 0) { const char *e = getenv("LRB_FOLD_FUSED"); fused = e ? atoi(e) : 0; }
         if (fused) { fold_rel_kernel<<<bl, FR_THREADS, 0, st>>>(a, a.rep, a.lstart, a.evmask, a.hard); LRB_COUNT_LAUNCH(); }
         else {
             fold_rep_kernel<<<bl, 256, 0, st>>>(a, a.rep, a.lstart, a.hard); LRB_COUNT_LAUNCH();

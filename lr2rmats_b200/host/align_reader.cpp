@@ -9,10 +9,48 @@
 #include <cerrno>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <thread>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 #include "lrb_host.h"
 
 namespace lrb {
+
+// ---- host threads (the reference decodes on one thread; htslib's own answer is hts_set_threads, hts.c:969)
+// LRB_THREADS=n overrides; 1 gives the purely sequential code paths below.
+int host_threads()
+{
+    static int n = 0;
+    if (!n) {
+        const char *e = getenv("LRB_THREADS");
+        n = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+        if (n < 1) n = 1;
+        if (n > 64) n = 64;
+    }
+    return n;
+}
+// LRB_IO_TRACE=1: stage timings of the decoders on stderr
+struct IoTrace {
+    bool on = getenv("LRB_IO_TRACE") != nullptr; std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char *what) { if (!on) return; auto n = std::chrono::steady_clock::now(); fprintf(stderr, "[lrb io] %-14s %.3f s\n", what, std::chrono::duration<double>(n - t).count()); t = n; }
+};
+// fn(i) for i in [0, n) on up to host_threads() threads (dynamic, one index at a time: the work items are coarse)
+void parallel_for(size_t n, const std::function<void(size_t)> &fn)
+{
+    size_t nt = (size_t)host_threads(); if (nt > n) nt = n;
+    if (nt <= 1) { for (size_t i = 0; i < n; ++i) fn(i); return; }
+    std::atomic<size_t> next{0};
+    auto work = [&] { for (size_t i; (i = next.fetch_add(1)) < n;) fn(i); };
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < nt; ++t) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+}
 
 uint64_t hash_name(const char *s, size_t n)
 {
@@ -39,8 +77,26 @@ lrb_batch Records::view() const
     return b;
 }
 
-static bool slurp(const std::string &path, std::vector<uint8_t> &buf, std::string &err)
+static bool slurp(const std::string &path, Bytes &buf, std::string &err)
 {
+    if (path != "-") {                                                 // regular file: sized once, read by all threads (pread)
+        int fd = open(path.c_str(), O_RDONLY);
+        if (fd < 0) { err = "Cannot open \"" + path + "\""; return false; }
+        struct stat st;
+        if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+            const size_t n = (size_t)st.st_size, CH = 8u << 20, nch = (n + CH - 1) / CH;
+            buf.reserve(n + 1); buf.resize(n);                          // one spare byte: parse_sam terminates the last line in place
+            std::atomic<bool> bad{false};
+            parallel_for(nch, [&](size_t k) {
+                size_t o = k * CH, e = o + CH < n ? o + CH : n;
+                while (o < e) { ssize_t g = pread(fd, buf.data() + o, e - o, (off_t)o); if (g <= 0) { bad = true; return; } o += (size_t)g; }
+            });
+            close(fd);
+            if (bad) { err = "Cannot read \"" + path + "\""; return false; }
+            return true;
+        }
+        close(fd);
+    }
     FILE *fp = (path == "-") ? stdin : fopen(path.c_str(), "rb");
     if (!fp) { err = "Cannot open \"" + path + "\""; return false; }
     size_t cap = 1 << 20, n = 0;
@@ -57,7 +113,7 @@ static bool slurp(const std::string &path, std::vector<uint8_t> &buf, std::strin
 }
 
 // concatenated gzip members (BGZF blocks are gzip members, bgzf.c) -> one buffer
-static bool gunzip_all(const std::vector<uint8_t> &in, std::vector<uint8_t> &out, std::string &err)
+static bool gunzip_all(const Bytes &in, Bytes &out, std::string &err)
 {
     z_stream zs; memset(&zs, 0, sizeof zs);
     if (inflateInit2(&zs, 15 + 32) != Z_OK) { err = "zlib init failed"; return false; }
@@ -92,6 +148,60 @@ static bool gunzip_all(const std::vector<uint8_t> &in, std::vector<uint8_t> &out
 
 static inline uint32_t rd32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
 static inline int32_t rdi32(const uint8_t *p) { int32_t v; memcpy(&v, p, 4); return v; }
+
+// BGZF (bgzf.c block format): every block is a gzip member whose extra field carries 'BC' = block size - 1 and whose
+// trailer carries the inflated size, so the blocks can be located without inflating and inflated independently, straight
+// into their final place.  Returns false (out untouched) when the stream is not pure BGZF -- the caller then falls back
+// to the sequential gunzip_all.  A truncated or corrupt block ends the stream there (bgzf_read_block fails => sam_read1 < 0).
+struct BgzfBlock { size_t in_off, hdr, in_len; uint32_t isize; size_t out_off; };
+static bool bgzf_index(const Bytes &in, std::vector<BgzfBlock> &blocks)
+{
+    size_t p = 0, out = 0;
+    while (p < in.size()) {
+        if (in.size() - p < 18) break;                                   // truncated tail
+        const uint8_t *b = in.data() + p;
+        if (b[0] != 0x1f || b[1] != 0x8b || b[2] != 8 || !(b[3] & 4)) return false;
+        const size_t xlen = b[10] | ((size_t)b[11] << 8);
+        if (in.size() - p < 12 + xlen) break;
+        size_t bsize = 0;
+        for (size_t x = 0; x + 4 <= xlen;) {
+            const uint8_t *f = b + 12 + x; const size_t sl = f[2] | ((size_t)f[3] << 8);
+            if (f[0] == 'B' && f[1] == 'C' && sl == 2 && x + 6 <= xlen) bsize = (f[4] | ((size_t)f[5] << 8)) + 1;
+            x += 4 + sl;
+        }
+        if (!bsize) return false;                                        // a gzip member without BC: not BGZF
+        if (bsize < 12 + xlen + 8 || in.size() - p < bsize) break;       // truncated block
+        BgzfBlock k; k.in_off = p; k.hdr = 12 + xlen; k.in_len = bsize; k.isize = (uint32_t)b[bsize - 4] | ((uint32_t)b[bsize - 3] << 8) | ((uint32_t)b[bsize - 2] << 16) | ((uint32_t)b[bsize - 1] << 24);
+        k.out_off = out; out += k.isize;
+        blocks.push_back(k);
+        p += bsize;
+    }
+    return true;
+}
+static bool bgzf_inflate_mt(const Bytes &in, Bytes &out)
+{
+    std::vector<BgzfBlock> blocks;
+    if (!bgzf_index(in, blocks)) return false;
+    const size_t total = blocks.empty() ? 0 : blocks.back().out_off + blocks.back().isize;
+    out.reserve(total + 1); out.resize(total);
+    const size_t GRP = 64, ng = (blocks.size() + GRP - 1) / GRP;
+    std::atomic<size_t> first_bad{blocks.size()};
+    parallel_for(ng, [&](size_t g) {
+        z_stream zs; memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, -15) != Z_OK) { size_t b = g * GRP, cur = first_bad.load(); while (b < cur && !first_bad.compare_exchange_weak(cur, b)) {} return; }
+        for (size_t i = g * GRP; i < blocks.size() && i < (g + 1) * GRP; ++i) {
+            const BgzfBlock &k = blocks[i];
+            zs.next_in = (Bytef *)in.data() + k.in_off + k.hdr; zs.avail_in = (uInt)(k.in_len - k.hdr - 8);
+            zs.next_out = out.data() + k.out_off; zs.avail_out = k.isize;
+            const int rc = k.isize || zs.avail_in ? inflate(&zs, Z_FINISH) : Z_STREAM_END;
+            if (rc != Z_STREAM_END || zs.avail_out != 0) { size_t cur = first_bad.load(); while (i < cur && !first_bad.compare_exchange_weak(cur, i)) {} break; }
+            inflateReset(&zs);
+        }
+        inflateEnd(&zs);
+    });
+    if (first_bad.load() < blocks.size()) out.resize(blocks[first_bad.load()].out_off);
+    return true;
+}
 
 static void push_name(Records &r, const char *s, size_t n)
 {
@@ -144,7 +254,7 @@ static void scan_aux(const uint8_t *p, const uint8_t *end, int32_t &nm, int8_t &
     }
 }
 
-static bool parse_bam(const std::vector<uint8_t> &d, Header &h, Records &r, std::string &err)
+static bool parse_bam(Bytes &d, Header &h, Records &r, std::string &err)
 {
     const uint8_t *p = d.data(), *end = p + d.size();
     if (end - p < 12 || memcmp(p, "BAM\1", 4)) { err = "not a BAM stream"; return false; }
@@ -161,28 +271,63 @@ static bool parse_bam(const std::vector<uint8_t> &d, Header &h, Records &r, std:
         std::string name((const char *)p, l_name > 0 ? (size_t)l_name - 1 : 0); p += l_name;
         h.add(name, rd32(p)); p += 4;
     }
+    // pass 1 (sequential, touches 36 bytes per record): record boundaries, as sam_read1 would accept them
+    std::vector<const uint8_t *> recs;
     while (p + 4 <= end) {
         int32_t bs = rdi32(p);
         if (bs < 32 || p + 4 + bs > end) break;                        // truncated tail: sam_read1 < 0 ends the loop
         const uint8_t *c = p + 4;
-        int32_t tid = rdi32(c), pos = rdi32(c + 4);
-        uint32_t bmn = rd32(c + 8), fnc = rd32(c + 12);
-        int32_t l_seq = rdi32(c + 16);
-        uint32_t l_qname = bmn & 0xff, n_cigar = fnc & 0xffff;
-        const uint8_t *q = c + 32;
-        const uint8_t *cig = q + l_qname;
-        const uint8_t *aux = cig + 4 * (size_t)n_cigar + ((size_t)l_seq + 1) / 2 + (size_t)l_seq;
-        if (aux > p + 4 + bs) break;
-        r.tid.push_back(tid); r.pos.push_back(pos); r.flag.push_back((uint16_t)(fnc >> 16)); r.l_qseq.push_back(l_seq);
-        push_name(r, (const char *)q, l_qname ? strnlen((const char *)q, l_qname) : 0);
-        size_t co = r.cigar.size(); r.cigar.resize(co + n_cigar);
-        if (n_cigar) memcpy(r.cigar.data() + co, cig, 4 * (size_t)n_cigar);
-        r.cigar_off.push_back((uint32_t)r.cigar.size());
-        int32_t nm; int8_t xs; scan_aux(aux, p + 4 + bs, nm, xs);
-        r.nm.push_back(nm); r.xs.push_back(xs);
-        if (r.keep_raw) { r.raw.insert(r.raw.end(), p, p + 4 + bs); r.raw_off.push_back(r.raw.size()); }
+        const uint32_t l_qname = rd32(c + 8) & 0xff, n_cigar = rd32(c + 12) & 0xffff; const int32_t l_seq = rdi32(c + 16);
+        if (c + 32 + l_qname + 4 * (size_t)n_cigar + ((size_t)l_seq + 1) / 2 + (size_t)l_seq > p + 4 + bs) break;
+        recs.push_back(p);
         p += 4 + bs;
     }
+    // pass 2: chunks of records sized (names, CIGAR words, raw bytes) in parallel, placed by a prefix sum, filled in parallel
+    const size_t n = recs.size(), base = r.n();
+    const size_t CH = 16384, nch = (n + CH - 1) / CH;
+    std::vector<size_t> c_cig(nch + 1, 0), c_nam(nch + 1, 0), c_raw(nch + 1, 0);
+    parallel_for(nch, [&](size_t k) {
+        size_t cg = 0, nm = 0, rw = 0;
+        for (size_t i = k * CH; i < n && i < (k + 1) * CH; ++i) {
+            const uint8_t *c = recs[i] + 4;
+            const uint32_t l_qname = rd32(c + 8) & 0xff;
+            cg += rd32(c + 12) & 0xffff;
+            nm += (l_qname ? strnlen((const char *)c + 32, l_qname) : 0) + 1;
+            rw += 4 + (size_t)rdi32(recs[i]);
+        }
+        c_cig[k + 1] = cg; c_nam[k + 1] = nm; c_raw[k + 1] = rw;
+    });
+    for (size_t k = 0; k < nch; ++k) { c_cig[k + 1] += c_cig[k]; c_nam[k + 1] += c_nam[k]; c_raw[k + 1] += c_raw[k]; }
+    const size_t cig0 = r.cigar.size(), nam0 = r.names.size(), raw0 = r.raw.size();
+    r.tid.resize(base + n); r.pos.resize(base + n); r.flag.resize(base + n); r.l_qseq.resize(base + n); r.nm.resize(base + n); r.xs.resize(base + n);
+    r.qhash.resize(base + n); r.cigar_off.resize(base + n + 1); r.name_off.resize(base + n + 1);
+    r.cigar.resize(cig0 + c_cig[nch]); r.names.resize(nam0 + c_nam[nch]);
+    // raw record bodies (for `filter`'s re-emission): the inflated stream itself is adopted when it is the first input
+    const bool adopt = r.keep_raw && raw0 == 0 && base == 0;
+    if (r.keep_raw) { if (!adopt) r.raw.resize(raw0 + c_raw[nch]); r.raw_off.resize(base + n + 1); if (adopt && n) r.raw_off[0] = (uint64_t)(recs[0] - d.data()); }
+    parallel_for(nch, [&](size_t k) {
+        size_t cg = cig0 + c_cig[k], nm = nam0 + c_nam[k], rw = raw0 + c_raw[k];
+        for (size_t i = k * CH; i < n && i < (k + 1) * CH; ++i) {
+            const uint8_t *rp = recs[i], *c = rp + 4; const int32_t bs = rdi32(rp);
+            const uint32_t bmn = rd32(c + 8), fnc = rd32(c + 12);
+            const int32_t l_seq = rdi32(c + 16);
+            const uint32_t l_qname = bmn & 0xff, n_cigar = fnc & 0xffff;
+            const uint8_t *q = c + 32, *cig = q + l_qname;
+            const uint8_t *aux = cig + 4 * (size_t)n_cigar + ((size_t)l_seq + 1) / 2 + (size_t)l_seq;
+            const size_t j = base + i;
+            r.tid[j] = rdi32(c); r.pos[j] = rdi32(c + 4); r.flag[j] = (uint16_t)(fnc >> 16); r.l_qseq[j] = l_seq;
+            const size_t ln = l_qname ? strnlen((const char *)q, l_qname) : 0;
+            memcpy(r.names.data() + nm, q, ln); r.names[nm + ln] = 0; nm += ln + 1;
+            r.name_off[j + 1] = (uint32_t)nm; r.qhash[j] = hash_name((const char *)q, ln);
+            if (n_cigar) memcpy(r.cigar.data() + cg, cig, 4 * (size_t)n_cigar);
+            cg += n_cigar; r.cigar_off[j + 1] = (uint32_t)cg;
+            int32_t nmv; int8_t xs; scan_aux(aux, rp + 4 + bs, nmv, xs);
+            r.nm[j] = nmv; r.xs[j] = xs;
+            if (adopt) r.raw_off[j + 1] = (uint64_t)(rp - d.data()) + 4 + (size_t)bs;
+            else if (r.keep_raw) { memcpy(r.raw.data() + rw, rp, 4 + (size_t)bs); rw += 4 + (size_t)bs; r.raw_off[j + 1] = rw; }
+        }
+    });
+    if (adopt) r.raw = std::move(d);
     return true;
 }
 
@@ -197,7 +342,7 @@ static int reg2bin(int64_t beg, int64_t end)
 
 static const char *CIGAR_OPS = "MIDNSHP=XB";
 
-static void put32(std::vector<uint8_t> &v, uint32_t x) { uint8_t b[4]; memcpy(b, &x, 4); v.insert(v.end(), b, b + 4); }
+template <class V> static void put32(V &v, uint32_t x) { uint8_t b[4]; memcpy(b, &x, 4); v.insert(v.end(), b, b + 4); }
 
 static uint8_t nt16(char c)
 {
@@ -299,7 +444,7 @@ static bool parse_sam_line(char *line, size_t len, const Header &h, Records &r)
     push_name(r, f[0], lq);
     r.cigar_off.push_back((uint32_t)r.cigar.size());
     if (r.keep_raw) {
-        std::vector<uint8_t> &o = r.raw; size_t base = o.size();
+        Bytes &o = r.raw; size_t base = o.size();
         put32(o, 0);                                                   // block_size placeholder
         put32(o, (uint32_t)tid); put32(o, (uint32_t)pos);
         int64_t endpos = pos + ((flag & 4) ? 1 : (n_cigar ? rlen : 1));
@@ -325,63 +470,147 @@ static bool parse_sam_line(char *line, size_t len, const Header &h, Records &r)
     return true;
 }
 
-static bool parse_sam(std::vector<uint8_t> &d, Header &h, Records &r, std::string &err)
+static void sam_header_line(const char *p, size_t len, size_t raw_len, Header &h)
 {
-    char *p = (char *)d.data(), *end = p + d.size();
+    h.text.append(p, raw_len); h.text.push_back('\n');
+    if (len > 3 && !memcmp(p, "@SQ", 3)) {
+        std::string line(p, len), sn; uint32_t ln = 0;
+        size_t s = 0;
+        while (s < line.size()) {
+            size_t t = line.find('\t', s); if (t == std::string::npos) t = line.size();
+            if (t - s > 3 && !line.compare(s, 3, "SN:")) sn = line.substr(s + 3, t - s - 3);
+            else if (t - s > 3 && !line.compare(s, 3, "LN:")) ln = (uint32_t)strtoul(line.c_str() + s + 3, nullptr, 10);
+            s = t + 1;
+        }
+        if (!sn.empty()) h.add(sn, ln);
+    }
+}
+
+// Lines of [p, end) parsed in place (the byte behind every line is overwritten with NUL; end[0] must be writable).
+// hdr != nullptr: '@' lines are header lines wherever they stand (sequential mode).  Returns false at a malformed record.
+static bool parse_sam_range(char *p, char *end, const Header &h, Header *hdr, Records &r)
+{
     while (p < end) {
         char *nl = (char *)memchr(p, '\n', (size_t)(end - p));
         char *le = nl ? nl : end;
         size_t len = (size_t)(le - p);
         if (len && p[len - 1] == '\r') --len;
-        if (len && p[0] == '@') {
-            h.text.append(p, (size_t)(le - p)); h.text.push_back('\n');
-            if (len > 3 && !memcmp(p, "@SQ", 3)) {
-                std::string line(p, len), sn; uint32_t ln = 0;
-                size_t s = 0;
-                while (s < line.size()) {
-                    size_t t = line.find('\t', s); if (t == std::string::npos) t = line.size();
-                    if (t - s > 3 && !line.compare(s, 3, "SN:")) sn = line.substr(s + 3, t - s - 3);
-                    else if (t - s > 3 && !line.compare(s, 3, "LN:")) ln = (uint32_t)strtoul(line.c_str() + s + 3, nullptr, 10);
-                    s = t + 1;
-                }
-                if (!sn.empty()) h.add(sn, ln);
-            }
-        } else if (len) {
-            std::vector<char> tmp(p, p + len); tmp.push_back(0);
-            if (!parse_sam_line(tmp.data(), len, h, r)) {
-                fprintf(stderr, "[lr2rmats_b200] malformed SAM record at row %zu; input truncated here (sam_read1 < 0)\n", r.n());
-                break;
-            }
+        if (len && p[0] == '@' && hdr) sam_header_line(p, len, (size_t)(le - p), *hdr);
+        else if (len) {
+            p[len] = 0;
+            if (!parse_sam_line(p, len, h, r)) return false;
         }
         if (!nl) break;
         p = nl + 1;
     }
+    return true;
+}
+
+static void sam_malformed(size_t row) { fprintf(stderr, "[lr2rmats_b200] malformed SAM record at row %zu; input truncated here (sam_read1 < 0)\n", row); }
+
+static bool parse_sam(Bytes &d, Header &h, Records &r, std::string &err)
+{
     (void)err;
+    IoTrace tr;
+    d.push_back(0);                                                    // writable byte behind the last line
+    char *p = (char *)d.data(), *end = p + d.size() - 1;
+    // the header: leading '@' (and empty) lines, sequential
+    while (p < end) {
+        char *nl = (char *)memchr(p, '\n', (size_t)(end - p));
+        char *le = nl ? nl : end;
+        size_t len = (size_t)(le - p);
+        if (len && p[len - 1] == '\r') --len;
+        if (len && p[0] != '@') break;
+        if (len) sam_header_line(p, len, (size_t)(le - p), h);
+        if (!nl) { p = end; break; }
+        p = nl + 1;
+    }
+    const size_t body = (size_t)(end - p);
+    const int nt = host_threads();
+    bool at_inside = false;                                            // header lines inside the body?  (scanned by all threads)
+    if (nt > 1 && body >= (1u << 20)) {
+        static const char at[2] = {'\n', '@'};
+        const size_t SC = 16u << 20, nsc = (body + SC - 1) / SC;
+        std::atomic<bool> hit{false};
+        parallel_for(nsc, [&](size_t k) { const size_t o = k * SC, e = o + SC + 1 < body ? o + SC + 1 : body; if (memmem(p + o, e - o, at, 2)) hit = true; });
+        at_inside = hit;
+    }
+    if (nt <= 1 || body < (1u << 20) || at_inside) {                   // small, single thread, or header lines inside the body
+        if (!parse_sam_range(p, end, h, &h, r)) sam_malformed(r.n());
+        return true;
+    }
+    // the body: chunks cut at line ends, parsed into chunk-local batches in parallel, concatenated in order
+    size_t nch = (size_t)nt * 4; if (nch > body >> 18) nch = body >> 18; if (nch < 1) nch = 1;
+    std::vector<char *> cut(nch + 1, end);
+    cut[0] = p;
+    for (size_t k = 1; k < nch; ++k) {
+        char *q = p + body / nch * k; if (q < cut[k - 1]) q = cut[k - 1];
+        char *nl = (char *)memchr(q, '\n', (size_t)(end - q));
+        cut[k] = nl ? nl + 1 : end;
+    }
+    tr.lap(" sam header");
+    std::vector<Records> part(nch);
+    std::vector<uint8_t> ok(nch, 1);
+    parallel_for(nch, [&](size_t k) {
+        part[k].keep_raw = r.keep_raw;
+        ok[k] = parse_sam_range(cut[k], cut[k + 1], h, nullptr, part[k]);
+    });
+    tr.lap(" sam chunks");
+    size_t used = nch;
+    for (size_t k = 0; k < nch; ++k) if (!ok[k]) { used = k + 1; break; }
+    std::vector<size_t> b_rec(used + 1, r.n()), b_cig(used + 1, r.cigar.size()), b_nam(used + 1, r.names.size()), b_raw(used + 1, r.raw.size());
+    for (size_t k = 0; k < used; ++k) {
+        b_rec[k + 1] = b_rec[k] + part[k].n(); b_cig[k + 1] = b_cig[k] + part[k].cigar.size();
+        b_nam[k + 1] = b_nam[k] + part[k].names.size(); b_raw[k + 1] = b_raw[k] + part[k].raw.size();
+    }
+    const size_t nn = b_rec[used];
+    r.tid.resize(nn); r.pos.resize(nn); r.flag.resize(nn); r.l_qseq.resize(nn); r.nm.resize(nn); r.xs.resize(nn); r.qhash.resize(nn);
+    r.cigar_off.resize(nn + 1); r.name_off.resize(nn + 1); r.cigar.resize(b_cig[used]); r.names.resize(b_nam[used]);
+    if (r.keep_raw) { r.raw.resize(b_raw[used]); r.raw_off.resize(nn + 1); }
+    parallel_for(used, [&](size_t k) {
+        const Records &q = part[k]; const size_t m = q.n(), o = b_rec[k];
+        if (!m) return;
+        memcpy(r.tid.data() + o, q.tid.data(), m * 4); memcpy(r.pos.data() + o, q.pos.data(), m * 4); memcpy(r.flag.data() + o, q.flag.data(), m * 2);
+        memcpy(r.l_qseq.data() + o, q.l_qseq.data(), m * 4); memcpy(r.nm.data() + o, q.nm.data(), m * 4); memcpy(r.xs.data() + o, q.xs.data(), m);
+        memcpy(r.qhash.data() + o, q.qhash.data(), m * 8);
+        memcpy(r.cigar.data() + b_cig[k], q.cigar.data(), q.cigar.size() * 4); memcpy(r.names.data() + b_nam[k], q.names.data(), q.names.size());
+        for (size_t i = 0; i < m; ++i) { r.cigar_off[o + i + 1] = (uint32_t)(q.cigar_off[i + 1] + b_cig[k]); r.name_off[o + i + 1] = (uint32_t)(q.name_off[i + 1] + b_nam[k]); }
+        if (r.keep_raw) {
+            memcpy(r.raw.data() + b_raw[k], q.raw.data(), q.raw.size());
+            for (size_t i = 0; i < m; ++i) r.raw_off[o + i + 1] = q.raw_off[i + 1] + b_raw[k];
+        }
+    });
+    tr.lap(" sam merge");
+    if (!ok[used - 1]) sam_malformed(r.n());
     return true;
 }
 
 bool read_alignments(const std::string &path, Header &h, Records &r, std::string &err)
 {
-    std::vector<uint8_t> raw;
+    IoTrace tr;
+    Bytes raw;
     if (!slurp(path, raw, err)) return false;
+    tr.lap("read file");
+    bool ok;
     if (raw.size() >= 2 && raw[0] == 0x1f && raw[1] == 0x8b) {
-        std::vector<uint8_t> d;
-        if (!gunzip_all(raw, d, err)) return false;
+        Bytes d;
+        if (!bgzf_inflate_mt(raw, d) && !gunzip_all(raw, d, err)) return false;
         raw.clear(); raw.shrink_to_fit();
-        if (d.size() >= 4 && !memcmp(d.data(), "BAM\1", 4)) return parse_bam(d, h, r, err);
-        return parse_sam(d, h, r, err);
-    }
-    return parse_sam(raw, h, r, err);
+        tr.lap("inflate");
+        ok = (d.size() >= 4 && !memcmp(d.data(), "BAM\1", 4)) ? parse_bam(d, h, r, err) : parse_sam(d, h, r, err);
+    } else ok = parse_sam(raw, h, r, err);
+    tr.lap("parse");
+    return ok;
 }
 
 // ---- BGZF writer (64 KiB blocks, BC extra field, EOF marker), bgzf.c block format
-static void bgzf_block(FILE *out, const uint8_t *src, size_t n)
+// one block: src[0..n) -> dst (>= n + 1024 bytes); returns the block's length
+static size_t bgzf_block(uint8_t *buf, size_t cap, const uint8_t *src, size_t n)
 {
-    uint8_t buf[0x10000 + 1024];
     z_stream zs; memset(&zs, 0, sizeof zs);
     deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
     zs.next_in = (Bytef *)src; zs.avail_in = (uInt)n;
-    zs.next_out = buf + 18; zs.avail_out = sizeof buf - 18 - 8;
+    zs.next_out = buf + 18; zs.avail_out = (uInt)(cap - 18 - 8);
     deflate(&zs, Z_FINISH);
     size_t clen = zs.total_out; deflateEnd(&zs);
     static const uint8_t hdr[12] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0};
@@ -389,12 +618,13 @@ static void bgzf_block(FILE *out, const uint8_t *src, size_t n)
     uint16_t bsize = (uint16_t)(clen + 25); memcpy(buf + 16, &bsize, 2);
     uint32_t crc = (uint32_t)crc32(crc32(0L, nullptr, 0), src, (uInt)n), isz = (uint32_t)n;
     memcpy(buf + 18 + clen, &crc, 4); memcpy(buf + 22 + clen, &isz, 4);
-    fwrite(buf, 1, clen + 26, out);
+    return clen + 26;
 }
 
 bool write_bam(FILE *out, const Header &h, const Records &r, const uint32_t *idx, int64_t n, std::string &err)
 {
     if (!r.keep_raw) { err = "records were read without raw BAM bodies"; return false; }
+    const size_t BLK = 0xff00, CAP = 0x10000 + 1024;
     std::vector<uint8_t> s;
     s.insert(s.end(), {'B', 'A', 'M', 1});
     put32(s, (uint32_t)h.text.size()); s.insert(s.end(), h.text.begin(), h.text.end());
@@ -404,19 +634,34 @@ bool write_bam(FILE *out, const Header &h, const Records &r, const uint32_t *idx
         s.insert(s.end(), h.names[i].begin(), h.names[i].end()); s.push_back(0);
         put32(s, h.lens[i]);
     }
-    const size_t BLK = 0xff00;
-    auto flush = [&](bool all) {
-        size_t o = 0;
-        while (s.size() - o >= BLK || (all && o < s.size())) { size_t k = s.size() - o < BLK ? s.size() - o : BLK; bgzf_block(out, s.data() + o, k); o += k; }
-        s.erase(s.begin(), s.begin() + (long)o);
-    };
-    flush(true);                                                       // header in its own block(s), like bam_hdr_write + flush
-    for (int64_t k = 0; k < n; ++k) {
-        uint32_t i = idx[k];
-        s.insert(s.end(), r.raw.begin() + (long)r.raw_off[i], r.raw.begin() + (long)r.raw_off[i + 1]);
-        if (s.size() >= 4 * BLK) flush(false);
+    {   // header in its own block(s), like bam_hdr_write + flush
+        std::vector<uint8_t> buf(CAP);
+        for (size_t o = 0; o < s.size(); o += BLK) { size_t k = s.size() - o < BLK ? s.size() - o : BLK; fwrite(buf.data(), 1, bgzf_block(buf.data(), CAP, s.data() + o, k), out); }
     }
-    flush(true);
+    // the selected records form one byte stream cut into BLK-byte blocks; groups of blocks are gathered and deflated in
+    // parallel (a block finds its first record by binary search on the running record sizes) and written in order
+    std::vector<uint64_t> pre((size_t)n + 1, 0);
+    for (int64_t k = 0; k < n; ++k) pre[(size_t)k + 1] = pre[(size_t)k] + (r.raw_off[idx[k] + 1] - r.raw_off[idx[k]]);
+    const uint64_t total = pre[(size_t)n];
+    const size_t nblk = (size_t)((total + BLK - 1) / BLK), GRP = (size_t)host_threads() * 8;
+    std::vector<uint8_t> comp(GRP * CAP), plain(GRP * BLK);
+    std::vector<size_t> clen(GRP);
+    for (size_t b0 = 0; b0 < nblk; b0 += GRP) {
+        const size_t nb = nblk - b0 < GRP ? nblk - b0 : GRP;
+        parallel_for(nb, [&](size_t j) {
+            const uint64_t lo = (uint64_t)(b0 + j) * BLK, hi = lo + BLK < total ? lo + BLK : total;
+            uint8_t *dst = plain.data() + j * BLK;
+            size_t k = (size_t)(std::upper_bound(pre.begin(), pre.end(), lo) - pre.begin()) - 1;    // record holding byte lo
+            for (uint64_t at = lo; at < hi; ++k) {
+                const uint64_t r0 = r.raw_off[idx[k]], skip = at - pre[k], len = pre[k + 1] - pre[k];
+                const uint64_t take = len - skip < hi - at ? len - skip : hi - at;
+                memcpy(dst + (at - lo), r.raw.data() + r0 + skip, (size_t)take);
+                at += take;
+            }
+            clen[j] = bgzf_block(comp.data() + j * CAP, CAP, dst, (size_t)(hi - lo));
+        });
+        for (size_t j = 0; j < nb; ++j) fwrite(comp.data() + j * CAP, 1, clen[j], out);
+    }
     static const uint8_t eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     fwrite(eof, 1, 28, out);
     return true;

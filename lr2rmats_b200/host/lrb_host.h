@@ -11,6 +11,8 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <functional>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -28,6 +30,15 @@ struct Header {
     void add(const std::string &n, uint32_t len) { if (!index.count(n)) index[n] = (int)names.size(); names.push_back(n); lens.push_back(len); }
 };
 
+// byte buffer whose resize() leaves new bytes uninitialised: the large I/O buffers are first touched by the worker
+// threads that fill them (page faults in parallel) instead of being zero-filled by one thread
+template <class T> struct NoInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { using other = NoInitAlloc<U>; };
+    template <class U> void construct(U *p) noexcept { ::new ((void *)p) U; }
+    template <class U, class... A> void construct(U *p, A &&...a) { ::new ((void *)p) U(std::forward<A>(a)...); }
+};
+using Bytes = std::vector<uint8_t, NoInitAlloc<uint8_t>>;
+
 struct Records {
     std::vector<int32_t> tid, pos, l_qseq, nm;
     std::vector<uint16_t> flag;
@@ -38,13 +49,17 @@ struct Records {
     std::vector<char> names;                       // NUL-terminated qnames
     bool keep_raw = false;                         // keep BAM-encoded records for `filter` re-emission
     std::vector<uint64_t> raw_off{0};
-    std::vector<uint8_t> raw;                      // block_size-prefixed BAM records
+    Bytes raw;                                     // block_size-prefixed BAM records
     size_t n() const { return tid.size(); }
     const char *qname(size_t i) const { return names.data() + name_off[i]; }
     lrb_batch view() const;
 };
 
 uint64_t hash_name(const char *s, size_t n);
+
+// host threads used by the decoders / encoders / emitters (LRB_THREADS, default: every hardware thread) and the loop helper
+int host_threads();
+void parallel_for(size_t n, const std::function<void(size_t)> &fn);
 
 // Reads SAM text or BAM (BGZF) -- autodetected like sam_open(..., "rb").  Returns false and sets err on failure.
 bool read_alignments(const std::string &path, Header &h, Records &r, std::string &err);

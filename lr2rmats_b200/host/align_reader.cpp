@@ -11,7 +11,6 @@
 #include <cstring>
 #include <algorithm>
 #include <atomic>
-#include <chrono>
 #include <thread>
 #include <fcntl.h>
 #include <sys/stat.h>
@@ -34,11 +33,6 @@ int host_threads()
     }
     return n;
 }
-// LRB_IO_TRACE=1: stage timings of the decoders on stderr
-struct IoTrace {
-    bool on = getenv("LRB_IO_TRACE") != nullptr; std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
-    void lap(const char *what) { if (!on) return; auto n = std::chrono::steady_clock::now(); fprintf(stderr, "[lrb io] %-14s %.3f s\n", what, std::chrono::duration<double>(n - t).count()); t = n; }
-};
 // fn(i) for i in [0, n) on up to host_threads() threads (dynamic, one index at a time: the work items are coarse)
 void parallel_for(size_t n, const std::function<void(size_t)> &fn)
 {
@@ -111,6 +105,8 @@ static bool slurp(const std::string &path, Bytes &buf, std::string &err)
     if (fp != stdin) fclose(fp);
     return true;
 }
+
+bool read_file_bytes(const std::string &path, Bytes &buf) { std::string e; return path != "-" && slurp(path, buf, e); }
 
 // concatenated gzip members (BGZF blocks are gzip members, bgzf.c) -> one buffer
 static bool gunzip_all(const Bytes &in, Bytes &out, std::string &err)

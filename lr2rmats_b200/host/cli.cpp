@@ -227,6 +227,7 @@ static int cmd_update(int argc, char **argv, Engine &eng)
     up.want_summary = (summary_fp || bed_fp) ? 1 : 0;
 
     Header h; Records rec; Anno chains, anno; ChrNames cn; std::string err;
+    IoTrace tr;
     if (input_mode == 0) {
         if (!read_alignments(argv[optind], h, rec, err)) fatal("update_gtf", err);
     } else {
@@ -236,15 +237,19 @@ static int cmd_update(int argc, char **argv, Engine &eng)
         if (!read_gtf(argv[optind], h, chains, true, err)) fatal("read_gtf_trans", err);
     }
     cn.seed(h);
+    tr.lap("alignments");
     logf("read_anno_trans", (std::string("reading transcript annotation from ") + argv[optind + 1] + " ...\n").c_str());
     if (!read_gtf(argv[optind + 1], h, anno, false, err)) fatal("read_anno_trans", err);
+    tr.lap("annotation gtf");
     logf("read_anno_trans", (std::string("reading transcript annotation from ") + argv[optind + 1] + " done.\n").c_str());
     SjTable sj;
     if (!sj_fn.empty() && !read_sj(sj_fn, cn, sj, err)) fatal("update_gtf", err);
 
+    tr.lap("sj table");
     lrb_anno av = anno.view(); lrb_sj sv = sj.view();
     int rc = eng.set_tables(eng.self, &av, nullptr, sj.tid.empty() ? nullptr : &sv);
     if (rc) engine_fail(eng, "update_gtf", rc);
+    tr.lap("tables upload");
     lrb_batch b = rec.view(); lrb_chains ch = chains.chains();
     RowNames rn; if (input_mode == 0) rn.rec = &rec; else rn.chains = &chains;
     const bool per_read_outputs = bam_gtf_fp || detail_fp || known_fp || novel_fp || unrecog_fp;
@@ -252,16 +257,19 @@ static int cmd_update(int argc, char **argv, Engine &eng)
         lrb_trans_table tab{}; lrb_bed_list bed{}; int32_t counts[LRB_S_COUNT] = {0};
         rc = eng.update_table(eng.self, input_mode == 0 ? &b : nullptr, input_mode == 0 ? nullptr : &ch, &ep, &up, &tab, up.want_summary ? &bed : nullptr, counts);
         if (rc) engine_fail(eng, "update_gtf", rc);
+        tr.lap("engine");
         emit_update_table(tab, up.want_summary ? &bed : nullptr, counts, rn, anno, h, cn, src.c_str(), anno.gene_n, (int)anno.n(), out_fp, summary_fp, bed_fp);
     } else {
         lrb_update_result res;
         rc = eng.update(eng.self, input_mode == 0 ? &b : nullptr, input_mode == 0 ? nullptr : &ch, &ep, &up, &res);
         if (rc) engine_fail(eng, "update_gtf", rc);
+        tr.lap("engine");
         emit_update_outputs(res, rn, anno, h, cn, src.c_str(), anno.gene_n, (int)anno.n(),
                             out_fp, bam_gtf_fp, detail_fp, known_fp, novel_fp, unrecog_fp, summary_fp, bed_fp);
     }
     FILE *fps[] = {out_fp, bed_fp, bam_gtf_fp, detail_fp, known_fp, novel_fp, unrecog_fp, summary_fp};
     for (FILE *f : fps) if (f && f != stdout) fclose(f);
+    tr.lap("emit");
     return 0;
 }
 

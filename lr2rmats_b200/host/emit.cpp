@@ -4,22 +4,52 @@
 // They consume the SoA result structs of the C ABI plus the name tables kept on the host.
 #include <cstring>
 #include <string>
+#include <vector>
 #include "lrb_host.h"
 
 namespace lrb {
 
 namespace {
 
-struct Buf {                                        // small append buffer in front of FILE* (fprintf per line is the slow part)
-    FILE *fp; std::string s;
+struct Buf {                                        // append buffer in front of FILE* (fprintf per line is the slow part)
+    FILE *fp; std::string s;                        // fp == nullptr: collect only (a chunk formatted by a worker thread)
     explicit Buf(FILE *f) : fp(f) { s.reserve(1 << 20); }
     ~Buf() { flush(); }
-    void flush() { if (fp && !s.empty()) fwrite(s.data(), 1, s.size(), fp); s.clear(); }
-    void put(const char *p) { s.append(p); if (s.size() > (1 << 20) - 4096) flush(); }
-    void put(const std::string &p) { s.append(p); if (s.size() > (1 << 20) - 4096) flush(); }
+    void flush() { if (fp && !s.empty()) { fwrite(s.data(), 1, s.size(), fp); s.clear(); } }
+    void put(const char *p) { s.append(p); if (fp && s.size() > (1 << 20) - 4096) flush(); }
+    void put(const std::string &p) { s.append(p); if (fp && s.size() > (1 << 20) - 4096) flush(); }
     void ch(char c) { s.push_back(c); }
-    void num(long v) { char t[24]; snprintf(t, sizeof t, "%ld", v); s.append(t); }
+    void num(long v)                                // "%ld"
+    {
+        char t[24]; int k = 24;
+        unsigned long u = v < 0 ? 0ul - (unsigned long)v : (unsigned long)v;
+        do { t[--k] = (char)('0' + u % 10); u /= 10; } while (u);
+        if (v < 0) t[--k] = '-';
+        s.append(t + k, (size_t)(24 - k));
+    }
 };
+
+// fn(o, i) for i in [0, n), output in order: the items are formatted by all host threads, a chunk of items per task into
+// its own buffer, and the buffers of a group of chunks are written out in sequence
+template <class F> void emit_items(FILE *fp, int64_t n, F &&fn)
+{
+    if (!fp) return;
+    const int nt = host_threads();
+    const int64_t CH = 1024;
+    if (nt <= 1 || n < 4 * CH) { Buf o(fp); for (int64_t i = 0; i < n; ++i) fn(o, i); return; }
+    const int64_t nch = (n + CH - 1) / CH, G = (int64_t)nt * 8;
+    std::vector<Buf> part; part.reserve((size_t)G);
+    for (int64_t j = 0; j < G; ++j) part.emplace_back(nullptr);
+    for (int64_t g0 = 0; g0 < nch; g0 += G) {
+        const int64_t nb = nch - g0 < G ? nch - g0 : G;
+        parallel_for((size_t)nb, [&](size_t j) {
+            Buf &o = part[j]; o.s.clear();
+            const int64_t lo = (g0 + (int64_t)j) * CH, hi = lo + CH < n ? lo + CH : n;
+            for (int64_t i = lo; i < hi; ++i) fn(o, i);
+        });
+        for (int64_t j = 0; j < nb; ++j) fwrite(part[(size_t)j].s.data(), 1, part[(size_t)j].s.size(), fp);
+    }
+}
 
 struct TransText { const char *gene_id, *gene_name, *trans_id, *trans_name; };
 
@@ -88,21 +118,19 @@ void put_summary(FILE *summary, const int32_t *s, int anno_gene_n, int anno_tran
 }
 void put_bed(FILE *bed, const lrb_bed_list &b, const Header &h)                          // update_gtf.c:571-576 (uses the BAM header names)
 {
-    Buf o(bed);
-    for (int64_t i = 0; i < b.n; ++i) {
+    emit_items(bed, b.n, [&](Buf &o, int64_t i) {
         o.put(h.names[b.tid[i]]); o.ch('\t'); o.num(b.start[i] - 1); o.ch('\t'); o.num(b.end[i]); o.ch('\t');
         o.ch("TIS"[b.type[i]]); o.put("_exon\t"); o.num(b.score[i]); o.ch('\t'); o.ch("+-"[b.is_rev[i]]); o.ch('\n');
-    }
+    });
 }
 }  // namespace
 
 // bam2gtf's loop: print_trans for every mapped record (bam2gtf.c:150-156, gtf.c:597-605)
 void emit_bam2gtf(FILE *out, const lrb_exon_result &ex, const Records &rec, const ChrNames &cn, const char *src)
 {
-    Buf o(out);
-    for (int64_t r = 0; r < ex.n_reads; ++r) {
+    emit_items(out, ex.n_reads, [&](Buf &o, int64_t r) {
         uint32_t lo = ex.exon_off[r], hi = ex.exon_off[r + 1];
-        if (hi == lo) continue;
+        if (hi == lo) return;
         const char *q = rec.qname(ex.read_idx ? ex.read_idx[r] : r);
         const char *chr = cn.names[ex.tid[r]].c_str();
         char strand = "+-"[ex.is_rev[r]];
@@ -112,7 +140,7 @@ void emit_bam2gtf(FILE *out, const lrb_exon_result &ex, const Records &rec, cons
         };
         line("transcript", ex.exon_start[lo], ex.exon_end[hi - 1]);
         for (uint32_t j = lo; j < hi; ++j) line("exon", ex.exon_start[j], ex.exon_end[j]);
-    }
+    });
 }
 
 void emit_update_outputs(const lrb_update_result &res, const RowNames &rn, const Anno &anno, const Header &h, const ChrNames &cn,
@@ -148,17 +176,15 @@ void emit_update_outputs(const lrb_update_result &res, const RowNames &rn, const
         put_read_trans(o, cn.names[ttid].c_str(), src, tstart, tend, trev, t, cov, n, ex.exon_start + lo, ex.exon_end + lo, fs, le, echr, ex.is_rev[row]);
     };
 
-    if (updated) {
-        Buf o(updated);
-        for (int64_t i = 0; i < res.updated.n; ++i)
-            put_list_row(o, res.updated.cand[i], res.updated.cov[i], res.updated.t_tid[i], res.updated.t_start[i], res.updated.t_end[i],
-                         res.updated.first_start[i], res.updated.last_end[i], true);
-    }
-    if (bam_gtf) { Buf o(bam_gtf); for (int64_t r = 0; r < ex.n_reads; ++r) put_row(o, r); }
+    emit_items(updated, res.updated.n, [&](Buf &o, int64_t i) {
+        put_list_row(o, res.updated.cand[i], res.updated.cov[i], res.updated.t_tid[i], res.updated.t_start[i], res.updated.t_end[i],
+                     res.updated.first_start[i], res.updated.last_end[i], true);
+    });
+    emit_items(bam_gtf, ex.n_reads, [&](Buf &o, int64_t r) { put_row(o, r); });
     if (detail) {                                                    // print_bam_detail_trans, update_gtf.c:297-419
-        Buf o(detail);
-        o.put("ReadName\tchr\tstrand\tNovel\tGeneID\tGeneName\tExonCount\tExonStart\tExonEnd\tNovelExonCount\tNovelExonIndex\tNovelSiteCount\tNovelSiteIndex\tNovelJunctionCount\tNovelJunctionIndex\tUnreliableJunctionCount\tUnreliableJunctionIndex\n");
-        for (int64_t r = 0; r < ex.n_reads; ++r) {
+        { Buf o(detail);
+        o.put("ReadName\tchr\tstrand\tNovel\tGeneID\tGeneName\tExonCount\tExonStart\tExonEnd\tNovelExonCount\tNovelExonIndex\tNovelSiteCount\tNovelSiteIndex\tNovelJunctionCount\tNovelJunctionIndex\tUnreliableJunctionCount\tUnreliableJunctionIndex\n"); }
+        emit_items(detail, ex.n_reads, [&](Buf &o, int64_t r) {
             uint32_t lo = ex.exon_off[r]; int n = (int)(ex.exon_off[r + 1] - lo);
             const uint8_t *f = res.exon_flag + lo;
             uint32_t c = res.cls[r];
@@ -186,11 +212,11 @@ void emit_update_outputs(const lrb_update_result &res, const RowNames &rn, const
             idx_list(n - 1, 1, LRB_F_NOVEL_JUNC, 0, false);
             idx_list(n - 1, 1, LRB_F_UNRELIABLE, 0, true);
             o.ch('\n');
-        }
+        });
     }
-    if (known) { Buf o(known); for (int64_t i = 0; i < res.n_known; ++i) put_row(o, res.known_idx[i]); }
-    if (novel) { Buf o(novel); for (int64_t c = 0; c < res.novel.n; ++c) put_list_row(o, c, 1, 0, 0, 0, 0, 0, false); }
-    if (unrecog) { Buf o(unrecog); for (int64_t i = 0; i < res.n_unrecog; ++i) put_row(o, res.unrecog_idx[i]); }
+    emit_items(known, res.n_known, [&](Buf &o, int64_t i) { put_row(o, res.known_idx[i]); });
+    emit_items(novel, res.novel.n, [&](Buf &o, int64_t c) { put_list_row(o, c, 1, 0, 0, 0, 0, 0, false); });
+    emit_items(unrecog, res.n_unrecog, [&](Buf &o, int64_t i) { put_row(o, res.unrecog_idx[i]); });
     if (summary) put_summary(summary, res.summary, anno_gene_n, anno_trans_n);
     if (bed) put_bed(bed, res.bed, h);
 }
@@ -198,9 +224,8 @@ void emit_update_outputs(const lrb_update_result &res, const RowNames &rn, const
 void emit_update_table(const lrb_trans_table &tab, const lrb_bed_list *bed, const int32_t *summary_counts, const RowNames &rn, const Anno &anno,
                        const Header &h, const ChrNames &cn, const char *src, int anno_gene_n, int anno_trans_n, FILE *updated, FILE *summary, FILE *bed_fp)
 {
-    if (updated) {
-        Buf o(updated);
-        for (int64_t i = 0; i < tab.n; ++i) {
+    {
+        emit_items(updated, tab.n, [&](Buf &o, int64_t i) {
             const uint32_t lo = tab.exon_off[i]; const int n = (int)(tab.exon_off[i + 1] - lo);
             const int64_t k = tab.name_idx[i];
             TransText t;
@@ -212,7 +237,7 @@ void emit_update_table(const lrb_trans_table &tab, const lrb_bed_list *bed, cons
             t.trans_id = id.c_str(); t.trans_name = name.c_str();
             put_read_trans(o, cn.names[tab.t_tid[i]].c_str(), src, tab.t_start[i], tab.t_end[i], tab.t_rev[i], t, tab.cov[i], n, tab.exon_start + lo,
                            tab.exon_end + lo, tab.exon_start[lo], tab.exon_end[lo + n - 1], cn.names[tab.e_tid[i]].c_str(), tab.e_rev[i]);
-        }
+        });
     }
     if (summary && summary_counts) put_summary(summary, summary_counts, anno_gene_n, anno_trans_n);
     if (bed_fp && bed) put_bed(bed_fp, *bed, h);
@@ -223,27 +248,26 @@ void emit_unique(FILE *out, const lrb_unique_result &res, const RowNames &rn, co
 {
     const lrb_exon_result &ex = res.ex;
     Namer nm(rn, ex);
-    Buf o(out);
     auto names = [&](int64_t row, TransText &t) {
         t.trans_id = nm.tid_(row); t.trans_name = nm.tname_(row);
         if (rn.chains) { t.gene_id = rn.chains->gene_id[row].c_str(); t.gene_name = rn.chains->gene_name[row].c_str(); }
         else { t.gene_id = t.trans_id; t.gene_name = t.trans_id; }
     };
     if (intersect) {
-        for (int64_t i = 0; i < res.n_shared; ++i) {
+        emit_items(out, res.n_shared, [&](Buf &o, int64_t i) {
             int64_t row = res.shared_idx[i]; uint32_t lo = ex.exon_off[row]; int n = (int)(ex.exon_off[row + 1] - lo);
             TransText t; names(row, t);
             const char *chr = cn.names[ex.tid[row]].c_str();
             put_read_trans(o, chr, src, ex.exon_start[lo], ex.exon_end[lo + n - 1], ex.is_rev[row], t, 1, n, ex.exon_start + lo, ex.exon_end + lo,
                            ex.exon_start[lo], ex.exon_end[lo + n - 1], chr, ex.is_rev[row]);
-        }
+        });
     } else {
-        for (int64_t i = 0; i < res.uniq.n; ++i) {
+        emit_items(out, res.uniq.n, [&](Buf &o, int64_t i) {
             int64_t row = res.uniq.cand[i]; uint32_t lo = ex.exon_off[row]; int n = (int)(ex.exon_off[row + 1] - lo);
             TransText t; names(row, t);
             put_read_trans(o, cn.names[res.uniq.t_tid[i]].c_str(), src, res.uniq.t_start[i], res.uniq.t_end[i], ex.is_rev[row], t, res.uniq.cov[i], n,
                            ex.exon_start + lo, ex.exon_end + lo, res.uniq.first_start[i], res.uniq.last_end[i], cn.names[ex.tid[row]].c_str(), ex.is_rev[row]);
-        }
+        });
     }
 }
 

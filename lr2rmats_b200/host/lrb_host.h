@@ -10,7 +10,9 @@
 #define LRB_HOST_H
 
 #include <cstdint>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <memory>
 #include <string>
@@ -60,6 +62,11 @@ uint64_t hash_name(const char *s, size_t n);
 // host threads used by the decoders / encoders / emitters (LRB_THREADS, default: every hardware thread) and the loop helper
 int host_threads();
 void parallel_for(size_t n, const std::function<void(size_t)> &fn);
+// LRB_IO_TRACE=1: stage timings of the host side (decode, table readers, engine call, emitters) on stderr
+struct IoTrace {
+    bool on = getenv("LRB_IO_TRACE") != nullptr; std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char *what) { if (!on) return; auto n = std::chrono::steady_clock::now(); fprintf(stderr, "[lrb io] %-16s %.3f s\n", what, std::chrono::duration<double>(n - t).count()); t = n; }
+};
 
 // Reads SAM text or BAM (BGZF) -- autodetected like sam_open(..., "rb").  Returns false and sets err on failure.
 bool read_alignments(const std::string &path, Header &h, Records &r, std::string &err);

@@ -85,3 +85,86 @@ def test_truncated_bgzf_and_malformed_sam(big, tmp_path):
             run(op.PORT_BIN, ["bam2gtf", str(tmp_path / name)], tmp_path / f"{name}.t{t}.gtf", threads=t)
             outs.append(open(tmp_path / f"{name}.t{t}.gtf", "rb").read())
         assert outs[0] == outs[1] and len(outs[0]) > 1 << 19
+
+
+def test_emitters_threads(big, tmp_path):
+    """Row f-2: every text output of update-gtf / unique-gtf formatted by 8 threads == 1 thread == the reference's printers."""
+    from lr2rmats_b200 import cabi
+    anno = synth.make_annotation(3000, n_chrom=6, seed=41)
+    synth.write_gtf(tmp_path / "anno.gtf", anno)
+    files = ["detail.txt", "summary.txt", "bed", "bam.gtf", "known.gtf", "novel.gtf", "unrecog.gtf", "updated.gtf"]
+    flags = ["-A", "-y", "-E", "-a", "-k", "-v", "-u", "-o"]
+    outs = {}
+    for who, binary, t in (("ref", op.REF_BIN, None), ("t1", op.PORT_BIN, 1), ("t8", op.PORT_BIN, 8)):
+        d = tmp_path / who; d.mkdir()
+        a = ["update-gtf", "-l", "5", str(big / "in.sam"), str(tmp_path / "anno.gtf")]
+        for fl, fn in zip(flags, files):
+            a += [fl, str(d / fn)]
+        run(binary, a, d / "stdout", threads=t)
+        run(binary, ["unique-gtf", str(big / "in.sam")], d / "uniq.gtf", threads=t)
+        outs[who] = {fn: open(d / fn, "rb").read() for fn in files + ["uniq.gtf"]}
+    for fn in files + ["uniq.gtf"]:
+        assert outs["ref"][fn] == outs["t1"][fn] == outs["t8"][fn], fn
+    assert len(outs["ref"]["updated.gtf"]) > 1 << 20 and len(outs["ref"]["detail.txt"]) > 1 << 20 and len(outs["ref"]["known.gtf"]) > 1 << 16
+
+
+@pytest.mark.parametrize("quirk", ["plain", "comments_cds", "blank_separated", "long_line", "no_names"])
+def test_gtf_reader_threads(big, tmp_path, quirk):
+    """The all-threads annotation reader takes plain files only; anything else must fall back to the reference's own parsing
+    (fgets 1024 + sscanf state) -- the outputs equal the reference binary's either way."""
+    anno = synth.make_annotation(3000, n_chrom=6, seed=41)
+    synth.write_gtf(tmp_path / "anno.gtf", anno)
+    lines = open(tmp_path / "anno.gtf").read().split("\n")
+    k = len(lines) // 2
+    while "\texon\t" not in lines[k]:
+        k += 1
+    if quirk == "comments_cds":
+        lines[k:k] = ["# a comment", lines[k].replace("\texon\t", "\tCDS\t"), "#another"]
+    elif quirk == "blank_separated":
+        lines[k] = lines[k].replace("\t", " ", 4)
+    elif quirk == "long_line":
+        lines[k] = lines[k] + " note \"" + "ab " * 400 + "\";"          # tokens stay below the reference's ref[100] / type[20] buffers
+    elif quirk == "no_names":
+        lines[k] = lines[k].split("gene_name")[0].rstrip()
+    open(tmp_path / "anno.gtf", "w").write("\n".join(lines))
+    outs = []
+    for binary, env in ((op.REF_BIN, {}), (op.PORT_BIN, {"LRB_THREADS": "8"}), (op.PORT_BIN, {"LRB_GTF_SEQUENTIAL": "1"})):
+        d = tmp_path / f"o{len(outs)}"; d.mkdir()
+        e = dict(os.environ); e.update(env)
+        with open(d / "updated.gtf", "wb") as f:
+            p = subprocess.run([binary, "update-gtf", "-l", "5", str(big / "in.sam"), str(tmp_path / "anno.gtf"), "-y", str(d / "summary.txt"), "-k", str(d / "known.gtf")],
+                               stdout=f, stderr=subprocess.DEVNULL, env=e)
+        outs.append((p.returncode, open(d / "updated.gtf", "rb").read(), open(d / "summary.txt", "rb").read(), open(d / "known.gtf", "rb").read()))
+    assert outs[0] == outs[1] == outs[2]
+    assert outs[0][0] == 0 and len(outs[0][1]) > 1 << 20
+
+
+@pytest.mark.parametrize("quirk", ["plain", "short_line", "unknown_chrom_blank"])
+def test_sj_reader_threads(big, tmp_path, quirk):
+    """SJ.out.tab through the all-threads reader (plain files) or the reference's sscanf loop (anything else): same
+    junction support, same chromosome-id extension (gtf.c:389-449)."""
+    from lr2rmats_b200 import cabi
+    anno = synth.make_annotation(3000, n_chrom=6, seed=41)
+    rr = synth.make_rrna(anno, 30, seed=42)
+    reads = synth.make_reads(anno, 40000, seed=43, ont=False, reject_frac=0.2, rrna=rr, quirk_frac=0.02)
+    ex = op.bam2gtf(reads.soa(), cabi.ExonParams.default())
+    sj = synth.make_sj((ex["tid"], ex["exon_off"], ex["exon_start"], ex["exon_end"]), 0.7, seed=5)
+    synth.write_gtf(tmp_path / "anno.gtf", anno); synth.write_sj(tmp_path / "sj.tab", sj, anno.chrom_names)
+    lines = open(tmp_path / "sj.tab").read().split("\n")
+    assert len(lines) > 20000
+    k = len(lines) // 2
+    if quirk == "short_line":
+        lines[k] = "\t".join(lines[k].split("\t")[:5])               # later columns keep the previous line's values
+    elif quirk == "unknown_chrom_blank":
+        lines[k] = lines[k].replace("\t", " ", 2); lines[k + 1] = "chrUn_x\t" + lines[k + 1].split("\t", 1)[1]
+    open(tmp_path / "sj.tab", "w").write("\n".join(lines))
+    outs = []
+    for binary, env in ((op.REF_BIN, {}), (op.PORT_BIN, {"LRB_THREADS": "8"}), (op.PORT_BIN, {"LRB_GTF_SEQUENTIAL": "1"})):
+        d = tmp_path / f"o{len(outs)}"; d.mkdir()
+        e = dict(os.environ); e.update(env)
+        with open(d / "updated.gtf", "wb") as f:
+            p = subprocess.run([binary, "update-gtf", "-s", "-l", "3", "-j", str(tmp_path / "sj.tab"), str(big / "in.sam"), str(tmp_path / "anno.gtf"),
+                                "-y", str(d / "summary.txt"), "-A", str(d / "detail.txt")], stdout=f, stderr=subprocess.DEVNULL, env=e)
+        outs.append((p.returncode, open(d / "updated.gtf", "rb").read(), open(d / "summary.txt", "rb").read(), open(d / "detail.txt", "rb").read()))
+    assert outs[0] == outs[1] == outs[2]
+    assert outs[0][0] == 0 and len(outs[0][1]) > 1 << 20

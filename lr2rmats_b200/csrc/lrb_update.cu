@@ -289,10 +289,11 @@ __global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a, const
 // replaces the reference's three nested loops; the four per-exon flag arrays live in four 32-bit registers.
 static constexpr int CR_THREADS = 128;
 
-__global__ void __launch_bounds__(CR_THREADS) classify_row_kernel(ClassArgs a, uint8_t *__restrict__ slow, const uint8_t *__restrict__ row_nonmono)
+__global__ void __launch_bounds__(CR_THREADS) classify_row_kernel(ClassArgs a, uint8_t *__restrict__ slow, const uint8_t *__restrict__ row_nonmono, int by_exon_count)
 {
     __shared__ int s_win[6];
-    const int t = threadIdx.x;
+    __shared__ int s_hist[34]; __shared__ uint8_t s_perm[CR_THREADS];
+    int t = threadIdx.x;
     const int dis = a.up.ss_dis, level = a.up.full_level;
     const int64_t r0 = (int64_t)blockIdx.x * CR_THREADS, r1 = min(a.rows.n, r0 + (int64_t)CR_THREADS);
     {   // bracket the three cursors for the rows of this tile (rows are sorted): six cooperative 33-ary searches, warps 0..3
@@ -312,6 +313,31 @@ __global__ void __launch_bounds__(CR_THREADS) classify_row_kernel(ClassArgs a, u
         }
     }
     __syncthreads();
+    if (by_exon_count) {
+        // the rows of the tile are dealt to the threads in order of their exon count (stable counting sort in shared memory):
+        // the lanes of a warp then run merge walks of the same length, at the price of sweeping different transcripts
+        if (t < 34) s_hist[t] = 0;
+        __syncthreads();
+        const int64_t rr = r0 + t;
+        int key = 33, rank = 0;
+        if (rr < r1) { const int nn = (int)a.rows.ex_n[rr]; key = nn < 0 ? 0 : nn > 32 ? 32 : nn; }
+        // rank inside the key class = number of earlier threads with the same key (warp ballots + per-warp offsets)
+        const unsigned peers = __match_any_sync(FULL, key);
+        const int lane = lane_id();
+        rank = __popc(peers & ((1u << lane) - 1u));
+        __shared__ int s_wcnt[CR_THREADS / 32][34];
+        for (int q = t; q < (CR_THREADS / 32) * 34; q += CR_THREADS) (&s_wcnt[0][0])[q] = 0;
+        __syncthreads();
+        if (rank == 0) s_wcnt[warp_id()][key] = __popc(peers);
+        __syncthreads();
+        if (t < 34) { int acc = 0; for (int w = 0; w < CR_THREADS / 32; ++w) { const int v = s_wcnt[w][t]; s_wcnt[w][t] = acc; acc += v; } s_hist[t] = acc; }
+        __syncthreads();
+        if (t == 0) { int acc = 0; for (int k = 0; k < 34; ++k) { const int v = s_hist[k]; s_hist[k] = acc; acc += v; } }
+        __syncthreads();
+        s_perm[s_hist[key] + s_wcnt[warp_id()][key] + rank] = (uint8_t)t;
+        __syncthreads();
+        t = s_perm[t];
+    }
     const int64_t row = r0 + t;
     if (row >= r1) return;
     const int Flo = s_win[0], Fhi = max(s_win[0], s_win[1]), Slo = s_win[2], Shi = max(s_win[2], s_win[3]), Dlo = s_win[4], Dhi = max(s_win[4], s_win[5]);
@@ -500,11 +526,11 @@ template <int G, int SLOTS> static void launch_classify_t(const ClassArgs &a, co
 void launch_classify(const ClassArgs &a, uint8_t *slow, cudaStream_t st)
 {
     if (a.rows.n <= 0) return;
-    static int g = -1, fast = -1;
-    if (g < 0) { const char *e = getenv("LRB_CLASSIFY_G"); g = e ? atoi(e) : 4; e = getenv("LRB_CLASSIFY_FAST"); fast = e ? atoi(e) : 1; }
+    static int g = -1, fast = -1, by_n = 0;
+    if (g < 0) { const char *e = getenv("LRB_CLASSIFY_G"); g = e ? atoi(e) : 4; e = getenv("LRB_CLASSIFY_FAST"); fast = e ? atoi(e) : 1; e = getenv("LRB_CR_SORT"); by_n = e ? atoi(e) : 1; }
     const uint8_t *only = nullptr;
     if (fast && a.up.ss_dis == 0 && slow) {
-        classify_row_kernel<<<(unsigned)((a.rows.n + CR_THREADS - 1) / CR_THREADS), CR_THREADS, 0, st>>>(a, slow, a.row_nonmono);
+        classify_row_kernel<<<(unsigned)((a.rows.n + CR_THREADS - 1) / CR_THREADS), CR_THREADS, 0, st>>>(a, slow, a.row_nonmono, by_n);
         LRB_COUNT_LAUNCH();
         only = slow;
     }

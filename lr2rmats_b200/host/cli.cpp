@@ -79,7 +79,9 @@ static int cmd_filter(int argc, char **argv, Engine &eng)
     }
     if (argc - optind != 1) return filter_usage();
     Header h; Records rec; rec.keep_raw = true; std::string err;
+    IoTrace tr;
     if (!read_alignments(argv[optind], h, rec, err)) fatal("bam_filter", err);
+    tr.lap("alignments");
     Anno rm;
     if (!rm_fn.empty()) {
         logf("read_anno_trans", ("reading transcript annotation from " + rm_fn + " ...\n").c_str());
@@ -89,10 +91,13 @@ static int cmd_filter(int argc, char **argv, Engine &eng)
     lrb_anno rmv = rm.view();
     int rc = eng.set_tables(eng.self, nullptr, rm_fn.empty() ? nullptr : &rmv, nullptr);
     if (rc) engine_fail(eng, "bam_filter", rc);
+    tr.lap("tables upload");
     lrb_batch b = rec.view(); lrb_filter_result res;
     rc = eng.filter(eng.self, &b, &fp, &res);
     if (rc) engine_fail(eng, "bam_filter", rc);
+    tr.lap("engine");
     if (!write_bam(stdout, h, rec, res.keep_idx, res.n_keep, err)) fatal("bam_filter", err);
+    tr.lap("emit");
     logf("bam_filter", ("Filtered alignments: " + std::to_string(res.n_keep) + "\n").c_str());
     return 0;
 }

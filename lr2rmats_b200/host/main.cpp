@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <future>
+#include <unistd.h>
 #include "lrb_host.h"
 
 namespace {
@@ -66,8 +67,12 @@ int main(int argc, char **argv)
     }
     eng.self = &ce; eng.set_tables = set_tables; eng.filter = do_filter; eng.bam2gtf = do_bam2gtf; eng.update = do_update; eng.update_table = getenv("LRB_FULL_FETCH") ? nullptr : do_update_table;
     eng.unique = do_unique; eng.error = err;
+    lrb::IoTrace tr;
     int rc = lrb::cli_main(argc, argv, eng);
     if (ce.pending.valid()) ce.pending.wait();        // usage errors return before any engine call
+    // a one-shot process: the outputs are flushed and the driver reclaims the device memory at exit; freeing ~150 device
+    // and pinned buffers one by one costs more than the whole GPU stage (LRB_CLEAN_EXIT=1 keeps the orderly teardown)
+    if (!getenv("LRB_CLEAN_EXIT")) { fflush(NULL); tr.lap("total"); _exit(rc); }
     if (ce.ctx) lrb_ctx_destroy(ce.ctx);
     return rc;
 }

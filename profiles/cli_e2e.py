@@ -16,19 +16,32 @@ synth.write_gtf(f"{wd}/anno.gtf", anno); synth.write_rm_gtf(f"{wd}/rm.gtf", rr, 
 synth.write_sam(f"{wd}/in.sam", reads, with_seq=True)
 
 
+def stages(err_bytes):
+    """the [lrb io] stage lines of LRB_IO_TRACE=1 (host decode / table readers / engine / emitters), seconds"""
+    out = {}
+    for line in err_bytes.decode(errors="replace").splitlines():
+        if line.startswith("[lrb io]"):
+            k, v = line[8:].rsplit(None, 2)[0].strip(), float(line.split()[-2])
+            out[k] = round(out.get(k, 0.0) + v, 4)
+    return out
+
+
 def run(binary, tag, threads=None):
     env = dict(os.environ)
+    env["LRB_IO_TRACE"] = "1"
     if threads:
         env["LRB_THREADS"] = str(threads)
     t = {}
     t0 = time.perf_counter()
     with open(f"{wd}/{tag}.f.bam", "wb") as f:
-        subprocess.run([binary, "filter", "-r", f"{wd}/rm.gtf", f"{wd}/in.sam"], stdout=f, stderr=subprocess.DEVNULL, check=True, env=env)
+        p = subprocess.run([binary, "filter", "-r", f"{wd}/rm.gtf", f"{wd}/in.sam"], stdout=f, stderr=subprocess.PIPE, check=True, env=env)
     t["filter_s"] = time.perf_counter() - t0
+    t["filter_stages"] = stages(p.stderr)
     t0 = time.perf_counter()
-    subprocess.run([binary, "update-gtf", "-s", "-l", "3", "-J", "1", "-j", f"{wd}/sj.tab", f"{wd}/{tag}.f.bam", f"{wd}/anno.gtf", "-y", f"{wd}/{tag}.sum.txt",
-                    "-E", f"{wd}/{tag}.bed", "-o", f"{wd}/{tag}.upd.gtf"], stderr=subprocess.DEVNULL, check=True, env=env)
+    p = subprocess.run([binary, "update-gtf", "-s", "-l", "3", "-J", "1", "-j", f"{wd}/sj.tab", f"{wd}/{tag}.f.bam", f"{wd}/anno.gtf", "-y", f"{wd}/{tag}.sum.txt",
+                        "-E", f"{wd}/{tag}.bed", "-o", f"{wd}/{tag}.upd.gtf"], stderr=subprocess.PIPE, check=True, env=env)
     t["update_s"] = time.perf_counter() - t0
+    t["update_stages"] = stages(p.stderr)
     t["aln_per_s"] = reads.n / (t["filter_s"] + t["update_s"])
     return t
 

@@ -250,7 +250,8 @@ DMerged merged_view(Buf &cand, Buf &cov, Buf &tid, Buf &st, Buf &en, Buf &fs, Bu
 // candidate) folded in one pass and only the survivors per sub-stream are counted (class_alive); else the survivors are
 // compacted into m.o_*.  totals[0] <- number of loci, totals[1] <- number of survivors (device).
 int run_merge_async(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_cand, const uint64_t *n_cand_dev, const lrb_update_params &up,
-                    uint64_t *totals, const uint8_t *kls = nullptr, uint32_t *class_alive = nullptr, bool time_fold = false, bool side = false)
+                    uint64_t *totals, const uint8_t *kls = nullptr, uint32_t *class_alive = nullptr, bool time_fold = false, bool side = false,
+                    bool single_locus = false)
 {
     int rc;
     cudaStream_t st = side ? c->st2 : c->st;
@@ -271,7 +272,7 @@ int run_merge_async(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_
     a.cd.n = m.c_n.as<int32_t>(); a.cd.fs = m.c_fs.as<int32_t>(); a.cd.le = m.c_le.as<int32_t>(); a.cd.gbeg = m.c_gbeg.as<uint32_t>();
     a.cd.hash = m.c_hash.as<uint64_t>(); a.cd.j0 = m.c_j0.as<uint64_t>(); a.cd.sig = m.c_sig.as<uint64_t>();
     a.tile_state = side ? c->tile_state2.as<uint64_t>() : c->tile_state.as<uint64_t>(); a.ticket = side ? d_ticket2(c) : d_ticket(c); a.totals = totals;
-    a.kls = kls; a.class_alive = class_alive;
+    a.kls = kls; a.class_alive = class_alive; a.single_locus = single_locus ? 1 : 0;
     launch_merge_prepare(a, st);
     if (time_fold) tick(c, 10);
     launch_merge_fold(a, st);                        // locus count is consumed on the device: no host round trip
@@ -282,10 +283,10 @@ int run_merge_async(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_
     return LRB_OK;
 }
 
-int run_merge(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_cand, const lrb_update_params &up)
+int run_merge(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_cand, const lrb_update_params &up, bool single_locus = false)
 {
     int rc;
-    if ((rc = run_merge_async(c, m, list, n_cand, nullptr, up, d_totals(c), nullptr, nullptr, true)) != LRB_OK) return rc;
+    if ((rc = run_merge_async(c, m, list, n_cand, nullptr, up, d_totals(c), nullptr, nullptr, true, false, single_locus)) != LRB_OK) return rc;
     uint64_t t[2];
     if ((rc = read_totals(c, t, 2)) != LRB_OK) return rc;
     m.n_loci = (int64_t)t[0]; m.n_out = (int64_t)t[1];
@@ -300,8 +301,6 @@ int setup_list(lrb_ctx *c, DTransList &l, Buf &row, Buf &lo, Buf &cnt, Buf &piec
     l.n = n; l.cap = n; l.row = row.as<uint32_t>(); l.lo = lo.as<uint32_t>(); l.cnt = cnt.as<uint32_t>(); l.piece = piece.as<int32_t>();
     return LRB_OK;
 }
-
-uint64_t pow2_at_least(uint64_t x) { uint64_t p = 1024; while (p < x) p <<= 1; return p; }
 
 }  // namespace
 
@@ -601,12 +600,13 @@ int lrb_pipeline_run(lrb_ctx *c, const lrb_filter_params *fp, const lrb_exon_par
     return LRB_OK;
 }
 
-static int check_err_flags(lrb_ctx *c)
+static int check_err_flags(lrb_ctx *c, uint32_t *flags = nullptr)
 {
     uint32_t e = 0;
     CK(cudaMemcpyAsync(c->h_scalars.p, d_err(c), 4, cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
     memcpy(&e, c->h_scalars.p, 4);
+    if (flags) *flags = e;
     if (e & 2u) return fail(c, LRB_E_UNMAPPED, "unmapped record / empty exon chain in update/unique input (the reference aborts here, bam2gtf.c:95-100)");
     if (e & 1u) return fail(c, LRB_E_UNSORTED, "reads are not sorted by (tid,start) (update_gtf.c:41)");
     return LRB_OK;
@@ -624,7 +624,10 @@ __global__ void rows_check_kernel(DRows rows, uint32_t *err, int check_sorted)
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows.n) return;
     if (rows.ex_n[r] == 0) atomicOr(err, 2u);
-    (void)check_sorted;
+    if (check_sorted && r > 0) {                     // bit 2: not sorted by (tid,start) -- allowed for unique (a concatenation of samples)
+        const int pt = rows.tid[r - 1], ps = rows.start[r - 1], ct = rows.tid[r], cs = rows.start[r];
+        if (pt > ct || (pt == ct && ps > cs)) atomicOr(err, 4u);
+    }
 }
 
 int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
@@ -658,12 +661,12 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
     int64_t cap = up->split_trans ? n + n / 8 + 1024 : n;
     cap = std::max<int64_t>(cap, std::min<int64_t>(c->novel_cap_hint, n + c->ex.n / 2 + 1));
     SummaryArgs sa{};
-    int64_t n_novel = 0, nu = 0; uint64_t n_elem = 0;
+    int64_t n_novel = 0, nu = 0; uint64_t n_elem = 0, n_exon_elem = 0;
     uint32_t cnt16[16];
     for (int attempt = 0; n > 0; ++attempt) {
         if ((rc = setup_list(c, c->novel, c->n_row, c->n_lo, c->n_cnt, c->n_piece, cap))) return rc;
         c->novel.cap = cap;
-        CK(cudaMemsetAsync(c->y_counts.p, 0, 64, c->st)); CK(cudaMemsetAsync(c->y_nelem.p, 0, 8, c->st));
+        CK(cudaMemsetAsync(c->y_counts.p, 0, 64, c->st)); CK(cudaMemsetAsync(c->y_nelem.p, 0, 16, c->st));
         ListArgs la{};
         la.rows = rows; la.ex = c->ex; la.up = *up; la.cls = ca.cls; la.n_novel = ca.n_novel; la.novel = c->novel;
         la.known = c->u_known.as<uint32_t>(); la.unrecog = c->u_unrecog.as<uint32_t>();
@@ -705,10 +708,10 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
         uint8_t *hp = (uint8_t *)c->h_scalars.p;
         CK(cudaMemcpyAsync(hp, c->scalars.p, T_SLOTS * 8 + 8, cudaMemcpyDeviceToHost, c->st));
         CK(cudaMemcpyAsync(hp + 320, c->y_counts.p, 64, cudaMemcpyDeviceToHost, c->st));
-        CK(cudaMemcpyAsync(hp + 384, c->y_nelem.p, 8, cudaMemcpyDeviceToHost, c->st));
+        CK(cudaMemcpyAsync(hp + 384, c->y_nelem.p, 16, cudaMemcpyDeviceToHost, c->st));
         CK(cudaStreamSynchronize(c->st));
         uint64_t t[T_SLOTS]; uint32_t e[2];
-        memcpy(t, hp, sizeof t); memcpy(e, hp + T_SLOTS * 8, 8); memcpy(cnt16, hp + 320, 64); memcpy(&n_elem, hp + 384, 8);
+        memcpy(t, hp, sizeof t); memcpy(e, hp + T_SLOTS * 8, 8); memcpy(cnt16, hp + 320, 64); memcpy(&n_elem, hp + 384, 8); memcpy(&n_exon_elem, hp + 392, 8);
         if (e[1] & 2u) return fail(c, LRB_E_UNMAPPED, "unmapped record / empty exon chain in update/unique input (the reference aborts here, bam2gtf.c:95-100)");
         if (e[1] & 1u) return fail(c, LRB_E_UNSORTED, "reads are not sorted by (tid,start) (update_gtf.c:41)");
         n_novel = (int64_t)t[T_NOVEL]; c->n_known = (int64_t)t[T_KNOWN]; c->n_unrecog = (int64_t)t[T_UNREC];
@@ -733,10 +736,14 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
         for (int k = 0; k < 4; ++k) s[cnt_idx[k]] = (int32_t)cnt16[12 + k];
         s[LRB_S_NOVEL_BAM] = s[LRB_S_NOVEL_RELIABLE] + s[LRB_S_NOVEL_UNRELIABLE];
         sa.n_upd = nu; sa.n_upd_dev = nullptr; sa.upd.n = nu;
-        const uint64_t capn = pow2_at_least(2 * (n_elem + (uint64_t)s[LRB_S_KNOWN_TRANS]) + 1024);
+        // distinct table keys: one per exon element, up to two per gene / site / junction element (the tid-0 phase and the
+        // segment phase key them differently), one per known read; the table stays below that bound's next power of two
+        // (load <= 0.8 in the worst case, ~0.4 on the bench shape; the slot index is a multiply-high, so no power of two is needed)
+        const uint64_t worst = 2 * n_elem - std::min(n_exon_elem, n_elem) + (uint64_t)s[LRB_S_KNOWN_TRANS];
+        const uint64_t capn = worst + worst / 4 + 1024;
         NEED(c->h_khi, capn * sizeof(HashSlot));
         CK(cudaMemsetAsync(c->h_khi.p, 0xFF, capn * sizeof(HashSlot), c->st));
-        sa.tab.mask = capn - 1; sa.tab.slots = c->h_khi.as<HashSlot>();
+        sa.tab.cap = capn; sa.tab.slots = c->h_khi.as<HashSlot>();
         // BED rows are the first occurrences of the exon set: at most one per counted element
         const size_t nb = (size_t)std::max<uint64_t>(n_elem, 1);
         NEED(c->bd_tid, nb * 4); NEED(c->bd_s, nb * 4); NEED(c->bd_e, nb * 4); NEED(c->bd_sc, nb * 4); NEED(c->bd_ty, nb); NEED(c->bd_rv, nb);
@@ -781,11 +788,15 @@ int lrb_unique_run(lrb_ctx *c, const lrb_update_params *up)
     int rc;
     CK(cudaMemsetAsync(d_err(c), 0, 4, c->st));
     tick(c, 0);
-    if (n) { rows_check_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->st>>>(rows, d_err(c), 0); CK(cudaGetLastError()); }
-    if ((rc = check_err_flags(c))) return rc;
+    if (n) { rows_check_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->st>>>(rows, d_err(c), 1); CK(cudaGetLastError()); }
+    uint32_t flags = 0;
+    if ((rc = check_err_flags(c, &flags))) return rc;
     if ((rc = setup_list(c, c->tmp_list, c->t_row, c->t_lo, c->t_cnt, c->t_piece, n))) return rc;
     launch_rows_as_list(rows, nullptr, n, c->tmp_list, c->st);
-    if ((rc = run_merge(c, c->mg, c->tmp_list, n, *up))) return rc;
+    // unique-gtf's input may be a concatenation of sorted samples (Snakefile:189-192).  The locus cuts (App. B.3) are only
+    // proven for (tid,start)-sorted streams, so an unsorted list is folded as ONE locus: the back-scan of merge_trans is
+    // replayed entry by entry (merge_fold_kernel), early-termination quirks included.
+    if ((rc = run_merge(c, c->mg, c->tmp_list, n, *up, (flags & 4u) != 0))) return rc;
     // shared_T = rows the fold absorbed: complement of the alive mask (kept in mg.dropped); mg.head is free again
     NEED(c->q_shared, (size_t)std::max<int64_t>(n, 1) * 4);
     c->n_shared = 0;

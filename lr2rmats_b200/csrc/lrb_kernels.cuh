@@ -124,6 +124,7 @@ struct MergeArgs {
     int64_t n_cand;                                 // candidates (host value, or the host's upper bound when n_cand_dev is set)
     const uint64_t *n_cand_dev;                     // optional: the true count, produced on the device
     int n_tiles;
+    int single_locus;                               // 1: the whole list is ONE locus (unsorted input: no cut is safe, the fold is replayed in order)
     const uint8_t *kls;                             // optional: sub-stream id per candidate (class folds: four independent folds in one pass); NULL: one stream
     uint64_t *samemask;                             // flat fold with kls: earlier candidates of the locus in the same sub-stream
     uint32_t *class_alive;                          // [4] surviving entries per sub-stream

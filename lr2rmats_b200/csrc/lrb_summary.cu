@@ -32,25 +32,25 @@ LRB_DEVINL uint64_t key_lo(int k1, int k2) { return ((uint64_t)(uint32_t)k1 << 3
 // insert-or-find; returns the slot
 LRB_DEVINL uint64_t tab_upsert(const HashTab &t, uint64_t hi, uint64_t lo)
 {
-    uint64_t s = mix64(hi * 0x9E3779B97F4A7C15ull ^ mix64(lo)) & t.mask;
+    uint64_t s = __umul64hi(mix64(hi * 0x9E3779B97F4A7C15ull ^ mix64(lo)), t.cap);      // any capacity, not only powers of two
     for (;;) {
         unsigned long long p = atomicCAS((unsigned long long *)&t.slots[s].khi, (unsigned long long)EMPTY, (unsigned long long)hi);
         if (p == EMPTY || p == hi) {
             unsigned long long q = atomicCAS((unsigned long long *)&t.slots[s].klo, (unsigned long long)EMPTY, (unsigned long long)lo);
             if (q == EMPTY || q == lo) return s;
         }
-        s = (s + 1) & t.mask;
+        s = s + 1 == t.cap ? 0 : s + 1;
     }
 }
 LRB_DEVINL uint64_t tab_find(const HashTab &t, uint64_t hi, uint64_t lo)
 {
-    uint64_t s = mix64(hi * 0x9E3779B97F4A7C15ull ^ mix64(lo)) & t.mask;
+    uint64_t s = __umul64hi(mix64(hi * 0x9E3779B97F4A7C15ull ^ mix64(lo)), t.cap);      // any capacity, not only powers of two
     for (;;) {
         const ulonglong2 k = *(const ulonglong2 *)&t.slots[s].khi;      // both key words in one 16-byte load
         const uint64_t a = k.x;
         if (a == hi && k.y == lo) return s;
         if (a == EMPTY) return EMPTY;
-        s = (s + 1) & t.mask;
+        s = s + 1 == t.cap ? 0 : s + 1;
     }
 }
 LRB_DEVINL void tab_min(const HashTab &t, uint64_t s, uint64_t pos) { atomicMin((unsigned long long *)&t.slots[s].minpos, (unsigned long long)pos); }
@@ -90,19 +90,20 @@ __global__ void sum_count_kernel(SummaryArgs a, unsigned long long *n_elems)
 {
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / SG;
     const int gl = threadIdx.x % SG;
-    int c = 0;
+    int c = 0, cx = 0;                               // all elements; exon elements (one table key each -- the others can take two)
     if (i < (a.n_upd_dev ? (int64_t)*a.n_upd_dev : a.n_upd)) {
         EntryView e = load_entry(a, i);
         const uint8_t *f = a.ex.flag + e.gbeg;
         c = gl == 0 ? 1 : 0;
         for (int j = gl; j < e.n; j += SG) {
             uint8_t x = f[j];
-            c += (x & LRB_F_NOVEL_EXON) != 0;
+            cx += (x & LRB_F_NOVEL_EXON) != 0;
             if (j < e.n - 1) c += ((x & LRB_F_NOVEL_DON) != 0) + ((x & LRB_F_NOVEL_ACC) != 0) + ((x & LRB_F_NOVEL_JUNC) != 0);
         }
+        c += cx;
     }
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
-    if (lane_id() == 0 && c) atomicAdd(n_elems, (unsigned long long)c);
+    for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(FULL, c, o); cx += __shfl_xor_sync(FULL, cx, o); }
+    if (lane_id() == 0 && c) { atomicAdd(n_elems, (unsigned long long)c); if (cx) atomicAdd(n_elems + 1, (unsigned long long)cx); }
 }
 
 // phase 1: exons (all entries), tid-0 elements of D/A/J, every gene element (gene equality ignores tid)

@@ -9,7 +9,7 @@ namespace lrbk {
 // (the score therefore starts at -1).
 struct __align__(32) HashSlot { uint64_t khi, klo, minpos; int32_t score, pad; };
 struct HashTab {
-    uint64_t mask = 0;
+    uint64_t cap = 0;                               // number of slots
     HashSlot *slots = nullptr;
 };
 

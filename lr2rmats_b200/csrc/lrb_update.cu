@@ -287,8 +287,8 @@ __global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a, const
 // reads of a warp are neighbours in (tid,start) order, so they sweep the same transcripts -- annotation loads are warp
 // broadcasts and the lanes stay converged.  Per (read, transcript) pair one merge walk over the two sorted exon lists
 // replaces the reference's three nested loops; the four per-exon flag arrays live in four 32-bit registers.
-static constexpr int CR_THREADS = 128;
 
+template <int CR_THREADS>
 __global__ void __launch_bounds__(CR_THREADS) classify_row_kernel(ClassArgs a, uint8_t *__restrict__ slow, const uint8_t *__restrict__ row_nonmono, int by_exon_count)
 {
     __shared__ int s_win[6];
@@ -530,7 +530,11 @@ void launch_classify(const ClassArgs &a, uint8_t *slow, cudaStream_t st)
     if (g < 0) { const char *e = getenv("LRB_CLASSIFY_G"); g = e ? atoi(e) : 4; e = getenv("LRB_CLASSIFY_FAST"); fast = e ? atoi(e) : 1; e = getenv("LRB_CR_SORT"); by_n = e ? atoi(e) : 1; }
     const uint8_t *only = nullptr;
     if (fast && a.up.ss_dis == 0 && slow) {
-        classify_row_kernel<<<(unsigned)((a.rows.n + CR_THREADS - 1) / CR_THREADS), CR_THREADS, 0, st>>>(a, slow, a.row_nonmono, by_n);
+        static int crt = -1;
+        if (crt < 0) { const char *e = getenv("LRB_CR_THREADS"); crt = e ? atoi(e) : 128; }
+        if (crt >= 256) classify_row_kernel<256><<<(unsigned)((a.rows.n + 255) / 256), 256, 0, st>>>(a, slow, a.row_nonmono, by_n);
+        else if (crt <= 64) classify_row_kernel<64><<<(unsigned)((a.rows.n + 63) / 64), 64, 0, st>>>(a, slow, a.row_nonmono, by_n);
+        else classify_row_kernel<128><<<(unsigned)((a.rows.n + 127) / 128), 128, 0, st>>>(a, slow, a.row_nonmono, by_n);
         LRB_COUNT_LAUNCH();
         only = slow;
     }
@@ -702,7 +706,7 @@ __global__ void __launch_bounds__(FP_THREADS) fold_prepare_kernel(MergeArgs a)
 #pragma unroll
     for (int i = 0; i < FP_ITEMS; ++i) {
         if (c0 + i < n_cand) {
-            const bool h = (c0 + i == 0) || key_start[i] > before;
+            const bool h = (c0 + i == 0) || (!a.single_locus && key_start[i] > before);
             if (h) { head |= 1u << i; ++nhead; }
             a.head[c0 + i] = h ? 1 : 0;
             before = key_end[i] > before ? key_end[i] : before;
@@ -968,6 +972,53 @@ __global__ void __launch_bounds__(256) fold_relrep_kernel(MergeArgs a, const uin
     }
 }
 
+// The same relation, warp-cooperative (LRB_FOLD_RELW=1; measured SLOWER on B200 -- fold 0.33 vs 0.27 ms -- and therefore not the
+// default): only class representatives have work in fold_relrep_kernel and their loops have
+// different lengths (3.8 active threads per instruction measured), so here the warp takes its representatives one after the
+// other (ballot) and all 32 lanes share the scan over that representative's predecessors: descriptor test and junction-signature
+// filter run on coalesced loads with full lanes, and only the rare signature hit walks the exon pools.
+__global__ void __launch_bounds__(256) fold_relrep_warp_kernel(MergeArgs a, const uint32_t *__restrict__ lstart)
+{
+    const int64_t c64 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const CandSoA &cd = a.cd;
+    const bool force = a.up.force_strand != 0;
+    const int lane = lane_id();
+    uint32_t ls = FF_BIG, d = 64u, gb_c = 0; int nc = 0; uint64_t sig_c = 0, j0_c = 0; int mono_c = 0;
+    bool is_rep = false;
+    if (c64 < cand_count(a)) {
+        ls = lstart[c64];
+        if (ls != FF_BIG) {
+            d = a.desc[c64];
+            is_rep = !(d & 64u) && (d & 63u) == (uint32_t)c64 - ls && (uint32_t)c64 > ls;      // multi-exon representative with predecessors
+            if (is_rep) { nc = cd.n[c64]; sig_c = cd.sig[c64]; j0_c = cd.j0[c64]; gb_c = cd.gbeg[c64]; mono_c = (cd.rev[c64] & 2) != 0; }
+        }
+    }
+    for (unsigned m = __ballot_sync(FULL, is_rep); m; m &= m - 1) {
+        const int src = __ffs(m) - 1;
+        const uint32_t r_c = (uint32_t)__shfl_sync(FULL, (uint32_t)c64, src), r_ls = __shfl_sync(FULL, ls, src), r_d = __shfl_sync(FULL, d, src);
+        const uint32_t r_gb = __shfl_sync(FULL, gb_c, src);
+        const int r_n = __shfl_sync(FULL, nc, src), r_mono = __shfl_sync(FULL, mono_c, src);
+        const uint64_t r_sig = __shfl_sync(FULL, sig_c, src), r_j0 = __shfl_sync(FULL, j0_c, src);
+        for (uint32_t e = r_ls + (uint32_t)lane; e < r_c; e += 32) {
+            const uint32_t de = a.desc[e];
+            if ((de & 64u) || (de & 63u) != e - r_ls || ((de ^ r_d) & 0x300u)) continue;          // single / not a representative / other sub-stream
+            if (force && ((de ^ r_d) & 128u)) continue;
+            const int ne = cd.n[e];
+            if (ne == r_n) continue;
+            bool hit;
+            if (r_n > ne) {
+                const uint64_t j0_e = cd.j0[e];
+                hit = ((r_sig >> junc_bit(j0_e)) & 1ull) && partial_static(a.ex, r_gb, r_n, r_mono != 0, j0_e, cd.gbeg[e], ne);
+            } else
+                hit = ((cd.sig[e] >> junc_bit(r_j0)) & 1ull) && partial_static(a.ex, cd.gbeg[e], ne, (cd.rev[e] & 2) != 0, r_j0, r_gb, r_n);
+            if (hit) {
+                atomicOr((unsigned long long *)&a.relsym[r_c], 1ull << (e - r_ls));
+                atomicOr((unsigned long long *)&a.relsym[e], 1ull << (r_c - r_ls));
+            }
+        }
+    }
+}
+
 // per candidate: the mask (over the <= 63 earlier candidates of its locus) of the entries that could absorb it -- members of its
 // own class (identical chains), members of classes in partial-match relation, other single-exon reads -- and, for class
 // folds, the mask of the earlier candidates of its own sub-stream
@@ -1108,11 +1159,15 @@ __global__ void __launch_bounds__(FR_THREADS) fold_rel_kernel(MergeArgs a, uint3
 // of merge_trans is a walk down the slots; a locus with more than FS_SLOTS survivors is handed to merge_fold_kernel.
 // A slot keeps exon[0].start / exon[last].end; T.start / T.end equal them except for a split piece that was not extended
 // yet (0 / 0) -- two flag bits.
-static constexpr int FS_THREADS = 64, FS_SLOTS = 32;
+// T.tid of an entry is not stored: the candidates of a locus carry one non-zero tid (checked; a locus mixing chromosomes -- unsorted
+// input -- goes to merge_fold_kernel), so "t.tid > T.tid" (update_gtf.c:148) can only hold for an entry with tid 0 (a split piece,
+// flag bit 4) under a candidate with tid > 0.
+static constexpr int FS_THREADS = 64;
+template <int FS_SLOTS>
 __global__ void __launch_bounds__(FS_THREADS) fold_seq_kernel(MergeArgs a, const uint32_t *__restrict__ rep, const uint64_t *__restrict__ evmask,
                                                               uint8_t *locus_hard, uint8_t *alive_out)
 {
-    __shared__ int s_tid[FS_SLOTS][FS_THREADS], s_fs[FS_SLOTS][FS_THREADS], s_le[FS_SLOTS][FS_THREADS];
+    __shared__ int s_fs[FS_SLOTS][FS_THREADS], s_le[FS_SLOTS][FS_THREADS];
     __shared__ uint8_t s_cov[FS_SLOTS][FS_THREADS], s_rep[FS_SLOTS][FS_THREADS], s_cand[FS_SLOTS][FS_THREADS], s_flag[FS_SLOTS][FS_THREADS];
     const int t = threadIdx.x;
     const int64_t loc = (int64_t)blockIdx.x * FS_THREADS + t;
@@ -1125,7 +1180,7 @@ __global__ void __launch_bounds__(FS_THREADS) fold_seq_kernel(MergeArgs a, const
     const int end_dis = a.up.end_dis;
     const bool end_free = end_dis == 0x7fffffff;                      // the default: check_iden's end tests always pass
     uint64_t alive = 0;
-    int cnt = 0;
+    int cnt = 0, ltid = 0;
     // candidate k+1 is loaded while candidate k is folded
     int t_tid = cd.tid[ls], t_start = cd.start[ls], t_end = cd.end[ls], nc = cd.n[ls], fs = cd.fs[ls], lend = cd.le[ls];
     uint32_t rc = rep[ls]; uint64_t ev = evmask[ls], same = a.kls ? a.samemask[ls] : ~0ull;
@@ -1137,14 +1192,18 @@ __global__ void __launch_bounds__(FS_THREADS) fold_seq_kernel(MergeArgs a, const
             t_tid = cd.tid[c + 1]; t_start = cd.start[c + 1]; t_end = cd.end[c + 1]; nc = cd.n[c + 1]; fs = cd.fs[c + 1]; lend = cd.le[c + 1];
             rc = rep[c + 1]; ev = evmask[c + 1]; if (a.kls) same = a.samemask[c + 1];
         }
+        if (c_tid != 0) {                                             // unsorted input can put two chromosomes into one locus: not for the slots
+            if (ltid == 0) ltid = c_tid; else if (c_tid != ltid) { locus_hard[ls] = 1; return; }
+        }
         int kind = 0, hit = 0;                                        // kind: 0 append, 1 merge (identical), 2 drop (partial)
         for (int sl = cnt - 1; sl >= 0; --sl) {
             const int b = s_cand[sl][t];
             if (!(c_ev & alive & ((2ull << b) - 1ull))) break;        // no candidate event at or below this entry: append whatever the stops say
             if (!((c_same >> b) & 1ull)) continue;                    // another sub-stream: invisible
             const int efs = s_fs[sl][t], ele = s_le[sl][t];
-            const int e_end = (s_flag[sl][t] & 2) ? 0 : ele;          // T.end
-            if (c_tid > s_tid[sl][t] || c_start > e_end) break;       // update_gtf.c:148
+            const int fl = s_flag[sl][t];
+            const int e_end = (fl & 2) ? 0 : ele;                     // T.end
+            if (((fl & 4) && c_tid > 0) || c_start > e_end) break;    // update_gtf.c:148
             if ((c_ev >> b) & 1ull) {
                 bool ok = true;
                 if (!end_free || c_n == 1) {
@@ -1161,9 +1220,9 @@ __global__ void __launch_bounds__(FS_THREADS) fold_seq_kernel(MergeArgs a, const
         } else if (kind == 0) {
             if (cnt == FS_SLOTS) { locus_hard[ls] = 1; return; }      // too many survivors for the slots: merge_fold_kernel redoes the locus
             alive |= 1ull << k;
-            s_tid[cnt][t] = c_tid; s_fs[cnt][t] = c_fs; s_le[cnt][t] = c_le; s_cov[cnt][t] = 1;
+            s_fs[cnt][t] = c_fs; s_le[cnt][t] = c_le; s_cov[cnt][t] = 1;
             s_rep[cnt][t] = (uint8_t)c_rep; s_cand[cnt][t] = (uint8_t)k;
-            s_flag[cnt][t] = (uint8_t)((c_start != c_fs ? 1 : 0) | (c_end != c_le ? 2 : 0));   // only an unextended piece (start = end = 0)
+            s_flag[cnt][t] = (uint8_t)((c_start != c_fs ? 1 : 0) | (c_end != c_le ? 2 : 0) | (c_tid == 0 ? 4 : 0));   // bits 0,1: only an unextended piece (start = end = 0)
             ++cnt;
         }
         alive_out[c] = kind == 0 ? 1 : 0;
@@ -1225,10 +1284,19 @@ void launch_merge_fold(const MergeArgs &a, cudaStream_t st)
         if (fused) { fold_rel_kernel<<<bl, FR_THREADS, 0, st>>>(a, a.rep, a.lstart, a.evmask, a.hard); LRB_COUNT_LAUNCH(); }
         else {
             fold_rep_kernel<<<bl, 256, 0, st>>>(a, a.rep, a.lstart, a.hard); LRB_COUNT_LAUNCH();
-            fold_relrep_kernel<<<bl, 256, 0, st>>>(a, a.lstart); LRB_COUNT_LAUNCH();
+            static int relw = -1;
+            if (relw < 0) { const char *e = getenv("LRB_FOLD_RELW"); relw = e ? atoi(e) : 0; }
+            if (relw) fold_relrep_warp_kernel<<<bl, 256, 0, st>>>(a, a.lstart); else fold_relrep_kernel<<<bl, 256, 0, st>>>(a, a.lstart);
+            LRB_COUNT_LAUNCH();
             fold_relasm_kernel<<<bl, 256, 0, st>>>(a, a.lstart, a.evmask); LRB_COUNT_LAUNCH();
         }
-        fold_seq_kernel<<<(unsigned)((a.n_cand + FS_THREADS - 1) / FS_THREADS), FS_THREADS, 0, st>>>(a, a.rep, a.evmask, a.hard, a.dropped); LRB_COUNT_LAUNCH();
+        static int slots = -1;
+        if (slots < 0) { const char *e = getenv("LRB_FOLD_SLOTS"); slots = e ? atoi(e) : 32; }
+        const unsigned bs = (unsigned)((a.n_cand + FS_THREADS - 1) / FS_THREADS);
+        if (slots <= 16) fold_seq_kernel<16><<<bs, FS_THREADS, 0, st>>>(a, a.rep, a.evmask, a.hard, a.dropped);
+        else if (slots <= 24) fold_seq_kernel<24><<<bs, FS_THREADS, 0, st>>>(a, a.rep, a.evmask, a.hard, a.dropped);
+        else fold_seq_kernel<32><<<bs, FS_THREADS, 0, st>>>(a, a.rep, a.evmask, a.hard, a.dropped);
+        LRB_COUNT_LAUNCH();
         // loci beyond the masks, and the (hash-collision) hard ones
         int64_t bl2 = (a.n_cand / (FF_MAX + 1) + 1 + 3) / 4 + 8; if (bl2 > 148 * 8) bl2 = 148 * 8;
         merge_fold_kernel<32><<<(unsigned)bl2, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, a.hard, FF_MAX + 1, 0x7fffffff);

@@ -299,3 +299,27 @@ def test_update_fetch_table(ctx, data, which):
     assert_dict_equal(t["bed"], g["bed"])
     assert np.array_equal(t["summary"], g["summary"])
     assert (t["table"]["piece"] >= 0).sum() > 0
+
+
+def test_unique_unsorted_concatenation(ctx, data):
+    """unique-gtf -m g on a CONCATENATION of samples (Snakefile:189-192: not globally sorted): loci then mix chromosomes and
+    the early-stop quirks of merge_trans (update_gtf.c:148) decide; the fold must follow the port there too."""
+    _, chains = _kept_chains(data, "iso")
+    off = chains["exon_off"].astype(np.int64)
+    n = len(chains["tid"])
+    rng = np.random.default_rng(7)
+    halves = [np.sort(rng.choice(n, n // 2, replace=False)), np.sort(rng.choice(n, n // 3, replace=False)), np.arange(0, n, 5)[::-1].copy()]
+    order = np.concatenate(halves)
+    cnt = (off[1:] - off[:-1])[order]
+    eo = np.zeros(len(order) + 1, np.uint32); eo[1:] = np.cumsum(cnt)
+    idx = np.concatenate([np.arange(off[r], off[r + 1]) for r in order])
+    cat = dict(tid=chains["tid"][order].copy(), is_rev=chains["is_rev"][order].copy(), exon_off=eo,
+               exon_start=chains["exon_start"][idx].copy(), exon_end=chains["exon_end"][idx].copy())
+    for kw in (dict(), dict(force_strand=1), dict(ss_dis=3)):
+        up = cabi.UpdateParams.default(**kw)
+        ctx.upload_chains(cat)
+        g = ctx.unique_gtf(None, cabi.ExonParams.default(), up)
+        rc, o = op.unique(dict(cat, read_idx=None, n_reads=len(order)), up)
+        assert rc == 0
+        o["ex"]["read_idx"] = g["ex"]["read_idx"]
+        assert_dict_equal(g, o)

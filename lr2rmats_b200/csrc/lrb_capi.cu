@@ -59,6 +59,7 @@ struct lrb_ctx {
     // side stream: work of a stage that is independent of its main chain (the class folds of the summary) runs here,
     // forked / joined with events, on its own look-back state
     cudaStream_t st2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool side_stream = true;
+    cudaStream_t st3 = nullptr; cudaEvent_t ev_fork3 = nullptr, ev_join3 = nullptr; bool sum_split = true;   // exon chain of the summary sets
     // tables
     DAnno anno; DSj sj; DRmIndex rm;
     Buf a_tid, a_start, a_end, a_gene, a_rev, a_off, a_es, a_ee, a_pmax, a_mono;
@@ -322,6 +323,9 @@ int lrb_ctx_create(int device, lrb_ctx **out)
     if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { delete c; return LRB_E_CUDA; }
     if (cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(c->st); delete c; return LRB_E_CUDA; }
     cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
+    if (cudaStreamCreateWithFlags(&c->st3, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(c->st2); cudaStreamDestroy(c->st); delete c; return LRB_E_CUDA; }
+    cudaEventCreateWithFlags(&c->ev_fork3, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming);
+    { const char *e = getenv("LRB_SUM_SPLIT"); if (e) c->sum_split = atoi(e) != 0; }
     { const char *e = getenv("LRB_SIDE_STREAM"); if (e) c->side_stream = atoi(e) != 0; }
     if (!c->scalars.ensure(512) || !c->h_scalars.ensure(512)) { delete c; return LRB_E_NOMEM; }
     cudaMemsetAsync(c->scalars.p, 0, 512, c->st);
@@ -337,7 +341,7 @@ void lrb_ctx_destroy(lrb_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->st); cudaStreamSynchronize(c->st2);
+    cudaStreamSynchronize(c->st); cudaStreamSynchronize(c->st2); cudaStreamSynchronize(c->st3);
     Buf *bufs[] = {&c->a_tid, &c->a_start, &c->a_end, &c->a_gene, &c->a_rev, &c->a_off, &c->a_es, &c->a_ee, &c->a_pmax, &c->a_mono, &c->s_tid, &c->s_don, &c->s_acc,
                    &c->s_u, &c->s_m, &c->s_pmax, &c->s_dkey, &c->r_gtid, &c->r_goff, &c->r_start, &c->r_pmax, &c->b_tid, &c->b_pos, &c->b_lq, &c->b_nm,
                    &c->b_flag, &c->b_xs, &c->b_qh, &c->b_coff, &c->b_cig, &c->f_pass, &c->f_score, &c->f_intron, &c->f_keep_row_mask, &c->f_keep_rec_mask,
@@ -359,6 +363,7 @@ void lrb_ctx_destroy(lrb_ctx *c)
     for (int i = 0; i < 12; ++i) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 8; ++i) cudaEventDestroy(c->marks[i]);
     cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
+    cudaEventDestroy(c->ev_fork3); cudaEventDestroy(c->ev_join3); cudaStreamDestroy(c->st3);
     cudaStreamDestroy(c->st2); cudaStreamDestroy(c->st);
     delete c;
 }
@@ -750,8 +755,8 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
         sa.bed_tid = c->bd_tid.as<int32_t>(); sa.bed_start = c->bd_s.as<int32_t>(); sa.bed_end = c->bd_e.as<int32_t>(); sa.bed_score = c->bd_sc.as<int32_t>();
         sa.bed_type = c->bd_ty.as<uint8_t>(); sa.bed_rev = c->bd_rv.as<uint8_t>();
         CK(cudaMemsetAsync(c->y_counts.p, 0, 32, c->st));
-        launch_summary_sets(sa, ca.cls, n, c->tile_state.as<uint64_t>(), (uint32_t *)(c->y_nelem.as<uint8_t>() + 16), T + T_BED, c->st);
-        launch_summary_bed(sa, c->st);
+        launch_summary_sets(sa, ca.cls, n, c->tile_state.as<uint64_t>(), (uint32_t *)(c->y_nelem.as<uint8_t>() + 16), T + T_BED, c->st,
+                            c->sum_split ? c->st3 : c->st, c->ev_fork3, c->ev_join3);
         CK(cudaGetLastError());
         if (c->side_stream) CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
         uint8_t *hp = (uint8_t *)c->h_scalars.p;

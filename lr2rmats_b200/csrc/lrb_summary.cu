@@ -106,16 +106,50 @@ __global__ void sum_count_kernel(SummaryArgs a, unsigned long long *n_elems)
     if (lane_id() == 0 && c) { atomicAdd(n_elems, (unsigned long long)c); if (cx) atomicAdd(n_elems + 1, (unsigned long long)cx); }
 }
 
+// The exon set does not interact with the other four (plain first occurrence, its own keys), so it runs as its own chain
+// of kernels on a side stream (insert -> count -> scan -> BED rows) next to the barrier-aware chain of the gene / site /
+// junction sets: both are bound by dependent table look-ups, not by throughput, and overlap almost completely.
+// `parts` bit 0: the exon elements are handled by this launch (0 when the exon chain runs separately).
+__global__ void sum_exon_insert_kernel(SummaryArgs a)
+{
+    SUM_ENTRY_PROLOGUE(a.n_upd)
+    EntryView e = load_entry(a, i);
+    const uint8_t *f = a.ex.flag + e.gbeg;
+    for (int j = gl; j < e.n; j += SG)
+        if (f[j] & LRB_F_NOVEL_EXON) {
+            uint64_t s = tab_upsert(a.tab, key_hi(SET_E, 0, e.real_tid), key_lo(ent_s(a, e, j), ent_e(a, e, j)));
+            tab_min(a.tab, s, pos_of(i, j));
+            atomicAdd(&a.tab.slots[s].score, e.cov);
+        }
+}
+__global__ void sum_exon_count_kernel(SummaryArgs a)
+{
+    SUM_ENTRY_PROLOGUE(a.n_upd)
+    EntryView e = load_entry(a, i);
+    const uint8_t *f = a.ex.flag + e.gbeg;
+    int ce = 0;
+    for (int j = gl; j < e.n; j += SG)
+        if (f[j] & LRB_F_NOVEL_EXON) {
+            uint64_t s = tab_find(a.tab, key_hi(SET_E, 0, e.real_tid), key_lo(ent_s(a, e, j), ent_e(a, e, j)));
+            ce += a.tab.slots[s].minpos == pos_of(i, j);
+        }
+    ce = group_sum<SG>(gm, ce);
+    if (gl != 0) return;
+    a.bed_cnt[i] = ce;
+    if (ce) atomicAdd(&a.counts[SET_E], (uint32_t)ce);
+}
+
 // phase 1: exons (all entries), tid-0 elements of D/A/J, every gene element (gene equality ignores tid)
-__global__ void sum_phase1_kernel(SummaryArgs a)
+__global__ void sum_phase1_kernel(SummaryArgs a, int parts)
 {
     SUM_ENTRY_PROLOGUE(a.n_upd)
     EntryView e = load_entry(a, i);
     const uint8_t *f = a.ex.flag + e.gbeg;
     if (gl == 0) tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_G, SEG_TID0, 0), key_lo(e.gene, 0)), pos_of(i, 0));
+    if (!(parts & 1) && e.t_tid != 0) return;
     for (int j = gl; j < e.n; j += SG) {
         uint8_t x = f[j];
-        if (x & LRB_F_NOVEL_EXON) {
+        if ((parts & 1) && (x & LRB_F_NOVEL_EXON)) {
             uint64_t s = tab_upsert(a.tab, key_hi(SET_E, 0, e.real_tid), key_lo(ent_s(a, e, j), ent_e(a, e, j)));
             tab_min(a.tab, s, pos_of(i, j));
             atomicAdd(&a.tab.slots[s].score, e.cov);
@@ -129,7 +163,7 @@ __global__ void sum_phase1_kernel(SummaryArgs a)
 }
 
 // phase 2: per entry, how many of its tid-0 elements were inserted (= barriers), per set; exon first occurrences
-__global__ void sum_phase2_kernel(SummaryArgs a)
+__global__ void sum_phase2_kernel(SummaryArgs a, int parts)
 {
     SUM_ENTRY_PROLOGUE(a.n_upd)
     EntryView e = load_entry(a, i);
@@ -139,9 +173,9 @@ __global__ void sum_phase2_kernel(SummaryArgs a)
         uint64_t s = tab_find(a.tab, key_hi(SET_G, SEG_TID0, 0), key_lo(e.gene, 0));
         cg = a.tab.slots[s].minpos == pos_of(i, 0);
     }
-    for (int j = gl; j < e.n; j += SG) {
+    for (int j = gl; j < e.n && ((parts & 1) || e.t_tid == 0); j += SG) {
         uint8_t x = f[j];
-        if (x & LRB_F_NOVEL_EXON) {
+        if ((parts & 1) && (x & LRB_F_NOVEL_EXON)) {
             uint64_t s = tab_find(a.tab, key_hi(SET_E, 0, e.real_tid), key_lo(ent_s(a, e, j), ent_e(a, e, j)));
             ce += a.tab.slots[s].minpos == pos_of(i, j);
         }
@@ -155,7 +189,7 @@ __global__ void sum_phase2_kernel(SummaryArgs a)
     if (e.t_tid == 0) { cd = group_sum<SG>(gm, cd); ca = group_sum<SG>(gm, ca); cj = group_sum<SG>(gm, cj); cg = group_sum<SG>(gm, cg); }
     if (gl != 0) return;
     a.bar_cnt[0 * a.n_upd + i] = cd; a.bar_cnt[1 * a.n_upd + i] = ca; a.bar_cnt[2 * a.n_upd + i] = cj; a.bar_cnt[3 * a.n_upd + i] = cg;
-    a.bed_cnt[i] = ce;
+    if (parts & 1) a.bed_cnt[i] = ce;
     a.gene_bar[i] = cg ? (uint64_t)(i + 1) : 0;       // for the "last inserted tid-0 gene entry before x" max-scan
     if (cd | ca | cj | cg) {
         if (cd) atomicAdd(&a.counts[SET_D], (uint32_t)cd);
@@ -247,10 +281,10 @@ __global__ void sum_bed_kernel(SummaryArgs a)
 // barrier counts, 4 inclusive running max of gene_bar in place, 5 exclusive sum of bed_cnt with its total); every
 // sequence has its own ticket and look-back words
 static constexpr int MS_THREADS = 256, MS_ITEMS = 8;
-__global__ void __launch_bounds__(MS_THREADS) sum_scans_kernel(SummaryArgs a, uint64_t *tile_state, uint32_t *tickets, int n_tiles, uint64_t *bed_total)
+__global__ void __launch_bounds__(MS_THREADS) sum_scans_kernel(SummaryArgs a, uint64_t *tile_state, uint32_t *tickets, int n_tiles, uint64_t *bed_total, int which0)
 {
     __shared__ uint32_t s_scan[33]; __shared__ uint64_t s_w[MS_THREADS / 32]; __shared__ uint32_t s_tile; __shared__ uint64_t s_excl;
-    const int which = blockIdx.y;
+    const int which = which0 + blockIdx.y;
     if (threadIdx.x == 0) s_tile = atomicAdd(tickets + which, 1u);
     __syncthreads();
     const int tile = (int)s_tile, lane = lane_id(), w = warp_id();
@@ -310,25 +344,34 @@ void launch_summary_count(const SummaryArgs &a, unsigned long long *n_elems, cud
     if (a.n_upd <= 0) return;
     sum_count_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a, n_elems); LRB_COUNT_LAUNCH();
 }
-// tile_state: 6 * (n_upd / 2048 + 1) words; tickets: 6 words (zeroed here)
-void launch_summary_sets(const SummaryArgs &a, const uint32_t *cls, int64_t n_rows, uint64_t *tile_state, uint32_t *tickets, uint64_t *bed_total, cudaStream_t st)
+// tile_state: 6 * (n_upd / 2048 + 1) words; tickets: 6 words (zeroed here).  st_exon != st: the exon chain (and the BED rows)
+// runs on st_exon between ev_fork and ev_join; st waits for ev_join at the end
+void launch_summary_sets(const SummaryArgs &a, const uint32_t *cls, int64_t n_rows, uint64_t *tile_state, uint32_t *tickets, uint64_t *bed_total,
+                         cudaStream_t st, cudaStream_t st_exon, cudaEvent_t ev_fork, cudaEvent_t ev_join)
 {
+    const bool split = st_exon != st && a.n_upd > 0;
+    const int n_tiles = (int)((a.n_upd + MS_THREADS * MS_ITEMS - 1) / (MS_THREADS * MS_ITEMS));
+    if (a.n_upd > 0) { cudaMemsetAsync(tile_state, 0, (size_t)n_tiles * 6 * 8, st); cudaMemsetAsync(tickets, 0, 6 * 4, st); }
+    if (split) {
+        cudaEventRecord(ev_fork, st); cudaStreamWaitEvent(st_exon, ev_fork, 0);
+        sum_exon_insert_kernel<<<nblk_g(a.n_upd), 256, 0, st_exon>>>(a); LRB_COUNT_LAUNCH();
+        sum_exon_count_kernel<<<nblk_g(a.n_upd), 256, 0, st_exon>>>(a); LRB_COUNT_LAUNCH();
+        sum_scans_kernel<<<dim3((unsigned)n_tiles, 1), MS_THREADS, 0, st_exon>>>(a, tile_state, tickets, n_tiles, bed_total, 5); LRB_COUNT_LAUNCH();
+        sum_bed_kernel<<<nblk_g(a.n_upd), 256, 0, st_exon>>>(a); LRB_COUNT_LAUNCH();
+        cudaEventRecord(ev_join, st_exon);
+    }
+    const int parts = split ? 0 : 1;
     if (n_rows > 0) { sum_known_genes_kernel<<<nblk(n_rows), 256, 0, st>>>(a, cls, n_rows, 0); LRB_COUNT_LAUNCH(); }
     if (a.n_upd > 0) {
-        sum_phase1_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
-        sum_phase2_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
-        const int n_tiles = (int)((a.n_upd + MS_THREADS * MS_ITEMS - 1) / (MS_THREADS * MS_ITEMS));
-        cudaMemsetAsync(tile_state, 0, (size_t)n_tiles * 6 * 8, st); cudaMemsetAsync(tickets, 0, 6 * 4, st);
-        sum_scans_kernel<<<dim3((unsigned)n_tiles, 6), MS_THREADS, 0, st>>>(a, tile_state, tickets, n_tiles, bed_total); LRB_COUNT_LAUNCH();
+        sum_phase1_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a, parts); LRB_COUNT_LAUNCH();
+        sum_phase2_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a, parts); LRB_COUNT_LAUNCH();
+        sum_scans_kernel<<<dim3((unsigned)n_tiles, split ? 5 : 6), MS_THREADS, 0, st>>>(a, tile_state, tickets, n_tiles, bed_total, 0); LRB_COUNT_LAUNCH();
         sum_phase3_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
         sum_phase4_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
     } else cudaMemsetAsync(bed_total, 0, 8, st);
     if (n_rows > 0) { sum_known_genes_kernel<<<nblk(n_rows), 256, 0, st>>>(a, cls, n_rows, 1); LRB_COUNT_LAUNCH(); }
-}
-void launch_summary_bed(const SummaryArgs &a, cudaStream_t st)
-{
-    if (a.n_upd <= 0) return;
-    sum_bed_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
+    if (split) cudaStreamWaitEvent(st, ev_join, 0);
+    else if (a.n_upd > 0) { sum_bed_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH(); }
 }
 
 }  // namespace lrbk

@@ -26,8 +26,9 @@ struct SummaryArgs {
 };
 
 void launch_summary_count(const SummaryArgs &a, unsigned long long *n_elems, cudaStream_t st);
-void launch_summary_sets(const SummaryArgs &a, const uint32_t *cls, int64_t n_rows, uint64_t *tile_state, uint32_t *ticket, uint64_t *bed_total, cudaStream_t st);
-void launch_summary_bed(const SummaryArgs &a, cudaStream_t st);
+// all sets + BED rows; the exon chain runs on st_exon (pass st for a single stream)
+void launch_summary_sets(const SummaryArgs &a, const uint32_t *cls, int64_t n_rows, uint64_t *tile_state, uint32_t *ticket, uint64_t *bed_total,
+                         cudaStream_t st, cudaStream_t st_exon, cudaEvent_t ev_fork, cudaEvent_t ev_join);
 
 // from lrb_update.cu
 void launch_rows_as_list(const DRows &rows, const uint32_t *subset, int64_t n, DTransList &out, cudaStream_t st);

@@ -252,6 +252,11 @@ int lrb_exon_run(lrb_ctx *ctx, const lrb_exon_params *p, int use_keep_list);  /*
 int lrb_pipeline_run(lrb_ctx *ctx, const lrb_filter_params *fp, const lrb_exon_params *ep); /* fused filter + exon pass */
 int lrb_update_run(lrb_ctx *ctx, const lrb_update_params *p);                 /* update_gtf.c:936-965 (+421-587) */
 int lrb_unique_run(lrb_ctx *ctx, const lrb_update_params *p);                 /* unique_gtf.c:73-84 */
+/* Coordinate sort of the current rows on the device (after lrb_exon_run / lrb_pipeline_run / lrb_chains_upload, before
+ * lrb_update_run): replaces the external `samtools sort` between `lr2rmats filter` and `lr2rmats update-gtf`
+ * (Snakefile:90); update_gtf needs (tid,start)-sorted input (update_gtf.c:41).  Stable, samtools' coordinate key
+ * tid << 32 | (pos + 1) << 1 | FLAG 0x10; row r of the later results refers to record read_idx[r] of the batch. */
+int lrb_rows_sort(lrb_ctx *ctx);
 int lrb_sync(lrb_ctx *ctx);
 
 /* Results -> pinned host buffers owned by the ctx. */

@@ -19,7 +19,7 @@ CLI_PATH = os.path.join(_HERE, "host", "lr2rmats-b200")
 ENTRY_POINTS = [
     "lrb_ctx_create", "lrb_ctx_destroy", "lrb_last_error", "lrb_version", "lrb_anno_upload", "lrb_rm_upload", "lrb_sj_upload",
     "lrb_batch_upload", "lrb_chains_upload", "lrb_filter_run", "lrb_exon_run", "lrb_pipeline_run", "lrb_update_run", "lrb_unique_run",
-    "lrb_sync", "lrb_filter_fetch", "lrb_exon_fetch", "lrb_update_fetch", "lrb_unique_fetch", "lrb_filter", "lrb_bam2gtf",
+    "lrb_sync", "lrb_rows_sort", "lrb_filter_fetch", "lrb_exon_fetch", "lrb_update_fetch", "lrb_unique_fetch", "lrb_filter", "lrb_bam2gtf",
     "lrb_update_gtf", "lrb_unique_gtf", "lrb_timing_enable", "lrb_timing_get", "lrb_launch_count", "lrb_shard_cuts",
     "lrb_mark", "lrb_elapsed_ms", "lrb_host_alloc", "lrb_host_free", "lrb_update_fetch_table", "lrb_filter_fetch_keep",
 ]
@@ -61,6 +61,7 @@ def load_library():
     L.lrb_update_run.argtypes = [vp, P(cabi.UpdateParams)]
     L.lrb_unique_run.argtypes = [vp, P(cabi.UpdateParams)]
     L.lrb_sync.argtypes = [vp]
+    L.lrb_rows_sort.argtypes = [vp]
     L.lrb_filter_fetch.argtypes = [vp, P(cabi.FilterResult)]
     L.lrb_exon_fetch.argtypes = [vp, P(cabi.ExonResult)]
     L.lrb_filter_fetch_keep.argtypes = [vp, P(C.c_int64), P(cabi.u32p)]
@@ -146,6 +147,7 @@ class Context:
     def update_run(self, p): self._ck(self.L.lrb_update_run(self.h, C.byref(p)))
     def unique_run(self, p): self._ck(self.L.lrb_unique_run(self.h, C.byref(p)))
     def sync(self): self._ck(self.L.lrb_sync(self.h))
+    def rows_sort(self): self._ck(self.L.lrb_rows_sort(self.h))          # device-side `samtools sort` of the kept rows
 
     def filter_fetch(self) -> dict:
         r = cabi.FilterResult(); self._ck(self.L.lrb_filter_fetch(self.h, C.byref(r))); return cabi.filter_to_np(r)

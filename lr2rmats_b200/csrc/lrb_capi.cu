@@ -12,7 +12,7 @@
 #include "lrb_kernels.cuh"
 #include "lrb_summary.cuh"
 
-namespace lrbk { extern int64_t g_launches_update, g_launches_summary; }
+namespace lrbk { extern int64_t g_launches_update, g_launches_summary, g_launches_sort; }
 using namespace lrbk;
 
 namespace {
@@ -72,9 +72,10 @@ struct lrb_ctx {
     Buf f_pass, f_score, f_intron, f_keep_row_mask, f_keep_rec_mask, f_keep_idx, f_keep_rows;
     int64_t n_pass = 0, n_keep = 0; bool have_filter = false;
     // rows + exons
-    DRows rows, rows2; DRows *cur = nullptr; DExons ex;
+    DRows rows, rows2, rows3; DRows *cur = nullptr; DExons ex;      // rows3: the coordinate-sorted copy made by lrb_rows_sort
     Buf r_read, r_tid, r_rs, r_re, r_rev, r_beg, r_n, r_nonmono;
     Buf q_read, q_tid, q_rs, q_re, q_rev, q_beg, q_n;
+    Buf s_read, s_rtid, s_rs, s_re, s_rev, s_beg, s_n, s_key0, s_key1, s_idx0, s_idx1, s_hist;   // lrb_rows_sort
     Buf e_s, e_e, e_f;
     bool have_exons = false, rows_compact = false;
     // update
@@ -101,7 +102,7 @@ struct lrb_ctx {
 
 namespace {
 
-int64_t total_launches() { return lrbk::count_launches() + lrbk::g_launches_update + lrbk::g_launches_summary; }
+int64_t total_launches() { return lrbk::count_launches() + lrbk::g_launches_update + lrbk::g_launches_summary + lrbk::g_launches_sort; }
 
 int fail(lrb_ctx *c, int code, const std::string &msg) { c->err = msg; return code; }
 #define CK(call)                                                                                               \
@@ -350,6 +351,7 @@ void lrb_ctx_destroy(lrb_ctx *c)
                    &c->u_mu, &c->u_ck, &c->u_cr, &c->u_cu, &c->u_cn, &c->u_known, &c->u_unrecog, &c->u_sub, &c->n_row, &c->n_lo, &c->n_cnt, &c->n_piece,
                    &c->t_row, &c->t_lo, &c->t_cnt, &c->t_piece, &c->h_khi, &c->h_klo, &c->h_min, &c->h_score, &c->y_barcnt, &c->y_barseg, &c->y_genebar,
                    &c->y_bedcnt, &c->y_bedoff, &c->y_counts, &c->y_nelem, &c->bd_tid, &c->bd_s, &c->bd_e, &c->bd_sc, &c->bd_ty, &c->bd_rv, &c->q_shared, &c->tb_name, &c->tb_piece, &c->tb_ttid, &c->tb_tstart, &c->tb_tend, &c->tb_trev, &c->tb_etid, &c->tb_erev, &c->tb_cov, &c->tb_ref, &c->tb_cnt, &c->tb_off, &c->tb_es, &c->tb_ee,
+                   &c->s_read, &c->s_rtid, &c->s_rs, &c->s_re, &c->s_rev, &c->s_beg, &c->s_n, &c->s_key0, &c->s_key1, &c->s_idx0, &c->s_idx1, &c->s_hist,
                    &c->tile_state, &c->tile_state2, &c->scalars};
     for (Buf *b : bufs) b->release();
     for (MergeBufs *m : {&c->mg, &c->mg2}) {
@@ -717,8 +719,13 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
         CK(cudaStreamSynchronize(c->st));
         uint64_t t[T_SLOTS]; uint32_t e[2];
         memcpy(t, hp, sizeof t); memcpy(e, hp + T_SLOTS * 8, 8); memcpy(cnt16, hp + 320, 64); memcpy(&n_elem, hp + 384, 8); memcpy(&n_exon_elem, hp + 392, 8);
-        if (e[1] & 2u) return fail(c, LRB_E_UNMAPPED, "unmapped record / empty exon chain in update/unique input (the reference aborts here, bam2gtf.c:95-100)");
-        if (e[1] & 1u) return fail(c, LRB_E_UNSORTED, "reads are not sorted by (tid,start) (update_gtf.c:41)");
+        if (e[1] & 3u) {
+            // the class folds may still be running on the side stream: they must be over before the caller can start another
+            // stage on this context (they share its buffers and counters)
+            if (up->want_summary && c->side_stream) cudaStreamSynchronize(c->st2);
+            if (e[1] & 2u) return fail(c, LRB_E_UNMAPPED, "unmapped record / empty exon chain in update/unique input (the reference aborts here, bam2gtf.c:95-100)");
+            return fail(c, LRB_E_UNSORTED, "reads are not sorted by (tid,start) (update_gtf.c:41)");
+        }
         n_novel = (int64_t)t[T_NOVEL]; c->n_known = (int64_t)t[T_KNOWN]; c->n_unrecog = (int64_t)t[T_UNREC];
         if (n_novel > cap) {                          // novel_T did not fit: once more with the exact size
             if (attempt >= 1) return fail(c, LRB_E_CUDA, "novel_T size changed between passes");
@@ -815,6 +822,43 @@ int lrb_unique_run(lrb_ctx *c, const lrb_update_params *up)
     tick(c, 1);
     c->have_unique = true; c->launches_last = total_launches() - l0;
     if (c->timing) { CK(cudaStreamSynchronize(c->st)); cudaEventElapsedTime(&c->ms[LRB_T_MERGE], c->ev[0], c->ev[1]); }
+    return LRB_OK;
+}
+
+// Coordinate sort of the current rows on the device: what `samtools sort` does between `lr2rmats filter` and
+// `lr2rmats update-gtf` (Snakefile:90), without leaving HBM.  Stable LSD radix sort on tid << 32 | (pos + 1) << 1 | FLAG 0x10.
+int lrb_rows_sort(lrb_ctx *c)
+{
+    if (!c) return LRB_E_ARG;
+    if (!c->have_exons) return fail(c, LRB_E_ARG, "lrb_rows_sort: exon chains missing (run lrb_exon_run / lrb_pipeline_run / lrb_chains_upload)");
+    CK(cudaSetDevice(c->device));
+    int64_t l0 = total_launches();
+    if (c->cur == &c->rows3) return LRB_OK;                           // sorted already (every upload / stage run resets cur)
+    DRows &rows = *c->cur; const int64_t n = rows.n; int rc;
+    if (n == 0) return LRB_OK;
+    if (n >= (int64_t)1 << 32) return fail(c, LRB_E_ARG, "lrb_rows_sort: more than 2^32 rows");
+    const size_t nn = (size_t)n;
+    NEED(c->s_key0, nn * 8); NEED(c->s_key1, nn * 8); NEED(c->s_idx0, nn * 4); NEED(c->s_idx1, nn * 4);
+    NEED(c->s_hist, (size_t)256 * (size_t)lrbk::sort_tiles(n) * 4);
+    if ((rc = setup_rows(c, c->rows3, c->s_read, c->s_rtid, c->s_rs, c->s_re, c->s_rev, c->s_beg, c->s_n, n))) return rc;
+    unsigned long long *d_max = (unsigned long long *)(d_totals(c) + 3);
+    CK(cudaMemsetAsync(d_max, 0, 8, c->st));
+    launch_sort_keys(rows, c->have_batch ? c->b.flag : nullptr, c->s_key0.as<uint64_t>(), c->s_idx0.as<uint32_t>(), d_max, c->st);
+    CK(cudaGetLastError());
+    uint64_t t[4];
+    if ((rc = read_totals(c, t, 4))) return rc;
+    int bits = 0; for (uint64_t m = t[3]; m; m >>= 1) ++bits;
+    uint64_t *k[2] = {c->s_key0.as<uint64_t>(), c->s_key1.as<uint64_t>()}; uint32_t *v[2] = {c->s_idx0.as<uint32_t>(), c->s_idx1.as<uint32_t>()};
+    int cur = 0;
+    for (int shift = 0; shift < bits; shift += 8) {                  // only the digits the largest key has
+        launch_sort_pass(k[cur], v[cur], k[cur ^ 1], v[cur ^ 1], n, shift, c->s_hist.as<uint32_t>(), c->st);
+        cur ^= 1;
+    }
+    c->rows3.n = n;
+    launch_rows_permute(rows, c->rows3, v[cur], c->st);
+    CK(cudaGetLastError());
+    c->cur = &c->rows3; c->rows_compact = false; c->have_update = c->have_unique = false;
+    c->launches_last = total_launches() - l0;
     return LRB_OK;
 }
 

@@ -146,6 +146,12 @@ void launch_merge_fold(const MergeArgs &a, cudaStream_t st);        // number of
 void launch_merge_class_counts(const MergeArgs &a, cudaStream_t st);
 void launch_merge_finish(MergeArgs a, cudaStream_t st);             // survivors compacted into a.out; totals[1] = their number
 
+// lrb_sort.cu: stable LSD radix sort of rows by samtools' coordinate key
+int sort_tiles(int64_t n);
+void launch_sort_keys(const DRows &rows, const uint16_t *flag, uint64_t *keys, uint32_t *idx, unsigned long long *max_key, cudaStream_t st);
+void launch_sort_pass(const uint64_t *kin, const uint32_t *vin, uint64_t *kout, uint32_t *vout, int64_t n, int shift, uint32_t *hist, cudaStream_t st);
+void launch_rows_permute(const DRows &in, const DRows &out, const uint32_t *perm, cudaStream_t st);
+
 // generic device scans used by the stages above
 void launch_scan_max_u64(uint64_t *data, int64_t n, uint64_t *tile_state, uint32_t *ticket, cudaStream_t st);   // inclusive prefix max, in place
 void launch_scan_sum_u32(const uint32_t *in, uint32_t *out_excl, int64_t n, uint64_t *tile_state, uint32_t *ticket, uint64_t *total, cudaStream_t st);

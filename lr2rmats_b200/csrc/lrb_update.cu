@@ -288,8 +288,8 @@ __global__ void __launch_bounds__(CL_THREADS) classify_kernel(ClassArgs a, const
 // broadcasts and the lanes stay converged.  Per (read, transcript) pair one merge walk over the two sorted exon lists
 // replaces the reference's three nested loops; the four per-exon flag arrays live in four 32-bit registers.
 
-template <int CR_THREADS>
-__global__ void __launch_bounds__(CR_THREADS) classify_row_kernel(ClassArgs a, uint8_t *__restrict__ slow, const uint8_t *__restrict__ row_nonmono, int by_exon_count)
+template <int CR_THREADS, int CR_MINB>
+__global__ void __launch_bounds__(CR_THREADS, CR_MINB) classify_row_kernel(ClassArgs a, uint8_t *__restrict__ slow, const uint8_t *__restrict__ row_nonmono, int by_exon_count)
 {
     __shared__ int s_win[6];
     __shared__ int s_hist[34]; __shared__ uint8_t s_perm[CR_THREADS];
@@ -532,9 +532,12 @@ void launch_classify(const ClassArgs &a, uint8_t *slow, cudaStream_t st)
     if (fast && a.up.ss_dis == 0 && slow) {
         static int crt = -1;
         if (crt < 0) { const char *e = getenv("LRB_CR_THREADS"); crt = e ? atoi(e) : 128; }
-        if (crt >= 256) classify_row_kernel<256><<<(unsigned)((a.rows.n + 255) / 256), 256, 0, st>>>(a, slow, a.row_nonmono, by_n);
-        else if (crt <= 64) classify_row_kernel<64><<<(unsigned)((a.rows.n + 63) / 64), 64, 0, st>>>(a, slow, a.row_nonmono, by_n);
-        else classify_row_kernel<128><<<(unsigned)((a.rows.n + 127) / 128), 128, 0, st>>>(a, slow, a.row_nonmono, by_n);
+        static int minb = -1;
+        if (minb < 0) { const char *e = getenv("LRB_CR_MINB"); minb = e ? atoi(e) : 8; }
+        if (crt >= 256) classify_row_kernel<256, 4><<<(unsigned)((a.rows.n + 255) / 256), 256, 0, st>>>(a, slow, a.row_nonmono, by_n);
+        else if (crt <= 64) classify_row_kernel<64, 16><<<(unsigned)((a.rows.n + 63) / 64), 64, 0, st>>>(a, slow, a.row_nonmono, by_n);
+        else if (minb >= 10) classify_row_kernel<128, 10><<<(unsigned)((a.rows.n + 127) / 128), 128, 0, st>>>(a, slow, a.row_nonmono, by_n);   // <= 51 registers, a few spills
+        else classify_row_kernel<128, 8><<<(unsigned)((a.rows.n + 127) / 128), 128, 0, st>>>(a, slow, a.row_nonmono, by_n);
         LRB_COUNT_LAUNCH();
         only = slow;
     }

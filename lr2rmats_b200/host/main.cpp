@@ -33,11 +33,19 @@ int set_tables(void *s, const lrb_anno *a, const lrb_anno *rm, const lrb_sj *sj)
 }
 int do_filter(void *s, const lrb_batch *b, const lrb_filter_params *p, lrb_filter_result *o) { return lrb_filter(((CudaEngine *)s)->get(), b, p, o); }
 int do_bam2gtf(void *s, const lrb_batch *b, const lrb_exon_params *p, lrb_exon_result *o) { return lrb_bam2gtf(((CudaEngine *)s)->get(), b, p, o); }
+// LRB_SORT_INPUT=1: update-gtf takes a BAM that is NOT coordinate sorted (filter's output as it is) and sorts the rows on the
+// device -- the `samtools sort` hop of the pipeline (Snakefile:90) without the extra BAM round trip
+bool sort_input() { static const bool on = getenv("LRB_SORT_INPUT") && atoi(getenv("LRB_SORT_INPUT")) != 0; return on; }
+
 int do_update(void *s, const lrb_batch *b, const lrb_chains *ch, const lrb_exon_params *ep, const lrb_update_params *up, lrb_update_result *o)
 {
-    lrb_ctx *c = ((CudaEngine *)s)->get();
-    if (!b) { int rc = lrb_chains_upload(c, ch); if (rc) return rc; }
-    return lrb_update_gtf(c, b, ep, up, o);
+    lrb_ctx *c = ((CudaEngine *)s)->get(); int rc;
+    if (!b) { if ((rc = lrb_chains_upload(c, ch))) return rc; }
+    if (!sort_input()) return lrb_update_gtf(c, b, ep, up, o);
+    if (b) { if ((rc = lrb_batch_upload(c, b))) return rc; if ((rc = lrb_exon_run(c, ep, 0))) return rc; }
+    if ((rc = lrb_rows_sort(c))) return rc;
+    if ((rc = lrb_update_run(c, up))) return rc;
+    return lrb_update_fetch(c, o);
 }
 int do_update_table(void *s, const lrb_batch *b, const lrb_chains *ch, const lrb_exon_params *ep, const lrb_update_params *up,
                     lrb_trans_table *tab, lrb_bed_list *bed, int32_t *summary)
@@ -45,6 +53,7 @@ int do_update_table(void *s, const lrb_batch *b, const lrb_chains *ch, const lrb
     lrb_ctx *c = ((CudaEngine *)s)->get(); int rc;
     if (b) { if ((rc = lrb_batch_upload(c, b))) return rc; if ((rc = lrb_exon_run(c, ep, 0))) return rc; }
     else if ((rc = lrb_chains_upload(c, ch))) return rc;
+    if (sort_input() && (rc = lrb_rows_sort(c))) return rc;
     if ((rc = lrb_update_run(c, up))) return rc;
     return lrb_update_fetch_table(c, tab, bed, summary);
 }

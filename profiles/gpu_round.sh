@@ -10,4 +10,4 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --
 python profiles/launch_table.py gpurun_out/launches.csv > gpurun_out/launch_table.txt; cat gpurun_out/launch_table.txt
 [ "$1" = quick ] && exit 0
 # full ncu capture of the heavy kernels of the last step (skip the first two steps)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'cigar_scan|classify_row|fold_rel_|fold_seq|fold_prepare|sum_phase|compact_gather' -s 26 -c 13 -o gpurun_out/prof -f python profiles/run_step.py 1000000 3 > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'cigar_scan|classify_row|fold_relrep|sum_exon|sum_bed|fold_seq|fold_prepare|sum_phase|compact_gather' -s 30 -c 15 -o gpurun_out/prof -f python profiles/run_step.py 1000000 3 > gpurun_out/ncu_full.log 2>&1; tail -3 gpurun_out/ncu_full.log

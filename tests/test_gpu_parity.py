@@ -323,3 +323,79 @@ def test_unique_unsorted_concatenation(ctx, data):
         assert rc == 0
         o["ex"]["read_idx"] = g["ex"]["read_idx"]
         assert_dict_equal(g, o)
+
+
+def _shuffle_runs(reads, seed):
+    """Name-grouped but NOT coordinate-sorted: whole qname runs in random order (what `filter` reads and writes)."""
+    h = reads.qname_hash
+    starts = np.r_[0, np.nonzero(h[1:] != h[:-1])[0] + 1]; ends = np.r_[starts[1:], len(h)]
+    order = np.random.default_rng(seed).permutation(len(starts))
+    return reads.take(np.concatenate([np.arange(starts[k], ends[k]) for k in order]))
+
+
+def _samtools_order(kept):
+    """samtools sort's coordinate key (bam_sort.c bam1_lt): tid, pos, reverse-strand flag; stable."""
+    key = (kept.tid.astype(np.int64) << 32) | ((kept.pos.astype(np.int64) + 1) << 1) | ((kept.flag & 16) != 0).astype(np.int64)
+    return np.argsort(key, kind="stable")
+
+
+@pytest.mark.parametrize("which,one_chrom", [("iso", False), ("ont", False), ("iso", True)])
+def test_rows_sort_replaces_samtools_sort(ctx, data, which, one_chrom):
+    """filter -> [device radix sort] -> update-gtf on coordinate-UNSORTED input equals the oracle on the samtools-sorted
+    kept records (Snakefile:90), row for row; the row -> record map comes back in read_idx."""
+    reads = data[which]
+    if one_chrom:
+        reads = reads.take(np.nonzero(reads.tid <= 0)[0])          # keys below 2^32: one radix pass less
+    sh = _shuffle_runs(reads, 11)
+    fp, ep = cabi.FilterParams.default(), cabi.ExonParams.default()
+    up = cabi.UpdateParams.default(full_level=3, split_trans=1)
+    of = op.filter(sh.soa(), data["rr"], fp)
+    kept = sh.take(of["keep_idx"])
+    order = _samtools_order(kept)
+    assert (np.diff(order) < 0).sum() > len(order) // 4, "the fixture must really be unsorted"
+    oex = op.bam2gtf(kept.take(order).soa(), ep)
+    sj = synth.make_sj((oex["tid"], oex["exon_off"], oex["exon_start"], oex["exon_end"]), 0.7, seed=5)
+    rc, ou = op.update(oex, data["anno"].soa(), sj, up)
+    assert rc == 0
+    ctx.set_anno(data["anno"].soa()); ctx.set_rm(data["rr"]); ctx.set_sj(sj)
+    ctx.upload(sh.soa()); ctx.pipeline_run(fp, ep)
+    with pytest.raises(Exception):
+        ctx.update_run(up)                                         # unsorted input is refused (LRB_E_UNSORTED), not silently mis-swept
+    ctx.upload(sh.soa()); ctx.pipeline_run(fp, ep); ctx.rows_sort(); ctx.rows_sort(); ctx.update_run(up)
+    gu = ctx.update_fetch()
+    assert np.array_equal(gu["ex"]["read_idx"], of["keep_idx"][order])
+    ou["ex"]["read_idx"] = gu["ex"]["read_idx"]
+    assert_dict_equal(gu, ou)
+    assert len(ou["updated"]["cand"]) > 100
+
+
+def test_cli_sort_input(data, tmp_path):
+    """LRB_SORT_INPUT=1: `lr2rmats-b200 update-gtf` on filter's unsorted BAM == the reference binary on the sorted records."""
+    import filecmp, os, subprocess
+    from lr2rmats_b200 import api
+    if not op.have_ref_bin():
+        pytest.skip("reference binary not built")
+    anno, rr = data["anno"], data["rr"]
+    sh = _shuffle_runs(data["iso"], 12)
+    synth.write_gtf(tmp_path / "anno.gtf", anno); synth.write_rm_gtf(tmp_path / "rm.gtf", rr, anno.chrom_names)
+    synth.write_sam(tmp_path / "in.sam", sh, with_seq=True)
+    of = op.filter(sh.soa(), rr, cabi.FilterParams.default())
+    kept = sh.take(of["keep_idx"])
+    synth.write_sam(tmp_path / "sorted.sam", kept.take(_samtools_order(kept)), with_seq=True)     # stands in for `samtools sort`
+    outs = ["-y", "@sum.txt", "-E", "@bed", "-A", "@detail.txt", "-k", "@known.gtf", "-o", "@updated.gtf"]
+    op.run_bin(op.REF_BIN, ["update-gtf", "-l", "3", str(tmp_path / "sorted.sam"), str(tmp_path / "anno.gtf")] + [x.replace("@", str(tmp_path) + "/ref.") for x in outs])
+    with open(tmp_path / "f.bam", "wb") as f:
+        subprocess.run([api.CLI_PATH, "filter", "-r", str(tmp_path / "rm.gtf"), str(tmp_path / "in.sam")], stdout=f, stderr=subprocess.DEVNULL, check=True)
+    env = dict(os.environ, LRB_SORT_INPUT="1")
+    subprocess.run([api.CLI_PATH, "update-gtf", "-l", "3", str(tmp_path / "f.bam"), str(tmp_path / "anno.gtf")] + [x.replace("@", str(tmp_path) + "/our.") for x in outs],
+                   stderr=subprocess.DEVNULL, check=True, env=env)
+    for fn in ("sum.txt", "bed", "detail.txt", "known.gtf", "updated.gtf"):
+        assert filecmp.cmp(tmp_path / f"ref.{fn}", tmp_path / f"our.{fn}", shallow=False), fn
+    # the table-only fetch path (-o / -y / -E alone)
+    few = ["-y", "@sum.txt", "-E", "@bed", "-o", "@updated.gtf"]
+    subprocess.run([api.CLI_PATH, "update-gtf", "-l", "3", str(tmp_path / "f.bam"), str(tmp_path / "anno.gtf")] + [x.replace("@", str(tmp_path) + "/few.") for x in few],
+                   stderr=subprocess.DEVNULL, check=True, env=env)
+    for fn in ("sum.txt", "bed", "updated.gtf"):
+        assert filecmp.cmp(tmp_path / f"ref.{fn}", tmp_path / f"few.{fn}", shallow=False), fn
+    p = subprocess.run([api.CLI_PATH, "update-gtf", "-l", "3", str(tmp_path / "f.bam"), str(tmp_path / "anno.gtf")], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    assert p.returncode != 0                                       # without the knob the unsorted BAM is refused, as documented

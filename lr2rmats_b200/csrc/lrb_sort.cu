@@ -8,9 +8,9 @@
 // ex_beg / ex_n).  Hand-written, no CUB: 8-bit digits, per pass  histogram -> exclusive scan -> stable scatter; only the
 // passes the largest key needs are run.
 //   sort_keys_kernel      key + identity permutation per row, block-reduced maximum key
-//   sort_hist_kernel      digit counts per 1024-row tile, digit-major (hist[d * n_tiles + tile])
+//   sort_hist_kernel      digit counts per 2048-row tile, digit-major (hist[d * n_tiles + tile])
 //   sort_scan_kernel      exclusive scan of that matrix (one CTA: <= 256 * n_tiles counters)
-//   sort_scatter_kernel   a warp owns 128 consecutive rows and ranks them in four rounds of 32 with __match_any_sync (rank =
+//   sort_scatter_kernel   a warp owns 256 consecutive rows and ranks them in rounds of 32 with __match_any_sync (rank =
 //                         earlier rows of the tile with the same digit), so equal digits keep their order
 //   rows_permute_kernel   gathers the seven row fields through the sorted permutation
 #include "lrb_common.cuh"
@@ -22,7 +22,7 @@ extern int64_t g_launches_sort;
 int64_t g_launches_sort = 0;
 #define LRB_COUNT_LAUNCH() (++g_launches_sort)
 
-static constexpr int RS_THREADS = 256, RS_TILE = 1024, RS_WARPS = RS_THREADS / 32;
+static constexpr int RS_THREADS = 256, RS_TILE = 2048, RS_WARPS = RS_THREADS / 32, RS_ROUNDS = RS_TILE / RS_THREADS;   // a warp owns RS_ROUNDS * 32 consecutive rows
 
 __global__ void __launch_bounds__(RS_THREADS) sort_keys_kernel(DRows rows, const uint16_t *__restrict__ flag, uint64_t *__restrict__ keys,
                                                                uint32_t *__restrict__ idx, unsigned long long *max_key)
@@ -87,10 +87,10 @@ __global__ void __launch_bounds__(RS_THREADS) sort_scatter_kernel(const uint64_t
     const int t = threadIdx.x, w = t >> 5, lane = t & 31;
     for (int q = t; q < RS_WARPS * 256; q += RS_THREADS) (&s_cnt[0][0])[q] = 0;
     __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * RS_TILE + w * (RS_TILE / RS_WARPS);       // this warp's 128 consecutive rows
-    uint64_t k[4]; uint32_t v[4], rk[4]; int d[4];
+    const int64_t base = (int64_t)blockIdx.x * RS_TILE + w * (RS_TILE / RS_WARPS);       // this warp's consecutive rows
+    uint64_t k[RS_ROUNDS]; uint32_t v[RS_ROUNDS], rk[RS_ROUNDS]; int d[RS_ROUNDS];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < RS_ROUNDS; ++r) {
         const int64_t i = base + r * 32 + lane;
         const bool ok = i < n;
         k[r] = ok ? kin[i] : 0; v[r] = ok ? vin[i] : 0;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(RS_THREADS) sort_scatter_kernel(const uint64_t
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < RS_ROUNDS; ++r)
         if (d[r] < 256) {
             const uint32_t dst = hist[(size_t)d[r] * n_tiles + blockIdx.x] + s_cnt[w][d[r]] + rk[r];
             kout[dst] = k[r]; vout[dst] = v[r];

@@ -179,8 +179,13 @@ int run_scan(lrb_ctx *c, int mode, const lrb_filter_params *fp, const lrb_exon_p
     const double avg = (double)c->b.n_cigar / (double)n;
     const bool warp_mode = avg > 48.0;
     int R = 256;
-    if (warp_mode) { R = (int)(4096.0 / avg); R = std::max(8, std::min(256, R)); }
+    static int flat_mode = -1;                        // LRB_SCAN_FLAT: 0 warp per read, 1 flat on staged tiles, 2 flat on 256-read tiles read from the pool
+    if (flat_mode < 0) { const char *e = getenv("LRB_SCAN_FLAT"); flat_mode = e ? atoi(e) : 2; }
+    if (warp_mode && flat_mode != 2) { R = (int)(4096.0 / avg); R = std::max(8, std::min(256, R)); }
     int stage_words = (int)(R * avg * (warp_mode ? 1.6 : 1.3)) + (warp_mode ? 512 : 256); stage_words = (stage_words + 255) & ~255; stage_words = std::max(2048, std::min(12288, stage_words));
+    // flat tiles read their ops from the pool: no stage and no exon staging, so that the SM keeps its L1 for the op slices
+    // (with 4 x 48 KB of shared memory per SM the L1 hit rate of the slices was 28 %)
+    if (warp_mode && flat_mode == 2) stage_words = 0;
     const int n_tiles = (int)((n + R - 1) / R);
     if (mode != 0) {
         int64_t bound = c->b.n_cigar + n + 16, est = c->b.n_cigar / 2 + n + 4096;
@@ -194,7 +199,7 @@ int run_scan(lrb_ctx *c, int mode, const lrb_filter_params *fp, const lrb_exon_p
         a.reads_per_tile = R; a.stage_words = stage_words; a.rows_by_record = by_record ? 1 : 0;
         CK(cudaMemsetAsync(c->tile_state.p, 0, (size_t)n_tiles * 8, c->st));
         CK(cudaMemsetAsync(c->scalars.p, 0, 8 * 8, c->st)); CK(cudaMemsetAsync(d_ticket(c), 0, 4, c->st));
-        size_t smem = (size_t)stage_words * 4 + (warp_mode ? (size_t)3072 * 8 : 0);   // exon staging only in warp mode
+        size_t smem = (size_t)stage_words * 4 + (warp_mode && stage_words ? (size_t)3072 * 8 : 0);   // exon staging only in warp mode
         tick(c, 8);
         launch_cigar_scan(a, n_tiles, warp_mode, smem, c->st);
         tick(c, 9);

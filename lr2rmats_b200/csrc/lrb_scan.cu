@@ -147,9 +147,27 @@ LRB_DEVINL bool filter_pass(const ScanArgs &a, int64_t r, uint32_t c0, uint32_t 
     return true;
 }
 
-template <bool WARP_MODE>
+// ---- flat mode (long CIGARs): the staged words of a tile are ONE array of ops, 256 threads take equal slices of it whatever
+// the read boundaries are, and everything a walk carries from op to op becomes a block-wide scan:
+//   reference bases consumed so far   exclusive sum over the slices; a read's own origin = the value at its first op
+//   the latest cut op and the reference position behind it   exclusive max-scan of (op index, position) pairs
+//   exons emitted so far              exclusive sum of the emit flags; a read's exon k = emitted cuts since its first op
+// so a read of 2000 ops costs each of 256 threads a few ops instead of one warp 63 rounds of shuffles.
+template <int WM> struct FlatSmem { };
+template <> struct FlatSmem<2> {
+    int off[SCAN_THREADS + 1], pos[SCAN_THREADS];
+    uint32_t base[SCAN_THREADS], pend[SCAN_THREADS], intron[SCAN_THREADS], del[SCAN_THREADS], EB[SCAN_THREADS], EE[SCAN_THREADS];
+    uint16_t ebl[SCAN_THREADS], ebo[SCAN_THREADS], eel[SCAN_THREADS], eeo[SCAN_THREADS];
+    uint32_t tE[SCAN_THREADS]; unsigned long long w64[SCAN_THREADS / 32 + 1];
+    uint8_t emit[SCAN_THREADS];
+};
+
+// WM: 0 one thread per read (short CIGARs), 1 one warp per read, 2 flat (tiles that do not fit the stage fall back to 1)
+template <int WM>
 __global__ void __launch_bounds__(SCAN_THREADS) cigar_scan_kernel(ScanArgs a)
 {
+    constexpr bool WARP_MODE = WM != 0;
+    __shared__ FlatSmem<WM> fs;
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *s_words = smem;                                   // stage_words
     int *s_es = (int *)(smem + a.stage_words), *s_ee = s_es + EX_STAGE;
@@ -206,7 +224,92 @@ __global__ void __launch_bounds__(SCAN_THREADS) cigar_scan_kernel(ScanArgs a)
         s_start[li] = w.first_start; s_end[li] = w.last_end;
     };
     bool parked = false, park_ovf = false; int park_last_start = 0;      // thread mode: exons parked in the staged words by walk 1
-    if (!WARP_MODE) {
+    // flat mode state of this thread's slice [fa0, fa1) of the tile's ops
+    bool flat = false; int fa0 = 0, fa1 = 0, fli = 0; uint32_t fP = 0, fE = 0; int fcut = -1; uint32_t fcutP = 0;
+    // the ops are read from the staged copy when the tile fits the stage, else straight from the pool (the slices are contiguous:
+    // every pass streams them again through L1 / L2), so a flat tile is not bounded by shared memory
+    const uint32_t *f_words = staged ? s_words : a.b.cigar + w_lo;
+    if constexpr (WM == 2) flat = nr <= SCAN_THREADS;
+    if constexpr (WM == 2) if (flat) {
+        if (tid < nr) fs.off[tid] = (int)(a.b.cigar_off[r0 + tid] - w_lo);
+        if (tid == 0) fs.off[nr] = (int)nw;
+        if (tid < nr) { fs.pos[tid] = a.b.pos[r0 + tid]; fs.intron[tid] = 0; fs.del[tid] = 0; fs.base[tid] = 0; fs.pend[tid] = 0; fs.ebl[tid] = fs.ebo[tid] = fs.eel[tid] = fs.eeo[tid] = 0; }
+        __syncthreads();
+        const int K = (int)((nw + SCAN_THREADS - 1) / SCAN_THREADS);
+        fa0 = min((int)nw, tid * K); fa1 = min((int)nw, fa0 + K);
+        {   // read of the first op of the slice: first r with off[r + 1] > fa0
+            int lo = 0, hi = nr;
+            while (lo < hi) { const int m = (lo + hi) >> 1; if (fs.off[m + 1] > fa0) hi = m; else lo = m + 1; }
+            fli = lo;
+        }
+        // pass 1: reference bases of the slice -> exclusive sum
+        uint32_t tot = 0;
+        for (int i = fa0; i < fa1; ++i) { const uint32_t x = f_words[i]; if (op_ref(x & 15u)) tot += x >> 4; }
+        uint32_t all; fP = block_excl_sum(tot, s_scan, &all);
+        // pass 2: read origins, per-read filter statistics, the slice's last cut
+        {
+            uint32_t P = fP; int li = fli; uint32_t intr = 0, dl = 0; unsigned long long lastcut = 0;
+            for (int i = fa0; i < fa1; ++i) {
+                while (i >= fs.off[li + 1]) { if (intr) atomicAdd(&fs.intron[li], intr); if (dl) atomicAdd(&fs.del[li], dl); intr = dl = 0; ++li; }
+                if (i == fs.off[li]) fs.base[li] = P;
+                const uint32_t x = f_words[i], l = x >> 4, op = x & 15u;
+                if (op == OP_N) ++intr; else if (op == OP_D) dl += l;
+                const bool cut = (op == OP_N && (int)l >= a.ep.min_intron) || (op == OP_D && (int)l > a.ep.max_delet);
+                if (op_ref(op)) P += l;
+                if (cut) lastcut = ((unsigned long long)(uint32_t)(i + 1) << 32) | P;
+                if (i == fs.off[li + 1] - 1) fs.pend[li] = P;
+            }
+            if (fa0 < fa1) { if (intr) atomicAdd(&fs.intron[li], intr); if (dl) atomicAdd(&fs.del[li], dl); }
+            // exclusive max-scan of (cut index + 1, position behind the cut) over the slices
+            unsigned long long inc = lastcut;
+            const int lane = lane_id(), w = warp_id();
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(FULL, inc, o); if (lane >= o && y > inc) inc = y; }
+            if (lane == 31) fs.w64[w] = inc;
+            __syncthreads();
+            unsigned long long pre = 0;
+            for (int k = 0; k < w; ++k) pre = fs.w64[k] > pre ? fs.w64[k] : pre;
+            unsigned long long left = __shfl_up_sync(FULL, inc, 1); if (lane == 0) left = 0;
+            const unsigned long long ex = left > pre ? left : pre;
+            fcut = (int)(ex >> 32) - 1; fcutP = (uint32_t)ex;
+        }
+        __syncthreads();
+        // pass 3: emit flags -> per-slice counts, per-read (owner slice, local count) at the first and behind the last op
+        {
+            uint32_t P = fP; int li = fli, lc = fcut; uint32_t lcP = fcutP, ec = 0;
+            for (int i = fa0; i < fa1; ++i) {
+                while (i >= fs.off[li + 1]) ++li;
+                if (i == fs.off[li]) { fs.ebl[li] = (uint16_t)ec; fs.ebo[li] = (uint16_t)tid; }
+                const uint32_t x = f_words[i], l = x >> 4, op = x & 15u;
+                const bool cut = (op == OP_N && (int)l >= a.ep.min_intron) || (op == OP_D && (int)l > a.ep.max_delet);
+                if (cut) {
+                    const bool first_cut = lc < fs.off[li];
+                    const int end_before = fs.pos[li] + (int)(P - fs.base[li]);
+                    const int start = first_cut ? fs.pos[li] + 1 : fs.pos[li] + (int)(lcP - fs.base[li]) + 1;
+                    if (first_cut || end_before - start + 1 >= a.ep.min_exon) ++ec;
+                }
+                if (op_ref(op)) P += l;
+                if (cut) { lc = i; lcP = P; }
+                if (i == fs.off[li + 1] - 1) { fs.eel[li] = (uint16_t)ec; fs.eeo[li] = (uint16_t)tid; }
+            }
+            uint32_t eall; fE = block_excl_sum(ec, s_scan, &eall);
+            fs.tE[tid] = fE;
+        }
+        __syncthreads();
+        if (tid < nr) {
+            const int64_t r = r0 + tid;
+            const int n_c = fs.off[tid + 1] - fs.off[tid];
+            const uint32_t c0 = n_c > 0 ? f_words[fs.off[tid]] : 0u, c1 = n_c > 0 ? f_words[fs.off[tid + 1] - 1] : 0u;
+            WalkStats w;
+            fs.EB[tid] = n_c > 0 ? fs.tE[fs.ebo[tid]] + fs.ebl[tid] : 0u;
+            fs.EE[tid] = n_c > 0 ? fs.tE[fs.eeo[tid]] + fs.eel[tid] : 0u;
+            w.n_exon = (int)(fs.EE[tid] - fs.EB[tid]) + 1; w.intron_n = (int)fs.intron[tid]; w.del_len = (int)fs.del[tid];
+            w.ref_len = n_c > 0 ? (int)(fs.pend[tid] - fs.base[tid]) : 0; w.first_start = fs.pos[tid] + 1; w.last_end = fs.pos[tid] + w.ref_len;
+            finish_read(tid, r, c0, c1, n_c, w);
+        }
+    }
+    if (flat) { }
+    else if (!WARP_MODE) {
         if (tid < nr) {
             int64_t r = r0 + tid;
             const uint32_t *c = read_ptr(r); int n_c = (int)(a.b.cigar_off[r + 1] - a.b.cigar_off[r]);
@@ -257,12 +360,41 @@ __global__ void __launch_bounds__(SCAN_THREADS) cigar_scan_kernel(ScanArgs a)
     // ---- walk 2: emit exons (into the shared staging buffer when the tile fits, else straight to HBM)
     // warp mode stages the exons of the tile and writes them out coalesced; thread mode moves each read's parked exons
     // straight to the pools (one staging buffer less: 6 instead of 4 resident CTAs per SM cover the look-back waits)
-    const bool ex_staged = WARP_MODE && ex_total <= (uint32_t)EX_STAGE;
+    const bool ex_staged = WARP_MODE && a.stage_words > 0 && ex_total <= (uint32_t)EX_STAGE;
     s_cnt[tid] = (int)ex_excl;                                   // reuse as local exon offset (own slot only)
+    if constexpr (WM == 2) if (flat && tid < nr) fs.emit[tid] = my_ex > 0;
     __syncthreads();
     const bool room = (int64_t)ex_base + ex_total <= a.ex.cap;   // host re-runs with a larger pool otherwise
     if (!room) return;
-    if (!WARP_MODE) {
+    if constexpr (WM == 2) if (flat) {
+        // every slice replays its ops once more, now with the exon slot of each emitted cut: slot of the read + cuts emitted since its first op
+        int *bes = ex_staged ? s_es : a.ex.es + ex_base, *bee = ex_staged ? s_ee : a.ex.ee + ex_base;
+        uint32_t P = fP, E = fE; int li = fli, lc = fcut; uint32_t lcP = fcutP;
+        for (int i = fa0; i < fa1; ++i) {
+            while (i >= fs.off[li + 1]) ++li;
+            const uint32_t x = f_words[i], l = x >> 4, op = x & 15u;
+            const bool cut = (op == OP_N && (int)l >= a.ep.min_intron) || (op == OP_D && (int)l > a.ep.max_delet);
+            if (cut) {
+                const bool first_cut = lc < fs.off[li];
+                const int end_before = fs.pos[li] + (int)(P - fs.base[li]);
+                const int start = first_cut ? fs.pos[li] + 1 : fs.pos[li] + (int)(lcP - fs.base[li]) + 1;
+                if (first_cut || end_before - start + 1 >= a.ep.min_exon) {
+                    if (fs.emit[li]) { const uint32_t k = (uint32_t)s_cnt[li] + (E - fs.EB[li]); bes[k] = start; bee[k] = end_before; }
+                    ++E;
+                }
+            }
+            if (op_ref(op)) P += l;
+            if (cut) { lc = i; lcP = P; }
+            if (i == fs.off[li + 1] - 1 && fs.emit[li]) {           // the open exon behind the last op (bam2gtf.c:74-76)
+                const uint32_t k = (uint32_t)s_cnt[li] + (fs.EE[li] - fs.EB[li]);
+                bes[k] = lc >= fs.off[li] ? fs.pos[li] + (int)(lcP - fs.base[li]) + 1 : fs.pos[li] + 1;
+                bee[k] = fs.pos[li] + (int)(P - fs.base[li]);
+            }
+        }
+        if (tid < nr && fs.emit[tid] && fs.off[tid + 1] == fs.off[tid]) { bes[s_cnt[tid]] = fs.pos[tid] + 1; bee[s_cnt[tid]] = fs.pos[tid]; }   // no ops at all
+    }
+    if (flat) { }
+    else if (!WARP_MODE) {
         if (tid < nr && my_ex) {
             int64_t r = r0 + tid;
             const uint32_t *c = read_ptr(r); int n_c = (int)(a.b.cigar_off[r + 1] - a.b.cigar_off[r]);
@@ -299,12 +431,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) cigar_scan_kernel(ScanArgs a)
 void launch_cigar_scan(const ScanArgs &a, int n_tiles, bool warp_mode, size_t smem_bytes, cudaStream_t st)
 {
     if (n_tiles <= 0) return;
-    if (warp_mode) {
-        cudaFuncSetAttribute(cigar_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cigar_scan_kernel<true><<<n_tiles, SCAN_THREADS, smem_bytes, st>>>(a);
+    static int flat = -1;
+    if (flat < 0) { const char *e = getenv("LRB_SCAN_FLAT"); flat = e ? atoi(e) : 1; }
+    if (warp_mode && flat) {
+        cudaFuncSetAttribute(cigar_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cigar_scan_kernel<2><<<n_tiles, SCAN_THREADS, smem_bytes, st>>>(a);
+    } else if (warp_mode) {
+        cudaFuncSetAttribute(cigar_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cigar_scan_kernel<1><<<n_tiles, SCAN_THREADS, smem_bytes, st>>>(a);
     } else {
-        cudaFuncSetAttribute(cigar_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cigar_scan_kernel<false><<<n_tiles, SCAN_THREADS, smem_bytes, st>>>(a);
+        cudaFuncSetAttribute(cigar_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cigar_scan_kernel<0><<<n_tiles, SCAN_THREADS, smem_bytes, st>>>(a);
     }
     LRB_COUNT_LAUNCH();
 }

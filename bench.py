@@ -406,7 +406,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=1_000_000)
     ap.add_argument("--genes", type=int, default=60_000)
-    ap.add_argument("--cpu-reads", type=int, default=400_000, help="sample size of the cpu_baseline leg (about 10 s of one core; the reference's summary is quadratic, so the rate falls with the sample)")
+    ap.add_argument("--cpu-reads", type=int, default=300_000, help="sample size of the cpu_baseline leg (about 10 s of one core; the reference's summary is quadratic, so the rate falls with the sample)")
     ap.add_argument("--ref-reads", type=int, default=100_000, help="sample size per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-fetch", default="outputs", choices=["outputs", "full"],

@@ -182,6 +182,7 @@ int run_scan(lrb_ctx *c, int mode, const lrb_filter_params *fp, const lrb_exon_p
     static int flat_mode = -1;                        // LRB_SCAN_FLAT: 0 warp per read, 1 flat on staged tiles, 2 flat on 256-read tiles read from the pool
     if (flat_mode < 0) { const char *e = getenv("LRB_SCAN_FLAT"); flat_mode = e ? atoi(e) : 2; }
     if (warp_mode && flat_mode != 2) { R = (int)(4096.0 / avg); R = std::max(8, std::min(256, R)); }
+    if (warp_mode && flat_mode == 2) { static int fr = -1; if (fr < 0) { const char *e = getenv("LRB_SCAN_FLAT_R"); fr = e ? atoi(e) : 128; } R = std::max(8, std::min(256, fr)); }
     int stage_words = (int)(R * avg * (warp_mode ? 1.6 : 1.3)) + (warp_mode ? 512 : 256); stage_words = (stage_words + 255) & ~255; stage_words = std::max(2048, std::min(12288, stage_words));
     // flat tiles read their ops from the pool: no stage and no exon staging, so that the SM keeps its L1 for the op slices
     // (with 4 x 48 KB of shared memory per SM the L1 hit rate of the slices was 28 %)

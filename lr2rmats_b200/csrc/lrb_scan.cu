@@ -163,9 +163,11 @@ template <> struct FlatSmem<2> {
 };
 
 // WM: 0 one thread per read (short CIGARs), 1 one warp per read, 2 flat (tiles that do not fit the stage fall back to 1)
-template <int WM>
-__global__ void __launch_bounds__(SCAN_THREADS) cigar_scan_kernel(ScanArgs a)
+// WM 3 = flat mode compiled for 6 resident CTAs per SM (40 registers) instead of 5
+template <int WMX>
+__global__ void __launch_bounds__(SCAN_THREADS, WMX == 3 ? 6 : 0) cigar_scan_kernel(ScanArgs a)
 {
+    constexpr int WM = WMX == 3 ? 2 : WMX;
     constexpr bool WARP_MODE = WM != 0;
     __shared__ FlatSmem<WM> fs;
     extern __shared__ __align__(16) uint32_t smem[];
@@ -433,7 +435,12 @@ void launch_cigar_scan(const ScanArgs &a, int n_tiles, bool warp_mode, size_t sm
     if (n_tiles <= 0) return;
     static int flat = -1;
     if (flat < 0) { const char *e = getenv("LRB_SCAN_FLAT"); flat = e ? atoi(e) : 1; }
-    if (warp_mode && flat) {
+    static int occ6 = -1;
+    if (occ6 < 0) { const char *e = getenv("LRB_SCAN_OCC6"); occ6 = e ? atoi(e) : 1; }
+    if (warp_mode && flat && occ6) {
+        cudaFuncSetAttribute(cigar_scan_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cigar_scan_kernel<3><<<n_tiles, SCAN_THREADS, smem_bytes, st>>>(a);
+    } else if (warp_mode && flat) {
         cudaFuncSetAttribute(cigar_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         cigar_scan_kernel<2><<<n_tiles, SCAN_THREADS, smem_bytes, st>>>(a);
     } else if (warp_mode) {

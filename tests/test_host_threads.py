@@ -168,3 +168,19 @@ def test_sj_reader_threads(big, tmp_path, quirk):
         outs.append((p.returncode, open(d / "updated.gtf", "rb").read(), open(d / "summary.txt", "rb").read(), open(d / "detail.txt", "rb").read()))
     assert outs[0] == outs[1] == outs[2]
     assert outs[0][0] == 0 and len(outs[0][1]) > 1 << 20
+
+
+def test_io_bench_tool_digest(big):
+    """lrb-io-bench (the host decode / encode timer of DESIGN 6.4) decodes to the same SoA batch on 1 and 8 threads."""
+    import json
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lr2rmats_b200", "host", "lrb-io-bench")
+    if not os.path.exists(tool):
+        pytest.skip("lrb-io-bench not built")
+    outs = []
+    for t in (1, 8):
+        env = dict(os.environ, LRB_THREADS=str(t))
+        p = subprocess.run([tool, str(big / "in.sam"), str(big / f"iob_t{t}.bam")], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True, env=env)
+        outs.append(json.loads(p.stdout))
+    assert outs[0]["digest"] == outs[1]["digest"] and outs[0]["records"] == outs[1]["records"] > 40000
+    assert outs[0]["threads"] == 1 and outs[1]["threads"] == 8
+    assert open(big / "iob_t1.bam", "rb").read() == open(big / "iob_t8.bam", "rb").read()

@@ -46,7 +46,7 @@ typedef struct {
     const int32_t  *nm;          /* NM:i value (bam_aux2i), 0 when absent */
     const int8_t   *xs;          /* XS:A value (bam_aux2A): 0 = tag absent */
     const uint64_t *qname_hash;  /* 64-bit hash of qname; equal names <=> equal hash */
-    const uint32_t *cigar_off;   /* n+1 offsets into cigar[] */
+    const uint64_t *cigar_off;   /* n+1 offsets into cigar[] (64-bit: a batch may hold more than 2^32 CIGAR ops) */
     const uint32_t *cigar;       /* cigar_off[n] words */
 } lrb_batch;
 

@@ -14,7 +14,7 @@ i32p, u32p, u16p, u8p, i8p, u64p = (C.POINTER(t) for t in (C.c_int32, C.c_uint32
 
 class Batch(C.Structure):
     _fields_ = [("n", C.c_int64), ("tid", i32p), ("pos", i32p), ("flag", u16p), ("l_qseq", i32p), ("nm", i32p),
-                ("xs", i8p), ("qname_hash", u64p), ("cigar_off", u32p), ("cigar", u32p)]
+                ("xs", i8p), ("qname_hash", u64p), ("cigar_off", u64p), ("cigar", u32p)]
 
 
 class Anno(C.Structure):
@@ -113,7 +113,7 @@ C_KNOWN, C_KNOWN_SITE, C_UNRELIABLE, C_FULL, C_LFULL, C_RFULL, C_LNOTH, C_RNOTH,
 F_NOVEL_EXON, F_NOVEL_DON, F_NOVEL_ACC, F_NOVEL_JUNC, F_UNRELIABLE = (1 << k for k in range(5))
 
 _DT = {"tid": np.int32, "pos": np.int32, "flag": np.uint16, "l_qseq": np.int32, "nm": np.int32, "xs": np.int8,
-       "qname_hash": np.uint64, "cigar_off": np.uint32, "cigar": np.uint32, "start": np.int32, "end": np.int32,
+       "qname_hash": np.uint64, "cigar_off": np.uint64, "cigar": np.uint32, "start": np.int32, "end": np.int32,
        "is_rev": np.uint8, "gene": np.int32, "exon_off": np.uint32, "exon_start": np.int32, "exon_end": np.int32,
        "don": np.int32, "acc": np.int32, "uniq_c": np.int32, "multi_c": np.int32}
 

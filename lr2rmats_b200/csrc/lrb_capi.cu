@@ -177,16 +177,11 @@ int run_scan(lrb_ctx *c, int mode, const lrb_filter_params *fp, const lrb_exon_p
     if (mode != 1) { NEED(c->f_pass, (size_t)n + 1); NEED(c->f_score, (size_t)n * 4 + 4); NEED(c->f_intron, (size_t)n * 4 + 4); }
     if (n == 0) { c->rows.n = 0; c->ex.n = 0; if (mode != 0 && (rc = setup_exons(c, 16)) != LRB_OK) return rc; return LRB_OK; }
     const double avg = (double)c->b.n_cigar / (double)n;
-    const bool warp_mode = avg > 48.0;
-    int R = 256;
-    static int flat_mode = -1;                        // LRB_SCAN_FLAT: 0 warp per read, 1 flat on staged tiles, 2 flat on 256-read tiles read from the pool
-    if (flat_mode < 0) { const char *e = getenv("LRB_SCAN_FLAT"); flat_mode = e ? atoi(e) : 2; }
-    if (warp_mode && flat_mode != 2) { R = (int)(4096.0 / avg); R = std::max(8, std::min(256, R)); }
-    if (warp_mode && flat_mode == 2) { static int fr = -1; if (fr < 0) { const char *e = getenv("LRB_SCAN_FLAT_R"); fr = e ? atoi(e) : 128; } R = std::max(8, std::min(256, fr)); }
-    int stage_words = (int)(R * avg * (warp_mode ? 1.6 : 1.3)) + (warp_mode ? 512 : 256); stage_words = (stage_words + 255) & ~255; stage_words = std::max(2048, std::min(12288, stage_words));
-    // flat tiles read their ops from the pool: no stage and no exon staging, so that the SM keeps its L1 for the op slices
-    // (with 4 x 48 KB of shared memory per SM the L1 hit rate of the slices was 28 %)
-    if (warp_mode && flat_mode == 2) stage_words = 0;
+    // short CIGARs (Iso-Seq like): thread per read on staged tiles of 256 reads; long CIGARs (ONT like): the streaming kernel
+    const bool stream_mode = avg > 48.0;
+    const int R = stream_mode ? stream_reads_per_tile() : 256;
+    int stage_words = (int)(R * avg * 1.3) + 256; stage_words = (stage_words + 255) & ~255; stage_words = std::max(2048, std::min(12288, stage_words));
+    if (stream_mode) stage_words = 0;
     const int n_tiles = (int)((n + R - 1) / R);
     if (mode != 0) {
         int64_t bound = c->b.n_cigar + n + 16, est = c->b.n_cigar / 2 + n + 4096;
@@ -200,9 +195,9 @@ int run_scan(lrb_ctx *c, int mode, const lrb_filter_params *fp, const lrb_exon_p
         a.reads_per_tile = R; a.stage_words = stage_words; a.rows_by_record = by_record ? 1 : 0;
         CK(cudaMemsetAsync(c->tile_state.p, 0, (size_t)n_tiles * 8, c->st));
         CK(cudaMemsetAsync(c->scalars.p, 0, 8 * 8, c->st)); CK(cudaMemsetAsync(d_ticket(c), 0, 4, c->st));
-        size_t smem = (size_t)stage_words * 4 + (warp_mode && stage_words ? (size_t)3072 * 8 : 0);   // exon staging only in warp mode
+        size_t smem = (size_t)stage_words * 4;
         tick(c, 8);
-        launch_cigar_scan(a, n_tiles, warp_mode, smem, c->st);
+        launch_cigar_scan(a, n_tiles, stream_mode, smem, c->st);
         tick(c, 9);
         CK(cudaGetLastError());
         if (by_record) return LRB_OK;
@@ -492,6 +487,8 @@ int lrb_batch_upload(lrb_ctx *c, const lrb_batch *b)
     const size_t n = (size_t)b->n;
     const size_t nc = n ? b->cigar_off[n] : 0;
     if (b->n >= (1ll << 31) - 1) return fail(c, LRB_E_ARG, "batch too large: at most 2^31-2 records per batch");
+    if (n && b->cigar_off[0] != 0) return fail(c, LRB_E_ARG, "cigar_off[0] must be 0");
+    if (nc >= (1ull << 40)) return fail(c, LRB_E_ARG, "batch too large: at most 2^40 CIGAR ops per batch");
     int rc;
     if ((rc = h2d(c, c->b_tid, b->tid, n))) return rc;
     if ((rc = h2d(c, c->b_pos, b->pos, n))) return rc;
@@ -501,11 +498,11 @@ int lrb_batch_upload(lrb_ctx *c, const lrb_batch *b)
     if ((rc = h2d(c, c->b_xs, b->xs, n))) return rc;
     if ((rc = h2d(c, c->b_qh, b->qname_hash, n))) return rc;
     if (n) { if ((rc = h2d(c, c->b_coff, b->cigar_off, n + 1))) return rc; }
-    else { uint32_t z = 0; NEED(c->b_coff, 8); CK(cudaMemcpyAsync(c->b_coff.p, &z, 4, cudaMemcpyHostToDevice, c->st)); CK(cudaStreamSynchronize(c->st)); }
+    else { NEED(c->b_coff, 8); CK(cudaMemsetAsync(c->b_coff.p, 0, 8, c->st)); }
     if ((rc = h2d(c, c->b_cig, b->cigar, nc))) return rc;
     c->b.n = b->n; c->b.n_cigar = (int64_t)nc;
     c->b.tid = c->b_tid.as<int32_t>(); c->b.pos = c->b_pos.as<int32_t>(); c->b.flag = c->b_flag.as<uint16_t>(); c->b.l_qseq = c->b_lq.as<int32_t>();
-    c->b.nm = c->b_nm.as<int32_t>(); c->b.xs = c->b_xs.as<int8_t>(); c->b.qhash = c->b_qh.as<uint64_t>(); c->b.cigar_off = c->b_coff.as<uint32_t>();
+    c->b.nm = c->b_nm.as<int32_t>(); c->b.xs = c->b_xs.as<int8_t>(); c->b.qhash = c->b_qh.as<uint64_t>(); c->b.cigar_off = c->b_coff.as<uint64_t>();
     c->b.cigar = c->b_cig.as<uint32_t>();
     c->have_batch = true; c->have_filter = c->have_exons = c->have_update = c->have_unique = false;
     return LRB_OK;

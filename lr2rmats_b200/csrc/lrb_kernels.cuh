@@ -13,7 +13,7 @@ struct DBatch {
     uint16_t *flag = nullptr;
     int8_t *xs = nullptr;
     uint64_t *qhash = nullptr;
-    uint32_t *cigar_off = nullptr, *cigar = nullptr;
+    uint64_t *cigar_off = nullptr; uint32_t *cigar = nullptr;
 };
 
 // ---- remove table (-r GTF) as an index: per tid the entries visible to remove_overlap()'s early exit
@@ -69,7 +69,8 @@ struct ScanArgs {
     int rows_by_record;                             // 1: a passing record's row is written at its record index (no row compaction)
 };
 
-void launch_cigar_scan(const ScanArgs &a, int n_tiles, bool warp_mode, size_t smem_bytes, cudaStream_t st);
+void launch_cigar_scan(const ScanArgs &a, int n_tiles, bool stream_mode, size_t smem_bytes, cudaStream_t st);
+int stream_reads_per_tile();                        // tile size of the long-CIGAR streaming kernel
 void launch_select_runs(const DBatch &b, const uint32_t *row_read, int64_t n_rows, const int32_t *score, const int32_t *intron_n,
                         lrb_filter_params fp, uint8_t *keep_row_mask, uint8_t *keep_rec_mask, cudaStream_t st);
 // ordered compaction of the set positions of a byte mask: out[k] = index of k-th nonzero (optionally mapped through `map`)

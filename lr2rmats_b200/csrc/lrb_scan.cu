@@ -22,7 +22,6 @@ int64_t count_launches() { return g_launches; }
 #define LRB_COUNT_LAUNCH() (++g_launches)
 
 static constexpr int SCAN_THREADS = 256;
-static constexpr int EX_STAGE = 3072;             // exon staging slots per tile (24 KB for starts+ends)
 
 enum { OP_M = 0, OP_I, OP_D, OP_N, OP_S, OP_H, OP_P, OP_EQ, OP_X, OP_B };
 
@@ -147,32 +146,11 @@ LRB_DEVINL bool filter_pass(const ScanArgs &a, int64_t r, uint32_t c0, uint32_t 
     return true;
 }
 
-// ---- flat mode (long CIGARs): the staged words of a tile are ONE array of ops, 256 threads take equal slices of it whatever
-// the read boundaries are, and everything a walk carries from op to op becomes a block-wide scan:
-//   reference bases consumed so far   exclusive sum over the slices; a read's own origin = the value at its first op
-//   the latest cut op and the reference position behind it   exclusive max-scan of (op index, position) pairs
-//   exons emitted so far              exclusive sum of the emit flags; a read's exon k = emitted cuts since its first op
-// so a read of 2000 ops costs each of 256 threads a few ops instead of one warp 63 rounds of shuffles.
-template <int WM> struct FlatSmem { };
-template <> struct FlatSmem<2> {
-    int off[SCAN_THREADS + 1], pos[SCAN_THREADS];
-    uint32_t base[SCAN_THREADS], pend[SCAN_THREADS], intron[SCAN_THREADS], del[SCAN_THREADS], EB[SCAN_THREADS], EE[SCAN_THREADS];
-    uint16_t ebl[SCAN_THREADS], ebo[SCAN_THREADS], eel[SCAN_THREADS], eeo[SCAN_THREADS];
-    uint32_t tE[SCAN_THREADS]; unsigned long long w64[SCAN_THREADS / 32 + 1];
-    uint8_t emit[SCAN_THREADS];
-};
-
-// WM: 0 one thread per read (short CIGARs), 1 one warp per read, 2 flat (tiles that do not fit the stage fall back to 1)
-// WM 3 = flat mode compiled for 6 resident CTAs per SM (40 registers) instead of 5
-template <int WMX>
-__global__ void __launch_bounds__(SCAN_THREADS, WMX == 3 ? 6 : 0) cigar_scan_kernel(ScanArgs a)
+// Short CIGARs (Iso-Seq like): one thread per read on a staged tile.  Long CIGARs go through cigar_stream_kernel below.
+__global__ void __launch_bounds__(SCAN_THREADS) cigar_scan_kernel(ScanArgs a)
 {
-    constexpr int WM = WMX == 3 ? 2 : WMX;
-    constexpr bool WARP_MODE = WM != 0;
-    __shared__ FlatSmem<WM> fs;
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *s_words = smem;                                   // stage_words
-    int *s_es = (int *)(smem + a.stage_words), *s_ee = s_es + EX_STAGE;
     __shared__ uint32_t s_scan[33];
     __shared__ int s_cnt[SCAN_THREADS], s_start[SCAN_THREADS], s_end[SCAN_THREADS];
     __shared__ uint8_t s_mask[SCAN_THREADS];
@@ -185,16 +163,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, WMX == 3 ? 6 : 0) cigar_scan_ker
     const int tile = (int)s_tile;
     const int64_t r0 = (int64_t)tile * R, r1 = min(a.b.n, r0 + R);
     const int nr = (int)(r1 - r0);
-    const uint32_t w_lo = a.b.cigar_off[r0], w_hi = a.b.cigar_off[r1];
-    const uint32_t nw = w_hi - w_lo;
-    const bool staged = nw <= (uint32_t)a.stage_words;
+    const uint64_t w_lo = a.b.cigar_off[r0], w_hi = a.b.cigar_off[r1];
+    const uint64_t nw = w_hi - w_lo;
+    const bool staged = nw <= (uint64_t)a.stage_words;
     const bool do_filter = a.mode != 1, do_exon = a.mode != 0;
     if (staged) {
         // coalesced stage: scalar head up to 16-byte alignment, then 128-bit streaming loads
         const uint32_t *src = a.b.cigar + w_lo;
-        uint32_t head = (uint32_t)((4 - (w_lo & 3)) & 3); if (head > nw) head = nw;
+        uint32_t head = (uint32_t)((4 - (w_lo & 3)) & 3); if (head > nw) head = (uint32_t)nw;
         if ((uint32_t)tid < head) s_words[tid] = ldg_stream_u32(src + tid);
-        uint32_t nv = (nw - head) >> 2;
+        uint32_t nv = ((uint32_t)nw - head) >> 2;
         const uint4 *v = (const uint4 *)(src + head);
         for (uint32_t i = tid; i < nv; i += SCAN_THREADS) {
             uint4 q = ldg_stream_u4(v + i);
@@ -209,10 +187,17 @@ __global__ void __launch_bounds__(SCAN_THREADS, WMX == 3 ? 6 : 0) cigar_scan_ker
 
     // ---- walk 1: statistics, exon count, filter predicate
     auto read_ptr = [&](int64_t r) -> const uint32_t * {
-        uint32_t off = a.b.cigar_off[r];
+        const uint64_t off = a.b.cigar_off[r];
         return staged ? (s_words + (off - w_lo)) : (a.b.cigar + off);
     };
-    auto finish_read = [&](int li, int64_t r, uint32_t c0, uint32_t c1, int n_c, const WalkStats &w) {
+    bool parked = false, park_ovf = false; int park_last_start = 0;      // exons parked in the staged words by walk 1
+    if (tid < nr) {
+        int64_t r = r0 + tid;
+        const uint32_t *c = read_ptr(r); int n_c = (int)(a.b.cigar_off[r + 1] - a.b.cigar_off[r]);
+        const uint32_t c0 = n_c > 0 ? c[0] : 0u, c1 = n_c > 0 ? c[n_c - 1] : 0u;
+        WalkStats w;
+        if (staged && do_exon) { parked = true; walk_seq_inplace(const_cast<uint32_t *>(c), n_c, a.b.pos[r], a.ep, w, &park_ovf, &park_last_start); }
+        else walk_seq<false>(c, n_c, a.b.pos[r], a.ep, nullptr, nullptr, w);
         bool mask;
         if (do_filter) {
             int sc = 0; bool p = filter_pass(a, r, c0, c1, n_c, w, &sc);
@@ -220,114 +205,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, WMX == 3 ? 6 : 0) cigar_scan_ker
             if (p) { a.score[r] = sc; a.intron_n[r] = w.intron_n; }
             mask = p;
         } else mask = a.sel_mask ? (a.sel_mask[r] != 0) : true;
-        bool unmapped = (a.b.flag[r] & 4) != 0;
-        s_mask[li] = mask ? 1 : 0;
-        s_cnt[li] = (mask && do_exon && !unmapped) ? w.n_exon : 0;
-        s_start[li] = w.first_start; s_end[li] = w.last_end;
-    };
-    bool parked = false, park_ovf = false; int park_last_start = 0;      // thread mode: exons parked in the staged words by walk 1
-    // flat mode state of this thread's slice [fa0, fa1) of the tile's ops
-    bool flat = false; int fa0 = 0, fa1 = 0, fli = 0; uint32_t fP = 0, fE = 0; int fcut = -1; uint32_t fcutP = 0;
-    // the ops are read from the staged copy when the tile fits the stage, else straight from the pool (the slices are contiguous:
-    // every pass streams them again through L1 / L2), so a flat tile is not bounded by shared memory
-    const uint32_t *f_words = staged ? s_words : a.b.cigar + w_lo;
-    if constexpr (WM == 2) flat = nr <= SCAN_THREADS;
-    if constexpr (WM == 2) if (flat) {
-        if (tid < nr) fs.off[tid] = (int)(a.b.cigar_off[r0 + tid] - w_lo);
-        if (tid == 0) fs.off[nr] = (int)nw;
-        if (tid < nr) { fs.pos[tid] = a.b.pos[r0 + tid]; fs.intron[tid] = 0; fs.del[tid] = 0; fs.base[tid] = 0; fs.pend[tid] = 0; fs.ebl[tid] = fs.ebo[tid] = fs.eel[tid] = fs.eeo[tid] = 0; }
-        __syncthreads();
-        const int K = (int)((nw + SCAN_THREADS - 1) / SCAN_THREADS);
-        fa0 = min((int)nw, tid * K); fa1 = min((int)nw, fa0 + K);
-        {   // read of the first op of the slice: first r with off[r + 1] > fa0
-            int lo = 0, hi = nr;
-            while (lo < hi) { const int m = (lo + hi) >> 1; if (fs.off[m + 1] > fa0) hi = m; else lo = m + 1; }
-            fli = lo;
-        }
-        // pass 1: reference bases of the slice -> exclusive sum
-        uint32_t tot = 0;
-        for (int i = fa0; i < fa1; ++i) { const uint32_t x = f_words[i]; if (op_ref(x & 15u)) tot += x >> 4; }
-        uint32_t all; fP = block_excl_sum(tot, s_scan, &all);
-        // pass 2: read origins, per-read filter statistics, the slice's last cut
-        {
-            uint32_t P = fP; int li = fli; uint32_t intr = 0, dl = 0; unsigned long long lastcut = 0;
-            for (int i = fa0; i < fa1; ++i) {
-                while (i >= fs.off[li + 1]) { if (intr) atomicAdd(&fs.intron[li], intr); if (dl) atomicAdd(&fs.del[li], dl); intr = dl = 0; ++li; }
-                if (i == fs.off[li]) fs.base[li] = P;
-                const uint32_t x = f_words[i], l = x >> 4, op = x & 15u;
-                if (op == OP_N) ++intr; else if (op == OP_D) dl += l;
-                const bool cut = (op == OP_N && (int)l >= a.ep.min_intron) || (op == OP_D && (int)l > a.ep.max_delet);
-                if (op_ref(op)) P += l;
-                if (cut) lastcut = ((unsigned long long)(uint32_t)(i + 1) << 32) | P;
-                if (i == fs.off[li + 1] - 1) fs.pend[li] = P;
-            }
-            if (fa0 < fa1) { if (intr) atomicAdd(&fs.intron[li], intr); if (dl) atomicAdd(&fs.del[li], dl); }
-            // exclusive max-scan of (cut index + 1, position behind the cut) over the slices
-            unsigned long long inc = lastcut;
-            const int lane = lane_id(), w = warp_id();
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(FULL, inc, o); if (lane >= o && y > inc) inc = y; }
-            if (lane == 31) fs.w64[w] = inc;
-            __syncthreads();
-            unsigned long long pre = 0;
-            for (int k = 0; k < w; ++k) pre = fs.w64[k] > pre ? fs.w64[k] : pre;
-            unsigned long long left = __shfl_up_sync(FULL, inc, 1); if (lane == 0) left = 0;
-            const unsigned long long ex = left > pre ? left : pre;
-            fcut = (int)(ex >> 32) - 1; fcutP = (uint32_t)ex;
-        }
-        __syncthreads();
-        // pass 3: emit flags -> per-slice counts, per-read (owner slice, local count) at the first and behind the last op
-        {
-            uint32_t P = fP; int li = fli, lc = fcut; uint32_t lcP = fcutP, ec = 0;
-            for (int i = fa0; i < fa1; ++i) {
-                while (i >= fs.off[li + 1]) ++li;
-                if (i == fs.off[li]) { fs.ebl[li] = (uint16_t)ec; fs.ebo[li] = (uint16_t)tid; }
-                const uint32_t x = f_words[i], l = x >> 4, op = x & 15u;
-                const bool cut = (op == OP_N && (int)l >= a.ep.min_intron) || (op == OP_D && (int)l > a.ep.max_delet);
-                if (cut) {
-                    const bool first_cut = lc < fs.off[li];
-                    const int end_before = fs.pos[li] + (int)(P - fs.base[li]);
-                    const int start = first_cut ? fs.pos[li] + 1 : fs.pos[li] + (int)(lcP - fs.base[li]) + 1;
-                    if (first_cut || end_before - start + 1 >= a.ep.min_exon) ++ec;
-                }
-                if (op_ref(op)) P += l;
-                if (cut) { lc = i; lcP = P; }
-                if (i == fs.off[li + 1] - 1) { fs.eel[li] = (uint16_t)ec; fs.eeo[li] = (uint16_t)tid; }
-            }
-            uint32_t eall; fE = block_excl_sum(ec, s_scan, &eall);
-            fs.tE[tid] = fE;
-        }
-        __syncthreads();
-        if (tid < nr) {
-            const int64_t r = r0 + tid;
-            const int n_c = fs.off[tid + 1] - fs.off[tid];
-            const uint32_t c0 = n_c > 0 ? f_words[fs.off[tid]] : 0u, c1 = n_c > 0 ? f_words[fs.off[tid + 1] - 1] : 0u;
-            WalkStats w;
-            fs.EB[tid] = n_c > 0 ? fs.tE[fs.ebo[tid]] + fs.ebl[tid] : 0u;
-            fs.EE[tid] = n_c > 0 ? fs.tE[fs.eeo[tid]] + fs.eel[tid] : 0u;
-            w.n_exon = (int)(fs.EE[tid] - fs.EB[tid]) + 1; w.intron_n = (int)fs.intron[tid]; w.del_len = (int)fs.del[tid];
-            w.ref_len = n_c > 0 ? (int)(fs.pend[tid] - fs.base[tid]) : 0; w.first_start = fs.pos[tid] + 1; w.last_end = fs.pos[tid] + w.ref_len;
-            finish_read(tid, r, c0, c1, n_c, w);
-        }
-    }
-    if (flat) { }
-    else if (!WARP_MODE) {
-        if (tid < nr) {
-            int64_t r = r0 + tid;
-            const uint32_t *c = read_ptr(r); int n_c = (int)(a.b.cigar_off[r + 1] - a.b.cigar_off[r]);
-            const uint32_t c0 = n_c > 0 ? c[0] : 0u, c1 = n_c > 0 ? c[n_c - 1] : 0u;
-            WalkStats w;
-            if (staged && do_exon) { parked = true; walk_seq_inplace(const_cast<uint32_t *>(c), n_c, a.b.pos[r], a.ep, w, &park_ovf, &park_last_start); }
-            else walk_seq<false>(c, n_c, a.b.pos[r], a.ep, nullptr, nullptr, w);
-            finish_read(tid, r, c0, c1, n_c, w);
-        }
-    } else {
-        for (int li = warp_id(); li < nr; li += SCAN_THREADS / 32) {
-            int64_t r = r0 + li;
-            const uint32_t *c = read_ptr(r); int n_c = (int)(a.b.cigar_off[r + 1] - a.b.cigar_off[r]);
-            WalkStats w; walk_warp<false>(c, n_c, a.b.pos[r], a.ep, nullptr, nullptr, w);
-            if (lane_id() == 0) finish_read(li, r, n_c > 0 ? c[0] : 0u, n_c > 0 ? c[n_c - 1] : 0u, n_c, w);
-        }
+        const bool unmapped = (a.b.flag[r] & 4) != 0;
+        s_mask[tid] = mask ? 1 : 0;
+        s_cnt[tid] = (mask && do_exon && !unmapped) ? w.n_exon : 0;
+        s_start[tid] = w.first_start; s_end[tid] = w.last_end;
     }
     __syncthreads();
 
@@ -359,96 +240,331 @@ __global__ void __launch_bounds__(SCAN_THREADS, WMX == 3 ? 6 : 0) cigar_scan_ker
     }
     if (!do_exon || ex_total == 0) return;
 
-    // ---- walk 2: emit exons (into the shared staging buffer when the tile fits, else straight to HBM)
-    // warp mode stages the exons of the tile and writes them out coalesced; thread mode moves each read's parked exons
-    // straight to the pools (one staging buffer less: 6 instead of 4 resident CTAs per SM cover the look-back waits)
-    const bool ex_staged = WARP_MODE && a.stage_words > 0 && ex_total <= (uint32_t)EX_STAGE;
-    s_cnt[tid] = (int)ex_excl;                                   // reuse as local exon offset (own slot only)
-    if constexpr (WM == 2) if (flat && tid < nr) fs.emit[tid] = my_ex > 0;
-    __syncthreads();
+    // ---- walk 2: each read's parked exons move straight to the pools (no staging buffer: 6 resident CTAs per SM cover
+    // the look-back waits)
     const bool room = (int64_t)ex_base + ex_total <= a.ex.cap;   // host re-runs with a larger pool otherwise
     if (!room) return;
-    if constexpr (WM == 2) if (flat) {
-        // every slice replays its ops once more, now with the exon slot of each emitted cut: slot of the read + cuts emitted since its first op
-        int *bes = ex_staged ? s_es : a.ex.es + ex_base, *bee = ex_staged ? s_ee : a.ex.ee + ex_base;
-        uint32_t P = fP, E = fE; int li = fli, lc = fcut; uint32_t lcP = fcutP;
-        for (int i = fa0; i < fa1; ++i) {
-            while (i >= fs.off[li + 1]) ++li;
-            const uint32_t x = f_words[i], l = x >> 4, op = x & 15u;
-            const bool cut = (op == OP_N && (int)l >= a.ep.min_intron) || (op == OP_D && (int)l > a.ep.max_delet);
-            if (cut) {
-                const bool first_cut = lc < fs.off[li];
-                const int end_before = fs.pos[li] + (int)(P - fs.base[li]);
-                const int start = first_cut ? fs.pos[li] + 1 : fs.pos[li] + (int)(lcP - fs.base[li]) + 1;
-                if (first_cut || end_before - start + 1 >= a.ep.min_exon) {
-                    if (fs.emit[li]) { const uint32_t k = (uint32_t)s_cnt[li] + (E - fs.EB[li]); bes[k] = start; bee[k] = end_before; }
-                    ++E;
-                }
-            }
-            if (op_ref(op)) P += l;
-            if (cut) { lc = i; lcP = P; }
-            if (i == fs.off[li + 1] - 1 && fs.emit[li]) {           // the open exon behind the last op (bam2gtf.c:74-76)
-                const uint32_t k = (uint32_t)s_cnt[li] + (fs.EE[li] - fs.EB[li]);
-                bes[k] = lc >= fs.off[li] ? fs.pos[li] + (int)(lcP - fs.base[li]) + 1 : fs.pos[li] + 1;
-                bee[k] = fs.pos[li] + (int)(P - fs.base[li]);
-            }
+    if (tid < nr && my_ex) {
+        int64_t r = r0 + tid;
+        const uint32_t *c = read_ptr(r); int n_c = (int)(a.b.cigar_off[r + 1] - a.b.cigar_off[r]);
+        int *es = a.ex.es + ex_base + ex_excl, *ee = a.ex.ee + ex_base + ex_excl;
+        if (parked && !park_ovf) {                            // move the parked exons; the open one is still in registers
+            const int last = (int)my_ex - 1;
+            for (int k = 0; k < last; ++k) { es[k] = (int)c[2 * k]; ee[k] = (int)c[2 * k + 1]; }
+            es[last] = park_last_start; ee[last] = s_end[tid];
+        } else {
+            if (parked) c = a.b.cigar + a.b.cigar_off[r];     // the staged copy is partly overwritten: walk the pool
+            WalkStats w; walk_seq<true>(c, n_c, a.b.pos[r], a.ep, es, ee, w);
         }
-        if (tid < nr && fs.emit[tid] && fs.off[tid + 1] == fs.off[tid]) { bes[s_cnt[tid]] = fs.pos[tid] + 1; bee[s_cnt[tid]] = fs.pos[tid]; }   // no ops at all
-    }
-    if (flat) { }
-    else if (!WARP_MODE) {
-        if (tid < nr && my_ex) {
-            int64_t r = r0 + tid;
-            const uint32_t *c = read_ptr(r); int n_c = (int)(a.b.cigar_off[r + 1] - a.b.cigar_off[r]);
-            int *es = ex_staged ? s_es + ex_excl : a.ex.es + ex_base + ex_excl;
-            int *ee = ex_staged ? s_ee + ex_excl : a.ex.ee + ex_base + ex_excl;
-            if (parked && !park_ovf) {                            // move the parked exons; the open one is still in registers
-                const int last = (int)my_ex - 1;
-                for (int k = 0; k < last; ++k) { es[k] = (int)c[2 * k]; ee[k] = (int)c[2 * k + 1]; }
-                es[last] = park_last_start; ee[last] = s_end[tid];
-            } else {
-                if (parked) c = a.b.cigar + a.b.cigar_off[r];     // the staged copy is partly overwritten: walk the pool
-                WalkStats w; walk_seq<true>(c, n_c, a.b.pos[r], a.ep, es, ee, w);
-            }
-        }
-    } else {
-        for (int li = warp_id(); li < nr; li += SCAN_THREADS / 32) {
-            // my_ex of read li lives in thread li's registers: fetch count via the row test below
-            int64_t r = r0 + li;
-            bool walk = s_mask[li] && !(a.b.flag[r] & 4);
-            if (!walk) continue;
-            const uint32_t *c = read_ptr(r); int n_c = (int)(a.b.cigar_off[r + 1] - a.b.cigar_off[r]);
-            uint32_t lo = (uint32_t)s_cnt[li];
-            int *es = ex_staged ? s_es + lo : a.ex.es + ex_base + lo;
-            int *ee = ex_staged ? s_ee + lo : a.ex.ee + ex_base + lo;
-            WalkStats w; walk_warp<true>(c, n_c, a.b.pos[r], a.ep, es, ee, w);
-        }
-    }
-    if (ex_staged) {
-        __syncthreads();
-        for (uint32_t i = tid; i < ex_total; i += SCAN_THREADS) { a.ex.es[ex_base + i] = s_es[i]; a.ex.ee[ex_base + i] = s_ee[i]; }
     }
 }
 
-void launch_cigar_scan(const ScanArgs &a, int n_tiles, bool warp_mode, size_t smem_bytes, cudaStream_t st)
+// ------------------------------------------------------------------------------------ long CIGARs: streaming scan
+// ONT-like reads carry hundreds of ops, so the pass is a stream over the CIGAR pool with a segmented scan on top.
+//
+//   * a CTA owns a tile of <= ST_R consecutive reads = ONE contiguous range of the pool; its 8 warps split that range at
+//     read boundaries into spans of about equal op counts, so a read never straddles two warps and no block-wide
+//     synchronisation happens while the ops stream;
+//   * every warp pulls its span through its own shared-memory ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier
+//     complete_tx, ST_STAGES stages in flight: the loads of the next rounds run under the scan of the current one) and
+//     consumes it in rounds of 256 ops, 8 consecutive ops per lane (two conflict-free 128-bit shared loads);
+//   * what a sequential walk carries from op to op is a flat prefix over the span, read boundaries ignored: reference
+//     bases consumed (32-bit, modular), deletion bases, N ops, cut ops -- two warp scans per round; per-read values are
+//     differences of that prefix between the read's last and first op, so the pool is read exactly ONCE;
+//   * the flat prefix of the reference bases is written back over the ops in the ring, so the (few) cut ops find the
+//     exon end in front of them and the exon start behind them with two shared loads; exon k of a read lands in the warp's
+//     staging slot (cuts so far in the span) + (reads so far in the span), whatever the read boundaries are;
+//   * the tile's reads are then finished by one thread each (filter predicate, short internal exons dropped as
+//     bam2gtf.c:45 does), placed by the same (rows, exons) look-back as the short-CIGAR kernel and copied to the pools.
+// A tile whose exons overflow the staging slots is redone by walk_warp (one warp per read, two walks).
+static constexpr int ST_THREADS = 256, ST_WARPS = ST_THREADS / 32;
+static constexpr int ST_R = 128;                    // reads per tile (upper bound)
+static constexpr int ST_ROUND = 256;                // ops per warp round = 8 per lane
+static constexpr int ST_CHUNK = 256;                // words per ring stage (one round)
+static constexpr int ST_STAGES = 4;
+static constexpr int ST_EXW = 256;                  // exon staging slots per warp
+
+LRB_DEVINL uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+LRB_DEVINL void mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+LRB_DEVINL void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+LRB_DEVINL void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+LRB_DEVINL bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+struct StreamSmem {
+    alignas(128) uint32_t ring[ST_WARPS][ST_STAGES][ST_CHUNK];
+    int es[ST_WARPS][ST_EXW], ee[ST_WARPS][ST_EXW];
+    alignas(8) uint64_t bar[ST_WARPS][ST_STAGES];
+    int off[ST_R + 1], pos[ST_R];
+    uint2 dslot[ST_R];                              // x: D = pos - (flat reference prefix at the read's first op), y: reads before it in the span
+    int ref_len[ST_R], del_len[ST_R], intron_n[ST_R];
+    uint16_t ncut[ST_R], sbeg[ST_R]; uint8_t wof[ST_R];
+    int cnt[ST_THREADS], start[ST_THREADS], end[ST_THREADS];
+    uint8_t mask[ST_THREADS];
+    uint32_t scan[33]; uint32_t tile; int ovf; uint64_t excl;
+};
+
+__global__ void __launch_bounds__(ST_THREADS, 3) cigar_stream_kernel(ScanArgs a)
+{
+    extern __shared__ __align__(128) uint8_t st_raw[];
+    StreamSmem &S = *reinterpret_cast<StreamSmem *>(st_raw);
+    const int tid = threadIdx.x, lane = lane_id(), w = warp_id(), R = a.reads_per_tile;
+    if (tid == 0) { S.tile = atomicAdd(a.ticket, 1u); S.ovf = 0; }
+    if (lane == 0) for (int s = 0; s < ST_STAGES; ++s) mbar_init(&S.bar[w][s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const int tile = (int)S.tile;
+    const int64_t r0 = (int64_t)tile * R, r1 = min(a.b.n, r0 + R);
+    const int nr = (int)(r1 - r0);
+    const uint64_t w_lo = a.b.cigar_off[r0], w_hi = a.b.cigar_off[r1];
+    const bool do_filter = a.mode != 1, do_exon = a.mode != 0;
+    // a tile of more than 2^30 ops (128 reads of 65535 ops are 8.4 M) cannot exist with 16-bit n_cigar; guard anyway
+    const bool huge = w_hi - w_lo >= (1ull << 30);
+    const int nw = huge ? 0 : (int)(w_hi - w_lo);
+    if (tid <= nr) S.off[tid] = huge ? 0 : (int)(a.b.cigar_off[r0 + tid] - w_lo);
+    if (tid < nr) S.pos[tid] = a.b.pos[r0 + tid];
+    S.cnt[tid] = 0; S.mask[tid] = 0;
+    if (huge && tid == 0) S.ovf = 1;
+    __syncthreads();
+
+    // ---- phase A: every warp streams its span of reads
+    if (nw > 0) {
+        // span of warp w: reads [rs, re) = those that START in its share of the op range
+        auto first_read_at = [&](int t) { int lo = 0, hi = nr; while (lo < hi) { const int m = (lo + hi) >> 1; if (S.off[m] < t) lo = m + 1; else hi = m; } return lo; };
+        const int rs = w == 0 ? 0 : first_read_at((int)((int64_t)nw * w / ST_WARPS));
+        const int re = w == ST_WARPS - 1 ? nr : first_read_at((int)((int64_t)nw * (w + 1) / ST_WARPS));
+        const int a_op = S.off[rs], b_op = S.off[re];                    // ops [a_op, b_op) of the tile
+        if (a_op < b_op) {
+            uint32_t *ring = &S.ring[w][0][0]; uint64_t *bar = &S.bar[w][0];
+            int *xes = S.es[w], *xee = S.ee[w];
+            const uint64_t g_abs = (w_lo + (uint64_t)a_op) & ~3ull;      // 16-byte aligned start of the stream
+            const int lead = (int)(w_lo + (uint64_t)a_op - g_abs);       // pad words in front of the span (0..3)
+            const int n_words = lead + (b_op - a_op);                    // words of the stream
+            const int n_chunks = (n_words + ST_CHUNK - 1) / ST_CHUNK;
+            const uint32_t *src = a.b.cigar + g_abs;
+            auto issue = [&](int c) {
+                const int s = c % ST_STAGES;
+                int words = n_words - c * ST_CHUNK; words = words > ST_CHUNK ? ST_CHUNK : ((words + 3) & ~3);
+                mbar_expect_tx(&bar[s], (uint32_t)words * 4u);
+                bulk_g2s(ring + s * ST_CHUNK, src + (size_t)c * ST_CHUNK, (uint32_t)words * 4u, &bar[s]);
+            };
+            if (lane == 0) for (int c = 0; c < ST_STAGES && c < n_chunks; ++c) issue(c);
+            // warp-uniform state of the read being walked
+            int r = rs; while (S.off[r + 1] == a_op) ++r;                // first read with ops (a_op < b_op: it exists)
+            int nb = S.off[r + 1];                                       // its end
+            uint32_t baseS = 0, baseD = 0, baseN = 0, baseC = 0;         // flat prefixes at its first op
+            int ridx = 0;                                                // reads with ops started before it in the span
+            uint32_t carryS = 0, carryD = 0, carryN = 0, carryC = 0;     // flat prefixes at the start of the round
+            if (lane == 0) {
+                S.dslot[r] = make_uint2((uint32_t)S.pos[r], 0u); S.sbeg[r] = 0; S.wof[r] = (uint8_t)w;
+                if (do_exon) xes[0] = S.pos[r] + 1;
+            }
+            // per-lane read tracking for the cut ops
+            int rL = r, nbL = nb;
+            bool done = false;
+            for (int c = 0; c < n_chunks && !done; ++c) {
+                const int s = c % ST_STAGES;
+                while (!mbar_try_wait(&bar[s], (uint32_t)(c / ST_STAGES) & 1u)) { }
+                uint32_t *rw = ring + s * ST_CHUNK;
+                const int g = a_op - lead + c * ST_CHUNK;                // tile op index of the round's first word
+                const int i0 = g + 8 * lane;
+                uint4 q0 = *reinterpret_cast<const uint4 *>(rw + 8 * lane), q1 = *reinterpret_cast<const uint4 *>(rw + 8 * lane + 4);
+                uint32_t x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                uint32_t sp[8], dp[8], cm = 0, nm = 0, sacc = 0, dacc = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i = i0 + k;
+                    const uint32_t xv = (i >= a_op && i < b_op) ? x[k] : 0xFu;   // outside the span: op 15 consumes nothing
+                    const uint32_t l = xv >> 4, op = xv & 15u;
+                    if ((0x18Du >> op) & 1u) sacc += l;
+                    if (op == OP_D) dacc += l;
+                    const bool isn = op == OP_N;
+                    const bool cut = (isn && (int)l >= a.ep.min_intron) || (op == OP_D && (int)l > a.ep.max_delet);
+                    nm |= (isn ? 1u : 0u) << k; cm |= (cut ? 1u : 0u) << k;
+                    sp[k] = sacc; dp[k] = dacc;
+                }
+                // two warp scans: reference bases; (deletion bases : N ops : cut ops) packed
+                uint32_t incS = sacc;
+                unsigned long long bpk = ((unsigned long long)dacc << 32) | ((unsigned long long)__popc(nm) << 16) | (unsigned long long)__popc(cm);
+                unsigned long long incB = bpk;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(FULL, incS, o); const unsigned long long u = __shfl_up_sync(FULL, incB, o);
+                    if (lane >= o) { incS += t; incB += u; }
+                }
+                const uint32_t exS = carryS + incS - sacc;
+                const unsigned long long exB = incB - bpk;
+                const uint32_t exD = carryD + (uint32_t)(exB >> 32), exN = carryN + (uint32_t)((exB >> 16) & 0xffffu), exC = carryC + (uint32_t)(exB & 0xffffu);
+                // the flat reference prefix BEHIND every op goes back over the ops (the cut ops read it from there)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) sp[k] += exS;
+                *reinterpret_cast<uint4 *>(rw + 8 * lane) = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+                *reinterpret_cast<uint4 *>(rw + 8 * lane + 4) = make_uint4(sp[4], sp[5], sp[6], sp[7]);
+                // ---- read boundaries of this round, warp-uniform: position nb lies behind op nb - 1
+                const int gend = g + ST_ROUND;
+                while (nb <= gend) {
+                    const int p = nb - 1 - g, ol = p >> 3, ok = p & 7;   // owner lane / slot of the read's last op
+                    uint32_t vS = sp[0], vD = dp[0];
+                    if (ok == 1) { vS = sp[1]; vD = dp[1]; } else if (ok == 2) { vS = sp[2]; vD = dp[2]; } else if (ok == 3) { vS = sp[3]; vD = dp[3]; }
+                    else if (ok == 4) { vS = sp[4]; vD = dp[4]; } else if (ok == 5) { vS = sp[5]; vD = dp[5]; } else if (ok == 6) { vS = sp[6]; vD = dp[6]; }
+                    else if (ok == 7) { vS = sp[7]; vD = dp[7]; }
+                    const uint32_t low = (2u << ok) - 1u;
+                    const uint32_t Sb = __shfl_sync(FULL, vS, ol), Db = __shfl_sync(FULL, exD + vD, ol);
+                    const uint32_t Nb = __shfl_sync(FULL, exN + __popc(nm & low), ol), Cb = __shfl_sync(FULL, exC + __popc(cm & low), ol);
+                    if (lane == 0) {
+                        S.ref_len[r] = (int)(Sb - baseS); S.del_len[r] = (int)(Db - baseD); S.intron_n[r] = (int)(Nb - baseN);
+                        const uint32_t nc = Cb - baseC; S.ncut[r] = (uint16_t)(nc > 0xffffu ? 0xffffu : nc);
+                        if (do_exon) { const uint32_t sl = Cb + (uint32_t)ridx; if (sl < (uint32_t)ST_EXW) xee[sl] = S.pos[r] + (int)(Sb - baseS); else S.ovf = 1; }
+                    }
+                    int rn = r + 1; while (rn < re && S.off[rn + 1] == nb) ++rn;          // next read with ops
+                    if (rn >= re) { done = true; break; }
+                    r = rn; nb = S.off[r + 1]; baseS = Sb; baseD = Db; baseN = Nb; baseC = Cb; ++ridx;
+                    if (lane == 0) {
+                        const uint32_t sl = Cb + (uint32_t)ridx;
+                        S.dslot[r] = make_uint2((uint32_t)S.pos[r] - Sb, (uint32_t)ridx); S.sbeg[r] = (uint16_t)(sl < (uint32_t)ST_EXW ? sl : ST_EXW); S.wof[r] = (uint8_t)w;
+                        if (do_exon) { if (sl < (uint32_t)ST_EXW) xes[sl] = S.pos[r] + 1; else S.ovf = 1; }
+                    }
+                }
+                __syncwarp();
+                // ---- cut ops: exon end in front of the cut, exon start behind it
+                if (do_exon) {
+                    uint32_t m = cm;
+                    while (m) {
+                        const int k = __ffs(m) - 1; m &= m - 1;
+                        const int i = i0 + k, wi = 8 * lane + k;
+                        while (i >= nbL) { ++rL; nbL = S.off[rL + 1]; }
+                        const uint2 ds = S.dslot[rL];
+                        const uint32_t s_after = rw[wi], s_before = wi ? rw[wi - 1] : carryS;
+                        const uint32_t sl = exC + __popc(cm & ((1u << k) - 1u)) + ds.y;
+                        if (sl + 1 < (uint32_t)ST_EXW) { xee[sl] = (int)(ds.x + s_before); xes[sl + 1] = (int)(ds.x + s_after) + 1; }
+                        else S.ovf = 1;
+                    }
+                }
+                // ---- carries into the next round
+                const unsigned long long totB = __shfl_sync(FULL, incB, 31);
+                carryS += __shfl_sync(FULL, incS, 31); carryD += (uint32_t)(totB >> 32); carryN += (uint32_t)((totB >> 16) & 0xffffu); carryC += (uint32_t)(totB & 0xffffu);
+                __syncwarp();
+                if (lane == 0 && c + ST_STAGES < n_chunks) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); issue(c + ST_STAGES); }
+            }
+        }
+    }
+    __syncthreads();
+    const bool ovf = S.ovf != 0;
+
+    // ---- phase B: one thread finishes one read
+    auto finish_read = [&](int li, int64_t rr, uint32_t c0, uint32_t c1, int n_c, const WalkStats &ws) {
+        bool mask;
+        if (do_filter) {
+            int sc = 0; bool p = filter_pass(a, rr, c0, c1, n_c, ws, &sc);
+            a.pass[rr] = p ? 1 : 0;
+            if (p) { a.score[rr] = sc; a.intron_n[rr] = ws.intron_n; }
+            mask = p;
+        } else mask = a.sel_mask ? (a.sel_mask[rr] != 0) : true;
+        const bool unmapped = (a.b.flag[rr] & 4) != 0;
+        S.mask[li] = mask ? 1 : 0;
+        S.cnt[li] = (mask && do_exon && !unmapped) ? ws.n_exon : 0;
+        S.start[li] = ws.first_start; S.end[li] = ws.last_end;
+    };
+    if (!ovf) {
+        if (tid < nr) {
+            const int64_t rr = r0 + tid;
+            const int n_c = S.off[tid + 1] - S.off[tid];
+            const uint32_t *cg = a.b.cigar + w_lo;
+            const uint32_t c0 = n_c > 0 ? cg[S.off[tid]] : 0u, c1 = n_c > 0 ? cg[S.off[tid + 1] - 1] : 0u;
+            WalkStats ws;
+            ws.first_start = S.pos[tid] + 1;
+            if (n_c > 0) {
+                ws.ref_len = S.ref_len[tid]; ws.del_len = S.del_len[tid]; ws.intron_n = S.intron_n[tid];
+                int n = (int)S.ncut[tid] + 1;
+                if (do_exon && n > 2) {                          // short internal exons vanish (bam2gtf.c:45), the first and the last stay
+                    int *xs = S.es[S.wof[tid]] + S.sbeg[tid], *xe = S.ee[S.wof[tid]] + S.sbeg[tid];
+                    int o = 1;
+                    for (int k = 1; k < n - 1; ++k) if (xe[k] - xs[k] + 1 >= a.ep.min_exon) { xs[o] = xs[k]; xe[o] = xe[k]; ++o; }
+                    xs[o] = xs[n - 1]; xe[o] = xe[n - 1]; n = o + 1;
+                }
+                ws.n_exon = n;
+            } else { ws.ref_len = 0; ws.del_len = 0; ws.intron_n = 0; ws.n_exon = 1; }
+            ws.last_end = S.pos[tid] + ws.ref_len;
+            finish_read(tid, rr, c0, c1, n_c, ws);
+        }
+    } else {
+        for (int li = w; li < nr; li += ST_WARPS) {
+            const int64_t rr = r0 + li;
+            const uint32_t *c = a.b.cigar + a.b.cigar_off[rr]; const int n_c = (int)(a.b.cigar_off[rr + 1] - a.b.cigar_off[rr]);
+            WalkStats ws; walk_warp<false>(c, n_c, a.b.pos[rr], a.ep, nullptr, nullptr, ws);
+            if (lane == 0) finish_read(li, rr, n_c > 0 ? c[0] : 0u, n_c > 0 ? c[n_c - 1] : 0u, n_c, ws);
+        }
+    }
+    __syncthreads();
+
+    // ---- tile offsets: block scan of (rows, exons) + look-back across tiles
+    const uint32_t my_row = S.mask[tid], my_ex = (uint32_t)S.cnt[tid];
+    uint32_t rows_total, ex_total;
+    const uint32_t row_excl = block_excl_sum(my_row, S.scan, &rows_total);
+    const uint32_t ex_excl = block_excl_sum(my_ex, S.scan, &ex_total);
+    if (w == 0) {
+        const uint64_t e = lookback_exclusive(a.tile_state, tile, pack_pair(rows_total, ex_total), OpAdd());
+        if (lane == 0) S.excl = e;
+    }
+    __syncthreads();
+    const uint32_t row_base = pair_hi(S.excl), ex_base = pair_lo(S.excl);
+    if (r1 == a.b.n && tid == 0) { a.totals[0] = (uint64_t)row_base + rows_total; a.totals[1] = (uint64_t)ex_base + ex_total; }
+    if (tid < nr && my_row) {
+        const int64_t rr = r0 + tid; const uint32_t row = a.rows_by_record ? (uint32_t)rr : row_base + row_excl;
+        if ((int64_t)row < a.rows.cap) {
+            a.rows.read_idx[row] = (uint32_t)rr;
+            if (do_exon) {
+                const int8_t xs = a.b.xs[rr];
+                a.rows.tid[row] = a.b.tid[rr];
+                a.rows.is_rev[row] = xs == 0 ? ((a.b.flag[rr] & 16) != 0) : (xs == '+' ? 0 : 1);    // bam2gtf.c:35-37
+                a.rows.start[row] = S.start[tid]; a.rows.end[row] = S.end[tid];
+                a.rows.ex_beg[row] = ex_base + ex_excl; a.rows.ex_n[row] = my_ex;
+            }
+        }
+    }
+    if (!do_exon || ex_total == 0) return;
+    if ((int64_t)ex_base + ex_total > a.ex.cap) return;          // host re-runs with a larger pool
+    if (!ovf) {
+        if (tid < nr && my_ex) {
+            int *es = a.ex.es + ex_base + ex_excl, *ee = a.ex.ee + ex_base + ex_excl;
+            if (S.off[tid + 1] == S.off[tid]) { es[0] = S.pos[tid] + 1; ee[0] = S.pos[tid]; }   // no ops at all: the open exon (bam2gtf.c:74-76)
+            else {
+                const int *xs = S.es[S.wof[tid]] + S.sbeg[tid], *xe = S.ee[S.wof[tid]] + S.sbeg[tid];
+                for (uint32_t k = 0; k < my_ex; ++k) { es[k] = xs[k]; ee[k] = xe[k]; }
+            }
+        }
+    } else {
+        S.cnt[tid] = (int)ex_excl;
+        __syncthreads();
+        for (int li = w; li < nr; li += ST_WARPS) {
+            const int64_t rr = r0 + li;
+            if (!(S.mask[li] && !(a.b.flag[rr] & 4))) continue;
+            const uint32_t *c = a.b.cigar + a.b.cigar_off[rr]; const int n_c = (int)(a.b.cigar_off[rr + 1] - a.b.cigar_off[rr]);
+            WalkStats ws; walk_warp<true>(c, n_c, a.b.pos[rr], a.ep, a.ex.es + ex_base + S.cnt[li], a.ex.ee + ex_base + S.cnt[li], ws);
+        }
+    }
+}
+
+int stream_reads_per_tile() { return ST_R; }
+
+void launch_cigar_scan(const ScanArgs &a, int n_tiles, bool stream_mode, size_t smem_bytes, cudaStream_t st)
 {
     if (n_tiles <= 0) return;
-    static int flat = -1;
-    if (flat < 0) { const char *e = getenv("LRB_SCAN_FLAT"); flat = e ? atoi(e) : 1; }
-    static int occ6 = -1;
-    if (occ6 < 0) { const char *e = getenv("LRB_SCAN_OCC6"); occ6 = e ? atoi(e) : 1; }
-    if (warp_mode && flat && occ6) {
-        cudaFuncSetAttribute(cigar_scan_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cigar_scan_kernel<3><<<n_tiles, SCAN_THREADS, smem_bytes, st>>>(a);
-    } else if (warp_mode && flat) {
-        cudaFuncSetAttribute(cigar_scan_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cigar_scan_kernel<2><<<n_tiles, SCAN_THREADS, smem_bytes, st>>>(a);
-    } else if (warp_mode) {
-        cudaFuncSetAttribute(cigar_scan_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cigar_scan_kernel<1><<<n_tiles, SCAN_THREADS, smem_bytes, st>>>(a);
+    if (stream_mode) {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(cigar_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem)); attr = true; }
+        cigar_stream_kernel<<<n_tiles, ST_THREADS, sizeof(StreamSmem), st>>>(a);
     } else {
-        cudaFuncSetAttribute(cigar_scan_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-        cigar_scan_kernel<0><<<n_tiles, SCAN_THREADS, smem_bytes, st>>>(a);
+        cudaFuncSetAttribute(cigar_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cigar_scan_kernel<<<n_tiles, SCAN_THREADS, smem_bytes, st>>>(a);
     }
     LRB_COUNT_LAUNCH();
 }

@@ -202,7 +202,7 @@ static bool bgzf_inflate_mt(const Bytes &in, Bytes &out)
 static void push_name(Records &r, const char *s, size_t n)
 {
     r.names.insert(r.names.end(), s, s + n); r.names.push_back(0);
-    r.name_off.push_back((uint32_t)r.names.size());
+    r.name_off.push_back((uint64_t)r.names.size());
     r.qhash.push_back(hash_name(s, n));
 }
 
@@ -314,9 +314,9 @@ static bool parse_bam(Bytes &d, Header &h, Records &r, std::string &err)
             r.tid[j] = rdi32(c); r.pos[j] = rdi32(c + 4); r.flag[j] = (uint16_t)(fnc >> 16); r.l_qseq[j] = l_seq;
             const size_t ln = l_qname ? strnlen((const char *)q, l_qname) : 0;
             memcpy(r.names.data() + nm, q, ln); r.names[nm + ln] = 0; nm += ln + 1;
-            r.name_off[j + 1] = (uint32_t)nm; r.qhash[j] = hash_name((const char *)q, ln);
+            r.name_off[j + 1] = (uint64_t)nm; r.qhash[j] = hash_name((const char *)q, ln);
             if (n_cigar) memcpy(r.cigar.data() + cg, cig, 4 * (size_t)n_cigar);
-            cg += n_cigar; r.cigar_off[j + 1] = (uint32_t)cg;
+            cg += n_cigar; r.cigar_off[j + 1] = (uint64_t)cg;
             int32_t nmv; int8_t xs; scan_aux(aux, rp + 4 + bs, nmv, xs);
             r.nm[j] = nmv; r.xs[j] = xs;
             if (adopt) r.raw_off[j + 1] = (uint64_t)(rp - d.data()) + 4 + (size_t)bs;
@@ -438,7 +438,7 @@ static bool parse_sam_line(char *line, size_t len, const Header &h, Records &r)
     r.tid.push_back(tid); r.pos.push_back((int32_t)pos); r.flag.push_back((uint16_t)flag); r.l_qseq.push_back(l_seq);
     r.nm.push_back(nm); r.xs.push_back(xs);
     push_name(r, f[0], lq);
-    r.cigar_off.push_back((uint32_t)r.cigar.size());
+    r.cigar_off.push_back((uint64_t)r.cigar.size());
     if (r.keep_raw) {
         Bytes &o = r.raw; size_t base = o.size();
         put32(o, 0);                                                   // block_size placeholder
@@ -570,7 +570,7 @@ static bool parse_sam(Bytes &d, Header &h, Records &r, std::string &err)
         memcpy(r.l_qseq.data() + o, q.l_qseq.data(), m * 4); memcpy(r.nm.data() + o, q.nm.data(), m * 4); memcpy(r.xs.data() + o, q.xs.data(), m);
         memcpy(r.qhash.data() + o, q.qhash.data(), m * 8);
         memcpy(r.cigar.data() + b_cig[k], q.cigar.data(), q.cigar.size() * 4); memcpy(r.names.data() + b_nam[k], q.names.data(), q.names.size());
-        for (size_t i = 0; i < m; ++i) { r.cigar_off[o + i + 1] = (uint32_t)(q.cigar_off[i + 1] + b_cig[k]); r.name_off[o + i + 1] = (uint32_t)(q.name_off[i + 1] + b_nam[k]); }
+        for (size_t i = 0; i < m; ++i) { r.cigar_off[o + i + 1] = (uint64_t)(q.cigar_off[i + 1] + b_cig[k]); r.name_off[o + i + 1] = (uint64_t)(q.name_off[i + 1] + b_nam[k]); }
         if (r.keep_raw) {
             memcpy(r.raw.data() + b_raw[k], q.raw.data(), q.raw.size());
             for (size_t i = 0; i < m; ++i) r.raw_off[o + i + 1] = q.raw_off[i + 1] + b_raw[k];

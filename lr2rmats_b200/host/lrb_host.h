@@ -46,8 +46,8 @@ struct Records {
     std::vector<uint16_t> flag;
     std::vector<int8_t> xs;
     std::vector<uint64_t> qhash;
-    std::vector<uint32_t> cigar_off{0}, cigar;
-    std::vector<uint32_t> name_off{0};
+    std::vector<uint64_t> cigar_off{0}; std::vector<uint32_t> cigar;   // 64-bit running totals: no silent wrap past 2^32 ops / name bytes
+    std::vector<uint64_t> name_off{0};
     std::vector<char> names;                       // NUL-terminated qnames
     bool keep_raw = false;                         // keep BAM-encoded records for `filter` re-emission
     std::vector<uint64_t> raw_off{0};

@@ -131,10 +131,10 @@ class Reads:
         r = Reads()
         for k in ("tid", "pos", "flag", "l_qseq", "nm", "xs", "qname_hash", "qid"):
             setattr(r, k, getattr(self, k)[idx].copy())
-        lens = (self.cigar_off[idx + 1] - self.cigar_off[idx]).astype(np.int64)
+        lens = self.cigar_off[idx + 1].astype(np.int64) - self.cigar_off[idx].astype(np.int64)
         off = np.zeros(len(idx) + 1, np.int64); np.cumsum(lens, out=off[1:])
         src = np.repeat(self.cigar_off[idx].astype(np.int64) - off[:-1], lens) + np.arange(off[-1])
-        r.cigar = self.cigar[src].copy(); r.cigar_off = off.astype(np.uint32)
+        r.cigar = self.cigar[src].copy(); r.cigar_off = off.astype(np.uint64)
         r.chrom_names, r.chrom_lens = self.chrom_names, self.chrom_lens
         return r
 
@@ -235,7 +235,7 @@ def _concat(a: Reads, b: Reads) -> Reads:
     for k in ("tid", "pos", "flag", "l_qseq", "nm", "xs", "qname_hash", "qid"):
         setattr(r, k, np.concatenate([getattr(a, k), getattr(b, k)]))
     r.cigar = np.concatenate([a.cigar, b.cigar])
-    r.cigar_off = np.concatenate([a.cigar_off[:-1].astype(np.int64), b.cigar_off.astype(np.int64) + int(a.cigar_off[-1])]).astype(np.uint32)
+    r.cigar_off = np.concatenate([a.cigar_off[:-1].astype(np.int64), b.cigar_off.astype(np.int64) + int(a.cigar_off[-1])]).astype(np.uint64)
     return r
 
 
@@ -326,7 +326,7 @@ def _assemble(rng, n, tid, rev, s, e, keep, ont, cls, quirk_frac) -> Reads:
     r.xs = xs
     r.qid = np.arange(n, dtype=np.int64)
     r.qname_hash = splitmix64(r.qid)
-    r.cigar = cigar; r.cigar_off = coff.astype(np.uint32)
+    r.cigar = cigar; r.cigar_off = coff.astype(np.uint64)
 
     if quirk_frac > 0:
         _inject_quirks(rng, r, quirk_frac)

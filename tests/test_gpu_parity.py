@@ -180,7 +180,7 @@ def test_edge_cases(ctx, data):
     rds.flag = np.array([0, 16, 0, 4, 0], np.uint16); rds.nm = np.array([3, 0, 1, 0, 0], np.int32); rds.xs = np.array([0, ord('+'), ord('-'), 0, 7], np.int8)
     qn = lambda c: sum((x >> 4) for x in c if (x & 15) in (M, I, S, 7, 8))
     rds.l_qseq = np.array([qn(c) for c in cigs], np.int32); rds.qid = np.arange(5); rds.qname_hash = synth.splitmix64(np.arange(5))
-    rds.cigar = np.array(sum(cigs, []), np.uint32); rds.cigar_off = np.cumsum([0] + [len(c) for c in cigs]).astype(np.uint32)
+    rds.cigar = np.array(sum(cigs, []), np.uint32); rds.cigar_off = np.cumsum([0] + [len(c) for c in cigs]).astype(np.uint64)
     for e in (ep, cabi.ExonParams.default(min_exon=0, min_intron=0, max_delet=0)):
         g = ctx.bam2gtf(rds.soa(), e); o = op.bam2gtf(rds.soa(), e); g["read_idx"] = None
         assert_dict_equal(g, o)
@@ -224,7 +224,7 @@ def test_random_cigars(ctx, data):
         rds.xs = rng.choice([0, ord('+'), ord('-')], size=n).astype(np.int8)
         rds.l_qseq = np.array([max(1, sum((x >> 4) for x in c if (x & 15) in (0, 1, 4, 7, 8))) for c in cigs], np.int32)
         rds.qid = np.arange(n); rds.qname_hash = synth.splitmix64(np.arange(n))
-        rds.cigar = np.array(sum(cigs, []), np.uint32); rds.cigar_off = np.cumsum([0] + [len(c) for c in cigs]).astype(np.uint32)
+        rds.cigar = np.array(sum(cigs, []), np.uint32); rds.cigar_off = np.cumsum([0] + [len(c) for c in cigs]).astype(np.uint64)
         for e in (cabi.ExonParams.default(), cabi.ExonParams.default(min_exon=0, min_intron=0, max_delet=0), cabi.ExonParams.default(min_exon=30, min_intron=3, max_delet=2)):
             g = ctx.bam2gtf(rds.soa(), e); o = op.bam2gtf(rds.soa(), e); g["read_idx"] = None
             assert_dict_equal(g, o)
@@ -233,6 +233,58 @@ def test_random_cigars(ctx, data):
         ctx.upload(rds.soa()); ctx.pipeline_run(fp, cabi.ExonParams.default())
         keep = ctx.filter_fetch()["keep_idx"]
         g = ctx.exon_fetch(); o = op.bam2gtf(rds.take(keep).soa(), cabi.ExonParams.default())
+        for k in ("exon_off", "exon_start", "exon_end", "is_rev"):
+            assert np.array_equal(g[k], o[k]), k
+
+
+def test_stream_scan_edge_cases(ctx, data):
+    """The long-CIGAR streaming kernel (mean ops > 48): reads of 0 / 1 / 2 ops and unmapped records between long reads, runs of
+    empty reads at tile and warp-span borders, short internal exons that vanish, a read whose exons overflow the staging
+    slots (tile redone by the warp walk), several tiles, sub-batches that start at odd word offsets."""
+    ctx.set_rm(None)
+    rng = np.random.default_rng(5)
+    fp = cabi.FilterParams.default()
+    def w(l, o): return (int(l) << 4) | int(o)
+    cigs = []
+    for i in range(700):
+        kind = int(rng.integers(0, 12))
+        if kind == 0: c = []
+        elif kind == 1: c = [w(rng.integers(1, 300), rng.choice([0, 3, 2, 4]))]
+        elif kind == 2: c = [w(30, 0), w(rng.integers(1, 200), 3)]
+        elif kind == 3:                              # many tiny internal exons (holes) between real ones
+            c = []
+            for k in range(int(rng.integers(20, 120))): c += [w(rng.integers(1, 6), 0), w(rng.integers(3, 90), 3)]
+            c.append(w(40, 0))
+        elif kind == 4 and i % 5 == 0:               # far more exons than the staging slots of a warp
+            c = []
+            for k in range(int(rng.integers(300, 700))): c += [w(rng.integers(3, 50), 0), w(rng.integers(60, 90), 2 if k % 4 == 0 else 3)]
+            c.append(w(10, 0))
+        else:
+            k = int(rng.integers(100, 900))
+            ops = rng.choice([0, 0, 0, 0, 1, 2, 2, 3, 7, 8], size=k)
+            lens = np.where(ops == 3, rng.integers(1, 2000, k), rng.integers(1, 60, k))
+            c = [w(5, 4)] + ((lens.astype(np.uint32) << 4) | ops.astype(np.uint32)).tolist() + [w(7, 4)]
+        cigs.append(c)
+    for lo in range(100, 140): cigs[lo] = []          # a run of empty reads around the first tile border (128)
+    n = len(cigs)
+    rds = synth.Reads()
+    rds.tid = np.zeros(n, np.int32); rds.pos = np.sort(rng.integers(0, 1_000_000, n)).astype(np.int32)
+    rds.flag = rng.choice([0, 16], size=n).astype(np.uint16); rds.nm = rng.integers(0, 10, n).astype(np.int32)
+    empty = np.array([len(c) == 0 for c in cigs])
+    rds.flag[empty & (rng.random(n) < 0.5)] = 4       # some of the empty ones are unmapped records
+    rds.xs = rng.choice([0, ord('+'), ord('-')], size=n).astype(np.int8)
+    rds.l_qseq = np.array([max(1, sum((x >> 4) for x in c if (x & 15) in (0, 1, 4, 7, 8))) for c in cigs], np.int32)
+    rds.qid = np.arange(n); rds.qname_hash = synth.splitmix64(np.arange(n))
+    rds.cigar = np.array(sum(cigs, []), np.uint32); rds.cigar_off = np.cumsum([0] + [len(c) for c in cigs]).astype(np.uint64)
+    assert rds.cigar.size / n > 48
+    for sub in (rds, rds.take(np.arange(3, n)), rds.take(np.arange(131, 400))):
+        for e in (cabi.ExonParams.default(), cabi.ExonParams.default(min_exon=0, min_intron=0, max_delet=0), cabi.ExonParams.default(min_exon=30, min_intron=3, max_delet=2)):
+            g = ctx.bam2gtf(sub.soa(), e); o = op.bam2gtf(sub.soa(), e); g["read_idx"] = None
+            assert_dict_equal(g, o)
+        assert_dict_equal(filter_valid(ctx.filter(sub.soa(), fp)), filter_valid(op.filter(sub.soa(), None, fp)))
+        ctx.upload(sub.soa()); ctx.pipeline_run(fp, cabi.ExonParams.default())
+        keep = ctx.filter_fetch()["keep_idx"]
+        g = ctx.exon_fetch(); o = op.bam2gtf(sub.take(keep).soa(), cabi.ExonParams.default())
         for k in ("exon_off", "exon_start", "exon_end", "is_rev"):
             assert np.array_equal(g[k], o[k]), k
 

@@ -262,27 +262,27 @@ __global__ void __launch_bounds__(SCAN_THREADS) cigar_scan_kernel(ScanArgs a)
 // ------------------------------------------------------------------------------------ long CIGARs: streaming scan
 // ONT-like reads carry hundreds of ops, so the pass is a stream over the CIGAR pool with a segmented scan on top.
 //
-//   * a CTA owns a tile of <= ST_R consecutive reads = ONE contiguous range of the pool; its 8 warps split that range at
-//     read boundaries into spans of about equal op counts, so a read never straddles two warps and no block-wide
-//     synchronisation happens while the ops stream;
-//   * every warp pulls its span through its own shared-memory ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier
-//     complete_tx, ST_STAGES stages in flight: the loads of the next rounds run under the scan of the current one) and
-//     consumes it in rounds of 256 ops, 8 consecutive ops per lane (two conflict-free 128-bit shared loads);
-//   * what a sequential walk carries from op to op is a flat prefix over the span, read boundaries ignored: reference
+//   * a WARP owns a tile of <= 32 consecutive reads = ONE contiguous range of the pool, and is autonomous: own ticket,
+//     own shared-memory ring, own staging slots, no block-wide synchronisation anywhere (a CTA is only a container);
+//   * the warp pulls its range through the ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx,
+//     ST_STAGES rounds in flight: the loads of the next rounds run under the scan of the current one) and consumes it
+//     in rounds of 256 ops, 8 consecutive ops per lane (two conflict-free 128-bit shared loads);
+//   * what a sequential walk carries from op to op is a flat prefix over the tile, read boundaries ignored: reference
 //     bases consumed (32-bit, modular), deletion bases, N ops, cut ops -- two warp scans per round; per-read values are
 //     differences of that prefix between the read's last and first op, so the pool is read exactly ONCE;
 //   * the flat prefix of the reference bases is written back over the ops in the ring, so the (few) cut ops find the
-//     exon end in front of them and the exon start behind them with two shared loads; exon k of a read lands in the warp's
-//     staging slot (cuts so far in the span) + (reads so far in the span), whatever the read boundaries are;
-//   * the tile's reads are then finished by one thread each (filter predicate, short internal exons dropped as
-//     bam2gtf.c:45 does), placed by the same (rows, exons) look-back as the short-CIGAR kernel and copied to the pools.
-// A tile whose exons overflow the staging slots is redone by walk_warp (one warp per read, two walks).
-static constexpr int ST_THREADS = 256, ST_WARPS = ST_THREADS / 32;
-static constexpr int ST_R = 128;                    // reads per tile (upper bound)
-static constexpr int ST_ROUND = 256;                // ops per warp round = 8 per lane
-static constexpr int ST_CHUNK = 256;                // words per ring stage (one round)
-static constexpr int ST_STAGES = 4;
-static constexpr int ST_EXW = 256;                  // exon staging slots per warp
+//     exon end in front of them and the exon start behind them with two shared loads; exon k of a read lands in staging
+//     slot (cuts so far in the tile) + (reads so far in the tile), whatever the read boundaries are;
+//   * read boundaries are warp-uniform events: lane j keeps the statistics of read j of the tile in registers and
+//     finishes it (filter predicate, short internal exons dropped as bam2gtf.c:45 does, row, exons to the pools).
+// Output placement: the fused pipeline writes rows at their record index, so a tile only needs room for its exons -- one
+// atomicAdd; the other modes keep the pools in read order with the (rows, exons) look-back, one word per warp tile.
+// A tile whose exons overflow the staging slots is redone by walk_warp (two walks per read).
+static constexpr int ST_THREADS = 128, ST_WARPS = ST_THREADS / 32;
+static constexpr int ST_R = 32;                     // reads per warp tile: one lane per read
+static constexpr int ST_ROUND = 256;                // ops per warp round = 8 per lane = one ring stage
+static constexpr int ST_STAGES = 3;
+static constexpr int ST_EXW = 512;                  // exon staging slots per warp tile
 
 LRB_DEVINL uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 LRB_DEVINL void mbar_init(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
@@ -299,233 +299,222 @@ LRB_DEVINL bool mbar_try_wait(uint64_t *bar, uint32_t parity)
     return ok != 0;
 }
 
-struct StreamSmem {
-    alignas(128) uint32_t ring[ST_WARPS][ST_STAGES][ST_CHUNK];
-    int es[ST_WARPS][ST_EXW], ee[ST_WARPS][ST_EXW];
-    alignas(8) uint64_t bar[ST_WARPS][ST_STAGES];
-    int off[ST_R + 1], pos[ST_R];
-    uint2 dslot[ST_R];                              // x: D = pos - (flat reference prefix at the read's first op), y: reads before it in the span
-    int ref_len[ST_R], del_len[ST_R], intron_n[ST_R];
-    uint16_t ncut[ST_R], sbeg[ST_R]; uint8_t wof[ST_R];
-    int cnt[ST_THREADS], start[ST_THREADS], end[ST_THREADS];
-    uint8_t mask[ST_THREADS];
-    uint32_t scan[33]; uint32_t tile; int ovf; uint64_t excl;
+// one step of an inclusive warp scan: shfl.up hands back "source lane in range" as a predicate, the add rides on it
+LRB_DEVINL void scan_up_add(uint32_t &v, int o)
+{
+    asm volatile("{\n.reg .u32 t;\n.reg .pred p;\nshfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n@p add.u32 %0, %0, t;\n}" : "+r"(v) : "r"(o));
+}
+
+struct StreamWarp {
+    alignas(128) uint32_t ring[ST_STAGES][ST_ROUND];
+    alignas(16) uint32_t dpre[ST_ROUND];            // flat prefix of the deletion bases behind every op of the round
+    int es[ST_EXW], ee[ST_EXW];
+    alignas(8) uint64_t bar[ST_STAGES];
+    uint2 dslot[ST_R];                              // x: pos - (flat reference prefix at the read's first op), y: reads with ops before it in the tile
+    int off[ST_R + 1];
 };
 
-__global__ void __launch_bounds__(ST_THREADS, 3) cigar_stream_kernel(ScanArgs a)
+__global__ void __launch_bounds__(ST_THREADS) cigar_stream_kernel(ScanArgs a, int n_tiles)
 {
-    extern __shared__ __align__(128) uint8_t st_raw[];
-    StreamSmem &S = *reinterpret_cast<StreamSmem *>(st_raw);
-    const int tid = threadIdx.x, lane = lane_id(), w = warp_id(), R = a.reads_per_tile;
-    if (tid == 0) { S.tile = atomicAdd(a.ticket, 1u); S.ovf = 0; }
-    if (lane == 0) for (int s = 0; s < ST_STAGES; ++s) mbar_init(&S.bar[w][s], 1);
+    __shared__ StreamWarp s_warp[ST_WARPS];
+    StreamWarp &S = s_warp[warp_id()];
+    const int lane = lane_id();
+    const bool do_filter = a.mode != 1, do_exon = a.mode != 0;
+    int tile = 0;
+    if (lane == 0) { tile = (int)atomicAdd(a.ticket, 1u); for (int s = 0; s < ST_STAGES; ++s) mbar_init(&S.bar[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    __syncthreads();
-    const int tile = (int)S.tile;
-    const int64_t r0 = (int64_t)tile * R, r1 = min(a.b.n, r0 + R);
+    tile = __shfl_sync(FULL, tile, 0);
+    if (tile >= n_tiles) return;                     // (the grid is rounded up to whole CTAs)
+    const int64_t r0 = (int64_t)tile * ST_R, r1 = min(a.b.n, r0 + ST_R);
     const int nr = (int)(r1 - r0);
     const uint64_t w_lo = a.b.cigar_off[r0], w_hi = a.b.cigar_off[r1];
-    const bool do_filter = a.mode != 1, do_exon = a.mode != 0;
-    // a tile of more than 2^30 ops (128 reads of 65535 ops are 8.4 M) cannot exist with 16-bit n_cigar; guard anyway
-    const bool huge = w_hi - w_lo >= (1ull << 30);
+    const bool huge = w_hi - w_lo >= (1ull << 30);   // cannot happen with 16-bit n_cigar (32 x 65535 ops); guard anyway
     const int nw = huge ? 0 : (int)(w_hi - w_lo);
-    if (tid <= nr) S.off[tid] = huge ? 0 : (int)(a.b.cigar_off[r0 + tid] - w_lo);
-    if (tid < nr) S.pos[tid] = a.b.pos[r0 + tid];
-    S.cnt[tid] = 0; S.mask[tid] = 0;
-    if (huge && tid == 0) S.ovf = 1;
-    __syncthreads();
+    const int64_t rr = r0 + lane;                    // this lane's read
+    const bool mine = lane < nr;
+    const int my_beg = mine ? (int)(min(a.b.cigar_off[rr], w_hi) - w_lo) : nw, my_end = mine ? (int)(min(a.b.cigar_off[rr + 1], w_hi) - w_lo) : nw;
+    const int my_pos = mine ? a.b.pos[rr] : 0;
+    // the record fields the filter predicate needs and the read's first / last op: loaded now, used after the stream
+    const uint32_t my_flag = mine ? a.b.flag[rr] : 4u;
+    const uint32_t c0 = (mine && my_end > my_beg) ? a.b.cigar[w_lo + (uint64_t)my_beg] : 0u, c1 = (mine && my_end > my_beg) ? a.b.cigar[w_lo + (uint64_t)my_end - 1] : 0u;
+    S.off[lane] = my_beg; if (lane == 31) S.off[32] = my_end;
+    int my_ref = 0, my_del = 0, my_int = 0; uint32_t my_ncut = 0, my_sbeg = 0;
+    bool ovf = huge;
+    __syncwarp();
 
-    // ---- phase A: every warp streams its span of reads
+    // ---- phase A: stream the tile's ops
     if (nw > 0) {
-        // span of warp w: reads [rs, re) = those that START in its share of the op range
-        auto first_read_at = [&](int t) { int lo = 0, hi = nr; while (lo < hi) { const int m = (lo + hi) >> 1; if (S.off[m] < t) lo = m + 1; else hi = m; } return lo; };
-        const int rs = w == 0 ? 0 : first_read_at((int)((int64_t)nw * w / ST_WARPS));
-        const int re = w == ST_WARPS - 1 ? nr : first_read_at((int)((int64_t)nw * (w + 1) / ST_WARPS));
-        const int a_op = S.off[rs], b_op = S.off[re];                    // ops [a_op, b_op) of the tile
-        if (a_op < b_op) {
-            uint32_t *ring = &S.ring[w][0][0]; uint64_t *bar = &S.bar[w][0];
-            int *xes = S.es[w], *xee = S.ee[w];
-            const uint64_t g_abs = (w_lo + (uint64_t)a_op) & ~3ull;      // 16-byte aligned start of the stream
-            const int lead = (int)(w_lo + (uint64_t)a_op - g_abs);       // pad words in front of the span (0..3)
-            const int n_words = lead + (b_op - a_op);                    // words of the stream
-            const int n_chunks = (n_words + ST_CHUNK - 1) / ST_CHUNK;
-            const uint32_t *src = a.b.cigar + g_abs;
-            auto issue = [&](int c) {
-                const int s = c % ST_STAGES;
-                int words = n_words - c * ST_CHUNK; words = words > ST_CHUNK ? ST_CHUNK : ((words + 3) & ~3);
-                mbar_expect_tx(&bar[s], (uint32_t)words * 4u);
-                bulk_g2s(ring + s * ST_CHUNK, src + (size_t)c * ST_CHUNK, (uint32_t)words * 4u, &bar[s]);
-            };
-            if (lane == 0) for (int c = 0; c < ST_STAGES && c < n_chunks; ++c) issue(c);
-            // warp-uniform state of the read being walked
-            int r = rs; while (S.off[r + 1] == a_op) ++r;                // first read with ops (a_op < b_op: it exists)
-            int nb = S.off[r + 1];                                       // its end
-            uint32_t baseS = 0, baseD = 0, baseN = 0, baseC = 0;         // flat prefixes at its first op
-            int ridx = 0;                                                // reads with ops started before it in the span
-            uint32_t carryS = 0, carryD = 0, carryN = 0, carryC = 0;     // flat prefixes at the start of the round
-            if (lane == 0) {
-                S.dslot[r] = make_uint2((uint32_t)S.pos[r], 0u); S.sbeg[r] = 0; S.wof[r] = (uint8_t)w;
-                if (do_exon) xes[0] = S.pos[r] + 1;
+        uint32_t *ring = &S.ring[0][0];
+        const uint64_t g_abs = w_lo & ~3ull;                         // 16-byte aligned start of the stream
+        const int lead = (int)(w_lo - g_abs);                        // pad words in front of the tile (0..3)
+        const int n_words = lead + nw;
+        const int n_chunks = (n_words + ST_ROUND - 1) / ST_ROUND;
+        const uint32_t *src = a.b.cigar + g_abs;
+        auto issue = [&](int c) {
+            const int s = c % ST_STAGES;
+            int words = n_words - c * ST_ROUND; words = words > ST_ROUND ? ST_ROUND : ((words + 3) & ~3);
+            mbar_expect_tx(&S.bar[s], (uint32_t)words * 4u);
+            bulk_g2s(ring + s * ST_ROUND, src + (size_t)c * ST_ROUND, (uint32_t)words * 4u, &S.bar[s]);
+        };
+        if (lane == 0) for (int c = 0; c < ST_STAGES && c < n_chunks; ++c) issue(c);
+        const uint32_t nonempty = __ballot_sync(FULL, my_end > my_beg);
+        // warp-uniform state of the read being walked
+        int r = __ffs(nonempty) - 1;                                 // first read with ops (nw > 0: it exists)
+        int nb = __shfl_sync(FULL, my_end, r);                       // its end
+        uint32_t baseS = 0, baseD = 0, baseN = 0, baseC = 0;         // flat prefixes at its first op
+        uint32_t ridx = 0;                                           // reads with ops started before it
+        uint32_t carryS = 0, carryD = 0, carryN = 0, carryC = 0;     // flat prefixes at the start of the round
+        if (lane == r) { S.dslot[r] = make_uint2((uint32_t)my_pos, 0u); my_sbeg = 0; }
+        bool done = false;
+        for (int c = 0; c < n_chunks && !done; ++c) {
+            const int s = c % ST_STAGES;
+            while (!mbar_try_wait(&S.bar[s], (uint32_t)(c / ST_STAGES) & 1u)) { }
+            uint32_t *rw = ring + s * ST_ROUND;
+            const int g = c * ST_ROUND - lead;                       // tile op index of the round's first word
+            const int i0 = g + 8 * lane;
+            // (lanes 4..7 of every quarter warp fetch their two quads in swapped order: the eight 16-byte accesses of a
+            // shared-memory phase then fall into eight different bank groups)
+            const int hsw = (lane >> 2) & 1;
+            const uint4 qa = *reinterpret_cast<const uint4 *>(rw + 8 * lane + 4 * hsw), qb = *reinterpret_cast<const uint4 *>(rw + 8 * lane + 4 - 4 * hsw);
+            const uint4 q0 = hsw ? qb : qa, q1 = hsw ? qa : qb;
+            uint32_t x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            if (g < 0 || g + ST_ROUND > nw) {                        // first / last round: words outside the tile consume nothing (op 15)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (i0 + k < 0 || i0 + k >= nw) x[k] = 0xFu;
             }
-            // per-lane read tracking for the cut ops
-            int rL = r, nbL = nb;
-            bool done = false;
-            for (int c = 0; c < n_chunks && !done; ++c) {
-                const int s = c % ST_STAGES;
-                while (!mbar_try_wait(&bar[s], (uint32_t)(c / ST_STAGES) & 1u)) { }
-                uint32_t *rw = ring + s * ST_CHUNK;
-                const int g = a_op - lead + c * ST_CHUNK;                // tile op index of the round's first word
-                const int i0 = g + 8 * lane;
-                uint4 q0 = *reinterpret_cast<const uint4 *>(rw + 8 * lane), q1 = *reinterpret_cast<const uint4 *>(rw + 8 * lane + 4);
-                uint32_t x[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-                uint32_t sp[8], dp[8], cm = 0, nm = 0, sacc = 0, dacc = 0;
+            // lane-local prefixes BEHIND every op go to shared memory at once (the reference bases over the ops themselves);
+            // the lane's own offsets exS / exD are added by whoever reads them
+            uint32_t sp[8], dp[8], cm = 0, nm = 0, sacc = 0, dacc = 0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int i = i0 + k;
-                    const uint32_t xv = (i >= a_op && i < b_op) ? x[k] : 0xFu;   // outside the span: op 15 consumes nothing
-                    const uint32_t l = xv >> 4, op = xv & 15u;
-                    if ((0x18Du >> op) & 1u) sacc += l;
-                    if (op == OP_D) dacc += l;
-                    const bool isn = op == OP_N;
-                    const bool cut = (isn && (int)l >= a.ep.min_intron) || (op == OP_D && (int)l > a.ep.max_delet);
-                    nm |= (isn ? 1u : 0u) << k; cm |= (cut ? 1u : 0u) << k;
-                    sp[k] = sacc; dp[k] = dacc;
-                }
-                // two warp scans: reference bases; (deletion bases : N ops : cut ops) packed
-                uint32_t incS = sacc;
-                unsigned long long bpk = ((unsigned long long)dacc << 32) | ((unsigned long long)__popc(nm) << 16) | (unsigned long long)__popc(cm);
-                unsigned long long incB = bpk;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(FULL, incS, o); const unsigned long long u = __shfl_up_sync(FULL, incB, o);
-                    if (lane >= o) { incS += t; incB += u; }
-                }
-                const uint32_t exS = carryS + incS - sacc;
-                const unsigned long long exB = incB - bpk;
-                const uint32_t exD = carryD + (uint32_t)(exB >> 32), exN = carryN + (uint32_t)((exB >> 16) & 0xffffu), exC = carryC + (uint32_t)(exB & 0xffffu);
-                // the flat reference prefix BEHIND every op goes back over the ops (the cut ops read it from there)
-#pragma unroll
-                for (int k = 0; k < 8; ++k) sp[k] += exS;
-                *reinterpret_cast<uint4 *>(rw + 8 * lane) = make_uint4(sp[0], sp[1], sp[2], sp[3]);
-                *reinterpret_cast<uint4 *>(rw + 8 * lane + 4) = make_uint4(sp[4], sp[5], sp[6], sp[7]);
-                // ---- read boundaries of this round, warp-uniform: position nb lies behind op nb - 1
-                const int gend = g + ST_ROUND;
-                while (nb <= gend) {
-                    const int p = nb - 1 - g, ol = p >> 3, ok = p & 7;   // owner lane / slot of the read's last op
-                    uint32_t vS = sp[0], vD = dp[0];
-                    if (ok == 1) { vS = sp[1]; vD = dp[1]; } else if (ok == 2) { vS = sp[2]; vD = dp[2]; } else if (ok == 3) { vS = sp[3]; vD = dp[3]; }
-                    else if (ok == 4) { vS = sp[4]; vD = dp[4]; } else if (ok == 5) { vS = sp[5]; vD = dp[5]; } else if (ok == 6) { vS = sp[6]; vD = dp[6]; }
-                    else if (ok == 7) { vS = sp[7]; vD = dp[7]; }
-                    const uint32_t low = (2u << ok) - 1u;
-                    const uint32_t Sb = __shfl_sync(FULL, vS, ol), Db = __shfl_sync(FULL, exD + vD, ol);
-                    const uint32_t Nb = __shfl_sync(FULL, exN + __popc(nm & low), ol), Cb = __shfl_sync(FULL, exC + __popc(cm & low), ol);
-                    if (lane == 0) {
-                        S.ref_len[r] = (int)(Sb - baseS); S.del_len[r] = (int)(Db - baseD); S.intron_n[r] = (int)(Nb - baseN);
-                        const uint32_t nc = Cb - baseC; S.ncut[r] = (uint16_t)(nc > 0xffffu ? 0xffffu : nc);
-                        if (do_exon) { const uint32_t sl = Cb + (uint32_t)ridx; if (sl < (uint32_t)ST_EXW) xee[sl] = S.pos[r] + (int)(Sb - baseS); else S.ovf = 1; }
-                    }
-                    int rn = r + 1; while (rn < re && S.off[rn + 1] == nb) ++rn;          // next read with ops
-                    if (rn >= re) { done = true; break; }
-                    r = rn; nb = S.off[r + 1]; baseS = Sb; baseD = Db; baseN = Nb; baseC = Cb; ++ridx;
-                    if (lane == 0) {
-                        const uint32_t sl = Cb + (uint32_t)ridx;
-                        S.dslot[r] = make_uint2((uint32_t)S.pos[r] - Sb, (uint32_t)ridx); S.sbeg[r] = (uint16_t)(sl < (uint32_t)ST_EXW ? sl : ST_EXW); S.wof[r] = (uint8_t)w;
-                        if (do_exon) { if (sl < (uint32_t)ST_EXW) xes[sl] = S.pos[r] + 1; else S.ovf = 1; }
-                    }
-                }
-                __syncwarp();
-                // ---- cut ops: exon end in front of the cut, exon start behind it
-                if (do_exon) {
-                    uint32_t m = cm;
-                    while (m) {
-                        const int k = __ffs(m) - 1; m &= m - 1;
-                        const int i = i0 + k, wi = 8 * lane + k;
-                        while (i >= nbL) { ++rL; nbL = S.off[rL + 1]; }
-                        const uint2 ds = S.dslot[rL];
-                        const uint32_t s_after = rw[wi], s_before = wi ? rw[wi - 1] : carryS;
-                        const uint32_t sl = exC + __popc(cm & ((1u << k) - 1u)) + ds.y;
-                        if (sl + 1 < (uint32_t)ST_EXW) { xee[sl] = (int)(ds.x + s_before); xes[sl + 1] = (int)(ds.x + s_after) + 1; }
-                        else S.ovf = 1;
-                    }
-                }
-                // ---- carries into the next round
-                const unsigned long long totB = __shfl_sync(FULL, incB, 31);
-                carryS += __shfl_sync(FULL, incS, 31); carryD += (uint32_t)(totB >> 32); carryN += (uint32_t)((totB >> 16) & 0xffffu); carryC += (uint32_t)(totB & 0xffffu);
-                __syncwarp();
-                if (lane == 0 && c + ST_STAGES < n_chunks) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); issue(c + ST_STAGES); }
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t l = x[k] >> 4, op = x[k] & 15u;
+                if ((0x18Du >> op) & 1u) sacc += l;
+                const bool isd = op == OP_D, isn = op == OP_N;
+                if (isd) dacc += l;
+                const bool cut = (isn && (int)l >= a.ep.min_intron) || (isd && (int)l > a.ep.max_delet);
+                nm |= (isn ? 1u : 0u) << k; cm |= (cut ? 1u : 0u) << k;
+                sp[k] = sacc; dp[k] = dacc;
             }
+            *reinterpret_cast<uint4 *>(rw + 8 * lane) = make_uint4(sp[0], sp[1], sp[2], sp[3]);
+            *reinterpret_cast<uint4 *>(rw + 8 * lane + 4) = make_uint4(sp[4], sp[5], sp[6], sp[7]);
+            *reinterpret_cast<uint4 *>(S.dpre + 8 * lane) = make_uint4(dp[0], dp[1], dp[2], dp[3]);
+            *reinterpret_cast<uint4 *>(S.dpre + 8 * lane + 4) = make_uint4(dp[4], dp[5], dp[6], dp[7]);
+            // three warp scans: reference bases, deletion bases, (N ops : cut ops) packed (<= 256 each per round)
+            uint32_t incS = sacc, incD = dacc;
+            const uint32_t ncp = ((uint32_t)__popc(nm) << 16) | (uint32_t)__popc(cm);
+            uint32_t incP = ncp;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { scan_up_add(incS, o); scan_up_add(incD, o); scan_up_add(incP, o); }
+            const uint32_t exS = carryS + incS - sacc, exD = carryD + incD - dacc;
+            const uint32_t exP = incP - ncp, exN = carryN + (exP >> 16), exC = carryC + (exP & 0xffffu);
+            __syncwarp();
+            int rL = r, nbL = nb;                                    // read of the round's first op: where the cut ops start looking for theirs
+            // ---- read boundaries of this round, warp-uniform: position nb lies behind op nb - 1
+            const int gend = g + ST_ROUND;
+            while (nb <= gend) {
+                const int p = nb - 1 - g;                            // word of the read's last op
+                const uint32_t low = (2u << (p & 7)) - 1u;
+                const uint32_t Sb = rw[p] + __shfl_sync(FULL, exS, p >> 3), Db = S.dpre[p] + __shfl_sync(FULL, exD, p >> 3);
+                const uint32_t Nb = __shfl_sync(FULL, exN + __popc(nm & low), p >> 3), Cb = __shfl_sync(FULL, exC + __popc(cm & low), p >> 3);
+                if (lane == r) { my_ref = (int)(Sb - baseS); my_del = (int)(Db - baseD); my_int = (int)(Nb - baseN); my_ncut = Cb - baseC; }
+                const uint32_t rest = r >= 31 ? 0u : (nonempty & ~((2u << r) - 1u));
+                if (!rest) { done = true; break; }
+                r = __ffs(rest) - 1; nb = __shfl_sync(FULL, my_end, r);
+                baseS = Sb; baseD = Db; baseN = Nb; baseC = Cb; ++ridx;
+                if (lane == r) { S.dslot[r] = make_uint2((uint32_t)my_pos - Sb, ridx); my_sbeg = Cb + ridx; }
+            }
+            __syncwarp();
+            // ---- cut ops: exon end in front of the cut, exon start behind it
+            if (do_exon) {
+                uint32_t m = cm;
+                while (m) {
+                    const int k = __ffs(m) - 1; m &= m - 1;
+                    const int i = i0 + k, wi = 8 * lane + k;
+                    while (i >= nbL) { ++rL; nbL = S.off[rL + 1]; }
+                    const uint2 ds = S.dslot[rL];
+                    const uint32_t s_after = exS + rw[wi], s_before = k ? exS + rw[wi - 1] : exS;
+                    const uint32_t sl = exC + __popc(cm & ((1u << k) - 1u)) + ds.y;
+                    if (sl + 1 < (uint32_t)ST_EXW) { S.ee[sl] = (int)(ds.x + s_before); S.es[sl + 1] = (int)(ds.x + s_after) + 1; }
+                    else ovf = true;
+                }
+            }
+            // ---- carries into the next round
+            const uint32_t totP = __shfl_sync(FULL, incP, 31);
+            carryS += __shfl_sync(FULL, incS, 31); carryD += __shfl_sync(FULL, incD, 31); carryN += totP >> 16; carryC += totP & 0xffffu;
+            __syncwarp();
+            if (lane == 0 && c + ST_STAGES < n_chunks) { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); issue(c + ST_STAGES); }
         }
     }
-    __syncthreads();
-    const bool ovf = S.ovf != 0;
+    ovf = __any_sync(FULL, ovf || (mine && my_end > my_beg && my_sbeg + my_ncut >= (uint32_t)ST_EXW));
 
-    // ---- phase B: one thread finishes one read
-    auto finish_read = [&](int li, int64_t rr, uint32_t c0, uint32_t c1, int n_c, const WalkStats &ws) {
-        bool mask;
+    // ---- phase B: lane j finishes read j of the tile
+    WalkStats ws; ws.n_exon = 0; ws.intron_n = 0; ws.del_len = 0; ws.ref_len = 0; ws.first_start = my_pos + 1; ws.last_end = my_pos;
+    uint32_t f0 = c0, f1 = c1; const int n_c = my_end - my_beg;
+    if (!ovf) {
+        if (mine) {
+            if (n_c > 0) {
+                ws.ref_len = my_ref; ws.del_len = my_del; ws.intron_n = my_int;
+                int n = (int)my_ncut + 1;
+                if (do_exon) {
+                    int *xs = S.es + my_sbeg, *xe = S.ee + my_sbeg;
+                    xs[0] = my_pos + 1; xe[n - 1] = my_pos + my_ref;
+                    if (n > 2) {                                 // short internal exons vanish (bam2gtf.c:45), the first and the last stay
+                        int o = 1;
+                        for (int k = 1; k < n - 1; ++k) if (xe[k] - xs[k] + 1 >= a.ep.min_exon) { xs[o] = xs[k]; xe[o] = xe[k]; ++o; }
+                        xs[o] = xs[n - 1]; xe[o] = xe[n - 1]; n = o + 1;
+                    }
+                }
+                ws.n_exon = n;
+            } else ws.n_exon = 1;
+            ws.last_end = my_pos + ws.ref_len;
+        }
+    } else {
+        for (int li = 0; li < nr; ++li) {                        // staging overflow: one warp walk per read
+            const int64_t q = r0 + li;
+            const uint32_t *cg = a.b.cigar + a.b.cigar_off[q]; const int nc = (int)(a.b.cigar_off[q + 1] - a.b.cigar_off[q]);
+            WalkStats t; walk_warp<false>(cg, nc, a.b.pos[q], a.ep, nullptr, nullptr, t);
+            if (lane == li) ws = t;
+        }
+    }
+    bool mask = false;
+    if (mine) {
         if (do_filter) {
-            int sc = 0; bool p = filter_pass(a, rr, c0, c1, n_c, ws, &sc);
+            int sc = 0; const bool p = filter_pass(a, rr, f0, f1, n_c, ws, &sc);
             a.pass[rr] = p ? 1 : 0;
             if (p) { a.score[rr] = sc; a.intron_n[rr] = ws.intron_n; }
             mask = p;
         } else mask = a.sel_mask ? (a.sel_mask[rr] != 0) : true;
-        const bool unmapped = (a.b.flag[rr] & 4) != 0;
-        S.mask[li] = mask ? 1 : 0;
-        S.cnt[li] = (mask && do_exon && !unmapped) ? ws.n_exon : 0;
-        S.start[li] = ws.first_start; S.end[li] = ws.last_end;
-    };
-    if (!ovf) {
-        if (tid < nr) {
-            const int64_t rr = r0 + tid;
-            const int n_c = S.off[tid + 1] - S.off[tid];
-            const uint32_t *cg = a.b.cigar + w_lo;
-            const uint32_t c0 = n_c > 0 ? cg[S.off[tid]] : 0u, c1 = n_c > 0 ? cg[S.off[tid + 1] - 1] : 0u;
-            WalkStats ws;
-            ws.first_start = S.pos[tid] + 1;
-            if (n_c > 0) {
-                ws.ref_len = S.ref_len[tid]; ws.del_len = S.del_len[tid]; ws.intron_n = S.intron_n[tid];
-                int n = (int)S.ncut[tid] + 1;
-                if (do_exon && n > 2) {                          // short internal exons vanish (bam2gtf.c:45), the first and the last stay
-                    int *xs = S.es[S.wof[tid]] + S.sbeg[tid], *xe = S.ee[S.wof[tid]] + S.sbeg[tid];
-                    int o = 1;
-                    for (int k = 1; k < n - 1; ++k) if (xe[k] - xs[k] + 1 >= a.ep.min_exon) { xs[o] = xs[k]; xe[o] = xe[k]; ++o; }
-                    xs[o] = xs[n - 1]; xe[o] = xe[n - 1]; n = o + 1;
-                }
-                ws.n_exon = n;
-            } else { ws.ref_len = 0; ws.del_len = 0; ws.intron_n = 0; ws.n_exon = 1; }
-            ws.last_end = S.pos[tid] + ws.ref_len;
-            finish_read(tid, rr, c0, c1, n_c, ws);
+    }
+    const uint32_t my_row = mask ? 1u : 0u;
+    const uint32_t my_ex = (mask && do_exon && !(my_flag & 4u)) ? (uint32_t)ws.n_exon : 0u;
+    // ---- placement: warp scan of (rows, exons), then one atomicAdd (rows by record) or the look-back across warp tiles
+    uint32_t row_inc = my_row, ex_inc = my_ex;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, row_inc, o), u = __shfl_up_sync(FULL, ex_inc, o); if (lane >= o) { row_inc += t; ex_inc += u; } }
+    const uint32_t rows_total = __shfl_sync(FULL, row_inc, 31), ex_total = __shfl_sync(FULL, ex_inc, 31);
+    const uint32_t row_excl = row_inc - my_row, ex_excl = ex_inc - my_ex;
+    uint32_t row_base = 0, ex_base = 0;
+    if (a.rows_by_record) {
+        unsigned long long eb = 0;
+        if (lane == 0) {
+            if (rows_total) atomicAdd((unsigned long long *)&a.totals[0], (unsigned long long)rows_total);
+            if (ex_total) eb = atomicAdd((unsigned long long *)&a.totals[1], (unsigned long long)ex_total);
         }
+        ex_base = (uint32_t)__shfl_sync(FULL, eb, 0);
     } else {
-        for (int li = w; li < nr; li += ST_WARPS) {
-            const int64_t rr = r0 + li;
-            const uint32_t *c = a.b.cigar + a.b.cigar_off[rr]; const int n_c = (int)(a.b.cigar_off[rr + 1] - a.b.cigar_off[rr]);
-            WalkStats ws; walk_warp<false>(c, n_c, a.b.pos[rr], a.ep, nullptr, nullptr, ws);
-            if (lane == 0) finish_read(li, rr, n_c > 0 ? c[0] : 0u, n_c > 0 ? c[n_c - 1] : 0u, n_c, ws);
-        }
+        const uint64_t e = __shfl_sync(FULL, lookback_exclusive(a.tile_state, tile, pack_pair(rows_total, ex_total), OpAdd()), 0);
+        row_base = pair_hi(e); ex_base = pair_lo(e);
+        if (r1 == a.b.n && lane == 0) { a.totals[0] = (uint64_t)row_base + rows_total; a.totals[1] = (uint64_t)ex_base + ex_total; }
     }
-    __syncthreads();
-
-    // ---- tile offsets: block scan of (rows, exons) + look-back across tiles
-    const uint32_t my_row = S.mask[tid], my_ex = (uint32_t)S.cnt[tid];
-    uint32_t rows_total, ex_total;
-    const uint32_t row_excl = block_excl_sum(my_row, S.scan, &rows_total);
-    const uint32_t ex_excl = block_excl_sum(my_ex, S.scan, &ex_total);
-    if (w == 0) {
-        const uint64_t e = lookback_exclusive(a.tile_state, tile, pack_pair(rows_total, ex_total), OpAdd());
-        if (lane == 0) S.excl = e;
-    }
-    __syncthreads();
-    const uint32_t row_base = pair_hi(S.excl), ex_base = pair_lo(S.excl);
-    if (r1 == a.b.n && tid == 0) { a.totals[0] = (uint64_t)row_base + rows_total; a.totals[1] = (uint64_t)ex_base + ex_total; }
-    if (tid < nr && my_row) {
-        const int64_t rr = r0 + tid; const uint32_t row = a.rows_by_record ? (uint32_t)rr : row_base + row_excl;
+    if (my_row) {
+        const uint32_t row = a.rows_by_record ? (uint32_t)rr : row_base + row_excl;
         if ((int64_t)row < a.rows.cap) {
             a.rows.read_idx[row] = (uint32_t)rr;
             if (do_exon) {
                 const int8_t xs = a.b.xs[rr];
                 a.rows.tid[row] = a.b.tid[rr];
                 a.rows.is_rev[row] = xs == 0 ? ((a.b.flag[rr] & 16) != 0) : (xs == '+' ? 0 : 1);    // bam2gtf.c:35-37
-                a.rows.start[row] = S.start[tid]; a.rows.end[row] = S.end[tid];
+                a.rows.start[row] = ws.first_start; a.rows.end[row] = ws.last_end;
                 a.rows.ex_beg[row] = ex_base + ex_excl; a.rows.ex_n[row] = my_ex;
             }
         }
@@ -533,22 +522,21 @@ __global__ void __launch_bounds__(ST_THREADS, 3) cigar_stream_kernel(ScanArgs a)
     if (!do_exon || ex_total == 0) return;
     if ((int64_t)ex_base + ex_total > a.ex.cap) return;          // host re-runs with a larger pool
     if (!ovf) {
-        if (tid < nr && my_ex) {
+        if (my_ex) {
             int *es = a.ex.es + ex_base + ex_excl, *ee = a.ex.ee + ex_base + ex_excl;
-            if (S.off[tid + 1] == S.off[tid]) { es[0] = S.pos[tid] + 1; ee[0] = S.pos[tid]; }   // no ops at all: the open exon (bam2gtf.c:74-76)
+            if (n_c == 0) { es[0] = my_pos + 1; ee[0] = my_pos; }    // no ops at all: the open exon (bam2gtf.c:74-76)
             else {
-                const int *xs = S.es[S.wof[tid]] + S.sbeg[tid], *xe = S.ee[S.wof[tid]] + S.sbeg[tid];
+                const int *xs = S.es + my_sbeg, *xe = S.ee + my_sbeg;
                 for (uint32_t k = 0; k < my_ex; ++k) { es[k] = xs[k]; ee[k] = xe[k]; }
             }
         }
     } else {
-        S.cnt[tid] = (int)ex_excl;
-        __syncthreads();
-        for (int li = w; li < nr; li += ST_WARPS) {
-            const int64_t rr = r0 + li;
-            if (!(S.mask[li] && !(a.b.flag[rr] & 4))) continue;
-            const uint32_t *c = a.b.cigar + a.b.cigar_off[rr]; const int n_c = (int)(a.b.cigar_off[rr + 1] - a.b.cigar_off[rr]);
-            WalkStats ws; walk_warp<true>(c, n_c, a.b.pos[rr], a.ep, a.ex.es + ex_base + S.cnt[li], a.ex.ee + ex_base + S.cnt[li], ws);
+        for (int li = 0; li < nr; ++li) {
+            const uint32_t cnt = __shfl_sync(FULL, my_ex, li), lo = __shfl_sync(FULL, ex_excl, li);
+            if (!cnt) continue;
+            const int64_t q = r0 + li;
+            const uint32_t *cg = a.b.cigar + a.b.cigar_off[q]; const int nc = (int)(a.b.cigar_off[q + 1] - a.b.cigar_off[q]);
+            WalkStats t; walk_warp<true>(cg, nc, a.b.pos[q], a.ep, a.ex.es + ex_base + lo, a.ex.ee + ex_base + lo, t);
         }
     }
 }
@@ -558,11 +546,8 @@ int stream_reads_per_tile() { return ST_R; }
 void launch_cigar_scan(const ScanArgs &a, int n_tiles, bool stream_mode, size_t smem_bytes, cudaStream_t st)
 {
     if (n_tiles <= 0) return;
-    if (stream_mode) {
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(cigar_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem)); attr = true; }
-        cigar_stream_kernel<<<n_tiles, ST_THREADS, sizeof(StreamSmem), st>>>(a);
-    } else {
+    if (stream_mode) cigar_stream_kernel<<<(n_tiles + ST_WARPS - 1) / ST_WARPS, ST_THREADS, 0, st>>>(a, n_tiles);
+    else {
         cudaFuncSetAttribute(cigar_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         cigar_scan_kernel<<<n_tiles, SCAN_THREADS, smem_bytes, st>>>(a);
     }

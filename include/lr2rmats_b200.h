@@ -31,6 +31,9 @@ extern "C" {
 #define LRB_E_UNSORTED   -4   /* update/unique need (tid,start)-sorted reads (update_gtf.c:41) */
 #define LRB_E_UNMAPPED   -5   /* unmapped record given to update/unique (reference aborts, bam2gtf.c:95-100) */
 #define LRB_E_NODEVICE   -6   /* no CUDA device: there is NO CPU fallback */
+#define LRB_E_NCCL       -7   /* NCCL missing or a collective failed (message in lrb_last_error) */
+#define LRB_E_XSHARD     -8   /* multi-GPU merge: a split piece shares a junction with a transcript of another shard; the
+                                 reference could merge them (update_gtf.c:148) -- rerun this input unsharded */
 
 /* ------------------------------------------------------------------ inputs */
 
@@ -299,12 +302,43 @@ int lrb_elapsed_ms(lrb_ctx *ctx, int slot_from, int slot_to, float *ms);   /* sy
 void *lrb_host_alloc(size_t bytes);
 void lrb_host_free(void *p);
 
-/* Multi-GPU plumbing: the caller (one process per GPU) owns the communicator;
- * tables are broadcast by the caller (torch.distributed / NCCL) into host or
- * device buffers and uploaded per rank.  Read shards are cut at locus gaps
- * (SURVEY App. B.3); this helper finds the cut points on the host. */
+/* ---------------------------------------------------------------- multi-GPU
+ * One process per GPU, one lrb_ctx per process, one NCCL communicator per ctx (the reference is a single
+ * thread -- its analogue is one `lr2rmats update-gtf` per chromosome shard and a `cat` of the outputs, App. B.3).
+ *
+ *   1. the caller cuts ONE (tid,start)-sorted read stream into locus-aligned shards (lrb_shard_cuts / _weighted);
+ *   2. lrb_comm_id on one rank, the 128 bytes shipped to the others by whatever launched them, lrb_comm_init on all;
+ *   3. lrb_tables_broadcast: the root's annotation / remove / SJ tables are replicated HBM -> HBM over NVLink
+ *      (replaces read_anno_trans / read_sj_group on every other rank);
+ *   4. every rank runs its shard (lrb_batch_upload, lrb_pipeline_run / lrb_exon_run, lrb_update_run);
+ *   5. lrb_update_gather: per-shard updated_T tables, BED rows and known-gene pairs go to rank 0 (count all-gather +
+ *      send/recv gatherv) and are merged canonically there: ordered concatenation, counters summed, the gene sets
+ *      (Updated_Genes, Genes_of_Known...: add_simp_gene update_gtf.c:175-189,503-506 -- a gene can span two loci)
+ *      recomputed / unioned over the gathered table, the piece-aware tid-0 sets (update_gtf.c:421-534)
+ *      recomputed when two shards share a tid-0 key;
+ *   6. lrb_gather_fetch on rank 0: the result exactly as one GPU (and the reference) would produce it for the whole stream.
+ */
+#define LRB_COMM_ID_BYTES 128
+int lrb_comm_id(void *id_out /* LRB_COMM_ID_BYTES */);
+int lrb_comm_init(lrb_ctx *ctx, const void *id, int rank, int n_ranks);
+int lrb_comm_destroy(lrb_ctx *ctx);
+int lrb_comm_rank(const lrb_ctx *ctx, int *rank, int *n_ranks);
+/* rank `root` passes its host tables (any may be NULL), the other ranks pass NULL; collective */
+int lrb_tables_broadcast(lrb_ctx *ctx, int root, const lrb_anno *anno, const lrb_anno *rm, const lrb_sj *sj);
+/* collective, after lrb_update_run on every rank.  name_base = index of this shard's first record in the whole read
+ * stream (name_idx of the merged table then indexes the whole stream).  LRB_E_XSHARD: see above. */
+int lrb_update_gather(lrb_ctx *ctx, int64_t name_base);
+/* rank 0: merged updated_T + BED rows + summary (anno counters [0],[1] left 0); other ranks: empty.  Any argument may be NULL. */
+int lrb_gather_fetch(lrb_ctx *ctx, lrb_trans_table *updated, lrb_bed_list *bed, int32_t summary[LRB_S_COUNT]);
+int lrb_gather_timing(lrb_ctx *ctx, float *ms_gather, float *ms_merge);   /* CUDA-event times of the last lrb_update_gather */
+
+/* Read shards are cut at locus gaps (where a read starts beyond every earlier end on its chromosome the
+ * outputs concatenate exactly); this helper finds n_shards-1 such cuts near the ideal boundaries on the host.
+ * _weighted balances the shards by `weight` (e.g. CIGAR ops per read) instead of by read count. */
 int lrb_shard_cuts(const int32_t *tid, const int32_t *start, const int32_t *end, int64_t n,
                    int n_shards, int64_t *cuts /* n_shards+1 */);
+int lrb_shard_cuts_weighted(const int32_t *tid, const int32_t *start, const int32_t *end, const int64_t *weight, int64_t n,
+                            int n_shards, int64_t *cuts /* n_shards+1 */);
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,8 @@ ENTRY_POINTS = [
     "lrb_sync", "lrb_rows_sort", "lrb_filter_fetch", "lrb_exon_fetch", "lrb_update_fetch", "lrb_unique_fetch", "lrb_filter", "lrb_bam2gtf",
     "lrb_update_gtf", "lrb_unique_gtf", "lrb_timing_enable", "lrb_timing_get", "lrb_launch_count", "lrb_shard_cuts",
     "lrb_mark", "lrb_elapsed_ms", "lrb_host_alloc", "lrb_host_free", "lrb_update_fetch_table", "lrb_filter_fetch_keep",
+    "lrb_comm_id", "lrb_comm_init", "lrb_comm_destroy", "lrb_comm_rank", "lrb_tables_broadcast", "lrb_update_gather", "lrb_gather_fetch",
+    "lrb_gather_timing", "lrb_shard_cuts_weighted",
 ]
 
 T_NAMES = ["filter", "exon", "classify", "merge", "summary", "k_scan", "k_fold"]
@@ -80,6 +82,15 @@ def load_library():
     L.lrb_host_free.argtypes = [C.c_void_p]; L.lrb_host_free.restype = None
     L.lrb_launch_count.argtypes = [vp]; L.lrb_launch_count.restype = C.c_int64
     L.lrb_shard_cuts.argtypes = [cabi.i32p, cabi.i32p, cabi.i32p, C.c_int64, C.c_int, P(C.c_int64)]
+    L.lrb_shard_cuts_weighted.argtypes = [cabi.i32p, cabi.i32p, cabi.i32p, P(C.c_int64), C.c_int64, C.c_int, P(C.c_int64)]
+    L.lrb_comm_id.argtypes = [C.c_void_p]
+    L.lrb_comm_init.argtypes = [vp, C.c_void_p, C.c_int, C.c_int]
+    L.lrb_comm_destroy.argtypes = [vp]
+    L.lrb_comm_rank.argtypes = [vp, P(C.c_int), P(C.c_int)]
+    L.lrb_tables_broadcast.argtypes = [vp, C.c_int, P(cabi.Anno), P(cabi.Anno), P(cabi.Sj)]
+    L.lrb_update_gather.argtypes = [vp, C.c_int64]
+    L.lrb_gather_fetch.argtypes = [vp, P(cabi.TransTable), P(cabi.BedList), P(C.c_int32 * cabi.S_COUNT)]
+    L.lrb_gather_timing.argtypes = [vp, P(C.c_float), P(C.c_float)]
     _lib = L
     return L
 
@@ -202,6 +213,34 @@ class Context:
             self._ck(self.L.lrb_unique_gtf(self.h, C.byref(b), C.byref(ep), C.byref(up), C.byref(r)))
         return cabi.unique_to_np(r)
 
+    # ---- multi-GPU (one process per GPU; see lr2rmats_b200/multi.py for the driver)
+    def comm_init(self, comm_id: bytes, rank: int, n_ranks: int):
+        self._comm_id = C.create_string_buffer(bytes(comm_id), COMM_ID_BYTES)
+        self._ck(self.L.lrb_comm_init(self.h, self._comm_id, rank, n_ranks))
+
+    def comm_destroy(self): self._ck(self.L.lrb_comm_destroy(self.h))
+
+    def tables_broadcast(self, root: int, anno: dict | None, rm: dict | None, sj: dict | None):
+        """Collective: the root passes its host tables, every other rank passes None."""
+        a = r = s = None
+        if anno is not None: a, self._keep["anno"] = cabi.make_anno(anno)
+        if rm is not None: r, self._keep["rm"] = cabi.make_anno(rm)
+        if sj is not None and len(sj["tid"]): s, self._keep["sj"] = cabi.make_sj(sj)
+        self._ck(self.L.lrb_tables_broadcast(self.h, root, C.byref(a) if a is not None else None, C.byref(r) if r is not None else None,
+                                             C.byref(s) if s is not None else None))
+
+    def update_gather(self, name_base: int): self._ck(self.L.lrb_update_gather(self.h, int(name_base)))
+
+    def gather_fetch(self, raw=False, want_bed=True):
+        t = cabi.TransTable(); b = cabi.BedList(); s = (C.c_int32 * cabi.S_COUNT)()
+        self._ck(self.L.lrb_gather_fetch(self.h, C.byref(t), C.byref(b) if want_bed else None, C.byref(s)))
+        if raw:
+            return t, b, s
+        return dict(table=cabi.table_to_np(t), bed=cabi.bed_to_np(b) if want_bed else None, summary=np.array(list(s), np.int32))
+
+    def gather_timing(self):
+        a = C.c_float(); b = C.c_float(); self._ck(self.L.lrb_gather_timing(self.h, C.byref(a), C.byref(b))); return float(a.value), float(b.value)
+
     # ---- measurement
     def timing(self, on=True): self._ck(self.L.lrb_timing_enable(self.h, 1 if on else 0))
 
@@ -219,11 +258,27 @@ class Context:
         ms = C.c_float(); self._ck(self.L.lrb_elapsed_ms(self.h, a, b, C.byref(ms))); return float(ms.value)
 
 
-def shard_cuts(tid, start, end, n_shards: int) -> np.ndarray:
+COMM_ID_BYTES = 128
+
+
+def comm_id() -> bytes:
+    """ncclGetUniqueId through the library: call on ONE rank and ship the bytes to the others."""
+    L = load_library()
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = L.lrb_comm_id(buf)
+    if rc != 0:
+        raise LrbError(rc, "lrb_comm_id (libnccl.so.2 not loadable?)")
+    return buf.raw
+
+
+def shard_cuts(tid, start, end, n_shards: int, weight=None) -> np.ndarray:
     L = load_library()
     tid = np.ascontiguousarray(tid, np.int32); start = np.ascontiguousarray(start, np.int32); end = np.ascontiguousarray(end, np.int32)
     cuts = (C.c_int64 * (n_shards + 1))()
-    rc = L.lrb_shard_cuts(tid.ctypes.data_as(cabi.i32p), start.ctypes.data_as(cabi.i32p), end.ctypes.data_as(cabi.i32p), len(tid), n_shards, cuts)
+    w = None
+    if weight is not None:
+        weight = np.ascontiguousarray(weight, np.int64); w = weight.ctypes.data_as(C.POINTER(C.c_int64))
+    rc = L.lrb_shard_cuts_weighted(tid.ctypes.data_as(cabi.i32p), start.ctypes.data_as(cabi.i32p), end.ctypes.data_as(cabi.i32p), w, len(tid), n_shards, cuts)
     if rc != 0:
-        raise LrbError(rc, "lrb_shard_cuts")
+        raise LrbError(rc, "lrb_shard_cuts_weighted")
     return np.array(list(cuts), np.int64)

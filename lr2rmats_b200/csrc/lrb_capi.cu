@@ -8,145 +8,11 @@
 #include <map>
 #include <string>
 #include <vector>
-#include "lrb_common.cuh"
-#include "lrb_kernels.cuh"
-#include "lrb_summary.cuh"
+#include "lrb_ctx.cuh"
 
-namespace lrbk { extern int64_t g_launches_update, g_launches_summary, g_launches_sort; }
 using namespace lrbk;
 
 namespace {
-
-struct Buf {                                        // device buffer, grow-only, contents not preserved on growth
-    void *p = nullptr; size_t cap = 0;
-    bool ensure(size_t bytes)
-    {
-        if (bytes <= cap) return true;
-        if (p) cudaFree(p);
-        size_t nc = bytes + bytes / 4 + 256;
-        if (cudaMalloc(&p, nc) != cudaSuccess) { p = nullptr; cap = 0; cudaGetLastError(); return false; }
-        cap = nc; return true;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-    template <class T> T *as() const { return (T *)p; }
-};
-struct PBuf {                                       // pinned host buffer
-    void *p = nullptr; size_t cap = 0;
-    bool ensure(size_t bytes)
-    {
-        if (bytes <= cap) return true;
-        if (p) cudaFreeHost(p);
-        size_t nc = bytes + bytes / 4 + 256;
-        if (cudaMallocHost(&p, nc) != cudaSuccess) { p = nullptr; cap = 0; cudaGetLastError(); return false; }
-        cap = nc; return true;
-    }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
-    template <class T> T *as() const { return (T *)p; }
-};
-
-struct MergeBufs {                                  // scratch + output of one merge fold
-    Buf keys, head, locus_start, locus_cnt, dropped, rep, lstart, evmask, samemask, hard, desc, relsym;
-    Buf w_cand, w_cov, w_tid, w_start, w_end, w_fs, w_le;
-    Buf o_cand, o_cov, o_tid, o_start, o_end, o_fs, o_le;
-    Buf c_tid, c_start, c_end, c_rev, c_n, c_fs, c_le, c_gbeg, c_hash, c_j0, c_sig;
-    int64_t n_out = 0, n_loci = 0;
-};
-
-}  // namespace
-
-struct lrb_ctx {
-    int device = 0; cudaStream_t st = nullptr; std::string err;
-    // side stream: work of a stage that is independent of its main chain (the class folds of the summary) runs here,
-    // forked / joined with events, on its own look-back state
-    cudaStream_t st2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; bool side_stream = true;
-    cudaStream_t st3 = nullptr; cudaEvent_t ev_fork3 = nullptr, ev_join3 = nullptr; bool sum_split = true;   // exon chain of the summary sets
-    // tables
-    DAnno anno; DSj sj; DRmIndex rm;
-    Buf a_tid, a_start, a_end, a_gene, a_rev, a_off, a_es, a_ee, a_pmax, a_mono;
-    Buf s_tid, s_don, s_acc, s_u, s_m, s_pmax, s_dkey;
-    Buf r_gtid, r_goff, r_start, r_pmax;
-    // batch
-    DBatch b; Buf b_tid, b_pos, b_lq, b_nm, b_flag, b_xs, b_qh, b_coff, b_cig;
-    bool have_batch = false;
-    // filter
-    Buf f_pass, f_score, f_intron, f_keep_row_mask, f_keep_rec_mask, f_keep_idx, f_keep_rows;
-    int64_t n_pass = 0, n_keep = 0; bool have_filter = false;
-    // rows + exons
-    DRows rows, rows2, rows3; DRows *cur = nullptr; DExons ex;      // rows3: the coordinate-sorted copy made by lrb_rows_sort
-    Buf r_read, r_tid, r_rs, r_re, r_rev, r_beg, r_n, r_nonmono;
-    Buf q_read, q_tid, q_rs, q_re, q_rev, q_beg, q_n;
-    Buf s_read, s_rtid, s_rs, s_re, s_rev, s_beg, s_n, s_key0, s_key1, s_idx0, s_idx1, s_hist;   // lrb_rows_sort
-    Buf e_s, e_e, e_f;
-    bool have_exons = false, rows_compact = false;
-    // update
-    Buf u_cls, u_ref, u_nnovel, u_noff, u_mk, u_mu, u_ck, u_cr, u_cu, u_cn, u_known, u_unrecog, u_sub;
-    DTransList novel; Buf n_row, n_lo, n_cnt, n_piece;
-    DTransList tmp_list; Buf t_row, t_lo, t_cnt, t_piece;
-    MergeBufs mg, mg2;
-    int64_t n_known = 0, n_unrecog = 0, novel_cap_hint = 0; bool have_update = false, have_unique = false;
-    int32_t summary[LRB_S_COUNT];
-    // summary
-    Buf h_khi, h_klo, h_min, h_score, y_barcnt, y_barseg, y_genebar, y_bedcnt, y_bedoff, y_counts, y_nelem;
-    Buf bd_tid, bd_s, bd_e, bd_sc, bd_ty, bd_rv; int64_t n_bed = 0;
-    // unique
-    Buf q_shared; int64_t n_shared = 0;
-    // look-back state, small device scalars and their pinned mirror
-    Buf tile_state, tile_state2, scalars; PBuf h_scalars;
-    // pinned result buffers
-    PBuf p[48];
-    Buf tb_name, tb_piece, tb_ttid, tb_tstart, tb_tend, tb_trev, tb_etid, tb_erev, tb_cov, tb_ref, tb_cnt, tb_off, tb_es, tb_ee;
-    // timing
-    bool timing = false; cudaEvent_t ev[12]; cudaEvent_t marks[8]; float ms[LRB_T_COUNT]; int64_t launches0 = 0, launches_last = 0;
-    lrb_update_params last_up;
-};
-
-namespace {
-
-int64_t total_launches() { return lrbk::count_launches() + lrbk::g_launches_update + lrbk::g_launches_summary + lrbk::g_launches_sort; }
-
-int fail(lrb_ctx *c, int code, const std::string &msg) { c->err = msg; return code; }
-#define CK(call)                                                                                               \
-    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(c, LRB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
-#define NEED(buf, bytes) do { if (!(buf).ensure(bytes)) return fail(c, LRB_E_NOMEM, "device allocation failed: " #buf); } while (0)
-#define NEEDP(buf, bytes) do { if (!(buf).ensure(bytes)) return fail(c, LRB_E_NOMEM, "pinned allocation failed: " #buf); } while (0)
-
-// device scalars: [0..31] uint64 totals, then uint32 ticket, err flags.  Slots 0..7 are scratch of the stage that is
-// running; the update stage parks its results in fixed slots so that ONE copy brings them all to the host:
-enum { T_NOVEL = 8, T_KNOWN = 9, T_UNREC = 10, T_LOCI = 11, T_UPD = 12, T_LOCI2 = 13, T_UPD2 = 14, T_NELEM = 15, T_BED = 16, T_SLOTS = 32 };
-uint64_t *d_totals(lrb_ctx *c) { return c->scalars.as<uint64_t>(); }
-uint32_t *d_ticket(lrb_ctx *c) { return (uint32_t *)(c->scalars.as<uint64_t>() + T_SLOTS); }
-uint32_t *d_err(lrb_ctx *c) { return d_ticket(c) + 1; }
-uint32_t *d_ticket2(lrb_ctx *c) { return d_ticket(c) + 2; }          // ticket of the side stream
-
-int read_totals(lrb_ctx *c, uint64_t *out, int n)
-{
-    CK(cudaMemcpyAsync(c->h_scalars.p, d_totals(c), 8 * (size_t)n, cudaMemcpyDeviceToHost, c->st));
-    CK(cudaStreamSynchronize(c->st));
-    memcpy(out, c->h_scalars.p, 8 * (size_t)n);
-    return LRB_OK;
-}
-
-int ensure_tiles(lrb_ctx *c, int64_t n_items)
-{
-    int64_t tiles = n_items / 8 + 1024;             // generous for every tiling used (>= n/256/8, n/reads_per_tile>=8)
-    NEED(c->tile_state, (size_t)tiles * 8);
-    return LRB_OK;
-}
-
-void tick(lrb_ctx *c, int k) { if (c->timing) cudaEventRecord(c->ev[k], c->st); }
-
-template <class T> int h2d(lrb_ctx *c, Buf &dst, const T *src, size_t n)
-{
-    NEED(dst, std::max<size_t>(n, 1) * sizeof(T));
-    if (n) CK(cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, c->st));
-    return LRB_OK;
-}
-template <class T> int d2h(lrb_ctx *c, PBuf &dst, const T *src, size_t n)
-{
-    NEEDP(dst, std::max<size_t>(n, 1) * sizeof(T));
-    if (n) CK(cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyDeviceToHost, c->st));
-    return LRB_OK;
-}
 
 int setup_rows(lrb_ctx *c, DRows &r, Buf &read, Buf &tid, Buf &rs, Buf &re, Buf &rev, Buf &beg, Buf &cnt, int64_t cap)
 {
@@ -329,6 +195,7 @@ int lrb_ctx_create(int device, lrb_ctx **out)
     cudaEventCreateWithFlags(&c->ev_fork3, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming);
     { const char *e = getenv("LRB_SUM_SPLIT"); if (e) c->sum_split = atoi(e) != 0; }
     { const char *e = getenv("LRB_SIDE_STREAM"); if (e) c->side_stream = atoi(e) != 0; }
+    { const char *e = getenv("LRB_FORCE_SINGLE_FOLD"); if (e) c->force_single_fold = atoi(e) != 0; }    // test hook: updated_T always folded by the one-locus replay
     if (!c->scalars.ensure(512) || !c->h_scalars.ensure(512)) { delete c; return LRB_E_NOMEM; }
     cudaMemsetAsync(c->scalars.p, 0, 512, c->st);
     for (int i = 0; i < 12; ++i) cudaEventCreate(&c->ev[i]);
@@ -351,9 +218,9 @@ void lrb_ctx_destroy(lrb_ctx *c)
                    &c->q_rs, &c->q_re, &c->q_rev, &c->q_beg, &c->q_n, &c->e_s, &c->e_e, &c->e_f, &c->u_cls, &c->u_ref, &c->u_nnovel, &c->u_noff, &c->u_mk,
                    &c->u_mu, &c->u_ck, &c->u_cr, &c->u_cu, &c->u_cn, &c->u_known, &c->u_unrecog, &c->u_sub, &c->n_row, &c->n_lo, &c->n_cnt, &c->n_piece,
                    &c->t_row, &c->t_lo, &c->t_cnt, &c->t_piece, &c->h_khi, &c->h_klo, &c->h_min, &c->h_score, &c->y_barcnt, &c->y_barseg, &c->y_genebar,
-                   &c->y_bedcnt, &c->y_bedoff, &c->y_counts, &c->y_nelem, &c->bd_tid, &c->bd_s, &c->bd_e, &c->bd_sc, &c->bd_ty, &c->bd_rv, &c->q_shared, &c->tb_name, &c->tb_piece, &c->tb_ttid, &c->tb_tstart, &c->tb_tend, &c->tb_trev, &c->tb_etid, &c->tb_erev, &c->tb_cov, &c->tb_ref, &c->tb_cnt, &c->tb_off, &c->tb_es, &c->tb_ee,
+                   &c->y_bedcnt, &c->y_bedoff, &c->y_counts, &c->y_nelem, &c->bd_tid, &c->bd_s, &c->bd_e, &c->bd_sc, &c->bd_ty, &c->bd_rv, &c->q_shared, &c->tb_name, &c->tb_piece, &c->tb_ttid, &c->tb_tstart, &c->tb_tend, &c->tb_trev, &c->tb_etid, &c->tb_erev, &c->tb_cov, &c->tb_ref, &c->tb_cnt, &c->tb_off, &c->tb_es, &c->tb_ee, &c->tb_flag,
                    &c->s_read, &c->s_rtid, &c->s_rs, &c->s_re, &c->s_rev, &c->s_beg, &c->s_n, &c->s_key0, &c->s_key1, &c->s_idx0, &c->s_idx1, &c->s_hist,
-                   &c->tile_state, &c->tile_state2, &c->scalars};
+                   &c->tile_state, &c->tile_state2, &c->scalars, &c->kg_pairs};
     for (Buf *b : bufs) b->release();
     for (MergeBufs *m : {&c->mg, &c->mg2}) {
         Buf *w[] = {&m->keys, &m->head, &m->locus_start, &m->locus_cnt, &m->dropped, &m->rep, &m->lstart, &m->evmask, &m->samemask, &m->hard, &m->desc, &m->relsym, &m->w_cand, &m->w_cov, &m->w_tid, &m->w_start, &m->w_end, &m->w_fs,
@@ -361,6 +228,7 @@ void lrb_ctx_destroy(lrb_ctx *c)
                     &m->c_tid, &m->c_start, &m->c_end, &m->c_rev, &m->c_n, &m->c_fs, &m->c_le, &m->c_gbeg, &m->c_hash, &m->c_j0, &m->c_sig};
         for (Buf *b : w) b->release();
     }
+    lrbk::multi_release(c);
     for (PBuf &p : c->p) p.release();
     c->h_scalars.release();
     for (int i = 0; i < 12; ++i) cudaEventDestroy(c->ev[i]);
@@ -670,6 +538,14 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
     uint64_t *T = d_totals(c);
     int64_t cap = up->split_trans ? n + n / 8 + 1024 : n;
     cap = std::max<int64_t>(cap, std::min<int64_t>(c->novel_cap_hint, n + c->ex.n / 2 + 1));
+    // A split piece scans the WHOLE of updated_T in the reference (its tid/start/end are 0: update_gtf.c:148 never stops it), so it
+    // can be absorbed by a chain on another chromosome.  The locus-parallel fold cannot see that; the set kernels probe for the
+    // necessary condition (a junction of a piece that also exists on another chromosome, CNT_XLOCUS) and the fold is then replayed
+    // once more as ONE locus (merge_fold_kernel: the exact back-scan, entry by entry).  With -d > 0 junctions match approximately and
+    // the exact-key probe proves nothing: any surviving piece sends the fold to the replay.
+    const bool detect = up->split_trans != 0, run_sets = up->want_summary || detect;
+    bool single = c->force_single_fold;
+    for (int fold_pass = 0; fold_pass < 2; ++fold_pass) {
     SummaryArgs sa{};
     int64_t n_novel = 0, nu = 0; uint64_t n_elem = 0, n_exon_elem = 0;
     uint32_t cnt16[16];
@@ -684,7 +560,7 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
         la.tile_state = c->tile_state.as<uint64_t>(); la.ticket = d_ticket(c); la.totals = T + T_NOVEL;
         launch_build_lists(la, c->st);
         CK(cudaGetLastError());
-        if (attempt == 0) tick(c, 2);
+        if (attempt == 0 && fold_pass == 0) tick(c, 2);
         if (up->want_summary) {
             // class counts + uniq_* folds over bam_T (update_gtf.c:501-528): the four classes partition the rows; they are
             // folded in ONE pass over all rows, each candidate seeing only the entries of its own class.  Independent of the
@@ -698,13 +574,13 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
             if (side) CK(cudaEventRecord(c->ev_join, c->st2));
         }
         // updated_T = merge fold over novel_T (update_gtf.c:949,956)
-        if ((rc = run_merge_async(c, c->mg, c->novel, cap, T + T_NOVEL, *up, T + T_LOCI, nullptr, nullptr, true))) return rc;
-        if (attempt == 0) tick(c, 3);
-        if (up->want_summary) {
+        if ((rc = run_merge_async(c, c->mg, c->novel, cap, T + T_NOVEL, *up, T + T_LOCI, nullptr, nullptr, true, false, single))) return rc;
+        if (attempt == 0 && fold_pass == 0) tick(c, 3);
+        if (run_sets) {
             // sets over updated_T: element count (sizes the hash table)
             const size_t capn = (size_t)std::max<int64_t>(cap, 1);
             NEED(c->y_barcnt, capn * 16); NEED(c->y_barseg, capn * 16); NEED(c->y_genebar, capn * 8); NEED(c->y_bedcnt, capn * 4); NEED(c->y_bedoff, capn * 4);
-            sa = SummaryArgs{};
+            sa = SummaryArgs{}; sa.sets = up->want_summary ? SUM_ALL : 0;
             sa.rows = rows; sa.ex = c->ex; sa.list = c->novel; sa.n_upd = cap; sa.n_upd_dev = T + T_UPD;
             sa.upd = merged_view(c->mg.o_cand, c->mg.o_cov, c->mg.o_tid, c->mg.o_start, c->mg.o_end, c->mg.o_fs, c->mg.o_le, cap);
             sa.ref = c->u_ref.as<int32_t>(); sa.anno_gene = c->anno.gene;
@@ -741,46 +617,54 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
     }
     if (n == 0) { if ((rc = setup_list(c, c->novel, c->n_row, c->n_lo, c->n_cnt, c->n_piece, 0))) return rc; c->mg.n_out = c->mg.n_loci = 0; tick(c, 2); tick(c, 3); }
     c->novel.n = n_novel; c->novel.cap = std::max<int64_t>(cap, 0);
-    if (c->timing && n) { CK(cudaStreamSynchronize(c->st)); cudaEventElapsedTime(&c->ms[LRB_T_K_FOLD], c->ev[10], c->ev[11]); }
+    if (c->timing && n && fold_pass == 0) { CK(cudaStreamSynchronize(c->st)); cudaEventElapsedTime(&c->ms[LRB_T_K_FOLD], c->ev[10], c->ev[11]); }
 
-    // ---- summary sets (print_trans_summary, update_gtf.c:421-587)
-    if (up->want_summary && n > 0) {
-        int32_t *s = c->summary;
-        const int cnt_idx[4] = {LRB_S_KNOWN_TRANS, LRB_S_NOVEL_RELIABLE, LRB_S_NOVEL_UNRELIABLE, LRB_S_UNRECOG};
-        const int uniq_idx[4] = {LRB_S_UNIQ_KNOWN, LRB_S_UNIQ_RELIABLE, LRB_S_UNIQ_UNRELIABLE, LRB_S_UNIQ_UNRECOG};
+    // ---- summary sets (print_trans_summary, update_gtf.c:421-587) and / or the probe for pieces that meet another chromosome
+    if (!(run_sets && n > 0)) break;
+    int32_t *s = c->summary;
+    const int cnt_idx[4] = {LRB_S_KNOWN_TRANS, LRB_S_NOVEL_RELIABLE, LRB_S_NOVEL_UNRELIABLE, LRB_S_UNRECOG};
+    const int uniq_idx[4] = {LRB_S_UNIQ_KNOWN, LRB_S_UNIQ_RELIABLE, LRB_S_UNIQ_UNRELIABLE, LRB_S_UNIQ_UNRECOG};
+    const int64_t n_known_reads = up->want_summary ? (int64_t)cnt16[12] : 0;
+    sa.n_upd = nu; sa.n_upd_dev = nullptr; sa.upd.n = nu;
+    // distinct table keys: one per exon element, up to two per gene / site / junction element (the tid-0 phase and the
+    // segment phase key them differently), one per known read; the table stays below that bound's next power of two
+    // (load <= 0.8 in the worst case, ~0.4 on the bench shape; the slot index is a multiply-high, so no power of two is needed)
+    const uint64_t worst = 2 * n_elem - std::min(n_exon_elem, n_elem) + (uint64_t)n_known_reads;
+    const uint64_t capn = worst + worst / 4 + 1024;
+    NEED(c->h_khi, capn * sizeof(HashSlot));
+    CK(cudaMemsetAsync(c->h_khi.p, 0xFF, capn * sizeof(HashSlot), c->st));
+    sa.tab.cap = capn; sa.tab.slots = c->h_khi.as<HashSlot>();
+    // BED rows are the first occurrences of the exon set: at most one per counted element
+    const size_t nb = (size_t)std::max<uint64_t>(n_elem, 1);
+    NEED(c->bd_tid, nb * 4); NEED(c->bd_s, nb * 4); NEED(c->bd_e, nb * 4); NEED(c->bd_sc, nb * 4); NEED(c->bd_ty, nb); NEED(c->bd_rv, nb);
+    sa.bed_tid = c->bd_tid.as<int32_t>(); sa.bed_start = c->bd_s.as<int32_t>(); sa.bed_end = c->bd_e.as<int32_t>(); sa.bed_score = c->bd_sc.as<int32_t>();
+    sa.bed_type = c->bd_ty.as<uint8_t>(); sa.bed_rev = c->bd_rv.as<uint8_t>();
+    if (c->want_kg_pairs && up->want_summary) { NEED(c->kg_pairs, (size_t)std::max<int64_t>(n_known_reads, 1) * 8); sa.kg_pairs = c->kg_pairs.as<int2>(); }
+    CK(cudaMemsetAsync(c->y_counts.p, 0, 32, c->st));
+    launch_summary_sets(sa, ca.cls, n, c->tile_state.as<uint64_t>(), (uint32_t *)(c->y_nelem.as<uint8_t>() + 16), T + T_BED, c->st,
+                        c->sum_split ? c->st3 : c->st, c->ev_fork3, c->ev_join3);
+    CK(cudaGetLastError());
+    if (up->want_summary && c->side_stream) CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
+    uint8_t *hp = (uint8_t *)c->h_scalars.p;
+    CK(cudaMemcpyAsync(hp, T + T_BED, 8, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaMemcpyAsync(hp + 64, c->y_counts.p, 48, cudaMemcpyDeviceToHost, c->st));
+    CK(cudaStreamSynchronize(c->st));
+    uint64_t nbed; uint32_t cnt[12];
+    memcpy(&nbed, hp, 8); memcpy(cnt, hp + 64, 48);
+    c->xlocus_seen = detect && (cnt[CNT_XLOCUS] != 0 || (up->ss_dis > 0 && cnt[CNT_PARTIAL] != 0));
+    if (c->xlocus_seen && !single) { single = true; c->n_xlocus_replays++; continue; }       // replay the fold as one locus
+    if (up->want_summary) {
         for (int k = 0; k < 4; ++k) s[cnt_idx[k]] = (int32_t)cnt16[12 + k];
         s[LRB_S_NOVEL_BAM] = s[LRB_S_NOVEL_RELIABLE] + s[LRB_S_NOVEL_UNRELIABLE];
-        sa.n_upd = nu; sa.n_upd_dev = nullptr; sa.upd.n = nu;
-        // distinct table keys: one per exon element, up to two per gene / site / junction element (the tid-0 phase and the
-        // segment phase key them differently), one per known read; the table stays below that bound's next power of two
-        // (load <= 0.8 in the worst case, ~0.4 on the bench shape; the slot index is a multiply-high, so no power of two is needed)
-        const uint64_t worst = 2 * n_elem - std::min(n_exon_elem, n_elem) + (uint64_t)s[LRB_S_KNOWN_TRANS];
-        const uint64_t capn = worst + worst / 4 + 1024;
-        NEED(c->h_khi, capn * sizeof(HashSlot));
-        CK(cudaMemsetAsync(c->h_khi.p, 0xFF, capn * sizeof(HashSlot), c->st));
-        sa.tab.cap = capn; sa.tab.slots = c->h_khi.as<HashSlot>();
-        // BED rows are the first occurrences of the exon set: at most one per counted element
-        const size_t nb = (size_t)std::max<uint64_t>(n_elem, 1);
-        NEED(c->bd_tid, nb * 4); NEED(c->bd_s, nb * 4); NEED(c->bd_e, nb * 4); NEED(c->bd_sc, nb * 4); NEED(c->bd_ty, nb); NEED(c->bd_rv, nb);
-        sa.bed_tid = c->bd_tid.as<int32_t>(); sa.bed_start = c->bd_s.as<int32_t>(); sa.bed_end = c->bd_e.as<int32_t>(); sa.bed_score = c->bd_sc.as<int32_t>();
-        sa.bed_type = c->bd_ty.as<uint8_t>(); sa.bed_rev = c->bd_rv.as<uint8_t>();
-        CK(cudaMemsetAsync(c->y_counts.p, 0, 32, c->st));
-        launch_summary_sets(sa, ca.cls, n, c->tile_state.as<uint64_t>(), (uint32_t *)(c->y_nelem.as<uint8_t>() + 16), T + T_BED, c->st,
-                            c->sum_split ? c->st3 : c->st, c->ev_fork3, c->ev_join3);
-        CK(cudaGetLastError());
-        if (c->side_stream) CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
-        uint8_t *hp = (uint8_t *)c->h_scalars.p;
-        CK(cudaMemcpyAsync(hp, T + T_BED, 8, cudaMemcpyDeviceToHost, c->st));
-        CK(cudaMemcpyAsync(hp + 64, c->y_counts.p, 48, cudaMemcpyDeviceToHost, c->st));
-        CK(cudaStreamSynchronize(c->st));
-        uint64_t nbed; uint32_t cnt[12];
-        memcpy(&nbed, hp, 8); memcpy(cnt, hp + 64, 48);
         for (int k = 0; k < 4; ++k) s[uniq_idx[k]] = (int32_t)cnt[8 + k];
         c->n_bed = nu ? (int64_t)nbed : 0;
-        s[LRB_S_UPD_GENES] = (int32_t)cnt[4]; s[LRB_S_NOVEL_TRANS] = (int32_t)nu; s[LRB_S_NOVEL_PARTIAL] = (int32_t)cnt[6];
-        s[LRB_S_NOVEL_FULL] = (int32_t)nu - (int32_t)cnt[6]; s[LRB_S_NOVEL_EXONS] = (int32_t)cnt[0]; s[LRB_S_NOVEL_SITES] = (int32_t)(cnt[1] + cnt[2]);
-        s[LRB_S_NOVEL_JUNC] = (int32_t)cnt[3]; s[LRB_S_KNOWN_GENES] = (int32_t)cnt[5];
+        s[LRB_S_UPD_GENES] = (int32_t)cnt[CNT_G]; s[LRB_S_NOVEL_TRANS] = (int32_t)nu; s[LRB_S_NOVEL_PARTIAL] = (int32_t)cnt[CNT_PARTIAL];
+        s[LRB_S_NOVEL_FULL] = (int32_t)nu - (int32_t)cnt[CNT_PARTIAL]; s[LRB_S_NOVEL_EXONS] = (int32_t)cnt[CNT_E]; s[LRB_S_NOVEL_SITES] = (int32_t)(cnt[CNT_D] + cnt[CNT_A]);
+        s[LRB_S_NOVEL_JUNC] = (int32_t)cnt[CNT_J]; s[LRB_S_KNOWN_GENES] = (int32_t)cnt[CNT_KG];
+        c->n_kg_pairs = (int64_t)cnt[CNT_KG];
     }
+    break;
+    }   // fold_pass
     tick(c, 4);
     c->have_update = true; c->launches_last = total_launches() - l0;
     if (c->timing) {
@@ -1012,7 +896,7 @@ int lrb_update_fetch(lrb_ctx *c, lrb_update_result *out)
 struct TabArgs {
     DRows rows; DExons ex; DTransList list; DMerged upd; const int32_t *ref; int rows_have_read_idx;
     uint32_t *name_idx; int32_t *piece, *t_tid, *t_start, *t_end, *e_tid, *cov, *ref_out; uint8_t *t_rev, *e_rev; uint32_t *cnt;
-    const uint32_t *off; int32_t *es, *ee;
+    const uint32_t *off; int32_t *es, *ee; uint8_t *fl;
 };
 __global__ void tab_rows_kernel(TabArgs a)
 {
@@ -1036,8 +920,46 @@ __global__ void tab_exons_kernel(TabArgs a)
     for (int j = 0; j < n; ++j) {
         a.es[o + j] = j == 0 ? a.upd.fs[i] : a.ex.es[gb + j];
         a.ee[o + j] = j == n - 1 ? a.upd.le[i] : a.ex.ee[gb + j];
+        if (a.fl) a.fl[o + j] = a.ex.flag[gb + j];
     }
 }
+
+}  // extern "C" (reopened below)
+
+// updated_T as a self-contained table in device memory (c->tb_*): rows + exon offsets + exon pools (+ the exon flag bytes for the
+// gather root of a multi-GPU run).  One host round trip (the exon total).
+int lrbk::build_update_table(lrb_ctx *c, int64_t *n_exon_out, bool with_flags)
+{
+    int rc;
+    const int64_t nu = c->mg.n_out; const size_t k = (size_t)std::max<int64_t>(nu, 1);
+    Buf *b4[] = {&c->tb_name, &c->tb_piece, &c->tb_ttid, &c->tb_tstart, &c->tb_tend, &c->tb_etid, &c->tb_cov, &c->tb_ref, &c->tb_cnt};
+    for (Buf *b : b4) NEED(*b, k * 4);
+    NEED(c->tb_trev, k); NEED(c->tb_erev, k); NEED(c->tb_off, (k + 1) * 4);
+    TabArgs a{};
+    a.rows = *c->cur; a.ex = c->ex; a.list = c->novel; a.ref = c->u_ref.as<int32_t>(); a.rows_have_read_idx = c->have_batch ? 1 : 0;
+    a.upd = merged_view(c->mg.o_cand, c->mg.o_cov, c->mg.o_tid, c->mg.o_start, c->mg.o_end, c->mg.o_fs, c->mg.o_le, nu);
+    a.name_idx = c->tb_name.as<uint32_t>(); a.piece = c->tb_piece.as<int32_t>(); a.t_tid = c->tb_ttid.as<int32_t>(); a.t_start = c->tb_tstart.as<int32_t>();
+    a.t_end = c->tb_tend.as<int32_t>(); a.e_tid = c->tb_etid.as<int32_t>(); a.cov = c->tb_cov.as<int32_t>(); a.ref_out = c->tb_ref.as<int32_t>();
+    a.t_rev = c->tb_trev.as<uint8_t>(); a.e_rev = c->tb_erev.as<uint8_t>(); a.cnt = c->tb_cnt.as<uint32_t>(); a.off = c->tb_off.as<uint32_t>();
+    int64_t ne = 0;
+    if (nu) {
+        if ((rc = ensure_tiles(c, nu))) return rc;
+        tab_rows_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, c->st>>>(a);
+        launch_scan_sum_u32(a.cnt, c->tb_off.as<uint32_t>(), nu, c->tile_state.as<uint64_t>(), d_ticket(c), d_totals(c), c->st);
+        CK(cudaGetLastError());
+        uint64_t t; if ((rc = read_totals(c, &t, 1))) return rc;
+        ne = (int64_t)t;
+        NEED(c->tb_es, (size_t)std::max<int64_t>(ne, 1) * 4); NEED(c->tb_ee, (size_t)std::max<int64_t>(ne, 1) * 4);
+        if (with_flags) NEED(c->tb_flag, (size_t)std::max<int64_t>(ne, 1));
+        a.es = c->tb_es.as<int32_t>(); a.ee = c->tb_ee.as<int32_t>(); a.fl = with_flags ? c->tb_flag.as<uint8_t>() : nullptr;
+        tab_exons_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, c->st>>>(a);
+        CK(cudaGetLastError());
+    }
+    *n_exon_out = ne;
+    return LRB_OK;
+}
+
+extern "C" {
 
 int lrb_update_fetch_table(lrb_ctx *c, lrb_trans_table *tab, lrb_bed_list *bed, int32_t *summary)
 {
@@ -1058,40 +980,19 @@ int lrb_update_fetch_table(lrb_ctx *c, lrb_trans_table *tab, lrb_bed_list *bed, 
         bed->score = c->p[29].as<int32_t>(); bed->type = c->p[30].as<uint8_t>(); bed->is_rev = c->p[31].as<uint8_t>();
     }
     if (tab) {
-        const int64_t nu = c->mg.n_out; const size_t k = (size_t)std::max<int64_t>(nu, 1);
-        Buf *b4[] = {&c->tb_name, &c->tb_piece, &c->tb_ttid, &c->tb_tstart, &c->tb_tend, &c->tb_etid, &c->tb_cov, &c->tb_ref, &c->tb_cnt};
-        for (Buf *b : b4) NEED(*b, k * 4);
-        NEED(c->tb_trev, k); NEED(c->tb_erev, k); NEED(c->tb_off, (k + 1) * 4);
-        TabArgs a{};
-        a.rows = *c->cur; a.ex = c->ex; a.list = c->novel; a.ref = c->u_ref.as<int32_t>(); a.rows_have_read_idx = c->have_batch ? 1 : 0;
-        a.upd = merged_view(c->mg.o_cand, c->mg.o_cov, c->mg.o_tid, c->mg.o_start, c->mg.o_end, c->mg.o_fs, c->mg.o_le, nu);
-        a.name_idx = c->tb_name.as<uint32_t>(); a.piece = c->tb_piece.as<int32_t>(); a.t_tid = c->tb_ttid.as<int32_t>(); a.t_start = c->tb_tstart.as<int32_t>();
-        a.t_end = c->tb_tend.as<int32_t>(); a.e_tid = c->tb_etid.as<int32_t>(); a.cov = c->tb_cov.as<int32_t>(); a.ref_out = c->tb_ref.as<int32_t>();
-        a.t_rev = c->tb_trev.as<uint8_t>(); a.e_rev = c->tb_erev.as<uint8_t>(); a.cnt = c->tb_cnt.as<uint32_t>(); a.off = c->tb_off.as<uint32_t>();
         int64_t ne = 0;
-        if (nu) {
-            if ((rc = ensure_tiles(c, nu))) return rc;
-            tab_rows_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, c->st>>>(a);
-            launch_scan_sum_u32(a.cnt, c->tb_off.as<uint32_t>(), nu, c->tile_state.as<uint64_t>(), d_ticket(c), d_totals(c), c->st);
-            CK(cudaGetLastError());
-            uint64_t t; if ((rc = read_totals(c, &t, 1))) return rc;
-            ne = (int64_t)t;
-            NEED(c->tb_es, (size_t)std::max<int64_t>(ne, 1) * 4); NEED(c->tb_ee, (size_t)std::max<int64_t>(ne, 1) * 4);
-            a.es = c->tb_es.as<int32_t>(); a.ee = c->tb_ee.as<int32_t>();
-            tab_exons_kernel<<<(unsigned)((nu + 255) / 256), 256, 0, c->st>>>(a);
-            CK(cudaGetLastError());
-        }
-        const size_t n = (size_t)nu;
-        if ((rc = d2h(c, c->p[32], a.name_idx, n))) return rc;
-        if ((rc = d2h(c, c->p[33], a.piece, n))) return rc;
-        if ((rc = d2h(c, c->p[34], a.t_tid, n))) return rc;
-        if ((rc = d2h(c, c->p[35], a.t_start, n))) return rc;
-        if ((rc = d2h(c, c->p[36], a.t_end, n))) return rc;
-        if ((rc = d2h(c, c->p[37], a.t_rev, n))) return rc;
-        if ((rc = d2h(c, c->p[38], a.e_tid, n))) return rc;
-        if ((rc = d2h(c, c->p[39], a.e_rev, n))) return rc;
-        if ((rc = d2h(c, c->p[40], a.cov, n))) return rc;
-        if ((rc = d2h(c, c->p[41], a.ref_out, n))) return rc;
+        if ((rc = lrbk::build_update_table(c, &ne, false))) return rc;
+        const int64_t nu = c->mg.n_out; const size_t n = (size_t)nu;
+        if ((rc = d2h(c, c->p[32], c->tb_name.as<uint32_t>(), n))) return rc;
+        if ((rc = d2h(c, c->p[33], c->tb_piece.as<int32_t>(), n))) return rc;
+        if ((rc = d2h(c, c->p[34], c->tb_ttid.as<int32_t>(), n))) return rc;
+        if ((rc = d2h(c, c->p[35], c->tb_tstart.as<int32_t>(), n))) return rc;
+        if ((rc = d2h(c, c->p[36], c->tb_tend.as<int32_t>(), n))) return rc;
+        if ((rc = d2h(c, c->p[37], c->tb_trev.as<uint8_t>(), n))) return rc;
+        if ((rc = d2h(c, c->p[38], c->tb_etid.as<int32_t>(), n))) return rc;
+        if ((rc = d2h(c, c->p[39], c->tb_erev.as<uint8_t>(), n))) return rc;
+        if ((rc = d2h(c, c->p[40], c->tb_cov.as<int32_t>(), n))) return rc;
+        if ((rc = d2h(c, c->p[41], c->tb_ref.as<int32_t>(), n))) return rc;
         NEEDP(c->p[42], (n + 1) * 4);
         if (n) CK(cudaMemcpyAsync(c->p[42].p, c->tb_off.p, n * 4, cudaMemcpyDeviceToHost, c->st));
         if ((rc = d2h(c, c->p[43], c->tb_es.as<int32_t>(), (size_t)ne))) return rc;
@@ -1180,21 +1081,28 @@ void *lrb_host_alloc(size_t bytes) { void *p = nullptr; if (cudaMallocHost(&p, b
 void lrb_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 // ----------------------------------------------------------------------------------------------------- shards
-int lrb_shard_cuts(const int32_t *tid, const int32_t *start, const int32_t *end, int64_t n, int n_shards, int64_t *cuts)
+int lrb_shard_cuts_weighted(const int32_t *tid, const int32_t *start, const int32_t *end, const int64_t *weight, int64_t n, int n_shards, int64_t *cuts)
 {
     if (n_shards <= 0 || !cuts || n < 0) return LRB_E_ARG;
     // a cut is exact where the read starts beyond every earlier end on its chromosome;
-    // take the first such position at or after each ideal boundary k*n/n_shards
+    // take the first such position at or after each ideal boundary (k/n_shards of the total weight)
     cuts[0] = 0; cuts[n_shards] = n;
-    uint64_t run = 0; int k = 1; int64_t want = n_shards > 1 ? n / n_shards : n;
+    __int128 total = 0;
+    if (weight) for (int64_t i = 0; i < n; ++i) total += weight[i]; else total = n;
+    uint64_t run = 0; int k = 1; __int128 acc = 0, want = n_shards > 1 ? total / n_shards : total;
     for (int64_t i = 0; i < n && k < n_shards; ++i) {
         uint64_t ks = ((uint64_t)(uint32_t)(tid[i] + 1) << 32) | (uint32_t)start[i];
-        if (i >= want && i > cuts[k - 1] && ks > run) { cuts[k++] = i; want = (int64_t)((__int128)n * k / n_shards); }
+        if (acc >= want && i > cuts[k - 1] && ks > run) { cuts[k++] = i; want = total * k / n_shards; }
         uint64_t ke = ((uint64_t)(uint32_t)(tid[i] + 1) << 32) | (uint32_t)end[i];
         if (ke > run) run = ke;
+        acc += weight ? weight[i] : 1;
     }
     for (; k < n_shards; ++k) cuts[k] = n;
     return LRB_OK;
+}
+int lrb_shard_cuts(const int32_t *tid, const int32_t *start, const int32_t *end, int64_t n, int n_shards, int64_t *cuts)
+{
+    return lrb_shard_cuts_weighted(tid, start, end, nullptr, n, n_shards, cuts);
 }
 
 }  // extern "C"

@@ -72,7 +72,7 @@ LRB_DEVINL int ent_s(const SummaryArgs &a, const EntryView &e, int j) { return j
 LRB_DEVINL int ent_e(const SummaryArgs &a, const EntryView &e, int j) { return j == e.n - 1 ? e.le : a.ex.ee[e.gbeg + j]; }
 LRB_DEVINL uint64_t pos_of(int64_t i, int j) { return ((uint64_t)i << 20) | (uint32_t)j; }
 
-enum { SET_E = 0, SET_D = 1, SET_A = 2, SET_J = 3, SET_G = 4, SET_KG = 5 };
+enum { SET_E = 0, SET_D = 1, SET_A = 2, SET_J = 3, SET_G = 4, SET_KG = 5, SET_PJ = 6, SET_PJ0 = 7 };
 
 // Every pass below runs SG lanes per updated entry: lane l takes the exons l, l + SG, ... of the entry, so the dependent
 // chain of table operations per thread is one or two elements long instead of the whole exon list (the passes are bound
@@ -94,13 +94,14 @@ __global__ void sum_count_kernel(SummaryArgs a, unsigned long long *n_elems)
     if (i < (a.n_upd_dev ? (int64_t)*a.n_upd_dev : a.n_upd)) {
         EntryView e = load_entry(a, i);
         const uint8_t *f = a.ex.flag + e.gbeg;
-        c = gl == 0 ? 1 : 0;
-        for (int j = gl; j < e.n; j += SG) {
+        c = (gl == 0 && (a.sets & SUM_G)) ? 1 : 0;
+        for (int j = gl; j < e.n && (a.sets & (SUM_E | SUM_DAJ)); j += SG) {
             uint8_t x = f[j];
-            cx += (x & LRB_F_NOVEL_EXON) != 0;
-            if (j < e.n - 1) c += ((x & LRB_F_NOVEL_DON) != 0) + ((x & LRB_F_NOVEL_ACC) != 0) + ((x & LRB_F_NOVEL_JUNC) != 0);
+            if (a.sets & SUM_E) cx += (x & LRB_F_NOVEL_EXON) != 0;
+            if (j < e.n - 1 && (a.sets & SUM_DAJ)) c += ((x & LRB_F_NOVEL_DON) != 0) + ((x & LRB_F_NOVEL_ACC) != 0) + ((x & LRB_F_NOVEL_JUNC) != 0);
         }
         c += cx;
+        if (e.piece >= 0 && gl == 0) c += e.n;      // the junction keys of a split piece (cross-chromosome probe of phase 1 / 2)
     }
     for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(FULL, c, o); cx += __shfl_xor_sync(FULL, cx, o); }
     if (lane_id() == 0 && c) { atomicAdd(n_elems, (unsigned long long)c); if (cx) atomicAdd(n_elems + 1, (unsigned long long)cx); }
@@ -139,22 +140,43 @@ __global__ void sum_exon_count_kernel(SummaryArgs a)
     if (ce) atomicAdd(&a.counts[SET_E], (uint32_t)ce);
 }
 
+LRB_DEVINL int shard_of(const int64_t *shard_end, int n_shards, int64_t i) { int k = 0; while (k < n_shards - 1 && i >= shard_end[k]) ++k; return k; }
+// what must differ between a split piece and an entry with an equal junction for the pair to be a cross-locus meeting: the chromosome,
+// or (gather root of a multi-GPU run, where the shards have settled the meetings inside themselves) the shard
+LRB_DEVINL int xl_group(const SummaryArgs &a, const EntryView &e, int64_t i) { return a.n_shards > 0 ? shard_of(a.shard_end, a.n_shards, i) : e.real_tid; }
+
 // phase 1: exons (all entries), tid-0 elements of D/A/J, every gene element (gene equality ignores tid)
 __global__ void sum_phase1_kernel(SummaryArgs a, int parts)
 {
     SUM_ENTRY_PROLOGUE(a.n_upd)
     EntryView e = load_entry(a, i);
     const uint8_t *f = a.ex.flag + e.gbeg;
-    if (gl == 0) tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_G, SEG_TID0, 0), key_lo(e.gene, 0)), pos_of(i, 0));
-    if (!(parts & 1) && e.t_tid != 0) return;
+    if (gl == 0 && (a.sets & SUM_G)) tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_G, SEG_TID0, 0), key_lo(e.gene, 0)), pos_of(i, 0));
+    if (e.piece >= 0 && gl == 0) {
+        // a split piece scans the WHOLE of updated_T in the reference (its tid/start/end are 0, update_gtf.c:148 never stops it), so
+        // it can meet an equal or partially matching chain on another chromosome.  Its junctions go into the table here and
+        // phase 2 lets every entry probe them: a hit across chromosomes raises CNT_XLOCUS and the fold is replayed as one locus.
+        atomicAdd(&a.counts[CNT_PARTIAL], 1u);       // partial-read transcripts
+        const int grp = xl_group(a, e, i);
+        for (int j = 0; j < e.n - 1; ++j) {
+            const uint64_t s = tab_upsert(a.tab, key_hi(SET_PJ, 0, 0), key_lo(ent_e(a, e, j), ent_s(a, e, j + 1)));
+            atomicMin((unsigned long long *)&a.tab.slots[s].minpos, (unsigned long long)(uint32_t)grp); atomicMax(&a.tab.slots[s].pad, grp);
+            if (j == 0) {
+                const uint64_t s0 = tab_upsert(a.tab, key_hi(SET_PJ0, 0, 0), key_lo(ent_e(a, e, 0), ent_s(a, e, 1)));
+                atomicMin((unsigned long long *)&a.tab.slots[s0].minpos, (unsigned long long)(uint32_t)grp); atomicMax(&a.tab.slots[s0].pad, grp);
+            }
+        }
+    }
+    const bool do_e = (parts & 1) && (a.sets & SUM_E), do_t0 = e.t_tid == 0 && (a.sets & SUM_DAJ);
+    if (!do_e && !do_t0) return;
     for (int j = gl; j < e.n; j += SG) {
         uint8_t x = f[j];
-        if ((parts & 1) && (x & LRB_F_NOVEL_EXON)) {
+        if (do_e && (x & LRB_F_NOVEL_EXON)) {
             uint64_t s = tab_upsert(a.tab, key_hi(SET_E, 0, e.real_tid), key_lo(ent_s(a, e, j), ent_e(a, e, j)));
             tab_min(a.tab, s, pos_of(i, j));
             atomicAdd(&a.tab.slots[s].score, e.cov);
         }
-        if (e.t_tid == 0 && j < e.n - 1) {
+        if (do_t0 && j < e.n - 1) {
             if (x & LRB_F_NOVEL_DON) tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_D, SEG_TID0, 0), key_lo(ent_e(a, e, j), 0)), pos_of(i, j));
             if (x & LRB_F_NOVEL_ACC) tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_A, SEG_TID0, 0), key_lo(ent_s(a, e, j + 1), 0)), pos_of(i, j));
             if (x & LRB_F_NOVEL_JUNC) tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_J, SEG_TID0, 0), key_lo(ent_e(a, e, j), ent_s(a, e, j + 1))), pos_of(i, j));
@@ -169,17 +191,31 @@ __global__ void sum_phase2_kernel(SummaryArgs a, int parts)
     EntryView e = load_entry(a, i);
     const uint8_t *f = a.ex.flag + e.gbeg;
     int cd = 0, ca = 0, cj = 0, cg = 0, ce = 0;
-    if (e.t_tid == 0 && gl == 0) {
+    if (e.t_tid == 0 && gl == 0 && (a.sets & SUM_G)) {
         uint64_t s = tab_find(a.tab, key_hi(SET_G, SEG_TID0, 0), key_lo(e.gene, 0));
         cg = a.tab.slots[s].minpos == pos_of(i, 0);
     }
-    for (int j = gl; j < e.n && ((parts & 1) || e.t_tid == 0); j += SG) {
+    if (gl == 0 && e.n > 1 && a.counts[CNT_PARTIAL] != 0) {
+        // cross-chromosome meeting of a split piece (see phase 1): the first junction of this entry among the junctions of a
+        // piece, or a junction of this entry equal to the first junction of a piece -- the necessary condition of check_iden != -1
+        bool hit = false;
+        const int grp = xl_group(a, e, i);
+        uint64_t s = tab_find(a.tab, key_hi(SET_PJ, 0, 0), key_lo(ent_e(a, e, 0), ent_s(a, e, 1)));
+        if (s != EMPTY) hit = (int)(uint32_t)a.tab.slots[s].minpos != grp || a.tab.slots[s].pad != grp;
+        for (int j = 0; j < e.n - 1 && !hit; ++j) {
+            s = tab_find(a.tab, key_hi(SET_PJ0, 0, 0), key_lo(ent_e(a, e, j), ent_s(a, e, j + 1)));
+            if (s != EMPTY) hit = (int)(uint32_t)a.tab.slots[s].minpos != grp || a.tab.slots[s].pad != grp;
+        }
+        if (hit) a.counts[CNT_XLOCUS] = 1u;
+    }
+    const bool do_e = (parts & 1) && (a.sets & SUM_E), do_t0 = e.t_tid == 0 && (a.sets & SUM_DAJ);
+    for (int j = gl; j < e.n && (do_e || do_t0); j += SG) {
         uint8_t x = f[j];
-        if ((parts & 1) && (x & LRB_F_NOVEL_EXON)) {
+        if (do_e && (x & LRB_F_NOVEL_EXON)) {
             uint64_t s = tab_find(a.tab, key_hi(SET_E, 0, e.real_tid), key_lo(ent_s(a, e, j), ent_e(a, e, j)));
             ce += a.tab.slots[s].minpos == pos_of(i, j);
         }
-        if (e.t_tid == 0 && j < e.n - 1) {
+        if (do_t0 && j < e.n - 1) {
             if (x & LRB_F_NOVEL_DON) cd += a.tab.slots[tab_find(a.tab, key_hi(SET_D, SEG_TID0, 0), key_lo(ent_e(a, e, j), 0))].minpos == pos_of(i, j);
             if (x & LRB_F_NOVEL_ACC) ca += a.tab.slots[tab_find(a.tab, key_hi(SET_A, SEG_TID0, 0), key_lo(ent_s(a, e, j + 1), 0))].minpos == pos_of(i, j);
             if (x & LRB_F_NOVEL_JUNC) cj += a.tab.slots[tab_find(a.tab, key_hi(SET_J, SEG_TID0, 0), key_lo(ent_e(a, e, j), ent_s(a, e, j + 1)))].minpos == pos_of(i, j);
@@ -198,7 +234,6 @@ __global__ void sum_phase2_kernel(SummaryArgs a, int parts)
         if (cg) atomicAdd(&a.counts[SET_G], (uint32_t)cg);
     }
     if (ce) atomicAdd(&a.counts[SET_E], (uint32_t)ce);
-    if (e.piece >= 0) atomicAdd(&a.counts[6], 1u);   // partial-read transcripts
 }
 
 // phase 3: tid>0 elements go into their segment
@@ -209,7 +244,8 @@ __global__ void sum_phase3_kernel(SummaryArgs a)
     if (e.t_tid == 0) return;
     const uint8_t *f = a.ex.flag + e.gbeg;
     const uint32_t sd = a.bar_seg[0 * a.n_upd + i], sa = a.bar_seg[1 * a.n_upd + i], sj = a.bar_seg[2 * a.n_upd + i], sg = a.bar_seg[3 * a.n_upd + i];
-    if (gl == 0) tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_G, sg, e.t_tid), key_lo(e.gene, 0)), pos_of(i, 0));
+    if (gl == 0 && (a.sets & SUM_G)) tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_G, sg, e.t_tid), key_lo(e.gene, 0)), pos_of(i, 0));
+    if (!(a.sets & SUM_DAJ)) return;
     for (int j = gl; j < e.n - 1; j += SG) {
         uint8_t x = f[j];
         if (x & LRB_F_NOVEL_DON) tab_min(a.tab, tab_upsert(a.tab, key_hi(SET_D, sd, e.t_tid), key_lo(ent_e(a, e, j), 0)), pos_of(i, j));
@@ -225,7 +261,7 @@ __global__ void sum_phase4_kernel(SummaryArgs a)
     const uint8_t *f = a.ex.flag + e.gbeg;
     const uint32_t sd = a.bar_seg[0 * a.n_upd + i], sa = a.bar_seg[1 * a.n_upd + i], sj = a.bar_seg[2 * a.n_upd + i], sg = a.bar_seg[3 * a.n_upd + i];
     int cd = 0, ca = 0, cj = 0, cg = 0;
-    if (gl == 0) {
+    if (gl == 0 && (a.sets & SUM_G)) {
         uint64_t s = tab_find(a.tab, key_hi(SET_G, sg, e.t_tid), key_lo(e.gene, 0));
         bool first = a.tab.slots[s].minpos == pos_of(i, 0);
         uint64_t bar = a.gene_bar[i];                // index+1 of the last inserted tid-0 gene entry before i (inclusive scan, own value 0)
@@ -235,7 +271,7 @@ __global__ void sum_phase4_kernel(SummaryArgs a)
         }
         cg = first;
     }
-    for (int j = gl; j < e.n - 1; j += SG) {
+    for (int j = gl; j < e.n - 1 && (a.sets & SUM_DAJ); j += SG) {
         uint8_t x = f[j];
         if (x & LRB_F_NOVEL_DON) cd += a.tab.slots[tab_find(a.tab, key_hi(SET_D, sd, e.t_tid), key_lo(ent_e(a, e, j), 0))].minpos == pos_of(i, j);
         if (x & LRB_F_NOVEL_ACC) ca += a.tab.slots[tab_find(a.tab, key_hi(SET_A, sa, e.t_tid), key_lo(ent_s(a, e, j + 1), 0))].minpos == pos_of(i, j);
@@ -333,7 +369,64 @@ __global__ void sum_known_genes_kernel(SummaryArgs a, const uint32_t *__restrict
     int ref = a.ref[r]; int gene = ref >= 0 ? a.anno_gene[ref] : -1;
     uint64_t hi = key_hi(SET_KG, 0, a.rows.tid[r]), lo = key_lo(gene, 0);
     if (pass == 0) tab_min(a.tab, tab_upsert(a.tab, hi, lo), (uint64_t)r);
-    else if (a.tab.slots[tab_find(a.tab, hi, lo)].minpos == (uint64_t)r) atomicAdd(&a.counts[SET_KG], 1u);
+    else if (a.tab.slots[tab_find(a.tab, hi, lo)].minpos == (uint64_t)r) {
+        const uint32_t k = atomicAdd(&a.counts[SET_KG], 1u);
+        if (a.kg_pairs) a.kg_pairs[k] = make_int2(a.rows.tid[r], gene);       // for the union across shards (order is irrelevant)
+    }
+}
+
+// ---- helpers of the gather root (lrb_multi.cu)
+__global__ void table_view_kernel(GatheredTable t, uint32_t *ident, uint32_t *zeros, uint32_t *cnt, int32_t *fs, int32_t *le)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= t.n) return;
+    const uint32_t lo = t.exon_off[i], hi = t.exon_off[i + 1];
+    ident[i] = (uint32_t)i; zeros[i] = 0; cnt[i] = hi - lo; fs[i] = t.es[lo]; le[i] = t.ee[hi - 1];
+}
+void launch_table_view(const GatheredTable &t, uint32_t *ident, uint32_t *zeros, uint32_t *cnt, int32_t *fs, int32_t *le, cudaStream_t st)
+{
+    if (t.n <= 0) return;
+    table_view_kernel<<<(unsigned)((t.n + 255) / 256), 256, 0, st>>>(t, ident, zeros, cnt, fs, le); LRB_COUNT_LAUNCH();
+}
+
+// pass 0: every tid-0 site / junction element leaves the lowest and the highest shard that holds its key; pass 1: a key seen in two shards
+__global__ void tid0_coincidence_kernel(SummaryArgs a, int pass, uint32_t *flag)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_upd) return;
+    EntryView e = load_entry(a, i);
+    if (e.t_tid != 0) return;
+    const int sh = shard_of(a.shard_end, a.n_shards, i);
+    const uint8_t *f = a.ex.flag + e.gbeg;
+    for (int j = 0; j < e.n - 1; ++j) {
+        const uint8_t x = f[j];
+        for (int q = 0; q < 3; ++q) {
+            if (!(x & (LRB_F_NOVEL_DON << q))) continue;
+            const uint64_t hi = key_hi(SET_D + q, SEG_TID0, 0);
+            const uint64_t lo = q == 0 ? key_lo(ent_e(a, e, j), 0) : q == 1 ? key_lo(ent_s(a, e, j + 1), 0) : key_lo(ent_e(a, e, j), ent_s(a, e, j + 1));
+            if (pass == 0) { const uint64_t s = tab_upsert(a.tab, hi, lo); atomicMin((unsigned long long *)&a.tab.slots[s].minpos, (unsigned long long)sh); atomicMax(&a.tab.slots[s].pad, sh); }
+            else { const uint64_t s = tab_find(a.tab, hi, lo); if ((int)a.tab.slots[s].minpos != a.tab.slots[s].pad) *flag = 1u; }
+        }
+    }
+}
+void launch_tid0_coincidence(const SummaryArgs &a, uint32_t *flag, cudaStream_t st)
+{
+    if (a.n_upd <= 0 || a.n_shards <= 1) return;
+    for (int pass = 0; pass < 2; ++pass) { tid0_coincidence_kernel<<<(unsigned)((a.n_upd + 255) / 256), 256, 0, st>>>(a, pass, flag); LRB_COUNT_LAUNCH(); }
+}
+
+__global__ void pairs_distinct_kernel(HashTab tab, const int2 *__restrict__ pairs, int64_t n, int pass, uint32_t *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t hi = key_hi(SET_KG, 0, pairs[i].x), lo = key_lo(pairs[i].y, 0);
+    if (pass == 0) tab_min(tab, tab_upsert(tab, hi, lo), (uint64_t)i);
+    else if (tab.slots[tab_find(tab, hi, lo)].minpos == (uint64_t)i) atomicAdd(out, 1u);
+}
+void launch_pairs_distinct(const HashTab &tab, const int2 *pairs, int64_t n, uint32_t *out, cudaStream_t st)
+{
+    if (n <= 0) return;
+    for (int pass = 0; pass < 2; ++pass) { pairs_distinct_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tab, pairs, n, pass, out); LRB_COUNT_LAUNCH(); }
 }
 
 static inline unsigned nblk(int64_t n) { return (unsigned)((n + 255) / 256); }
@@ -349,7 +442,7 @@ void launch_summary_count(const SummaryArgs &a, unsigned long long *n_elems, cud
 void launch_summary_sets(const SummaryArgs &a, const uint32_t *cls, int64_t n_rows, uint64_t *tile_state, uint32_t *tickets, uint64_t *bed_total,
                          cudaStream_t st, cudaStream_t st_exon, cudaEvent_t ev_fork, cudaEvent_t ev_join)
 {
-    const bool split = st_exon != st && a.n_upd > 0;
+    const bool split = st_exon != st && a.n_upd > 0 && (a.sets & SUM_E);
     const int n_tiles = (int)((a.n_upd + MS_THREADS * MS_ITEMS - 1) / (MS_THREADS * MS_ITEMS));
     if (a.n_upd > 0) { cudaMemsetAsync(tile_state, 0, (size_t)n_tiles * 6 * 8, st); cudaMemsetAsync(tickets, 0, 6 * 4, st); }
     if (split) {
@@ -361,17 +454,21 @@ void launch_summary_sets(const SummaryArgs &a, const uint32_t *cls, int64_t n_ro
         cudaEventRecord(ev_join, st_exon);
     }
     const int parts = split ? 0 : 1;
-    if (n_rows > 0) { sum_known_genes_kernel<<<nblk(n_rows), 256, 0, st>>>(a, cls, n_rows, 0); LRB_COUNT_LAUNCH(); }
+    const bool kg = n_rows > 0 && (a.sets & SUM_KG), segs = (a.sets & (SUM_G | SUM_DAJ)) != 0;
+    if (kg) { sum_known_genes_kernel<<<nblk(n_rows), 256, 0, st>>>(a, cls, n_rows, 0); LRB_COUNT_LAUNCH(); }
     if (a.n_upd > 0) {
         sum_phase1_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a, parts); LRB_COUNT_LAUNCH();
         sum_phase2_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a, parts); LRB_COUNT_LAUNCH();
-        sum_scans_kernel<<<dim3((unsigned)n_tiles, split ? 5 : 6), MS_THREADS, 0, st>>>(a, tile_state, tickets, n_tiles, bed_total, 0); LRB_COUNT_LAUNCH();
-        sum_phase3_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
-        sum_phase4_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
-    } else cudaMemsetAsync(bed_total, 0, 8, st);
-    if (n_rows > 0) { sum_known_genes_kernel<<<nblk(n_rows), 256, 0, st>>>(a, cls, n_rows, 1); LRB_COUNT_LAUNCH(); }
+        if (segs || (!split && (a.sets & SUM_E))) { sum_scans_kernel<<<dim3((unsigned)n_tiles, split ? 5 : 6), MS_THREADS, 0, st>>>(a, tile_state, tickets, n_tiles, bed_total, 0); LRB_COUNT_LAUNCH(); }
+        if (segs) {
+            sum_phase3_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
+            sum_phase4_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();
+        }
+    }
+    if (a.n_upd <= 0 || !(a.sets & SUM_E)) cudaMemsetAsync(bed_total, 0, 8, st);
+    if (kg) { sum_known_genes_kernel<<<nblk(n_rows), 256, 0, st>>>(a, cls, n_rows, 1); LRB_COUNT_LAUNCH(); }
     if (split) cudaStreamWaitEvent(st, ev_join, 0);
-    else if (a.n_upd > 0) { sum_bed_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH(); }
+    else if (a.n_upd > 0 && (a.sets & SUM_E)) { sum_bed_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH(); }
 }
 
 }  // namespace lrbk

@@ -385,6 +385,58 @@ def make_sj(reads_soa_exons, frac: float = 0.7, seed: int = 5):
                 uniq_c=uniq.astype(np.int32), multi_c=multi.astype(np.int32))
 
 
+def read_junctions(reads: Reads, min_intron: int = 3):
+    """(tid, don, acc) of every N op of at least min_intron bases, STAR's SJ.out.tab convention (first / last intron base, 1-based):
+    what bam2gtf's cuts leave as exon[j].end + 1 / exon[j+1].start - 1, up to its rare corner cases (vanishing short exons, D cuts)."""
+    off = reads.cigar_off.astype(np.int64)
+    cig = reads.cigar
+    op = cig & np.uint32(15); ln = (cig >> np.uint32(4)).astype(np.int64)
+    consume = np.where((op == M) | (op == D) | (op == N) | (op == EQ) | (op == X), ln, 0)
+    cs = np.zeros(len(cig) + 1, np.int64); np.cumsum(consume, out=cs[1:])
+    rid = np.repeat(np.arange(reads.n), np.diff(off))
+    before = cs[:-1] - cs[off[:-1]][rid]                      # reference bases consumed by the read's earlier ops
+    j = np.nonzero((op == N) & (ln >= min_intron))[0]
+    don = reads.pos[rid[j]].astype(np.int64) + before[j] + 1
+    return reads.tid[rid[j]].astype(np.int64), don, don + ln[j] - 1
+
+
+def make_sj_from_reads(reads: Reads, frac: float = 0.7, seed: int = 5, min_intron: int = 3):
+    """SJ.out.tab rows: `frac` of the distinct read-derived junctions with uniq U[0,5], multi U[0,2], sorted by (tid, don, acc)."""
+    rng = np.random.default_rng(seed)
+    t, d, a = read_junctions(reads, min_intron)
+    key = np.unique((t << 52) | (d << 26) | a) if len(t) and d.max() < (1 << 26) and a.max() < (1 << 26) else None
+    if key is not None:
+        kt, kd, ka = key >> 52, (key >> 26) & ((1 << 26) - 1), key & ((1 << 26) - 1)
+    else:
+        k3 = np.unique(np.stack([t, d, a], 1), axis=0) if len(t) else np.zeros((0, 3), np.int64)
+        kt, kd, ka = k3[:, 0], k3[:, 1], k3[:, 2]
+    keepm = rng.random(len(kt)) < frac
+    kt, kd, ka = kt[keepm], kd[keepm], ka[keepm]
+    return dict(tid=kt.astype(np.int32), don=kd.astype(np.int32), acc=ka.astype(np.int32),
+                uniq_c=rng.integers(0, 6, len(kt)).astype(np.int32), multi_c=rng.integers(0, 3, len(kt)).astype(np.int32))
+
+
+def clone_chromosome(anno_soa: dict, reads: Reads, sj: dict, n_chrom: int):
+    """The same annotation / reads / junctions once more on `n_chrom` further chromosomes (tid + n_chrom) at the SAME coordinates, with
+    gene ids of their own: split pieces of the copy meet equal chains on the original chromosome (the cross-locus case)."""
+    a = dict(anno_soa)
+    ng = int(a["gene"].max()) + 1 if len(a["gene"]) else 0
+    a2 = {k: np.concatenate([a[k], a[k]]) for k in ("start", "end", "is_rev", "exon_start", "exon_end")}
+    a2["tid"] = np.concatenate([a["tid"], a["tid"] + n_chrom]).astype(np.int32)
+    a2["gene"] = np.concatenate([a["gene"], a["gene"] + ng]).astype(np.int32)
+    off = a["exon_off"].astype(np.int64)
+    a2["exon_off"] = np.concatenate([off[:-1], off + off[-1]]).astype(np.uint32)
+    r2 = reads.take(np.arange(reads.n))
+    r2.tid = (r2.tid + n_chrom).astype(np.int32)
+    r2.qid = r2.qid + (int(reads.qid.max()) + 1 if reads.n else 0)
+    r2.qname_hash = splitmix64(r2.qid)
+    both = _concat(reads, r2)
+    both.chrom_names = [f"chr{i + 1}" for i in range(2 * n_chrom)]; both.chrom_lens = list(reads.chrom_lens[:n_chrom]) * 2 if reads.chrom_lens else None
+    s2 = {k: np.concatenate([sj[k], sj[k]]) for k in ("don", "acc", "uniq_c", "multi_c")}
+    s2["tid"] = np.concatenate([sj["tid"], sj["tid"] + n_chrom]).astype(np.int32)
+    return a2, both, s2
+
+
 # ----------------------------------------------------------------------------- text renderers (reference inputs)
 
 def cigar_string(words) -> str:

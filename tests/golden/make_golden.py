@@ -128,6 +128,16 @@ c7 = HDR + rec("r2", 16, 1139100, "241M1409N123M892N50M", 0) + rec("r3", 0, 1139
 case("c7_barrier", {"in.sam": c7, "anno.gtf": "@TOY", "sj1.tab": "chr1\t1139341\t1140749\t2\t2\t0\t3\t0\t40\n"},
      {"nosplit": f"update-gtf -l 3 -J 1 -j sj1.tab in.sam anno.gtf {ALLOUT}", "split": f"update-gtf -s -l 3 -J 1 -j sj1.tab in.sam anno.gtf {ALLOUT}"})
 
+# ---- C.8 a split piece meets an equal chain on ANOTHER chromosome (Q14.2: a piece's back-scan never stops, update_gtf.c:148)
+c8h = "@HD\tVN:1.0\tSO:coordinate\n@SQ\tSN:chr1\tLN:1153837\n@SQ\tSN:chr2\tLN:1153837\n"
+c8 = c8h
+for ch, sfx in (("chr1", ""), ("chr2", "x")):
+    c8 += rec("r2" + sfx, 16, 1139100, "241M1409N123M892N50M", 0, chrom=ch) + rec("r3" + sfx, 0, 1139200, "141M438N88M883N100M10D23M892N60M", 0, chrom=ch) + \
+        rec("r2b" + sfx, 16, 1139250, "91M1409N123M892N50M", 0, chrom=ch)
+case("c8_xlocus", {"in.sam": c8, "anno.gtf": "@TOY_TWO_CHROM", "sj.tab": "chr1\t1139341\t1140749\t2\t2\t0\t3\t0\t40\nchr2\t1139341\t1140749\t2\t2\t0\t3\t0\t40\n"},
+     {"split": f"update-gtf -s -l 3 -J 1 -j sj.tab in.sam anno.gtf {ALLOUT}", "nosplit": f"update-gtf -l 3 -J 1 -j sj.tab in.sam anno.gtf {ALLOUT}",
+      "split_noy": "update-gtf -s -l 3 -J 1 -j sj.tab in.sam anno.gtf -o updated.gtf", "split_d": f"update-gtf -s -d 2 -l 3 -J 1 -j sj.tab in.sam anno.gtf {SMALLOUT}"})
+
 
 def add_synthetic():
     import numpy as np
@@ -176,6 +186,10 @@ def main():
             for fn, content in files.items():
                 if content == "@TOY": content = toy
                 elif content == "@RRNA": content = rrna
+                elif content == "@TOY_TWO_CHROM":      # the toy annotation twice: chr1 and a chr2 copy at the same coordinates with its own ids
+                    import re
+                    content = toy + "".join(re.sub(r'(gene_id|transcript_id) "([^"]+)"', r'\1 "\2_B"', ln).replace("chr1\t", "chr2\t", 1)
+                                            for ln in toy.splitlines(True) if ln.startswith("chr1\t"))
                 elif content.startswith("@TOY_PREPEND:"): content = content[len("@TOY_PREPEND:"):] + toy
                 open(os.path.join(d, fn), "w").write(content)
         manifest[name] = {}

@@ -1,5 +1,6 @@
 """GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs --
 bit-exact on every output array -- plus size-independent properties (shard invariance, fused == unfused, idempotence)."""
+import os
 import numpy as np
 import pytest
 
@@ -451,3 +452,44 @@ def test_cli_sort_input(data, tmp_path):
         assert filecmp.cmp(tmp_path / f"ref.{fn}", tmp_path / f"few.{fn}", shallow=False), fn
     p = subprocess.run([api.CLI_PATH, "update-gtf", "-l", "3", str(tmp_path / "f.bam"), str(tmp_path / "anno.gtf")], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
     assert p.returncode != 0                                       # without the knob the unsorted BAM is refused, as documented
+
+
+@pytest.mark.gpu
+def test_single_locus_replay_equals_locus_fold(tmp_path):
+    """The one-locus replay of the updated_T fold (what a split piece meeting another chromosome falls back to) gives the
+    same tables as the locus-parallel fold on data without such a meeting: run the CLI with and without LRB_FORCE_SINGLE_FOLD."""
+    import subprocess
+    from lr2rmats_b200 import api
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "syn_iso")
+    outs = []
+    for force in ("0", "1"):
+        o = tmp_path / f"f{force}"; o.mkdir()
+        env = dict(os.environ, LRB_FORCE_SINGLE_FOLD=force)
+        p = subprocess.run([api.CLI_PATH, "update-gtf", "-s", "-l", "3", "-J", "1", "-j", os.path.join(d, "sj.tab"), os.path.join(d, "in.sam"), os.path.join(d, "anno.gtf"),
+                            "-y", "summary.txt", "-E", "bed.bed", "-o", "updated.gtf"], cwd=o, env=env, stderr=subprocess.PIPE)
+        assert p.returncode == 0, p.stderr.decode()[-1000:]
+        outs.append({f: open(o / f, "rb").read() for f in ("summary.txt", "bed.bed", "updated.gtf")})
+    assert outs[0] == outs[1]
+
+
+@pytest.mark.parametrize("summary", [1, 0])
+def test_cross_chromosome_piece_replay(ctx, summary):
+    """Every read twice, on chromosomes 1-2 and on clones of them at the same coordinates: the split pieces of the clones meet equal
+    chains on the originals, which the reference merges across chromosomes (a piece's back-scan never stops, update_gtf.c:148; golden
+    c8_xlocus).  The set kernels must notice and the fold must be replayed as one locus: every table equals the port's."""
+    anno = synth.make_annotation(1500, n_chrom=2, seed=41)
+    reads = synth.make_reads(anno, 12_000, seed=43, reject_frac=0.0)
+    sj = synth.make_sj_from_reads(reads, frac=0.7, seed=44)
+    a2, both, s2 = synth.clone_chromosome(anno.soa(), reads, sj, 2)
+    ep = cabi.ExonParams.default()
+    up = cabi.UpdateParams.default(full_level=3, split_trans=1, min_sj_cnt=1, want_summary=summary)
+    oex = op.bam2gtf(both.soa(), ep)
+    rc, ou = op.update(oex, a2, s2, up)
+    assert rc == 0
+    ctx.set_anno(a2); ctx.set_sj(s2)
+    gu = ctx.update_gtf(both.soa(), ep, up)
+    ou["ex"]["read_idx"] = gu["ex"]["read_idx"]
+    assert_dict_equal(gu, ou)
+    # the case is live: at least one piece of a clone chromosome was absorbed by an original (cov > 1 on a piece)
+    upd = gu["updated"]; piece = gu["novel"]["piece"][upd["cand"]]
+    assert ((piece >= 0) & (upd["cov"] > 1)).sum() > 0

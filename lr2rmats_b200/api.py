@@ -215,6 +215,7 @@ class Context:
 
     # ---- multi-GPU (one process per GPU; see lr2rmats_b200/multi.py for the driver)
     def comm_init(self, comm_id: bytes, rank: int, n_ranks: int):
+        _prefer_bundled_nccl()
         self._comm_id = C.create_string_buffer(bytes(comm_id), COMM_ID_BYTES)
         self._ck(self.L.lrb_comm_init(self.h, self._comm_id, rank, n_ranks))
 
@@ -261,8 +262,27 @@ class Context:
 COMM_ID_BYTES = 128
 
 
+def _prefer_bundled_nccl():
+    """The library binds NCCL at run time (dlopen of libnccl.so.2).  In a Python process that also imports torch, both must end up
+    on the SAME copy: torch's own (site-packages/nvidia/nccl) is newer than the system one, and the dynamic loader reuses whichever
+    libnccl.so.2 came first for everybody.  Point the library at torch's copy unless the caller chose one (LRB_NCCL_LIB)."""
+    if os.environ.get("LRB_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.isfile(cand):
+                os.environ["LRB_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
 def comm_id() -> bytes:
     """ncclGetUniqueId through the library: call on ONE rank and ship the bytes to the others."""
+    _prefer_bundled_nccl()
     L = load_library()
     buf = C.create_string_buffer(COMM_ID_BYTES)
     rc = L.lrb_comm_id(buf)

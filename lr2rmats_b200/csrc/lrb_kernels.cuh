@@ -138,7 +138,8 @@ struct MergeArgs {
     uint8_t *dropped;                               // per candidate: absorbed/dropped by the fold
     uint32_t *rep, *lstart; uint64_t *evmask;       // flat fold: class representative, locus head, absorber mask per candidate
     uint16_t *desc; uint64_t *relsym;               // flat fold: class descriptor per candidate; per representative the related representatives
-    uint8_t *hard;                                  // flat fold: per locus head, 1 = leave to merge_fold_kernel
+    uint8_t *hard;                                  // per locus head: 1 = not for the flat kernels, >= 2 = not for fold_big_kernel either (merge_fold_kernel)
+    uint64_t *ckey; uint32_t *cmin;                 // class table of the big loci: 2 * n_cand + 64 slots (NULL: big loci go to merge_fold_kernel)
     DMerged out;                                    // compacted result
     uint64_t *tile_state; uint32_t *ticket; uint64_t *totals;  // [0] n_loci, [1] n_out
 };

@@ -43,7 +43,7 @@ static NcclApi *nccl_api(std::string *err)
     if (!tried) {
         tried = true;
         const char *names[] = {getenv("LRB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
-        for (const char *nm : names) { if (nm && *nm && (api.h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break; }
+        for (const char *nm : names) { if (nm && *nm && (api.h = dlopen(nm, RTLD_NOW | RTLD_LOCAL))) break; }
         if (!api.h) why = std::string("libnccl.so.2 not found (") + (dlerror() ? dlerror() : "dlopen failed") + "); set LRB_NCCL_LIB";
         else {
 #define LRB_SYM(field, name) do { *(void **)&api.field = dlsym(api.h, name); if (!api.field) why = std::string("NCCL symbol missing: ") + name; } while (0)

@@ -809,7 +809,7 @@ LRB_DEVINL int chain_iden(const DExons &ex, const Entry &t1, const Entry &t2, in
 static constexpr int MF_THREADS = 128;
 // G lanes per locus; tlist[ls + k] = candidate index of the k-th entry of the locus' T; mutable entry data lives at work[cand]
 template <int G>
-__global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uint32_t *tlist, uint8_t *alive, const uint8_t *locus_hard, int min_m, int max_m)
+__global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uint32_t *tlist, uint8_t *alive, const uint8_t *locus_hard, int min_m, int max_m, int hard_level)
 {
     const int64_t n_loci = (int64_t)a.totals[0];
     constexpr int GPB = MF_THREADS / G;
@@ -819,7 +819,7 @@ __global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uin
     const CandSoA &cd = a.cd;
     for (int64_t loc = (int64_t)blockIdx.x * GPB + threadIdx.x / G; loc < n_loci; loc += (int64_t)gridDim.x * GPB) {
         const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : cand_count(a);
-        if ((le - ls < min_m || le - ls > max_m) && !(locus_hard && locus_hard[ls])) continue;   // other loci: flat kernels / another group width
+        if ((le - ls < min_m || le - ls > max_m) && !(locus_hard && (hard_level ? locus_hard[ls] >= hard_level : locus_hard[ls] != 0))) continue;   // other loci: flat kernels / another group width
         int cnt = 0;
         for (int64_t c = ls; c < le; ++c) {
             const int t_tid = cd.tid[c], t_start = cd.start[c], t_rv = cd.rev[c], t_rev = t_rv & 1;
@@ -870,20 +870,7 @@ __global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uin
     }
 }
 
-// ------------------------------------------------------------------------------------------ flat fold (ss_dis == 0)
-// With exact splice-site matching the relation between two multi-exon chains is STATIC (internal boundaries only; the
-// mutable first start / last end enter through the end_dis tests alone), identity is transitive, and the partial-match
-// relation is a relation between identity classes.  That moves every exon-pool access out of the ordered part:
-//   fold_rep_kernel   thread per candidate: its identity class = first earlier candidate of the locus with the same
-//                     (exon count, chain hash[, strand]), verified once on the pools (a hash collision marks the locus
-//                     "hard": it is left to merge_fold_kernel);
-//   fold_rel_kernel   thread per candidate: bit mask (over the <= 64 earlier candidates of its locus) of the entries that
-//                     could absorb it -- same class, a class in partial-match relation (junction-signature pre-filter,
-//                     verified on the pools, decided once per class representative), other single-exon reads;
-//   fold_seq_kernel   thread per locus: the ordered fold itself on that mask and an alive mask held in registers: walk
-//                     the alive entries from the newest, stop on the reference's stop rule (dynamic end), take the first
-//                     confirmed event.  A warp folds 32 loci in lock step.
-static constexpr int FF_MAX = 64;                   // loci up to this many candidates; larger ones -> merge_fold_kernel
+static constexpr int FF_MAX = 64;                   // loci up to this many candidates; larger ones -> fold_big_kernel
 static constexpr uint32_t FF_BIG = 0xffffffffu;
 
 // does the chain s (fewer exons) continue the chain l from the first occurrence of its first junction on?  (gtf.c:79-88, dis 0)
@@ -910,6 +897,211 @@ LRB_DEVINL bool partial_static(const DExons &ex, uint32_t l_gbeg, int l_n, bool 
     }
     return false;
 }
+
+// ------------------------------------------------------------------------------- big loci (ss_dis == 0): classes + warp replay
+// Deep data (hundreds of reads per gene) puts most candidates into loci beyond the 64-candidate masks of the flat fold.  Replaying
+// those through merge_fold_kernel costs a chain of dependent L2 / HBM loads per survivor visited (candidate fields, then both exon
+// chains for every identity or partial-match test): ~2.4 us per candidate.  With exact splice-site matching the tests are STATIC:
+//   fold_big_mark_kernel     warp per locus: members of loci beyond the masks (or left over by the flat kernels) learn their locus head;
+//   fold_class_insert/verify thread per member: identity class = the first member of the locus with the same (chromosome, exon count,
+//                            chain hash, strand if -c, sub-stream), through one lock-free table; verified ONCE on the exon pools
+//                            (a 64-bit collision sends the locus to merge_fold_kernel);
+//   fold_big_kernel          warp per locus, the ordered replay itself with the survivors in SHARED memory: identity is an integer
+//                            compare of class ids, the partial-match relation between two classes (junction-signature pre-filter, then
+//                            the pools) is decided once and kept in a direct-mapped per-warp cache, the stop rule reads the slots.
+//                            32 survivors per step, 32 candidates loaded per batch, one per lane.
+// A locus whose survivors outgrow the slots (hard = 2) is redone by merge_fold_kernel -- exact either way.
+static constexpr int FB_WARPS = 4, FB_SLOTS = 416, FB_CACHE = 1024, FB_MAXREL = 32768;
+static constexpr uint16_t FB_MEMBER = 0xFFFFu;      // desc[] of a member of a big locus (the flat kernels are done with desc by then)
+struct FbSlots {                                    // per warp, structure of arrays: lane l reads slot base - l, conflict free
+    uint64_t j0[FB_SLOTS], sig[FB_SLOTS];
+    int fs[FB_SLOTS], le[FB_SLOTS], end[FB_SLOTS], start[FB_SLOTS], tid[FB_SLOTS], cov[FB_SLOTS];
+    uint32_t gbeg[FB_SLOTS], cand[FB_SLOTS], meta[FB_SLOTS], rep[FB_SLOTS];       // meta: n << 8 | kls << 2 | mono bit 1 | rev bit 0
+    uint32_t cache[FB_CACHE];                       // partial-match relation of two classes: valid 31 | result 30 | relA 29:15 | relB 14:0
+};
+struct ClassTab { unsigned long long *key; uint32_t *minidx; uint64_t cap; };
+
+__global__ void __launch_bounds__(256) fold_big_mark_kernel(MergeArgs a, const uint8_t *__restrict__ locus_hard, uint32_t *__restrict__ lstart)
+{
+    const int64_t n_loci = (int64_t)a.totals[0];
+    const int lane = lane_id();
+    for (int64_t loc = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32; loc < n_loci; loc += (int64_t)gridDim.x * blockDim.x / 32) {
+        const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : cand_count(a);
+        if (le - ls <= FF_MAX && !locus_hard[ls]) continue;
+        for (int64_t c = ls + lane; c < le; c += 32) { a.desc[c] = FB_MEMBER; lstart[c] = (uint32_t)ls; }
+    }
+}
+LRB_DEVINL uint64_t class_key(const MergeArgs &a, int64_t c, uint32_t ls)
+{
+    const CandSoA &cd = a.cd;
+    uint64_t k = mixh(cd.hash[c], (uint32_t)cd.n[c] | ((a.kls ? (uint32_t)a.kls[c] : 0u) << 16) | ((a.up.force_strand ? (uint32_t)(cd.rev[c] & 1) : 0u) << 20));
+    k = mixh(k, ls);                                // classes are per locus (check_iden itself never looks at the chromosome)
+    return k == ~0ull ? 0x1234567ull : k;
+}
+LRB_DEVINL uint64_t class_slot(const ClassTab &t, uint64_t k) { return __umul64hi(k * 0x9E3779B97F4A7C15ull, t.cap); }
+__global__ void __launch_bounds__(256) fold_class_insert_kernel(MergeArgs a, ClassTab t, const uint32_t *__restrict__ lstart)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cand_count(a) || a.desc[c] != FB_MEMBER || a.cd.n[c] < 2) return;
+    const uint64_t k = class_key(a, c, lstart[c]);
+    uint64_t s = class_slot(t, k);
+    for (;;) {
+        const unsigned long long p = atomicCAS(&t.key[s], ~0ull, (unsigned long long)k);
+        if (p == ~0ull || p == k) { atomicMin(&t.minidx[s], (uint32_t)c); return; }
+        s = s + 1 == t.cap ? 0 : s + 1;
+    }
+}
+__global__ void __launch_bounds__(256) fold_class_verify_kernel(MergeArgs a, ClassTab t, uint32_t *__restrict__ rep, const uint32_t *__restrict__ lstart, uint8_t *locus_hard)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cand_count(a) || a.desc[c] != FB_MEMBER) return;
+    const CandSoA &cd = a.cd;
+    const int nc = cd.n[c];
+    if (nc < 2) { rep[c] = (uint32_t)c; return; }
+    const uint32_t ls = lstart[c];
+    const uint64_t k = class_key(a, c, ls);
+    uint64_t s = class_slot(t, k);
+    while (t.key[s] != k) s = s + 1 == t.cap ? 0 : s + 1;
+    const uint32_t r = t.minidx[s];
+    rep[c] = r;
+    if (r == (uint32_t)c) return;
+    bool same = r >= ls && cd.n[r] == nc;           // same key in another locus (only an unsorted concatenation can do that) or a collision
+    if (same) {
+        const uint32_t gc = cd.gbeg[c], gr = cd.gbeg[r];
+        for (int i = 0; i < nc - 1; ++i) same = same && a.ex.ee[gc + i] == a.ex.ee[gr + i] && a.ex.es[gc + i + 1] == a.ex.es[gr + i + 1];
+        if (a.up.force_strand) same = same && ((cd.rev[c] ^ cd.rev[r]) & 1) == 0;
+        if (a.kls) same = same && a.kls[c] == a.kls[r];
+    }
+    if (!same) locus_hard[ls] = 3;                  // merge_fold_kernel replays this locus on the pools
+}
+
+__global__ void __launch_bounds__(FB_WARPS * 32) fold_big_kernel(MergeArgs a, const uint32_t *__restrict__ rep, uint8_t *alive, uint8_t *locus_hard, uint32_t *next_locus)
+{
+    extern __shared__ __align__(16) unsigned char fb_smem[];
+    FbSlots &S = reinterpret_cast<FbSlots *>(fb_smem)[warp_id()];
+    const int64_t n_loci = (int64_t)a.totals[0];
+    const int lane = lane_id();
+    const CandSoA &cd = a.cd;
+    const bool force = a.up.force_strand != 0;
+    const int end_dis = a.up.end_dis;
+    for (;;) {
+        // loci are claimed one at a time (their sizes differ by orders of magnitude)
+        uint32_t li = 0;
+        if (lane == 0) li = atomicAdd(next_locus, 1u);
+        const int64_t loc = (int64_t)__shfl_sync(FULL, li, 0);
+        if (loc >= n_loci) return;
+        const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : cand_count(a);
+        const int hd = locus_hard[ls];
+        if ((le - ls <= FF_MAX && !hd) || hd >= 2) continue;         // the flat kernels folded it / left to merge_fold_kernel
+        if (le - ls >= FB_MAXREL) { if (lane == 0) locus_hard[ls] = 2; continue; }
+        for (int i = lane; i < FB_CACHE; i += 32) S.cache[i] = 0;
+        __syncwarp();
+        int cnt = 0; bool overflow = false;
+        for (int64_t c0 = ls; c0 < le && !overflow; c0 += 32) {
+            // 32 candidates, one per lane
+            const int64_t cl = c0 + lane; const bool have = cl < le;
+            const int l_tid = have ? cd.tid[cl] : 0, l_start = have ? cd.start[cl] : 0, l_end = have ? cd.end[cl] : 0, l_rv = have ? cd.rev[cl] : 0;
+            const int l_n = have ? cd.n[cl] : 0, l_fs = have ? cd.fs[cl] : 0, l_le = have ? cd.le[cl] : 0; const uint32_t l_gbeg = have ? cd.gbeg[cl] : 0;
+            const uint64_t l_j0 = have ? cd.j0[cl] : 0, l_sig = have ? cd.sig[cl] : 0;
+            const uint32_t l_rep = have ? rep[cl] : 0;
+            const int l_kls = (have && a.kls) ? a.kls[cl] : 0;
+            int l_alive = 0;
+            const int nb = (int)min((int64_t)32, le - c0);
+            for (int q = 0; q < nb; ++q) {
+                const int t_tid = __shfl_sync(FULL, l_tid, q), t_start = __shfl_sync(FULL, l_start, q), t_end = __shfl_sync(FULL, l_end, q), t_rv = __shfl_sync(FULL, l_rv, q);
+                const int t_kls = __shfl_sync(FULL, l_kls, q), t_n = __shfl_sync(FULL, l_n, q), t_fs = __shfl_sync(FULL, l_fs, q), t_le = __shfl_sync(FULL, l_le, q);
+                const uint32_t t_gbeg = __shfl_sync(FULL, l_gbeg, q), t_rep = __shfl_sync(FULL, l_rep, q);
+                const uint64_t t_j0 = __shfl_sync(FULL, l_j0, q), t_sig = __shfl_sync(FULL, l_sig, q);
+                const int t_rev = t_rv & 1;
+                const uint32_t t_rel = t_rep - (uint32_t)ls;
+                int result = 0;                                      // 0 append, 1 absorbed / dropped
+                for (int base = cnt - 1; base >= 0; base -= 32) {
+                    const int k = base - lane;
+                    int ev = 0;                                      // 1 stop, 2 merge (identical), 3 drop (partial)
+                    if (k >= 0) {
+                        const uint32_t mt = S.meta[k];
+                        const int e_n = (int)(mt >> 8);
+                        if (a.kls && (int)((mt >> 2) & 3u) != t_kls) ev = 0;                          // another sub-stream: invisible
+                        else if (t_tid > S.tid[k] || t_start > S.end[k]) ev = 1;                      // update_gtf.c:148
+                        else if (!(force && t_rev != (int)(mt & 1u))) {                               // :149
+                            const int e_fs = S.fs[k], e_le = S.le[k];
+                            if (t_n == 1 && e_n == 1) {                                               // merge_trans2 :122-140
+                                if (iabs_dev(t_fs - e_fs) <= end_dis && iabs_dev(t_le - e_le) <= end_dis &&
+                                    ovlp_frac(t_fs, t_le, e_fs, e_le) >= a.up.single_exon_ovlp_frac) ev = 2;
+                            } else if (t_n > 1 && e_n > 1 && iabs_dev(t_fs - e_fs) <= end_dis && iabs_dev(t_le - e_le) <= end_dis) {   // merge_trans1 :98-119, check_iden
+                                if (t_n == e_n) { if (S.rep[k] == t_rep) ev = 2; }
+                                else {
+                                    // the shorter chain's first junction must be a junction of the longer (signature), then the static relation
+                                    const bool t_long = t_n > e_n;
+                                    const uint64_t lsig = t_long ? t_sig : S.sig[k], sj0 = t_long ? S.j0[k] : t_j0;
+                                    if ((lsig >> junc_bit(sj0)) & 1ull) {
+                                        const uint32_t e_rel = S.rep[k] - (uint32_t)ls;
+                                        const uint32_t pair = (t_rel << 15) | e_rel;
+                                        const uint32_t ci = ((t_rel * 0x9E37u) ^ (e_rel * 0x85EBu) ^ (e_rel >> 5)) & (FB_CACHE - 1);
+                                        const uint32_t ce = S.cache[ci];
+                                        bool rel;
+                                        if ((ce >> 31) && (ce & 0x3FFFFFFFu) == pair) rel = (ce >> 30) & 1u;
+                                        else {
+                                            rel = t_long ? partial_static(a.ex, t_gbeg, t_n, (t_rv & 2) != 0, sj0, S.gbeg[k], e_n)
+                                                         : partial_static(a.ex, S.gbeg[k], e_n, (mt & 2u) != 0, sj0, t_gbeg, t_n);
+                                            S.cache[ci] = 0x80000000u | (rel ? 0x40000000u : 0u) | pair;
+                                        }
+                                        if (rel) ev = 3;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    const unsigned m = __ballot_sync(FULL, ev != 0);
+                    if (m) {
+                        const int win = __ffs(m) - 1;                // lowest lane = entry nearest to the end of T
+                        const int wev = __shfl_sync(FULL, ev, win);
+                        if (wev == 2 && lane == win) {
+                            S.cov[k] += 1;
+                            if (t_fs < S.fs[k]) { S.fs[k] = t_fs; S.start[k] = t_fs; }
+                            if (t_le > S.le[k]) { S.le[k] = t_le; S.end[k] = t_le; }
+                        }
+                        result = wev == 1 ? 0 : 1;
+                        break;
+                    }
+                }
+                __syncwarp();
+                if (result == 0) {
+                    if (cnt == FB_SLOTS) { overflow = true; break; }
+                    if (lane == 0) {
+                        S.j0[cnt] = t_j0; S.sig[cnt] = t_sig; S.fs[cnt] = t_fs; S.le[cnt] = t_le; S.end[cnt] = t_end; S.start[cnt] = t_start;
+                        S.tid[cnt] = t_tid; S.cov[cnt] = 1; S.gbeg[cnt] = t_gbeg; S.cand[cnt] = (uint32_t)(c0 + q - ls); S.rep[cnt] = t_rep;
+                        S.meta[cnt] = ((uint32_t)t_n << 8) | ((uint32_t)t_kls << 2) | (uint32_t)(t_rv & 3);
+                    }
+                    ++cnt;
+                    if (lane == q) l_alive = 1;
+                }
+                __syncwarp();
+            }
+            if (!overflow && have) alive[cl] = (uint8_t)l_alive;
+        }
+        if (overflow) { if (lane == 0) locus_hard[ls] = 2; continue; }   // merge_fold_kernel redoes the locus from scratch
+        for (int k = lane; k < cnt; k += 32) {
+            const int64_t c = ls + S.cand[k];
+            a.work.cov[c] = S.cov[k]; a.work.start[c] = S.start[k]; a.work.end[c] = S.end[k]; a.work.fs[c] = S.fs[k]; a.work.le[c] = S.le[k];
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------ flat fold (ss_dis == 0)
+// With exact splice-site matching the relation between two multi-exon chains is STATIC (internal boundaries only; the
+// mutable first start / last end enter through the end_dis tests alone), identity is transitive, and the partial-match
+// relation is a relation between identity classes.  That moves every exon-pool access out of the ordered part:
+//   fold_rep_kernel   thread per candidate: its identity class = first earlier candidate of the locus with the same
+//                     (exon count, chain hash[, strand]), verified once on the pools (a hash collision marks the locus
+//                     "hard": it is left to merge_fold_kernel);
+//   fold_rel_kernel   thread per candidate: bit mask (over the <= 64 earlier candidates of its locus) of the entries that
+//                     could absorb it -- same class, a class in partial-match relation (junction-signature pre-filter,
+//                     verified on the pools, decided once per class representative), other single-exon reads;
+//   fold_seq_kernel   thread per locus: the ordered fold itself on that mask and an alive mask held in registers: walk
+//                     the alive entries from the newest, stop on the reference's stop rule (dynamic end), take the first
+//                     confirmed event.  A warp folds 32 loci in lock step.
 
 __global__ void __launch_bounds__(256) fold_rep_kernel(MergeArgs a, uint32_t *__restrict__ rep, uint32_t *__restrict__ lstart, uint8_t *locus_hard)
 {
@@ -1300,9 +1492,28 @@ void launch_merge_fold(const MergeArgs &a, cudaStream_t st)
         else if (slots <= 24) fold_seq_kernel<24><<<bs, FS_THREADS, 0, st>>>(a, a.rep, a.evmask, a.hard, a.dropped);
         else fold_seq_kernel<32><<<bs, FS_THREADS, 0, st>>>(a, a.rep, a.evmask, a.hard, a.dropped);
         LRB_COUNT_LAUNCH();
-        // loci beyond the masks, and the (hash-collision) hard ones
+        // loci beyond the masks and the ones the flat kernels gave up on: classes through one table, then warp per locus with the survivors
+        // in shared memory; what outgrows the slots there (hard >= 2) is replayed from global memory
+        static int big = -1;
+        if (big < 0) { const char *e = getenv("LRB_FOLD_BIG"); big = e ? atoi(e) : 1; }
         int64_t bl2 = (a.n_cand / (FF_MAX + 1) + 1 + 3) / 4 + 8; if (bl2 > 148 * 8) bl2 = 148 * 8;
-        merge_fold_kernel<32><<<(unsigned)bl2, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, a.hard, FF_MAX + 1, 0x7fffffff);
+        if (big && a.ckey) {
+            static bool attr = false;
+            const size_t smem = sizeof(FbSlots) * FB_WARPS;
+            if (!attr) { cudaFuncSetAttribute(fold_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+            ClassTab tab{(unsigned long long *)a.ckey, a.cmin, (uint64_t)a.n_cand * 2 + 64};
+            cudaMemsetAsync(a.ckey, 0xFF, tab.cap * 8, st); cudaMemsetAsync(a.cmin, 0xFF, tab.cap * 4, st);
+            int64_t blm = (a.n_cand / 8 + 255) / 256 + 1; if (blm > 148 * 8) blm = 148 * 8;
+            fold_big_mark_kernel<<<(unsigned)blm, 256, 0, st>>>(a, a.hard, a.lstart); LRB_COUNT_LAUNCH();
+            fold_class_insert_kernel<<<bl, 256, 0, st>>>(a, tab, a.lstart); LRB_COUNT_LAUNCH();
+            fold_class_verify_kernel<<<bl, 256, 0, st>>>(a, tab, a.rep, a.lstart, a.hard); LRB_COUNT_LAUNCH();
+            uint32_t *next_locus = a.ticket;                         // the prepare pass is over: its ticket is free
+            cudaMemsetAsync(next_locus, 0, 4, st);
+            int64_t blb = (a.n_cand / (FF_MAX + 1) + 1 + FB_WARPS - 1) / FB_WARPS + 1; if (blb > 148 * 2) blb = 148 * 2;
+            fold_big_kernel<<<(unsigned)blb, FB_WARPS * 32, smem, st>>>(a, a.rep, a.dropped, a.hard, next_locus); LRB_COUNT_LAUNCH();
+            merge_fold_kernel<32><<<(unsigned)bl2, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, a.hard, 0x7fffffff, 0x7fffffff, 2);
+        } else
+            merge_fold_kernel<32><<<(unsigned)bl2, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, a.hard, FF_MAX + 1, 0x7fffffff, 0);
         LRB_COUNT_LAUNCH();
         return;
     }
@@ -1310,12 +1521,12 @@ void launch_merge_fold(const MergeArgs &a, cudaStream_t st)
     {
         constexpr int GPB = MF_THREADS / 8;
         int64_t bl = (a.n_cand + GPB - 1) / GPB; if (bl > 148 * 12) bl = 148 * 12;
-        merge_fold_kernel<8><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, nullptr, 1, 32);
+        merge_fold_kernel<8><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, nullptr, 1, 32, 0);
         LRB_COUNT_LAUNCH();
     }
     {
         int64_t bl = (a.n_cand / 33 + 1 + 3) / 4; if (bl > 148 * 8) bl = 148 * 8;
-        merge_fold_kernel<32><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, nullptr, 33, 0x7fffffff);
+        merge_fold_kernel<32><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, nullptr, 33, 0x7fffffff, 0);
         LRB_COUNT_LAUNCH();
     }
 }

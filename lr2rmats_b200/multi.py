@@ -52,6 +52,18 @@ def take_shard(batch: dict, lo: int, hi: int) -> dict:
     return d
 
 
+def take_rows(batch: dict, idx) -> dict:
+    """Sub-batch of the records idx (in that order), e.g. filter's kept records."""
+    idx = np.asarray(idx, np.int64)
+    off = np.asarray(batch["cigar_off"]).astype(np.int64)
+    d = {k: np.ascontiguousarray(np.asarray(batch[k])[idx]) for k in ("tid", "pos", "flag", "l_qseq", "nm", "xs", "qname_hash")}
+    lens = off[idx + 1] - off[idx]
+    o = np.zeros(len(idx) + 1, np.int64); np.cumsum(lens, out=o[1:])
+    src = np.repeat(off[idx] - o[:-1], lens) + np.arange(o[-1])
+    d["cigar_off"] = o.astype(np.uint64); d["cigar"] = np.ascontiguousarray(np.asarray(batch["cigar"])[src])
+    return d
+
+
 def run_shard(ctx: api.Context, shard: dict | None, name_base: int, fp, ep, up, filtered: bool = True, fetch: bool = True):
     """One rank's part: upload, (filter +) CIGAR walk, update, gather to rank 0.  Returns the merged result on rank 0."""
     if shard is not None:

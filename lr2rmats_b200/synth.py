@@ -140,13 +140,22 @@ class Reads:
 
 
 def make_reads(anno: Annotation, n_reads: int, seed: int = 3, ont: bool = False, reject_frac: float = 0.0,
-               rrna=None, quirk_frac: float = 0.01, chrom_len: int = 150_000_000) -> Reads:
-    """n_reads primary alignments (+ secondaries when reject_frac>0), coordinate sorted and name grouped."""
+               rrna=None, quirk_frac: float = 0.01, chrom_len: int = 150_000_000, chrom: int | None = None, qid_base: int = 0) -> Reads:
+    """n_reads primary alignments (+ secondaries when reject_frac>0), coordinate sorted and name grouped.
+    chrom: draw from the transcripts (and rRNA entries) of that chromosome only -- a data set can then be generated chromosome by
+    chromosome (in parallel, or by the rank that owns the chromosome) and concatenated; qid_base keeps the read names distinct."""
     rng = np.random.default_rng(seed)
     ps, pe, tne = _padded_exons(anno)
     n = n_reads
     inter = rng.random(n) < 0.05
-    t = rng.integers(0, anno.n_trans, n)
+    if chrom is None:
+        t = rng.integers(0, anno.n_trans, n)
+    else:
+        on = np.nonzero(anno.tid == chrom)[0]
+        t = on[rng.integers(0, len(on), n)]
+        if rrna is not None:
+            m = rrna["tid"] == chrom
+            rrna = {k: v[m] for k, v in rrna.items()}
     ne = tne[t]
     # exon window [a, b] of the transcript kept by the read
     trunc = (rng.random(n) < 0.40) & (ne > 2)
@@ -209,7 +218,9 @@ def make_reads(anno: Annotation, n_reads: int, seed: int = 3, ont: bool = False,
             e[rr, 0] = s[rr, 0] + rng.integers(150, 600, int(rr.sum()))
             inter = inter | rr
 
+    QID_BASE[0] = int(qid_base)
     r = _assemble(rng, n, tid, rev, s, e, keep, ont, cls, quirk_frac)
+    QID_BASE[0] = 0
     # ---- secondary alignments: same qname, a slightly worse / equal copy right after the primary
     if reject_frac > 0:
         sec = np.nonzero(cls == 4)[0]
@@ -228,6 +239,9 @@ def make_reads(anno: Annotation, n_reads: int, seed: int = 3, ont: bool = False,
     r.chrom_names = list(anno.chrom_names)
     r.chrom_lens = [chrom_len] * len(anno.chrom_names)
     return r
+
+
+QID_BASE = [0]          # read-name offset of the batch being assembled (make_reads' qid_base)
 
 
 def _concat(a: Reads, b: Reads) -> Reads:
@@ -324,7 +338,7 @@ def _assemble(rng, n, tid, rev, s, e, keep, ont, cls, quirk_frac) -> Reads:
     tagged = rng.random(n) < 0.10
     xs[tagged] = np.where(rng.random(int(tagged.sum())) < 0.5, ord("+"), ord("-")).astype(np.int8)
     r.xs = xs
-    r.qid = np.arange(n, dtype=np.int64)
+    r.qid = np.arange(n, dtype=np.int64) + QID_BASE[0]
     r.qname_hash = splitmix64(r.qid)
     r.cigar = cigar; r.cigar_off = coff.astype(np.uint64)
 
@@ -414,6 +428,18 @@ def make_sj_from_reads(reads: Reads, frac: float = 0.7, seed: int = 5, min_intro
     kt, kd, ka = kt[keepm], kd[keepm], ka[keepm]
     return dict(tid=kt.astype(np.int32), don=kd.astype(np.int32), acc=ka.astype(np.int32),
                 uniq_c=rng.integers(0, 6, len(kt)).astype(np.int32), multi_c=rng.integers(0, 3, len(kt)).astype(np.int32))
+
+
+def concat_reads(parts):
+    """Batches of consecutive chromosome blocks (each coordinate sorted) as one stream."""
+    r = Reads()
+    for k in ("tid", "pos", "flag", "l_qseq", "nm", "xs", "qname_hash", "qid"):
+        setattr(r, k, np.concatenate([getattr(p, k) for p in parts]))
+    r.cigar = np.concatenate([p.cigar for p in parts])
+    base = np.cumsum([0] + [int(p.cigar_off[-1]) for p in parts])
+    r.cigar_off = np.concatenate([parts[i].cigar_off[:-1].astype(np.int64) + base[i] for i in range(len(parts))] + [base[-1:]]).astype(np.uint64)
+    r.chrom_names, r.chrom_lens = parts[0].chrom_names, parts[0].chrom_lens
+    return r
 
 
 def clone_chromosome(anno_soa: dict, reads: Reads, sj: dict, n_chrom: int):

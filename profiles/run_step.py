@@ -9,7 +9,8 @@ n_steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 ont = len(sys.argv) > 3 and sys.argv[3] == "ont"
 fp, ep = cabi.FilterParams.default(), cabi.ExonParams.default()
 up = cabi.UpdateParams.default(full_level=3, split_trans=1, want_summary=1)
-anno, rr, reads = bench.make_workload(n_reads, int(60_000 * n_reads / 1_000_000), seed=3, ont=ont)
+n_genes = int(sys.argv[4]) if len(sys.argv) > 4 else int(60_000 * n_reads / 1_000_000)
+anno, rr, reads = bench.make_workload(n_reads, n_genes, seed=3, ont=ont)
 sj = bench.make_sj_table(reads, ep)
 ctx = api.Context(0)
 ctx.set_anno(anno.soa()); ctx.set_rm(rr); ctx.set_sj(sj)

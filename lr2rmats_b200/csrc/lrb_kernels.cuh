@@ -134,11 +134,12 @@ struct MergeArgs {
     uint8_t *head;                                  // locus head flags
     uint32_t *locus_start;                          // compacted heads (+ sentinel)
     DMerged work;                                   // per-candidate slots (T entries live at their locus' range)
-    uint32_t *locus_cnt;                            // surviving entries per locus
+    uint32_t *locus_cnt;                            // big loci: number of multi-exon classes (FB_NOROWS: too many for the relation rows)
     uint8_t *dropped;                               // per candidate: absorbed/dropped by the fold
     uint32_t *rep, *lstart; uint64_t *evmask;       // flat fold: class representative, locus head, absorber mask per candidate
     uint16_t *desc; uint64_t *relsym;               // flat fold: class descriptor per candidate; per representative the related representatives
     uint8_t *hard;                                  // per locus head: 1 = not for the flat kernels, >= 2 = not for fold_big_kernel either (merge_fold_kernel)
+    uint8_t *cord; uint32_t *clist; uint64_t *crow;  // big loci: class ordinal per candidate; per locus (at its offset) the class representatives and their 128-bit relation rows
     uint64_t *ckey; uint32_t *cmin;                 // class table of the big loci: 2 * n_cand + 64 slots (NULL: big loci go to merge_fold_kernel)
     DMerged out;                                    // compacted result
     uint64_t *tile_state; uint32_t *ticket; uint64_t *totals;  // [0] n_loci, [1] n_out

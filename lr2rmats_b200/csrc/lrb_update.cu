@@ -809,7 +809,7 @@ LRB_DEVINL int chain_iden(const DExons &ex, const Entry &t1, const Entry &t2, in
 static constexpr int MF_THREADS = 128;
 // G lanes per locus; tlist[ls + k] = candidate index of the k-th entry of the locus' T; mutable entry data lives at work[cand]
 template <int G>
-__global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uint32_t *tlist, uint8_t *alive, const uint8_t *locus_hard, int min_m, int max_m, int hard_level)
+__global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uint32_t *tlist, uint8_t *alive, const uint8_t *locus_hard, int min_m, int max_m, int hard_mask)
 {
     const int64_t n_loci = (int64_t)a.totals[0];
     constexpr int GPB = MF_THREADS / G;
@@ -819,7 +819,7 @@ __global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uin
     const CandSoA &cd = a.cd;
     for (int64_t loc = (int64_t)blockIdx.x * GPB + threadIdx.x / G; loc < n_loci; loc += (int64_t)gridDim.x * GPB) {
         const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : cand_count(a);
-        if ((le - ls < min_m || le - ls > max_m) && !(locus_hard && (hard_level ? locus_hard[ls] >= hard_level : locus_hard[ls] != 0))) continue;   // other loci: flat kernels / another group width
+        if ((le - ls < min_m || le - ls > max_m) && !(locus_hard && ((hard_mask >> locus_hard[ls]) & 1))) continue;   // other loci: flat kernels / another group width
         int cnt = 0;
         for (int64_t c = ls; c < le; ++c) {
             const int t_tid = cd.tid[c], t_start = cd.start[c], t_rv = cd.rev[c], t_rev = t_rv & 1;
@@ -911,13 +911,17 @@ LRB_DEVINL bool partial_static(const DExons &ex, uint32_t l_gbeg, int l_n, bool 
 //                            the pools) is decided once and kept in a direct-mapped per-warp cache, the stop rule reads the slots.
 //                            32 survivors per step, 32 candidates loaded per batch, one per lane.
 // A locus whose survivors outgrow the slots (hard = 2) is redone by merge_fold_kernel -- exact either way.
-static constexpr int FB_WARPS = 4, FB_SLOTS = 416, FB_CACHE = 1024, FB_MAXREL = 32768;
+static constexpr int FB_THREADS = 128, FB_MAXREL = 32768;
 static constexpr uint16_t FB_MEMBER = 0xFFFFu;      // desc[] of a member of a big locus (the flat kernels are done with desc by then)
-struct FbSlots {                                    // per warp, structure of arrays: lane l reads slot base - l, conflict free
-    uint64_t j0[FB_SLOTS], sig[FB_SLOTS];
-    int fs[FB_SLOTS], le[FB_SLOTS], end[FB_SLOTS], start[FB_SLOTS], tid[FB_SLOTS], cov[FB_SLOTS];
-    uint32_t gbeg[FB_SLOTS], cand[FB_SLOTS], meta[FB_SLOTS], rep[FB_SLOTS];       // meta: n << 8 | kls << 2 | mono bit 1 | rev bit 0
-    uint32_t cache[FB_CACHE];                       // partial-match relation of two classes: valid 31 | result 30 | relA 29:15 | relB 14:0
+// G lanes per locus: lane l reads slot base - l (conflict free inside the group); two tiers -- 8 lanes / 64 slots for the common
+// locus (a few dozen survivors: four loci per warp), a whole warp / 416 slots for what outgrows that
+template <int SLOTS, int CACHE>
+struct FbSlots {
+    uint64_t j0[SLOTS], sig[SLOTS];
+    int fs[SLOTS], le[SLOTS], end[SLOTS], start[SLOTS], tid[SLOTS], cov[SLOTS];
+    uint32_t gbeg[SLOTS], cand[SLOTS], meta[SLOTS], rep[SLOTS];       // meta: n << 8 | kls << 2 | mono bit 1 | rev bit 0
+    uint32_t cache[CACHE];                          // partial-match relation of two classes: valid 31 | result 30 | relA 29:15 | relB 14:0
+    uint32_t pad[8];                                // group stride = 8 banks mod 32: the four 8-lane groups of a warp read disjoint banks
 };
 struct ClassTab { unsigned long long *key; uint32_t *minidx; uint64_t cap; };
 
@@ -975,12 +979,66 @@ __global__ void __launch_bounds__(256) fold_class_verify_kernel(MergeArgs a, Cla
     if (!same) locus_hard[ls] = 3;                  // merge_fold_kernel replays this locus on the pools
 }
 
-__global__ void __launch_bounds__(FB_WARPS * 32) fold_big_kernel(MergeArgs a, const uint32_t *__restrict__ rep, uint8_t *alive, uint8_t *locus_hard, uint32_t *next_locus)
+// Warp per big locus: the multi-exon classes of the locus get dense ordinals in order of first occurrence (single-exon candidates share
+// the pseudo class FB_SINGLE: their relation is dynamic, decided on the slots), and the STATIC relation between every two classes of
+// the locus (identity on the diagonal, partial match elsewhere: gtf.c:76-91 on the chains of the two representatives) becomes a
+// 128-bit row per class.  The replay then needs no exon pool at all: "can this survivor absorb the candidate" is one bit test.
+// Loci with more than FB_MAXCLS classes keep locus_cnt = FB_NOROWS and the replay falls back to its relation cache.
+static constexpr int FB_MAXCLS = 127; static constexpr uint32_t FB_SINGLE = 127u, FB_NOROWS = 0xffffffffu;
+__global__ void __launch_bounds__(256) fold_class_rows_kernel(MergeArgs a, const uint32_t *__restrict__ rep, const uint8_t *__restrict__ locus_hard)
 {
-    extern __shared__ __align__(16) unsigned char fb_smem[];
-    FbSlots &S = reinterpret_cast<FbSlots *>(fb_smem)[warp_id()];
     const int64_t n_loci = (int64_t)a.totals[0];
     const int lane = lane_id();
+    const CandSoA &cd = a.cd;
+    for (int64_t loc = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32; loc < n_loci; loc += (int64_t)gridDim.x * blockDim.x / 32) {
+        const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : cand_count(a);
+        const int hd = locus_hard[ls];
+        if ((le - ls <= FF_MAX && !hd) || hd >= 2) continue;
+        int K = 0;
+        for (int64_t c0 = ls; c0 < le; c0 += 32) {
+            const int64_t c = c0 + lane;
+            const bool headc = c < le && cd.n[c] > 1 && rep[c] == (uint32_t)c;
+            const unsigned b = __ballot_sync(FULL, headc);
+            if (headc) {
+                const int o = K + __popc(b & ((1u << lane) - 1u));
+                if (o < FB_MAXCLS) { a.cord[c] = (uint8_t)o; a.clist[ls + o] = (uint32_t)c; a.crow[2 * (ls + o)] = o < 64 ? 1ull << o : 0; a.crow[2 * (ls + o) + 1] = o >= 64 ? 1ull << (o - 64) : 0; }
+            }
+            K += __popc(b);
+        }
+        if (lane == 0) a.locus_cnt[loc] = K <= FB_MAXCLS ? (uint32_t)K : FB_NOROWS;
+        if (K > FB_MAXCLS) continue;
+        __syncwarp();
+        for (int64_t c = ls + lane; c < le; c += 32) {
+            if (cd.n[c] < 2) a.cord[c] = (uint8_t)FB_SINGLE;
+            else if (rep[c] != (uint32_t)c) a.cord[c] = a.cord[rep[c]];
+        }
+        for (int p = lane; p < K * K; p += 32) {
+            const int i = p / K, j = p - i * K;
+            if (i >= j) continue;
+            const uint32_t A = a.clist[ls + i], B = a.clist[ls + j];
+            const int nA = cd.n[A], nB = cd.n[B];
+            if (nA == nB) continue;                                  // equal exon counts: identical or unrelated, never partial
+            if (a.kls && a.kls[A] != a.kls[B]) continue;             // sub-streams never see each other
+            const uint32_t L = nA > nB ? A : B, Sh = nA > nB ? B : A;
+            const uint64_t sj0 = cd.j0[Sh];
+            if (!((cd.sig[L] >> junc_bit(sj0)) & 1ull)) continue;
+            if (!partial_static(a.ex, cd.gbeg[L], cd.n[L], (cd.rev[L] & 2) != 0, sj0, cd.gbeg[Sh], cd.n[Sh])) continue;
+            atomicOr((unsigned long long *)&a.crow[2 * (ls + i) + (j >> 6)], 1ull << (j & 63));
+            atomicOr((unsigned long long *)&a.crow[2 * (ls + j) + (i >> 6)], 1ull << (i & 63));
+        }
+    }
+}
+
+// tier 0: loci beyond the masks or left over by the flat kernels (hard == 1); overflow -> hard = 4.  tier 1: hard == 4; overflow -> hard = 2.
+template <int G, int SLOTS, int CACHE, int TIER>
+__global__ void __launch_bounds__(FB_THREADS) fold_big_kernel(MergeArgs a, const uint32_t *__restrict__ rep, uint8_t *alive, uint8_t *locus_hard, uint32_t *next_locus)
+{
+    extern __shared__ __align__(16) unsigned char fb_smem[];
+    FbSlots<SLOTS, CACHE> &S = reinterpret_cast<FbSlots<SLOTS, CACHE> *>(fb_smem)[threadIdx.x / G];
+    const int64_t n_loci = (int64_t)a.totals[0];
+    const int lane = threadIdx.x % G;
+    const unsigned gm = group_mask<G>();
+    const int sh = (lane_id() / G) * G;
     const CandSoA &cd = a.cd;
     const bool force = a.up.force_strand != 0;
     const int end_dis = a.up.end_dis;
@@ -988,16 +1046,17 @@ __global__ void __launch_bounds__(FB_WARPS * 32) fold_big_kernel(MergeArgs a, co
         // loci are claimed one at a time (their sizes differ by orders of magnitude)
         uint32_t li = 0;
         if (lane == 0) li = atomicAdd(next_locus, 1u);
-        const int64_t loc = (int64_t)__shfl_sync(FULL, li, 0);
+        const int64_t loc = (int64_t)__shfl_sync(gm, li, 0, G);
         if (loc >= n_loci) return;
         const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : cand_count(a);
         const int hd = locus_hard[ls];
-        if ((le - ls <= FF_MAX && !hd) || hd >= 2) continue;         // the flat kernels folded it / left to merge_fold_kernel
+        if (TIER == 0 ? ((le - ls <= FF_MAX && !hd) || hd >= 2) : hd != 4) continue;       // folded already / another tier's / merge_fold_kernel's
         if (le - ls >= FB_MAXREL) { if (lane == 0) locus_hard[ls] = 2; continue; }
-        for (int i = lane; i < FB_CACHE; i += 32) S.cache[i] = 0;
-        __syncwarp();
+        const bool use_rows = a.locus_cnt[loc] != FB_NOROWS;         // the static relation of the locus' classes is tabulated
+        if (!use_rows) for (int i = lane; i < CACHE; i += G) S.cache[i] = 0;
+        __syncwarp(gm);
         int cnt = 0; bool overflow = false;
-        for (int64_t c0 = ls; c0 < le && !overflow; c0 += 32) {
+        for (int64_t c0 = ls; c0 < le && !overflow; c0 += G) {
             // 32 candidates, one per lane
             const int64_t cl = c0 + lane; const bool have = cl < le;
             const int l_tid = have ? cd.tid[cl] : 0, l_start = have ? cd.start[cl] : 0, l_end = have ? cd.end[cl] : 0, l_rv = have ? cd.rev[cl] : 0;
@@ -1005,17 +1064,21 @@ __global__ void __launch_bounds__(FB_WARPS * 32) fold_big_kernel(MergeArgs a, co
             const uint64_t l_j0 = have ? cd.j0[cl] : 0, l_sig = have ? cd.sig[cl] : 0;
             const uint32_t l_rep = have ? rep[cl] : 0;
             const int l_kls = (have && a.kls) ? a.kls[cl] : 0;
+            const uint32_t l_ord = (have && use_rows) ? a.cord[cl] : FB_SINGLE;
+            const uint64_t l_row0 = l_ord != FB_SINGLE ? a.crow[2 * (ls + l_ord)] : 0, l_row1 = l_ord != FB_SINGLE ? a.crow[2 * (ls + l_ord) + 1] : 0;
             int l_alive = 0;
-            const int nb = (int)min((int64_t)32, le - c0);
+            const int nb = (int)min((int64_t)G, le - c0);
             for (int q = 0; q < nb; ++q) {
-                const int t_tid = __shfl_sync(FULL, l_tid, q), t_start = __shfl_sync(FULL, l_start, q), t_end = __shfl_sync(FULL, l_end, q), t_rv = __shfl_sync(FULL, l_rv, q);
-                const int t_kls = __shfl_sync(FULL, l_kls, q), t_n = __shfl_sync(FULL, l_n, q), t_fs = __shfl_sync(FULL, l_fs, q), t_le = __shfl_sync(FULL, l_le, q);
-                const uint32_t t_gbeg = __shfl_sync(FULL, l_gbeg, q), t_rep = __shfl_sync(FULL, l_rep, q);
-                const uint64_t t_j0 = __shfl_sync(FULL, l_j0, q), t_sig = __shfl_sync(FULL, l_sig, q);
+                const int t_tid = __shfl_sync(gm, l_tid, q, G), t_start = __shfl_sync(gm, l_start, q, G), t_end = __shfl_sync(gm, l_end, q, G), t_rv = __shfl_sync(gm, l_rv, q, G);
+                const int t_kls = __shfl_sync(gm, l_kls, q, G), t_n = __shfl_sync(gm, l_n, q, G), t_fs = __shfl_sync(gm, l_fs, q, G), t_le = __shfl_sync(gm, l_le, q, G);
+                const uint32_t t_gbeg = __shfl_sync(gm, l_gbeg, q, G), t_rep = __shfl_sync(gm, l_rep, q, G);
+                const uint64_t t_j0 = __shfl_sync(gm, l_j0, q, G), t_sig = __shfl_sync(gm, l_sig, q, G);
+                const uint64_t t_row0 = __shfl_sync(gm, l_row0, q, G), t_row1 = __shfl_sync(gm, l_row1, q, G);
+                const uint32_t t_ord = __shfl_sync(gm, l_ord, q, G);
                 const int t_rev = t_rv & 1;
                 const uint32_t t_rel = t_rep - (uint32_t)ls;
                 int result = 0;                                      // 0 append, 1 absorbed / dropped
-                for (int base = cnt - 1; base >= 0; base -= 32) {
+                for (int base = cnt - 1; base >= 0; base -= G) {
                     const int k = base - lane;
                     int ev = 0;                                      // 1 stop, 2 merge (identical), 3 drop (partial)
                     if (k >= 0) {
@@ -1029,7 +1092,10 @@ __global__ void __launch_bounds__(FB_WARPS * 32) fold_big_kernel(MergeArgs a, co
                                 if (iabs_dev(t_fs - e_fs) <= end_dis && iabs_dev(t_le - e_le) <= end_dis &&
                                     ovlp_frac(t_fs, t_le, e_fs, e_le) >= a.up.single_exon_ovlp_frac) ev = 2;
                             } else if (t_n > 1 && e_n > 1 && iabs_dev(t_fs - e_fs) <= end_dis && iabs_dev(t_le - e_le) <= end_dis) {   // merge_trans1 :98-119, check_iden
-                                if (t_n == e_n) { if (S.rep[k] == t_rep) ev = 2; }
+                                if (use_rows) {
+                                    const uint32_t e_ord = S.cand[k] >> 16;
+                                    if ((((e_ord & 64u) ? t_row1 : t_row0) >> (e_ord & 63u)) & 1ull) ev = e_ord == t_ord ? 2 : 3;
+                                } else if (t_n == e_n) { if (S.rep[k] == t_rep) ev = 2; }
                                 else {
                                     // the shorter chain's first junction must be a junction of the longer (signature), then the static relation
                                     const bool t_long = t_n > e_n;
@@ -1037,7 +1103,7 @@ __global__ void __launch_bounds__(FB_WARPS * 32) fold_big_kernel(MergeArgs a, co
                                     if ((lsig >> junc_bit(sj0)) & 1ull) {
                                         const uint32_t e_rel = S.rep[k] - (uint32_t)ls;
                                         const uint32_t pair = (t_rel << 15) | e_rel;
-                                        const uint32_t ci = ((t_rel * 0x9E37u) ^ (e_rel * 0x85EBu) ^ (e_rel >> 5)) & (FB_CACHE - 1);
+                                        const uint32_t ci = ((t_rel * 0x9E37u) ^ (e_rel * 0x85EBu) ^ (e_rel >> 5)) & (CACHE - 1);
                                         const uint32_t ce = S.cache[ci];
                                         bool rel;
                                         if ((ce >> 31) && (ce & 0x3FFFFFFFu) == pair) rel = (ce >> 30) & 1u;
@@ -1052,10 +1118,10 @@ __global__ void __launch_bounds__(FB_WARPS * 32) fold_big_kernel(MergeArgs a, co
                             }
                         }
                     }
-                    const unsigned m = __ballot_sync(FULL, ev != 0);
+                    const unsigned m = (__ballot_sync(gm, ev != 0) >> sh) & lane_bits<G>();
                     if (m) {
                         const int win = __ffs(m) - 1;                // lowest lane = entry nearest to the end of T
-                        const int wev = __shfl_sync(FULL, ev, win);
+                        const int wev = __shfl_sync(gm, ev, win, G);
                         if (wev == 2 && lane == win) {
                             S.cov[k] += 1;
                             if (t_fs < S.fs[k]) { S.fs[k] = t_fs; S.start[k] = t_fs; }
@@ -1065,27 +1131,27 @@ __global__ void __launch_bounds__(FB_WARPS * 32) fold_big_kernel(MergeArgs a, co
                         break;
                     }
                 }
-                __syncwarp();
+                __syncwarp(gm);
                 if (result == 0) {
-                    if (cnt == FB_SLOTS) { overflow = true; break; }
+                    if (cnt == SLOTS) { overflow = true; break; }
                     if (lane == 0) {
                         S.j0[cnt] = t_j0; S.sig[cnt] = t_sig; S.fs[cnt] = t_fs; S.le[cnt] = t_le; S.end[cnt] = t_end; S.start[cnt] = t_start;
-                        S.tid[cnt] = t_tid; S.cov[cnt] = 1; S.gbeg[cnt] = t_gbeg; S.cand[cnt] = (uint32_t)(c0 + q - ls); S.rep[cnt] = t_rep;
+                        S.tid[cnt] = t_tid; S.cov[cnt] = 1; S.gbeg[cnt] = t_gbeg; S.cand[cnt] = (uint32_t)(c0 + q - ls) | (t_ord << 16); S.rep[cnt] = t_rep;
                         S.meta[cnt] = ((uint32_t)t_n << 8) | ((uint32_t)t_kls << 2) | (uint32_t)(t_rv & 3);
                     }
                     ++cnt;
                     if (lane == q) l_alive = 1;
                 }
-                __syncwarp();
+                __syncwarp(gm);
             }
             if (!overflow && have) alive[cl] = (uint8_t)l_alive;
         }
-        if (overflow) { if (lane == 0) locus_hard[ls] = 2; continue; }   // merge_fold_kernel redoes the locus from scratch
-        for (int k = lane; k < cnt; k += 32) {
-            const int64_t c = ls + S.cand[k];
+        if (overflow) { if (lane == 0) locus_hard[ls] = TIER == 0 ? 4 : 2; continue; }   // the next tier / merge_fold_kernel redoes the locus from scratch
+        for (int k = lane; k < cnt; k += G) {
+            const int64_t c = ls + (S.cand[k] & 0xFFFFu);
             a.work.cov[c] = S.cov[k]; a.work.start[c] = S.start[k]; a.work.end[c] = S.end[k]; a.work.fs[c] = S.fs[k]; a.work.le[c] = S.le[k];
         }
-        __syncwarp();
+        __syncwarp(gm);
     }
 }
 
@@ -1498,22 +1564,42 @@ void launch_merge_fold(const MergeArgs &a, cudaStream_t st)
         if (big < 0) { const char *e = getenv("LRB_FOLD_BIG"); big = e ? atoi(e) : 1; }
         int64_t bl2 = (a.n_cand / (FF_MAX + 1) + 1 + 3) / 4 + 8; if (bl2 > 148 * 8) bl2 = 148 * 8;
         if (big && a.ckey) {
+            using S0 = FbSlots<64, 256>; using S1 = FbSlots<416, 1024>;
+            auto k0 = fold_big_kernel<8, 64, 256, 0>; auto k1 = fold_big_kernel<32, 416, 1024, 1>;
+            const size_t smem0 = sizeof(S0) * (FB_THREADS / 8), smem1 = sizeof(S1) * (FB_THREADS / 32);
             static bool attr = false;
-            const size_t smem = sizeof(FbSlots) * FB_WARPS;
-            if (!attr) { cudaFuncSetAttribute(fold_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+            if (!attr) { cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0); cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1); attr = true; }
             ClassTab tab{(unsigned long long *)a.ckey, a.cmin, (uint64_t)a.n_cand * 2 + 64};
             cudaMemsetAsync(a.ckey, 0xFF, tab.cap * 8, st); cudaMemsetAsync(a.cmin, 0xFF, tab.cap * 4, st);
             int64_t blm = (a.n_cand / 8 + 255) / 256 + 1; if (blm > 148 * 8) blm = 148 * 8;
             fold_big_mark_kernel<<<(unsigned)blm, 256, 0, st>>>(a, a.hard, a.lstart); LRB_COUNT_LAUNCH();
             fold_class_insert_kernel<<<bl, 256, 0, st>>>(a, tab, a.lstart); LRB_COUNT_LAUNCH();
             fold_class_verify_kernel<<<bl, 256, 0, st>>>(a, tab, a.rep, a.lstart, a.hard); LRB_COUNT_LAUNCH();
+            fold_class_rows_kernel<<<(unsigned)blm, 256, 0, st>>>(a, a.rep, a.hard); LRB_COUNT_LAUNCH();
             uint32_t *next_locus = a.ticket;                         // the prepare pass is over: its ticket is free
             cudaMemsetAsync(next_locus, 0, 4, st);
-            int64_t blb = (a.n_cand / (FF_MAX + 1) + 1 + FB_WARPS - 1) / FB_WARPS + 1; if (blb > 148 * 2) blb = 148 * 2;
-            fold_big_kernel<<<(unsigned)blb, FB_WARPS * 32, smem, st>>>(a, a.rep, a.dropped, a.hard, next_locus); LRB_COUNT_LAUNCH();
-            merge_fold_kernel<32><<<(unsigned)bl2, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, a.hard, 0x7fffffff, 0x7fffffff, 2);
+            int64_t blb = (a.n_cand / (FF_MAX + 1) + 1) / (FB_THREADS / 8) + 1; if (blb > 148 * 3) blb = 148 * 3;
+            static int fbg = -1;
+            if (fbg < 0) { const char *e = getenv("LRB_FB_G"); fbg = e ? atoi(e) : 8; }
+            if (fbg == 16) {
+                auto k16 = fold_big_kernel<16, 96, 256, 0>; const size_t sm16 = sizeof(FbSlots<96, 256>) * (FB_THREADS / 16);
+                static bool a16 = false; if (!a16) { cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16); a16 = true; }
+                blb = (a.n_cand / (FF_MAX + 1) + 1) / (FB_THREADS / 16) + 1; if (blb > 148 * 4) blb = 148 * 4;
+                k16<<<(unsigned)blb, FB_THREADS, sm16, st>>>(a, a.rep, a.dropped, a.hard, next_locus);
+            } else if (fbg == 32) {
+                auto k32 = fold_big_kernel<32, 128, 256, 0>; const size_t sm32 = sizeof(FbSlots<128, 256>) * (FB_THREADS / 32);
+                static bool a32 = false; if (!a32) { cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm32); a32 = true; }
+                blb = (a.n_cand / (FF_MAX + 1) + 1) / (FB_THREADS / 32) + 1; if (blb > 148 * 6) blb = 148 * 6;
+                k32<<<(unsigned)blb, FB_THREADS, sm32, st>>>(a, a.rep, a.dropped, a.hard, next_locus);
+            } else
+                k0<<<(unsigned)blb, FB_THREADS, smem0, st>>>(a, a.rep, a.dropped, a.hard, next_locus);
+            LRB_COUNT_LAUNCH();
+            cudaMemsetAsync(next_locus, 0, 4, st);
+            blb = (a.n_cand / (FF_MAX + 1) + 1) / (FB_THREADS / 32) + 1; if (blb > 148 * 2) blb = 148 * 2;
+            k1<<<(unsigned)blb, FB_THREADS, smem1, st>>>(a, a.rep, a.dropped, a.hard, next_locus); LRB_COUNT_LAUNCH();
+            merge_fold_kernel<32><<<(unsigned)bl2, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, a.hard, 0x7fffffff, 0x7fffffff, (1 << 2) | (1 << 3));
         } else
-            merge_fold_kernel<32><<<(unsigned)bl2, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, a.hard, FF_MAX + 1, 0x7fffffff, 0);
+            merge_fold_kernel<32><<<(unsigned)bl2, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, a.hard, FF_MAX + 1, 0x7fffffff, 0xFE);
         LRB_COUNT_LAUNCH();
         return;
     }

@@ -46,8 +46,11 @@ UNIT = "alignments/s"
 N_CHROM = 24
 
 
+_T0 = time.time()
+
+
 def log(*a):
-    print(*a, file=sys.stderr, flush=True)
+    print(f"[{time.time() - _T0:7.1f}s]", *a, file=sys.stderr, flush=True)
 
 
 # ----------------------------------------------------------------------------------------------- workload
@@ -362,8 +365,11 @@ def bench_ours(args, rank, world, local_rank):
     # ---- device-resident timing
     ctx.upload_struct(batch); ctx.sync()
     ctx.timing(True)
-    for _ in range(args.warmup):
-        step_resident()
+    for i in range(args.warmup):
+        if i == 0:
+            ctx.pipeline_run(fp, ep); ctx.sync(); log(f"[rank {rank}] first pipeline_run done: {ctx.timing_get()[0]}")
+        step_resident(); ctx.sync()
+        log(f"[rank {rank}] warm-up step {i} done: {ctx.timing_get()[0]}")
     clocks = ClockSampler(dev); clocks.start()
     times, stage_ms, gather_ms, launches = [], [], [], 0
     barrier()
@@ -385,6 +391,7 @@ def bench_ours(args, rank, world, local_rank):
             gather_ms.append(ctx.gather_timing())
     barrier()
     ms_step = float(np.mean(times))
+    log(f"[rank {rank}] device-resident: {ms_step:.3f} ms/step")
     tb = ctx.update_fetch_table(want_bed=True)
     n_kept = int(ctx.filter_fetch_keep(raw=True)[0])
     ne_rows = None
@@ -436,10 +443,12 @@ def bench_ours(args, rank, world, local_rank):
         return 1e3 * (time.perf_counter() - t1)
 
     run_e2e(max(n_ctx, min(args.warmup, 3)))
+    log(f"[rank {rank}] e2e warm-up done")
     flush.fill_(1); torch.cuda.synchronize(dev)
     barrier()
     e2e_total_ms = run_e2e(args.steps)
     barrier()
+    log(f"[rank {rank}] e2e: {e2e_total_ms / args.steps:.3f} ms/step")
     d2h_bytes = last[0]
     e2e_ms = e2e_total_ms / args.steps
     for cx in ctxs[1:]:
@@ -521,6 +530,7 @@ def bench_ours(args, rank, world, local_rank):
                     shutil.rmtree(wd, ignore_errors=True)
         except Exception as e:  # noqa: BLE001
             cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"failed: {e}"}
+    log("cpu_baseline / files_e2e legs done")
     if world == 1 and not args.no_other_configs:
         try:
             ctx.timing(True)
@@ -548,7 +558,7 @@ def bench_ours(args, rank, world, local_rank):
                               "frac": path_bytes / (ms_step * 1e-3) / 1e9 / peak / world, "note": "whole job, per GPU: bytes / step time / N / peak"}},
         "stage_ms": st, "rank_ms": rank_ms,
         "cpu_baseline": cpu, "files_e2e": files, "other_configs": others,
-        "merged": {"updated_transcripts": int(n_upd_total), "summary_counters": [int(x) for x in summary]},
+        "merged": {"updated_transcripts": int(n_upd_total), "summary_counters": [int(x) for x in summary], "rank0_diag": ctx.update_diag()},
     }
     print(json.dumps(out))
     if dist is not None:

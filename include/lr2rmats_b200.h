@@ -298,6 +298,9 @@ int64_t lrb_launch_count(const lrb_ctx *ctx);   /* kernels launched since ctx cr
 /* CUDA events on the ctx stream (the stream every kernel of this library is launched on): slot in [0,8) */
 int lrb_mark(lrb_ctx *ctx, int slot);
 int lrb_elapsed_ms(lrb_ctx *ctx, int slot_from, int slot_to, float *ms);   /* synchronises on slot_to */
+/* Diagnostics of the last lrb_update_run: split pieces that were absorbed by an entry on ANOTHER chromosome (the reference's
+ * back-scan of a piece never stops, update_gtf.c:148; settled in rounds on the device) and folds replayed as one locus. */
+int lrb_update_diag(const lrb_ctx *ctx, int64_t *pieces_across_chromosomes, int64_t *one_locus_replays);
 /* pinned host memory for record batches (what the host decoder fills) */
 void *lrb_host_alloc(size_t bytes);
 void lrb_host_free(void *p);

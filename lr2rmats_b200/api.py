@@ -23,7 +23,7 @@ ENTRY_POINTS = [
     "lrb_update_gtf", "lrb_unique_gtf", "lrb_timing_enable", "lrb_timing_get", "lrb_launch_count", "lrb_shard_cuts",
     "lrb_mark", "lrb_elapsed_ms", "lrb_host_alloc", "lrb_host_free", "lrb_update_fetch_table", "lrb_filter_fetch_keep",
     "lrb_comm_id", "lrb_comm_init", "lrb_comm_destroy", "lrb_comm_rank", "lrb_tables_broadcast", "lrb_update_gather", "lrb_gather_fetch",
-    "lrb_gather_timing", "lrb_shard_cuts_weighted",
+    "lrb_gather_timing", "lrb_shard_cuts_weighted", "lrb_update_diag",
 ]
 
 T_NAMES = ["filter", "exon", "classify", "merge", "summary", "k_scan", "k_fold"]
@@ -91,6 +91,7 @@ def load_library():
     L.lrb_update_gather.argtypes = [vp, C.c_int64]
     L.lrb_gather_fetch.argtypes = [vp, P(cabi.TransTable), P(cabi.BedList), P(C.c_int32 * cabi.S_COUNT)]
     L.lrb_gather_timing.argtypes = [vp, P(C.c_float), P(C.c_float)]
+    L.lrb_update_diag.argtypes = [vp, P(C.c_int64), P(C.c_int64)]
     _lib = L
     return L
 
@@ -241,6 +242,10 @@ class Context:
 
     def gather_timing(self):
         a = C.c_float(); b = C.c_float(); self._ck(self.L.lrb_gather_timing(self.h, C.byref(a), C.byref(b))); return float(a.value), float(b.value)
+
+    def update_diag(self):
+        a = C.c_int64(); b = C.c_int64(); self._ck(self.L.lrb_update_diag(self.h, C.byref(a), C.byref(b)))
+        return dict(pieces_across_chromosomes=int(a.value), one_locus_replays=int(b.value))
 
     # ---- measurement
     def timing(self, on=True): self._ck(self.L.lrb_timing_enable(self.h, 1 if on else 0))

@@ -120,7 +120,7 @@ DMerged merged_view(Buf &cand, Buf &cov, Buf &tid, Buf &st, Buf &en, Buf &fs, Bu
 // compacted into m.o_*.  totals[0] <- number of loci, totals[1] <- number of survivors (device).
 int run_merge_async(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_cand, const uint64_t *n_cand_dev, const lrb_update_params &up,
                     uint64_t *totals, const uint8_t *kls = nullptr, uint32_t *class_alive = nullptr, bool time_fold = false, bool side = false,
-                    bool single_locus = false)
+                    bool single_locus = false, bool xl = false)
 {
     int rc;
     cudaStream_t st = side ? c->st2 : c->st;
@@ -142,10 +142,21 @@ int run_merge_async(lrb_ctx *c, MergeBufs &m, const DTransList &list, int64_t n_
     a.cd.hash = m.c_hash.as<uint64_t>(); a.cd.j0 = m.c_j0.as<uint64_t>(); a.cd.sig = m.c_sig.as<uint64_t>();
     a.tile_state = side ? c->tile_state2.as<uint64_t>() : c->tile_state.as<uint64_t>(); a.ticket = side ? d_ticket2(c) : d_ticket(c); a.totals = totals;
     a.kls = kls; a.class_alive = class_alive; a.single_locus = single_locus ? 1 : 0;
+    if (xl) {
+        // split pieces that meet another chromosome (xl_* kernels): marks per candidate, a key set sized for the pieces' junctions
+        // (pieces are a small share of the candidates), lists in buffers the fold is done with by then
+        const uint64_t tcap = std::max<uint64_t>(1u << 16, (uint64_t)n_cand / 2);
+        NEED(c->xl_key, tcap * 8); NEED(c->xl_min, tcap * 4); NEED(c->xl_max, tcap * 4); NEED(c->xl_cnt, 64);
+        a.forced = c->xl_forced.as<uint8_t>();
+        c->xl = XlArgs{c->xl_key.as<unsigned long long>(), c->xl_min.as<uint32_t>(), c->xl_max.as<uint32_t>(), tcap, a.clist, a.lstart, (uint32_t)std::min<int64_t>(n_cand, 1 << 20),
+                       a.relsym, c->xl_cnt.as<uint32_t>()};
+    }
+    m.args = a;
     launch_merge_prepare(a, st);
     if (time_fold) tick(c, 10);
     launch_merge_fold(a, st);                        // locus count is consumed on the device: no host round trip
     if (time_fold) tick(c, 11);
+    if (xl) launch_xlocus_detect(a, c->xl, st);
     if (kls) launch_merge_class_counts(a, st);
     else launch_merge_finish(a, st);
     CK(cudaGetLastError());
@@ -220,7 +231,7 @@ void lrb_ctx_destroy(lrb_ctx *c)
                    &c->t_row, &c->t_lo, &c->t_cnt, &c->t_piece, &c->h_khi, &c->h_klo, &c->h_min, &c->h_score, &c->y_barcnt, &c->y_barseg, &c->y_genebar,
                    &c->y_bedcnt, &c->y_bedoff, &c->y_counts, &c->y_nelem, &c->bd_tid, &c->bd_s, &c->bd_e, &c->bd_sc, &c->bd_ty, &c->bd_rv, &c->q_shared, &c->tb_name, &c->tb_piece, &c->tb_ttid, &c->tb_tstart, &c->tb_tend, &c->tb_trev, &c->tb_etid, &c->tb_erev, &c->tb_cov, &c->tb_ref, &c->tb_cnt, &c->tb_off, &c->tb_es, &c->tb_ee, &c->tb_flag,
                    &c->s_read, &c->s_rtid, &c->s_rs, &c->s_re, &c->s_rev, &c->s_beg, &c->s_n, &c->s_key0, &c->s_key1, &c->s_idx0, &c->s_idx1, &c->s_hist,
-                   &c->tile_state, &c->tile_state2, &c->scalars, &c->kg_pairs};
+                   &c->tile_state, &c->tile_state2, &c->scalars, &c->kg_pairs, &c->xl_key, &c->xl_min, &c->xl_max, &c->xl_cnt, &c->xl_forced};
     for (Buf *b : bufs) b->release();
     for (MergeBufs *m : {&c->mg, &c->mg2}) {
         Buf *w[] = {&m->keys, &m->head, &m->locus_start, &m->locus_cnt, &m->dropped, &m->rep, &m->lstart, &m->evmask, &m->samemask, &m->hard, &m->desc, &m->relsym, &m->ckey, &m->cmin, &m->cord, &m->clist, &m->crow, &m->w_cand, &m->w_cov, &m->w_tid, &m->w_start, &m->w_end, &m->w_fs,
@@ -543,8 +554,12 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
     // necessary condition (a junction of a piece that also exists on another chromosome, CNT_XLOCUS) and the fold is then replayed
     // once more as ONE locus (merge_fold_kernel: the exact back-scan, entry by entry).  With -d > 0 junctions match approximately and
     // the exact-key probe proves nothing: any surviving piece sends the fold to the replay.
-    const bool detect = up->split_trans != 0, run_sets = up->want_summary || detect;
+    // With the default exact matching (-d 0, no -D) that is settled in rounds on the device (xl_* kernels in lrb_update.cu): exact and
+    // cheap.  The one-locus replay remains for -d > 0 / -D, where check_iden depends on the entries' moving ends.
+    const bool xl_exact = up->split_trans != 0 && up->ss_dis == 0 && up->end_dis == 0x7fffffff && !c->force_single_fold;
+    const bool detect = up->split_trans != 0 && !xl_exact, run_sets = up->want_summary || detect;
     bool single = c->force_single_fold;
+    c->n_xlocus_pieces = 0;
     for (int fold_pass = 0; fold_pass < 2; ++fold_pass) {
     SummaryArgs sa{};
     int64_t n_novel = 0, nu = 0; uint64_t n_elem = 0, n_exon_elem = 0;
@@ -574,13 +589,14 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
             if (side) CK(cudaEventRecord(c->ev_join, c->st2));
         }
         // updated_T = merge fold over novel_T (update_gtf.c:949,956)
-        if ((rc = run_merge_async(c, c->mg, c->novel, cap, T + T_NOVEL, *up, T + T_LOCI, nullptr, nullptr, true, false, single))) return rc;
+        if (xl_exact) { NEED(c->xl_forced, (size_t)std::max<int64_t>(cap, 1)); CK(cudaMemsetAsync(c->xl_forced.p, 0, (size_t)std::max<int64_t>(cap, 1), c->st)); }
+        if ((rc = run_merge_async(c, c->mg, c->novel, cap, T + T_NOVEL, *up, T + T_LOCI, nullptr, nullptr, true, false, single, xl_exact))) return rc;
         if (attempt == 0 && fold_pass == 0) tick(c, 3);
         if (run_sets) {
             // sets over updated_T: element count (sizes the hash table)
             const size_t capn = (size_t)std::max<int64_t>(cap, 1);
             NEED(c->y_barcnt, capn * 16); NEED(c->y_barseg, capn * 16); NEED(c->y_genebar, capn * 8); NEED(c->y_bedcnt, capn * 4); NEED(c->y_bedoff, capn * 4);
-            sa = SummaryArgs{}; sa.sets = up->want_summary ? SUM_ALL : 0;
+            sa = SummaryArgs{}; sa.sets = up->want_summary ? SUM_ALL : 0; sa.probe = detect ? 1 : 0;
             sa.rows = rows; sa.ex = c->ex; sa.list = c->novel; sa.n_upd = cap; sa.n_upd_dev = T + T_UPD;
             sa.upd = merged_view(c->mg.o_cand, c->mg.o_cov, c->mg.o_tid, c->mg.o_start, c->mg.o_end, c->mg.o_fs, c->mg.o_le, cap);
             sa.ref = c->u_ref.as<int32_t>(); sa.anno_gene = c->anno.gene;
@@ -595,9 +611,11 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
         CK(cudaMemcpyAsync(hp, c->scalars.p, T_SLOTS * 8 + 8, cudaMemcpyDeviceToHost, c->st));
         CK(cudaMemcpyAsync(hp + 320, c->y_counts.p, 64, cudaMemcpyDeviceToHost, c->st));
         CK(cudaMemcpyAsync(hp + 384, c->y_nelem.p, 16, cudaMemcpyDeviceToHost, c->st));
+        if (xl_exact) CK(cudaMemcpyAsync(hp + 400, c->xl_cnt.p, XL_NCNT * 4, cudaMemcpyDeviceToHost, c->st));
         CK(cudaStreamSynchronize(c->st));
-        uint64_t t[T_SLOTS]; uint32_t e[2];
+        uint64_t t[T_SLOTS]; uint32_t e[2], xc[XL_NCNT] = {0};
         memcpy(t, hp, sizeof t); memcpy(e, hp + T_SLOTS * 8, 8); memcpy(cnt16, hp + 320, 64); memcpy(&n_elem, hp + 384, 8); memcpy(&n_exon_elem, hp + 392, 8);
+        if (xl_exact) memcpy(xc, hp + 400, sizeof xc);
         if (e[1] & 3u) {
             // the class folds may still be running on the side stream: they must be over before the caller can start another
             // stage on this context (they share its buffers and counters)
@@ -613,8 +631,38 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
             continue;
         }
         c->mg.n_loci = (int64_t)t[T_LOCI]; c->mg.n_out = nu = (int64_t)t[T_UPD];
+        if (xl_exact && (xc[XL_OVERFLOW] || xc[XL_CHANGED])) {
+            // some piece is absorbed by an entry on another chromosome: fold again with the marks until they are stable (round k fixes
+            // the k-th affected piece at the latest), then let the absorbing entries take cov / ends, compact and count again
+            int rounds = 0;
+            while (!xc[XL_OVERFLOW] && xc[XL_CHANGED] && rounds < 32) {
+                ++rounds;
+                launch_xlocus_reset(c->mg.args, c->xl, c->st);
+                launch_merge_fold(c->mg.args, c->st);
+                launch_xlocus_detect(c->mg.args, c->xl, c->st);
+                CK(cudaMemcpyAsync(hp + 400, c->xl_cnt.p, XL_NCNT * 4, cudaMemcpyDeviceToHost, c->st));
+                CK(cudaStreamSynchronize(c->st));
+                memcpy(xc, hp + 400, sizeof xc);
+            }
+            if (xc[XL_OVERFLOW] || xc[XL_CHANGED]) {                 // more hits than the lists hold, or no fixed point in 32 rounds: the exact replay
+                if (up->want_summary && c->side_stream) CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
+                single = true; c->n_xlocus_replays++; n_novel = -1; break;
+            }
+            c->n_xlocus_pieces = xc[XL_NFORCED];
+            launch_xlocus_apply(c->mg.args, c->xl, c->st);
+            CK(cudaMemsetAsync(T + T_UPD, 0, 8, c->st));
+            launch_merge_finish(c->mg.args, c->st);
+            if (run_sets) { CK(cudaMemsetAsync(c->y_nelem.p, 0, 16, c->st)); launch_summary_count(sa, c->y_nelem.as<unsigned long long>(), c->st); }
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(hp, c->scalars.p, T_SLOTS * 8 + 8, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaMemcpyAsync(hp + 384, c->y_nelem.p, 16, cudaMemcpyDeviceToHost, c->st));
+            CK(cudaStreamSynchronize(c->st));
+            memcpy(t, hp, sizeof t); memcpy(&n_elem, hp + 384, 8); memcpy(&n_exon_elem, hp + 392, 8);
+            c->mg.n_out = nu = (int64_t)t[T_UPD];
+        }
         break;
     }
+    if (n_novel < 0) continue;                                        // the marks did not settle: once more as ONE locus
     if (n == 0) { if ((rc = setup_list(c, c->novel, c->n_row, c->n_lo, c->n_cnt, c->n_piece, 0))) return rc; c->mg.n_out = c->mg.n_loci = 0; tick(c, 2); tick(c, 3); }
     c->novel.n = n_novel; c->novel.cap = std::max<int64_t>(cap, 0);
     if (c->timing && n && fold_pass == 0) { CK(cudaStreamSynchronize(c->st)); cudaEventElapsedTime(&c->ms[LRB_T_K_FOLD], c->ev[10], c->ev[11]); }
@@ -1075,6 +1123,13 @@ int lrb_elapsed_ms(lrb_ctx *c, int a, int b, float *ms)
     CK(cudaSetDevice(c->device));
     CK(cudaEventSynchronize(c->marks[b]));
     CK(cudaEventElapsedTime(ms, c->marks[a], c->marks[b]));
+    return LRB_OK;
+}
+int lrb_update_diag(const lrb_ctx *c, int64_t *pieces, int64_t *replays)
+{
+    if (!c) return LRB_E_ARG;
+    if (pieces) *pieces = c->n_xlocus_pieces;
+    if (replays) *replays = c->n_xlocus_replays;
     return LRB_OK;
 }
 void *lrb_host_alloc(size_t bytes) { void *p = nullptr; if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }

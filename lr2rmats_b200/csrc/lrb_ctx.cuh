@@ -46,6 +46,7 @@ struct MergeBufs {                                  // scratch + output of one m
     Buf o_cand, o_cov, o_tid, o_start, o_end, o_fs, o_le;
     Buf c_tid, c_start, c_end, c_rev, c_n, c_fs, c_le, c_gbeg, c_hash, c_j0, c_sig;
     int64_t n_out = 0, n_loci = 0;
+    MergeArgs args;                                 // of the last fold (refolds of the split-piece rounds reuse them)
 };
 
 struct MultiState;                                  // lrb_multi.cu
@@ -87,7 +88,8 @@ struct lrb_ctx {
     MergeBufs mg, mg2;
     int64_t n_known = 0, n_unrecog = 0, novel_cap_hint = 0; bool have_update = false, have_unique = false;
     int32_t summary[LRB_S_COUNT];
-    bool force_single_fold = false, xlocus_seen = false, want_kg_pairs = false; int64_t n_xlocus_replays = 0, n_kg_pairs = 0; Buf kg_pairs;
+    bool force_single_fold = false, xlocus_seen = false, want_kg_pairs = false; int64_t n_xlocus_replays = 0, n_xlocus_pieces = 0, n_kg_pairs = 0; Buf kg_pairs;
+    Buf xl_key, xl_min, xl_max, xl_cnt, xl_forced; lrbk::XlArgs xl;      // split pieces that meet another chromosome (xl_* kernels)
     // summary
     Buf h_khi, h_klo, h_min, h_score, y_barcnt, y_barseg, y_genebar, y_bedcnt, y_bedoff, y_counts, y_nelem;
     Buf bd_tid, bd_s, bd_e, bd_sc, bd_ty, bd_rv; int64_t n_bed = 0;

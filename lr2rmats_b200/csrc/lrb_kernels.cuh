@@ -142,8 +142,20 @@ struct MergeArgs {
     uint8_t *cord; uint32_t *clist; uint64_t *crow;  // big loci: class ordinal per candidate; per locus (at its offset) the class representatives and their 128-bit relation rows
     uint64_t *ckey; uint32_t *cmin;                 // class table of the big loci: 2 * n_cand + 64 slots (NULL: big loci go to merge_fold_kernel)
     DMerged out;                                    // compacted result
+    uint8_t *forced;                                // optional (split pieces, see XlArgs): 1 = this piece is absorbed by an entry of an earlier locus when its own locus has nothing for it (3: that happened in the last fold)
     uint64_t *tile_state; uint32_t *ticket; uint64_t *totals;  // [0] n_loci, [1] n_out
 };
+// split pieces that meet another chromosome (lrb_update.cu, xl_* kernels)
+enum { XL_NPL = 0, XL_NHX = 1, XL_CHANGED = 2, XL_NFORCED = 3, XL_OVERFLOW = 4, XL_NCNT = 8 };
+struct XlArgs {
+    unsigned long long *tkey; uint32_t *tmin, *tmax; uint64_t tcap;   // key set of the pieces' junctions with the range of chromosomes that own each
+    uint32_t *pl, *hx; uint32_t hx_cap;             // piece list, hit list (surviving entries that share a key with a piece of another chromosome)
+    uint64_t *best;                                 // per candidate: (absorbing entry + 1) << 2 | 1 identical / 2 partial
+    uint32_t *cnt;                                  // XL_* counters (device)
+};
+void launch_xlocus_detect(const MergeArgs &a, const XlArgs &x, cudaStream_t st);    // after launch_merge_fold, before launch_merge_finish
+void launch_xlocus_apply(const MergeArgs &a, const XlArgs &x, cudaStream_t st);
+void launch_xlocus_reset(const MergeArgs &a, const XlArgs &x, cudaStream_t st);     // before the fold runs again with new marks
 void launch_merge_prepare(MergeArgs a, cudaStream_t st);            // candidates, locus heads, locus_start; totals[0] = number of loci
 void launch_merge_fold(const MergeArgs &a, cudaStream_t st);        // number of loci is read from a.totals[0] on the device
 void launch_merge_class_counts(const MergeArgs &a, cudaStream_t st);

@@ -317,7 +317,7 @@ int lrb_update_gather(lrb_ctx *c, int64_t name_base)
         sa.ref = m->g_ref.as<int32_t>(); sa.anno_gene = c->anno.gene; sa.n_upd = N;
         sa.bar_cnt = m->y_barcnt.as<uint32_t>(); sa.bar_seg = m->y_barseg.as<uint32_t>(); sa.gene_bar = m->y_genebar.as<uint64_t>();
         sa.bed_cnt = m->y_bedcnt.as<uint32_t>(); sa.bed_off = m->y_bedoff.as<uint32_t>(); sa.counts = m->y_counts.as<uint32_t>();
-        sa.shard_end = m->shard_end_dev.as<int64_t>(); sa.n_shards = R;
+        sa.shard_end = m->shard_end_dev.as<int64_t>(); sa.n_shards = R; sa.probe = detect ? 1 : 0;
         // pieces anywhere: their tid-0 site / junction keys may coincide across shards (probe needs those elements in the table)
         const bool pieces = partial > 0 || detect;
         for (int pass = 0; pass < 2; ++pass) {

@@ -101,7 +101,7 @@ __global__ void sum_count_kernel(SummaryArgs a, unsigned long long *n_elems)
             if (j < e.n - 1 && (a.sets & SUM_DAJ)) c += ((x & LRB_F_NOVEL_DON) != 0) + ((x & LRB_F_NOVEL_ACC) != 0) + ((x & LRB_F_NOVEL_JUNC) != 0);
         }
         c += cx;
-        if (e.piece >= 0 && gl == 0) c += e.n;      // the junction keys of a split piece (cross-chromosome probe of phase 1 / 2)
+        if (a.probe && e.piece >= 0 && gl == 0) c += e.n;      // the junction keys of a split piece (cross-chromosome / cross-shard probe of phase 1 / 2)
     }
     for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(FULL, c, o); cx += __shfl_xor_sync(FULL, cx, o); }
     if (lane_id() == 0 && c) { atomicAdd(n_elems, (unsigned long long)c); if (cx) atomicAdd(n_elems + 1, (unsigned long long)cx); }
@@ -158,7 +158,7 @@ __global__ void sum_phase1_kernel(SummaryArgs a, int parts)
         // phase 2 lets every entry probe them: a hit across chromosomes raises CNT_XLOCUS and the fold is replayed as one locus.
         atomicAdd(&a.counts[CNT_PARTIAL], 1u);       // partial-read transcripts
         const int grp = xl_group(a, e, i);
-        for (int j = 0; j < e.n - 1; ++j) {
+        for (int j = 0; j < e.n - 1 && a.probe; ++j) {
             const uint64_t s = tab_upsert(a.tab, key_hi(SET_PJ, 0, 0), key_lo(ent_e(a, e, j), ent_s(a, e, j + 1)));
             atomicMin((unsigned long long *)&a.tab.slots[s].minpos, (unsigned long long)(uint32_t)grp); atomicMax(&a.tab.slots[s].pad, grp);
             if (j == 0) {
@@ -195,7 +195,7 @@ __global__ void sum_phase2_kernel(SummaryArgs a, int parts)
         uint64_t s = tab_find(a.tab, key_hi(SET_G, SEG_TID0, 0), key_lo(e.gene, 0));
         cg = a.tab.slots[s].minpos == pos_of(i, 0);
     }
-    if (gl == 0 && e.n > 1 && a.counts[CNT_PARTIAL] != 0) {
+    if (a.probe && gl == 0 && e.n > 1 && a.counts[CNT_PARTIAL] != 0) {
         // cross-chromosome meeting of a split piece (see phase 1): the first junction of this entry among the junctions of a
         // piece, or a junction of this entry equal to the first junction of a piece -- the necessary condition of check_iden != -1
         bool hit = false;

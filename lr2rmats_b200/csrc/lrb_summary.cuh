@@ -29,6 +29,7 @@ struct SummaryArgs {
     int2 *kg_pairs;
     // gather root: entry i belongs to shard k iff shard_end[k-1] <= i < shard_end[k] (device array); 0 shards = single-GPU run
     const int64_t *shard_end; int n_shards;
+    int probe;                                      // 1: the junction keys of split pieces are probed for a meeting with another chromosome / shard (CNT_XLOCUS)
 };
 enum { SUM_E = 1, SUM_DAJ = 2, SUM_G = 4, SUM_KG = 8, SUM_ALL = 15 };
 // counts[] slots of the summary kernels

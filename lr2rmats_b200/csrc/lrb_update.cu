@@ -858,6 +858,10 @@ __global__ void __launch_bounds__(MF_THREADS) merge_fold_kernel(MergeArgs a, uin
                 }
             }
             __syncwarp(gm);
+            if (result == 0 && a.forced && a.forced[c]) {             // absorbed by an entry of an earlier locus (xl_* below): not appended
+                if (gl == 0) a.forced[c] = 3;
+                result = 1;
+            }
             if (result == 0) {
                 if (gl == 0) {
                     tlist[ls + cnt] = (uint32_t)c; alive[c] = 1;
@@ -1132,6 +1136,10 @@ __global__ void __launch_bounds__(FB_THREADS) fold_big_kernel(MergeArgs a, const
                     }
                 }
                 __syncwarp(gm);
+                if (result == 0 && a.forced && a.forced[c0 + q]) {   // absorbed by an entry of an earlier locus (xl_* below): not appended
+                    if (lane == 0) a.forced[c0 + q] = 3;
+                    result = 1;
+                }
                 if (result == 0) {
                     if (cnt == SLOTS) { overflow = true; break; }
                     if (lane == 0) {
@@ -1478,6 +1486,8 @@ __global__ void __launch_bounds__(FS_THREADS) fold_seq_kernel(MergeArgs a, const
             s_cov[hit][t] += 1;                                       // <= 64 candidates per locus: fits a byte
             if (c_fs < s_fs[hit][t]) { s_fs[hit][t] = c_fs; s_flag[hit][t] &= ~1; }
             if (c_le > s_le[hit][t]) { s_le[hit][t] = c_le; s_flag[hit][t] &= ~2; }
+        } else if (kind == 0 && a.forced && a.forced[c]) {
+            a.forced[c] = 3; kind = 3;                                // absorbed by an entry of an earlier locus (see xl_* below): not appended
         } else if (kind == 0) {
             if (cnt == FS_SLOTS) { locus_hard[ls] = 1; return; }      // too many survivors for the slots: merge_fold_kernel redoes the locus
             alive |= 1ull << k;
@@ -1580,7 +1590,7 @@ void launch_merge_fold(const MergeArgs &a, cudaStream_t st)
             cudaMemsetAsync(next_locus, 0, 4, st);
             int64_t blb = (a.n_cand / (FF_MAX + 1) + 1) / (FB_THREADS / 8) + 1; if (blb > 148 * 3) blb = 148 * 3;
             static int fbg = -1;
-            if (fbg < 0) { const char *e = getenv("LRB_FB_G"); fbg = e ? atoi(e) : 8; }
+            if (fbg < 0) { const char *e = getenv("LRB_FB_G"); fbg = e ? atoi(e) : 32; }
             if (fbg == 16) {
                 auto k16 = fold_big_kernel<16, 96, 256, 0>; const size_t sm16 = sizeof(FbSlots<96, 256>) * (FB_THREADS / 16);
                 static bool a16 = false; if (!a16) { cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16); a16 = true; }
@@ -1615,6 +1625,144 @@ void launch_merge_fold(const MergeArgs &a, cudaStream_t st)
         merge_fold_kernel<32><<<(unsigned)bl, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, nullptr, 33, 0x7fffffff, 0);
         LRB_COUNT_LAUNCH();
     }
+}
+
+// ------------------------------------------------------------------------------ split pieces that meet ANOTHER chromosome
+// A split piece carries tid = start = end = 0, so its back-scan in merge_trans never stops (update_gtf.c:148): after the
+// entries of its own locus it walks ALL earlier entries of updated_T, on every chromosome, and the first one with check_iden != -1
+// absorbs it.  The locus-parallel fold cannot see that.  It is settled in rounds instead:
+//   detect   after a fold: the junctions of the surviving (or already forced) pieces go into a small key set; every surviving entry
+//            probes it (its first junction among a piece's junctions / a piece's first junction among its own: the necessary condition
+//            of gtf.c:61-91); the few hits are joined with the pieces and check_iden is evaluated exactly; best[p] = nearest earlier
+//            entry on another chromosome that absorbs p;
+//   force    pieces with such an entry are marked; if the marks changed, the fold runs again with them: a marked piece that finds
+//            nothing in its own locus is NOT appended (and no longer a barrier there);
+//   apply    once the marks are stable: the absorbing entries take cov / first start / last end as merge_trans1 would (update_gtf.c:104-111).
+// What a piece meets depends only on earlier entries, so round k fixes the k-th affected piece at the latest.  Steady state (no piece
+// meets anything): one round, three small kernels.
+LRB_DEVINL uint64_t xl_key(uint32_t kind, uint32_t e, uint32_t s) { uint64_t k = mixh(mixh(0x51ED270B3Full + kind, e), s); return k == ~0ull ? 0x77ull : k; }
+LRB_DEVINL bool xl_upsert(const XlArgs &x, uint64_t k, uint32_t rt)
+{
+    uint64_t s = __umul64hi(k * 0x9E3779B97F4A7C15ull, x.tcap);
+    for (int probes = 0; probes < 4096; ++probes) {
+        const unsigned long long p = atomicCAS(&x.tkey[s], ~0ull, (unsigned long long)k);
+        if (p == ~0ull || p == k) { atomicMin(&x.tmin[s], rt); atomicMax(&x.tmax[s], rt + 1u); return true; }
+        s = s + 1 == x.tcap ? 0 : s + 1;
+    }
+    return false;
+}
+LRB_DEVINL bool xl_other_chrom(const XlArgs &x, uint64_t k, uint32_t rt)      // is the key owned by a piece of another chromosome?
+{
+    uint64_t s = __umul64hi(k * 0x9E3779B97F4A7C15ull, x.tcap);
+    for (int probes = 0; probes < 4096; ++probes) {
+        const unsigned long long p = x.tkey[s];
+        if (p == ~0ull) return false;
+        if (p == k) return x.tmin[s] != rt || x.tmax[s] != rt + 1u;
+        s = s + 1 == x.tcap ? 0 : s + 1;
+    }
+    return true;
+}
+__global__ void __launch_bounds__(256) xl_insert_kernel(MergeArgs a, XlArgs x, const uint8_t *__restrict__ alive)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cand_count(a) || a.list.piece[c] < 0) return;
+    const int n = a.cd.n[c];
+    if (n < 2 || !(alive[c] || a.forced[c])) return;
+    const uint32_t i = atomicAdd(&x.cnt[XL_NPL], 1u);
+    x.pl[i] = (uint32_t)c; x.best[c] = 0;
+    const uint32_t g = a.cd.gbeg[c], rt = (uint32_t)a.rows.tid[a.list.row[c]];
+    bool ok = true;
+    for (int j = 0; j < n - 1; ++j) {
+        const uint32_t e = (uint32_t)a.ex.ee[g + j], s = (uint32_t)a.ex.es[g + j + 1];
+        ok = ok && xl_upsert(x, xl_key(0, e, s), rt);
+        if (j == 0) ok = ok && xl_upsert(x, xl_key(1, e, s), rt);
+    }
+    if (!ok) x.cnt[XL_OVERFLOW] = 1u;
+}
+__global__ void __launch_bounds__(256) xl_probe_kernel(MergeArgs a, XlArgs x, const uint8_t *__restrict__ alive)
+{
+    if (x.cnt[XL_NPL] == 0) return;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cand_count(a) || !alive[c]) return;
+    const int n = a.cd.n[c];
+    if (n < 2) return;
+    const uint32_t g = a.cd.gbeg[c], rt = (uint32_t)a.rows.tid[a.list.row[c]];
+    bool hit = xl_other_chrom(x, xl_key(0, (uint32_t)a.ex.ee[g], (uint32_t)a.ex.es[g + 1]), rt);
+    for (int j = 0; j < n - 1 && !hit; ++j) hit = xl_other_chrom(x, xl_key(1, (uint32_t)a.ex.ee[g + j], (uint32_t)a.ex.es[g + j + 1]), rt);
+    if (!hit) return;
+    const uint32_t k = atomicAdd(&x.cnt[XL_NHX], 1u);
+    if (k < x.hx_cap) x.hx[k] = (uint32_t)c; else x.cnt[XL_OVERFLOW] = 1u;
+}
+// pieces x hits: exact check_iden of the piece against the surviving entry (dynamic first start / last end of the entry)
+__global__ void __launch_bounds__(256) xl_join_kernel(MergeArgs a, XlArgs x)
+{
+    const uint32_t n_pl = x.cnt[XL_NPL], n_hx = min(x.cnt[XL_NHX], x.hx_cap);
+    const CandSoA &cd = a.cd;
+    for (uint32_t h = blockIdx.y; h < n_hx; h += gridDim.y) {
+        const uint32_t e = x.hx[h];
+        const int e_tid = a.rows.tid[a.list.row[e]];
+        const Entry E = {cd.n[e], cd.gbeg[e], a.work.fs[e], a.work.le[e], cd.hash[e], cd.rev[e] & 2, cd.j0[e], cd.sig[e]};
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pl; i += gridDim.x * blockDim.x) {
+            const uint32_t p = x.pl[i];
+            if (e >= p || a.rows.tid[a.list.row[p]] == e_tid) continue;          // only EARLIER entries, and its own chromosome is the fold's business
+            if (a.up.force_strand && ((cd.rev[e] ^ cd.rev[p]) & 1)) continue;    // pieces carry is_rev 0 in cd.rev (update_gtf.c:149)
+            const Entry P = {cd.n[p], cd.gbeg[p], cd.fs[p], cd.le[p], cd.hash[p], cd.rev[p] & 2, cd.j0[p], cd.sig[p]};
+            const int r = chain_iden(a.ex, P, E, 0, a.up.end_dis);
+            if (r == 0 || r == 2) atomicMax((unsigned long long *)&x.best[p], ((unsigned long long)(e + 1u) << 2) | (r == 0 ? 1ull : 2ull));
+        }
+    }
+}
+__global__ void __launch_bounds__(256) xl_force_kernel(MergeArgs a, XlArgs x)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= x.cnt[XL_NPL]) return;
+    const uint32_t p = x.pl[i];
+    const bool want = x.best[p] != 0, is = a.forced[p] != 0;
+    if (want != is) { a.forced[p] = want ? 1 : 0; atomicAdd(&x.cnt[XL_CHANGED], 1u); }     // else: 3 (absorbed across chromosomes in the fold that just ran) stays for xl_apply
+    if (want) atomicAdd(&x.cnt[XL_NFORCED], 1u);
+}
+// before a fold runs again: "absorbed across chromosomes in the last fold" (3) is history
+__global__ void __launch_bounds__(256) xl_reset_kernel(MergeArgs a, XlArgs x)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < x.cnt[XL_NPL] && a.forced[x.pl[i]] == 3) a.forced[x.pl[i]] = 1;
+}
+void launch_xlocus_reset(const MergeArgs &a, const XlArgs &x, cudaStream_t st)
+{
+    if (a.n_cand <= 0) return;
+    xl_reset_kernel<<<(unsigned)((a.n_cand / 16 + 255) / 256 + 1), 256, 0, st>>>(a, x); LRB_COUNT_LAUNCH();
+}
+// the marks are stable: entries that absorbed a piece by identity take cov + 1 and the piece's ends (merge_trans1, update_gtf.c:104-111)
+__global__ void __launch_bounds__(256) xl_apply_kernel(MergeArgs a, XlArgs x, int pass)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= x.cnt[XL_NPL]) return;
+    const uint32_t p = x.pl[i];
+    if (a.forced[p] != 3 || (x.best[p] & 3ull) != 1ull) return;                  // absorbed inside its locus after all / dropped as a partial match
+    const uint32_t e = (uint32_t)(x.best[p] >> 2) - 1u;
+    if (pass == 0) { atomicAdd(&a.work.cov[e], 1); atomicMin(&a.work.fs[e], a.cd.fs[p]); atomicMax(&a.work.le[e], a.cd.le[p]); }
+    else {                                           // T.start / T.end follow an extension (:108-111); equal values race benignly
+        if (a.work.fs[e] < a.cd.fs[e]) a.work.start[e] = a.work.fs[e];
+        if (a.work.le[e] > a.cd.le[e]) a.work.end[e] = a.work.le[e];
+    }
+}
+void launch_xlocus_detect(const MergeArgs &a, const XlArgs &x, cudaStream_t st)
+{
+    if (a.n_cand <= 0) return;
+    cudaMemsetAsync(x.tkey, 0xFF, x.tcap * 8, st); cudaMemsetAsync(x.tmin, 0xFF, x.tcap * 4, st); cudaMemsetAsync(x.tmax, 0, x.tcap * 4, st);
+    cudaMemsetAsync(x.cnt, 0, XL_NCNT * 4, st);
+    const unsigned bl = (unsigned)((a.n_cand + 255) / 256);
+    xl_insert_kernel<<<bl, 256, 0, st>>>(a, x, a.dropped); LRB_COUNT_LAUNCH();
+    xl_probe_kernel<<<bl, 256, 0, st>>>(a, x, a.dropped); LRB_COUNT_LAUNCH();
+    xl_join_kernel<<<dim3(64, 64), 256, 0, st>>>(a, x); LRB_COUNT_LAUNCH();
+    int64_t blp = (a.n_cand / 16 + 255) / 256 + 1;                   // pieces are a small share of the candidates; the kernel checks the true count
+    xl_force_kernel<<<(unsigned)blp, 256, 0, st>>>(a, x); LRB_COUNT_LAUNCH();
+}
+void launch_xlocus_apply(const MergeArgs &a, const XlArgs &x, cudaStream_t st)
+{
+    if (a.n_cand <= 0) return;
+    int64_t blp = (a.n_cand / 16 + 255) / 256 + 1;
+    for (int pass = 0; pass < 2; ++pass) { xl_apply_kernel<<<(unsigned)blp, 256, 0, st>>>(a, x, pass); LRB_COUNT_LAUNCH(); }
 }
 
 __global__ void __launch_bounds__(256) merge_class_counts_kernel(MergeArgs a, const uint8_t *__restrict__ alive)

@@ -493,3 +493,5 @@ def test_cross_chromosome_piece_replay(ctx, summary):
     # the case is live: at least one piece of a clone chromosome was absorbed by an original (cov > 1 on a piece)
     upd = gu["updated"]; piece = gu["novel"]["piece"][upd["cand"]]
     assert ((piece >= 0) & (upd["cov"] > 1)).sum() > 0
+    d = ctx.update_diag()
+    assert d["pieces_across_chromosomes"] > 0, d         # settled by the rounds on the device, not by the one-locus replay

@@ -307,7 +307,7 @@ def bench_ours(args, rank, world, local_rank):
     from lr2rmats_b200 import api, cabi
     dist = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")         # keeps NCCL's version banner off stdout (the JSON line is the only stdout)
+
         import torch.distributed as dist_
         dist = dist_
         torch.cuda.set_device(local_rank)

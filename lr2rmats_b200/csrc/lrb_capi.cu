@@ -206,6 +206,7 @@ int lrb_ctx_create(int device, lrb_ctx **out)
     cudaEventCreateWithFlags(&c->ev_fork3, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join3, cudaEventDisableTiming);
     { const char *e = getenv("LRB_SUM_SPLIT"); if (e) c->sum_split = atoi(e) != 0; }
     { const char *e = getenv("LRB_SIDE_STREAM"); if (e) c->side_stream = atoi(e) != 0; }
+    { const char *e = getenv("LRB_TEST_SMALL_NOVEL_CAP"); if (e) c->test_small_novel_cap = atoi(e) != 0; }      // test hook: novel_T sized too small on the first attempt
     { const char *e = getenv("LRB_FORCE_SINGLE_FOLD"); if (e) c->force_single_fold = atoi(e) != 0; }    // test hook: updated_T always folded by the one-locus replay
     if (!c->scalars.ensure(512) || !c->h_scalars.ensure(512)) { delete c; return LRB_E_NOMEM; }
     cudaMemsetAsync(c->scalars.p, 0, 512, c->st);
@@ -549,6 +550,7 @@ int lrb_update_run(lrb_ctx *c, const lrb_update_params *up)
     uint64_t *T = d_totals(c);
     int64_t cap = up->split_trans ? n + n / 8 + 1024 : n;
     cap = std::max<int64_t>(cap, std::min<int64_t>(c->novel_cap_hint, n + c->ex.n / 2 + 1));
+    if (c->test_small_novel_cap) cap = std::max<int64_t>(1, n / 4);   // test hook: forces the undersized-list retry
     // A split piece scans the WHOLE of updated_T in the reference (its tid/start/end are 0: update_gtf.c:148 never stops it), so it
     // can be absorbed by a chain on another chromosome.  The locus-parallel fold cannot see that; the set kernels probe for the
     // necessary condition (a junction of a piece that also exists on another chromosome, CNT_XLOCUS) and the fold is then replayed

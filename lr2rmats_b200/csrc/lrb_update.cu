@@ -660,7 +660,9 @@ LRB_DEVINL uint64_t mixh(uint64_t h, uint32_t v) { h ^= v; h *= 0x9E3779B97F4A7C
 LRB_DEVINL int junc_bit(uint64_t jk) { jk *= 0xD6E8FEB86659FD93ull; return (int)(jk >> 58); }
 
 // (clamped to the host bound: an undersized list is detected and redone by the host, the kernels must only stay in bounds)
-LRB_DEVINL int64_t cand_count(const MergeArgs &a) { return a.n_cand_dev ? min((int64_t)*a.n_cand_dev, a.n_cand) : a.n_cand; }
+// (an undersized list -- more candidates on the device than the host's bound -- folds as EMPTY: its tail was never written, the host
+// sees the true count in the same round trip and repeats the pass with the exact size)
+LRB_DEVINL int64_t cand_count(const MergeArgs &a) { if (!a.n_cand_dev) return a.n_cand; const int64_t n = (int64_t)*a.n_cand_dev; return n > a.n_cand ? 0 : n; }
 
 // One pass over the candidates: flatten (CandSoA), running max of (tid,end) across tiles (look-back, max), locus heads
 // (a candidate that starts beyond every earlier end on its chromosome, App. B.3) and their compaction into locus_start

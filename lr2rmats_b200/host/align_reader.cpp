@@ -168,6 +168,7 @@ static bool bgzf_index(const Bytes &in, std::vector<BgzfBlock> &blocks)
         if (!bsize) return false;                                        // a gzip member without BC: not BGZF
         if (bsize < 12 + xlen + 8 || in.size() - p < bsize) break;       // truncated block
         BgzfBlock k; k.in_off = p; k.hdr = 12 + xlen; k.in_len = bsize; k.isize = (uint32_t)b[bsize - 4] | ((uint32_t)b[bsize - 3] << 8) | ((uint32_t)b[bsize - 2] << 16) | ((uint32_t)b[bsize - 1] << 24);
+        if (k.isize > 65536) break;                                      // a BGZF block inflates to at most 64 KiB: a damaged trailer ends the stream here
         k.out_off = out; out += k.isize;
         blocks.push_back(k);
         p += bsize;
@@ -190,7 +191,10 @@ static bool bgzf_inflate_mt(const Bytes &in, Bytes &out)
             zs.next_in = (Bytef *)in.data() + k.in_off + k.hdr; zs.avail_in = (uInt)(k.in_len - k.hdr - 8);
             zs.next_out = out.data() + k.out_off; zs.avail_out = k.isize;
             const int rc = k.isize || zs.avail_in ? inflate(&zs, Z_FINISH) : Z_STREAM_END;
-            if (rc != Z_STREAM_END || zs.avail_out != 0) { size_t cur = first_bad.load(); while (i < cur && !first_bad.compare_exchange_weak(cur, i)) {} break; }
+            const uint8_t *tr = (const uint8_t *)in.data() + k.in_off + k.in_len - 8;
+            const uint32_t want_crc = (uint32_t)tr[0] | ((uint32_t)tr[1] << 8) | ((uint32_t)tr[2] << 16) | ((uint32_t)tr[3] << 24);
+            const bool crc_ok = rc == Z_STREAM_END && (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef *)out.data() + k.out_off, k.isize) == want_crc;
+            if (rc != Z_STREAM_END || zs.avail_out != 0 || !crc_ok) { size_t cur = first_bad.load(); while (i < cur && !first_bad.compare_exchange_weak(cur, i)) {} break; }
             inflateReset(&zs);
         }
         inflateEnd(&zs);
@@ -255,15 +259,16 @@ static bool parse_bam(Bytes &d, Header &h, Records &r, std::string &err)
     const uint8_t *p = d.data(), *end = p + d.size();
     if (end - p < 12 || memcmp(p, "BAM\1", 4)) { err = "not a BAM stream"; return false; }
     int32_t l_text = rdi32(p + 4); p += 8;
-    if (p + l_text + 4 > end) { err = "truncated BAM header"; return false; }
+    if (l_text < 0 || (size_t)l_text + 4 > (size_t)(end - p)) { err = "truncated or damaged BAM header"; return false; }
     h.text.assign((const char *)p, (size_t)l_text);
     while (!h.text.empty() && h.text.back() == 0) h.text.pop_back();
     p += l_text;
     int32_t n_ref = rdi32(p); p += 4;
+    if (n_ref < 0) { err = "damaged BAM header (n_ref < 0)"; return false; }
     for (int i = 0; i < n_ref; ++i) {
-        if (p + 4 > end) { err = "truncated BAM header"; return false; }
+        if ((size_t)(end - p) < 4) { err = "truncated BAM header"; return false; }
         int32_t l_name = rdi32(p); p += 4;
-        if (p + l_name + 4 > end) { err = "truncated BAM header"; return false; }
+        if (l_name <= 0 || (size_t)l_name + 4 > (size_t)(end - p)) { err = "truncated or damaged BAM header"; return false; }
         std::string name((const char *)p, l_name > 0 ? (size_t)l_name - 1 : 0); p += l_name;
         h.add(name, rd32(p)); p += 4;
     }

@@ -4,6 +4,7 @@
 // bam2gtf's long names are exon-min / intron-len -- SURVEY.md App. A.5/A.9/D.1), defaults, output files and exit codes as
 // main.c:37-49, bam_filter.c:98-164, bam2gtf.c:120-161, update_gtf.c:995-1117, unique_gtf.c:86-158.  The per-alignment
 // work itself is done by the engine (the CUDA library in the product binary).
+#include <unistd.h>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
@@ -20,7 +21,9 @@ static void logf(const char *func, const char *msg)
     time_t raw; time(&raw); char buf[80]; strftime(buf, 80, "%m-%d-%Y %X", localtime(&raw));
     fprintf(stderr, "=== %s === [%s] %s", buf, func, msg);
 }
-[[noreturn]] static void fatal(const char *func, const std::string &msg) { fprintf(stderr, "[%s] %s\n", func, msg.c_str()); exit(EXIT_FAILURE); }
+// _exit, not exit: the CUDA context may still be under construction on the helper thread (main.cpp), and exit() would run the
+// runtime's static destructors underneath it
+[[noreturn]] static void fatal(const char *func, const std::string &msg) { fprintf(stderr, "[%s] %s\n", func, msg.c_str()); fflush(NULL); _exit(EXIT_FAILURE); }
 static void engine_fail(Engine &e, const char *func, int rc)
 {
     const char *m = e.error ? e.error(e.self) : nullptr;

@@ -455,6 +455,27 @@ def test_cli_sort_input(data, tmp_path):
 
 
 @pytest.mark.gpu
+def test_undersized_novel_list_is_retried(tmp_path):
+    """novel_T is sized optimistically (pieces are rare); when it turns out too small the fold must see an EMPTY list (its tail was never
+    written), and the pass is repeated with the exact size.  LRB_TEST_SMALL_NOVEL_CAP forces that on the first attempt."""
+    import subprocess
+    from lr2rmats_b200 import api
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "syn_iso")
+    outs = []
+    for small in ("0", "1"):
+        o = tmp_path / f"s{small}"; o.mkdir()
+        env = dict(os.environ, LRB_TEST_SMALL_NOVEL_CAP=small)
+        p = subprocess.run([api.CLI_PATH, "update-gtf", "-s", "-l", "3", "-J", "1", "-j", os.path.join(d, "sj.tab"), os.path.join(d, "in.sam"), os.path.join(d, "anno.gtf"),
+                            "-y", "summary.txt", "-E", "bed.bed", "-o", "updated.gtf", "-v", "novel.gtf"], cwd=o, env=env, stderr=subprocess.PIPE)
+        assert p.returncode == 0, p.stderr.decode()[-1000:]
+        outs.append({f: open(o / f, "rb").read() for f in ("summary.txt", "bed.bed", "updated.gtf", "novel.gtf")})
+    assert outs[0] == outs[1]
+    exp = os.path.join(d, "expected", "p2s")
+    for f, g in (("summary.txt", "summary.txt"), ("bed.bed", "novel_exon.bed"), ("updated.gtf", "updated.gtf"), ("novel.gtf", "novel.gtf")):
+        assert outs[1][f] == open(os.path.join(exp, g), "rb").read(), f
+
+
+@pytest.mark.gpu
 def test_single_locus_replay_equals_locus_fold(tmp_path):
     """The one-locus replay of the updated_T fold (what a split piece meeting another chromosome falls back to) gives the
     same tables as the locus-parallel fold on data without such a meeting: run the CLI with and without LRB_FORCE_SINGLE_FOLD."""

@@ -100,6 +100,11 @@ typedef struct {               /* bam2gtf.c:122, gtf.h:118-120 */
     int32_t max_delet;         /* -t 50 */
 } lrb_exon_params;
 
+typedef struct {               /* sj_para, parse_bam.c:71-84 (the fields bam2sj_core reads) */
+    int32_t min_intron;        /* -i 3 (INTRON_MIN_LEN, gtf.h:118) */
+    int32_t pair_only;         /* read_type == PAIR_T: 1 in the reference whatever the options say (parse_bam.c:76,997) */
+} lrb_sj_params;
+
 typedef struct {               /* update_gtf_para, update_gtf.h:8-15; defaults update_gtf.c:24-35 */
     int32_t min_sj_cnt;        /* -J 1 */
     int32_t ss_dis;            /* -d 0 */
@@ -261,6 +266,18 @@ int lrb_unique_run(lrb_ctx *ctx, const lrb_update_params *p);                 /*
  * tid << 32 | (pos + 1) << 1 | FLAG 0x10; row r of the later results refers to record read_idx[r] of the batch. */
 int lrb_rows_sort(lrb_ctx *ctx);
 int lrb_sync(lrb_ctx *ctx);
+
+/* `lr2rmats bam2sj` (bam2sj_core parse_bam.c:896-924 + gen_sj :402-442 + sj_update_group :353-380): the distinct splice
+ * junctions (tid, don = first, acc = last intron base) of the batch, ordered by (tid, don, acc), with the numbers of unique-
+ * (NH:i == 1: is_uniq[i] != 0) and multi-mapped records over each.  b == NULL: the batch uploaded last.  The record stream
+ * must be ordered by reference id (LRB_E_UNSORTED otherwise: the reference's insertion only keeps its order then).  The
+ * strand / motif columns of print_sj (:974-985) are a genome lookup per junction (intr_deri_str :319-337) left to the caller. */
+int lrb_bam2sj(lrb_ctx *ctx, const lrb_batch *b, const uint8_t *is_uniq, const lrb_sj_params *p, lrb_sj *out);
+
+/* Stable sort of n records by three unsigned keys, most significant first; *perm (pinned, owned by the ctx) = record indices
+ * in sorted order.  Replaces the `sort -n -k1 -n -k2 -n -k3 -n -k4` of src/sort_gtf.sh:29 -- chromosome rank, transcript
+ * start, transcript end, and the line number as the input order a stable sort keeps (Snakefile:192, the pipeline's last step). */
+int lrb_sort3(lrb_ctx *ctx, const uint32_t *k0, const uint32_t *k1, const uint32_t *k2, int64_t n, const uint32_t **perm);
 
 /* Results -> pinned host buffers owned by the ctx. */
 int lrb_filter_fetch(lrb_ctx *ctx, lrb_filter_result *out);

@@ -23,7 +23,7 @@ ENTRY_POINTS = [
     "lrb_update_gtf", "lrb_unique_gtf", "lrb_timing_enable", "lrb_timing_get", "lrb_launch_count", "lrb_shard_cuts",
     "lrb_mark", "lrb_elapsed_ms", "lrb_host_alloc", "lrb_host_free", "lrb_update_fetch_table", "lrb_filter_fetch_keep",
     "lrb_comm_id", "lrb_comm_init", "lrb_comm_destroy", "lrb_comm_rank", "lrb_tables_broadcast", "lrb_update_gather", "lrb_gather_fetch",
-    "lrb_gather_timing", "lrb_shard_cuts_weighted", "lrb_update_diag",
+    "lrb_gather_timing", "lrb_shard_cuts_weighted", "lrb_update_diag", "lrb_bam2sj", "lrb_sort3",
 ]
 
 T_NAMES = ["filter", "exon", "classify", "merge", "summary", "k_scan", "k_fold"]
@@ -92,6 +92,8 @@ def load_library():
     L.lrb_gather_fetch.argtypes = [vp, P(cabi.TransTable), P(cabi.BedList), P(C.c_int32 * cabi.S_COUNT)]
     L.lrb_gather_timing.argtypes = [vp, P(C.c_float), P(C.c_float)]
     L.lrb_update_diag.argtypes = [vp, P(C.c_int64), P(C.c_int64)]
+    L.lrb_bam2sj.argtypes = [vp, P(cabi.Batch), cabi.u8p, P(cabi.SjParams), P(cabi.Sj)]
+    L.lrb_sort3.argtypes = [vp, cabi.u32p, cabi.u32p, cabi.u32p, C.c_int64, P(cabi.u32p)]
     _lib = L
     return L
 
@@ -204,6 +206,19 @@ class Context:
             b, k = cabi.make_batch(batch_soa)
             self._ck(self.L.lrb_update_gtf(self.h, C.byref(b), C.byref(ep), C.byref(up), C.byref(r)))
         return cabi.update_to_np(r)
+
+    def bam2sj(self, batch_soa, is_uniq, sp) -> dict:
+        b, k = cabi.make_batch(batch_soa); r = cabi.Sj()
+        u = np.ascontiguousarray(is_uniq, np.uint8)
+        self._ck(self.L.lrb_bam2sj(self.h, C.byref(b), u.ctypes.data_as(cabi.u8p), C.byref(sp), C.byref(r)))
+        return cabi.sj_to_np(r)
+
+    def sort3(self, k0, k1, k2) -> np.ndarray:
+        """Stable sort by three unsigned keys (the `sort -n` of src/sort_gtf.sh); returns the permutation."""
+        a = [np.ascontiguousarray(k, np.uint32) for k in (k0, k1, k2)]
+        p = cabi.u32p()
+        self._ck(self.L.lrb_sort3(self.h, *[x.ctypes.data_as(cabi.u32p) for x in a], len(a[0]), C.byref(p)))
+        return cabi._arr(p, len(a[0]), np.uint32).copy()
 
     def unique_gtf(self, batch_soa, ep, up) -> dict:
         r = cabi.UniqueResult()

@@ -26,6 +26,21 @@ class Sj(C.Structure):
     _fields_ = [("n", C.c_int64), ("tid", i32p), ("don", i32p), ("acc", i32p), ("uniq_c", i32p), ("multi_c", i32p)]
 
 
+class SjParams(C.Structure):
+    _fields_ = [("min_intron", C.c_int32), ("pair_only", C.c_int32)]
+
+    @classmethod
+    def default(cls, **kw):
+        p = cls(3, 1)
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+
+def sj_to_np(s: "Sj") -> dict:
+    return {k: _arr(getattr(s, k), s.n, np.int32) for k in ("tid", "don", "acc", "uniq_c", "multi_c")}
+
+
 class Chains(C.Structure):
     _fields_ = [("n", C.c_int64), ("tid", i32p), ("is_rev", u8p), ("exon_off", u32p), ("exon_start", i32p), ("exon_end", i32p)]
 

@@ -232,7 +232,8 @@ void lrb_ctx_destroy(lrb_ctx *c)
                    &c->t_row, &c->t_lo, &c->t_cnt, &c->t_piece, &c->h_khi, &c->h_klo, &c->h_min, &c->h_score, &c->y_barcnt, &c->y_barseg, &c->y_genebar,
                    &c->y_bedcnt, &c->y_bedoff, &c->y_counts, &c->y_nelem, &c->bd_tid, &c->bd_s, &c->bd_e, &c->bd_sc, &c->bd_ty, &c->bd_rv, &c->q_shared, &c->tb_name, &c->tb_piece, &c->tb_ttid, &c->tb_tstart, &c->tb_tend, &c->tb_trev, &c->tb_etid, &c->tb_erev, &c->tb_cov, &c->tb_ref, &c->tb_cnt, &c->tb_off, &c->tb_es, &c->tb_ee, &c->tb_flag,
                    &c->s_read, &c->s_rtid, &c->s_rs, &c->s_re, &c->s_rev, &c->s_beg, &c->s_n, &c->s_key0, &c->s_key1, &c->s_idx0, &c->s_idx1, &c->s_hist,
-                   &c->tile_state, &c->tile_state2, &c->scalars, &c->kg_pairs, &c->xl_key, &c->xl_min, &c->xl_max, &c->xl_cnt, &c->xl_forced};
+                   &c->tile_state, &c->tile_state2, &c->scalars, &c->kg_pairs, &c->xl_key, &c->xl_min, &c->xl_max, &c->xl_cnt, &c->xl_forced,
+                   &c->j_cnt, &c->j_off, &c->j_uq, &c->j_tid, &c->j_don, &c->j_acc, &c->j_u, &c->j_head, &c->j_hpos, &c->jo_tid, &c->jo_don, &c->jo_acc, &c->jo_u, &c->jo_m};
     for (Buf *b : bufs) b->release();
     for (MergeBufs *m : {&c->mg, &c->mg2}) {
         Buf *w[] = {&m->keys, &m->head, &m->locus_start, &m->locus_cnt, &m->dropped, &m->rep, &m->lstart, &m->evmask, &m->samemask, &m->hard, &m->desc, &m->relsym, &m->ckey, &m->cmin, &m->cord, &m->clist, &m->crow, &m->w_cand, &m->w_cov, &m->w_tid, &m->w_start, &m->w_end, &m->w_fs,

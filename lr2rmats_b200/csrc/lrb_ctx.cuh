@@ -93,6 +93,8 @@ struct lrb_ctx {
     // summary
     Buf h_khi, h_klo, h_min, h_score, y_barcnt, y_barseg, y_genebar, y_bedcnt, y_bedoff, y_counts, y_nelem;
     Buf bd_tid, bd_s, bd_e, bd_sc, bd_ty, bd_rv; int64_t n_bed = 0;
+    // bam2sj
+    Buf j_cnt, j_off, j_uq, j_tid, j_don, j_acc, j_u, j_head, j_hpos, jo_tid, jo_don, jo_acc, jo_u, jo_m;
     // unique
     Buf q_shared; int64_t n_shared = 0;
     // look-back state, small device scalars and their pinned mirror

@@ -211,10 +211,10 @@ static void push_name(Records &r, const char *s, size_t n)
 }
 
 // aux walk: find first NM (bam_aux2i semantics) and first XS (bam_aux2A semantics)
-static void scan_aux(const uint8_t *p, const uint8_t *end, int32_t &nm, int8_t &xs)
+static void scan_aux(const uint8_t *p, const uint8_t *end, int32_t &nm, int8_t &xs, int8_t &nh)
 {
-    bool got_nm = false, got_xs = false;
-    nm = 0; xs = 0;
+    bool got_nm = false, got_xs = false, got_nh = false;
+    nm = 0; xs = 0; nh = 0;
     while (p + 3 <= end) {
         const uint8_t *tag = p; uint8_t type = p[2]; p += 3;
         const uint8_t *val = p; size_t sz = 0;
@@ -249,6 +249,20 @@ static void scan_aux(const uint8_t *p, const uint8_t *end, int32_t &nm, int8_t &
             got_xs = true;
             xs = (type == 'A') ? (int8_t)val[0] : (int8_t)1;           // bam_aux2A returns 0 for non-'A' => is_rev=1 (bam2gtf.c:37)
             if (xs == 0) xs = 1;
+        }
+        if (!got_nh && tag[0] == 'N' && tag[1] == 'H') {
+            got_nh = true;
+            long v = 0;
+            switch (type) {
+            case 'c': v = (int8_t)val[0]; break;
+            case 'C': v = val[0]; break;
+            case 's': { int16_t x; memcpy(&x, val, 2); v = x; break; }
+            case 'S': { uint16_t x; memcpy(&x, val, 2); v = x; break; }
+            case 'i': v = rdi32(val); break;
+            case 'I': v = (long)rd32(val); break;
+            default: v = 0;
+            }
+            nh = v == 1 ? 1 : 2;
         }
         p += sz;
     }
@@ -300,7 +314,7 @@ static bool parse_bam(Bytes &d, Header &h, Records &r, std::string &err)
     });
     for (size_t k = 0; k < nch; ++k) { c_cig[k + 1] += c_cig[k]; c_nam[k + 1] += c_nam[k]; c_raw[k + 1] += c_raw[k]; }
     const size_t cig0 = r.cigar.size(), nam0 = r.names.size(), raw0 = r.raw.size();
-    r.tid.resize(base + n); r.pos.resize(base + n); r.flag.resize(base + n); r.l_qseq.resize(base + n); r.nm.resize(base + n); r.xs.resize(base + n);
+    r.tid.resize(base + n); r.pos.resize(base + n); r.flag.resize(base + n); r.l_qseq.resize(base + n); r.nm.resize(base + n); r.xs.resize(base + n); r.nh.resize(base + n);
     r.qhash.resize(base + n); r.cigar_off.resize(base + n + 1); r.name_off.resize(base + n + 1);
     r.cigar.resize(cig0 + c_cig[nch]); r.names.resize(nam0 + c_nam[nch]);
     // raw record bodies (for `filter`'s re-emission): the inflated stream itself is adopted when it is the first input
@@ -322,8 +336,8 @@ static bool parse_bam(Bytes &d, Header &h, Records &r, std::string &err)
             r.name_off[j + 1] = (uint64_t)nm; r.qhash[j] = hash_name((const char *)q, ln);
             if (n_cigar) memcpy(r.cigar.data() + cg, cig, 4 * (size_t)n_cigar);
             cg += n_cigar; r.cigar_off[j + 1] = (uint64_t)cg;
-            int32_t nmv; int8_t xs; scan_aux(aux, rp + 4 + bs, nmv, xs);
-            r.nm[j] = nmv; r.xs[j] = xs;
+            int32_t nmv; int8_t xs, nh; scan_aux(aux, rp + 4 + bs, nmv, xs, nh);
+            r.nm[j] = nmv; r.xs[j] = xs; r.nh[j] = nh;
             if (adopt) r.raw_off[j + 1] = (uint64_t)(rp - d.data()) + 4 + (size_t)bs;
             else if (r.keep_raw) { memcpy(r.raw.data() + rw, rp, 4 + (size_t)bs); rw += 4 + (size_t)bs; r.raw_off[j + 1] = rw; }
         }
@@ -392,7 +406,7 @@ static bool parse_sam_line(char *line, size_t len, const Header &h, Records &r)
     }
     if (strcmp(f[10], "*") && (int32_t)strlen(f[10]) != l_seq) { r.cigar.resize(co); return false; }
     // aux
-    int32_t nm = 0; int8_t xs = 0; bool got_nm = false, got_xs = false;
+    int32_t nm = 0; int8_t xs = 0, nh = 0; bool got_nm = false, got_xs = false, got_nh = false;
     std::vector<uint8_t> auxenc;
     for (char *a = aux; a && *a;) {
         char *t = strchr(a, '\t'); if (t) *t = 0;
@@ -401,6 +415,7 @@ static bool parse_sam_line(char *line, size_t len, const Header &h, Records &r)
         char type = a[3]; char *v = a + 5;
         if (!got_nm && a[0] == 'N' && a[1] == 'M') { got_nm = true; nm = (type == 'i' || type == 'I') ? (int32_t)(*v == '-' ? strtol(v, nullptr, 10) : (long)strtoul(v, nullptr, 10)) : 0; }
         if (!got_xs && a[0] == 'X' && a[1] == 'S') { got_xs = true; xs = (type == 'A' || type == 'a' || type == 'c' || type == 'C') ? (int8_t)*v : (int8_t)1; if (!xs) xs = 1; }
+        if (!got_nh && a[0] == 'N' && a[1] == 'H') { got_nh = true; nh = ((type == 'i' || type == 'I') && strtol(v, nullptr, 10) == 1) ? 1 : 2; }
         if (r.keep_raw) {
             auxenc.push_back((uint8_t)a[0]); auxenc.push_back((uint8_t)a[1]);
             if (type == 'A' || type == 'a' || type == 'c' || type == 'C') { auxenc.push_back('A'); auxenc.push_back((uint8_t)*v); }
@@ -441,7 +456,7 @@ static bool parse_sam_line(char *line, size_t len, const Header &h, Records &r)
     size_t lq = strlen(f[0]);
     if (lq > 254) { r.cigar.resize(co); return false; }
     r.tid.push_back(tid); r.pos.push_back((int32_t)pos); r.flag.push_back((uint16_t)flag); r.l_qseq.push_back(l_seq);
-    r.nm.push_back(nm); r.xs.push_back(xs);
+    r.nm.push_back(nm); r.xs.push_back(xs); r.nh.push_back(nh);
     push_name(r, f[0], lq);
     r.cigar_off.push_back((uint64_t)r.cigar.size());
     if (r.keep_raw) {
@@ -565,14 +580,14 @@ static bool parse_sam(Bytes &d, Header &h, Records &r, std::string &err)
         b_nam[k + 1] = b_nam[k] + part[k].names.size(); b_raw[k + 1] = b_raw[k] + part[k].raw.size();
     }
     const size_t nn = b_rec[used];
-    r.tid.resize(nn); r.pos.resize(nn); r.flag.resize(nn); r.l_qseq.resize(nn); r.nm.resize(nn); r.xs.resize(nn); r.qhash.resize(nn);
+    r.tid.resize(nn); r.pos.resize(nn); r.flag.resize(nn); r.l_qseq.resize(nn); r.nm.resize(nn); r.xs.resize(nn); r.nh.resize(nn); r.qhash.resize(nn);
     r.cigar_off.resize(nn + 1); r.name_off.resize(nn + 1); r.cigar.resize(b_cig[used]); r.names.resize(b_nam[used]);
     if (r.keep_raw) { r.raw.resize(b_raw[used]); r.raw_off.resize(nn + 1); }
     parallel_for(used, [&](size_t k) {
         const Records &q = part[k]; const size_t m = q.n(), o = b_rec[k];
         if (!m) return;
         memcpy(r.tid.data() + o, q.tid.data(), m * 4); memcpy(r.pos.data() + o, q.pos.data(), m * 4); memcpy(r.flag.data() + o, q.flag.data(), m * 2);
-        memcpy(r.l_qseq.data() + o, q.l_qseq.data(), m * 4); memcpy(r.nm.data() + o, q.nm.data(), m * 4); memcpy(r.xs.data() + o, q.xs.data(), m);
+        memcpy(r.l_qseq.data() + o, q.l_qseq.data(), m * 4); memcpy(r.nm.data() + o, q.nm.data(), m * 4); memcpy(r.xs.data() + o, q.xs.data(), m); memcpy(r.nh.data() + o, q.nh.data(), m);
         memcpy(r.qhash.data() + o, q.qhash.data(), m * 8);
         memcpy(r.cigar.data() + b_cig[k], q.cigar.data(), q.cigar.size() * 4); memcpy(r.names.data() + b_nam[k], q.names.data(), q.names.size());
         for (size_t i = 0; i < m; ++i) { r.cigar_off[o + i + 1] = (uint64_t)(q.cigar_off[i + 1] + b_cig[k]); r.name_off[o + i + 1] = (uint64_t)(q.name_off[i + 1] + b_nam[k]); }

@@ -5,11 +5,14 @@
 // main.c:37-49, bam_filter.c:98-164, bam2gtf.c:120-161, update_gtf.c:995-1117, unique_gtf.c:86-158.  The per-alignment
 // work itself is done by the engine (the CUDA library in the product binary).
 #include <unistd.h>
+#include <zlib.h>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
 #include <getopt.h>
 #include <string>
+#include <unordered_map>
+#include <vector>
 #include "lrb_host.h"
 
 namespace lrb {
@@ -140,6 +143,182 @@ static int cmd_bam2gtf(int argc, char **argv, Engine &eng)
     int rc = eng.bam2gtf(eng.self, &b, &ep, &res);
     if (rc) engine_fail(eng, "bam2gtf", rc);
     emit_bam2gtf(stdout, res, rec, cn, src.c_str());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ bam2sj
+// parse_bam.c:44-69 (usage), :987-1060 (bam2sj): option letters, long names and the output layout are the drop-in contract
+static int bam2sj_usage()
+{
+    fprintf(stderr, "\n");
+    fprintf(stderr, "Usage:   %s bam2sj [option] <in.bam> > out.sj\n\n", PROG);
+    fprintf(stderr, "Note:    in.bam should be sorted in advance\n\n");
+    fprintf(stderr, "Input Options:\n\n");
+    fprintf(stderr, "         -G --gtf-anno    [STR]    GTF annotation file, indicating known splice-junctions. \n");
+    fprintf(stderr, "         -g --genome-file [STR]    genome.fa. Use genome sequence to classify intron-motif. \n");
+    fprintf(stderr, "                                   If no genome file is give, intron-motif will be set as 0\n");
+    fprintf(stderr, "                                   (non-canonical) [None]\n");
+    fprintf(stderr, "\nFilter Options:\n\n");
+    fprintf(stderr, "         -p --prop-pair            set -p to force to filter out reads mapped in improper pair. [False]\n");
+    fprintf(stderr, "         -a --anchor-len  [INT,INT,INT,INT,INT]\n");
+    fprintf(stderr, "                                   minimum anchor length for junction read, [annotated, non-canonical,\n");
+    fprintf(stderr, "                                    GT/AG, GC/AG, AT/AC]. [%d,%d,%d,%d,%d]\n", 1, 30, 12, 12, 12);
+    fprintf(stderr, "         -U --uniq-map    [INT,INT,INT,INT,INT]\n");
+    fprintf(stderr, "                                   minimum uniq-map read count for junction read, [annotated,\n");
+    fprintf(stderr, "                                   non-canonical, GT/AG, GC/AG, AT/AC]. [%d,%d,%d,%d,%d]\n", 0, 3, 1, 1, 1);
+    fprintf(stderr, "         -A --all-map     [INT,INT,INT,INT,INT]\n");
+    fprintf(stderr, "                                   minimum total uniq-map and multi-map read count for junction\n");
+    fprintf(stderr, "                                   read, [annotated, non-canonical, GT/AG, GC/AG, AT/AC].\n");
+    fprintf(stderr, "                                   [%d,%d,%d,%d,%d]\n", 0, 3, 1, 1, 1);
+    fprintf(stderr, "         -i --intron-len  [INT]    minimum intron length for junction read. [%d]\n", 3);
+    fprintf(stderr, "\n");
+    return 1;
+}
+// kseq_load_genome (parse_bam.c:382-400): sequences in file order (bam2sj indexes them by tid), plain or gzip
+static bool load_genome(const char *fn, std::vector<std::string> &seqs)
+{
+    gzFile fp = gzopen(fn, "r");
+    if (!fp) return false;
+    std::vector<char> buf(1 << 22); std::string line; int n; bool in_seq = false;
+    auto feed = [&](const std::string &l) {
+        if (!l.empty() && l[0] == '>') { seqs.emplace_back(); in_seq = true; }
+        else if (in_seq) { for (char ch : l) if (!isspace((unsigned char)ch)) seqs.back().push_back(ch); }
+    };
+    while ((n = gzread(fp, buf.data(), (unsigned)buf.size())) > 0) {
+        const char *p = buf.data(), *e = p + n;
+        while (p < e) { const char *q = (const char *)memchr(p, '\n', (size_t)(e - p)); if (!q) { line.append(p, e); break; } line.append(p, q); feed(line); line.clear(); p = q + 1; }
+    }
+    if (!line.empty()) feed(line);
+    gzclose(fp);
+    return true;
+}
+static int five_ints(const char *arg) { char *p; strtol(arg, &p, 10); for (int k = 0; k < 4; ++k) { if (*p == 0) return -1; strtol(p + 1, &p, 10); } return 0; }
+static int cmd_bam2sj(int argc, char **argv, Engine &eng)
+{
+    static const struct option lo[] = {{"proper-pair", 1, NULL, 'p'}, {"gtf-anno", 1, NULL, 'G'}, {"genome-file", 1, NULL, 'g'}, {"anchor-len", 1, NULL, 'a'},
+                                       {"uniq-map", 1, NULL, 'U'}, {"all-map", 1, NULL, 'A'}, {"intron-len", 1, NULL, 'i'}, {0, 0, 0, 0}};
+    lrb_sj_params sp = {3, 1}; std::string ref_fn; int c;
+    while ((c = getopt_long(argc, argv, "G:g:pa:i:A:U:", lo, NULL)) >= 0) {
+        switch (c) {
+        case 'g': ref_fn = optarg; break;
+        case 'p': sp.pair_only = 1; break;                              // PAIR_T again: no option reaches single-end mode (parse_bam.c:997)
+        case 'a': case 'U': case 'A': if (five_ints(optarg)) return bam2sj_usage(); break;      // parsed, never read by bam2sj_core
+        case 'i': sp.min_intron = atoi(optarg); break;
+        default: fprintf(stderr, "Error: unknown option: %s.\n", optarg); return bam2sj_usage();
+        }
+    }
+    if (argc - optind != 1) return bam2sj_usage();
+    std::vector<std::string> genome;
+    if (!ref_fn.empty()) {
+        if (!eng.bam2sj) fatal("bam2sj", "this engine has no bam2sj");
+        logf("kseq_load_genome", "loading genome fasta file ...\n");
+        if (!load_genome(ref_fn.c_str(), genome)) fatal("bam2sj", "Can not open genome file. " + ref_fn);
+        logf("kseq_load_genome", "loading genome fasta file done!\n");
+    }
+    Header h; Records rec; std::string err;
+    if (!read_alignments(argv[optind], h, rec, err)) fatal("bam2sj", err);
+    logf("bam2sj_core", "generating splice-junction with BAM file ...\n");
+    std::vector<uint8_t> uniq(rec.n());
+    for (size_t i = 0; i < rec.n(); ++i) {
+        if (rec.flag[i] & 4) continue;
+        if (rec.nh[i] == 0) fprintf(stderr, "No \"NH\" tag.\n");       // bam_is_uniq_NH, parse_bam.c:239-247: once per mapped record, before the pair test
+        uniq[i] = rec.nh[i] == 1;
+    }
+    lrb_batch b = rec.view(); lrb_sj res;
+    int rc = eng.bam2sj ? eng.bam2sj(eng.self, &b, uniq.data(), &sp, &res) : LRB_E_ARG;
+    if (rc) engine_fail(eng, "bam2sj", rc);
+    logf("bam2sj_core", "generating splice-junction with BAM file done!\n");
+    // print_sj (parse_bam.c:974-985); strand / motif from the genome (intr_deri_str :319-337), 0 / 0 without -g
+    static const char motifs[6][5] = {"GTAG", "CTAC", "GCAG", "CTGC", "ATAC", "GTAT"};
+    static const int motif_strand[6] = {1, 2, 1, 2, 1, 2};
+    std::string out;
+    out += "###STRAND 0:undefined, 1:+, 2:-\n###ANNO 0:novel, 1:annotated\n###MOTIF 0:non-canonical, 1:GT/AG, 2:CT/AC, 3:GC/AG, 4:CT/GC, 5:AT/AC, 6:GT/AT\n#CHR\tSTART\tEND\tSTRAND\tANNO\tUNIQ_C\tMULTI_C\tMOTIF\n";
+    char line[256];
+    for (int64_t k = 0; k < res.n; ++k) {
+        int strand = 0, motif = 0;
+        const int tid = res.tid[k], don = res.don[k], acc = res.acc[k];
+        if (!genome.empty()) {
+            if (tid >= (int)genome.size()) fatal("intr_deri_str", "unknown tid: " + std::to_string(tid) + "\n");
+            const std::string &g = genome[(size_t)tid];
+            auto at = [&](long pos) { return pos >= 0 && pos < (long)g.size() ? (char)toupper((unsigned char)g[(size_t)pos]) : '\0'; };
+            const char in[5] = {at(don - 1), at(don), at(acc - 2), at(acc - 1), 0};
+            for (int m = 0; m < 6; ++m) if (strcmp(in, motifs[m]) == 0) { motif = m + 1; strand = motif_strand[m]; break; }
+        }
+        const char *name = tid >= 0 && tid < (int)h.names.size() ? h.names[(size_t)tid].c_str() : "*";
+        out.append(line, (size_t)snprintf(line, sizeof line, "%s\t%d\t%d\t%d\t%d\t%d\t%d\t%d\n", name, don, acc, strand, 1, res.uniq_c[k], res.multi_c[k], motif));
+    }
+    fwrite(out.data(), 1, out.size(), stdout);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- sort-gtf
+// The last step of the pipeline sorts the concatenated GTF with src/sort_gtf.sh (Snakefile:192): an awk pass tags every `transcript` /
+// `exon` line with (chromosome rank, start, end of the last transcript line, line number), `sort -n -k1 -n -k2 -n -k3 -n -k4` orders
+// the tagged lines and a second awk pass prints the first nine tab-separated columns.  Here the tagging is one pass on the host (it
+// carries state from line to line), the sort runs on the device (a stable radix sort of the three keys; the line number is the input
+// order), and the lines are written through the permutation.  `lr2rmats-b200 sort-gtf in.unsort.gtf out.sort.gtf` replaces the script.
+static int sort_gtf_usage() { fprintf(stdout, "Usage: %s sort-gtf in.unsort.gtf out.sort.gtf\n       sort GTF file based on 'trans' lines\n", PROG); return 0; }
+static int cmd_sort_gtf(int argc, char **argv, Engine &eng)
+{
+    if (argc != 3) return sort_gtf_usage();                            // sort_gtf.sh:2-6: usage on stdout, exit status 0
+    if (!eng.sort3) fatal("sort-gtf", "this engine has no sort");
+    FILE *fp = fopen(argv[1], "rb");
+    if (!fp) fatal("sort-gtf", std::string("Cannot open \"") + argv[1] + "\"");
+    std::string text; { char buf[1 << 16]; size_t k; while ((k = fread(buf, 1, sizeof buf, fp)) > 0) text.append(buf, k); } fclose(fp);
+    struct Line { size_t off, len; };
+    std::vector<Line> lines; std::vector<uint32_t> k0, k1, k2;
+    std::unordered_map<std::string, uint32_t> chrom;
+    { static const char *fixed[] = {"chr1", "chr2", "chr3", "chr4", "chr5", "chr6", "chr7", "chr8", "chr9", "chr10", "chr11", "chr12", "chr13", "chr14", "chr15", "chr16",
+                                    "chr17", "chr18", "chr19", "chr20", "chr21", "chr22", "chrX", "chrY", "chrM"};
+      for (uint32_t i = 0; i < 25; ++i) chrom[fixed[i]] = i + 1; }
+    uint32_t chr = 0, chr_m = 25; long long start = 0, end = 0; bool end_set = false; uint64_t nr = 0;
+    auto is_blank = [](char ch) { return ch == ' ' || ch == '\t'; };
+    auto lead_int = [](const char *p, const char *e) { long long v = 0; bool neg = false; while (p < e && (*p == ' ' || *p == '\t')) ++p; if (p < e && *p == '-') { neg = true; ++p; }
+                                                        while (p < e && *p >= '0' && *p <= '9') { v = v * 10 + (*p - '0'); if (v > (1ll << 40)) break; ++p; } return neg ? -v : v; };
+    for (size_t p = 0; p < text.size();) {
+        size_t q = text.find('\n', p); if (q == std::string::npos) q = text.size();
+        ++nr;
+        const char *b = text.data() + p, *e = text.data() + q;
+        if (!(b < e && *b == '#')) {
+            // awk's default field splitting: runs of blanks separate fields, leading blanks are skipped
+            const char *f[5] = {nullptr, nullptr, nullptr, nullptr, nullptr}, *fe[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+            const char *c = b; int nf = 0;
+            while (nf < 5) { while (c < e && is_blank(*c)) ++c; if (c >= e) break; f[nf] = c; while (c < e && !is_blank(*c)) ++c; fe[nf] = c; ++nf; }
+            if (nf >= 3) {
+                const std::string t3(f[2], fe[2]);
+                if (t3.find("transcript") != std::string::npos || t3 == "exon") {
+                    if (t3 == "transcript") {
+                        const std::string c1(f[0], fe[0]);
+                        auto it = chrom.find(c1);
+                        if (it == chrom.end()) it = chrom.emplace(c1, ++chr_m).first;
+                        chr = it->second; start = nf > 3 ? lead_int(f[3], fe[3]) : 0; end = nf > 4 ? lead_int(f[4], fe[4]) : 0; end_set = true;
+                    }
+                    if (start < 0 || end < 0 || start > 0xffffffffll || end > 0xffffffffll || nr > 0xffffffffull) fatal("sort-gtf", "coordinate or line number beyond 2^32");
+                    // before the first transcript line awk's `end` is still empty: `sort` then sees the line number as its third field
+                    lines.push_back({p, q - p}); k0.push_back(chr); k1.push_back((uint32_t)start); k2.push_back(end_set ? (uint32_t)end : (uint32_t)nr);
+                }
+            }
+        }
+        p = q + 1;
+    }
+    const uint32_t *perm = nullptr;
+    int rc = eng.sort3(eng.self, k0.data(), k1.data(), k2.data(), (int64_t)lines.size(), &perm);
+    if (rc) engine_fail(eng, "sort-gtf", rc);
+    FILE *out = fopen(argv[2], "wb");
+    if (!out) fatal("sort-gtf", std::string("Cannot open \"") + argv[2] + "\"");
+    std::string o; o.reserve(text.size() + lines.size() * 8);
+    for (size_t i = 0; i < lines.size(); ++i) {
+        const Line &l = lines[perm[i]];
+        // the second awk pass (FS = tab) prints nine fields whatever the line holds
+        const char *b = text.data() + l.off, *e = b + l.len; int col = 0;
+        while (col < 9) {
+            const char *t = (const char *)memchr(b, '\t', (size_t)(e - b)); if (!t) t = e;
+            o.append(b, t); ++col; if (col < 9) o.push_back('\t');
+            b = t < e ? t + 1 : e;
+        }
+        o.push_back('\n');
+    }
+    fwrite(o.data(), 1, o.size(), out); fclose(out);
     return 0;
 }
 
@@ -361,7 +540,9 @@ int cli_main(int argc, char **argv, Engine &eng)
     else if (strcmp(argv[1], "update-gtf") == 0) return cmd_update(argc - 1, argv + 1, eng);
     else if (strcmp(argv[1], "unique-gtf") == 0) return cmd_unique(argc - 1, argv + 1, eng);
     else if (strcmp(argv[1], "bam2gtf") == 0) return cmd_bam2gtf(argc - 1, argv + 1, eng);
-    else if (strcmp(argv[1], "fusion") == 0 || strcmp(argv[1], "bam2sj") == 0) {
+    else if (strcmp(argv[1], "bam2sj") == 0) return cmd_bam2sj(argc - 1, argv + 1, eng);
+    else if (strcmp(argv[1], "sort-gtf") == 0) return cmd_sort_gtf(argc - 1, argv + 1, eng);       // src/sort_gtf.sh
+    else if (strcmp(argv[1], "fusion") == 0) {
         fprintf(stderr, "[main] command '%s' is outside the accelerated path of this build (see DESIGN.md); use the reference binary\n", argv[1]);
         return 1;
     }

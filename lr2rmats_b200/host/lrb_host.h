@@ -45,6 +45,7 @@ struct Records {
     std::vector<int32_t> tid, pos, l_qseq, nm;
     std::vector<uint16_t> flag;
     std::vector<int8_t> xs;
+    std::vector<int8_t> nh;                        // NH:i tag (bam2sj's bam_is_uniq_NH, parse_bam.c:239-247): 0 absent, 1 NH == 1, 2 otherwise
     std::vector<uint64_t> qhash;
     std::vector<uint64_t> cigar_off{0}; std::vector<uint32_t> cigar;   // 64-bit running totals: no silent wrap past 2^32 ops / name bytes
     std::vector<uint64_t> name_off{0};
@@ -128,6 +129,9 @@ struct Engine {
     // optional: run update and return only what -o / -y / -E print (NULL: the CLI uses `update` and the full tables)
     int (*update_table)(void *, const lrb_batch *, const lrb_chains *, const lrb_exon_params *, const lrb_update_params *,
                         lrb_trans_table *, lrb_bed_list *, int32_t *summary) = nullptr;
+    int (*bam2sj)(void *, const lrb_batch *, const uint8_t *is_uniq, const lrb_sj_params *, lrb_sj *) = nullptr;   // bam2sj_core, parse_bam.c:896
+    // stable sort of n records by (k0, k1, k2): the `sort -n` of src/sort_gtf.sh; *perm = record indices in sorted order
+    int (*sort3)(void *, const uint32_t *k0, const uint32_t *k1, const uint32_t *k2, int64_t n, const uint32_t **perm) = nullptr;
     const char *(*error)(void *) = nullptr;
 };
 

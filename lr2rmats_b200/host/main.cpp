@@ -33,6 +33,8 @@ int set_tables(void *s, const lrb_anno *a, const lrb_anno *rm, const lrb_sj *sj)
 }
 int do_filter(void *s, const lrb_batch *b, const lrb_filter_params *p, lrb_filter_result *o) { return lrb_filter(((CudaEngine *)s)->get(), b, p, o); }
 int do_bam2gtf(void *s, const lrb_batch *b, const lrb_exon_params *p, lrb_exon_result *o) { return lrb_bam2gtf(((CudaEngine *)s)->get(), b, p, o); }
+int do_sort3(void *s, const uint32_t *a, const uint32_t *b, const uint32_t *c, int64_t n, const uint32_t **perm) { return lrb_sort3(((CudaEngine *)s)->get(), a, b, c, n, perm); }
+int do_bam2sj(void *s, const lrb_batch *b, const uint8_t *u, const lrb_sj_params *p, lrb_sj *o) { return lrb_bam2sj(((CudaEngine *)s)->get(), b, u, p, o); }
 // LRB_SORT_INPUT=1: update-gtf takes a BAM that is NOT coordinate sorted (filter's output as it is) and sorts the rows on the
 // device -- the `samtools sort` hop of the pipeline (Snakefile:90) without the extra BAM round trip
 bool sort_input() { static const bool on = getenv("LRB_SORT_INPUT") && atoi(getenv("LRB_SORT_INPUT")) != 0; return on; }
@@ -74,7 +76,7 @@ int main(int argc, char **argv)
         const int device = dev ? atoi(dev) : 0;
         ce.pending = std::async(std::launch::async, [&ce, device] { return lrb_ctx_create(device, &ce.ctx); });
     }
-    eng.self = &ce; eng.set_tables = set_tables; eng.filter = do_filter; eng.bam2gtf = do_bam2gtf; eng.update = do_update; eng.update_table = getenv("LRB_FULL_FETCH") ? nullptr : do_update_table;
+    eng.self = &ce; eng.set_tables = set_tables; eng.filter = do_filter; eng.bam2gtf = do_bam2gtf; eng.bam2sj = do_bam2sj; eng.sort3 = do_sort3; eng.update = do_update; eng.update_table = getenv("LRB_FULL_FETCH") ? nullptr : do_update_table;
     eng.unique = do_unique; eng.error = err;
     lrb::IoTrace tr;
     int rc = lrb::cli_main(argc, argv, eng);

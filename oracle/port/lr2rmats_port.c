@@ -608,3 +608,50 @@ void orc_free_unique(lrb_unique_result *r)
     orc_free_exon(&r->ex); merged_free(&r->uniq); free((void *)r->shared_idx);
     memset(r, 0, sizeof *r);
 }
+
+
+/* ------------------------------------------------------------------------------------------------ bam2sj
+ * Restates bam2sj_core (parse_bam.c:896-924), gen_sj (:402-442), sj_sch_group (:339-351) and sj_update_group (:353-380):
+ * the junction array is kept by linear search from its end + memmove, with the reference's own (lopsided) comparison. */
+typedef struct { int tid, don, acc, uniq_c, multi_c; } psj_t;
+static int psj_search(const psj_t *S, int n, const psj_t *x, int *hit)
+{
+    *hit = 0;
+    for (int i = n - 1; i >= 0; --i) {
+        if (S[i].tid == x->tid && S[i].don == x->don && S[i].acc == x->acc) { *hit = 1; return i; }
+        else if (S[i].tid < x->tid || S[i].don < x->don || (S[i].don == x->don && S[i].acc < x->acc)) return i + 1;   /* parse_bam.c:348 */
+    }
+    return 0;
+}
+int orc_bam2sj(const lrb_batch *b, const uint8_t *is_uniq, const lrb_sj_params *p, lrb_sj *out)
+{
+    psj_t *S = NULL; int n = 0, m = 0;
+    for (int64_t r = 0; r < b->n; ++r) {
+        if (b->flag[r] & 4) continue;                                   /* bam_unmap, :909 */
+        const int uq = is_uniq ? (is_uniq[r] != 0) : 0;
+        if (p->pair_only && !(b->flag[r] & 2)) continue;                /* bam_is_prop / PAIR_T, :914 */
+        int end = b->pos[r];                                            /* start - 1, start = pos + 1 */
+        for (uint64_t k = b->cigar_off[r]; k < b->cigar_off[r + 1]; ++k) {
+            const uint32_t w = b->cigar[k], op = w & 15u; const int l = (int)(w >> 4);
+            if (op == 3) {
+                if (l >= p->min_intron) {
+                    psj_t x = {b->tid[r], end + 1, end + l, uq, 1 - uq};
+                    int hit, i = psj_search(S, n, &x, &hit);
+                    if (hit) { S[i].uniq_c += x.uniq_c; S[i].multi_c += x.multi_c; }
+                    else {
+                        if (n == m) { m = m ? 2 * m : 1024; S = (psj_t *)realloc(S, (size_t)m * sizeof *S); }
+                        memmove(S + i + 1, S + i, (size_t)(n - i) * sizeof *S);
+                        S[i] = x; ++n;
+                    }
+                }
+                end += l;
+            } else if (op == 0 || op == 7 || op == 8 || op == 2) end += l;
+        }
+    }
+    int32_t *t = (int32_t *)malloc((size_t)(n ? n : 1) * 5 * sizeof(int32_t));
+    for (int i = 0; i < n; ++i) { t[i] = S[i].tid; t[n + i] = S[i].don; t[2 * n + i] = S[i].acc; t[3 * n + i] = S[i].uniq_c; t[4 * n + i] = S[i].multi_c; }
+    free(S);
+    out->n = n; out->tid = t; out->don = t + n; out->acc = t + 2 * n; out->uniq_c = t + 3 * n; out->multi_c = t + 4 * n;
+    return 0;
+}
+void orc_free_sj(lrb_sj *r) { free((void *)r->tid); memset(r, 0, sizeof *r); }

@@ -36,6 +36,10 @@ void orc_free_update(lrb_update_result *r);
 int  orc_unique(const lrb_exon_result *chains, const lrb_update_params *p, lrb_unique_result *out);
 void orc_free_unique(lrb_unique_result *r);
 
+/* bam2sj_core (parse_bam.c:896-924): distinct junctions with uniq / multi counts, in the order the reference's insertion leaves them */
+int  orc_bam2sj(const lrb_batch *b, const uint8_t *is_uniq, const lrb_sj_params *p, lrb_sj *out);
+void orc_free_sj(lrb_sj *r);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,7 +4,9 @@
 // (oracle/port/lr2rmats_port.c) instead of the CUDA library.  It exists to pin the restatement -- and the host
 // readers/emitters it shares with the product -- against the compiled reference binary on identical input files
 // (tests/test_oracle_pin.py).  The product binary (lr2rmats_b200/host/main.cpp) never links this.
+#include <algorithm>
 #include <cstdio>
+#include <vector>
 #include "../lr2rmats_b200/host/lrb_host.h"
 #include "port/lr2rmats_port.h"
 
@@ -43,6 +45,14 @@ int do_unique(void *s, const lrb_batch *b, const lrb_chains *c, const lrb_exon_p
     if (b) { int rc = orc_bam2gtf(b, nullptr, 0, ep, &e->ex); if (rc) return rc; } else chains_view(c, &e->ex);
     return orc_unique(&e->ex, up, out);
 }
+int do_bam2sj(void *, const lrb_batch *b, const uint8_t *u, const lrb_sj_params *p, lrb_sj *out) { return orc_bam2sj(b, u, p, out); }
+int do_sort3(void *, const uint32_t *a, const uint32_t *b, const uint32_t *c, int64_t n, const uint32_t **perm)
+{
+    static std::vector<uint32_t> p; p.resize((size_t)n);
+    for (int64_t i = 0; i < n; ++i) p[(size_t)i] = (uint32_t)i;
+    std::stable_sort(p.begin(), p.end(), [&](uint32_t x, uint32_t y) { return a[x] != a[y] ? a[x] < a[y] : b[x] != b[y] ? b[x] < b[y] : c[x] < c[y]; });
+    *perm = p.data(); return 0;
+}
 const char *err(void *) { return "oracle port error"; }
 }  // namespace
 
@@ -50,6 +60,6 @@ int main(int argc, char **argv)
 {
     PortEngine pe; lrb::Engine eng;
     eng.self = &pe; eng.set_tables = set_tables; eng.filter = do_filter; eng.bam2gtf = do_bam2gtf; eng.update = do_update;
-    eng.unique = do_unique; eng.error = err;
+    eng.unique = do_unique; eng.bam2sj = do_bam2sj; eng.sort3 = do_sort3; eng.error = err;
     return lrb::cli_main(argc, argv, eng);
 }

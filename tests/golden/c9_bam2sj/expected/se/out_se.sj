@@ -1,0 +1,4 @@
+###STRAND 0:undefined, 1:+, 2:-
+###ANNO 0:novel, 1:annotated
+###MOTIF 0:non-canonical, 1:GT/AG, 2:CT/AC, 3:GC/AG, 4:CT/GC, 5:AT/AC, 6:GT/AT
+#CHR	START	END	STRAND	ANNO	UNIQ_C	MULTI_C	MOTIF

@@ -138,6 +138,48 @@ case("c8_xlocus", {"in.sam": c8, "anno.gtf": "@TOY_TWO_CHROM", "sj.tab": "chr1\t
      {"split": f"update-gtf -s -l 3 -J 1 -j sj.tab in.sam anno.gtf {ALLOUT}", "nosplit": f"update-gtf -l 3 -J 1 -j sj.tab in.sam anno.gtf {ALLOUT}",
       "split_noy": "update-gtf -s -l 3 -J 1 -j sj.tab in.sam anno.gtf -o updated.gtf", "split_d": f"update-gtf -s -d 2 -l 3 -J 1 -j sj.tab in.sam anno.gtf {SMALLOUT}"})
 
+# ---- C.9 bam2sj (parse_bam.c:896-985): proper pairs with NH tags, a genome for the motif / strand columns; single-end input gives the header only
+def c9_files():
+    import random
+    rnd = random.Random(5)
+    L = 6000
+    g = [[rnd.choice("acgtACGT") for _ in range(L)] for _ in range(2)]
+
+    def plant(c, don, acc, m):
+        g[c][don - 1] = m[0]; g[c][don] = m[1]; g[c][acc - 2] = m[2]; g[c][acc - 1] = m[3]
+    hdr = "@HD\tVN:1.0\tSO:coordinate\n@SQ\tSN:chrA\tLN:6000\n@SQ\tSN:chrB\tLN:6000\n"
+
+    def r(q, flag, ch, pos, cig, extra):
+        return f"{q}\t{flag}\t{ch}\t{pos}\t60\t{cig}\t=\t{pos + 200}\t300\t*\t*\tNM:i:0{extra}\n"
+    rows = [r("p1", 99, "chrA", 100, "50M100N50M", "\tNH:i:1"), r("p2", 147, "chrA", 120, "30M100N20M2D10M200N40M", "\tNH:i:1"),
+            r("p3", 83, "chrA", 120, "30M100N70M", "\tNH:i:3"), r("p4", 163, "chrA", 100, "50M2N48M", "\tNH:i:1"), r("s1", 0, "chrA", 100, "50M100N50M", "\tNH:i:1"),
+            r("p5", 99, "chrA", 500, "10S40M300N5I30M20=10X", ""), r("p6", 99, "chrA", 400, "60M400N40M", "\tNH:i:1"), "u1\t4\t*\t0\t0\t*\t*\t0\t0\t*\t*\tNM:i:0\n",
+            r("q1", 99, "chrB", 100, "50M100N50M", "\tNH:i:1"), r("q2", 147, "chrB", 90, "60M100N50M3N10M", "\tNH:i:2"), r("q3", 99, "chrB", 1000, "100M", "\tNH:i:1")]
+    plant(0, 150, 249, "GTAG"); plant(1, 150, 249, "CTAC"); plant(0, 460, 859, "GCAG")
+    fa = "".join(f">chr{n} test\n" + "\n".join("".join(s_[i:i + 60]) for i in range(0, L, 60)) + "\n" for n, s_ in zip("AB", g))
+    se = hdr + "se1\t0\tchrA\t100\t60\t50M100N50M\t*\t0\t0\t*\t*\tNM:i:0\tNH:i:1\n"
+    return {"in.sam": hdr + "".join(rows), "genome.fa": fa, "se.sam": se}
+case("c9_bam2sj", c9_files(), {"sj": "bam2sj -g genome.fa in.sam > out.sj", "sj_i": "bam2sj -i 150 in.sam > out_i.sj", "se": "bam2sj se.sam > out_se.sj"})
+
+# ---- C.10 sort_gtf.sh (the pipeline's last step, Snakefile:192): concatenated GTFs out of order, unknown chromosomes ranked by first sight,
+# gene / CDS / comment lines dropped, lines in front of the first transcript, fewer and more than nine tab-separated columns
+def c10_gtf():
+    def t(ch, s, e, tid, extra=""):
+        return f'{ch}\tlr2rmats\ttranscript\t{s}\t{e}\t.\t+\t.\tgene_id "G{tid}"; transcript_id "T{tid}";{extra}\n'
+
+    def x(ch, s, e, tid):
+        return f'{ch}\tlr2rmats\texon\t{s}\t{e}\t.\t+\t.\tgene_id "G{tid}"; transcript_id "T{tid}";\n'
+    g = "# a header comment\n" + x("chr3", 5, 9, 0) + "chr1\tsrc\tgene\t1\t100000\t.\t+\t.\tgene_id \"G\";\n"
+    g += t("chr2", 5000, 9000, 1) + x("chr2", 5000, 6000, 1) + x("chr2", 8000, 9000, 1)
+    g += t("chr1", 7000, 9000, 2) + x("chr1", 7000, 7500, 2) + "chr1\tsrc\tCDS\t7100\t7400\t.\t+\t0\tgene_id \"G2\";\n" + x("chr1", 8000, 9000, 2)
+    g += t("scaffold_9", 10, 500, 3) + x("scaffold_9", 10, 500, 3) + t("chrX", 300, 900, 4) + x("chrX", 300, 900, 4)
+    g += t("chr1", 7000, 8500, 5) + x("chr1", 7000, 8500, 5) + t("chr1", 7000, 9000, 6, "\textra\tcolumns") + x("chr1", 7000, 9000, 6)
+    g += "# a comment in the middle\n" + t("chrUn_1", 100, 200, 7) + "chrUn_1\tlr2rmats\texon\t100\t200\n" + t("chr10", 1, 50, 8) + x("chr10", 1, 50, 8)
+    g += t("chrM", 2, 40, 9) + x("chrM", 2, 40, 9) + t("scaffold_9", 5, 20, 10) + x("scaffold_9", 5, 20, 10) + "chr2\tlr2rmats\ttranscript_like\t1\t2\t.\t+\t.\tx\n"
+    g += t("chr2", 5000, 9000, 11) + x("chr2", 5000, 9000, 11) + "\n" + t("chr1", 100, 200, 12).replace("\t", " ", 2) + x("chr1", 100, 200, 12)
+    return g
+case("c10_sort_gtf", {"unsorted.gtf": c10_gtf()}, {"sort": "sort-gtf unsorted.gtf sorted.gtf"})
+
 
 def add_synthetic():
     import numpy as np
@@ -199,14 +241,17 @@ def main():
             stdout_to = None
             if " > " in cmd:
                 cmd, stdout_to = cmd.split(" > ")
-            args = [x if not x.endswith((".sam", ".gtf", ".tab")) or x in ALLOUT.split() else os.path.join(d, x) for x in cmd.split()]
+            args = [x if not x.endswith((".sam", ".gtf", ".tab", ".fa")) or x in ALLOUT.split() else os.path.join(d, x) for x in cmd.split()]
             # inputs live in the case dir, outputs go to expected/<cname>/ (cwd)
             args = []
             toks = cmd.split(); outs = set(ALLOUT.split()[1::2])
             for x in toks:
                 args.append(os.path.join(d, x) if (os.path.exists(os.path.join(d, x)) and x not in outs) else x)
             with open(os.path.join(out, stdout_to) if stdout_to else os.devnull, "wb") as so:
-                p = subprocess.run([REF] + args, cwd=out, stdout=so, stderr=subprocess.PIPE)
+                if args[0] == "sort-gtf":             # the reference's script, not its binary (src/sort_gtf.sh)
+                    p = subprocess.run(["bash", "/root/reference/src/sort_gtf.sh"] + args[1:], cwd=out, stdout=so, stderr=subprocess.PIPE)
+                else:
+                    p = subprocess.run([REF] + args, cwd=out, stdout=so, stderr=subprocess.PIPE)
             if p.returncode != 0:
                 sys.exit(f"{name}/{cname}: reference failed: {p.stderr.decode()[-500:]}")
             # BAM outputs: store the decompressed stream (the compressed bytes depend on zlib, the records do not)

@@ -40,7 +40,8 @@ def lib():
         L.orc_bam2gtf.argtypes = [P(cabi.Batch), cabi.u32p, C.c_int64, P(cabi.ExonParams), P(cabi.ExonResult)]
         L.orc_update.argtypes = [P(cabi.ExonResult), P(cabi.Anno), P(cabi.Sj), P(cabi.UpdateParams), P(cabi.UpdateResult)]
         L.orc_unique.argtypes = [P(cabi.ExonResult), P(cabi.UpdateParams), P(cabi.UniqueResult)]
-        for f in ("orc_free_filter", "orc_free_exon", "orc_free_update", "orc_free_unique"):
+        L.orc_bam2sj.argtypes = [P(cabi.Batch), cabi.u8p, P(cabi.SjParams), P(cabi.Sj)]
+        for f in ("orc_free_filter", "orc_free_exon", "orc_free_update", "orc_free_unique", "orc_free_sj"):
             getattr(L, f).restype = None
         _lib = L
     return _lib
@@ -93,6 +94,17 @@ def unique(chains: dict, params: cabi.UpdateParams):
     out = cabi.unique_to_np(res)
     lib().orc_free_unique(C.byref(res))
     return 0, out
+
+
+def bam2sj(batch_soa: dict, is_uniq, params: cabi.SjParams) -> dict:
+    b, k1 = cabi.make_batch(batch_soa)
+    u = np.ascontiguousarray(is_uniq, np.uint8)
+    res = cabi.Sj()
+    rc = lib().orc_bam2sj(C.byref(b), u.ctypes.data_as(cabi.u8p), C.byref(params), C.byref(res))
+    assert rc == 0
+    out = {k: v.copy() for k, v in cabi.sj_to_np(res).items()}
+    lib().orc_free_sj(C.byref(res))
+    return out
 
 
 def run_bin(binary: str, args: list, stdout_path: str | None = None, check=True):

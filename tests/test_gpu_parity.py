@@ -516,3 +516,43 @@ def test_cross_chromosome_piece_replay(ctx, summary):
     assert ((piece >= 0) & (upd["cov"] > 1)).sum() > 0
     d = ctx.update_diag()
     assert d["pieces_across_chromosomes"] > 0, d         # settled by the rounds on the device, not by the one-locus replay
+
+
+@pytest.mark.parametrize("which", ["iso", "ont"])
+def test_bam2sj(ctx, data, which):
+    """bam2sj (parse_bam.c:896-985) on the device against the port's replay of the reference's sorted insertion: distinct junctions in
+    (tid, don, acc) order with unique / multi read counts; proper-pair filter (the only mode the reference can reach), -i."""
+    r = data[which]
+    rng = np.random.default_rng(7)
+    soa = dict(r.soa())
+    flag = soa["flag"].copy()
+    paired = rng.random(r.n) < 0.7
+    flag[paired] |= np.uint16(3)
+    flag[rng.random(r.n) < 0.02] |= np.uint16(4)
+    soa["flag"] = flag
+    uniq = (rng.random(r.n) < 0.8).astype(np.uint8)
+    for sp in (cabi.SjParams.default(), cabi.SjParams.default(min_intron=400), cabi.SjParams.default(pair_only=0)):
+        g = ctx.bam2sj(soa, uniq, sp); o = op.bam2sj(soa, uniq, sp)
+        assert_dict_equal(g, o)
+        assert len(o["tid"]) > 100 and (o["uniq_c"] + o["multi_c"]).max() > 1
+    # a stream that is not ordered by reference id is refused (the reference's insertion would leave an unsorted table)
+    from lr2rmats_b200 import api
+    rev = {k: (v[::-1].copy() if k not in ("cigar", "cigar_off") else v) for k, v in soa.items()}
+    lens = np.diff(soa["cigar_off"].astype(np.int64))[::-1]
+    rev["cigar_off"] = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    rev["cigar"] = np.concatenate([soa["cigar"][int(a):int(b)] for a, b in zip(soa["cigar_off"][:-1][::-1], soa["cigar_off"][1:][::-1])]) if r.n < 10000 else None
+    if rev["cigar"] is not None:
+        with pytest.raises(api.LrbError) as e:
+            ctx.bam2sj(rev, uniq[::-1].copy(), cabi.SjParams.default())
+        assert e.value.code == -4
+
+
+def test_sort3_is_a_stable_lexicographic_sort(ctx):
+    """lrb_sort3 (the `sort -n -k1..-k4` of src/sort_gtf.sh on the device): equals numpy's stable lexsort, ties keep the input order."""
+    rng = np.random.default_rng(11)
+    for n in (0, 1, 5, 4097, 300_000):
+        k0 = rng.integers(0, 40, n).astype(np.uint32); k1 = rng.integers(0, 2**32 - 1, n, dtype=np.uint64).astype(np.uint32) // np.uint32(1 << 12)
+        k2 = rng.integers(0, 3, n).astype(np.uint32) * np.uint32(0x7fffffff)
+        got = ctx.sort3(k0, k1, k2)
+        want = np.lexsort((np.arange(n), k2, k1, k0)).astype(np.uint32)
+        assert np.array_equal(got, want)

@@ -99,8 +99,27 @@ static int cmd_filter(int argc, char **argv, Engine &eng)
     if (rc) engine_fail(eng, "bam_filter", rc);
     tr.lap("tables upload");
     lrb_batch b = rec.view(); lrb_filter_result res;
-    rc = eng.filter(eng.self, &b, &fp, &res);
-    if (rc) engine_fail(eng, "bam_filter", rc);
+    for (int attempt = 0;; ++attempt) {
+        rc = eng.filter(eng.self, &b, &fp, &res);
+        if (rc) engine_fail(eng, "bam_filter", rc);
+        // The device forms the qname runs (bam_filter.c:129-159, strcmp on the passing subsequence) on 64-bit hashes of the names.  Every
+        // pair it took for equal is checked against the names here; two different names with one hash (2^-64 per pair) get fresh
+        // hashes and the stage runs again.
+        bool clash = false; int64_t prev = -1;
+        for (int64_t i = 0; i < res.n; ++i) {
+            if (!res.pass[i]) continue;
+            if (prev >= 0 && rec.qhash[(size_t)i] == rec.qhash[(size_t)prev] && strcmp(rec.qname((size_t)i), rec.qname((size_t)prev)) != 0) { clash = true; break; }
+            prev = i;
+        }
+        if (!clash) break;
+        if (attempt == 3) fatal("bam_filter", "query-name hash collisions persist");
+        for (size_t i = 0; i < rec.n(); ++i) {        // another hash function of the NAME (a function of the old hash would collide again)
+            uint64_t hsh = 0xCBF29CE484222325ull ^ ((uint64_t)(attempt + 1) * 0xD1B54A32D192ED03ull);
+            for (const char *q = rec.qname(i); *q; ++q) { hsh ^= (uint8_t)*q; hsh *= 0x100000001B3ull; hsh ^= hsh >> 31; }
+            rec.qhash[i] = hsh;
+        }
+        b = rec.view();
+    }
     tr.lap("engine");
     if (!write_bam(stdout, h, rec, res.keep_idx, res.n_keep, err)) fatal("bam_filter", err);
     tr.lap("emit");

@@ -41,7 +41,7 @@ struct PBuf {                                       // pinned host buffer
 };
 
 struct MergeBufs {                                  // scratch + output of one merge fold
-    Buf keys, head, locus_start, locus_cnt, dropped, rep, lstart, evmask, samemask, hard, desc, relsym, ckey, cmin, cord, clist, crow;
+    Buf keys, head, locus_start, locus_cnt, dropped, rep, lstart, evmask, samemask, hard, desc, relsym, ckey, cmin, cord, clist, crow, fb_list, fb_cnt;
     Buf w_cand, w_cov, w_tid, w_start, w_end, w_fs, w_le;
     Buf o_cand, o_cov, o_tid, o_start, o_end, o_fs, o_le;
     Buf c_tid, c_start, c_end, c_rev, c_n, c_fs, c_le, c_gbeg, c_hash, c_j0, c_sig;

@@ -140,6 +140,7 @@ struct MergeArgs {
     uint16_t *desc; uint64_t *relsym;               // flat fold: class descriptor per candidate; per representative the related representatives
     uint8_t *hard;                                  // per locus head: 1 = not for the flat kernels, >= 2 = not for fold_big_kernel either (merge_fold_kernel)
     uint8_t *cord; uint32_t *clist; uint64_t *crow;  // big loci: class ordinal per candidate; per locus (at its offset) the class representatives and their 128-bit relation rows
+    uint32_t *fb_list, *fb_cnt;                     // big loci: [0, n_cand) list of their locus ordinals, [n_cand, 2 n_cand) those that outgrew tier 0; counters
     uint64_t *ckey; uint32_t *cmin;                 // class table of the big loci: 2 * n_cand + 64 slots (NULL: big loci go to merge_fold_kernel)
     DMerged out;                                    // compacted result
     uint8_t *forced;                                // optional (split pieces, see XlArgs): 1 = this piece is absorbed by an entry of an earlier locus when its own locus has nothing for it (3: that happened in the last fold)

@@ -526,28 +526,15 @@ template <int G, int SLOTS> static void launch_classify_t(const ClassArgs &a, co
 void launch_classify(const ClassArgs &a, uint8_t *slow, cudaStream_t st)
 {
     if (a.rows.n <= 0) return;
-    static int g = -1, fast = -1, by_n = 0;
-    if (g < 0) { const char *e = getenv("LRB_CLASSIFY_G"); g = e ? atoi(e) : 4; e = getenv("LRB_CLASSIFY_FAST"); fast = e ? atoi(e) : 1; e = getenv("LRB_CR_SORT"); by_n = e ? atoi(e) : 1; }
+    // the common case (-d 0) row by row with rows dealt to lanes by exon count (128 threads, 8 CTAs per SM: measured best on B200,
+    // profiles/r01_v13_classify_*_ab.txt); what that kernel flags as slow (> 32 exons, non-monotone chains) and every row of -d > 0 goes
+    // through the general kernel, 4 lanes per row
     const uint8_t *only = nullptr;
-    if (fast && a.up.ss_dis == 0 && slow) {
-        static int crt = -1;
-        if (crt < 0) { const char *e = getenv("LRB_CR_THREADS"); crt = e ? atoi(e) : 128; }
-        static int minb = -1;
-        if (minb < 0) { const char *e = getenv("LRB_CR_MINB"); minb = e ? atoi(e) : 8; }
-        if (crt >= 256) classify_row_kernel<256, 4><<<(unsigned)((a.rows.n + 255) / 256), 256, 0, st>>>(a, slow, a.row_nonmono, by_n);
-        else if (crt <= 64) classify_row_kernel<64, 16><<<(unsigned)((a.rows.n + 63) / 64), 64, 0, st>>>(a, slow, a.row_nonmono, by_n);
-        else if (minb >= 10) classify_row_kernel<128, 10><<<(unsigned)((a.rows.n + 127) / 128), 128, 0, st>>>(a, slow, a.row_nonmono, by_n);   // <= 51 registers, a few spills
-        else classify_row_kernel<128, 8><<<(unsigned)((a.rows.n + 127) / 128), 128, 0, st>>>(a, slow, a.row_nonmono, by_n);
-        LRB_COUNT_LAUNCH();
+    if (a.up.ss_dis == 0 && slow) {
+        classify_row_kernel<128, 8><<<(unsigned)((a.rows.n + 127) / 128), 128, 0, st>>>(a, slow, a.row_nonmono, 1); LRB_COUNT_LAUNCH();
         only = slow;
     }
-    switch (g) {
-    case 1: launch_classify_t<1, 16>(a, only, st); break;
-    case 2: launch_classify_t<2, 16>(a, only, st); break;
-    case 4: launch_classify_t<4, 16>(a, only, st); break;
-    default: launch_classify_t<8, 64>(a, only, st); break;
-    }
-    LRB_COUNT_LAUNCH();
+    launch_classify_t<4, 16>(a, only, st); LRB_COUNT_LAUNCH();
 }
 
 // ------------------------------------------------------------------ class lists: novel_T / known_T / unrecog_T in one pass
@@ -938,6 +925,7 @@ __global__ void __launch_bounds__(256) fold_big_mark_kernel(MergeArgs a, const u
     for (int64_t loc = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32; loc < n_loci; loc += (int64_t)gridDim.x * blockDim.x / 32) {
         const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : cand_count(a);
         if (le - ls <= FF_MAX && !locus_hard[ls]) continue;
+        if (lane == 0) a.fb_list[atomicAdd(&a.fb_cnt[0], 1u)] = (uint32_t)loc;      // the later passes walk this list, not all loci
         for (int64_t c = ls + lane; c < le; c += 32) { a.desc[c] = FB_MEMBER; lstart[c] = (uint32_t)ls; }
     }
 }
@@ -993,13 +981,15 @@ __global__ void __launch_bounds__(256) fold_class_verify_kernel(MergeArgs a, Cla
 static constexpr int FB_MAXCLS = 127; static constexpr uint32_t FB_SINGLE = 127u, FB_NOROWS = 0xffffffffu;
 __global__ void __launch_bounds__(256) fold_class_rows_kernel(MergeArgs a, const uint32_t *__restrict__ rep, const uint8_t *__restrict__ locus_hard)
 {
-    const int64_t n_loci = (int64_t)a.totals[0];
-    const int lane = lane_id();
+    // per warp: the classes of the locus (exon count, sub-stream, junction signature, first junction, representative)
+    __shared__ uint64_t s_sig[8][128], s_j0[8][128]; __shared__ uint32_t s_rep[8][128]; __shared__ uint32_t s_nk[8][128];
+    const int64_t n_loci = (int64_t)a.totals[0], n_big = (int64_t)a.fb_cnt[0];
+    const int lane = lane_id(), w = warp_id();
     const CandSoA &cd = a.cd;
-    for (int64_t loc = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32; loc < n_loci; loc += (int64_t)gridDim.x * blockDim.x / 32) {
+    for (int64_t bi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32; bi < n_big; bi += (int64_t)gridDim.x * blockDim.x / 32) {
+        const int64_t loc = a.fb_list[bi];
         const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : cand_count(a);
-        const int hd = locus_hard[ls];
-        if ((le - ls <= FF_MAX && !hd) || hd >= 2) continue;
+        if (locus_hard[ls] >= 2) continue;
         int K = 0;
         for (int64_t c0 = ls; c0 < le; c0 += 32) {
             const int64_t c = c0 + lane;
@@ -1007,7 +997,11 @@ __global__ void __launch_bounds__(256) fold_class_rows_kernel(MergeArgs a, const
             const unsigned b = __ballot_sync(FULL, headc);
             if (headc) {
                 const int o = K + __popc(b & ((1u << lane) - 1u));
-                if (o < FB_MAXCLS) { a.cord[c] = (uint8_t)o; a.clist[ls + o] = (uint32_t)c; a.crow[2 * (ls + o)] = o < 64 ? 1ull << o : 0; a.crow[2 * (ls + o) + 1] = o >= 64 ? 1ull << (o - 64) : 0; }
+                if (o < FB_MAXCLS) {
+                    a.cord[c] = (uint8_t)o; a.crow[2 * (ls + o)] = o < 64 ? 1ull << o : 0; a.crow[2 * (ls + o) + 1] = o >= 64 ? 1ull << (o - 64) : 0;
+                    s_sig[w][o] = cd.sig[c]; s_j0[w][o] = cd.j0[c]; s_rep[w][o] = (uint32_t)c;
+                    s_nk[w][o] = (uint32_t)cd.n[c] | ((a.kls ? (uint32_t)a.kls[c] : 0u) << 24);
+                }
             }
             K += __popc(b);
         }
@@ -1021,17 +1015,18 @@ __global__ void __launch_bounds__(256) fold_class_rows_kernel(MergeArgs a, const
         for (int p = lane; p < K * K; p += 32) {
             const int i = p / K, j = p - i * K;
             if (i >= j) continue;
-            const uint32_t A = a.clist[ls + i], B = a.clist[ls + j];
-            const int nA = cd.n[A], nB = cd.n[B];
-            if (nA == nB) continue;                                  // equal exon counts: identical or unrelated, never partial
-            if (a.kls && a.kls[A] != a.kls[B]) continue;             // sub-streams never see each other
-            const uint32_t L = nA > nB ? A : B, Sh = nA > nB ? B : A;
-            const uint64_t sj0 = cd.j0[Sh];
-            if (!((cd.sig[L] >> junc_bit(sj0)) & 1ull)) continue;
-            if (!partial_static(a.ex, cd.gbeg[L], cd.n[L], (cd.rev[L] & 2) != 0, sj0, cd.gbeg[Sh], cd.n[Sh])) continue;
+            const uint32_t nkA = s_nk[w][i], nkB = s_nk[w][j];
+            const int nA = (int)(nkA & 0xFFFFFFu), nB = (int)(nkB & 0xFFFFFFu);
+            if (nA == nB || (nkA >> 24) != (nkB >> 24)) continue;    // equal exon counts: identical or unrelated, never partial; sub-streams never see each other
+            const int L = nA > nB ? i : j, Sh = nA > nB ? j : i;
+            const uint64_t sj0 = s_j0[w][Sh];
+            if (!((s_sig[w][L] >> junc_bit(sj0)) & 1ull)) continue;
+            const uint32_t cl = s_rep[w][L], cs = s_rep[w][Sh];
+            if (!partial_static(a.ex, cd.gbeg[cl], cd.n[cl], (cd.rev[cl] & 2) != 0, sj0, cd.gbeg[cs], cd.n[cs])) continue;
             atomicOr((unsigned long long *)&a.crow[2 * (ls + i) + (j >> 6)], 1ull << (j & 63));
             atomicOr((unsigned long long *)&a.crow[2 * (ls + j) + (i >> 6)], 1ull << (i & 63));
         }
+        __syncwarp();
     }
 }
 
@@ -1050,13 +1045,17 @@ __global__ void __launch_bounds__(FB_THREADS) fold_big_kernel(MergeArgs a, const
     const int end_dis = a.up.end_dis;
     for (;;) {
         // loci are claimed one at a time (their sizes differ by orders of magnitude)
+        // tier 0 walks the list of big loci (fold_big_mark_kernel), tier 1 the list of those whose survivors outgrew tier 0's slots
+        const uint32_t *list = TIER == 0 ? a.fb_list : a.fb_list + a.n_cand;
+        const uint32_t n_list = a.fb_cnt[TIER == 0 ? 0 : 2];
         uint32_t li = 0;
         if (lane == 0) li = atomicAdd(next_locus, 1u);
-        const int64_t loc = (int64_t)__shfl_sync(gm, li, 0, G);
-        if (loc >= n_loci) return;
+        li = __shfl_sync(gm, li, 0, G);
+        if (li >= n_list) return;
+        const int64_t loc = (int64_t)list[li];
         const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : cand_count(a);
         const int hd = locus_hard[ls];
-        if (TIER == 0 ? ((le - ls <= FF_MAX && !hd) || hd >= 2) : hd != 4) continue;       // folded already / another tier's / merge_fold_kernel's
+        if (TIER == 0 ? hd >= 2 : hd != 4) continue;                 // merge_fold_kernel's (class verification failed)
         if (le - ls >= FB_MAXREL) { if (lane == 0) locus_hard[ls] = 2; continue; }
         const bool use_rows = a.locus_cnt[loc] != FB_NOROWS;         // the static relation of the locus' classes is tabulated
         if (!use_rows) for (int i = lane; i < CACHE; i += G) S.cache[i] = 0;
@@ -1156,7 +1155,10 @@ __global__ void __launch_bounds__(FB_THREADS) fold_big_kernel(MergeArgs a, const
             }
             if (!overflow && have) alive[cl] = (uint8_t)l_alive;
         }
-        if (overflow) { if (lane == 0) locus_hard[ls] = TIER == 0 ? 4 : 2; continue; }   // the next tier / merge_fold_kernel redoes the locus from scratch
+        if (overflow) {                                              // the next tier / merge_fold_kernel redoes the locus from scratch
+            if (lane == 0) { locus_hard[ls] = TIER == 0 ? 4 : 2; if (TIER == 0) a.fb_list[a.n_cand + atomicAdd(&a.fb_cnt[2], 1u)] = (uint32_t)loc; }
+            continue;
+        }
         for (int k = lane; k < cnt; k += G) {
             const int64_t c = ls + (S.cand[k] & 0xFFFFu);
             a.work.cov[c] = S.cov[k]; a.work.start[c] = S.start[k]; a.work.end[c] = S.end[k]; a.work.fs[c] = S.fs[k]; a.work.le[c] = S.le[k];
@@ -1243,53 +1245,6 @@ __global__ void __launch_bounds__(256) fold_relrep_kernel(MergeArgs a, const uin
     }
 }
 
-// The same relation, warp-cooperative (LRB_FOLD_RELW=1; measured SLOWER on B200 -- fold 0.33 vs 0.27 ms -- and therefore not the
-// default): only class representatives have work in fold_relrep_kernel and their loops have
-// different lengths (3.8 active threads per instruction measured), so here the warp takes its representatives one after the
-// other (ballot) and all 32 lanes share the scan over that representative's predecessors: descriptor test and junction-signature
-// filter run on coalesced loads with full lanes, and only the rare signature hit walks the exon pools.
-__global__ void __launch_bounds__(256) fold_relrep_warp_kernel(MergeArgs a, const uint32_t *__restrict__ lstart)
-{
-    const int64_t c64 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const CandSoA &cd = a.cd;
-    const bool force = a.up.force_strand != 0;
-    const int lane = lane_id();
-    uint32_t ls = FF_BIG, d = 64u, gb_c = 0; int nc = 0; uint64_t sig_c = 0, j0_c = 0; int mono_c = 0;
-    bool is_rep = false;
-    if (c64 < cand_count(a)) {
-        ls = lstart[c64];
-        if (ls != FF_BIG) {
-            d = a.desc[c64];
-            is_rep = !(d & 64u) && (d & 63u) == (uint32_t)c64 - ls && (uint32_t)c64 > ls;      // multi-exon representative with predecessors
-            if (is_rep) { nc = cd.n[c64]; sig_c = cd.sig[c64]; j0_c = cd.j0[c64]; gb_c = cd.gbeg[c64]; mono_c = (cd.rev[c64] & 2) != 0; }
-        }
-    }
-    for (unsigned m = __ballot_sync(FULL, is_rep); m; m &= m - 1) {
-        const int src = __ffs(m) - 1;
-        const uint32_t r_c = (uint32_t)__shfl_sync(FULL, (uint32_t)c64, src), r_ls = __shfl_sync(FULL, ls, src), r_d = __shfl_sync(FULL, d, src);
-        const uint32_t r_gb = __shfl_sync(FULL, gb_c, src);
-        const int r_n = __shfl_sync(FULL, nc, src), r_mono = __shfl_sync(FULL, mono_c, src);
-        const uint64_t r_sig = __shfl_sync(FULL, sig_c, src), r_j0 = __shfl_sync(FULL, j0_c, src);
-        for (uint32_t e = r_ls + (uint32_t)lane; e < r_c; e += 32) {
-            const uint32_t de = a.desc[e];
-            if ((de & 64u) || (de & 63u) != e - r_ls || ((de ^ r_d) & 0x300u)) continue;          // single / not a representative / other sub-stream
-            if (force && ((de ^ r_d) & 128u)) continue;
-            const int ne = cd.n[e];
-            if (ne == r_n) continue;
-            bool hit;
-            if (r_n > ne) {
-                const uint64_t j0_e = cd.j0[e];
-                hit = ((r_sig >> junc_bit(j0_e)) & 1ull) && partial_static(a.ex, r_gb, r_n, r_mono != 0, j0_e, cd.gbeg[e], ne);
-            } else
-                hit = ((cd.sig[e] >> junc_bit(r_j0)) & 1ull) && partial_static(a.ex, cd.gbeg[e], ne, (cd.rev[e] & 2) != 0, r_j0, r_gb, r_n);
-            if (hit) {
-                atomicOr((unsigned long long *)&a.relsym[r_c], 1ull << (e - r_ls));
-                atomicOr((unsigned long long *)&a.relsym[e], 1ull << (r_c - r_ls));
-            }
-        }
-    }
-}
-
 // per candidate: the mask (over the <= 63 earlier candidates of its locus) of the entries that could absorb it -- members of its
 // own class (identical chains), members of classes in partial-match relation, other single-exon reads -- and, for class
 // folds, the mask of the earlier candidates of its own sub-stream
@@ -1320,110 +1275,6 @@ __global__ void __launch_bounds__(256) fold_relasm_kernel(MergeArgs a, const uin
     }
     evmask[c] = mask;
     if (a.kls) a.samemask[c] = same;
-}
-
-// The three relation passes above in ONE launch, on shared memory: a block owns FR_THREADS consecutive candidates and stages
-// their flattened fields together with a halo of the FF_MAX-1 candidates in front (a candidate deeper than that in its locus
-// is beyond the masks anyway), so the class search, the representative-pair relation and the mask assembly of a locus never
-// leave the SM; the exon pools are touched only to verify a class (once per member) and a signature hit.  Relations between
-// halo representatives are recomputed by the block that needs them instead of being exchanged through global atomics.
-static constexpr int FR_THREADS = 256, FR_HALO = FF_MAX - 1, FR_N = FR_THREADS + FR_HALO;
-__global__ void __launch_bounds__(FR_THREADS) fold_rel_kernel(MergeArgs a, uint32_t *__restrict__ rep, uint32_t *__restrict__ lstart,
-                                                              uint64_t *__restrict__ evmask, uint8_t *locus_hard)
-{
-    __shared__ uint64_t s_hash[FR_N], s_j0[FR_N], s_sig[FR_N];
-    __shared__ unsigned long long s_rel[FR_N];
-    __shared__ uint32_t s_gbeg[FR_N];
-    __shared__ int s_n[FR_N];
-    __shared__ int16_t s_ls[FR_N];                  // tile slot of the locus head; -1: out of reach (deeper than the masks, or not needed)
-    __shared__ uint16_t s_desc[FR_N];               // [0:5] class representative (locus-local), [6] single exon, [7] strand, [8:9] sub-stream
-    __shared__ uint8_t s_fl[FR_N];                  // bit 0 locus head, bit 1 strand, bit 2 monotone exon ends
-    const int64_t n_cand = cand_count(a);
-    const int64_t c0 = (int64_t)blockIdx.x * FR_THREADS;
-    if (c0 >= n_cand) return;
-    const int64_t base = c0 - FR_HALO;              // candidate of tile slot 0 (negative in the first block)
-    const CandSoA &cd = a.cd;
-    const bool force = a.up.force_strand != 0;
-    for (int i = threadIdx.x; i < FR_N; i += FR_THREADS) {
-        const int64_t c = base + i;
-        if (c >= 0 && c < n_cand) {
-            const int rv = cd.rev[c];
-            s_n[i] = cd.n[c]; s_hash[i] = cd.hash[c]; s_j0[i] = cd.j0[c]; s_sig[i] = cd.sig[c]; s_gbeg[i] = cd.gbeg[c];
-            s_fl[i] = (uint8_t)((a.head[c] ? 1 : 0) | ((rv & 1) << 1) | ((rv & 2) << 1));
-            s_desc[i] = (uint16_t)(a.kls ? ((uint32_t)a.kls[c] << 8) : 0u);
-        } else { s_n[i] = 0; s_fl[i] = 1; s_desc[i] = 0; s_hash[i] = 0; s_j0[i] = 0; s_sig[i] = 0; s_gbeg[i] = 0; }
-        s_rel[i] = 0ull; s_ls[i] = -1;
-    }
-    __syncthreads();
-    // ---- classes: first earlier candidate of the locus with the same (exon count, chain hash[, strand], sub-stream)
-    for (int i = threadIdx.x; i < FR_N; i += FR_THREADS) {
-        const int64_t c = base + i;
-        if (c < 0 || c >= n_cand) continue;
-        const int nc = s_n[i]; const uint64_t hc = s_hash[i]; const uint32_t kc = s_desc[i] & 0x300u; const int rvc = (s_fl[i] >> 1) & 1;
-        int e = i, r = i, steps = 0; bool reach = true;
-        while (!(s_fl[e] & 1)) {
-            if (++steps >= FF_MAX || e == 0) { reach = false; break; }
-            --e;
-            if (nc > 1 && s_n[e] == nc && s_hash[e] == hc && (!force || ((s_fl[e] >> 1) & 1) == rvc) && (s_desc[e] & 0x300u) == kc) r = e;
-        }
-        if (!reach) continue;
-        if (r != i && i >= FR_HALO) {                // own member of a class: verify it on the pools (the halo's were verified by their block)
-            const uint32_t gc = s_gbeg[i], gr = s_gbeg[r];
-            bool same = true;
-            for (int k = 0; k < nc - 1; ++k) same = same && a.ex.ee[gc + k] == a.ex.ee[gr + k] && a.ex.es[gc + k + 1] == a.ex.es[gr + k + 1];
-            if (!same) locus_hard[base + e] = 1;
-        }
-        s_ls[i] = (int16_t)e;
-        s_desc[i] = (uint16_t)(kc | (uint32_t)(r - e) | (nc == 1 ? 64u : 0u) | ((uint32_t)rvc << 7));
-    }
-    __syncthreads();
-    // ---- partial-match relation between the class representatives of the loci that reach into the block's own range
-    const int first_ls = s_ls[FR_HALO] >= 0 ? s_ls[FR_HALO] : FR_HALO;
-    for (int i = threadIdx.x; i < FR_N; i += FR_THREADS) {
-        const int ls = s_ls[i];
-        if (ls < 0 || i < first_ls) continue;
-        const uint32_t d = s_desc[i];
-        if ((d & 64u) || (int)(d & 63u) != i - ls) continue;            // single exon, or not the representative of its class
-        const int nc = s_n[i]; const uint64_t sig_c = s_sig[i], j0_c = s_j0[i]; const uint32_t gb_c = s_gbeg[i]; const bool mono_c = (s_fl[i] & 4) != 0;
-        for (int e = ls; e < i; ++e) {
-            const uint32_t de = s_desc[e];
-            if ((de & 64u) || (int)(de & 63u) != e - ls || ((de ^ d) & 0x300u)) continue;
-            if (force && ((de ^ d) & 128u)) continue;
-            const int ne = s_n[e];
-            if (ne == nc) continue;
-            bool hit;
-            if (nc > ne) { const uint64_t j0_e = s_j0[e]; hit = ((sig_c >> junc_bit(j0_e)) & 1ull) && partial_static(a.ex, gb_c, nc, mono_c, j0_e, s_gbeg[e], ne); }
-            else hit = ((s_sig[e] >> junc_bit(j0_c)) & 1ull) && partial_static(a.ex, s_gbeg[e], ne, (s_fl[e] & 4) != 0, j0_c, gb_c, nc);
-            if (hit) { atomicOr(&s_rel[i], 1ull << (e - ls)); atomicOr(&s_rel[e], 1ull << (i - ls)); }
-        }
-    }
-    __syncthreads();
-    // ---- own candidates: the earlier entries of the locus that could absorb them (and, for class folds, those of their sub-stream)
-    {
-        const int i = FR_HALO + threadIdx.x; const int64_t c = base + i;
-        if (c >= n_cand) return;
-        const int ls = s_ls[i];
-        if (ls < 0) { lstart[c] = FF_BIG; rep[c] = (uint32_t)c; return; }
-        const uint32_t d = s_desc[i];
-        uint64_t mask = 0, same = 0;
-        if (d & 64u) {
-            for (int e = ls; e < i; ++e) {
-                const uint32_t de = s_desc[e]; const uint64_t bit = 1ull << (e - ls);
-                if (!((de ^ d) & 0x300u)) { same |= bit; if ((de & 64u) && !(force && ((de ^ d) & 128u))) mask |= bit; }
-            }
-        } else {
-            const uint32_t r = d & 63u;
-            const uint64_t rel = s_rel[ls + r] | (1ull << r);
-            for (int e = ls; e < i; ++e) {
-                const uint32_t de = s_desc[e]; const uint64_t bit = 1ull << (e - ls);
-                if (!((de ^ d) & 0x300u)) same |= bit;
-                if (!(de & 64u) && ((rel >> (de & 63u)) & 1ull)) mask |= bit;
-            }
-        }
-        rep[c] = (uint32_t)(base + ls + (d & 63u)); lstart[c] = (uint32_t)(base + ls);
-        evmask[c] = mask;
-        if (a.kls) a.samemask[c] = same;
-    }
 }
 
 // thread per locus.  The entries of T (the survivors so far) live in shared-memory slots in insertion order -- the back-scan
@@ -1547,68 +1398,37 @@ void launch_merge_fold(const MergeArgs &a, cudaStream_t st)
     if (a.n_cand <= 0) return;
     // tlist reuses the (no longer needed) 64-bit key scratch; alive goes to `dropped`.  Grids are sized for the worst
     // case (every candidate its own locus); the locus count is read on the device.
-    static int flat = -1;
-    if (flat < 0) { const char *e = getenv("LRB_FOLD_FLAT"); flat = e ? atoi(e) : 1; }
-    if (flat && a.up.ss_dis == 0) {
+    if (a.up.ss_dis == 0) {
         cudaMemsetAsync(a.hard, 0, (size_t)a.n_cand, st);
         const unsigned bl = (unsigned)((a.n_cand + 255) / 256);
-        static int fused = -1;
-        if (fused < 0) { const char *e = getenv("LRB_FOLD_FUSED"); fused = e ? atoi(e) : 0; }
-        if (fused) { fold_rel_kernel<<<bl, FR_THREADS, 0, st>>>(a, a.rep, a.lstart, a.evmask, a.hard); LRB_COUNT_LAUNCH(); }
-        else {
-            fold_rep_kernel<<<bl, 256, 0, st>>>(a, a.rep, a.lstart, a.hard); LRB_COUNT_LAUNCH();
-            static int relw = -1;
-            if (relw < 0) { const char *e = getenv("LRB_FOLD_RELW"); relw = e ? atoi(e) : 0; }
-            if (relw) fold_relrep_warp_kernel<<<bl, 256, 0, st>>>(a, a.lstart); else fold_relrep_kernel<<<bl, 256, 0, st>>>(a, a.lstart);
-            LRB_COUNT_LAUNCH();
-            fold_relasm_kernel<<<bl, 256, 0, st>>>(a, a.lstart, a.evmask); LRB_COUNT_LAUNCH();
-        }
-        static int slots = -1;
-        if (slots < 0) { const char *e = getenv("LRB_FOLD_SLOTS"); slots = e ? atoi(e) : 32; }
+        fold_rep_kernel<<<bl, 256, 0, st>>>(a, a.rep, a.lstart, a.hard); LRB_COUNT_LAUNCH();
+        fold_relrep_kernel<<<bl, 256, 0, st>>>(a, a.lstart); LRB_COUNT_LAUNCH();
+        fold_relasm_kernel<<<bl, 256, 0, st>>>(a, a.lstart, a.evmask); LRB_COUNT_LAUNCH();
         const unsigned bs = (unsigned)((a.n_cand + FS_THREADS - 1) / FS_THREADS);
-        if (slots <= 16) fold_seq_kernel<16><<<bs, FS_THREADS, 0, st>>>(a, a.rep, a.evmask, a.hard, a.dropped);
-        else if (slots <= 24) fold_seq_kernel<24><<<bs, FS_THREADS, 0, st>>>(a, a.rep, a.evmask, a.hard, a.dropped);
-        else fold_seq_kernel<32><<<bs, FS_THREADS, 0, st>>>(a, a.rep, a.evmask, a.hard, a.dropped);
-        LRB_COUNT_LAUNCH();
+        fold_seq_kernel<32><<<bs, FS_THREADS, 0, st>>>(a, a.rep, a.evmask, a.hard, a.dropped); LRB_COUNT_LAUNCH();
         // loci beyond the masks and the ones the flat kernels gave up on: classes through one table, then warp per locus with the survivors
         // in shared memory; what outgrows the slots there (hard >= 2) is replayed from global memory
-        static int big = -1;
-        if (big < 0) { const char *e = getenv("LRB_FOLD_BIG"); big = e ? atoi(e) : 1; }
         int64_t bl2 = (a.n_cand / (FF_MAX + 1) + 1 + 3) / 4 + 8; if (bl2 > 148 * 8) bl2 = 148 * 8;
-        if (big && a.ckey) {
-            using S0 = FbSlots<64, 256>; using S1 = FbSlots<416, 1024>;
-            auto k0 = fold_big_kernel<8, 64, 256, 0>; auto k1 = fold_big_kernel<32, 416, 1024, 1>;
-            const size_t smem0 = sizeof(S0) * (FB_THREADS / 8), smem1 = sizeof(S1) * (FB_THREADS / 32);
+        if (a.ckey) {
+            using S0 = FbSlots<128, 256>; using S1 = FbSlots<416, 1024>;
+            auto k0 = fold_big_kernel<32, 128, 256, 0>; auto k1 = fold_big_kernel<32, 416, 1024, 1>;
+            const size_t smem0 = sizeof(S0) * (FB_THREADS / 32), smem1 = sizeof(S1) * (FB_THREADS / 32);
             static bool attr = false;
             if (!attr) { cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0); cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1); attr = true; }
             ClassTab tab{(unsigned long long *)a.ckey, a.cmin, (uint64_t)a.n_cand * 2 + 64};
             cudaMemsetAsync(a.ckey, 0xFF, tab.cap * 8, st); cudaMemsetAsync(a.cmin, 0xFF, tab.cap * 4, st);
+            cudaMemsetAsync(a.fb_cnt, 0, 32, st);                     // [0] big loci, [1] tier-0 claims, [2] tier-0 overflows, [3] tier-1 claims
             int64_t blm = (a.n_cand / 8 + 255) / 256 + 1; if (blm > 148 * 8) blm = 148 * 8;
             fold_big_mark_kernel<<<(unsigned)blm, 256, 0, st>>>(a, a.hard, a.lstart); LRB_COUNT_LAUNCH();
             fold_class_insert_kernel<<<bl, 256, 0, st>>>(a, tab, a.lstart); LRB_COUNT_LAUNCH();
             fold_class_verify_kernel<<<bl, 256, 0, st>>>(a, tab, a.rep, a.lstart, a.hard); LRB_COUNT_LAUNCH();
             fold_class_rows_kernel<<<(unsigned)blm, 256, 0, st>>>(a, a.rep, a.hard); LRB_COUNT_LAUNCH();
-            uint32_t *next_locus = a.ticket;                         // the prepare pass is over: its ticket is free
-            cudaMemsetAsync(next_locus, 0, 4, st);
-            int64_t blb = (a.n_cand / (FF_MAX + 1) + 1) / (FB_THREADS / 8) + 1; if (blb > 148 * 3) blb = 148 * 3;
-            static int fbg = -1;
-            if (fbg < 0) { const char *e = getenv("LRB_FB_G"); fbg = e ? atoi(e) : 32; }
-            if (fbg == 16) {
-                auto k16 = fold_big_kernel<16, 96, 256, 0>; const size_t sm16 = sizeof(FbSlots<96, 256>) * (FB_THREADS / 16);
-                static bool a16 = false; if (!a16) { cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm16); a16 = true; }
-                blb = (a.n_cand / (FF_MAX + 1) + 1) / (FB_THREADS / 16) + 1; if (blb > 148 * 4) blb = 148 * 4;
-                k16<<<(unsigned)blb, FB_THREADS, sm16, st>>>(a, a.rep, a.dropped, a.hard, next_locus);
-            } else if (fbg == 32) {
-                auto k32 = fold_big_kernel<32, 128, 256, 0>; const size_t sm32 = sizeof(FbSlots<128, 256>) * (FB_THREADS / 32);
-                static bool a32 = false; if (!a32) { cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm32); a32 = true; }
-                blb = (a.n_cand / (FF_MAX + 1) + 1) / (FB_THREADS / 32) + 1; if (blb > 148 * 6) blb = 148 * 6;
-                k32<<<(unsigned)blb, FB_THREADS, sm32, st>>>(a, a.rep, a.dropped, a.hard, next_locus);
-            } else
-                k0<<<(unsigned)blb, FB_THREADS, smem0, st>>>(a, a.rep, a.dropped, a.hard, next_locus);
-            LRB_COUNT_LAUNCH();
-            cudaMemsetAsync(next_locus, 0, 4, st);
-            blb = (a.n_cand / (FF_MAX + 1) + 1) / (FB_THREADS / 32) + 1; if (blb > 148 * 2) blb = 148 * 2;
-            k1<<<(unsigned)blb, FB_THREADS, smem1, st>>>(a, a.rep, a.dropped, a.hard, next_locus); LRB_COUNT_LAUNCH();
+            // one warp per locus, loci claimed from the lists: a whole warp measured fastest (8 / 16 lanes per locus: 17.5 / 15.8 ms per
+            // step against 14.2 ms on the 10 M-read data set -- the lane groups of a warp diverge)
+            int64_t blb = (a.n_cand / (FF_MAX + 1) + 1) / (FB_THREADS / 32) + 1; if (blb > 148 * 6) blb = 148 * 6;
+            k0<<<(unsigned)blb, FB_THREADS, smem0, st>>>(a, a.rep, a.dropped, a.hard, a.fb_cnt + 1); LRB_COUNT_LAUNCH();
+            if (blb > 148 * 2) blb = 148 * 2;
+            k1<<<(unsigned)blb, FB_THREADS, smem1, st>>>(a, a.rep, a.dropped, a.hard, a.fb_cnt + 3); LRB_COUNT_LAUNCH();
             merge_fold_kernel<32><<<(unsigned)bl2, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, a.hard, 0x7fffffff, 0x7fffffff, (1 << 2) | (1 << 3));
         } else
             merge_fold_kernel<32><<<(unsigned)bl2, MF_THREADS, 0, st>>>(a, (uint32_t *)a.keys, a.dropped, a.hard, FF_MAX + 1, 0x7fffffff, 0xFE);

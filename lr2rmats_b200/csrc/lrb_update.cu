@@ -925,7 +925,12 @@ __global__ void __launch_bounds__(256) fold_big_mark_kernel(MergeArgs a, const u
     for (int64_t loc = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32; loc < n_loci; loc += (int64_t)gridDim.x * blockDim.x / 32) {
         const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : cand_count(a);
         if (le - ls <= FF_MAX && !locus_hard[ls]) continue;
-        if (lane == 0) a.fb_list[atomicAdd(&a.fb_cnt[0], 1u)] = (uint32_t)loc;      // the later passes walk this list, not all loci
+        // the later passes walk this list, not all loci; an entry is (locus, sub-stream): the four class folds of the summary run over the
+        // same rows but never see each other's entries, so each gets its own replay (and its own, four times shorter, survivor list)
+        if (lane < (a.kls ? 4 : 1)) {
+            const uint32_t i = atomicAdd(&a.fb_cnt[0], 1u);
+            if (i < (uint32_t)a.n_cand) a.fb_list[i] = ((uint32_t)loc << 2) | (uint32_t)lane; else a.hard[ls] = 2;    // (cannot happen for loci beyond the masks)
+        }
         for (int64_t c = ls + lane; c < le; c += 32) { a.desc[c] = FB_MEMBER; lstart[c] = (uint32_t)ls; }
     }
 }
@@ -978,7 +983,7 @@ __global__ void __launch_bounds__(256) fold_class_verify_kernel(MergeArgs a, Cla
 // the locus (identity on the diagonal, partial match elsewhere: gtf.c:76-91 on the chains of the two representatives) becomes a
 // 128-bit row per class.  The replay then needs no exon pool at all: "can this survivor absorb the candidate" is one bit test.
 // Loci with more than FB_MAXCLS classes keep locus_cnt = FB_NOROWS and the replay falls back to its relation cache.
-static constexpr int FB_MAXCLS = 127; static constexpr uint32_t FB_SINGLE = 127u, FB_NOROWS = 0xffffffffu;
+static constexpr int FB_MAXCLS = 127; static constexpr uint32_t FB_SINGLE = 127u, FB_NOROWS = 0xffu;
 __global__ void __launch_bounds__(256) fold_class_rows_kernel(MergeArgs a, const uint32_t *__restrict__ rep, const uint8_t *__restrict__ locus_hard)
 {
     // per warp: the classes of the locus (exon count, sub-stream, junction signature, first junction, representative)
@@ -986,45 +991,44 @@ __global__ void __launch_bounds__(256) fold_class_rows_kernel(MergeArgs a, const
     const int64_t n_loci = (int64_t)a.totals[0], n_big = (int64_t)a.fb_cnt[0];
     const int lane = lane_id(), w = warp_id();
     const CandSoA &cd = a.cd;
-    for (int64_t bi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32; bi < n_big; bi += (int64_t)gridDim.x * blockDim.x / 32) {
-        const int64_t loc = a.fb_list[bi];
+    for (int64_t bi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32; bi < min(n_big, a.n_cand); bi += (int64_t)gridDim.x * blockDim.x / 32) {
+        const int64_t loc = a.fb_list[bi] >> 2; const uint32_t my = a.fb_list[bi] & 3u;
         const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : cand_count(a);
         if (locus_hard[ls] >= 2) continue;
         int K = 0;
         for (int64_t c0 = ls; c0 < le; c0 += 32) {
             const int64_t c = c0 + lane;
-            const bool headc = c < le && cd.n[c] > 1 && rep[c] == (uint32_t)c;
+            const bool headc = c < le && cd.n[c] > 1 && rep[c] == (uint32_t)c && (!a.kls || a.kls[c] == my);
             const unsigned b = __ballot_sync(FULL, headc);
             if (headc) {
                 const int o = K + __popc(b & ((1u << lane) - 1u));
-                if (o < FB_MAXCLS) {
-                    a.cord[c] = (uint8_t)o; a.crow[2 * (ls + o)] = o < 64 ? 1ull << o : 0; a.crow[2 * (ls + o) + 1] = o >= 64 ? 1ull << (o - 64) : 0;
-                    s_sig[w][o] = cd.sig[c]; s_j0[w][o] = cd.j0[c]; s_rep[w][o] = (uint32_t)c;
-                    s_nk[w][o] = (uint32_t)cd.n[c] | ((a.kls ? (uint32_t)a.kls[c] : 0u) << 24);
+                if (o < FB_MAXCLS) {                 // rows live at the representative's own index: a class of the locus, whatever its sub-stream
+                    a.cord[c] = (uint8_t)o; a.crow[2 * c] = o < 64 ? 1ull << o : 0; a.crow[2 * c + 1] = o >= 64 ? 1ull << (o - 64) : 0;
+                    s_sig[w][o] = cd.sig[c]; s_j0[w][o] = cd.j0[c]; s_rep[w][o] = (uint32_t)c; s_nk[w][o] = (uint32_t)cd.n[c];
                 }
             }
             K += __popc(b);
         }
-        if (lane == 0) a.locus_cnt[loc] = K <= FB_MAXCLS ? (uint32_t)K : FB_NOROWS;
+        if (lane == 0) ((uint8_t *)&a.locus_cnt[loc])[my] = K <= FB_MAXCLS ? (uint8_t)K : (uint8_t)FB_NOROWS;
         if (K > FB_MAXCLS) continue;
         __syncwarp();
         for (int64_t c = ls + lane; c < le; c += 32) {
+            if (a.kls && a.kls[c] != my) continue;
             if (cd.n[c] < 2) a.cord[c] = (uint8_t)FB_SINGLE;
             else if (rep[c] != (uint32_t)c) a.cord[c] = a.cord[rep[c]];
         }
         for (int p = lane; p < K * K; p += 32) {
             const int i = p / K, j = p - i * K;
             if (i >= j) continue;
-            const uint32_t nkA = s_nk[w][i], nkB = s_nk[w][j];
-            const int nA = (int)(nkA & 0xFFFFFFu), nB = (int)(nkB & 0xFFFFFFu);
-            if (nA == nB || (nkA >> 24) != (nkB >> 24)) continue;    // equal exon counts: identical or unrelated, never partial; sub-streams never see each other
+            const int nA = (int)s_nk[w][i], nB = (int)s_nk[w][j];
+            if (nA == nB) continue;                                  // equal exon counts: identical or unrelated, never partial
             const int L = nA > nB ? i : j, Sh = nA > nB ? j : i;
             const uint64_t sj0 = s_j0[w][Sh];
             if (!((s_sig[w][L] >> junc_bit(sj0)) & 1ull)) continue;
             const uint32_t cl = s_rep[w][L], cs = s_rep[w][Sh];
             if (!partial_static(a.ex, cd.gbeg[cl], cd.n[cl], (cd.rev[cl] & 2) != 0, sj0, cd.gbeg[cs], cd.n[cs])) continue;
-            atomicOr((unsigned long long *)&a.crow[2 * (ls + i) + (j >> 6)], 1ull << (j & 63));
-            atomicOr((unsigned long long *)&a.crow[2 * (ls + j) + (i >> 6)], 1ull << (i & 63));
+            atomicOr((unsigned long long *)&a.crow[2 * (size_t)s_rep[w][i] + (j >> 6)], 1ull << (j & 63));
+            atomicOr((unsigned long long *)&a.crow[2 * (size_t)s_rep[w][j] + (i >> 6)], 1ull << (i & 63));
         }
         __syncwarp();
     }
@@ -1047,17 +1051,17 @@ __global__ void __launch_bounds__(FB_THREADS) fold_big_kernel(MergeArgs a, const
         // loci are claimed one at a time (their sizes differ by orders of magnitude)
         // tier 0 walks the list of big loci (fold_big_mark_kernel), tier 1 the list of those whose survivors outgrew tier 0's slots
         const uint32_t *list = TIER == 0 ? a.fb_list : a.fb_list + a.n_cand;
-        const uint32_t n_list = a.fb_cnt[TIER == 0 ? 0 : 2];
+        const uint32_t n_list = min(a.fb_cnt[TIER == 0 ? 0 : 2], (uint32_t)a.n_cand);
         uint32_t li = 0;
         if (lane == 0) li = atomicAdd(next_locus, 1u);
         li = __shfl_sync(gm, li, 0, G);
         if (li >= n_list) return;
-        const int64_t loc = (int64_t)list[li];
+        const int64_t loc = (int64_t)(list[li] >> 2); const int my = (int)(list[li] & 3u);      // (locus, sub-stream)
         const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : cand_count(a);
         const int hd = locus_hard[ls];
-        if (TIER == 0 ? hd >= 2 : hd != 4) continue;                 // merge_fold_kernel's (class verification failed)
+        if (TIER == 0 ? (hd == 2 || hd == 3) : hd != 4) continue;    // merge_fold_kernel's (class verification failed, list overflow)
         if (le - ls >= FB_MAXREL) { if (lane == 0) locus_hard[ls] = 2; continue; }
-        const bool use_rows = a.locus_cnt[loc] != FB_NOROWS;         // the static relation of the locus' classes is tabulated
+        const bool use_rows = ((const uint8_t *)&a.locus_cnt[loc])[my] != FB_NOROWS;      // the static relation of the sub-stream's classes is tabulated
         if (!use_rows) for (int i = lane; i < CACHE; i += G) S.cache[i] = 0;
         __syncwarp(gm);
         int cnt = 0; bool overflow = false;
@@ -1070,10 +1074,11 @@ __global__ void __launch_bounds__(FB_THREADS) fold_big_kernel(MergeArgs a, const
             const uint32_t l_rep = have ? rep[cl] : 0;
             const int l_kls = (have && a.kls) ? a.kls[cl] : 0;
             const uint32_t l_ord = (have && use_rows) ? a.cord[cl] : FB_SINGLE;
-            const uint64_t l_row0 = l_ord != FB_SINGLE ? a.crow[2 * (ls + l_ord)] : 0, l_row1 = l_ord != FB_SINGLE ? a.crow[2 * (ls + l_ord) + 1] : 0;
+            const uint64_t l_row0 = l_ord != FB_SINGLE ? a.crow[2 * (size_t)l_rep] : 0, l_row1 = l_ord != FB_SINGLE ? a.crow[2 * (size_t)l_rep + 1] : 0;
             int l_alive = 0;
             const int nb = (int)min((int64_t)G, le - c0);
             for (int q = 0; q < nb; ++q) {
+                if (a.kls && __shfl_sync(gm, l_kls, q, G) != my) continue;       // another sub-stream's row: its own replay takes it
                 const int t_tid = __shfl_sync(gm, l_tid, q, G), t_start = __shfl_sync(gm, l_start, q, G), t_end = __shfl_sync(gm, l_end, q, G), t_rv = __shfl_sync(gm, l_rv, q, G);
                 const int t_kls = __shfl_sync(gm, l_kls, q, G), t_n = __shfl_sync(gm, l_n, q, G), t_fs = __shfl_sync(gm, l_fs, q, G), t_le = __shfl_sync(gm, l_le, q, G);
                 const uint32_t t_gbeg = __shfl_sync(gm, l_gbeg, q, G), t_rep = __shfl_sync(gm, l_rep, q, G);
@@ -1153,10 +1158,10 @@ __global__ void __launch_bounds__(FB_THREADS) fold_big_kernel(MergeArgs a, const
                 }
                 __syncwarp(gm);
             }
-            if (!overflow && have) alive[cl] = (uint8_t)l_alive;
+            if (!overflow && have && (!a.kls || l_kls == my)) alive[cl] = (uint8_t)l_alive;
         }
         if (overflow) {                                              // the next tier / merge_fold_kernel redoes the locus from scratch
-            if (lane == 0) { locus_hard[ls] = TIER == 0 ? 4 : 2; if (TIER == 0) a.fb_list[a.n_cand + atomicAdd(&a.fb_cnt[2], 1u)] = (uint32_t)loc; }
+            if (lane == 0) { locus_hard[ls] = TIER == 0 ? 4 : 2; if (TIER == 0) a.fb_list[a.n_cand + atomicAdd(&a.fb_cnt[2], 1u)] = list[li]; }
             continue;
         }
         for (int k = lane; k < cnt; k += G) {

@@ -67,7 +67,7 @@ struct MultiState {
     Buf g_name, g_piece, g_ttid, g_tstart, g_tend, g_trev, g_etid, g_erev, g_cov, g_ref, g_off, g_es, g_ee, g_flag;
     Buf g_bd_tid, g_bd_s, g_bd_e, g_bd_sc, g_bd_ty, g_bd_rv, g_kg;
     Buf v_ident, v_zeros, v_cnt, v_fs, v_le;          // the gathered table in the shape the set kernels read
-    Buf tab, y_barcnt, y_barseg, y_genebar, y_bedcnt, y_bedoff, y_counts, y_nelem, tiles;
+    Buf tab, y_barcnt, y_barseg, y_genebar, y_bedcnt, y_bedoff, y_counts, y_nelem, tiles, xs_pl, xs_hx, xs_cnt;
     int64_t n = 0, n_exon = 0, n_bed = 0; int32_t summary[LRB_S_COUNT]; bool have = false, daj_recomputed = false;
     PBuf p[24];
     float ms_gather = 0, ms_merge = 0; cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -81,7 +81,7 @@ void multi_release(lrb_ctx *c)
     Buf *bufs[] = {&m->meta_dev, &m->shard_end_dev, &m->flags_dev, &m->g_name, &m->g_piece, &m->g_ttid, &m->g_tstart, &m->g_tend, &m->g_trev, &m->g_etid, &m->g_erev,
                    &m->g_cov, &m->g_ref, &m->g_off, &m->g_es, &m->g_ee, &m->g_flag, &m->g_bd_tid, &m->g_bd_s, &m->g_bd_e, &m->g_bd_sc, &m->g_bd_ty, &m->g_bd_rv, &m->g_kg,
                    &m->v_ident, &m->v_zeros, &m->v_cnt, &m->v_fs, &m->v_le, &m->tab, &m->y_barcnt, &m->y_barseg, &m->y_genebar, &m->y_bedcnt, &m->y_bedoff, &m->y_counts,
-                   &m->y_nelem, &m->tiles};
+                   &m->y_nelem, &m->tiles, &m->xs_pl, &m->xs_hx, &m->xs_cnt};
     for (Buf *b : bufs) b->release();
     m->meta_host.release();
     for (PBuf &p : m->p) p.release();
@@ -318,6 +318,10 @@ int lrb_update_gather(lrb_ctx *c, int64_t name_base)
         sa.bar_cnt = m->y_barcnt.as<uint32_t>(); sa.bar_seg = m->y_barseg.as<uint32_t>(); sa.gene_bar = m->y_genebar.as<uint64_t>();
         sa.bed_cnt = m->y_bedcnt.as<uint32_t>(); sa.bed_off = m->y_bedoff.as<uint32_t>(); sa.counts = m->y_counts.as<uint32_t>();
         sa.shard_end = m->shard_end_dev.as<int64_t>(); sa.n_shards = R; sa.probe = detect ? 1 : 0;
+        if (detect) {
+            NEED(m->xs_pl, n1 * 4); NEED(m->xs_hx, n1 * 4); NEED(m->xs_cnt, 64);
+            sa.xs_pl = m->xs_pl.as<uint32_t>(); sa.xs_hx = m->xs_hx.as<uint32_t>(); sa.xs_cnt = m->xs_cnt.as<uint32_t>(); sa.xs_cap = (uint32_t)std::min<int64_t>(N, 0x7fffffff);
+        }
         // pieces anywhere: their tid-0 site / junction keys may coincide across shards (probe needs those elements in the table)
         const bool pieces = partial > 0 || detect;
         for (int pass = 0; pass < 2; ++pass) {
@@ -325,6 +329,7 @@ int lrb_update_gather(lrb_ctx *c, int64_t name_base)
             sa.sets = (want_summary ? SUM_G : 0) | (pass == 1 ? SUM_DAJ : 0);
             SummaryArgs cnt_args = sa; cnt_args.sets = sa.sets | ((pieces && want_summary) ? SUM_DAJ : 0);
             CK(cudaMemsetAsync(m->y_nelem.p, 0, 64, c->st)); CK(cudaMemsetAsync(m->y_counts.p, 0, 64, c->st)); CK(cudaMemsetAsync(m->flags_dev.p, 0, 64, c->st));
+            if (detect) CK(cudaMemsetAsync(m->xs_cnt.p, 0, 64, c->st));
             launch_summary_count(cnt_args, m->y_nelem.as<unsigned long long>(), c->st);
             CK(cudaMemcpyAsync(mh, m->y_nelem.p, 16, cudaMemcpyDeviceToHost, c->st));
             CK(cudaStreamSynchronize(c->st));

@@ -158,6 +158,7 @@ __global__ void sum_phase1_kernel(SummaryArgs a, int parts)
         // phase 2 lets every entry probe them: a hit across chromosomes raises CNT_XLOCUS and the fold is replayed as one locus.
         atomicAdd(&a.counts[CNT_PARTIAL], 1u);       // partial-read transcripts
         const int grp = xl_group(a, e, i);
+        if (a.probe && a.xs_pl && e.n > 1) { const uint32_t k = atomicAdd(&a.xs_cnt[0], 1u); if (k < a.xs_cap) a.xs_pl[k] = (uint32_t)i; else a.counts[CNT_XLOCUS] = 1u; }
         for (int j = 0; j < e.n - 1 && a.probe; ++j) {
             const uint64_t s = tab_upsert(a.tab, key_hi(SET_PJ, 0, 0), key_lo(ent_e(a, e, j), ent_s(a, e, j + 1)));
             atomicMin((unsigned long long *)&a.tab.slots[s].minpos, (unsigned long long)(uint32_t)grp); atomicMax(&a.tab.slots[s].pad, grp);
@@ -206,7 +207,12 @@ __global__ void sum_phase2_kernel(SummaryArgs a, int parts)
             s = tab_find(a.tab, key_hi(SET_PJ0, 0, 0), key_lo(ent_e(a, e, j), ent_s(a, e, j + 1)));
             if (s != EMPTY) hit = (int)(uint32_t)a.tab.slots[s].minpos != grp || a.tab.slots[s].pad != grp;
         }
-        if (hit) a.counts[CNT_XLOCUS] = 1u;
+        if (hit) {
+            // the necessary condition only; with the lists the pair is settled exactly by sum_xjoin_kernel (one shared junction is common
+            // by chance in a deep data set, a chain the piece really merges into is not)
+            if (a.xs_hx) { const uint32_t k = atomicAdd(&a.xs_cnt[1], 1u); if (k < a.xs_cap) a.xs_hx[k] = (uint32_t)i; else a.counts[CNT_XLOCUS] = 1u; }
+            else a.counts[CNT_XLOCUS] = 1u;
+        }
     }
     const bool do_e = (parts & 1) && (a.sets & SUM_E), do_t0 = e.t_tid == 0 && (a.sets & SUM_DAJ);
     for (int j = gl; j < e.n && (do_e || do_t0); j += SG) {
@@ -234,6 +240,45 @@ __global__ void sum_phase2_kernel(SummaryArgs a, int parts)
         if (cg) atomicAdd(&a.counts[SET_G], (uint32_t)cg);
     }
     if (ce) atomicAdd(&a.counts[SET_E], (uint32_t)ce);
+}
+
+// check_iden (gtf.c:54-92) of two entries on their internal boundaries, exact matching (-d 0), the end tests left out (a superset of the
+// meetings under -D: the caller only grows more careful): 0 identical, 2 partial match, -1 unrelated
+LRB_DEVINL int entry_chain_rel(const SummaryArgs &a, const EntryView &p, const EntryView &q)
+{
+    if (p.n < 2 || q.n < 2) return -1;
+    if (p.n == q.n) {
+        for (int i = 0; i < p.n - 1; ++i)
+            if (a.ex.ee[p.gbeg + i] != a.ex.ee[q.gbeg + i] || a.ex.es[p.gbeg + i + 1] != a.ex.es[q.gbeg + i + 1]) return -1;
+        return 0;
+    }
+    const EntryView &l = p.n > q.n ? p : q, &s = p.n > q.n ? q : p;
+    const int s_e0 = a.ex.ee[s.gbeg], s_s1 = a.ex.es[s.gbeg + 1];
+    for (int i = 0; i < l.n - 1; ++i)
+        if (a.ex.ee[l.gbeg + i] == s_e0 && a.ex.es[l.gbeg + i + 1] == s_s1) {
+            int j = 1;
+            for (i = i + 1; i < l.n - 1 && j < s.n - 1; ++i, ++j)
+                if (a.ex.ee[l.gbeg + i] != a.ex.ee[s.gbeg + j] || a.ex.es[l.gbeg + i + 1] != a.ex.es[s.gbeg + j + 1]) return -1;
+            return 2;
+        }
+    return -1;
+}
+// pieces x hits: does an EARLIER entry of another chromosome / shard really absorb the piece?
+__global__ void __launch_bounds__(256) sum_xjoin_kernel(SummaryArgs a)
+{
+    const uint32_t n_pl = min(a.xs_cnt[0], a.xs_cap), n_hx = min(a.xs_cnt[1], a.xs_cap);
+    for (uint32_t h = blockIdx.y; h < n_hx; h += gridDim.y) {
+        const int64_t xi = a.xs_hx[h];
+        const EntryView x = load_entry(a, xi);
+        const int gx = xl_group(a, x, xi);
+        for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_pl; k += gridDim.x * blockDim.x) {
+            const int64_t pi = a.xs_pl[k];
+            if (xi >= pi) continue;
+            const EntryView p = load_entry(a, pi);
+            if (xl_group(a, p, pi) == gx || p.real_tid == x.real_tid) continue;      // the same chromosome is the fold's own business
+            if (entry_chain_rel(a, p, x) >= 0) a.counts[CNT_XLOCUS] = 1u;
+        }
+    }
 }
 
 // phase 3: tid>0 elements go into their segment
@@ -459,6 +504,7 @@ void launch_summary_sets(const SummaryArgs &a, const uint32_t *cls, int64_t n_ro
     if (a.n_upd > 0) {
         sum_phase1_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a, parts); LRB_COUNT_LAUNCH();
         sum_phase2_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a, parts); LRB_COUNT_LAUNCH();
+        if (a.probe && a.xs_pl && a.xs_hx) { sum_xjoin_kernel<<<dim3(64, 64), 256, 0, st>>>(a); LRB_COUNT_LAUNCH(); }
         if (segs || (!split && (a.sets & SUM_E))) { sum_scans_kernel<<<dim3((unsigned)n_tiles, split ? 5 : 6), MS_THREADS, 0, st>>>(a, tile_state, tickets, n_tiles, bed_total, 0); LRB_COUNT_LAUNCH(); }
         if (segs) {
             sum_phase3_kernel<<<nblk_g(a.n_upd), 256, 0, st>>>(a); LRB_COUNT_LAUNCH();

@@ -29,6 +29,7 @@ struct SummaryArgs {
     int2 *kg_pairs;
     // gather root: entry i belongs to shard k iff shard_end[k-1] <= i < shard_end[k] (device array); 0 shards = single-GPU run
     const int64_t *shard_end; int n_shards;
+    uint32_t *xs_pl, *xs_hx, *xs_cnt; uint32_t xs_cap;    // probe: piece list, hit list (entries sharing a junction key with a piece of another group), their counters [2] (zeroed by the caller)
     int probe;                                      // 1: the junction keys of split pieces are probed for a meeting with another chromosome / shard (CNT_XLOCUS)
 };
 enum { SUM_E = 1, SUM_DAJ = 2, SUM_G = 4, SUM_KG = 8, SUM_ALL = 15 };

@@ -303,6 +303,8 @@ def resident_config(ctx, api, cabi, torch, dev, n_reads, n_genes, ont, steps, wa
 
 
 def bench_ours(args, rank, world, local_rank):
+    # the JSON line must be the only thing on stdout: libraries that print there (NCCL's version banner) go to stderr until the end
+    sys.stdout.flush(); real_stdout = os.dup(1); os.dup2(2, 1)
     import torch
     from lr2rmats_b200 import api, cabi
     dist = None
@@ -560,7 +562,9 @@ def bench_ours(args, rank, world, local_rank):
         "cpu_baseline": cpu, "files_e2e": files, "other_configs": others,
         "merged": {"updated_transcripts": int(n_upd_total), "summary_counters": [int(x) for x in summary], "rank0_diag": ctx.update_diag()},
     }
-    print(json.dumps(out))
+    sys.stdout.flush(); os.dup2(real_stdout, 1)
+    print(json.dumps(out), flush=True)
+    os.dup2(2, 1)
     if dist is not None:
         ctx.comm_destroy(); dist.destroy_process_group()
 

@@ -501,9 +501,13 @@ def bench_ours(args, rank, world, local_rank):
     dms, dbytes = kernels[dom]
     achieved = dbytes / (dms * 1e-3) / 1e9 if dms > 0 else 0.0
     path_bytes = algorithmic_bytes(n_total, ops_total, ne_rank0 * (n_total / max(reads.n, 1)))
-    traffic = None
+    traffic = traffic_note = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(dom.split(" ")[0])
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        tk = tj["kernels"].get(dom.split(" ")[0])
+        if tk:                                        # measured on a smaller data set of the same shape: scaled to this launch by the record count
+            traffic = int(tk["dram_bytes"] * reads.n / tj["reads"])
+            traffic_note = f"ncu dram bytes of a {tj['reads']}-record capture ({tk.get('what', dom)}) scaled by records; see profiles/r02_traffic.json"
     except Exception:
         pass
 
@@ -554,7 +558,7 @@ def bench_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dbytes), "kernel_ms": dms, "rank": 0,
+                     "traffic_note": traffic_note, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(dbytes), "kernel_ms": dms, "rank": 0,
                      "all_kernels": {k: {"ms": v[0], "algorithmic_bytes": int(v[1]), "frac": (v[1] / (v[0] * 1e-3) / 1e9 / peak) if v[0] > 0 else None} for k, v in kernels.items()},
                      "path": {"algorithmic_bytes_per_step": int(path_bytes), "achieved": path_bytes / (ms_step * 1e-3) / 1e9,
                               "frac": path_bytes / (ms_step * 1e-3) / 1e9 / peak / world, "note": "whole job, per GPU: bytes / step time / N / peak"}},

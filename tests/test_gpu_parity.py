@@ -556,3 +556,36 @@ def test_sort3_is_a_stable_lexicographic_sort(ctx):
         got = ctx.sort3(k0, k1, k2)
         want = np.lexsort((np.arange(n), k2, k1, k0)).astype(np.uint32)
         assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("shape", ["iso", "ont"])
+def test_deep_loci_against_port(ctx, shape):
+    """Deep data: hundreds of reads per gene, so nearly every candidate sits in a locus beyond the 64-candidate masks of the flat fold
+    (identity classes through the table, tabulated class relation, warp replay with the survivors in shared memory; the four class folds
+    of the summary as sub-streams).  Every table and all counters equal the port's sequential merge_trans."""
+    anno = synth.make_annotation(120, n_chrom=3, seed=61)
+    rr = synth.make_rrna(anno, 4, seed=62)
+    reads = synth.make_reads(anno, 60_000 if shape == "iso" else 25_000, seed=63, ont=(shape == "ont"), reject_frac=0.2, rrna=rr)
+    sj = synth.make_sj_from_reads(reads, frac=0.7, seed=64)
+    fp, ep = cabi.FilterParams.default(), cabi.ExonParams.default()
+    for up in (cabi.UpdateParams.default(full_level=3, split_trans=1, min_sj_cnt=1, want_summary=1),
+               cabi.UpdateParams.default(full_level=5, split_trans=0, want_summary=1, force_strand=1)):
+        of = op.filter(reads.soa(), rr, fp)
+        kept = reads.take(of["keep_idx"])
+        oex = op.bam2gtf(kept.soa(), ep)
+        rc, ou = op.update(oex, anno.soa(), sj, up)
+        assert rc == 0
+        ctx.set_anno(anno.soa()); ctx.set_rm(rr); ctx.set_sj(sj)
+        ctx.upload(reads.soa())
+        ctx.pipeline_run(fp, ep)
+        ctx.update_run(up)
+        gu = ctx.update_fetch()
+        ou["ex"]["read_idx"] = gu["ex"]["read_idx"]
+        assert_dict_equal(gu, ou)
+        n_upd = len(gu["updated"]["cand"])
+        assert len(of["keep_idx"]) / max(n_upd, 1) > 4          # deep: most candidates are absorbed
+    # unique-gtf on the same deep stream (one fold over all rows)
+    rc, oq = op.unique(oex, cabi.UpdateParams.default())
+    gq = ctx.unique_gtf(kept.soa(), ep, cabi.UpdateParams.default())
+    oq["ex"]["read_idx"] = gq["ex"]["read_idx"]
+    assert_dict_equal(gq, oq)

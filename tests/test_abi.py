@@ -61,3 +61,30 @@ def test_shard_cuts_host_helper():
     for c in cuts[1:-1]:
         if 0 < c < 8:   # every cut is at a locus gap
             assert tid[c] != tid[c - 1] or start[c] > end[:c][tid[:c] == tid[c]].max()
+
+
+def test_shard_planning_is_locus_and_qname_safe():
+    """multi.plan_shards / lrb_shard_cuts_weighted (host helpers, no GPU): every cut sits where the record starts beyond every earlier end
+    on its chromosome, never inside a qname run, and the shards are balanced by CIGAR ops."""
+    import numpy as np
+    from lr2rmats_b200 import multi, synth
+    anno = synth.make_annotation(400, n_chrom=3, seed=5)
+    reads = synth.make_reads(anno, 20_000, seed=6, reject_frac=0.3)
+    b = reads.soa()
+    for n_sh in (2, 5, 8):
+        cuts = multi.plan_shards(b, n_sh)
+        assert cuts[0] == 0 and cuts[-1] == reads.n and np.all(np.diff(cuts) > 0)
+        start, end = multi.ref_span(b)
+        key_s = ((b["tid"].astype(np.int64) + 1) << 32) | start; key_e = ((b["tid"].astype(np.int64) + 1) << 32) | end
+        run_max = np.maximum.accumulate(key_e)
+        for c in cuts[1:-1]:
+            assert key_s[c] > run_max[c - 1], "cut inside a locus"
+            assert b["qname_hash"][c] != b["qname_hash"][c - 1], "cut inside a qname run"
+        ops = np.diff(b["cigar_off"].astype(np.int64)) + 16
+        per = np.array([ops[cuts[k]:cuts[k + 1]].sum() for k in range(n_sh)], float)
+        assert per.max() / per.mean() < 1.25
+        # the slices reassemble the stream
+        parts = [multi.take_shard(b, int(cuts[k]), int(cuts[k + 1])) for k in range(n_sh)]
+        assert sum(len(p["tid"]) for p in parts) == reads.n
+        assert np.array_equal(np.concatenate([p["cigar"] for p in parts]), b["cigar"])
+        assert all(p["cigar_off"][0] == 0 and p["cigar_off"][-1] == len(p["cigar"]) for p in parts)

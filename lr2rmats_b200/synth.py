@@ -469,7 +469,8 @@ def cigar_string(words) -> str:
     return "".join(f"{int(w) >> 4}{OPS[int(w) & 15]}" for w in words)
 
 
-def write_sam(path, reads: Reads, with_seq: bool = True, shuffle_tags: bool = False):
+def write_sam(path, reads: Reads, with_seq: bool = True, shuffle_tags: bool = False, nh=None):
+    """nh: optional per-record NH:i values (0 = no tag) for bam2sj inputs."""
     with open(path, "w") as f:
         f.write("@HD\tVN:1.0\tSO:coordinate\n")
         for nme, ln in zip(reads.chrom_names, reads.chrom_lens):
@@ -481,6 +482,8 @@ def write_sam(path, reads: Reads, with_seq: bool = True, shuffle_tags: bool = Fa
             tags = f"NM:i:{int(reads.nm[i])}"
             if reads.xs[i]:
                 tags += f"\tXS:A:{chr(int(reads.xs[i]))}"
+            if nh is not None and nh[i]:
+                tags += f"\tNH:i:{int(nh[i])}"
             chrom = reads.chrom_names[int(reads.tid[i])] if reads.tid[i] >= 0 else "*"
             f.write(f"read{int(reads.qid[i])}\t{int(reads.flag[i])}\t{chrom}\t{int(reads.pos[i]) + 1}\t60\t{cg}\t*\t0\t0\t{seq}\t*\t{tags}\n")
 

@@ -78,3 +78,21 @@ def test_gtf_input_mode(workdir):
     op.run_bin(op.REF_BIN, ["update-gtf", "-l", "3", sam, str(workdir / "anno.gtf")], str(o / "novel.gtf"))
     run_both(workdir, "gin_uniq", ["unique-gtf", "-m", "g", "-b", sam, str(o / "novel.gtf")], "out.gtf")
     run_both(workdir, "gin_upd", ["update-gtf", "-m", "g", "-b", sam, "-l", "5", str(o / "novel.gtf"), str(workdir / "anno.gtf")] + ALL)
+
+
+@pytest.mark.parametrize("which", ["iso", "ont"])
+def test_bam2sj(workdir, which, tmp_path):
+    """bam2sj on a few thousand paired records with NH tags (and some without): port == reference binary, default and -i; the single-end
+    original gives the header only (read_type is PAIR_T whatever the options say, parse_bam.c:76,997)."""
+    anno = synth.make_annotation(700, n_chrom=3, seed=31)
+    r = synth.make_reads(anno, 3000 if which == "iso" else 800, seed=35, ont=(which == "ont"), reject_frac=0.1)
+    rng = np.random.default_rng(36)
+    r.flag = (r.flag | np.where(rng.random(r.n) < 0.8, np.uint16(3), np.uint16(0))).astype(np.uint16)     # 80 % proper pairs
+    nh = rng.choice([0, 1, 1, 1, 2, 5], r.n)
+    sam = tmp_path / "paired.sam"
+    synth.write_sam(sam, r, with_seq=False, nh=nh)
+    names = run_both(workdir, f"{which}_sj", ["bam2sj", str(sam)], "out.sj")
+    run_both(workdir, f"{which}_sj_i", ["bam2sj", "-i", "300", str(sam)], "out.sj")
+    assert sum(1 for _ in open(workdir / f"{which}_sj_ref" / "out.sj")) > 50
+    run_both(workdir, f"{which}_sj_se", ["bam2sj", str(workdir / f"{which}.sam")], "out.sj")
+    assert sum(1 for _ in open(workdir / f"{which}_sj_se_ref" / "out.sj")) == 4

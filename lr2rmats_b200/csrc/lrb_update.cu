@@ -987,14 +987,18 @@ __global__ void __launch_bounds__(256) fold_class_verify_kernel(MergeArgs a, Cla
 // 128-bit row per class.  The replay then needs no exon pool at all: "can this survivor absorb the candidate" is one bit test.
 // Loci with more than FB_MAXCLS classes keep locus_cnt = FB_NOROWS and the replay falls back to its relation cache.
 static constexpr int FB_MAXCLS = 127; static constexpr uint32_t FB_SINGLE = 127u, FB_NOROWS = 0xffu;
-__global__ void __launch_bounds__(256) fold_class_rows_kernel(MergeArgs a, const uint32_t *__restrict__ rep, const uint8_t *__restrict__ locus_hard)
+__global__ void __launch_bounds__(256) fold_class_rows_kernel(MergeArgs a, const uint32_t *__restrict__ rep, const uint8_t *__restrict__ locus_hard, uint32_t *next_entry)
 {
     // per warp: the classes of the locus (exon count, sub-stream, junction signature, first junction, representative)
     __shared__ uint64_t s_sig[8][128], s_j0[8][128]; __shared__ uint32_t s_rep[8][128]; __shared__ uint32_t s_nk[8][128];
-    const int64_t n_loci = (int64_t)a.totals[0], n_big = (int64_t)a.fb_cnt[0];
+    const int64_t n_loci = (int64_t)a.totals[0], n_big = min((int64_t)a.fb_cnt[0], a.n_cand);
     const int lane = lane_id(), w = warp_id();
     const CandSoA &cd = a.cd;
-    for (int64_t bi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32; bi < min(n_big, a.n_cand); bi += (int64_t)gridDim.x * blockDim.x / 32) {
+    for (;;) {
+        uint32_t bi = 0;
+        if (lane == 0) bi = atomicAdd(next_entry, 1u);               // entries differ by orders of magnitude in size: claimed one at a time
+        bi = __shfl_sync(FULL, bi, 0);
+        if ((int64_t)bi >= n_big) return;
         const int64_t loc = a.fb_list[bi] >> 2; const uint32_t my = a.fb_list[bi] & 3u;
         const int64_t ls = a.locus_start[loc], le = (loc + 1 < n_loci) ? a.locus_start[loc + 1] : cand_count(a);
         if (locus_hard[ls] >= 2) continue;
@@ -1071,12 +1075,14 @@ __global__ void __launch_bounds__(FB_THREADS) fold_big_kernel(MergeArgs a, const
         for (int64_t c0 = ls; c0 < le && !overflow; c0 += G) {
             // 32 candidates, one per lane
             const int64_t cl = c0 + lane; const bool have = cl < le;
-            const int l_tid = have ? cd.tid[cl] : 0, l_start = have ? cd.start[cl] : 0, l_end = have ? cd.end[cl] : 0, l_rv = have ? cd.rev[cl] : 0;
-            const int l_n = have ? cd.n[cl] : 0, l_fs = have ? cd.fs[cl] : 0, l_le = have ? cd.le[cl] : 0; const uint32_t l_gbeg = have ? cd.gbeg[cl] : 0;
-            const uint64_t l_j0 = have ? cd.j0[cl] : 0, l_sig = have ? cd.sig[cl] : 0;
-            const uint32_t l_rep = have ? rep[cl] : 0;
             const int l_kls = (have && a.kls) ? a.kls[cl] : 0;
-            const uint32_t l_ord = (have && use_rows) ? a.cord[cl] : FB_SINGLE;
+            const bool mine = have && (!a.kls || l_kls == my);       // rows of the other sub-streams are skipped below: their fields are not loaded
+            if (!__any_sync(gm, mine)) continue;
+            const int l_tid = mine ? cd.tid[cl] : 0, l_start = mine ? cd.start[cl] : 0, l_end = mine ? cd.end[cl] : 0, l_rv = mine ? cd.rev[cl] : 0;
+            const int l_n = mine ? cd.n[cl] : 0, l_fs = mine ? cd.fs[cl] : 0, l_le = mine ? cd.le[cl] : 0; const uint32_t l_gbeg = mine ? cd.gbeg[cl] : 0;
+            const uint64_t l_j0 = mine ? cd.j0[cl] : 0, l_sig = mine ? cd.sig[cl] : 0;
+            const uint32_t l_rep = mine ? rep[cl] : 0;
+            const uint32_t l_ord = (mine && use_rows) ? a.cord[cl] : FB_SINGLE;
             const uint64_t l_row0 = l_ord != FB_SINGLE ? a.crow[2 * (size_t)l_rep] : 0, l_row1 = l_ord != FB_SINGLE ? a.crow[2 * (size_t)l_rep + 1] : 0;
             int l_alive = 0;
             const int nb = (int)min((int64_t)G, le - c0);
@@ -1430,7 +1436,7 @@ void launch_merge_fold(const MergeArgs &a, cudaStream_t st)
             fold_big_mark_kernel<<<(unsigned)blm, 256, 0, st>>>(a, a.hard, a.lstart); LRB_COUNT_LAUNCH();
             fold_class_insert_kernel<<<bl, 256, 0, st>>>(a, tab, a.lstart); LRB_COUNT_LAUNCH();
             fold_class_verify_kernel<<<bl, 256, 0, st>>>(a, tab, a.rep, a.lstart, a.hard); LRB_COUNT_LAUNCH();
-            fold_class_rows_kernel<<<(unsigned)blm, 256, 0, st>>>(a, a.rep, a.hard); LRB_COUNT_LAUNCH();
+            fold_class_rows_kernel<<<(unsigned)blm, 256, 0, st>>>(a, a.rep, a.hard, a.fb_cnt + 4); LRB_COUNT_LAUNCH();
             // one warp per locus, loci claimed from the lists: a whole warp measured fastest (8 / 16 lanes per locus: 17.5 / 15.8 ms per
             // step against 14.2 ms on the 10 M-read data set -- the lane groups of a warp diverge)
             int64_t blb = (a.n_cand / (FF_MAX + 1) + 1) / (FB_THREADS / 32) + 1; if (blb > 148 * 6) blb = 148 * 6;

@@ -87,6 +87,28 @@ def test_truncated_bgzf_and_malformed_sam(big, tmp_path):
         assert outs[0] == outs[1] and len(outs[0]) > 1 << 19
 
 
+def test_bgzf_crc_mismatch_is_read_like_the_reference(big, tmp_path):
+    """A block whose CRC field is damaged but whose deflate stream is intact: the reference's htslib (1.3) never looks at the CRC and reads
+    the file to its end; the product's decoder must give the same records (it only warns), on any thread count."""
+    if not os.path.exists(big / "f_ref.bam"):
+        run(op.REF_BIN, ["filter", "-r", str(big / "rm.gtf"), str(big / "in.sam")], big / "f_ref.bam")
+    d = bytearray(open(big / "f_ref.bam", "rb").read())
+    p, blocks = 0, []
+    while p + 18 <= len(d):
+        bsize = (d[p + 16] | (d[p + 17] << 8)) + 1
+        blocks.append((p, bsize)); p += bsize
+    assert len(blocks) > 10
+    for k in (3, len(blocks) // 2):
+        d[blocks[k][0] + blocks[k][1] - 8] ^= 0xFF               # first byte of the block's CRC32
+    open(tmp_path / "crc.bam", "wb").write(d)
+    run(op.REF_BIN, ["bam2gtf", str(tmp_path / "crc.bam")], tmp_path / "ref.gtf")
+    want = open(tmp_path / "ref.gtf", "rb").read()
+    assert len(want) > 1 << 19
+    for t in (1, 8):
+        run(op.PORT_BIN, ["bam2gtf", str(tmp_path / "crc.bam")], tmp_path / f"port.t{t}.gtf", threads=t)
+        assert open(tmp_path / f"port.t{t}.gtf", "rb").read() == want
+
+
 def test_emitters_threads(big, tmp_path):
     """Row f-2: every text output of update-gtf / unique-gtf formatted by 8 threads == 1 thread == the reference's printers."""
     from lr2rmats_b200 import cabi

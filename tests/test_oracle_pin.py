@@ -96,3 +96,40 @@ def test_bam2sj(workdir, which, tmp_path):
     assert sum(1 for _ in open(workdir / f"{which}_sj_ref" / "out.sj")) > 50
     run_both(workdir, f"{which}_sj_se", ["bam2sj", str(workdir / f"{which}.sam")], "out.sj")
     assert sum(1 for _ in open(workdir / f"{which}_sj_se_ref" / "out.sj")) == 4
+
+
+SORT_SCRIPT = "/root/reference/src/sort_gtf.sh"
+
+
+@pytest.mark.skipif(not os.path.exists(SORT_SCRIPT), reason="the reference's sort_gtf.sh is only present in the build container")
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_sort_gtf_fuzz(seed, tmp_path):
+    """`sort-gtf` (host tagging + stable three-key sort; the port CLI sorts with std::stable_sort where the product uses the device) against
+    the reference's own script on random concatenations: shuffled transcripts of known / unknown chromosomes, equal keys, foreign feature
+    lines, comments, blanks instead of tabs, short lines, leading zeros."""
+    import random
+    import subprocess
+    rnd = random.Random(seed)
+    chroms = ["chr1", "chr2", "chr10", "chrX", "chrM", "chrUn_a", "scaf7", "chr22", "KI270", "chrY"]
+    blocks = []
+    for t in range(rnd.randint(40, 120)):
+        ch = rnd.choice(chroms); s = rnd.choice([rnd.randint(1, 50), rnd.randint(1, 100000)]); e = s + rnd.randint(0, 5000)
+        ss = ("%05d" % s) if rnd.random() < 0.1 else str(s)
+        sep = " " if rnd.random() < 0.05 else "\t"
+        lines = [sep.join([ch, "src", "transcript", ss, str(e), ".", rnd.choice("+-"), "."]) + f'\tgene_id "G{t}"; transcript_id "T{t}";']
+        for x in range(rnd.randint(0, 4)):
+            kind = rnd.choice(["exon", "exon", "exon", "CDS", "start_codon", "transcript_part"])
+            cols = [ch, "src", kind, str(s + x), str(e - x), ".", "+", ".", f'gene_id "G{t}"; transcript_id "T{t}"; exon_number "{x}";']
+            if rnd.random() < 0.1: cols = cols[:rnd.randint(5, 8)]
+            if rnd.random() < 0.05: cols.append("extra")
+            lines.append("\t".join(cols))
+        if rnd.random() < 0.1: lines.insert(rnd.randint(0, len(lines)), "# comment " + str(t))
+        if rnd.random() < 0.05: lines.append("")
+        blocks.append(lines)
+    rnd.shuffle(blocks)
+    head = ["chr5\tsrc\texon\t10\t20\t.\t+\t.\tgene_id \"pre\";"] if seed % 2 else []
+    text = "\n".join(head + [ln for b in blocks for ln in b]) + "\n"
+    (tmp_path / "in.gtf").write_text(text)
+    subprocess.run(["bash", SORT_SCRIPT, str(tmp_path / "in.gtf"), str(tmp_path / "ref.gtf")], check=True, env=dict(os.environ, LC_ALL="C"))
+    op.run_bin(op.PORT_BIN, ["sort-gtf", str(tmp_path / "in.gtf"), str(tmp_path / "port.gtf")])
+    assert (tmp_path / "port.gtf").read_bytes() == (tmp_path / "ref.gtf").read_bytes()

@@ -88,3 +88,22 @@ def test_shard_planning_is_locus_and_qname_safe():
         assert sum(len(p["tid"]) for p in parts) == reads.n
         assert np.array_equal(np.concatenate([p["cigar"] for p in parts]), b["cigar"])
         assert all(p["cigar_off"][0] == 0 and p["cigar_off"][-1] == len(p["cigar"]) for p in parts)
+
+
+def test_header_binds_from_plain_c(tmp_path):
+    """The boundary is a C ABI: the header compiles as strict C99 and a C caller (what the reference's main.c would be) links against the
+    library and gets LRB_E_NODEVICE here (no GPU, no CPU fallback)."""
+    import subprocess
+    from lr2rmats_b200 import api
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "bind.c"
+    src.write_text('#include "lr2rmats_b200.h"\n#include <stdio.h>\n'
+                   'int main(void) { lrb_ctx *g = NULL; lrb_filter_params p = {0.67f, 0.75f, 0.98f, 0}; lrb_sj_params s = {3, 1}; (void)p; (void)s;\n'
+                   '  int rc = lrb_ctx_create(0, &g); printf("%s %d\\n", lrb_version(), rc); if (rc == LRB_OK) lrb_ctx_destroy(g);\n'
+                   '  return (rc == LRB_OK || rc == LRB_E_NODEVICE) ? 0 : 1; }\n')
+    libdir = os.path.dirname(api.LIB_PATH)
+    exe = tmp_path / "bind"
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-L", libdir, "-llr2rmats_b200",
+                    f"-Wl,-rpath,{libdir}", "-o", str(exe)], check=True)
+    p = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert p.returncode == 0 and "lr2rmats_b200" in p.stdout
